@@ -1,0 +1,219 @@
+/*
+ * rln_b200.h — C ABI of librln_b200.so, the B200-native drop-in for the hot path of the `rln` crate
+ * of vacp2p/zerokit (proof generation / verification / Poseidon Merkle tree).
+ *
+ * Every `ffi_*` symbol below has the name, argument order and ownership rules of the function the
+ * reference exports through safer-ffi (the reference's rln.h is generated, not checked in; the Rust
+ * definition each entry replaces is cited as file:line relative to the reference root).  Conventions
+ * (rln/src/ffi/ffi_utils.rs:15-36, rln/ffi_c_examples/README.md:42-48):
+ *   - repr_c::Box<T>            → owning, non-null T*; parameters typed &repr_c::Box<T> are T* const*
+ *   - repr_c::Vec<T>            → { T* ptr; size_t len; size_t cap; }
+ *   - repr_c::String            → Vec<uint8_t> holding UTF-8 plus a trailing NUL (print via .ptr)
+ *   - CResult<T,E>              → { ok; err; }: exactly one side is non-null
+ *   - CBoolResult               → { bool ok; String err; } (err.ptr == NULL when there is none)
+ *   - every returned object is caller-owned and released with its *_free function
+ *   - errors are the reference's Display strings, never codes
+ * CFr is opaque to callers (32 bytes); here it holds the canonical little-endian integer.
+ *
+ * The `rlnb200_*` symbols are extensions that do not exist in the reference: caller-supplied
+ * blinding scalars (mirrors generate_zk_proof_with_rs, rln/src/protocol/proof.rs:753-777), batched
+ * proving/verification and the raw kernels used by the benchmarks.  All computation behind this
+ * header runs on the GPU; the library returns an error string if no CUDA device is usable.
+ */
+#ifndef RLN_B200_H
+#define RLN_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ basic containers */
+typedef struct Vec_uint8 { uint8_t *ptr; size_t len; size_t cap; } Vec_uint8_t;
+typedef Vec_uint8_t RlnString;                         /* repr_c::String */
+typedef struct Vec_size { size_t *ptr; size_t len; size_t cap; } Vec_size_t;
+
+typedef struct CFr { uint8_t bytes[32]; } CFr_t;       /* rln/src/ffi/ffi_utils.rs:33-36 (opaque) */
+typedef struct Vec_CFr { CFr_t *ptr; size_t len; size_t cap; } Vec_CFr_t;
+
+typedef struct FFI_RLN FFI_RLN_t;                      /* rln/src/ffi/ffi_rln.rs:16-18 */
+typedef struct FFI_RLNProof FFI_RLNProof_t;            /* rln/src/ffi/ffi_rln.rs:153-155 */
+typedef struct FFI_RLNProofValues FFI_RLNProofValues_t;/* rln/src/ffi/ffi_rln.rs:714-716 */
+typedef struct FFI_RLNWitnessInput FFI_RLNWitnessInput_t; /* rln/src/ffi/ffi_rln.rs:322-324 */
+typedef struct FFI_MerkleProof {                       /* rln/src/ffi/ffi_tree.rs:13-18 */
+    Vec_CFr_t path_elements;
+    Vec_uint8_t path_index;
+} FFI_MerkleProof_t;
+
+typedef struct CBoolResult { bool ok; RlnString err; } CBoolResult_t;                 /* ffi_utils.rs:24-29 */
+typedef struct CResult_FFI_RLN { FFI_RLN_t *ok; RlnString err; } CResult_FFI_RLN_t;   /* ffi_utils.rs:15-20 */
+typedef struct CResult_FFI_RLNProof { FFI_RLNProof_t *ok; RlnString err; } CResult_FFI_RLNProof_t;
+typedef struct CResult_FFI_RLNProofValues { FFI_RLNProofValues_t *ok; RlnString err; } CResult_FFI_RLNProofValues_t;
+typedef struct CResult_FFI_RLNWitnessInput { FFI_RLNWitnessInput_t *ok; RlnString err; } CResult_FFI_RLNWitnessInput_t;
+typedef struct CResult_FFI_MerkleProof { FFI_MerkleProof_t *ok; RlnString err; } CResult_FFI_MerkleProof_t;
+typedef struct CResult_CFr { CFr_t *ok; RlnString err; } CResult_CFr_t;
+typedef struct CResult_Vec_uint8 { Vec_uint8_t ok; RlnString err; } CResult_Vec_uint8_t;
+
+/* ------------------------------------------------------------------ RLN object (rln/src/ffi/ffi_rln.rs) */
+CResult_FFI_RLN_t ffi_rln_new(size_t tree_depth, const char *config_path);                      /* :22-57  */
+CResult_FFI_RLN_t ffi_rln_new_with_params(size_t tree_depth, const Vec_uint8_t *zkey_data,
+                                          const Vec_uint8_t *graph_data, const char *config_path); /* :74-116 */
+void   ffi_rln_free(FFI_RLN_t *rln);                                                            /* :136-139 */
+size_t ffi_rln_get_tree_depth(FFI_RLN_t *const *rln);                                           /* :141-144 */
+size_t ffi_rln_get_max_out(FFI_RLN_t *const *rln);                                              /* :146-149 */
+
+/* ------------------------------------------------------------------ Merkle tree (rln/src/ffi/ffi_tree.rs) */
+CBoolResult_t ffi_set_tree(FFI_RLN_t **rln, size_t tree_depth);                                 /* :27-41  */
+CBoolResult_t ffi_delete_leaf(FFI_RLN_t **rln, size_t index);                                   /* :43-55  */
+CBoolResult_t ffi_set_leaf(FFI_RLN_t **rln, size_t index, const CFr_t *leaf);                   /* :57-69  */
+CResult_CFr_t ffi_get_leaf(FFI_RLN_t *const *rln, size_t index);                                /* :71-86  */
+size_t        ffi_leaves_set(FFI_RLN_t *const *rln);                                            /* :88-91  */
+CBoolResult_t ffi_set_next_leaf(FFI_RLN_t **rln, const CFr_t *leaf);                            /* :93-105 */
+CBoolResult_t ffi_set_leaves_from(FFI_RLN_t **rln, size_t index, const Vec_CFr_t *leaves);      /* :107-124 */
+CBoolResult_t ffi_init_tree_with_leaves(FFI_RLN_t **rln, const Vec_CFr_t *leaves);              /* :126-142 */
+CBoolResult_t ffi_atomic_operation(FFI_RLN_t **rln, size_t index, const Vec_CFr_t *leaves,
+                                   const Vec_size_t *indices);                                  /* :146-165 */
+CBoolResult_t ffi_seq_atomic_operation(FFI_RLN_t **rln, const Vec_CFr_t *leaves,
+                                       const Vec_uint8_t *indices);                             /* :167-186 */
+CFr_t        *ffi_get_root(FFI_RLN_t *const *rln);                                              /* :190-193 */
+CResult_FFI_MerkleProof_t ffi_get_merkle_proof(FFI_RLN_t *const *rln, size_t index);            /* :195-225 */
+void          ffi_merkle_proof_free(FFI_MerkleProof_t *merkle_proof);                           /* :20-23  */
+
+/* ------------------------------------------------------------------ witness input (rln/src/ffi/ffi_rln.rs) */
+CResult_FFI_RLNWitnessInput_t ffi_rln_witness_input_new_single(
+    const CFr_t *identity_secret, const CFr_t *user_message_limit, const CFr_t *message_id,
+    const Vec_CFr_t *path_elements, const Vec_uint8_t *identity_path_index,
+    const CFr_t *x, const CFr_t *external_nullifier);                                           /* :326-358 */
+CResult_Vec_uint8_t ffi_rln_witness_to_bytes_le(FFI_RLNWitnessInput_t *const *witness);         /* :476-490 */
+CResult_FFI_RLNWitnessInput_t ffi_bytes_le_to_rln_witness(const Vec_uint8_t *bytes);            /* :508-522 */
+void ffi_rln_witness_input_free(FFI_RLNWitnessInput_t *witness);                                /* :556-559 */
+
+/* ------------------------------------------------------------------ proving / verifying */
+CResult_FFI_RLNProof_t ffi_generate_rln_proof(FFI_RLN_t *const *rln,
+                                              FFI_RLNWitnessInput_t *const *witness);           /* :851-872 */
+CBoolResult_t ffi_verify_rln_proof(FFI_RLN_t *const *rln, FFI_RLNProof_t *const *rln_proof,
+                                   const CFr_t *x);                                             /* :964-984 */
+CBoolResult_t ffi_verify_with_roots(FFI_RLN_t *const *rln, FFI_RLNProof_t *const *rln_proof,
+                                    const Vec_CFr_t *roots, const CFr_t *x);                    /* :986-1010 */
+
+FFI_RLNProofValues_t *ffi_rln_proof_get_values(FFI_RLNProof_t *const *rln_proof);               /* :157-162 */
+uint8_t ffi_rln_proof_get_version_byte(FFI_RLNProof_t *const *rln_proof);                       /* :164-167 */
+CResult_Vec_uint8_t ffi_rln_proof_to_bytes_le(FFI_RLNProof_t *const *rln_proof);                /* :169-183 */
+CResult_Vec_uint8_t ffi_rln_proof_to_bytes_be(FFI_RLNProof_t *const *rln_proof);                /* :185-199 */
+CResult_FFI_RLNProof_t ffi_bytes_le_to_rln_proof(const Vec_uint8_t *bytes);                     /* :201-215 */
+void ffi_rln_proof_free(FFI_RLNProof_t *rln_proof);                                             /* :233-236 */
+
+CFr_t *ffi_rln_proof_values_get_root(FFI_RLNProofValues_t *const *pv);                          /* :718-721 */
+CFr_t *ffi_rln_proof_values_get_x(FFI_RLNProofValues_t *const *pv);                             /* :723-726 */
+CFr_t *ffi_rln_proof_values_get_external_nullifier(FFI_RLNProofValues_t *const *pv);            /* :728-733 */
+CResult_CFr_t ffi_rln_proof_values_get_y(FFI_RLNProofValues_t *const *pv);                      /* :735-743 */
+CResult_CFr_t ffi_rln_proof_values_get_nullifier(FFI_RLNProofValues_t *const *pv);              /* :745-753 */
+Vec_uint8_t ffi_rln_proof_values_to_bytes_le(FFI_RLNProofValues_t *const *pv);                  /* :802-805 */
+CResult_FFI_RLNProofValues_t ffi_bytes_le_to_rln_proof_values(const Vec_uint8_t *bytes);        /* :812-826 */
+void ffi_rln_proof_values_free(FFI_RLNProofValues_t *proof_values);                             /* :844-847 */
+
+/* ------------------------------------------------------------------ CFr / Vec helpers (rln/src/ffi/ffi_utils.rs) */
+CFr_t *ffi_cfr_zero(void);                                                                      /* :69-72  */
+CFr_t *ffi_cfr_one(void);                                                                       /* :74-77  */
+CResult_Vec_uint8_t ffi_cfr_to_bytes_le(const CFr_t *cfr);                                      /* :79-92  */
+CResult_Vec_uint8_t ffi_cfr_to_bytes_be(const CFr_t *cfr);                                      /* :94-107 */
+CResult_CFr_t ffi_bytes_le_to_cfr(const Vec_uint8_t *bytes);                                    /* :109-121 */
+CResult_CFr_t ffi_bytes_be_to_cfr(const Vec_uint8_t *bytes);                                    /* :123-135 */
+CFr_t *ffi_uint_to_cfr(uint32_t value);                                                         /* :137-140 */
+RlnString ffi_cfr_debug(const CFr_t *cfr);                                                      /* :142-148 */
+void   ffi_cfr_free(CFr_t *cfr);                                                                /* :150-153 */
+Vec_CFr_t ffi_vec_cfr_new(size_t capacity);                                                     /* :157-160 */
+Vec_CFr_t ffi_vec_cfr_from_cfr(const CFr_t *cfr);                                               /* :162-165 */
+void   ffi_vec_cfr_push(Vec_CFr_t *v, const CFr_t *cfr);                                        /* :167-175 */
+size_t ffi_vec_cfr_len(const Vec_CFr_t *v);                                                     /* :177-180 */
+const CFr_t *ffi_vec_cfr_get(const Vec_CFr_t *v, size_t i);                                     /* :182-185 */
+void   ffi_vec_cfr_free(Vec_CFr_t v);                                                           /* :268-271 */
+void   ffi_vec_u8_free(Vec_uint8_t v);                                                          /* :341-344 */
+void   ffi_c_string_free(RlnString s);                                                          /* :406-409 */
+CFr_t *ffi_hash_to_field_le(const Vec_uint8_t *input);                                          /* :348-351 */
+CFr_t *ffi_hash_to_field_be(const Vec_uint8_t *input);                                          /* :353-356 */
+CFr_t *ffi_poseidon_hash_pair(const CFr_t *a, const CFr_t *b);                                  /* :358-361 */
+Vec_CFr_t ffi_key_gen(void);                                                                    /* :365-369 */
+
+/* ================================================================== extensions (not in the reference) */
+
+/* generate_zk_proof_with_rs (rln/src/protocol/proof.rs:753-777) behind the ABI: r, s supplied by the
+ * caller so that proofs are reproducible bit for bit. */
+CResult_FFI_RLNProof_t rlnb200_generate_rln_proof_with_rs(FFI_RLN_t *const *rln, FFI_RLNWitnessInput_t *const *witness,
+                                                          const CFr_t *r, const CFr_t *s);
+
+/* Batched proving, HOST buffers.  witnesses: n concatenated rln_witness_to_bytes_le records (single
+ * message-id layout, rln/src/protocol/witness.rs:369-415; all of length 1+32*(5+depth)+16+depth).
+ * rs: n*64 bytes (r|s, canonical LE) or NULL for fresh randomness.  proofs_out: n records of
+ * rln_proof_to_bytes_le (1+128+1+160 = 290 bytes, rln/src/protocol/proof.rs:413-428).
+ * Returns 0 on success; otherwise a negative value and *err (free with ffi_c_string_free). */
+int rlnb200_prove_batch(FFI_RLN_t *const *rln, const uint8_t *witnesses, size_t n, const uint8_t *rs,
+                        uint8_t *proofs_out, RlnString *err);
+/* Batched verification of n rln_proof_to_bytes_le records against the handle's verifying key only
+ * (no root / signal check): ok_out[i] = 1 valid, 0 invalid, 2 malformed. */
+int rlnb200_verify_batch(FFI_RLN_t *const *rln, const uint8_t *proofs, size_t n, uint8_t *ok_out, RlnString *err);
+
+/* Batched proving, DEVICE buffers (inputs already resident in HBM):
+ *   d_inputs  n × input_slots × 32 bytes, canonical LE, the witness-graph input buffer layout
+ *             (rln/src/circuit/iden3calc.rs:106-181; slot 0 = 1) — see rlnb200_input_slot()
+ *   d_rs      n × 64 bytes
+ *   d_proofs  n × 128 bytes  (ark-compressed A|B|C)
+ *   d_values  n × 160 bytes  ([root, external_nullifier, x, y, nullifier], canonical LE) or NULL
+ *   d_affine  n × 256 bytes  (A|B|C affine canonical) or NULL
+ * stream: a cudaStream_t (0 = default stream). */
+int rlnb200_prove_batch_device(FFI_RLN_t *const *rln, const void *d_inputs, const void *d_rs, size_t n,
+                               void *d_proofs, void *d_values, void *d_affine, void *stream, RlnString *err);
+/* fills the input-slot buffer for one witness record on the host (layout helper for callers/tests) */
+int rlnb200_witness_to_input_slots(FFI_RLN_t *const *rln, const uint8_t *witness_le, size_t len, uint8_t *slots_out,
+                                   RlnString *err);
+size_t rlnb200_input_slots(FFI_RLN_t *const *rln);
+/* offset/len of a named circuit input ("identitySecret", "pathElements", …); returns 0 if unknown */
+int rlnb200_input_slot(FFI_RLN_t *const *rln, const char *name, uint32_t *offset, uint32_t *len);
+/* reserve workspace for batches of up to max_batch proofs (otherwise grown on demand) */
+int rlnb200_reserve(FFI_RLN_t *const *rln, size_t max_batch, RlnString *err);
+/* number of kernel launches issued by this library since load (bench bookkeeping) */
+uint64_t rlnb200_launch_count(void);
+/* last stage timings of rlnb200_prove_batch_device in milliseconds: witness, qap, msm+assemble, values */
+void rlnb200_last_stage_ms(FFI_RLN_t *const *rln, float out[4]);
+
+/* Merkle tree bulk operations on device/host buffers (FullMerkleTree semantics,
+ * utils/src/merkle_tree/full_merkle_tree.rs:197-223,288-304) */
+int rlnb200_set_leaves_from_bytes(FFI_RLN_t **rln, size_t index, const uint8_t *leaves_le, size_t count, RlnString *err);
+int rlnb200_get_merkle_proofs(FFI_RLN_t *const *rln, const uint64_t *indices, size_t n, uint8_t *elements_out /* n*depth*32 */,
+                              uint8_t *index_bits_out /* n*depth */, RlnString *err);
+/* tree build on data already in HBM: d_leaves = count × 32 canonical bytes */
+int rlnb200_set_leaves_from_device(FFI_RLN_t **rln, size_t index, const void *d_leaves, size_t count, void *stream, RlnString *err);
+
+/* Variable-base G1 MSM (rln/src/partial_proof.rs:98-104 `msm`, ark-ec msm_bigint): bases n × 64 bytes
+ * (x|y canonical LE, bit 0x40 of byte 63 = infinity), scalars n × 32 bytes; result 64 bytes. */
+typedef struct RlnB200Msm RlnB200Msm_t;
+RlnB200Msm_t *rlnb200_msm_new(size_t max_n, RlnString *err);
+void rlnb200_msm_free(RlnB200Msm_t *m);
+int rlnb200_msm_g1(RlnB200Msm_t *m, const uint8_t *bases, const uint8_t *scalars, size_t n, uint8_t *result, RlnString *err);
+/* device-resident variant: d_bases are Montgomery affine points produced by rlnb200_msm_upload_bases /
+ * rlnb200_msm_gen_bases; d_scalars n × 32 canonical bytes; d_result 64 bytes */
+int rlnb200_msm_upload_bases(RlnB200Msm_t *m, const uint8_t *bases, size_t n, void *d_bases_out, RlnString *err);
+int rlnb200_msm_gen_bases(RlnB200Msm_t *m, const void *d_scalars, size_t n, void *d_bases_out, void *stream, RlnString *err);
+int rlnb200_msm_g1_device(RlnB200Msm_t *m, const void *d_bases, const void *d_scalars, size_t n, void *d_result, void *stream,
+                          RlnString *err);
+
+/* raw kernels for parity tests (host buffers, canonical LE field elements) */
+int rlnb200_poseidon_hash(const uint8_t *inputs, int n_inputs /* 1..3 */, uint8_t *out32, RlnString *err);
+int rlnb200_hash_pairs(const uint8_t *pairs /* n*64 */, size_t n, uint8_t *out /* n*32 */, RlnString *err);
+/* op: 0 mul, 1 add, 2 sub ; field: 0 Fr, 1 Fq ; exercises the PTX field arithmetic */
+int rlnb200_field_op(int field, int op, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out, RlnString *err);
+/* measured Montgomery-product rate (products/s over all SMs, CUDA-event timed); < 0 on error */
+double rlnb200_mul_throughput(int iters);
+/* witness vector w (num_wires × 32) and quotient h (domain × 32) of one witness record */
+int rlnb200_debug_witness_and_h(FFI_RLN_t *const *rln, const uint8_t *witness_le, size_t len, uint8_t *w_out, uint8_t *h_out,
+                                RlnString *err);
+size_t rlnb200_num_wires(FFI_RLN_t *const *rln);
+size_t rlnb200_domain_size(FFI_RLN_t *const *rln);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLN_B200_H */

@@ -1,0 +1,88 @@
+// TEST HARNESS (not product): compiles the product's __host__ __device__ math headers with g++ so the
+// per-thread device functions can be checked on a CPU-only box against oracle/pyref before any GPU
+// time is spent.  Exports a tiny C API for ctypes.  Nothing in zerokit_b200/ links this.
+#include <cstring>
+
+#include "curve.cuh"
+#include "poseidon.cuh"
+#include "poseidon_constants.hpp"
+#include "pairing_constants.hpp"
+#include "tower.cuh"
+#include "vm.cuh"
+
+using namespace zk;
+
+template <class F>
+static F ld(const uint8_t* b) { u32 c[8]; memcpy(c, b, 32); return F::from_canonical(c); }
+template <class F>
+static void st(uint8_t* b, const F& v) { u32 c[8]; v.to_canonical(c); memcpy(b, c, 32); }
+
+static PoseidonTables g_pt;
+static bool g_pt_ready = false;
+static const PoseidonTables* tables() { if (!g_pt_ready) { poseidon_fill_tables(g_pt); g_pt_ready = true; } return &g_pt; }
+
+extern "C" {
+// op: 0 mul 1 add 2 sub 3 inv 4 neg ; field: 0 Fr 1 Fq
+void emu_field_op(int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+    if (field == 0) {
+        Fr x = ld<Fr>(a), y = ld<Fr>(b), r;
+        r = op == 0 ? x * y : op == 1 ? x + y : op == 2 ? x - y : op == 3 ? x.inv() : x.neg();
+        st(out, r);
+    } else {
+        Fq x = ld<Fq>(a), y = ld<Fq>(b), r;
+        r = op == 0 ? x * y : op == 1 ? x + y : op == 2 ? x - y : op == 3 ? x.inv() : x.neg();
+        st(out, r);
+    }
+}
+void emu_poseidon(const uint8_t* in, int n, uint8_t* out) {
+    Fr v[3];
+    for (int i = 0; i < n; i++) v[i] = ld<Fr>(in + 32 * i);
+    Fr r = n == 1 ? poseidon1(tables(), v[0]) : n == 2 ? poseidon2(tables(), v[0], v[1]) : poseidon3(tables(), v[0], v[1], v[2]);
+    st(out, r);
+}
+// G1: k·P via XYZZ double-and-add, and P+Q via mixed add; points 64 B canonical (all-zero = infinity)
+static G1Affine ld_g1(const uint8_t* b) { return {ld<Fq>(b), ld<Fq>(b + 32)}; }
+static void st_g1(uint8_t* b, const G1Affine& p) { st(b, p.x); st(b + 32, p.y); }
+static G2Affine ld_g2(const uint8_t* b) { return {{ld<Fq>(b), ld<Fq>(b + 32)}, {ld<Fq>(b + 64), ld<Fq>(b + 96)}}; }
+static void st_g2(uint8_t* b, const G2Affine& p) { st(b, p.x.a); st(b + 32, p.x.b); st(b + 64, p.y.a); st(b + 96, p.y.b); }
+void emu_g1_mul(const uint8_t* p, const uint8_t* k, uint8_t* out) {
+    u32 kk[8]; memcpy(kk, k, 32);
+    st_g1(out, G1XYZZ::from_affine(ld_g1(p)).mul(kk).to_affine());
+}
+void emu_g1_add(const uint8_t* p, const uint8_t* q, uint8_t* out) {
+    G1XYZZ a = G1XYZZ::from_affine(ld_g1(p));
+    G1Affine b = ld_g1(q);
+    if (!b.is_inf()) a.add_affine(b);
+    st_g1(out, a.to_affine());
+}
+void emu_g1_add_full(const uint8_t* p, const uint8_t* q, uint8_t* out) {  // XYZZ + XYZZ with non-trivial ZZ
+    G1XYZZ a = G1XYZZ::from_affine(ld_g1(p)).dbl(), b = G1XYZZ::from_affine(ld_g1(q)).dbl();
+    a.add(b);
+    st_g1(out, a.to_affine());  // = 2P + 2Q
+}
+void emu_g2_mul(const uint8_t* p, const uint8_t* k, uint8_t* out) {
+    u32 kk[8]; memcpy(kk, k, 32);
+    st_g2(out, G2XYZZ::from_affine(ld_g2(p)).mul(kk).to_affine());
+}
+void emu_g2_add(const uint8_t* p, const uint8_t* q, uint8_t* out) {
+    G2XYZZ a = G2XYZZ::from_affine(ld_g2(p));
+    G2Affine b = ld_g2(q);
+    if (!b.is_inf()) a.add_affine(b);
+    st_g2(out, a.to_affine());
+}
+// pairing check: Π e(P_i, Q_i) == 1 ; g1: n×64 B, g2: n×128 B
+int emu_pairing_check(const uint8_t* g1, const uint8_t* g2, int n) {
+    static PairingTables pt; static bool init = false;
+    if (!init) { pairing_tables_init(pt); init = true; }
+    Fq12 f = Fq12::one();
+    for (int i = 0; i < n; i++) f = f * miller_loop(&pt, ld_g2(g2 + 128 * i), ld_g1(g1 + 64 * i));
+    return final_exponentiation(&pt, f) == Fq12::one() ? 1 : 0;
+}
+// witness-graph VM: one op on canonical values
+int emu_vm_duo(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+    Fr r;
+    bool ok = vm_eval_duo(op, ld<Fr>(a), ld<Fr>(b), r);
+    st(out, r);
+    return ok ? 1 : 0;
+}
+}

@@ -1,0 +1,49 @@
+"""CPU: the C-ABI library loads without a GPU, exports every symbol include/rln_b200.h declares, and
+refuses to compute without a device (no CPU fallback)."""
+import ctypes
+import subprocess
+
+import pytest
+
+from zerokit_b200 import ffi
+
+
+def test_exports_match_header():
+    L = ffi.lib()
+    out = subprocess.check_output(["nm", "-D", "--defined-only", ffi.LIB_PATH], text=True)
+    exported = {l.split()[-1] for l in out.splitlines() if l.strip()}
+    declared = ffi.declared_symbols()
+    assert len(declared) > 80
+    missing = [s for s in declared if s not in exported]
+    assert not missing, missing
+    unbound = [s for s in declared if s not in L._signatures]
+    assert not unbound, unbound
+
+
+def test_host_only_helpers_work_without_gpu(goldens):
+    import zerokit_b200 as z
+    for msg, v in goldens["derived"]["hash_to_field"].items():
+        assert z.hash_to_field_le(msg.encode()) == int(v)
+        assert z.hash_to_field_be(msg.encode()) == int(v)
+    w = z.RLNWitnessInput.new_single(5, 10, 3, [1, 2], [0, 1], 7, 9)
+    b = w.to_bytes_le()
+    assert len(b) == 1 + 32 * 7 + 16 + 2 and z.RLNWitnessInput.from_bytes_le(b).to_bytes_le() == b
+    with pytest.raises(z.RLNError, match="User message limit cannot be zero"):
+        z.RLNWitnessInput.new_single(5, 0, 0, [1], [0], 7, 9)
+    with pytest.raises(z.RLNError, match=r"Message id \(10\) is not within user_message_limit \(10\)"):
+        z.RLNWitnessInput.new_single(5, 10, 10, [1], [0], 7, 9)
+    with pytest.raises(z.RLNError, match="Merkle proof length mismatch: expected 2, got 1"):
+        z.RLNWitnessInput.new_single(5, 10, 1, [1, 2], [0], 7, 9)
+    with pytest.raises(z.RLNError, match="Expected to read"):
+        z.RLNWitnessInput.from_bytes_le(b[:-1])
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import zerokit_b200 as z
+    with pytest.raises(z.RLNError, match="no usable CUDA device"):
+        z.RLN.new(20)
+    with pytest.raises(z.RLNError):
+        z.poseidon_hash([1, 2])

@@ -1,0 +1,8 @@
+"""zerokit_b200 — B200-native (sm_100a) drop-in for the proving hot path of vacp2p/zerokit's `rln` crate.
+
+The product is the CUDA shared library zerokit_b200/lib/librln_b200.so (C ABI: include/rln_b200.h);
+`zerokit_b200.rln` is a thin ctypes mirror of the reference's public API used by the tests and the
+benchmark.  Importing the API without the built library raises — there is no CPU fallback.
+"""
+from .rln import (RLN, RLNError, RLNProof, RLNProofValues, RLNWitnessInput, G1Msm, hash_to_field_le, hash_to_field_be,  # noqa: F401
+                  poseidon_hash, poseidon_hash_pair, keygen, field_op, hash_pairs, DEFAULT_TREE_DEPTH, R)

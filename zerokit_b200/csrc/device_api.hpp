@@ -1,0 +1,140 @@
+// Internal launcher API between the host layer (rln_host.cu) and the kernel translation units.
+// Everything here runs on the GPU; there is no host implementation behind any of these calls.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+
+#include <cstddef>
+#include <vector>
+
+#include "curve.cuh"
+#include "poseidon.cuh"
+#include "tower.cuh"
+#include "vm.cuh"
+
+namespace zk {
+
+#define ZK_CUDA_CHECK(expr)                                                            \
+    do {                                                                               \
+        cudaError_t _e = (expr);                                                       \
+        if (_e != cudaSuccess) throw ::zk::CudaError(_e, #expr, __FILE__, __LINE__);   \
+    } while (0)
+
+struct CudaError {
+    cudaError_t code;
+    const char* expr;
+    const char* file;
+    int line;
+    CudaError(cudaError_t c, const char* e, const char* f, int l) : code(c), expr(e), file(f), line(l) {}
+};
+
+// ---- k_poseidon.cu -------------------------------------------------------------------------
+void poseidon_upload_tables(const PoseidonTables& t);
+// canonical 32-byte LE integers (< r assumed; reduced otherwise) → Montgomery Fr, and back
+void launch_fr_from_bytes(const uint8_t* d_in, Fr* d_out, size_t n, cudaStream_t s);
+void launch_fr_to_bytes(const Fr* d_in, uint8_t* d_out, size_t n, cudaStream_t s);
+// out[i] = Poseidon(in[2i], in[2i+1])   (Montgomery in/out)
+void launch_hash_pairs(const Fr* d_in, Fr* d_out, size_t n, cudaStream_t s);
+// Merkle tree in HBM, 1-indexed heap: root = nodes[1], level l = nodes[2^l .. 2^(l+1)), leaf i = nodes[2^depth + i].
+// fill with the empty-tree values (zeros[k] per level)
+void launch_merkle_fill_empty(Fr* d_nodes, u32 depth, cudaStream_t s);
+// leaves (canonical bytes, on device) → nodes[2^depth+start ..), then rehash the touched ancestors level by level
+void launch_merkle_set_range(Fr* d_nodes, u32 depth, size_t start, const uint8_t* d_leaves_bytes, size_t count, cudaStream_t s);
+// rehash ancestors of leaf range [start, start+count)
+void launch_merkle_rehash(Fr* d_nodes, u32 depth, size_t start, size_t count, cudaStream_t s);
+// membership paths: for each index, depth sibling values (canonical bytes, leaf→root) and depth index bits
+void launch_merkle_paths(const Fr* d_nodes, u32 depth, const u64* d_indices, size_t n, uint8_t* d_elems_bytes, uint8_t* d_bits, cudaStream_t s);
+// proof values per witness (rln/src/protocol/witness.rs:759-828): inputs layout = circuit input slots
+// (canonical bytes, n × n_slots × 32); out = n × 5 × 32 bytes [root, ext_nullifier, x, y, nullifier]
+struct InputSlots { u32 secret, limit, message_id, path, index, x, ext_null, depth, n_slots; };
+void launch_proof_values(const uint8_t* d_inputs, InputSlots sl, size_t n, uint8_t* d_out, cudaStream_t s);
+// generic small helpers used by the FFI utilities (single-thread kernels)
+void launch_poseidon_n(const uint8_t* d_in_bytes, int n_inputs, uint8_t* d_out_bytes, cudaStream_t s);
+
+// ---- k_prover.cu ---------------------------------------------------------------------------
+struct CircuitDev {
+    // witness graph
+    u32 n_nodes, n_slots, n_wires;
+    const VmInstr* prog;
+    const Fr* consts;
+    const u32* signals;  // wire → node
+    // QAP
+    u32 n_constraints, n_instance, domain, log_domain;
+    const u32 *a_ptr, *a_col, *b_ptr, *b_col;
+    const Fr *a_val, *b_val;
+    const Fr* tw_inv;    // ω^{-k}, k < domain/2
+    const Fr* tw_fwd;    // ω^{k}
+    const Fr* coset;     // position p (bit-reversed order) → g^{rev(p)} / domain
+};
+// inputs: n × n_slots canonical bytes → vals [n_nodes][B] (Montgomery).  err[j] != 0 if node evaluation failed.
+void launch_witness(const CircuitDev& c, const uint8_t* d_inputs, Fr* d_vals, u32 B, u32* d_err, cudaStream_t s);
+// a,b,c [domain][B]; afterwards abuf holds h = a·b − c on the coset (natural order)
+void launch_qap(const CircuitDev& c, const Fr* d_vals, Fr* d_a, Fr* d_b, Fr* d_c, u32 B, cudaStream_t s);
+// plain batched NTT for tests: data [n][B] natural order in/out
+void launch_ntt_test(Fr* d_data, u32 log_n, u32 B, bool inverse, const Fr* tw, cudaStream_t s);
+
+// ---- k_msm_fixed.cu ------------------------------------------------------------------------
+struct MsmGroupDev {
+    u32 n_bases;         // non-infinity bases
+    const u32* row;      // scalar row index per base in the source matrix
+    const void* table;   // [base][window][2^(c-1)] affine points
+    u32 which_src;       // 0: vals matrix, 1: h matrix
+};
+struct FixedMsmPlan {
+    int c, K;            // window bits, windows
+    MsmGroupDev g1[4];   // A, B1, L, H
+    MsmGroupDev g2;      // B2
+};
+// builds [base][window][digit] tables from affine bases (Montgomery, no infinities)
+void launch_build_table_g1(const G1Affine* d_bases, u32 n, int c, int K, G1Affine* d_table, cudaStream_t s);
+void launch_build_table_g2(const G2Affine* d_bases, u32 n, int c, int K, G2Affine* d_table, cudaStream_t s);
+struct ProverKeyDev {  // fixed points of the proving key (affine, Montgomery)
+    G1Affine alpha_g1, beta_g1, delta_g1;
+    G2Affine beta_g2, delta_g2;
+};
+struct MsmTask { u32 group, lo, hi, pad; };  // bases [lo, hi) of one group, summed by one thread per proof
+struct MsmWorkspace {
+    G1XYZZ* part_g1;  // [tasks][B]
+    G2XYZZ* part_g2;
+    G1XYZZ* sum_g1;   // [4][B]
+    G2XYZZ* sum_g2;   // [B]
+    const MsmTask *tasks_g1, *tasks_g2;  // device arrays built from msm_make_tasks for this B
+    u32 n_tasks_g1, n_tasks_g2;
+};
+// all five MSMs for B proofs + assembly (partial_proof.rs:226-273) + affine + ark-compressed bytes.
+// rs: B × 64 canonical bytes (r | s).  proofs_out: B × 128 bytes.  proofs_affine (optional): B × 256 bytes canonical A|B|C
+void launch_msm_and_assemble(const FixedMsmPlan& plan, const ProverKeyDev& pk, const Fr* d_vals, const Fr* d_h, u32 B,
+                             const uint8_t* d_rs, MsmWorkspace& ws, uint8_t* d_proofs_out, uint8_t* d_proofs_affine,
+                             cudaStream_t s);
+std::vector<MsmTask> msm_make_tasks(const FixedMsmPlan& plan, u32 B, bool g2);
+
+// ---- k_msm_var.cu --------------------------------------------------------------------------
+// variable-base G1 Pippenger MSM (rln/src/partial_proof.rs:98-104 `msm`): bases affine Montgomery (device),
+// scalars canonical 32-byte LE (device).  result: 64 bytes canonical affine (x|y), all-zero = infinity.
+struct VarMsmWorkspace;
+VarMsmWorkspace* var_msm_workspace_create(size_t max_n);
+void var_msm_workspace_destroy(VarMsmWorkspace* w);
+void launch_var_msm_g1(VarMsmWorkspace* w, const G1Affine* d_bases, const uint8_t* d_scalars, size_t n, uint8_t* d_result,
+                       cudaStream_t s);
+// canonical x|y bytes → Montgomery affine (flags in the top bits of y's last byte: 0x40 = infinity)
+void launch_g1_from_bytes(const uint8_t* d_in, G1Affine* d_out, size_t n, cudaStream_t s);
+void launch_g2_from_bytes(const uint8_t* d_in, G2Affine* d_out, size_t n, cudaStream_t s);
+// bases[i] = k_i · G for the G1 generator (bench input generation on the device)
+void launch_g1_mul_gen(const uint8_t* d_scalars, G1Affine* d_out, size_t n, cudaStream_t s);
+
+// ---- k_verify.cu ---------------------------------------------------------------------------
+struct VerifyKeyDev {
+    G1Affine alpha_g1;
+    G2Affine beta_g2, gamma_g2, delta_g2;
+    const G1Affine* gamma_abc;  // device pointer, n_public + 1 entries
+    u32 n_public;
+};
+void pairing_upload_tables(const PairingTables& t);
+// proofs: n × 128 B ark-compressed; publics: n × n_public × 32 canonical bytes (circuit order);
+// ok[j] = 1 valid, 0 invalid, 2 malformed encoding (not on curve / bad flags)
+void launch_verify(const VerifyKeyDev& vk, const uint8_t* d_proofs, const uint8_t* d_publics, size_t n, uint8_t* d_ok, cudaStream_t s);
+// decompress n proofs to affine canonical bytes (256 B each: A 64 | B 128 | C 64); ok[j]=0 if malformed
+void launch_decompress(const uint8_t* d_proofs, size_t n, uint8_t* d_affine, uint8_t* d_ok, cudaStream_t s);
+
+}  // namespace zk

@@ -1,0 +1,406 @@
+// Host-side helpers of the boundary layer: byte/bigint utilities, Keccak-256 (hash_to_field),
+// the arkzkey and witnesscalc-graph parsers.  No proving arithmetic happens here: everything that
+// touches field elements beyond byte shuffling is handed to the GPU.
+//
+//   Keccak-256 / hash_to_field   rln/src/hashers.rs:73-93  (tiny-keccak 2.0.2, padding 0x01…0x80)
+//   arkzkey layout               rln/src/circuit/mod.rs:256-305 (ark-serialize uncompressed, unchecked)
+//   graph.bin layout             rln/src/circuit/iden3calc/storage.rs:16-22,265-302; proto.rs:7-117
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "vm.cuh"
+
+namespace zk {
+
+// ------------------------------------------------------------------------------- 256-bit byte helpers
+static const uint8_t FR_MODULUS_LE[32] = {0x01, 0x00, 0x00, 0xf0, 0x93, 0xf5, 0xe1, 0x43, 0x91, 0x70, 0xb9, 0x79, 0x48, 0xe8, 0x33, 0x28,
+                                          0x5d, 0x58, 0x81, 0x81, 0xb6, 0x45, 0x50, 0xb8, 0x29, 0xa0, 0x31, 0xe1, 0x72, 0x4e, 0x64, 0x30};
+
+inline int cmp_le32(const uint8_t* a, const uint8_t* b) {
+    for (int i = 31; i >= 0; i--) {
+        if (a[i] < b[i]) return -1;
+        if (a[i] > b[i]) return 1;
+    }
+    return 0;
+}
+inline bool fr_is_canonical(const uint8_t* a) { return cmp_le32(a, FR_MODULUS_LE) < 0; }
+inline void sub_le32(uint8_t* a, const uint8_t* b) {
+    int borrow = 0;
+    for (int i = 0; i < 32; i++) {
+        int d = (int)a[i] - b[i] - borrow;
+        borrow = d < 0;
+        a[i] = (uint8_t)(d & 0xff);
+    }
+}
+// value mod r for an arbitrary 256-bit little-endian integer (2^256 / r < 6)
+inline void fr_reduce(uint8_t* a) {
+    while (!fr_is_canonical(a)) sub_le32(a, FR_MODULUS_LE);
+}
+inline bool is_zero32(const uint8_t* a) {
+    for (int i = 0; i < 32; i++)
+        if (a[i]) return false;
+    return true;
+}
+// decimal string of a 256-bit little-endian integer (ark-ff Display prints decimal)
+inline std::string decimal_le32(const uint8_t* a) {
+    uint32_t w[8];
+    memcpy(w, a, 32);
+    std::string out;
+    for (;;) {
+        bool nz = false;
+        uint64_t rem = 0;
+        for (int i = 7; i >= 0; i--) {
+            uint64_t cur = (rem << 32) | w[i];
+            w[i] = (uint32_t)(cur / 10);
+            rem = cur % 10;
+            nz = nz || w[i];
+        }
+        out.push_back((char)('0' + rem));
+        if (!nz) break;
+    }
+    return std::string(out.rbegin(), out.rend());
+}
+
+// ------------------------------------------------------------------------------- Keccak-256
+inline void keccak_f1600(uint64_t st[25]) {
+    static const uint64_t RC[24] = {0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808AULL, 0x8000000080008000ULL,
+                                    0x000000000000808BULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
+                                    0x000000000000008AULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000AULL,
+                                    0x000000008000808BULL, 0x800000000000008BULL, 0x8000000000008089ULL, 0x8000000000008003ULL,
+                                    0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800AULL, 0x800000008000000AULL,
+                                    0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+    static const int ROT[24] = {1, 3, 6, 10, 15, 21, 28, 36, 45, 55, 2, 14, 27, 41, 56, 8, 25, 43, 62, 18, 39, 61, 20, 44};
+    static const int PIL[24] = {10, 7, 11, 17, 18, 3, 5, 16, 8, 21, 24, 4, 15, 23, 19, 13, 12, 2, 20, 14, 22, 9, 6, 1};
+    for (int round = 0; round < 24; round++) {
+        uint64_t bc[5];
+        for (int i = 0; i < 5; i++) bc[i] = st[i] ^ st[i + 5] ^ st[i + 10] ^ st[i + 15] ^ st[i + 20];
+        for (int i = 0; i < 5; i++) {
+            uint64_t t = bc[(i + 4) % 5] ^ ((bc[(i + 1) % 5] << 1) | (bc[(i + 1) % 5] >> 63));
+            for (int j = 0; j < 25; j += 5) st[j + i] ^= t;
+        }
+        uint64_t t = st[1];
+        for (int i = 0; i < 24; i++) {
+            int j = PIL[i];
+            uint64_t b = st[j];
+            st[j] = (t << ROT[i]) | (t >> (64 - ROT[i]));
+            t = b;
+        }
+        for (int j = 0; j < 25; j += 5) {
+            for (int i = 0; i < 5; i++) bc[i] = st[j + i];
+            for (int i = 0; i < 5; i++) st[j + i] ^= (~bc[(i + 1) % 5]) & bc[(i + 2) % 5];
+        }
+        st[0] ^= RC[round];
+    }
+}
+inline void keccak256(const uint8_t* data, size_t len, uint8_t out[32]) {
+    uint64_t st[25];
+    memset(st, 0, sizeof st);
+    const size_t rate = 136;
+    uint8_t block[136];
+    size_t off = 0;
+    for (;;) {
+        size_t take = len - off < rate ? len - off : rate;
+        memset(block, 0, rate);
+        memcpy(block, data + off, take);
+        off += take;
+        bool last = take < rate;
+        if (last) {
+            block[take] ^= 0x01;
+            block[rate - 1] ^= 0x80;
+        }
+        for (size_t i = 0; i < rate / 8; i++) {
+            uint64_t w;
+            memcpy(&w, block + 8 * i, 8);
+            st[i] ^= w;
+        }
+        keccak_f1600(st);
+        if (last) break;
+    }
+    memcpy(out, st, 32);
+}
+
+// ------------------------------------------------------------------------------- arkzkey
+struct ZkeyHost {
+    // raw point bytes exactly as in the file (x|y canonical LE, flags in the last byte)
+    std::vector<uint8_t> alpha_g1, beta_g1, delta_g1;     // 64 each
+    std::vector<uint8_t> beta_g2, gamma_g2, delta_g2;     // 128 each
+    std::vector<uint8_t> gamma_abc, a_query, b_g1, h_query, l_query;  // n × 64
+    std::vector<uint8_t> b_g2;                                      // n × 128
+    uint64_t num_instance = 0, num_witness = 0, num_constraints = 0;
+    // CSR matrices, coefficients canonical LE
+    std::vector<uint32_t> a_ptr, a_col, b_ptr, b_col;
+    std::vector<uint8_t> a_val, b_val;
+};
+
+struct ByteReader {
+    const uint8_t* p;
+    size_t n, o = 0;
+    void need(size_t k) const {
+        if (o + k > n) throw std::runtime_error("unexpected end of zkey data");
+    }
+    uint64_t u64() {
+        need(8);
+        uint64_t v;
+        memcpy(&v, p + o, 8);
+        o += 8;
+        return v;
+    }
+    void take(std::vector<uint8_t>& dst, size_t k) {
+        need(k);
+        dst.insert(dst.end(), p + o, p + o + k);
+        o += k;
+    }
+};
+
+inline void parse_zkey(const uint8_t* data, size_t n, ZkeyHost& z) {
+    ByteReader r{data, n};
+    r.take(z.alpha_g1, 64);
+    r.take(z.beta_g2, 128);
+    r.take(z.gamma_g2, 128);
+    r.take(z.delta_g2, 128);
+    auto vec = [&](std::vector<uint8_t>& dst, size_t elem) {
+        uint64_t k = r.u64();
+        if (k > n / elem) throw std::runtime_error("zkey vector length exceeds file size");
+        r.take(dst, k * elem);
+    };
+    vec(z.gamma_abc, 64);
+    r.take(z.beta_g1, 64);
+    r.take(z.delta_g1, 64);
+    vec(z.a_query, 64);
+    vec(z.b_g1, 64);
+    vec(z.b_g2, 128);
+    vec(z.h_query, 64);
+    vec(z.l_query, 64);
+    z.num_instance = r.u64();
+    z.num_witness = r.u64();
+    z.num_constraints = r.u64();
+    r.u64();
+    r.u64();
+    r.u64();
+    auto mat = [&](std::vector<uint32_t>& ptr, std::vector<uint32_t>& col, std::vector<uint8_t>& val) {
+        uint64_t rows = r.u64();
+        if (rows > n) throw std::runtime_error("zkey matrix too large");
+        ptr.assign(1, 0);
+        for (uint64_t i = 0; i < rows; i++) {
+            uint64_t k = r.u64();
+            if (k > n / 40) throw std::runtime_error("zkey matrix row too large");
+            for (uint64_t e = 0; e < k; e++) {
+                r.take(val, 32);
+                col.push_back((uint32_t)r.u64());
+            }
+            ptr.push_back((uint32_t)col.size());
+        }
+    };
+    mat(z.a_ptr, z.a_col, z.a_val);
+    mat(z.b_ptr, z.b_col, z.b_val);
+    std::vector<uint32_t> cp, cc;
+    std::vector<uint8_t> cv;
+    mat(cp, cc, cv);
+    if (r.o != n) throw std::runtime_error("trailing bytes after zkey");
+    if (z.a_ptr.size() != z.num_constraints + 1 || z.b_ptr.size() != z.num_constraints + 1)
+        throw std::runtime_error("zkey matrices do not match num_constraints");
+}
+
+// ------------------------------------------------------------------------------- graph.bin
+struct GraphHost {
+    std::vector<VmInstr> prog;
+    std::vector<uint8_t> consts;  // canonical LE, 32 bytes each (already reduced mod r)
+    std::vector<uint32_t> signals;
+    std::map<std::string, std::pair<uint32_t, uint32_t>> inputs;
+    uint32_t n_slots = 0;
+};
+
+inline bool rd_varint(const uint8_t* p, size_t n, size_t& o, uint64_t& v) {
+    v = 0;
+    for (int s = 0; s < 70; s += 7) {
+        if (o >= n) return false;
+        uint8_t c = p[o++];
+        v |= (uint64_t)(c & 0x7f) << s;
+        if (!(c & 0x80)) return true;
+    }
+    return false;
+}
+struct PbField {
+    uint64_t tag, wt, val;
+    const uint8_t* ptr;
+    size_t len;
+};
+inline bool pb_next(const uint8_t* p, size_t n, size_t& o, PbField& f) {
+    uint64_t key;
+    if (!rd_varint(p, n, o, key)) return false;
+    f.tag = key >> 3;
+    f.wt = key & 7;
+    f.val = 0;
+    f.ptr = nullptr;
+    f.len = 0;
+    switch (f.wt) {
+        case 0: return rd_varint(p, n, o, f.val);
+        case 2: {
+            uint64_t l;
+            if (!rd_varint(p, n, o, l) || o + l > n) return false;
+            f.ptr = p + o;
+            f.len = l;
+            o += l;
+            return true;
+        }
+        case 5: if (o + 4 > n) return false; o += 4; return true;
+        case 1: if (o + 8 > n) return false; o += 8; return true;
+        default: return false;
+    }
+}
+// little-endian bytes of any length reduced mod r (Fr::from_le_bytes_mod_order, storage.rs:45-47)
+inline void le_bytes_mod_r(const uint8_t* b, size_t n, uint8_t out[32]) {
+    // Horner over bytes from the most significant end with 320-bit scratch: acc = acc·256 + byte (mod r)
+    uint8_t acc[33];
+    memset(acc, 0, sizeof acc);
+    for (size_t i = n; i-- > 0;) {
+        for (int k = 32; k > 0; k--) acc[k] = acc[k - 1];
+        acc[0] = b[i];
+        // acc < 256·r < 2^264: subtract r·2^j greedily (at most 8 bits worth)
+        for (int bit = 8; bit >= 0; bit--) {
+            uint8_t m[33];
+            memset(m, 0, sizeof m);
+            // m = r << bit
+            unsigned carry = 0;
+            for (int k = 0; k < 32; k++) {
+                unsigned v = ((unsigned)FR_MODULUS_LE[k] << bit) | carry;
+                m[k] = (uint8_t)(v & 0xff);
+                carry = v >> 8;
+            }
+            m[32] = (uint8_t)carry;
+            int c = 0;
+            for (int k = 32; k >= 0; k--) {
+                if (acc[k] != m[k]) { c = acc[k] < m[k] ? -1 : 1; break; }
+            }
+            if (c >= 0) {
+                int borrow = 0;
+                for (int k = 0; k < 33; k++) {
+                    int d = (int)acc[k] - m[k] - borrow;
+                    borrow = d < 0;
+                    acc[k] = (uint8_t)(d & 0xff);
+                }
+            }
+        }
+    }
+    memcpy(out, acc, 32);
+}
+
+inline void parse_graph(const uint8_t* d, size_t n, GraphHost& g) {
+    static const char MAGIC[] = "wtns.graph.001";
+    if (n < 22 || memcmp(d, MAGIC, 14)) throw std::runtime_error("Invalid magic");
+    size_t o = 14;
+    uint64_t cnt;
+    memcpy(&cnt, d + o, 8);
+    o += 8;
+    if (cnt > n) throw std::runtime_error("graph node count exceeds file size");
+    g.prog.reserve(cnt);
+    for (uint64_t i = 0; i < cnt; i++) {
+        uint64_t len;
+        if (!rd_varint(d, n, o, len) || o + len > n) throw std::runtime_error("Unexpected EOF");
+        const uint8_t* m = d + o;
+        o += len;
+        size_t mo = 0;
+        PbField f;
+        if (!pb_next(m, len, mo, f) || f.wt != 2) throw std::runtime_error("Proto::Node must have a node field");
+        uint64_t vals[5] = {0, 0, 0, 0, 0};
+        const uint8_t* sub = nullptr;
+        size_t sublen = 0, bo = 0;
+        PbField bf;
+        while (bo < f.len) {
+            if (!pb_next(f.ptr, f.len, bo, bf)) throw std::runtime_error("malformed node");
+            if (bf.tag < 5 && bf.wt == 0) vals[bf.tag] = bf.val;
+            if (bf.tag == 1 && bf.wt == 2) { sub = bf.ptr; sublen = bf.len; }
+        }
+        VmInstr in{0, 0, 0, 0};
+        switch (f.tag) {
+            case 1: in.kind_op = VM_INPUT; in.a = (uint32_t)vals[1]; break;
+            case 2: {
+                const uint8_t* vb = nullptr;
+                size_t vl = 0, so = 0;
+                PbField sf;
+                if (!sub) throw std::runtime_error("Constant node must have a value");
+                while (so < sublen) {
+                    if (!pb_next(sub, sublen, so, sf)) throw std::runtime_error("malformed constant");
+                    if (sf.tag == 1 && sf.wt == 2) { vb = sf.ptr; vl = sf.len; }
+                }
+                in.kind_op = VM_CONST;
+                in.a = (uint32_t)(g.consts.size() / 32);
+                uint8_t c[32];
+                le_bytes_mod_r(vb, vl, c);
+                g.consts.insert(g.consts.end(), c, c + 32);
+                break;
+            }
+            case 3:
+                if (vals[1] > 1) throw std::runtime_error("UnoOp must be valid enum value");
+                in.kind_op = VM_UNO | ((uint32_t)vals[1] << 8); in.a = (uint32_t)vals[2]; break;
+            case 4:
+                if (vals[1] > 19) throw std::runtime_error("DuoOp must be valid enum value");
+                in.kind_op = VM_DUO | ((uint32_t)vals[1] << 8); in.a = (uint32_t)vals[2]; in.b = (uint32_t)vals[3]; break;
+            case 5:
+                if (vals[1] != 0) throw std::runtime_error("TresOp must be valid enum value");
+                in.kind_op = VM_TRES; in.a = (uint32_t)vals[2]; in.b = (uint32_t)vals[3]; in.c = (uint32_t)vals[4]; break;
+            default: throw std::runtime_error("Proto::Node must have a node field");
+        }
+        // operands must refer to earlier nodes (topological order is what evaluate() relies on)
+        uint32_t kind = in.kind_op & 0xff;
+        if ((kind == VM_UNO || kind == VM_DUO || kind == VM_TRES) && in.a >= i) throw std::runtime_error("node operand out of order");
+        if ((kind == VM_DUO || kind == VM_TRES) && in.b >= i) throw std::runtime_error("node operand out of order");
+        if (kind == VM_TRES && in.c >= i) throw std::runtime_error("node operand out of order");
+        g.prog.push_back(in);
+    }
+    uint64_t mdlen;
+    if (!rd_varint(d, n, o, mdlen) || o + mdlen > n) throw std::runtime_error("Unexpected EOF");
+    const uint8_t* md = d + o;
+    size_t mo = 0;
+    PbField f;
+    while (mo < mdlen) {
+        if (!pb_next(md, mdlen, mo, f)) throw std::runtime_error("malformed graph metadata");
+        if (f.tag == 1 && f.wt == 2) {
+            size_t po = 0;
+            uint64_t v;
+            while (po < f.len) {
+                if (!rd_varint(f.ptr, f.len, po, v)) throw std::runtime_error("malformed witness_signals");
+                g.signals.push_back((uint32_t)v);
+            }
+        } else if (f.tag == 1 && f.wt == 0) {
+            g.signals.push_back((uint32_t)f.val);
+        } else if (f.tag == 2 && f.wt == 2) {
+            size_t eo = 0;
+            PbField ef;
+            std::string key;
+            uint64_t off = 0, ln = 0;
+            while (eo < f.len) {
+                if (!pb_next(f.ptr, f.len, eo, ef)) throw std::runtime_error("malformed inputs map");
+                if (ef.tag == 1 && ef.wt == 2) key.assign((const char*)ef.ptr, ef.len);
+                if (ef.tag == 2 && ef.wt == 2) {
+                    size_t so = 0;
+                    PbField sf;
+                    while (so < ef.len) {
+                        if (!pb_next(ef.ptr, ef.len, so, sf)) throw std::runtime_error("malformed signal description");
+                        if (sf.tag == 1) off = sf.val;
+                        if (sf.tag == 2) ln = sf.val;
+                    }
+                }
+            }
+            g.inputs[key] = {(uint32_t)off, (uint32_t)ln};
+        }
+    }
+    for (uint32_t s : g.signals)
+        if (s >= g.prog.size()) throw std::runtime_error("witness signal index out of range");
+    bool started = false;  // iden3calc.rs:106-121 get_inputs_size
+    uint32_t mx = 0;
+    for (auto& in : g.prog) {
+        if ((in.kind_op & 0xff) == VM_INPUT) { mx = in.a > mx ? in.a : mx; started = true; }
+        else if (started) break;
+    }
+    g.n_slots = mx + 1;
+    for (auto& in : g.prog)
+        if ((in.kind_op & 0xff) == VM_INPUT && in.a >= g.n_slots) throw std::runtime_error("input index out of range");
+}
+
+}  // namespace zk

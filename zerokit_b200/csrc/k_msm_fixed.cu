@@ -1,0 +1,345 @@
+// Batched fixed-base multi-scalar multiplication and Groth16 proof assembly (sm_100a).
+//
+// Path covered: the five MSMs of ark-groth16's create_proof_with_assignment
+// as restated in rln/src/partial_proof.rs:226-273 (A, B in G1, B in G2, L, H) and the final
+//   g_a  = α₁ + Σ wᵢ·Aᵢ + r·δ₁
+//   g1_b = β₁ + Σ wᵢ·B¹ᵢ + s·δ₁          (only when r ≠ 0, partial_proof.rs:242-248)
+//   g2_b = β₂ + Σ wᵢ·B²ᵢ + s·δ₂
+//   g_c  = s·g_a + r·g1_b − rs·δ₁ + Σ wᵢ·Lᵢ + Σ hᵢ·Hᵢ
+// followed by into_affine() and ark-serialize's compressed encoding (rln/src/protocol/proof.rs:413-428).
+//
+// B200-first formulation: the bases never change (they come from the zkey), and a batch holds
+// thousands of independent proofs.  Instead of running Pippenger per proof (bucket reduction would
+// cost 25-40 % at n ≈ 6 K), every base gets a precomputed table T[base][window][d] = d·2^{c·window}·P
+// for d = 1 … 2^{c−1} (signed digits), resident in HBM (c = 12: ≈ 90 GB of the 180 GB).  An MSM
+// then is a pure stream of mixed additions of table entries — no doublings, no buckets — and a warp
+// of 32 proofs walks the same (base, window) sub-table together.  Partial sums per (task, proof) are
+// combined by a second kernel.  Additions are complete (∞, P = ±Q handled), because duplicate bases
+// in a zkey cannot be excluded.
+#include <vector>
+
+#include "device_api.hpp"
+
+namespace zk {
+
+// ------------------------------------------------------------------------------------------- table construction
+// wb[base*K + k] = 2^{c·k}·P_base (affine).  One thread per base.
+template <class F>
+__global__ void __launch_bounds__(64) k_window_bases(const Affine<F>* __restrict__ bases, u32 n, int c, int K, Affine<F>* __restrict__ wb) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    XYZZ<F> acc = XYZZ<F>::from_affine(bases[i]);
+    wb[(size_t)i * K] = bases[i];
+    for (int k = 1; k < K; k++) {
+        for (int t = 0; t < c; t++) acc = acc.dbl();
+        wb[(size_t)i * K + k] = acc.to_affine();
+    }
+}
+
+// table[(base*K + k)*half + d−1] = d·wb[base*K + k], d = 1 … half.  One thread per (base, window);
+// NB consecutive multiples are normalised with one shared inversion (Montgomery's trick).
+template <class F, int NB>
+__global__ void __launch_bounds__(64) k_fill_table(const Affine<F>* __restrict__ wb, size_t n_slots, u32 half, Affine<F>* __restrict__ table) {
+    const size_t slot = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
+    const Affine<F> P = wb[slot];
+    Affine<F>* out = table + slot * half;
+    XYZZ<F> acc = XYZZ<F>::from_affine(P);
+    for (u32 d0 = 0; d0 < half; d0 += NB) {
+        XYZZ<F> buf[NB];
+        F pref[NB];
+        F run = F::one();
+#pragma unroll 1
+        for (int t = 0; t < NB; t++) {
+            buf[t] = acc;
+            run = run * acc.ZZZ;
+            pref[t] = run;
+            acc.add_affine(P);
+        }
+        F inv = run.inv();
+#pragma unroll 1
+        for (int t = NB - 1; t >= 0; t--) {
+            F zi = t ? inv * pref[t - 1] : inv;  // 1/ZZZ_t
+            inv = inv * buf[t].ZZZ;
+            F zz_inv = (zi * buf[t].ZZ).sqr();
+            if (d0 + t < half) out[d0 + t] = {buf[t].X * zz_inv, buf[t].Y * zi};
+        }
+    }
+}
+
+void launch_build_table_g1(const G1Affine* d_bases, u32 n, int c, int K, G1Affine* d_table, cudaStream_t s) {
+    if (!n) return;
+    G1Affine* wb = nullptr;
+    ZK_CUDA_CHECK(cudaMallocAsync((void**)&wb, sizeof(G1Affine) * (size_t)n * K, s));
+    k_window_bases<Fq><<<(n + 63) / 64, 64, 0, s>>>(d_bases, n, c, K, wb);
+    size_t slots = (size_t)n * K;
+    k_fill_table<Fq, 16><<<(unsigned)((slots + 63) / 64), 64, 0, s>>>(wb, slots, 1u << (c - 1), d_table);
+    ZK_CUDA_CHECK(cudaFreeAsync(wb, s));
+}
+void launch_build_table_g2(const G2Affine* d_bases, u32 n, int c, int K, G2Affine* d_table, cudaStream_t s) {
+    if (!n) return;
+    G2Affine* wb = nullptr;
+    ZK_CUDA_CHECK(cudaMallocAsync((void**)&wb, sizeof(G2Affine) * (size_t)n * K, s));
+    k_window_bases<Fq2><<<(n + 63) / 64, 64, 0, s>>>(d_bases, n, c, K, wb);
+    size_t slots = (size_t)n * K;
+    k_fill_table<Fq2, 8><<<(unsigned)((slots + 63) / 64), 64, 0, s>>>(wb, slots, 1u << (c - 1), d_table);
+    ZK_CUDA_CHECK(cudaFreeAsync(wb, s));
+}
+
+// ------------------------------------------------------------------------------------------- accumulate
+
+template <class F>
+struct AccumArgs {
+    const Fr* src[2];            // scalar matrices [row][B]: 0 = witness values, 1 = h
+    const u32* row[4];           // per group: scalar row of each base
+    const Affine<F>* table[4];   // per group
+    u32 which[4];
+    const MsmTask* tasks;
+    XYZZ<F>* part;               // [task][B]
+    u32 B;
+    int c, K;
+};
+
+template <class F>
+__device__ __forceinline__ Affine<F> ld_point(const Affine<F>* p);
+template <>
+__device__ __forceinline__ Affine<Fq> ld_point<Fq>(const Affine<Fq>* p) {
+    return {ldg_fp(&p->x), ldg_fp(&p->y)};
+}
+template <>
+__device__ __forceinline__ Affine<Fq2> ld_point<Fq2>(const Affine<Fq2>* p) {
+    return {{ldg_fp(&p->x.a), ldg_fp(&p->x.b)}, {ldg_fp(&p->y.a), ldg_fp(&p->y.b)}};
+}
+
+// signed window digit k of the canonical scalar s (with incoming carry); returns digit in [−2^{c−1}, 2^{c−1}]
+__device__ __forceinline__ int window_digit(const u32* s, int k, int c, u32& carry) {
+    const int bit = k * c;
+    const int w = bit >> 5, sh = bit & 31;
+    u32 v = 0;
+    if (w < 8) {
+        v = s[w] >> sh;
+        if (sh + c > 32 && w + 1 < 8) v |= s[w + 1] << (32 - sh);
+    }
+    int d = (int)(v & ((1u << c) - 1)) + (int)carry;
+    if (d > (1 << (c - 1))) { d -= (1 << c); carry = 1; } else carry = 0;
+    return d;
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_accum(AccumArgs<F> a) {
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.B) return;
+    const MsmTask t = a.tasks[blockIdx.y];
+    const u32* __restrict__ rows = a.row[t.group];
+    const Affine<F>* __restrict__ table = a.table[t.group];
+    const Fr* __restrict__ src = a.src[a.which[t.group]];
+    const u32 half = 1u << (a.c - 1);
+    XYZZ<F> acc = XYZZ<F>::infinity();
+    for (u32 b = t.lo; b < t.hi; b++) {
+        u32 s[8];
+        ld_fp(src + (size_t)rows[b] * a.B + j).to_canonical(s);
+        u32 any = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) any |= s[i];
+        if (!any) continue;
+        const Affine<F>* tb = table + (size_t)b * a.K * half;
+        u32 carry = 0;
+        // software pipeline: fetch the table entry of window k+1 while adding that of window k
+        int d = window_digit(s, 0, a.c, carry);
+        Affine<F> nxt;
+        bool nxt_valid = d != 0;
+        if (nxt_valid) {
+            nxt = ld_point<F>(tb + ((d < 0 ? -d : d) - 1));
+            if (d < 0) nxt.y = nxt.y.neg();
+        }
+        for (int k = 0; k < a.K; k++) {
+            Affine<F> cur = nxt;
+            const bool cur_valid = nxt_valid;
+            nxt_valid = false;
+            if (k + 1 < a.K) {
+                d = window_digit(s, k + 1, a.c, carry);
+                nxt_valid = d != 0;
+                if (nxt_valid) {
+                    nxt = ld_point<F>(tb + (size_t)(k + 1) * half + ((d < 0 ? -d : d) - 1));
+                    if (d < 0) nxt.y = nxt.y.neg();
+                }
+            }
+            if (cur_valid) acc.add_affine(cur);
+        }
+    }
+    a.part[(size_t)blockIdx.y * a.B + j] = acc;
+}
+
+// sum[group][j] = Σ_{tasks of group} part[task][j]
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_reduce(const XYZZ<F>* __restrict__ part, const MsmTask* __restrict__ tasks, u32 n_tasks,
+                                                    u32 B, XYZZ<F>* __restrict__ sum) {
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 g = blockIdx.y;
+    if (j >= B) return;
+    XYZZ<F> acc = XYZZ<F>::infinity();
+    for (u32 t = 0; t < n_tasks; t++)
+        if (tasks[t].group == g) acc.add(part[(size_t)t * B + j]);
+    sum[(size_t)g * B + j] = acc;
+}
+
+// ------------------------------------------------------------------------------------------- assembly
+__device__ __forceinline__ void load_scalar_bytes(const uint8_t* p, u32* out) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w;
+    out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+    u32 m[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) m[i] = FrCfg::p(i);
+    while (Fr::raw_cmp(out, m) >= 0) Fr::raw_sub(out, out, m);
+}
+__device__ __forceinline__ bool fq_is_larger_half(const u32* y) {  // y > q − y  (y canonical, non-zero)
+    u32 q[8], n[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) q[i] = FqCfg::p(i);
+    Fq::raw_sub(n, q, y);
+    return Fq::raw_cmp(y, n) > 0;
+}
+__device__ __forceinline__ void store_words(uint8_t* p, const u32* w) {
+    u32* o = reinterpret_cast<u32*>(p);
+#pragma unroll
+    for (int i = 0; i < 8; i++) o[i] = w[i];
+}
+// ark-serialize 0.5 compressed short-Weierstrass point: x little-endian, bit 7 of the last byte =
+// "y is the larger of {y, −y}", bit 6 = infinity.
+__device__ void compress_g1(const G1Affine& p, uint8_t* out, uint8_t* affine_out) {
+    u32 x[8] = {0, 0, 0, 0, 0, 0, 0, 0}, y[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool inf = p.is_inf();
+    if (!inf) {
+        p.x.to_canonical(x);
+        p.y.to_canonical(y);
+    }
+    if (affine_out) {
+        store_words(affine_out, x);
+        store_words(affine_out + 32, y);
+        if (inf) affine_out[63] = 0x40;
+    }
+    if (inf) x[7] |= 0x40000000u;
+    else if (fq_is_larger_half(y)) x[7] |= 0x80000000u;
+    store_words(out, x);
+}
+__device__ void compress_g2(const G2Affine& p, uint8_t* out, uint8_t* affine_out) {
+    u32 x0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, x1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, y0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, y1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool inf = p.is_inf();
+    if (!inf) {
+        p.x.a.to_canonical(x0);
+        p.x.b.to_canonical(x1);
+        p.y.a.to_canonical(y0);
+        p.y.b.to_canonical(y1);
+    }
+    if (affine_out) {
+        store_words(affine_out, x0);
+        store_words(affine_out + 32, x1);
+        store_words(affine_out + 64, y0);
+        store_words(affine_out + 96, y1);
+        if (inf) affine_out[127] = 0x40;
+    }
+    if (inf) x1[7] |= 0x40000000u;
+    else {
+        // Fq2 ordering: compare c1 first, then c0 (y vs −y)
+        bool larger;
+        bool c1zero = true;
+        for (int i = 0; i < 8; i++) c1zero = c1zero && y1[i] == 0;
+        if (!c1zero) larger = fq_is_larger_half(y1);
+        else larger = fq_is_larger_half(y0);
+        if (larger) x1[7] |= 0x80000000u;
+    }
+    store_words(out, x0);
+    store_words(out + 32, x1);
+}
+
+__global__ void __launch_bounds__(64) k_assemble_g1(ProverKeyDev pk, const G1XYZZ* __restrict__ sum, u32 B, const uint8_t* __restrict__ rs,
+                                                    uint8_t* __restrict__ proofs, uint8_t* __restrict__ affine) {
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= B) return;
+    u32 r[8], s[8], rsv[8];
+    load_scalar_bytes(rs + 64 * (size_t)j, r);
+    load_scalar_bytes(rs + 64 * (size_t)j + 32, s);
+    (Fr::from_canonical(r) * Fr::from_canonical(s)).to_canonical(rsv);
+    u32 rnz = 0;
+    for (int i = 0; i < 8; i++) rnz |= r[i];
+    const G1XYZZ delta = G1XYZZ::from_affine(pk.delta_g1);
+    // g_a
+    G1XYZZ g_a = sum[0 * (size_t)B + j];
+    g_a.add_affine(pk.alpha_g1);
+    g_a.add(delta.mul(r));
+    // g_c = s·g_a + r·g1_b − rs·δ₁ + L + H
+    G1XYZZ g_c = g_a.mul(s);
+    if (rnz) {
+        G1XYZZ g1_b = sum[1 * (size_t)B + j];
+        g1_b.add_affine(pk.beta_g1);
+        g1_b.add(delta.mul(s));
+        g_c.add(g1_b.mul(r));
+    }
+    g_c.add(delta.mul(rsv).neg());
+    g_c.add(sum[2 * (size_t)B + j]);
+    g_c.add(sum[3 * (size_t)B + j]);
+    uint8_t* o = proofs + 128 * (size_t)j;
+    uint8_t* af = affine ? affine + 256 * (size_t)j : nullptr;
+    compress_g1(g_a.to_affine(), o, af);
+    compress_g1(g_c.to_affine(), o + 96, af ? af + 192 : nullptr);
+}
+__global__ void __launch_bounds__(64) k_assemble_g2(ProverKeyDev pk, const G2XYZZ* __restrict__ sum, u32 B, const uint8_t* __restrict__ rs,
+                                                    uint8_t* __restrict__ proofs, uint8_t* __restrict__ affine) {
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= B) return;
+    u32 s[8];
+    load_scalar_bytes(rs + 64 * (size_t)j + 32, s);
+    G2XYZZ g2_b = sum[j];
+    g2_b.add_affine(pk.beta_g2);
+    g2_b.add(G2XYZZ::from_affine(pk.delta_g2).mul(s));
+    compress_g2(g2_b.to_affine(), proofs + 128 * (size_t)j + 32, affine ? affine + 256 * (size_t)j + 64 : nullptr);
+}
+
+// ------------------------------------------------------------------------------------------- host orchestration
+static u32 pick_chunk(u32 total_bases, u32 B) {
+    // aim at roughly 300 K threads in flight (148 SMs × 2048 resident threads)
+    u64 want = ((u64)total_bases * B + 299999) / 300000;
+    if (want < 4) want = 4;
+    if (want > 256) want = 256;
+    return (u32)want;
+}
+std::vector<MsmTask> msm_make_tasks(const FixedMsmPlan& plan, u32 B, bool g2) {
+    const MsmGroupDev* g = g2 ? &plan.g2 : plan.g1;
+    const int n_groups = g2 ? 1 : 4;
+    u32 total = 0;
+    for (int i = 0; i < n_groups; i++) total += g[i].n_bases;
+    const u32 chunk = pick_chunk(total, B);
+    std::vector<MsmTask> tasks;
+    for (int i = 0; i < n_groups; i++)
+        for (u32 lo = 0; lo < g[i].n_bases; lo += chunk) tasks.push_back({(u32)i, lo, lo + chunk < g[i].n_bases ? lo + chunk : g[i].n_bases, 0});
+    return tasks;
+}
+
+void launch_msm_and_assemble(const FixedMsmPlan& plan, const ProverKeyDev& pk, const Fr* d_vals, const Fr* d_h, u32 B,
+                             const uint8_t* d_rs, MsmWorkspace& ws, uint8_t* d_proofs_out, uint8_t* d_proofs_affine, cudaStream_t s) {
+    const u32 bx = B >= 128 ? 128 : 32;
+    {   // G1: A, B1, L, H
+        AccumArgs<Fq> a;
+        a.src[0] = d_vals; a.src[1] = d_h;
+        for (int i = 0; i < 4; i++) { a.row[i] = plan.g1[i].row; a.table[i] = (const G1Affine*)plan.g1[i].table; a.which[i] = plan.g1[i].which_src; }
+        a.tasks = ws.tasks_g1; a.part = ws.part_g1; a.B = B; a.c = plan.c; a.K = plan.K;
+        dim3 grid((B + bx - 1) / bx, ws.n_tasks_g1);
+        k_msm_accum<Fq><<<grid, bx, 0, s>>>(a);
+        k_msm_reduce<Fq><<<dim3((B + bx - 1) / bx, 4), bx, 0, s>>>(ws.part_g1, ws.tasks_g1, ws.n_tasks_g1, B, ws.sum_g1);
+    }
+    {   // G2: B2
+        AccumArgs<Fq2> a;
+        a.src[0] = d_vals; a.src[1] = d_h;
+        for (int i = 0; i < 4; i++) { a.row[i] = plan.g2.row; a.table[i] = (const G2Affine*)plan.g2.table; a.which[i] = plan.g2.which_src; }
+        a.tasks = ws.tasks_g2; a.part = ws.part_g2; a.B = B; a.c = plan.c; a.K = plan.K;
+        dim3 grid((B + bx - 1) / bx, ws.n_tasks_g2);
+        k_msm_accum<Fq2><<<grid, bx, 0, s>>>(a);
+        k_msm_reduce<Fq2><<<dim3((B + bx - 1) / bx, 1), bx, 0, s>>>(ws.part_g2, ws.tasks_g2, ws.n_tasks_g2, B, ws.sum_g2);
+    }
+    k_assemble_g1<<<(B + 63) / 64, 64, 0, s>>>(pk, ws.sum_g1, B, d_rs, d_proofs_out, d_proofs_affine);
+    k_assemble_g2<<<(B + 63) / 64, 64, 0, s>>>(pk, ws.sum_g2, B, d_rs, d_proofs_out, d_proofs_affine);
+}
+
+}  // namespace zk

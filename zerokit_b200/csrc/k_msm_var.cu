@@ -1,0 +1,271 @@
+// Variable-base BN254 G1 multi-scalar multiplication (Pippenger bucket method) for sm_100a.
+//
+// Path covered: `msm<G>` in rln/src/partial_proof.rs:98-104 → ark-ec 0.5.0
+// VariableBaseMSM::msm_bigint (Cargo.lock:106).  Same mathematical object (Σ sᵢ·Pᵢ), so the affine
+// result is bit-identical; the schedule is GPU-shaped:
+//   1. signed radix-2^c digits per scalar                         (k_digits, 32 B read / scalar)
+//   2. sort (window,bucket) keys with their point indices          (cub radix sort, library)
+//   3. one thread per bucket: sum its points with XYZZ mixed adds  (k_bucket_sum: the hot kernel —
+//      128-bit loads of the 64-byte affine bases, ≈ 10 modular products per 64 bytes)
+//   4. per window: Σ (b+1)·B_b by segment running sums, warp-shuffle tree over the segments
+//   5. Horner over the windows, affine normalisation.
+// Algorithmic HBM bytes: 96 per term (32 B scalar + 64 B base).  The kernel is bound by the integer
+// multiply pipe (≈ 250 IMAD per byte), see DESIGN.md §roofline.
+#include <cub/cub.cuh>
+
+#include "device_api.hpp"
+
+namespace zk {
+
+struct VarMsmWorkspace {
+    size_t max_n = 0;
+    u32 *keys_in = nullptr, *keys_out = nullptr, *vals_in = nullptr, *vals_out = nullptr;
+    u32 *bucket_start = nullptr, *bucket_end = nullptr;
+    G1XYZZ* buckets = nullptr;
+    G1XYZZ* seg = nullptr;
+    G1XYZZ* win = nullptr;
+    void* cub_tmp = nullptr;
+    size_t cub_tmp_bytes = 0;
+    size_t max_buckets = 0;
+};
+
+static void msm_params(size_t n, int& c, int& K) {
+    int lg = 0;
+    while (((size_t)1 << lg) < n) lg++;
+    c = lg - 6;
+    if (c < 8) c = 8;
+    if (c > 16) c = 16;
+    K = (255 + c - 1) / c;  // K·c ≥ 255 keeps the top signed digit + carry below 2^(c−1)
+}
+static const int SEGS = 256;  // segments per window in the bucket reduction
+
+VarMsmWorkspace* var_msm_workspace_create(size_t max_n) {
+    VarMsmWorkspace* w = new VarMsmWorkspace();
+    w->max_n = max_n;
+    int c, K;
+    size_t max_items = 0, max_b = 0;
+    for (size_t n = 1; n <= max_n; n <<= 1) {
+        msm_params(n, c, K);
+        if (n * K > max_items) max_items = n * K;
+        size_t b = (size_t)K << (c - 1);
+        if (b > max_b) max_b = b;
+    }
+    msm_params(max_n, c, K);
+    if (max_n * K > max_items) max_items = max_n * K;
+    if (((size_t)K << (c - 1)) > max_b) max_b = (size_t)K << (c - 1);
+    w->max_buckets = max_b;
+    ZK_CUDA_CHECK(cudaMalloc(&w->keys_in, 4 * max_items));
+    ZK_CUDA_CHECK(cudaMalloc(&w->keys_out, 4 * max_items));
+    ZK_CUDA_CHECK(cudaMalloc(&w->vals_in, 4 * max_items));
+    ZK_CUDA_CHECK(cudaMalloc(&w->vals_out, 4 * max_items));
+    ZK_CUDA_CHECK(cudaMalloc(&w->bucket_start, 4 * (max_b + 1)));
+    ZK_CUDA_CHECK(cudaMalloc(&w->bucket_end, 4 * (max_b + 1)));
+    ZK_CUDA_CHECK(cudaMalloc(&w->buckets, sizeof(G1XYZZ) * max_b));
+    ZK_CUDA_CHECK(cudaMalloc(&w->seg, sizeof(G1XYZZ) * 32 * SEGS));
+    ZK_CUDA_CHECK(cudaMalloc(&w->win, sizeof(G1XYZZ) * 32));
+    cub::DeviceRadixSort::SortPairs(nullptr, w->cub_tmp_bytes, w->keys_in, w->keys_out, w->vals_in, w->vals_out, (int64_t)max_items, 0, 32);
+    ZK_CUDA_CHECK(cudaMalloc(&w->cub_tmp, w->cub_tmp_bytes));
+    return w;
+}
+void var_msm_workspace_destroy(VarMsmWorkspace* w) {
+    if (!w) return;
+    cudaFree(w->keys_in); cudaFree(w->keys_out); cudaFree(w->vals_in); cudaFree(w->vals_out);
+    cudaFree(w->bucket_start); cudaFree(w->bucket_end); cudaFree(w->buckets); cudaFree(w->seg); cudaFree(w->win); cudaFree(w->cub_tmp);
+    delete w;
+}
+
+// keys[k·n + i] = k·2^{c−1} + |d|−1 (or 0xffffffff when the digit is zero); vals = i | sign << 31
+__global__ void __launch_bounds__(256) k_digits(const uint8_t* __restrict__ scalars, size_t n, int c, int K, u32* __restrict__ keys,
+                                                u32* __restrict__ vals) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4* q = reinterpret_cast<const uint4*>(scalars + 32 * i);
+    uint4 a = q[0], b = q[1];
+    u32 s[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    u32 m[8];
+#pragma unroll
+    for (int t = 0; t < 8; t++) m[t] = FrCfg::p(t);
+    while (Fr::raw_cmp(s, m) >= 0) Fr::raw_sub(s, s, m);  // ark reduces through Fr::into_bigint
+    u32 carry = 0;
+    const u32 half = 1u << (c - 1);
+    for (int k = 0; k < K; k++) {
+        const int bit = k * c, w = bit >> 5, sh = bit & 31;
+        u32 v = 0;
+        if (w < 8) {
+            v = s[w] >> sh;
+            if (sh + c > 32 && w + 1 < 8) v |= s[w + 1] << (32 - sh);
+        }
+        int d = (int)(v & ((1u << c) - 1)) + (int)carry;
+        if (d > (int)half) { d -= (1 << c); carry = 1; } else carry = 0;
+        u32 key = 0xffffffffu, val = (u32)i;
+        if (d > 0) key = (u32)k * half + (u32)(d - 1);
+        else if (d < 0) { key = (u32)k * half + (u32)(-d - 1); val |= 0x80000000u; }
+        keys[(size_t)k * n + i] = key;
+        vals[(size_t)k * n + i] = val;
+    }
+}
+
+__global__ void k_bucket_bounds(const u32* __restrict__ keys, size_t items, u32* __restrict__ start, u32* __restrict__ end) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= items) return;
+    const u32 k = keys[i];
+    if (k == 0xffffffffu) return;
+    if (i == 0 || keys[i - 1] != k) start[k] = (u32)i;
+    if (i + 1 == items || keys[i + 1] != k) end[k] = (u32)i + 1;
+}
+
+// the hot kernel: bucket b = Σ ± bases[vals[t]] for t in [start[b], end[b])
+__global__ void __launch_bounds__(128) k_bucket_sum(const G1Affine* __restrict__ bases, const u32* __restrict__ vals,
+                                                    const u32* __restrict__ start, const u32* __restrict__ end, size_t n_buckets,
+                                                    G1XYZZ* __restrict__ buckets) {
+    size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (b >= n_buckets) return;
+    const u32 lo = start[b], hi = end[b];
+    G1XYZZ acc = G1XYZZ::infinity();
+    if (lo < hi) {
+        u32 v = vals[lo];
+        G1Affine nxt = {ldg_fp(&bases[v & 0x7fffffffu].x), ldg_fp(&bases[v & 0x7fffffffu].y)};
+        if (v >> 31) nxt.y = nxt.y.neg();
+        for (u32 t = lo; t < hi; t++) {
+            G1Affine cur = nxt;
+            if (t + 1 < hi) {  // prefetch the next point while the current addition runs
+                v = vals[t + 1];
+                nxt = {ldg_fp(&bases[v & 0x7fffffffu].x), ldg_fp(&bases[v & 0x7fffffffu].y)};
+                if (v >> 31) nxt.y = nxt.y.neg();
+            }
+            if (!cur.is_inf()) acc.add_affine(cur);
+        }
+    }
+    buckets[b] = acc;
+}
+
+// segment s of window k covers buckets [s·L, (s+1)·L): W = Σ (b+1)·B_b over the segment
+__global__ void __launch_bounds__(64) k_segment_reduce(const G1XYZZ* __restrict__ buckets, u32 half, u32 seg_len, G1XYZZ* __restrict__ seg) {
+    const u32 k = blockIdx.y;
+    const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 n_seg = half / seg_len;
+    if (s >= n_seg) return;
+    const G1XYZZ* B = buckets + (size_t)k * half + (size_t)s * seg_len;
+    G1XYZZ run = G1XYZZ::infinity(), acc = G1XYZZ::infinity();
+    for (int b = (int)seg_len - 1; b >= 0; b--) {
+        run.add(B[b]);
+        acc.add(run);  // after the loop: acc = Σ (b+1)·B_b (local index), run = Σ B_b
+    }
+    // shift the local weights by s·seg_len
+    u32 off[8] = {s * seg_len, 0, 0, 0, 0, 0, 0, 0};
+    if (off[0]) acc.add(run.mul(off));
+    seg[(size_t)k * n_seg + s] = acc;
+}
+
+__device__ __forceinline__ G1XYZZ shfl_xor_point(const G1XYZZ& p, int mask) {
+    G1XYZZ r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        r.X.l[i] = __shfl_xor_sync(0xffffffffu, p.X.l[i], mask);
+        r.Y.l[i] = __shfl_xor_sync(0xffffffffu, p.Y.l[i], mask);
+        r.ZZ.l[i] = __shfl_xor_sync(0xffffffffu, p.ZZ.l[i], mask);
+        r.ZZZ.l[i] = __shfl_xor_sync(0xffffffffu, p.ZZZ.l[i], mask);
+    }
+    return r;
+}
+// one block per window: warp-shuffle tree over the segment sums, then across warps through shared memory
+__global__ void __launch_bounds__(256) k_window_reduce(const G1XYZZ* __restrict__ seg, u32 n_seg, G1XYZZ* __restrict__ win) {
+    __shared__ G1XYZZ sh[8];
+    const u32 k = blockIdx.x;
+    G1XYZZ acc = G1XYZZ::infinity();
+    for (u32 s = threadIdx.x; s < n_seg; s += blockDim.x) acc.add(seg[(size_t)k * n_seg + s]);
+    for (int m = 16; m >= 1; m >>= 1) {
+        G1XYZZ o = shfl_xor_point(acc, m);
+        acc.add(o);
+    }
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        G1XYZZ t = sh[0];
+        for (u32 w = 1; w < blockDim.x / 32; w++) t.add(sh[w]);
+        win[k] = t;
+    }
+}
+
+__global__ void k_horner(const G1XYZZ* __restrict__ win, int c, int K, uint8_t* __restrict__ out) {
+    G1XYZZ t = win[K - 1];
+    for (int k = K - 2; k >= 0; k--) {
+        for (int i = 0; i < c; i++) t = t.dbl();
+        t.add(win[k]);
+    }
+    G1Affine a = t.to_affine();
+    u32 x[8] = {0, 0, 0, 0, 0, 0, 0, 0}, y[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (!a.is_inf()) { a.x.to_canonical(x); a.y.to_canonical(y); }
+    for (int i = 0; i < 8; i++) { reinterpret_cast<u32*>(out)[i] = x[i]; reinterpret_cast<u32*>(out)[8 + i] = y[i]; }
+}
+
+void launch_var_msm_g1(VarMsmWorkspace* w, const G1Affine* d_bases, const uint8_t* d_scalars, size_t n, uint8_t* d_result, cudaStream_t s) {
+    if (n == 0) { ZK_CUDA_CHECK(cudaMemsetAsync(d_result, 0, 64, s)); return; }
+    if (n > w->max_n) throw CudaError(cudaErrorInvalidValue, "var msm: n exceeds workspace", __FILE__, __LINE__);
+    int c, K;
+    msm_params(n, c, K);
+    const u32 half = 1u << (c - 1);
+    const size_t items = n * (size_t)K, n_buckets = (size_t)K * half;
+    k_digits<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_scalars, n, c, K, w->keys_in, w->vals_in);
+    int key_bits = 0;
+    while (((size_t)1 << key_bits) < n_buckets) key_bits++;
+    // zero digits carry key 0xffffffff: sort on all 32 bits so they land behind every bucket
+    size_t tmp = w->cub_tmp_bytes;
+    cub::DeviceRadixSort::SortPairs(w->cub_tmp, tmp, w->keys_in, w->keys_out, w->vals_in, w->vals_out, (int64_t)items, 0, 32, s);
+    ZK_CUDA_CHECK(cudaMemsetAsync(w->bucket_start, 0, 4 * n_buckets, s));
+    ZK_CUDA_CHECK(cudaMemsetAsync(w->bucket_end, 0, 4 * n_buckets, s));
+    k_bucket_bounds<<<(unsigned)((items + 255) / 256), 256, 0, s>>>(w->keys_out, items, w->bucket_start, w->bucket_end);
+    k_bucket_sum<<<(unsigned)((n_buckets + 127) / 128), 128, 0, s>>>(d_bases, w->vals_out, w->bucket_start, w->bucket_end, n_buckets, w->buckets);
+    const u32 n_seg = half < (u32)SEGS ? half : (u32)SEGS;
+    const u32 seg_len = half / n_seg;
+    k_segment_reduce<<<dim3((n_seg + 63) / 64, K), 64, 0, s>>>(w->buckets, half, seg_len, w->seg);
+    k_window_reduce<<<K, 256, 0, s>>>(w->seg, n_seg, w->win);
+    k_horner<<<1, 1, 0, s>>>(w->win, c, K, d_result);
+}
+
+// ------------------------------------------------------------------------------------------- point I/O helpers
+__device__ __forceinline__ Fq fq_from_bytes(const uint8_t* p, bool mask_flags) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    u32 c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (mask_flags) c[7] &= 0x3fffffffu;
+    return Fq::from_canonical(c);
+}
+__global__ void k_g1_from_bytes(const uint8_t* __restrict__ in, G1Affine* __restrict__ out, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* p = in + 64 * i;
+    G1Affine a = G1Affine::infinity();
+    if (!(p[63] & 0x40)) a = {fq_from_bytes(p, false), fq_from_bytes(p + 32, true)};
+    st_fp(&out[i].x, a.x);
+    st_fp(&out[i].y, a.y);
+}
+__global__ void k_g2_from_bytes(const uint8_t* __restrict__ in, G2Affine* __restrict__ out, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* p = in + 128 * i;
+    G2Affine a = G2Affine::infinity();
+    if (!(p[127] & 0x40)) a = {{fq_from_bytes(p, false), fq_from_bytes(p + 32, false)}, {fq_from_bytes(p + 64, false), fq_from_bytes(p + 96, true)}};
+    st_fp(&out[i].x.a, a.x.a); st_fp(&out[i].x.b, a.x.b);
+    st_fp(&out[i].y.a, a.y.a); st_fp(&out[i].y.b, a.y.b);
+}
+void launch_g1_from_bytes(const uint8_t* d_in, G1Affine* d_out, size_t n, cudaStream_t s) {
+    if (n) k_g1_from_bytes<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_in, d_out, n);
+}
+void launch_g2_from_bytes(const uint8_t* d_in, G2Affine* d_out, size_t n, cudaStream_t s) {
+    if (n) k_g2_from_bytes<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_in, d_out, n);
+}
+
+__global__ void __launch_bounds__(64) k_g1_mul_gen(const uint8_t* __restrict__ scalars, G1Affine* __restrict__ out, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 k[8];
+    for (int t = 0; t < 8; t++) k[t] = reinterpret_cast<const u32*>(scalars + 32 * i)[t];
+    G1Affine g = {Fq::from_u32(1), Fq::from_u32(2)};
+    out[i] = G1XYZZ::from_affine(g).mul(k).to_affine();
+}
+void launch_g1_mul_gen(const uint8_t* d_scalars, G1Affine* d_out, size_t n, cudaStream_t s) {
+    if (n) k_g1_mul_gen<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(d_scalars, d_out, n);
+}
+
+}  // namespace zk

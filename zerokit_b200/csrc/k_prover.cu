@@ -1,0 +1,182 @@
+// Batched witness generation and QAP witness-map kernels (sm_100a).
+//
+// Path covered:
+//   rln/src/circuit/iden3calc/graph.rs:246-272   graph::evaluate  (23 414 nodes → 5 844 wires per proof)
+//   rln/src/circuit/qap.rs:30-98                 CircomReduction::witness_map_from_matrices
+//
+// Data layout: every per-proof vector lives in a matrix [element][proof] (proof index fastest) so
+// that the B proofs of a batch are the coalescing dimension: a warp that processes 32 proofs reads
+// 32 consecutive 32-byte field elements (two 128-bit loads per lane).  The instruction stream of
+// the witness VM and the NTT twiddles are uniform across the warp.
+#include "device_api.hpp"
+
+namespace zk {
+
+__device__ __forceinline__ Fr load_canonical_fr(const uint8_t* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    u32 c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    u32 m[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) m[i] = FrCfg::p(i);
+    while (Fr::raw_cmp(c, m) >= 0) Fr::raw_sub(c, c, m);
+    return Fr::from_canonical(c);
+}
+
+// ------------------------------------------------------------------------------------------- witness VM
+// One proof per thread; the node program is read with uniform 128-bit loads.  vals[node][B].
+__global__ void __launch_bounds__(32) k_witness(CircuitDev c, const uint8_t* __restrict__ inputs, Fr* __restrict__ vals, u32 B,
+                                                u32* __restrict__ err) {
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= B) return;
+    const uint8_t* in = inputs + (size_t)j * c.n_slots * 32;
+    u32 bad = 0;
+    for (u32 i = 0; i < c.n_nodes; i++) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(c.prog + i));
+        const u32 kind = raw.x & 0xff, op = raw.x >> 8;
+        Fr v;
+        if (kind == VM_DUO) {
+            Fr a = ld_fp(vals + (size_t)raw.y * B + j);
+            Fr b = ld_fp(vals + (size_t)raw.z * B + j);
+            if (op == OP_MUL) v = a * b;
+            else if (op == OP_ADD) v = a + b;
+            else if (op == OP_SUB) v = a - b;
+            else if (!vm_eval_duo(op, a, b, v)) { bad = 1; v = Fr::zero(); }
+        } else if (kind == VM_CONST) {
+            v = ldg_fp(c.consts + raw.y);
+        } else if (kind == VM_INPUT) {
+            v = load_canonical_fr(in + 32 * raw.y);
+        } else if (kind == VM_UNO) {
+            if (op == 0) v = ld_fp(vals + (size_t)raw.y * B + j).neg();
+            else { bad = 1; v = Fr::zero(); }  // "uno operator Id not implemented" (graph.rs:189-193)
+        } else {  // TernCond (graph.rs:216-222)
+            Fr a = ld_fp(vals + (size_t)raw.y * B + j);
+            v = a.is_zero() ? ld_fp(vals + (size_t)raw.w * B + j) : ld_fp(vals + (size_t)raw.z * B + j);
+        }
+        st_fp(vals + (size_t)i * B + j, v);
+    }
+    err[j] = bad;
+}
+void launch_witness(const CircuitDev& c, const uint8_t* d_inputs, Fr* d_vals, u32 B, u32* d_err, cudaStream_t s) {
+    k_witness<<<(B + 31) / 32, 32, 0, s>>>(c, d_inputs, d_vals, B, d_err);
+}
+
+// ------------------------------------------------------------------------------------------- A·w, B·w, c = a∘b
+// grid: (ceil(B/128), domain).  Row i < n_constraints: sparse dot products (qap.rs:45-52);
+// rows n_constraints .. +n_instance of a copy the public wires (qap.rs:54-58); everything else is zero.
+__global__ void __launch_bounds__(128) k_matvec(CircuitDev c, const Fr* __restrict__ vals, Fr* __restrict__ a, Fr* __restrict__ b,
+                                                Fr* __restrict__ cc, u32 B) {
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 row = blockIdx.y;
+    if (j >= B) return;
+    Fr sa = Fr::zero(), sb = Fr::zero(), sc = Fr::zero();
+    if (row < c.n_constraints) {
+        for (u32 k = c.a_ptr[row]; k < c.a_ptr[row + 1]; k++) {
+            Fr w = ld_fp(vals + (size_t)c.signals[c.a_col[k]] * B + j);
+            sa += ldg_fp(c.a_val + k) * w;
+        }
+        for (u32 k = c.b_ptr[row]; k < c.b_ptr[row + 1]; k++) {
+            Fr w = ld_fp(vals + (size_t)c.signals[c.b_col[k]] * B + j);
+            sb += ldg_fp(c.b_val + k) * w;
+        }
+        sc = sa * sb;
+    } else if (row < c.n_constraints + c.n_instance) {
+        sa = ld_fp(vals + (size_t)c.signals[row - c.n_constraints] * B + j);
+    }
+    const size_t o = (size_t)row * B + j;
+    st_fp(a + o, sa);
+    st_fp(b + o, sb);
+    st_fp(cc + o, sc);
+}
+
+// ------------------------------------------------------------------------------------------- batched radix-2 NTT
+// Decimation-in-frequency stage (natural order in → bit-reversed out after all stages):
+//   u = x[k+j], v = x[k+j+half];  x[k+j] = u+v;  x[k+j+half] = (u−v)·tw[j·stride]
+// grid: (ceil(B/128), n/2).  The twiddle is uniform per block.
+__global__ void __launch_bounds__(128) k_ntt_dif_stage(Fr* __restrict__ x, u32 B, u32 half, u32 stride, const Fr* __restrict__ tw) {
+    const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    const u32 t = blockIdx.y;
+    const u32 j = t & (half - 1);
+    const u32 i0 = ((t - j) << 1) + j;
+    Fr* p0 = x + (size_t)i0 * B + p;
+    Fr* p1 = p0 + (size_t)half * B;
+    Fr u = ld_fp(p0), v = ld_fp(p1);
+    st_fp(p0, u + v);
+    Fr d = u - v;
+    if (j) d = d * ldg_fp(tw + (size_t)j * stride);
+    st_fp(p1, d);
+}
+// Decimation-in-time stage (bit-reversed in → natural out):
+//   u = x[k+j], v = x[k+j+half]·tw[j·stride];  x[k+j] = u+v;  x[k+j+half] = u−v
+__global__ void __launch_bounds__(128) k_ntt_dit_stage(Fr* __restrict__ x, u32 B, u32 half, u32 stride, const Fr* __restrict__ tw) {
+    const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    const u32 t = blockIdx.y;
+    const u32 j = t & (half - 1);
+    const u32 i0 = ((t - j) << 1) + j;
+    Fr* p0 = x + (size_t)i0 * B + p;
+    Fr* p1 = p0 + (size_t)half * B;
+    Fr u = ld_fp(p0), v = ld_fp(p1);
+    if (j) v = v * ldg_fp(tw + (size_t)j * stride);
+    st_fp(p0, u + v);
+    st_fp(p1, u - v);
+}
+// x[pos] *= factor[pos]   (coset shift g^{rev(pos)} and the 1/n of the inverse transform, fused)
+__global__ void __launch_bounds__(128) k_scale_rows(Fr* __restrict__ x, u32 B, const Fr* __restrict__ factor) {
+    const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    Fr* q = x + (size_t)blockIdx.y * B + p;
+    st_fp(q, ld_fp(q) * ldg_fp(factor + blockIdx.y));
+}
+// h = a·b − c  (qap.rs:84,93-95), written over a
+__global__ void __launch_bounds__(128) k_h_combine(Fr* __restrict__ a, const Fr* __restrict__ b, const Fr* __restrict__ c, u32 B) {
+    const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    const size_t o = (size_t)blockIdx.y * B + p;
+    st_fp(a + o, ld_fp(a + o) * ld_fp(b + o) - ld_fp(c + o));
+}
+
+static void ntt_dif(Fr* x, u32 log_n, u32 B, const Fr* tw, cudaStream_t s) {
+    const u32 n = 1u << log_n;
+    dim3 grid((B + 127) / 128, n / 2);
+    for (u32 half = n / 2, stride = 1; half >= 1; half >>= 1, stride <<= 1)
+        k_ntt_dif_stage<<<grid, 128, 0, s>>>(x, B, half, stride, tw);
+}
+static void ntt_dit(Fr* x, u32 log_n, u32 B, const Fr* tw, cudaStream_t s) {
+    const u32 n = 1u << log_n;
+    dim3 grid((B + 127) / 128, n / 2);
+    for (u32 half = 1, stride = n / 2; half < n; half <<= 1, stride >>= 1)
+        k_ntt_dit_stage<<<grid, 128, 0, s>>>(x, B, half, stride, tw);
+}
+
+void launch_qap(const CircuitDev& c, const Fr* d_vals, Fr* d_a, Fr* d_b, Fr* d_c, u32 B, cudaStream_t s) {
+    dim3 grid((B + 127) / 128, c.domain);
+    k_matvec<<<grid, 128, 0, s>>>(c, d_vals, d_a, d_b, d_c, B);
+    Fr* bufs[3] = {d_a, d_b, d_c};
+    for (Fr* x : bufs) {
+        ntt_dif(x, c.log_domain, B, c.tw_inv, s);            // ifft (unscaled), output bit-reversed
+        k_scale_rows<<<grid, 128, 0, s>>>(x, B, c.coset);    // · g^i / n   (qap.rs:72-79)
+        ntt_dit(x, c.log_domain, B, c.tw_fwd, s);            // fft on the coset, natural order
+    }
+    k_h_combine<<<grid, 128, 0, s>>>(d_a, d_b, d_c, B);
+}
+
+// test hook: natural-order forward / inverse transform of [n][B] (inverse leaves out the 1/n factor when tw = ω^{-k})
+__global__ void k_bitrev_rows(Fr* __restrict__ x, u32 B, u32 log_n) {
+    const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 i = blockIdx.y;
+    const u32 r = __brev(i) >> (32 - log_n);
+    if (p >= B || i >= r) return;
+    Fr a = ld_fp(x + (size_t)i * B + p), b = ld_fp(x + (size_t)r * B + p);
+    st_fp(x + (size_t)i * B + p, b);
+    st_fp(x + (size_t)r * B + p, a);
+}
+void launch_ntt_test(Fr* d_data, u32 log_n, u32 B, bool inverse, const Fr* tw, cudaStream_t s) {
+    (void)inverse;
+    ntt_dif(d_data, log_n, B, tw, s);
+    dim3 grid((B + 127) / 128, 1u << log_n);
+    k_bitrev_rows<<<grid, 128, 0, s>>>(d_data, B, log_n);
+}
+
+}  // namespace zk

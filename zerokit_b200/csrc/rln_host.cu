@@ -1,0 +1,1384 @@
+// Host side of librln_b200.so: the `Rln` object (mirror of rln::public::RLN, rln/src/public.rs:65-771)
+// that owns the circuit, the HBM-resident Merkle tree and the proving workspace, and the C ABI
+// declared in include/rln_b200.h.  The host only parses files, moves bytes and launches kernels;
+// every field / curve operation of the hot path runs on the GPU (there is no CPU fallback — a missing
+// device is an error).
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <memory>
+#include <mutex>
+#include <random>
+#include <sstream>
+
+#include "../../include/rln_b200.h"
+#include "device_api.hpp"
+#include "host_util.hpp"
+#include "pairing_constants.hpp"
+#include "poseidon_constants.hpp"
+
+namespace zk {
+
+std::atomic<uint64_t> g_launch_count{0};
+
+// ------------------------------------------------------------------------------------------- small RAII helpers
+struct DevMem {
+    void* p = nullptr;
+    size_t bytes = 0;
+    DevMem() {}
+    DevMem(const DevMem&) = delete;
+    DevMem& operator=(const DevMem&) = delete;
+    ~DevMem() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    void alloc(size_t n) {
+        release();
+        if (n == 0) n = 16;
+        ZK_CUDA_CHECK(cudaMalloc(&p, n));
+        bytes = n;
+    }
+    void ensure(size_t n) {
+        if (n > bytes) alloc(n);
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+    void upload(const void* src, size_t n) {
+        alloc(n);
+        if (n) ZK_CUDA_CHECK(cudaMemcpy(p, src, n, cudaMemcpyHostToDevice));
+    }
+};
+
+struct RlnError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+static std::once_flag g_init_flag;
+static std::string g_init_error;
+static void global_init() {
+    std::call_once(g_init_flag, [] {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0) {
+            g_init_error = std::string("no usable CUDA device (librln_b200 has no CPU path): ") + cudaGetErrorString(e);
+            return;
+        }
+        try {
+            auto pt = std::make_unique<PoseidonTables>();
+            poseidon_fill_tables(*pt);
+            poseidon_upload_tables(*pt);
+            PairingTables pr;
+            pairing_tables_init(pr);
+            pairing_upload_tables(pr);
+        } catch (const CudaError& ce) {
+            g_init_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(ce.code);
+        }
+    });
+    if (!g_init_error.empty()) throw RlnError(g_init_error);
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+static void random_fr(uint8_t out[32]) {
+    static thread_local std::random_device rd;
+    for (;;) {
+        for (int i = 0; i < 8; i++) {
+            uint32_t w = rd();
+            memcpy(out + 4 * i, &w, 4);
+        }
+        out[31] &= 0x3f;
+        if (fr_is_canonical(out)) return;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- witness record
+struct Witness {  // RLNWitnessInput, single message-id (rln/src/protocol/witness.rs:52-60)
+    uint8_t secret[32], limit[32], message_id[32], x[32], ext_null[32];
+    std::vector<uint8_t> path;   // depth × 32
+    std::vector<uint8_t> index;  // depth
+};
+struct ProofValues {  // RLNProofValues single (rln/src/protocol/proof.rs:100-190)
+    uint8_t root[32], ext_null[32], x[32], y[32], nullifier[32];
+};
+struct RlnProof {
+    uint8_t proof[128];  // ark-compressed A|B|C
+    ProofValues pv;
+};
+
+// rln_witness_to_bytes_le (witness.rs:369-415)
+static std::vector<uint8_t> witness_to_bytes(const Witness& w) {
+    std::vector<uint8_t> b;
+    b.push_back(0);
+    b.insert(b.end(), w.secret, w.secret + 32);
+    b.insert(b.end(), w.limit, w.limit + 32);
+    b.insert(b.end(), w.message_id, w.message_id + 32);
+    uint64_t n = w.path.size() / 32;
+    b.insert(b.end(), (uint8_t*)&n, (uint8_t*)&n + 8);
+    b.insert(b.end(), w.path.begin(), w.path.end());
+    n = w.index.size();
+    b.insert(b.end(), (uint8_t*)&n, (uint8_t*)&n + 8);
+    b.insert(b.end(), w.index.begin(), w.index.end());
+    b.insert(b.end(), w.x, w.x + 32);
+    b.insert(b.end(), w.ext_null, w.ext_null + 32);
+    return b;
+}
+static std::string msg_read_len(size_t expected, size_t got) {
+    std::ostringstream s;
+    s << "Expected to read " << expected << " bytes but read " << got << " bytes";
+    return s.str();
+}
+static void validate_witness(const Witness& w) {  // RLNWitnessInput::new_single (witness.rs:78-113)
+    if (is_zero32(w.limit)) throw RlnError("User message limit cannot be zero");
+    if (w.path.size() / 32 != w.index.size()) {
+        std::ostringstream s;
+        s << "Merkle proof length mismatch: expected " << w.path.size() / 32 << ", got " << w.index.size();
+        throw RlnError(s.str());
+    }
+    if (cmp_le32(w.message_id, w.limit) >= 0)
+        throw RlnError("Message id (" + decimal_le32(w.message_id) + ") is not within user_message_limit (" + decimal_le32(w.limit) + ")");
+}
+// bytes_le_to_rln_witness (witness.rs:470-560): returns bytes consumed
+static size_t witness_from_bytes(const uint8_t* b, size_t len, Witness& w) {
+    size_t o = 0;
+    auto need = [&](size_t k) {
+        if (o + k > len) throw RlnError(msg_read_len(o + k, len));
+    };
+    need(1);
+    if (b[0] != 0) {
+        char t[64];
+        snprintf(t, sizeof t, "Unknown message mode version byte: %#04x", b[0]);
+        throw RlnError(t);
+    }
+    o = 1;
+    auto fr = [&](uint8_t* dst) {
+        need(32);
+        memcpy(dst, b + o, 32);
+        if (!fr_is_canonical(dst)) throw RlnError("Non-canonical field element: value is not in [0, r-1]");
+        o += 32;
+    };
+    fr(w.secret);
+    fr(w.limit);
+    fr(w.message_id);
+    need(8);
+    uint64_t n;
+    memcpy(&n, b + o, 8);
+    o += 8;
+    if (n > (len - o) / 32) throw RlnError(msg_read_len(o + n * 32, len));
+    w.path.assign(b + o, b + o + 32 * n);
+    for (uint64_t i = 0; i < n; i++)
+        if (!fr_is_canonical(w.path.data() + 32 * i)) throw RlnError("Non-canonical field element: value is not in [0, r-1]");
+    o += 32 * n;
+    need(8);
+    memcpy(&n, b + o, 8);
+    o += 8;
+    if (n > len - o) throw RlnError(msg_read_len(o + n, len));
+    w.index.assign(b + o, b + o + n);
+    o += n;
+    fr(w.x);
+    fr(w.ext_null);
+    validate_witness(w);
+    return o;
+}
+// rln_proof_values_to_bytes_le (proof.rs:192-236): version | root | external_nullifier | x | y | nullifier
+static void proof_values_to_bytes(const ProofValues& pv, uint8_t out[161]) {
+    out[0] = 0;
+    memcpy(out + 1, pv.root, 32);
+    memcpy(out + 33, pv.ext_null, 32);
+    memcpy(out + 65, pv.x, 32);
+    memcpy(out + 97, pv.y, 32);
+    memcpy(out + 129, pv.nullifier, 32);
+}
+static size_t proof_values_from_bytes(const uint8_t* b, size_t len, ProofValues& pv) {
+    if (len < 1) throw RlnError(msg_read_len(1, 0));
+    if (b[0] != 0) {
+        char t[64];
+        snprintf(t, sizeof t, "Unknown message mode version byte: %#04x", b[0]);
+        throw RlnError(t);
+    }
+    if (len < 161) throw RlnError(msg_read_len(161, len));
+    uint8_t* dst[5] = {pv.root, pv.ext_null, pv.x, pv.y, pv.nullifier};
+    for (int i = 0; i < 5; i++) {
+        memcpy(dst[i], b + 1 + 32 * i, 32);
+        if (!fr_is_canonical(dst[i])) throw RlnError("Non-canonical field element: value is not in [0, r-1]");
+    }
+    return 161;
+}
+// rln_proof_to_bytes_le (proof.rs:413-428): version | proof(128) | proof_values
+static void rln_proof_to_bytes(const RlnProof& p, uint8_t out[290]) {
+    out[0] = 0;
+    memcpy(out + 1, p.proof, 128);
+    proof_values_to_bytes(p.pv, out + 129);
+}
+
+// ------------------------------------------------------------------------------------------- the RLN object
+class Rln {
+   public:
+    Rln(size_t tree_depth, const uint8_t* zkey, size_t zlen, const uint8_t* graph, size_t glen);
+    ~Rln();
+
+    size_t depth() const { return depth_; }
+    size_t tree_depth() const { return tree_depth_; }
+    uint32_t n_slots() const { return gh_.n_slots; }
+    uint32_t n_wires() const { return (uint32_t)gh_.signals.size(); }
+    uint32_t domain() const { return domain_; }
+    const GraphHost& graph() const { return gh_; }
+
+    // tree (FullMerkleTree semantics: utils/src/merkle_tree/full_merkle_tree.rs)
+    void set_tree(size_t depth);
+    void set_range_host(size_t start, const uint8_t* leaves, size_t count);
+    void set_range_device(size_t start, const uint8_t* d_leaves, size_t count, cudaStream_t s);
+    void override_range(size_t start, const uint8_t* leaves, size_t n_leaves, std::vector<size_t> indices);
+    void set_leaf(size_t index, const uint8_t* leaf);
+    void delete_leaf(size_t index);
+    void set_next(const uint8_t* leaf);
+    void get_leaf(size_t index, uint8_t out[32]);
+    void root(uint8_t out[32]);
+    size_t leaves_set() const { return next_index_; }
+    size_t capacity() const { return (size_t)1 << tree_depth_; }
+    void merkle_proofs(const uint64_t* idx, size_t n, uint8_t* elems, uint8_t* bits);
+
+    // proving
+    void reserve(size_t B);
+    void prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, uint8_t* d_proofs, uint8_t* d_values, uint8_t* d_affine,
+                      cudaStream_t s);
+    void prove_host(const std::vector<Witness>& ws, const uint8_t* rs, std::vector<RlnProof>& out);
+    void witness_slots(const Witness& w, uint8_t* slots) const;
+    void debug_w_h(const Witness& w, uint8_t* w_out, uint8_t* h_out);
+    void verify_batch(const uint8_t* proofs128, const uint8_t* publics160_circuit_order, size_t n, uint8_t* ok);
+    float stage_ms[4] = {0, 0, 0, 0};
+    std::mutex mu;
+
+   private:
+    struct TaskSet {
+        DevMem g1, g2;
+        u32 n1 = 0, n2 = 0;
+    };
+    TaskSet& tasks_for(u32 B);
+    void build_circuit();
+    void build_tables();
+    void check_graph_shape();
+
+    ZkeyHost zk_;
+    GraphHost gh_;
+    size_t depth_ = 0;       // circuit tree depth (len of pathElements)
+    size_t tree_depth_ = 0;  // depth of the stateful tree
+    uint32_t domain_ = 0, log_domain_ = 0;
+    InputSlots slots_{};
+
+    // device-resident circuit
+    DevMem d_prog_, d_consts_, d_signals_, d_a_ptr_, d_a_col_, d_a_val_, d_b_ptr_, d_b_col_, d_b_val_, d_tw_inv_, d_tw_fwd_, d_coset_;
+    CircuitDev circ_{};
+    // fixed-base tables
+    DevMem d_tab_[5], d_rows_[5], d_gamma_abc_;
+    FixedMsmPlan plan_{};
+    ProverKeyDev pk_{};
+    VerifyKeyDev vk_{};
+    // tree
+    DevMem d_nodes_;
+    size_t next_index_ = 0;
+    // workspace
+    size_t cap_ = 0, max_batch_ = 4096;
+    DevMem ws_inputs_, ws_rs_, ws_vals_, ws_a_, ws_b_, ws_c_, ws_err_, ws_part1_, ws_part2_, ws_sum1_, ws_sum2_, ws_proofs_, ws_values_, ws_affine_;
+    std::map<u32, std::unique_ptr<TaskSet>> tasks_;
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t ev_[5];
+};
+
+static void upload_points_g1(const std::vector<uint8_t>& raw, const std::vector<uint32_t>& pick, DevMem& out) {
+    std::vector<uint8_t> sel(pick.size() * 64);
+    for (size_t i = 0; i < pick.size(); i++) memcpy(sel.data() + 64 * i, raw.data() + 64 * (size_t)pick[i], 64);
+    DevMem tmp;
+    tmp.upload(sel.data(), sel.size());
+    out.alloc(sizeof(G1Affine) * pick.size());
+    launch_g1_from_bytes(tmp.as<uint8_t>(), out.as<G1Affine>(), pick.size(), 0);
+    g_launch_count++;
+    ZK_CUDA_CHECK(cudaDeviceSynchronize());
+}
+static void upload_points_g2(const std::vector<uint8_t>& raw, const std::vector<uint32_t>& pick, DevMem& out) {
+    std::vector<uint8_t> sel(pick.size() * 128);
+    for (size_t i = 0; i < pick.size(); i++) memcpy(sel.data() + 128 * i, raw.data() + 128 * (size_t)pick[i], 128);
+    DevMem tmp;
+    tmp.upload(sel.data(), sel.size());
+    out.alloc(sizeof(G2Affine) * pick.size());
+    launch_g2_from_bytes(tmp.as<uint8_t>(), out.as<G2Affine>(), pick.size(), 0);
+    g_launch_count++;
+    ZK_CUDA_CHECK(cudaDeviceSynchronize());
+}
+static G1Affine fetch_g1(const std::vector<uint8_t>& raw64) {
+    DevMem d;
+    std::vector<uint32_t> one = {0};
+    upload_points_g1(raw64, one, d);
+    G1Affine h;
+    ZK_CUDA_CHECK(cudaMemcpy(&h, d.p, sizeof h, cudaMemcpyDeviceToHost));
+    return h;
+}
+static G2Affine fetch_g2(const std::vector<uint8_t>& raw128) {
+    DevMem d;
+    std::vector<uint32_t> one = {0};
+    upload_points_g2(raw128, one, d);
+    G2Affine h;
+    ZK_CUDA_CHECK(cudaMemcpy(&h, d.p, sizeof h, cudaMemcpyDeviceToHost));
+    return h;
+}
+
+Rln::Rln(size_t tree_depth, const uint8_t* zkey, size_t zlen, const uint8_t* graph, size_t glen) {
+    global_init();
+    try {
+        parse_zkey(zkey, zlen, zk_);
+    } catch (const std::exception& e) {
+        throw RlnError(std::string("ZKey error: ") + e.what());
+    }
+    try {
+        parse_graph(graph, glen, gh_);
+    } catch (const std::exception& e) {
+        throw RlnError(std::string("Graph error: ") + e.what());
+    }
+    check_graph_shape();
+    max_batch_ = (size_t)env_int("RLN_B200_MAX_BATCH", 4096);
+    ZK_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    for (auto& e : ev_) ZK_CUDA_CHECK(cudaEventCreate(&e));
+    build_circuit();
+    build_tables();
+    set_tree(tree_depth);
+}
+Rln::~Rln() {
+    cudaDeviceSynchronize();
+    for (auto& e : ev_) cudaEventDestroy(e);
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+void Rln::check_graph_shape() {
+    auto need = [&](const char* name) -> std::pair<uint32_t, uint32_t> {
+        auto it = gh_.inputs.find(name);
+        if (it == gh_.inputs.end()) throw RlnError(std::string("Graph error: missing input signal ") + name);
+        return it->second;
+    };
+    if (gh_.inputs.count("selectorUsed"))
+        throw RlnError("Graph error: multi message-id circuits are not supported by this build (SURVEY §8f item 2)");
+    auto pe = need("pathElements"), pi = need("identityPathIndex");
+    depth_ = pe.second;
+    if (pi.second != depth_) throw RlnError("Graph error: pathElements / identityPathIndex length mismatch");
+    slots_.secret = need("identitySecret").first;
+    slots_.limit = need("userMessageLimit").first;
+    slots_.message_id = need("messageId").first;
+    slots_.path = pe.first;
+    slots_.index = pi.first;
+    slots_.x = need("x").first;
+    slots_.ext_null = need("externalNullifier").first;
+    slots_.depth = (u32)depth_;
+    slots_.n_slots = gh_.n_slots;
+    const size_t nw = gh_.signals.size();
+    if (zk_.a_query.size() / 64 != nw || zk_.b_g1.size() / 64 != nw || zk_.b_g2.size() / 128 != nw)
+        throw RlnError("ZKey error: query sizes do not match the witness graph");
+    if (zk_.l_query.size() / 64 + zk_.num_instance != nw) throw RlnError("ZKey error: l_query size does not match the witness graph");
+    for (auto c : zk_.a_col)
+        if (c >= nw) throw RlnError("ZKey error: matrix column out of range");
+    for (auto c : zk_.b_col)
+        if (c >= nw) throw RlnError("ZKey error: matrix column out of range");
+    size_t n = 1;
+    log_domain_ = 0;
+    while (n < zk_.num_constraints + zk_.num_instance) { n <<= 1; log_domain_++; }
+    domain_ = (uint32_t)n;
+    if (zk_.h_query.size() / 64 < domain_) throw RlnError("ZKey error: h_query shorter than the evaluation domain");
+    if (log_domain_ > 16 || log_domain_ < 2) throw RlnError("ZKey error: unsupported evaluation domain size");
+}
+
+void Rln::build_circuit() {
+    d_prog_.upload(gh_.prog.data(), gh_.prog.size() * sizeof(VmInstr));
+    {   // constants → Montgomery on the device
+        DevMem raw;
+        raw.upload(gh_.consts.data(), gh_.consts.size());
+        d_consts_.alloc(sizeof(Fr) * (gh_.consts.size() / 32 + 1));
+        launch_fr_from_bytes(raw.as<uint8_t>(), d_consts_.as<Fr>(), gh_.consts.size() / 32, 0);
+        g_launch_count++;
+    }
+    d_signals_.upload(gh_.signals.data(), gh_.signals.size() * 4);
+    auto up_mat = [&](std::vector<uint32_t>& ptr, std::vector<uint32_t>& col, std::vector<uint8_t>& val, DevMem& dptr, DevMem& dcol, DevMem& dval) {
+        dptr.upload(ptr.data(), ptr.size() * 4);
+        dcol.upload(col.data(), col.size() * 4);
+        DevMem raw;
+        raw.upload(val.data(), val.size());
+        dval.alloc(sizeof(Fr) * (val.size() / 32 + 1));
+        launch_fr_from_bytes(raw.as<uint8_t>(), dval.as<Fr>(), val.size() / 32, 0);
+        g_launch_count++;
+        ZK_CUDA_CHECK(cudaDeviceSynchronize());
+    };
+    up_mat(zk_.a_ptr, zk_.a_col, zk_.a_val, d_a_ptr_, d_a_col_, d_a_val_);
+    up_mat(zk_.b_ptr, zk_.b_col, zk_.b_val, d_b_ptr_, d_b_col_, d_b_val_);
+    // NTT tables (ark-poly radix-2 domain: generator 5, two-adicity 28).  One-off host arithmetic.
+    {
+        const u32 n = domain_;
+        u32 e[8];  // (r−1) >> 28
+        for (int i = 0; i < 8; i++) e[i] = FrCfg::p(i);
+        e[0] -= 1;
+        for (int sft = 0; sft < 28; sft++) {
+            for (int i = 0; i < 7; i++) e[i] = (e[i] >> 1) | (e[i + 1] << 31);
+            e[7] >>= 1;
+        }
+        Fr root28 = Fr::from_u32(5).pow(e);  // primitive 2^28-th root of unity
+        auto root_for = [&](u32 lg) {
+            Fr w = root28;
+            for (u32 i = 0; i < 28 - lg; i++) w = w.sqr();
+            return w;
+        };
+        const Fr om = root_for(log_domain_), om_inv = om.inv(), g = root_for(log_domain_ + 1);
+        std::vector<Fr> fwd(n / 2), inv(n / 2), coset(n);
+        Fr a = Fr::one(), b = Fr::one();
+        for (u32 k = 0; k < n / 2; k++) {
+            fwd[k] = a;
+            inv[k] = b;
+            a = a * om;
+            b = b * om_inv;
+        }
+        const Fr n_inv = Fr::from_u32(n).inv();
+        std::vector<Fr> gp(n);
+        Fr t = n_inv;
+        for (u32 i = 0; i < n; i++) { gp[i] = t; t = t * g; }
+        for (u32 p = 0; p < n; p++) {
+            u32 r = 0;
+            for (u32 bit = 0; bit < log_domain_; bit++) r |= ((p >> bit) & 1) << (log_domain_ - 1 - bit);
+            coset[p] = gp[r];
+        }
+        d_tw_fwd_.upload(fwd.data(), fwd.size() * sizeof(Fr));
+        d_tw_inv_.upload(inv.data(), inv.size() * sizeof(Fr));
+        d_coset_.upload(coset.data(), coset.size() * sizeof(Fr));
+    }
+    circ_.n_nodes = (u32)gh_.prog.size();
+    circ_.n_slots = gh_.n_slots;
+    circ_.n_wires = (u32)gh_.signals.size();
+    circ_.prog = d_prog_.as<VmInstr>();
+    circ_.consts = d_consts_.as<Fr>();
+    circ_.signals = d_signals_.as<u32>();
+    circ_.n_constraints = (u32)zk_.num_constraints;
+    circ_.n_instance = (u32)zk_.num_instance;
+    circ_.domain = domain_;
+    circ_.log_domain = log_domain_;
+    circ_.a_ptr = d_a_ptr_.as<u32>(); circ_.a_col = d_a_col_.as<u32>(); circ_.a_val = d_a_val_.as<Fr>();
+    circ_.b_ptr = d_b_ptr_.as<u32>(); circ_.b_col = d_b_col_.as<u32>(); circ_.b_val = d_b_val_.as<Fr>();
+    circ_.tw_inv = d_tw_inv_.as<Fr>();
+    circ_.tw_fwd = d_tw_fwd_.as<Fr>();
+    circ_.coset = d_coset_.as<Fr>();
+    ZK_CUDA_CHECK(cudaDeviceSynchronize());
+}
+
+void Rln::build_tables() {
+    // window size: as wide as HBM allows (tables are 64·2^(c−1)·K bytes per G1 base, twice that per G2 base)
+    size_t free_b = 0, total_b = 0;
+    ZK_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    const size_t nw = gh_.signals.size(), ni = zk_.num_instance;
+    // bases at infinity contribute nothing and are dropped (47 in a_query, 1 999 in b_query for the bundled key)
+    auto non_inf = [](const std::vector<uint8_t>& raw, size_t elem, size_t count, u32 first) {
+        std::vector<uint32_t> v;
+        for (size_t i = first; i < count; i++)
+            if (!(raw[elem * i + elem - 1] & 0x40)) v.push_back((uint32_t)i);
+        return v;
+    };
+    std::vector<uint32_t> pick[5];
+    pick[0] = non_inf(zk_.a_query, 64, nw, 0);
+    pick[1] = non_inf(zk_.b_g1, 64, nw, 0);
+    pick[2] = non_inf(zk_.l_query, 64, nw - ni, 0);
+    pick[3] = non_inf(zk_.h_query, 64, domain_, 0);
+    pick[4] = non_inf(zk_.b_g2, 128, nw, 0);
+    size_t n_g1 = pick[0].size() + pick[1].size() + pick[2].size() + pick[3].size(), n_g2 = pick[4].size();
+    int c = env_int("RLN_B200_WINDOW_BITS", 0);
+    if (c == 0) {
+        const size_t reserve = (size_t)24 << 30;  // proving workspace, tree, slack
+        for (c = 12; c > 5; c--) {
+            int K = (255 + c - 1) / c;
+            size_t need = (n_g1 * 64 + n_g2 * 128) * (size_t)K << (c - 1);
+            if (need + reserve < free_b) break;
+        }
+    }
+    if (c < 5 || c > 16) throw RlnError("Configuration error: RLN_B200_WINDOW_BITS must be in [5, 16]");
+    const int K = (255 + c - 1) / c;
+    plan_.c = c;
+    plan_.K = K;
+    // scalar row of each base: A/B use wire i → node signals[i]; L uses wire ni+i; H uses row i of the h matrix
+    for (int g = 0; g < 5; g++) {
+        std::vector<uint32_t> rows(pick[g].size());
+        for (size_t i = 0; i < rows.size(); i++) {
+            if (g == 3) rows[i] = pick[g][i];
+            else if (g == 2) rows[i] = gh_.signals[ni + pick[g][i]];
+            else rows[i] = gh_.signals[pick[g][i]];
+        }
+        d_rows_[g].upload(rows.data(), rows.size() * 4);
+        DevMem bases;
+        const size_t half = (size_t)1 << (c - 1);
+        if (g < 4) {
+            const std::vector<uint8_t>& raw = g == 0 ? zk_.a_query : g == 1 ? zk_.b_g1 : g == 2 ? zk_.l_query : zk_.h_query;
+            upload_points_g1(raw, pick[g], bases);
+            d_tab_[g].alloc(sizeof(G1Affine) * pick[g].size() * K * half);
+            launch_build_table_g1(bases.as<G1Affine>(), (u32)pick[g].size(), c, K, d_tab_[g].as<G1Affine>(), 0);
+        } else {
+            upload_points_g2(zk_.b_g2, pick[g], bases);
+            d_tab_[g].alloc(sizeof(G2Affine) * pick[g].size() * K * half);
+            launch_build_table_g2(bases.as<G2Affine>(), (u32)pick[g].size(), c, K, d_tab_[g].as<G2Affine>(), 0);
+        }
+        g_launch_count += 2;
+        ZK_CUDA_CHECK(cudaDeviceSynchronize());
+        MsmGroupDev& dst = g < 4 ? plan_.g1[g] : plan_.g2;
+        dst.n_bases = (u32)pick[g].size();
+        dst.row = d_rows_[g].as<u32>();
+        dst.table = d_tab_[g].p;
+        dst.which_src = g == 3 ? 1 : 0;
+    }
+    pk_.alpha_g1 = fetch_g1(zk_.alpha_g1);
+    pk_.beta_g1 = fetch_g1(zk_.beta_g1);
+    pk_.delta_g1 = fetch_g1(zk_.delta_g1);
+    pk_.beta_g2 = fetch_g2(zk_.beta_g2);
+    pk_.delta_g2 = fetch_g2(zk_.delta_g2);
+    vk_.alpha_g1 = pk_.alpha_g1;
+    vk_.beta_g2 = pk_.beta_g2;
+    vk_.gamma_g2 = fetch_g2(zk_.gamma_g2);
+    vk_.delta_g2 = pk_.delta_g2;
+    {
+        std::vector<uint32_t> all(zk_.gamma_abc.size() / 64);
+        for (size_t i = 0; i < all.size(); i++) all[i] = (uint32_t)i;
+        upload_points_g1(zk_.gamma_abc, all, d_gamma_abc_);
+        vk_.gamma_abc = d_gamma_abc_.as<G1Affine>();
+        vk_.n_public = (u32)all.size() - 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- tree
+void Rln::set_tree(size_t depth) {
+    if (depth == 0 || depth > 30) throw RlnError("Merkle tree error: Tree depth exceeds maximum allowed (must be < 64)");
+    tree_depth_ = depth;
+    d_nodes_.alloc(sizeof(Fr) * ((size_t)2 << depth));
+    launch_merkle_fill_empty(d_nodes_.as<Fr>(), (u32)depth, stream_);
+    g_launch_count += 2;
+    ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    next_index_ = 0;
+}
+void Rln::set_range_device(size_t start, const uint8_t* d_leaves, size_t count, cudaStream_t s) {
+    if (count == 0) return;
+    if (start + count > capacity() || start + count < start) throw RlnError("Merkle tree error: set_range got too many leaves");
+    launch_merkle_set_range(d_nodes_.as<Fr>(), (u32)tree_depth_, start, d_leaves, count, s);
+    g_launch_count += 1 + tree_depth_;
+    if (start + count > next_index_) next_index_ = start + count;
+}
+void Rln::set_range_host(size_t start, const uint8_t* leaves, size_t count) {
+    if (count == 0) return;
+    if (start + count > capacity() || start + count < start) throw RlnError("Merkle tree error: set_range got too many leaves");
+    DevMem tmp;
+    tmp.upload(leaves, 32 * count);
+    set_range_device(start, tmp.as<uint8_t>(), count, stream_);
+    ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+void Rln::set_leaf(size_t index, const uint8_t* leaf) {
+    if (index >= capacity()) throw RlnError("Merkle tree error: Leaf index out of bounds");
+    set_range_host(index, leaf, 1);
+}
+void Rln::delete_leaf(size_t index) {
+    if (index >= capacity()) throw RlnError("Merkle tree error: Leaf index out of bounds");
+    uint8_t zero[32] = {0};
+    size_t keep = next_index_;
+    set_range_host(index, zero, 1);
+    next_index_ = keep;  // delete never moves next_index (pm_tree_adapter.rs:365-374)
+}
+void Rln::set_next(const uint8_t* leaf) {
+    if (next_index_ >= capacity()) throw RlnError("Merkle tree error: Leaf index out of bounds");
+    set_range_host(next_index_, leaf, 1);
+}
+void Rln::get_leaf(size_t index, uint8_t out[32]) {
+    if (index >= capacity()) throw RlnError("Merkle tree error: Leaf index out of bounds");
+    DevMem tmp;
+    tmp.alloc(32);
+    launch_fr_to_bytes(d_nodes_.as<Fr>() + capacity() + index, tmp.as<uint8_t>(), 1, stream_);
+    g_launch_count++;
+    ZK_CUDA_CHECK(cudaMemcpyAsync(out, tmp.p, 32, cudaMemcpyDeviceToHost, stream_));
+    ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+void Rln::root(uint8_t out[32]) {
+    DevMem tmp;
+    tmp.alloc(32);
+    launch_fr_to_bytes(d_nodes_.as<Fr>() + 1, tmp.as<uint8_t>(), 1, stream_);
+    g_launch_count++;
+    ZK_CUDA_CHECK(cudaMemcpyAsync(out, tmp.p, 32, cudaMemcpyDeviceToHost, stream_));
+    ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+void Rln::merkle_proofs(const uint64_t* idx, size_t n, uint8_t* elems, uint8_t* bits) {
+    for (size_t i = 0; i < n; i++)
+        if (idx[i] >= capacity()) throw RlnError("Merkle tree error: Leaf index out of bounds");
+    DevMem d_idx, d_el, d_bits;
+    d_idx.upload(idx, 8 * n);
+    d_el.alloc(32 * n * tree_depth_);
+    d_bits.alloc(n * tree_depth_);
+    launch_merkle_paths(d_nodes_.as<Fr>(), (u32)tree_depth_, d_idx.as<u64>(), n, d_el.as<uint8_t>(), d_bits.as<uint8_t>(), stream_);
+    g_launch_count++;
+    ZK_CUDA_CHECK(cudaMemcpyAsync(elems, d_el.p, 32 * n * tree_depth_, cudaMemcpyDeviceToHost, stream_));
+    ZK_CUDA_CHECK(cudaMemcpyAsync(bits, d_bits.p, n * tree_depth_, cudaMemcpyDeviceToHost, stream_));
+    ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+// override_range with PmTree's "empty indices allowed" policy (rln/src/pm_tree_adapter.rs:320-356,
+// utils/src/merkle_tree/override_range_validation.rs:20-65)
+void Rln::override_range(size_t start, const uint8_t* leaves, size_t n_leaves, std::vector<size_t> indices) {
+    for (size_t i : indices)
+        if (i >= capacity()) throw RlnError("Merkle tree error: Invalid indices");
+    std::sort(indices.begin(), indices.end());
+    indices.erase(std::unique(indices.begin(), indices.end()), indices.end());
+    size_t end = 0;
+    if (n_leaves) {
+        end = start + n_leaves;
+        if (end < start || end > capacity()) throw RlnError("Merkle tree error: set_range got too many leaves");
+        if (!indices.empty() && (indices[0] > start || indices[0] >= end)) throw RlnError("Merkle tree error: Invalid indices");
+    }
+    if (n_leaves == 0 && indices.empty()) throw RlnError("Merkle tree error: Leaf index out of bounds");
+    size_t keep = next_index_;
+    uint8_t zero[32] = {0};
+    for (size_t i : indices) {  // removals: reset to the default leaf
+        DevMem tmp;
+        tmp.upload(zero, 32);
+        launch_merkle_set_range(d_nodes_.as<Fr>(), (u32)tree_depth_, i, tmp.as<uint8_t>(), 1, stream_);
+        g_launch_count += 1 + tree_depth_;
+        ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    }
+    next_index_ = keep;
+    if (n_leaves) set_range_host(start, leaves, n_leaves);
+}
+
+// ------------------------------------------------------------------------------------------- proving
+Rln::TaskSet& Rln::tasks_for(u32 B) {
+    auto it = tasks_.find(B);
+    if (it != tasks_.end()) return *it->second;
+    auto ts = std::make_unique<TaskSet>();
+    std::vector<MsmTask> t1 = msm_make_tasks(plan_, B, false), t2 = msm_make_tasks(plan_, B, true);
+    ts->g1.upload(t1.data(), t1.size() * sizeof(MsmTask));
+    ts->g2.upload(t2.data(), t2.size() * sizeof(MsmTask));
+    ts->n1 = (u32)t1.size();
+    ts->n2 = (u32)t2.size();
+    TaskSet& ref = *ts;
+    tasks_[B] = std::move(ts);
+    return ref;
+}
+void Rln::reserve(size_t B) {
+    if (B <= cap_) return;
+    if (B > max_batch_) B = max_batch_;
+    if (B <= cap_) return;
+    cap_ = 0;
+    // largest task counts over the batch sizes this capacity can serve
+    size_t t1 = 0, t2 = 0;
+    for (size_t b = 1; b <= B; b <<= 1) {
+        size_t a = msm_make_tasks(plan_, (u32)b, false).size() * b, c2 = msm_make_tasks(plan_, (u32)b, true).size() * b;
+        if (a > t1) t1 = a;
+        if (c2 > t2) t2 = c2;
+    }
+    {
+        size_t a = msm_make_tasks(plan_, (u32)B, false).size() * B, c2 = msm_make_tasks(plan_, (u32)B, true).size() * B;
+        if (a > t1) t1 = a;
+        if (c2 > t2) t2 = c2;
+    }
+    // non power-of-two batch sizes below B can need more partial slots than the probes above: add headroom
+    t1 += t1 / 2;
+    t2 += t2 / 2;
+    ws_inputs_.alloc(B * (size_t)gh_.n_slots * 32);
+    ws_rs_.alloc(B * 64);
+    ws_vals_.alloc(sizeof(Fr) * gh_.prog.size() * B);
+    ws_a_.alloc(sizeof(Fr) * (size_t)domain_ * B);
+    ws_b_.alloc(sizeof(Fr) * (size_t)domain_ * B);
+    ws_c_.alloc(sizeof(Fr) * (size_t)domain_ * B);
+    ws_err_.alloc(4 * B);
+    ws_part1_.alloc(sizeof(G1XYZZ) * t1);
+    ws_part2_.alloc(sizeof(G2XYZZ) * t2);
+    ws_sum1_.alloc(sizeof(G1XYZZ) * 4 * B);
+    ws_sum2_.alloc(sizeof(G2XYZZ) * B);
+    ws_proofs_.alloc(128 * B);
+    ws_values_.alloc(160 * B);
+    ws_affine_.alloc(256 * B);
+    cap_ = B;
+}
+
+void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, uint8_t* d_proofs, uint8_t* d_values, uint8_t* d_affine,
+                       cudaStream_t s) {
+    if (n == 0) return;
+    reserve(n);
+    float acc[4] = {0, 0, 0, 0};
+    for (size_t off = 0; off < n; off += cap_) {
+        const u32 B = (u32)(n - off < cap_ ? n - off : cap_);
+        TaskSet& ts = tasks_for(B);
+        if ((size_t)ts.n1 * B * sizeof(G1XYZZ) > ws_part1_.bytes || (size_t)ts.n2 * B * sizeof(G2XYZZ) > ws_part2_.bytes) {
+            ws_part1_.ensure((size_t)ts.n1 * B * sizeof(G1XYZZ));
+            ws_part2_.ensure((size_t)ts.n2 * B * sizeof(G2XYZZ));
+        }
+        const uint8_t* in = d_inputs + off * (size_t)gh_.n_slots * 32;
+        ZK_CUDA_CHECK(cudaEventRecord(ev_[0], s));
+        launch_witness(circ_, in, ws_vals_.as<Fr>(), B, ws_err_.as<u32>(), s);
+        ZK_CUDA_CHECK(cudaEventRecord(ev_[1], s));
+        launch_qap(circ_, ws_vals_.as<Fr>(), ws_a_.as<Fr>(), ws_b_.as<Fr>(), ws_c_.as<Fr>(), B, s);
+        ZK_CUDA_CHECK(cudaEventRecord(ev_[2], s));
+        MsmWorkspace mw;
+        mw.part_g1 = ws_part1_.as<G1XYZZ>();
+        mw.part_g2 = ws_part2_.as<G2XYZZ>();
+        mw.sum_g1 = ws_sum1_.as<G1XYZZ>();
+        mw.sum_g2 = ws_sum2_.as<G2XYZZ>();
+        mw.tasks_g1 = ts.g1.as<MsmTask>();
+        mw.tasks_g2 = ts.g2.as<MsmTask>();
+        mw.n_tasks_g1 = ts.n1;
+        mw.n_tasks_g2 = ts.n2;
+        launch_msm_and_assemble(plan_, pk_, ws_vals_.as<Fr>(), ws_a_.as<Fr>(), B, d_rs + 64 * off, mw, d_proofs + 128 * off,
+                                d_affine ? d_affine + 256 * off : nullptr, s);
+        ZK_CUDA_CHECK(cudaEventRecord(ev_[3], s));
+        if (d_values) launch_proof_values(in, slots_, B, d_values + 160 * off, s);
+        ZK_CUDA_CHECK(cudaEventRecord(ev_[4], s));
+        g_launch_count += 1 + (2 + 3 * (2 * log_domain_ + 1)) + 6 + (d_values ? 1 : 0);
+        // graph-evaluation failures surface as errors, like WitnessCalcError::GraphEvaluation (rln/src/circuit/iden3calc.rs:52-53)
+        std::vector<u32> err(B);
+        ZK_CUDA_CHECK(cudaMemcpyAsync(err.data(), ws_err_.p, 4 * B, cudaMemcpyDeviceToHost, s));
+        ZK_CUDA_CHECK(cudaStreamSynchronize(s));
+        for (int i = 0; i < 4; i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev_[i], ev_[i + 1]);
+            acc[i] += ms;
+        }
+        for (u32 j = 0; j < B; j++)
+            if (err[j]) throw RlnError("Protocol error: Error calculating witness: graph evaluation failed");
+    }
+    for (int i = 0; i < 4; i++) stage_ms[i] = acc[i];
+}
+
+void Rln::witness_slots(const Witness& w, uint8_t* slots) const {  // iden3calc.rs:106-181, witness.rs:832-881
+    memset(slots, 0, (size_t)gh_.n_slots * 32);
+    slots[0] = 1;
+    memcpy(slots + 32 * slots_.secret, w.secret, 32);
+    memcpy(slots + 32 * slots_.limit, w.limit, 32);
+    memcpy(slots + 32 * slots_.message_id, w.message_id, 32);
+    memcpy(slots + 32 * slots_.path, w.path.data(), 32 * depth_);
+    for (size_t i = 0; i < depth_; i++) slots[32 * (slots_.index + i)] = w.index[i];
+    memcpy(slots + 32 * slots_.x, w.x, 32);
+    memcpy(slots + 32 * slots_.ext_null, w.ext_null, 32);
+}
+
+void Rln::prove_host(const std::vector<Witness>& wsv, const uint8_t* rs, std::vector<RlnProof>& out) {
+    const size_t n = wsv.size();
+    out.resize(n);
+    if (!n) return;
+    for (const Witness& w : wsv) {  // validate_witness_against_graph (proof.rs:644-700)
+        if (w.path.size() / 32 != depth_) {
+            std::ostringstream s;
+            s << "Protocol error: The field path_elements has length " << w.path.size() / 32 << ", but the field tree_depth has length " << depth_;
+            throw RlnError(s.str());
+        }
+        if (w.index.size() != depth_) {
+            std::ostringstream s;
+            s << "Protocol error: The field identity_path_index has length " << w.index.size() << ", but the field tree_depth has length " << depth_;
+            throw RlnError(s.str());
+        }
+    }
+    const size_t chunk = n < max_batch_ ? n : max_batch_;
+    reserve(chunk);
+    std::vector<uint8_t> slots(chunk * (size_t)gh_.n_slots * 32), rsb(chunk * 64), proofs(chunk * 128), values(chunk * 160);
+    for (size_t off = 0; off < n; off += chunk) {
+        const size_t B = n - off < chunk ? n - off : chunk;
+        for (size_t j = 0; j < B; j++) witness_slots(wsv[off + j], slots.data() + j * (size_t)gh_.n_slots * 32);
+        if (rs) memcpy(rsb.data(), rs + 64 * off, 64 * B);
+        else
+            for (size_t j = 0; j < 2 * B; j++) random_fr(rsb.data() + 32 * j);  // r, s ← rng (proof.rs:743-745)
+        ZK_CUDA_CHECK(cudaMemcpyAsync(ws_inputs_.p, slots.data(), B * (size_t)gh_.n_slots * 32, cudaMemcpyHostToDevice, stream_));
+        ZK_CUDA_CHECK(cudaMemcpyAsync(ws_rs_.p, rsb.data(), 64 * B, cudaMemcpyHostToDevice, stream_));
+        prove_device(ws_inputs_.as<uint8_t>(), ws_rs_.as<uint8_t>(), B, ws_proofs_.as<uint8_t>(), ws_values_.as<uint8_t>(), nullptr, stream_);
+        ZK_CUDA_CHECK(cudaMemcpyAsync(proofs.data(), ws_proofs_.p, 128 * B, cudaMemcpyDeviceToHost, stream_));
+        ZK_CUDA_CHECK(cudaMemcpyAsync(values.data(), ws_values_.p, 160 * B, cudaMemcpyDeviceToHost, stream_));
+        // secrets do not linger in the staging buffers (reference zeroises them: rln/src/circuit/iden3calc.rs:44-57)
+        ZK_CUDA_CHECK(cudaMemsetAsync(ws_inputs_.p, 0, B * (size_t)gh_.n_slots * 32, stream_));
+        ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        for (size_t j = 0; j < B; j++) {
+            RlnProof& p = out[off + j];
+            memcpy(p.proof, proofs.data() + 128 * j, 128);
+            const uint8_t* v = values.data() + 160 * j;
+            memcpy(p.pv.root, v, 32);
+            memcpy(p.pv.ext_null, v + 32, 32);
+            memcpy(p.pv.x, v + 64, 32);
+            memcpy(p.pv.y, v + 96, 32);
+            memcpy(p.pv.nullifier, v + 128, 32);
+        }
+    }
+    memset(slots.data(), 0, slots.size());
+}
+
+void Rln::debug_w_h(const Witness& w, uint8_t* w_out, uint8_t* h_out) {
+    reserve(1);
+    std::vector<uint8_t> slots((size_t)gh_.n_slots * 32);
+    witness_slots(w, slots.data());
+    ZK_CUDA_CHECK(cudaMemcpyAsync(ws_inputs_.p, slots.data(), slots.size(), cudaMemcpyHostToDevice, stream_));
+    launch_witness(circ_, ws_inputs_.as<uint8_t>(), ws_vals_.as<Fr>(), 1, ws_err_.as<u32>(), stream_);
+    launch_qap(circ_, ws_vals_.as<Fr>(), ws_a_.as<Fr>(), ws_b_.as<Fr>(), ws_c_.as<Fr>(), 1, stream_);
+    g_launch_count += 3 + 3 * (2 * log_domain_ + 1);
+    DevMem vals_b, h_b;
+    vals_b.alloc(32 * gh_.prog.size());
+    h_b.alloc(32 * (size_t)domain_);
+    launch_fr_to_bytes(ws_vals_.as<Fr>(), vals_b.as<uint8_t>(), gh_.prog.size(), stream_);
+    launch_fr_to_bytes(ws_a_.as<Fr>(), h_b.as<uint8_t>(), domain_, stream_);
+    g_launch_count += 2;
+    std::vector<uint8_t> vals(32 * gh_.prog.size());
+    ZK_CUDA_CHECK(cudaMemcpyAsync(vals.data(), vals_b.p, vals.size(), cudaMemcpyDeviceToHost, stream_));
+    ZK_CUDA_CHECK(cudaMemcpyAsync(h_out, h_b.p, 32 * (size_t)domain_, cudaMemcpyDeviceToHost, stream_));
+    ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    for (size_t i = 0; i < gh_.signals.size(); i++) memcpy(w_out + 32 * i, vals.data() + 32 * (size_t)gh_.signals[i], 32);
+}
+
+void Rln::verify_batch(const uint8_t* proofs128, const uint8_t* publics, size_t n, uint8_t* ok) {
+    if (!n) return;
+    DevMem dp, dv, dok;
+    dp.upload(proofs128, 128 * n);
+    dv.upload(publics, 32 * n * vk_.n_public);
+    dok.alloc(n);
+    launch_verify(vk_, dp.as<uint8_t>(), dv.as<uint8_t>(), n, dok.as<uint8_t>(), stream_);
+    g_launch_count++;
+    ZK_CUDA_CHECK(cudaMemcpyAsync(ok, dok.p, n, cudaMemcpyDeviceToHost, stream_));
+    ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+}  // namespace zk
+
+// =============================================================================================== C ABI
+using namespace zk;
+
+struct FFI_RLN { std::unique_ptr<Rln> r; };
+struct FFI_RLNProof { RlnProof p; };
+struct FFI_RLNProofValues { ProofValues v; };
+struct FFI_RLNWitnessInput { Witness w; };
+struct RlnB200Msm { VarMsmWorkspace* ws; size_t max_n; };
+
+static RlnString mk_string(const std::string& s) {
+    RlnString out;
+    out.len = s.size();
+    out.cap = s.size() + 1;
+    out.ptr = (uint8_t*)malloc(out.cap);
+    memcpy(out.ptr, s.data(), s.size());
+    out.ptr[s.size()] = 0;
+    return out;
+}
+static RlnString no_string() { return RlnString{nullptr, 0, 0}; }
+static Vec_uint8_t mk_vec(const uint8_t* p, size_t n) {
+    Vec_uint8_t v;
+    v.len = n;
+    v.cap = n ? n : 1;
+    v.ptr = (uint8_t*)malloc(v.cap);
+    if (n) memcpy(v.ptr, p, n);
+    return v;
+}
+static CFr_t* mk_cfr(const uint8_t* b) {
+    CFr_t* c = (CFr_t*)malloc(sizeof(CFr_t));
+    memcpy(c->bytes, b, 32);
+    return c;
+}
+static std::string describe(const std::exception& e) { return e.what(); }
+static std::string describe(const CudaError& e) {
+    std::ostringstream s;
+    s << "CUDA error: " << cudaGetErrorString(e.code) << " (" << e.expr << " at " << e.file << ":" << e.line << ")";
+    return s.str();
+}
+#define GUARD_BEGIN try {
+#define GUARD_END(on_error)                                              \
+    }                                                                    \
+    catch (const CudaError& e) { std::string m = describe(e); on_error; } \
+    catch (const std::exception& e) { std::string m = describe(e); on_error; }
+
+// bundled circuit files live next to the library: <dir of librln_b200.so>/../resources
+static std::string resources_dir() {
+    const char* env = getenv("RLN_B200_RESOURCES");
+    if (env && *env) return env;
+    Dl_info info;
+    if (dladdr((void*)&resources_dir, &info) && info.dli_fname) {
+        std::string p = info.dli_fname;
+        size_t k = p.rfind('/');
+        std::string dir = k == std::string::npos ? "." : p.substr(0, k);
+        return dir + "/../resources";
+    }
+    return "resources";
+}
+static std::vector<uint8_t> read_file(const std::string& path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw RlnError("I/O error: cannot open " + path);
+    return std::vector<uint8_t>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+}
+
+extern "C" {
+
+// ---- RLN object -------------------------------------------------------------------------------
+CResult_FFI_RLN_t ffi_rln_new(size_t tree_depth, const char* config_path) {
+    (void)config_path;  // PmTree/sled persistence config: out of scope, the tree lives in HBM
+    GUARD_BEGIN
+    // bundled circuit resources, like the reference's include_bytes! (rln/src/circuit/mod.rs:29-78)
+    std::ostringstream dir;
+    dir << resources_dir() << "/tree_depth_" << tree_depth;
+    std::vector<uint8_t> zkey = read_file(dir.str() + "/rln_final.arkzkey"), graph = read_file(dir.str() + "/graph.bin");
+    FFI_RLN* h = new FFI_RLN();
+    try {
+        h->r = std::make_unique<Rln>(tree_depth, zkey.data(), zkey.size(), graph.data(), graph.size());
+    } catch (...) {
+        delete h;
+        throw;
+    }
+    return CResult_FFI_RLN_t{h, no_string()};
+    GUARD_END(return (CResult_FFI_RLN_t{nullptr, mk_string(m)}))
+}
+CResult_FFI_RLN_t ffi_rln_new_with_params(size_t tree_depth, const Vec_uint8_t* zkey_data, const Vec_uint8_t* graph_data, const char* config_path) {
+    (void)config_path;
+    GUARD_BEGIN
+    FFI_RLN* h = new FFI_RLN();
+    try {
+        h->r = std::make_unique<Rln>(tree_depth, zkey_data->ptr, zkey_data->len, graph_data->ptr, graph_data->len);
+    } catch (...) {
+        delete h;
+        throw;
+    }
+    return CResult_FFI_RLN_t{h, no_string()};
+    GUARD_END(return (CResult_FFI_RLN_t{nullptr, mk_string(m)}))
+}
+void ffi_rln_free(FFI_RLN_t* rln) { delete rln; }
+size_t ffi_rln_get_tree_depth(FFI_RLN_t* const* rln) { return (*rln)->r->depth(); }
+size_t ffi_rln_get_max_out(FFI_RLN_t* const* rln) { (void)rln; return 1; }
+
+// ---- tree -------------------------------------------------------------------------------------
+#define BOOL_OP(...)                                                      \
+    GUARD_BEGIN                                                           \
+    std::lock_guard<std::mutex> lk((*rln)->r->mu);                        \
+    __VA_ARGS__;                                                          \
+    return CBoolResult_t{true, no_string()};                              \
+    GUARD_END(return (CBoolResult_t{false, mk_string(m)}))
+
+CBoolResult_t ffi_set_tree(FFI_RLN_t** rln, size_t tree_depth) { BOOL_OP((*rln)->r->set_tree(tree_depth)) }
+CBoolResult_t ffi_delete_leaf(FFI_RLN_t** rln, size_t index) { BOOL_OP((*rln)->r->delete_leaf(index)) }
+CBoolResult_t ffi_set_leaf(FFI_RLN_t** rln, size_t index, const CFr_t* leaf) { BOOL_OP((*rln)->r->set_leaf(index, leaf->bytes)) }
+CBoolResult_t ffi_set_next_leaf(FFI_RLN_t** rln, const CFr_t* leaf) { BOOL_OP((*rln)->r->set_next(leaf->bytes)) }
+CBoolResult_t ffi_set_leaves_from(FFI_RLN_t** rln, size_t index, const Vec_CFr_t* leaves) {
+    BOOL_OP((*rln)->r->override_range(index, (const uint8_t*)leaves->ptr, leaves->len, {}))
+}
+CBoolResult_t ffi_init_tree_with_leaves(FFI_RLN_t** rln, const Vec_CFr_t* leaves) {
+    BOOL_OP((*rln)->r->set_tree((*rln)->r->tree_depth()); (*rln)->r->override_range(0, (const uint8_t*)leaves->ptr, leaves->len, {}))
+}
+CBoolResult_t ffi_atomic_operation(FFI_RLN_t** rln, size_t index, const Vec_CFr_t* leaves, const Vec_size_t* indices) {
+    BOOL_OP((*rln)->r->override_range(index, (const uint8_t*)leaves->ptr, leaves->len, std::vector<size_t>(indices->ptr, indices->ptr + indices->len)))
+}
+CBoolResult_t ffi_seq_atomic_operation(FFI_RLN_t** rln, const Vec_CFr_t* leaves, const Vec_uint8_t* indices) {
+    BOOL_OP(std::vector<size_t> idx(indices->ptr, indices->ptr + indices->len);
+            (*rln)->r->override_range((*rln)->r->leaves_set(), (const uint8_t*)leaves->ptr, leaves->len, idx))
+}
+size_t ffi_leaves_set(FFI_RLN_t* const* rln) { return (*rln)->r->leaves_set(); }
+CResult_CFr_t ffi_get_leaf(FFI_RLN_t* const* rln, size_t index) {
+    GUARD_BEGIN
+    std::lock_guard<std::mutex> lk((*rln)->r->mu);
+    uint8_t b[32];
+    (*rln)->r->get_leaf(index, b);
+    return CResult_CFr_t{mk_cfr(b), no_string()};
+    GUARD_END(return (CResult_CFr_t{nullptr, mk_string(m)}))
+}
+CFr_t* ffi_get_root(FFI_RLN_t* const* rln) {
+    uint8_t b[32] = {0};
+    try {
+        std::lock_guard<std::mutex> lk((*rln)->r->mu);
+        (*rln)->r->root(b);
+    } catch (...) {
+        abort();  // the reference's get_root is infallible
+    }
+    return mk_cfr(b);
+}
+CResult_FFI_MerkleProof_t ffi_get_merkle_proof(FFI_RLN_t* const* rln, size_t index) {
+    GUARD_BEGIN
+    std::lock_guard<std::mutex> lk((*rln)->r->mu);
+    const size_t d = (*rln)->r->tree_depth();
+    FFI_MerkleProof_t* mp = (FFI_MerkleProof_t*)malloc(sizeof(FFI_MerkleProof_t));
+    mp->path_elements.ptr = (CFr_t*)malloc(32 * d);
+    mp->path_elements.len = mp->path_elements.cap = d;
+    mp->path_index.ptr = (uint8_t*)malloc(d);
+    mp->path_index.len = mp->path_index.cap = d;
+    uint64_t idx = index;
+    try {
+        (*rln)->r->merkle_proofs(&idx, 1, (uint8_t*)mp->path_elements.ptr, mp->path_index.ptr);
+    } catch (...) {
+        free(mp->path_elements.ptr);
+        free(mp->path_index.ptr);
+        free(mp);
+        throw;
+    }
+    return CResult_FFI_MerkleProof_t{mp, no_string()};
+    GUARD_END(return (CResult_FFI_MerkleProof_t{nullptr, mk_string(m)}))
+}
+void ffi_merkle_proof_free(FFI_MerkleProof_t* mp) {
+    if (!mp) return;
+    free(mp->path_elements.ptr);
+    free(mp->path_index.ptr);
+    free(mp);
+}
+
+// ---- witness input ----------------------------------------------------------------------------
+CResult_FFI_RLNWitnessInput_t ffi_rln_witness_input_new_single(const CFr_t* identity_secret, const CFr_t* user_message_limit,
+                                                               const CFr_t* message_id, const Vec_CFr_t* path_elements,
+                                                               const Vec_uint8_t* identity_path_index, const CFr_t* x,
+                                                               const CFr_t* external_nullifier) {
+    GUARD_BEGIN
+    auto w = std::make_unique<FFI_RLNWitnessInput>();
+    memcpy(w->w.secret, identity_secret->bytes, 32);
+    memcpy(w->w.limit, user_message_limit->bytes, 32);
+    memcpy(w->w.message_id, message_id->bytes, 32);
+    memcpy(w->w.x, x->bytes, 32);
+    memcpy(w->w.ext_null, external_nullifier->bytes, 32);
+    w->w.path.assign((const uint8_t*)path_elements->ptr, (const uint8_t*)path_elements->ptr + 32 * path_elements->len);
+    w->w.index.assign(identity_path_index->ptr, identity_path_index->ptr + identity_path_index->len);
+    validate_witness(w->w);
+    return CResult_FFI_RLNWitnessInput_t{w.release(), no_string()};
+    GUARD_END(return (CResult_FFI_RLNWitnessInput_t{nullptr, mk_string(m)}))
+}
+CResult_Vec_uint8_t ffi_rln_witness_to_bytes_le(FFI_RLNWitnessInput_t* const* witness) {
+    std::vector<uint8_t> b = witness_to_bytes((*witness)->w);
+    return CResult_Vec_uint8_t{mk_vec(b.data(), b.size()), no_string()};
+}
+CResult_FFI_RLNWitnessInput_t ffi_bytes_le_to_rln_witness(const Vec_uint8_t* bytes) {
+    GUARD_BEGIN
+    auto w = std::make_unique<FFI_RLNWitnessInput>();
+    witness_from_bytes(bytes->ptr, bytes->len, w->w);
+    return CResult_FFI_RLNWitnessInput_t{w.release(), no_string()};
+    GUARD_END(return (CResult_FFI_RLNWitnessInput_t{nullptr, mk_string(m)}))
+}
+void ffi_rln_witness_input_free(FFI_RLNWitnessInput_t* w) {
+    if (w) memset(w->w.secret, 0, 32);  // IdSecret is zeroised on drop (rln/src/utils.rs:443-527)
+    delete w;
+}
+
+// ---- proving / verifying ----------------------------------------------------------------------
+static CResult_FFI_RLNProof_t prove_one(FFI_RLN_t* const* rln, FFI_RLNWitnessInput_t* const* witness, const uint8_t* rs) {
+    GUARD_BEGIN
+    std::lock_guard<std::mutex> lk((*rln)->r->mu);
+    std::vector<Witness> ws(1, (*witness)->w);
+    std::vector<RlnProof> out;
+    (*rln)->r->prove_host(ws, rs, out);
+    memset(ws[0].secret, 0, 32);
+    auto p = std::make_unique<FFI_RLNProof>();
+    p->p = out[0];
+    return CResult_FFI_RLNProof_t{p.release(), no_string()};
+    GUARD_END(return (CResult_FFI_RLNProof_t{nullptr, mk_string(m)}))
+}
+CResult_FFI_RLNProof_t ffi_generate_rln_proof(FFI_RLN_t* const* rln, FFI_RLNWitnessInput_t* const* witness) {
+    return prove_one(rln, witness, nullptr);
+}
+CResult_FFI_RLNProof_t rlnb200_generate_rln_proof_with_rs(FFI_RLN_t* const* rln, FFI_RLNWitnessInput_t* const* witness, const CFr_t* r,
+                                                          const CFr_t* s) {
+    uint8_t rs[64];
+    memcpy(rs, r->bytes, 32);
+    memcpy(rs + 32, s->bytes, 32);
+    return prove_one(rln, witness, rs);
+}
+
+// verify_zk_proof (proof.rs:856-894) then root / signal checks (public.rs:725-771)
+static CBoolResult_t verify_common(FFI_RLN_t* const* rln, const RlnProof& p, const uint8_t* x, const Vec_CFr_t* roots, bool use_tree_root) {
+    GUARD_BEGIN
+    std::lock_guard<std::mutex> lk((*rln)->r->mu);
+    uint8_t pub[160];  // circuit order [y, root, nullifier, x, external_nullifier] (proof.rs:863-869)
+    memcpy(pub, p.pv.y, 32);
+    memcpy(pub + 32, p.pv.root, 32);
+    memcpy(pub + 64, p.pv.nullifier, 32);
+    memcpy(pub + 96, p.pv.x, 32);
+    memcpy(pub + 128, p.pv.ext_null, 32);
+    uint8_t ok = 0;
+    (*rln)->r->verify_batch(p.proof, pub, 1, &ok);
+    if (ok != 1) throw RlnError("Verification error: Invalid proof provided");
+    if (use_tree_root) {
+        uint8_t root[32];
+        (*rln)->r->root(root);
+        if (memcmp(root, p.pv.root, 32)) throw RlnError("Verification error: Expected one of the provided roots");
+    } else if (roots && roots->len) {
+        bool found = false;
+        for (size_t i = 0; i < roots->len; i++) found = found || !memcmp(roots->ptr[i].bytes, p.pv.root, 32);
+        if (!found) throw RlnError("Verification error: Expected one of the provided roots");
+    }
+    if (memcmp(x, p.pv.x, 32)) throw RlnError("Verification error: Signal value does not match");
+    return CBoolResult_t{true, no_string()};
+    GUARD_END(return (CBoolResult_t{false, mk_string(m)}))
+}
+CBoolResult_t ffi_verify_rln_proof(FFI_RLN_t* const* rln, FFI_RLNProof_t* const* rln_proof, const CFr_t* x) {
+    return verify_common(rln, (*rln_proof)->p, x->bytes, nullptr, true);
+}
+CBoolResult_t ffi_verify_with_roots(FFI_RLN_t* const* rln, FFI_RLNProof_t* const* rln_proof, const Vec_CFr_t* roots, const CFr_t* x) {
+    return verify_common(rln, (*rln_proof)->p, x->bytes, roots, false);
+}
+
+FFI_RLNProofValues_t* ffi_rln_proof_get_values(FFI_RLNProof_t* const* rln_proof) {
+    FFI_RLNProofValues* v = new FFI_RLNProofValues();
+    v->v = (*rln_proof)->p.pv;
+    return v;
+}
+uint8_t ffi_rln_proof_get_version_byte(FFI_RLNProof_t* const* rln_proof) { (void)rln_proof; return 0; }
+CResult_Vec_uint8_t ffi_rln_proof_to_bytes_le(FFI_RLNProof_t* const* rln_proof) {
+    uint8_t b[290];
+    rln_proof_to_bytes((*rln_proof)->p, b);
+    return CResult_Vec_uint8_t{mk_vec(b, 290), no_string()};
+}
+// proof stays LE (arkworks), values big-endian (rln/src/protocol/proof.rs:430-446)
+CResult_Vec_uint8_t ffi_rln_proof_to_bytes_be(FFI_RLNProof_t* const* rln_proof) {
+    uint8_t b[290];
+    rln_proof_to_bytes((*rln_proof)->p, b);
+    for (int i = 0; i < 5; i++) std::reverse(b + 130 + 32 * i, b + 130 + 32 * (i + 1));
+    return CResult_Vec_uint8_t{mk_vec(b, 290), no_string()};
+}
+CResult_FFI_RLNProof_t ffi_bytes_le_to_rln_proof(const Vec_uint8_t* bytes) {
+    GUARD_BEGIN
+    global_init();
+    if (bytes->len == 0) throw RlnError(msg_read_len(1, 0));
+    if (bytes->ptr[0] != 0) {
+        char t[64];
+        snprintf(t, sizeof t, "Unknown message mode version byte: %#04x", bytes->ptr[0]);
+        throw RlnError(t);
+    }
+    if (bytes->len < 129) throw RlnError(msg_read_len(129, bytes->len));
+    auto p = std::make_unique<FFI_RLNProof>();
+    memcpy(p->p.proof, bytes->ptr + 1, 128);
+    {   // Proof::deserialize_compressed validates curve / subgroup membership (proof.rs:469)
+        DevMem dp, da, dok;
+        dp.upload(p->p.proof, 128);
+        da.alloc(256);
+        dok.alloc(1);
+        launch_decompress(dp.as<uint8_t>(), 1, da.as<uint8_t>(), dok.as<uint8_t>(), 0);
+        g_launch_count++;
+        uint8_t ok = 0;
+        ZK_CUDA_CHECK(cudaMemcpy(&ok, dok.p, 1, cudaMemcpyDeviceToHost));
+        if (!ok) throw RlnError("Proof serialization error: the input buffer contained invalid data");
+    }
+    size_t used = 129 + proof_values_from_bytes(bytes->ptr + 129, bytes->len - 129, p->p.pv);
+    if (used != bytes->len) throw RlnError(msg_read_len(used, bytes->len));
+    return CResult_FFI_RLNProof_t{p.release(), no_string()};
+    GUARD_END(return (CResult_FFI_RLNProof_t{nullptr, mk_string(m)}))
+}
+void ffi_rln_proof_free(FFI_RLNProof_t* p) { delete p; }
+
+CFr_t* ffi_rln_proof_values_get_root(FFI_RLNProofValues_t* const* pv) { return mk_cfr((*pv)->v.root); }
+CFr_t* ffi_rln_proof_values_get_x(FFI_RLNProofValues_t* const* pv) { return mk_cfr((*pv)->v.x); }
+CFr_t* ffi_rln_proof_values_get_external_nullifier(FFI_RLNProofValues_t* const* pv) { return mk_cfr((*pv)->v.ext_null); }
+CResult_CFr_t ffi_rln_proof_values_get_y(FFI_RLNProofValues_t* const* pv) { return CResult_CFr_t{mk_cfr((*pv)->v.y), no_string()}; }
+CResult_CFr_t ffi_rln_proof_values_get_nullifier(FFI_RLNProofValues_t* const* pv) { return CResult_CFr_t{mk_cfr((*pv)->v.nullifier), no_string()}; }
+Vec_uint8_t ffi_rln_proof_values_to_bytes_le(FFI_RLNProofValues_t* const* pv) {
+    uint8_t b[161];
+    proof_values_to_bytes((*pv)->v, b);
+    return mk_vec(b, 161);
+}
+CResult_FFI_RLNProofValues_t ffi_bytes_le_to_rln_proof_values(const Vec_uint8_t* bytes) {
+    GUARD_BEGIN
+    auto v = std::make_unique<FFI_RLNProofValues>();
+    size_t used = proof_values_from_bytes(bytes->ptr, bytes->len, v->v);
+    if (used != bytes->len) throw RlnError(msg_read_len(used, bytes->len));
+    return CResult_FFI_RLNProofValues_t{v.release(), no_string()};
+    GUARD_END(return (CResult_FFI_RLNProofValues_t{nullptr, mk_string(m)}))
+}
+void ffi_rln_proof_values_free(FFI_RLNProofValues_t* v) { delete v; }
+
+// ---- CFr / Vec helpers --------------------------------------------------------------------------
+CFr_t* ffi_cfr_zero(void) { uint8_t b[32] = {0}; return mk_cfr(b); }
+CFr_t* ffi_cfr_one(void) { uint8_t b[32] = {1}; return mk_cfr(b); }
+CFr_t* ffi_uint_to_cfr(uint32_t value) { uint8_t b[32] = {0}; memcpy(b, &value, 4); return mk_cfr(b); }
+CResult_Vec_uint8_t ffi_cfr_to_bytes_le(const CFr_t* cfr) { return CResult_Vec_uint8_t{mk_vec(cfr->bytes, 32), no_string()}; }
+CResult_Vec_uint8_t ffi_cfr_to_bytes_be(const CFr_t* cfr) {
+    uint8_t b[32];
+    for (int i = 0; i < 32; i++) b[i] = cfr->bytes[31 - i];
+    return CResult_Vec_uint8_t{mk_vec(b, 32), no_string()};
+}
+CResult_CFr_t ffi_bytes_le_to_cfr(const Vec_uint8_t* bytes) {
+    if (bytes->len < 32) return CResult_CFr_t{nullptr, mk_string("io error: failed to fill whole buffer")};
+    if (!fr_is_canonical(bytes->ptr)) return CResult_CFr_t{nullptr, mk_string("the input buffer contained invalid data")};
+    return CResult_CFr_t{mk_cfr(bytes->ptr), no_string()};
+}
+CResult_CFr_t ffi_bytes_be_to_cfr(const Vec_uint8_t* bytes) {
+    if (bytes->len < 32) return CResult_CFr_t{nullptr, mk_string(msg_read_len(32, bytes->len))};
+    uint8_t b[32];
+    for (int i = 0; i < 32; i++) b[i] = bytes->ptr[31 - i];
+    if (!fr_is_canonical(b)) return CResult_CFr_t{nullptr, mk_string("Non-canonical field element: value is not in [0, r-1]")};
+    return CResult_CFr_t{mk_cfr(b), no_string()};
+}
+RlnString ffi_cfr_debug(const CFr_t* cfr) { return mk_string(cfr ? decimal_le32(cfr->bytes) : std::string("None")); }
+void ffi_cfr_free(CFr_t* cfr) { free(cfr); }
+Vec_CFr_t ffi_vec_cfr_new(size_t capacity) {
+    Vec_CFr_t v;
+    v.len = 0;
+    v.cap = capacity ? capacity : 1;
+    v.ptr = (CFr_t*)malloc(sizeof(CFr_t) * v.cap);
+    return v;
+}
+Vec_CFr_t ffi_vec_cfr_from_cfr(const CFr_t* cfr) {
+    Vec_CFr_t v = ffi_vec_cfr_new(1);
+    v.ptr[0] = *cfr;
+    v.len = 1;
+    return v;
+}
+void ffi_vec_cfr_push(Vec_CFr_t* v, const CFr_t* cfr) {
+    if (v->len == v->cap) {
+        v->cap = v->cap ? v->cap * 2 : 4;
+        v->ptr = (CFr_t*)realloc(v->ptr, sizeof(CFr_t) * v->cap);
+    }
+    v->ptr[v->len++] = *cfr;
+}
+size_t ffi_vec_cfr_len(const Vec_CFr_t* v) { return v->len; }
+const CFr_t* ffi_vec_cfr_get(const Vec_CFr_t* v, size_t i) { return i < v->len ? &v->ptr[i] : nullptr; }
+void ffi_vec_cfr_free(Vec_CFr_t v) { free(v.ptr); }
+void ffi_vec_u8_free(Vec_uint8_t v) { free(v.ptr); }
+void ffi_c_string_free(RlnString s) { free(s.ptr); }
+
+CFr_t* ffi_hash_to_field_le(const Vec_uint8_t* input) {  // hashers.rs:73-81
+    uint8_t h[32];
+    keccak256(input->ptr, input->len, h);
+    fr_reduce(h);
+    return mk_cfr(h);
+}
+CFr_t* ffi_hash_to_field_be(const Vec_uint8_t* input) { return ffi_hash_to_field_le(input); }  // same Fr (hashers.rs:84-93)
+
+static void device_poseidon(const uint8_t* in, int n, uint8_t* out) {
+    global_init();
+    DevMem di, dout;
+    di.upload(in, 32 * (size_t)n);
+    dout.alloc(32);
+    launch_poseidon_n(di.as<uint8_t>(), n, dout.as<uint8_t>(), 0);
+    g_launch_count++;
+    ZK_CUDA_CHECK(cudaMemcpy(out, dout.p, 32, cudaMemcpyDeviceToHost));
+}
+CFr_t* ffi_poseidon_hash_pair(const CFr_t* a, const CFr_t* b) {
+    uint8_t in[64], out[32];
+    memcpy(in, a->bytes, 32);
+    memcpy(in + 32, b->bytes, 32);
+    try {
+        device_poseidon(in, 2, out);
+    } catch (...) {
+        abort();  // the reference's poseidon_hash_pair is infallible
+    }
+    return mk_cfr(out);
+}
+Vec_CFr_t ffi_key_gen(void) {  // keygen (rln/src/protocol/keygen.rs:20-30): secret ← rng, commitment = H(secret)
+    Vec_CFr_t v = ffi_vec_cfr_new(2);
+    random_fr(v.ptr[0].bytes);
+    try {
+        device_poseidon(v.ptr[0].bytes, 1, v.ptr[1].bytes);
+    } catch (...) {
+        abort();
+    }
+    v.len = 2;
+    return v;
+}
+
+// ---- extensions -------------------------------------------------------------------------------
+#define INT_OP(...)                                            \
+    GUARD_BEGIN                                                \
+    __VA_ARGS__;                                               \
+    return 0;                                                  \
+    GUARD_END(if (err) *err = mk_string(m); return -1)
+
+int rlnb200_prove_batch(FFI_RLN_t* const* rln, const uint8_t* witnesses, size_t n, const uint8_t* rs, uint8_t* proofs_out, RlnString* err) {
+    INT_OP(
+        std::lock_guard<std::mutex> lk((*rln)->r->mu);
+        const size_t d = (*rln)->r->depth(), rec = 1 + 32 * (5 + d) + 16 + d;
+        std::vector<Witness> ws(n);
+        for (size_t i = 0; i < n; i++) {
+            size_t used = witness_from_bytes(witnesses + rec * i, rec, ws[i]);
+            if (used != rec) throw RlnError(msg_read_len(used, rec));
+        }
+        std::vector<RlnProof> out;
+        (*rln)->r->prove_host(ws, rs, out);
+        for (auto& w : ws) memset(w.secret, 0, 32);
+        for (size_t i = 0; i < n; i++) rln_proof_to_bytes(out[i], proofs_out + 290 * i);)
+}
+int rlnb200_verify_batch(FFI_RLN_t* const* rln, const uint8_t* proofs, size_t n, uint8_t* ok_out, RlnString* err) {
+    INT_OP(
+        std::lock_guard<std::mutex> lk((*rln)->r->mu);
+        std::vector<uint8_t> p(128 * n), pub(160 * n);
+        for (size_t i = 0; i < n; i++) {
+            const uint8_t* b = proofs + 290 * i;
+            memcpy(p.data() + 128 * i, b + 1, 128);
+            const uint8_t* v = b + 130;  // root | ext_null | x | y | nullifier
+            uint8_t* o = pub.data() + 160 * i;
+            memcpy(o, v + 96, 32); memcpy(o + 32, v, 32); memcpy(o + 64, v + 128, 32); memcpy(o + 96, v + 64, 32); memcpy(o + 128, v + 32, 32);
+        }
+        (*rln)->r->verify_batch(p.data(), pub.data(), n, ok_out);)
+}
+int rlnb200_prove_batch_device(FFI_RLN_t* const* rln, const void* d_inputs, const void* d_rs, size_t n, void* d_proofs, void* d_values,
+                               void* d_affine, void* stream, RlnString* err) {
+    INT_OP(std::lock_guard<std::mutex> lk((*rln)->r->mu);
+           (*rln)->r->prove_device((const uint8_t*)d_inputs, (const uint8_t*)d_rs, n, (uint8_t*)d_proofs, (uint8_t*)d_values, (uint8_t*)d_affine,
+                                   (cudaStream_t)stream);)
+}
+int rlnb200_witness_to_input_slots(FFI_RLN_t* const* rln, const uint8_t* witness_le, size_t len, uint8_t* slots_out, RlnString* err) {
+    INT_OP(Witness w; witness_from_bytes(witness_le, len, w);
+           if (w.path.size() / 32 != (*rln)->r->depth() || w.index.size() != (*rln)->r->depth()) throw RlnError("Protocol error: witness depth does not match the circuit");
+           (*rln)->r->witness_slots(w, slots_out);)
+}
+size_t rlnb200_input_slots(FFI_RLN_t* const* rln) { return (*rln)->r->n_slots(); }
+int rlnb200_input_slot(FFI_RLN_t* const* rln, const char* name, uint32_t* offset, uint32_t* len) {
+    auto& m = (*rln)->r->graph().inputs;
+    auto it = m.find(name);
+    if (it == m.end()) return 0;
+    *offset = it->second.first;
+    *len = it->second.second;
+    return 1;
+}
+int rlnb200_reserve(FFI_RLN_t* const* rln, size_t max_batch, RlnString* err) {
+    INT_OP(std::lock_guard<std::mutex> lk((*rln)->r->mu); (*rln)->r->reserve(max_batch);)
+}
+uint64_t rlnb200_launch_count(void) { return g_launch_count.load(); }
+void rlnb200_last_stage_ms(FFI_RLN_t* const* rln, float out[4]) {
+    for (int i = 0; i < 4; i++) out[i] = (*rln)->r->stage_ms[i];
+}
+int rlnb200_set_leaves_from_bytes(FFI_RLN_t** rln, size_t index, const uint8_t* leaves_le, size_t count, RlnString* err) {
+    INT_OP(std::lock_guard<std::mutex> lk((*rln)->r->mu); (*rln)->r->set_range_host(index, leaves_le, count);)
+}
+int rlnb200_set_leaves_from_device(FFI_RLN_t** rln, size_t index, const void* d_leaves, size_t count, void* stream, RlnString* err) {
+    INT_OP(std::lock_guard<std::mutex> lk((*rln)->r->mu); (*rln)->r->set_range_device(index, (const uint8_t*)d_leaves, count, (cudaStream_t)stream);)
+}
+int rlnb200_get_merkle_proofs(FFI_RLN_t* const* rln, const uint64_t* indices, size_t n, uint8_t* elements_out, uint8_t* index_bits_out, RlnString* err) {
+    INT_OP(std::lock_guard<std::mutex> lk((*rln)->r->mu); (*rln)->r->merkle_proofs(indices, n, elements_out, index_bits_out);)
+}
+int rlnb200_debug_witness_and_h(FFI_RLN_t* const* rln, const uint8_t* witness_le, size_t len, uint8_t* w_out, uint8_t* h_out, RlnString* err) {
+    INT_OP(std::lock_guard<std::mutex> lk((*rln)->r->mu); Witness w; witness_from_bytes(witness_le, len, w); (*rln)->r->debug_w_h(w, w_out, h_out);)
+}
+size_t rlnb200_num_wires(FFI_RLN_t* const* rln) { return (*rln)->r->n_wires(); }
+size_t rlnb200_domain_size(FFI_RLN_t* const* rln) { return (*rln)->r->domain(); }
+
+RlnB200Msm_t* rlnb200_msm_new(size_t max_n, RlnString* err) {
+    GUARD_BEGIN
+    global_init();
+    auto m = std::make_unique<RlnB200Msm>();
+    m->ws = var_msm_workspace_create(max_n);
+    m->max_n = max_n;
+    return m.release();
+    GUARD_END(if (err) *err = mk_string(m); return nullptr)
+}
+void rlnb200_msm_free(RlnB200Msm_t* m) {
+    if (!m) return;
+    var_msm_workspace_destroy(m->ws);
+    delete m;
+}
+int rlnb200_msm_upload_bases(RlnB200Msm_t* m, const uint8_t* bases, size_t n, void* d_bases_out, RlnString* err) {
+    (void)m;
+    INT_OP(DevMem raw; raw.upload(bases, 64 * n); launch_g1_from_bytes(raw.as<uint8_t>(), (G1Affine*)d_bases_out, n, 0); g_launch_count++;
+           ZK_CUDA_CHECK(cudaDeviceSynchronize());)
+}
+int rlnb200_msm_gen_bases(RlnB200Msm_t* m, const void* d_scalars, size_t n, void* d_bases_out, void* stream, RlnString* err) {
+    (void)m;
+    INT_OP(launch_g1_mul_gen((const uint8_t*)d_scalars, (G1Affine*)d_bases_out, n, (cudaStream_t)stream); g_launch_count++;)
+}
+int rlnb200_msm_g1_device(RlnB200Msm_t* m, const void* d_bases, const void* d_scalars, size_t n, void* d_result, void* stream, RlnString* err) {
+    INT_OP(launch_var_msm_g1(m->ws, (const G1Affine*)d_bases, (const uint8_t*)d_scalars, n, (uint8_t*)d_result, (cudaStream_t)stream); g_launch_count += 9;)
+}
+int rlnb200_msm_g1(RlnB200Msm_t* m, const uint8_t* bases, const uint8_t* scalars, size_t n, uint8_t* result, RlnString* err) {
+    INT_OP(DevMem raw, db, ds, dr; raw.upload(bases, 64 * n); db.alloc(sizeof(G1Affine) * n); ds.upload(scalars, 32 * n); dr.alloc(64);
+           launch_g1_from_bytes(raw.as<uint8_t>(), db.as<G1Affine>(), n, 0);
+           launch_var_msm_g1(m->ws, db.as<G1Affine>(), ds.as<uint8_t>(), n, dr.as<uint8_t>(), 0); g_launch_count += 10;
+           ZK_CUDA_CHECK(cudaMemcpy(result, dr.p, 64, cudaMemcpyDeviceToHost));)
+}
+
+int rlnb200_poseidon_hash(const uint8_t* inputs, int n_inputs, uint8_t* out32, RlnString* err) {
+    INT_OP(if (n_inputs < 1 || n_inputs > 3) throw RlnError("Input length must be valid with supported round parameters");
+           device_poseidon(inputs, n_inputs, out32);)
+}
+int rlnb200_hash_pairs(const uint8_t* pairs, size_t n, uint8_t* out, RlnString* err) {
+    INT_OP(global_init(); DevMem raw, in, res, outb; raw.upload(pairs, 64 * n); in.alloc(sizeof(Fr) * 2 * n); res.alloc(sizeof(Fr) * n); outb.alloc(32 * n);
+           launch_fr_from_bytes(raw.as<uint8_t>(), in.as<Fr>(), 2 * n, 0); launch_hash_pairs(in.as<Fr>(), res.as<Fr>(), n, 0);
+           launch_fr_to_bytes(res.as<Fr>(), outb.as<uint8_t>(), n, 0); g_launch_count += 3;
+           ZK_CUDA_CHECK(cudaMemcpy(out, outb.p, 32 * n, cudaMemcpyDeviceToHost));)
+}
+int rlnb200_field_op(int field, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out, RlnString* err);  // k_selftest.cu
+
+}  // extern "C"

@@ -1,0 +1,128 @@
+// Fq6 / Fq12 tower and the optimal-ate pairing on BN254 for Groth16 verification on the device
+// (one proof per thread).  Replaces ark-groth16 0.5.0 `prepare_verifying_key` + `verify_proof`
+// as called from rln/src/protocol/proof.rs:856-894 (Cargo.lock:172; ark-ec pairing engine).
+//
+// Tower: Fq2 = Fq[u]/(u²+1), Fq6 = Fq2[v]/(v³−ξ), Fq12 = Fq6[w]/(w²−v), ξ = 9+u.
+// The running point of the Miller loop stays affine on the twist E'(Fq2): y² = x³ + 3/ξ; a line
+// through R with slope λ evaluated at P ∈ G1 is  −yP + (λ·xP)·w + (yR − λ·xR)·w³.
+#pragma once
+#include "curve.cuh"
+
+namespace zk {
+
+struct Fq6 {
+    Fq2 c0, c1, c2;
+    static HD Fq6 zero() { return {Fq2::zero(), Fq2::zero(), Fq2::zero()}; }
+    static HD Fq6 one() { return {Fq2::one(), Fq2::zero(), Fq2::zero()}; }
+    HD bool operator==(const Fq6& o) const { return c0 == o.c0 && c1 == o.c1 && c2 == o.c2; }
+    HD Fq6 operator+(const Fq6& o) const { return {c0 + o.c0, c1 + o.c1, c2 + o.c2}; }
+    HD Fq6 operator-(const Fq6& o) const { return {c0 - o.c0, c1 - o.c1, c2 - o.c2}; }
+    HD Fq6 neg() const { return {c0.neg(), c1.neg(), c2.neg()}; }
+    HDN Fq6 operator*(const Fq6& o) const {
+        Fq2 t0 = c0 * o.c0, t1 = c1 * o.c1, t2 = c2 * o.c2;
+        Fq2 r0 = ((c1 + c2) * (o.c1 + o.c2) - t1 - t2).mul_xi() + t0;
+        Fq2 r1 = (c0 + c1) * (o.c0 + o.c1) - t0 - t1 + t2.mul_xi();
+        Fq2 r2 = (c0 + c2) * (o.c0 + o.c2) - t0 - t2 + t1;
+        return {r0, r1, r2};
+    }
+    HD Fq6 mul_v() const { return {c2.mul_xi(), c0, c1}; }
+    HDN Fq6 inv() const {
+        Fq2 A = c0.sqr() - (c1 * c2).mul_xi();
+        Fq2 B = c2.sqr().mul_xi() - c0 * c1;
+        Fq2 C = c1.sqr() - c0 * c2;
+        Fq2 Fi = ((c2 * B + c1 * C).mul_xi() + c0 * A).inv();
+        return {A * Fi, B * Fi, C * Fi};
+    }
+};
+
+struct Fq12 {
+    Fq6 c0, c1;
+    static HD Fq12 one() { return {Fq6::one(), Fq6::zero()}; }
+    HD bool operator==(const Fq12& o) const { return c0 == o.c0 && c1 == o.c1; }
+    HDN Fq12 operator*(const Fq12& o) const {
+        Fq6 t0 = c0 * o.c0, t1 = c1 * o.c1;
+        Fq6 r1 = (c0 + c1) * (o.c0 + o.c1) - t0 - t1;
+        return {t0 + t1.mul_v(), r1};
+    }
+    HDN Fq12 sqr() const {  // complex squaring
+        Fq6 ab = c0 * c1;
+        Fq6 t = (c0 + c1) * (c0 + c1.mul_v()) - ab - ab.mul_v();
+        return {t, ab + ab};
+    }
+    HD Fq12 conj() const { return {c0, c1.neg()}; }
+    HDN Fq12 inv() const {
+        Fq6 d = (c0 * c0 - (c1 * c1).mul_v()).inv();
+        return {c0 * d, (c1 * d).neg()};
+    }
+};
+
+// Constants that depend only on q (computed once on the host, see pairing_tables_init in host code)
+struct PairingTables {
+    Fq2 gamma2;    // ξ^((q−1)/3)
+    Fq2 gamma3;    // ξ^((q−1)/2)
+    Fq frob2[6];   // ξ^(k(q²−1)/6), k = 0..5 (lie in Fq)
+    u32 hard[24];  // (q⁴ − q² + 1)/r, little-endian words (761 bits)
+};
+
+HD Fq12 line_eval(const Fq2& lam, const G2Affine& R, const G1Affine& P) {
+    Fq12 l;
+    l.c0 = {Fq2{P.y.neg(), Fq::zero()}, Fq2::zero(), Fq2::zero()};
+    l.c1 = {lam.scale(P.x), R.y - lam * R.x, Fq2::zero()};
+    return l;
+}
+
+// Miller loop f_{6x+2,Q}(P)·(Frobenius correction lines); no final exponentiation.
+HDN Fq12 miller_loop(const PairingTables* pt, const G2Affine& Qp, const G1Affine& P) {
+    if (Qp.is_inf() || P.is_inf()) return Fq12::one();
+    const u64 ATE_LOW = 0x9d797039be763ba8ULL;  // 6x+2 = 2^64 + ATE_LOW
+    G2Affine R = Qp;
+    Fq12 f = Fq12::one();
+    for (int i = 63; i >= 0; i--) {
+        {  // doubling step
+            Fq2 xx = R.x.sqr();
+            Fq2 lam = (xx.dbl() + xx) * R.y.dbl().inv();
+            f = f.sqr() * line_eval(lam, R, P);
+            Fq2 x3 = lam.sqr() - R.x.dbl();
+            R.y = lam * (R.x - x3) - R.y;
+            R.x = x3;
+        }
+        if ((ATE_LOW >> i) & 1) {
+            Fq2 lam = (Qp.y - R.y) * (Qp.x - R.x).inv();
+            f = f * line_eval(lam, R, P);
+            Fq2 x3 = lam.sqr() - R.x - Qp.x;
+            R.y = lam * (R.x - x3) - R.y;
+            R.x = x3;
+        }
+    }
+    G2Affine Q1 = {Qp.x.conj() * pt->gamma2, Qp.y.conj() * pt->gamma3};
+    G2Affine Q2 = {Q1.x.conj() * pt->gamma2, (Q1.y.conj() * pt->gamma3).neg()};
+    for (int k = 0; k < 2; k++) {
+        const G2Affine& S = k == 0 ? Q1 : Q2;
+        Fq2 lam = (S.y - R.y) * (S.x - R.x).inv();
+        f = f * line_eval(lam, R, P);
+        Fq2 x3 = lam.sqr() - R.x - S.x;
+        R.y = lam * (R.x - x3) - R.y;
+        R.x = x3;
+    }
+    return f;
+}
+
+HDN Fq12 frobenius2(const PairingTables* pt, const Fq12& f) {
+    Fq12 r;  // coefficient of w^k is scaled by frob2[k]; c0 = (w⁰,w²,w⁴), c1 = (w¹,w³,w⁵)
+    r.c0 = {f.c0.c0, f.c0.c1.scale(pt->frob2[2]), f.c0.c2.scale(pt->frob2[4])};
+    r.c1 = {f.c1.c0.scale(pt->frob2[1]), f.c1.c1.scale(pt->frob2[3]), f.c1.c2.scale(pt->frob2[5])};
+    return r;
+}
+
+HDN Fq12 final_exponentiation(const PairingTables* pt, const Fq12& f) {
+    Fq12 t = f.conj() * f.inv();      // ^(q⁶−1)
+    t = frobenius2(pt, t) * t;        // ^(q²+1)
+    Fq12 r = Fq12::one();             // ^((q⁴−q²+1)/r)
+    for (int i = 24 * 32 - 1; i >= 0; i--) {
+        r = r.sqr();
+        if ((pt->hard[i >> 5] >> (i & 31)) & 1) r = r * t;
+    }
+    return r;
+}
+
+}  // namespace zk

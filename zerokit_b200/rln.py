@@ -1,0 +1,418 @@
+"""Python mirror of the reference's public API for the hot path, over the C ABI of librln_b200.so.
+
+Method names, argument meaning and error behaviour follow `rln::public::RLN`
+(rln/src/public.rs:65-771): new / new_with_params, set_tree, set_leaf, get_leaf, set_next_leaf,
+delete_leaf, leaves_set, set_leaves_from, init_tree_with_leaves, atomic_operation, get_root,
+get_merkle_proof, generate_rln_proof, verify_rln_proof, verify_with_roots — so that tests read like
+rln/tests/{public,protocol,ffi}.rs.  Field elements are Python ints in [0, r).
+All computation happens in the CUDA library; this file only marshals bytes.
+"""
+import ctypes
+from ctypes import POINTER, byref, c_uint8, c_uint32, c_void_p, cast
+
+from . import ffi
+from .ffi import CFr, Vec_CFr, Vec_size, Vec_uint8
+
+R = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+DEFAULT_TREE_DEPTH = 20  # rln/src/circuit/mod.rs:81
+
+
+class RLNError(Exception):
+    """carries the reference's Display string of the error"""
+
+
+def _take_string(s):
+    if not s.ptr:
+        return None
+    msg = ctypes.string_at(s.ptr, s.len).decode("utf-8", "replace")
+    ffi.lib().ffi_c_string_free(s)
+    return msg
+
+
+def _cfr(v):
+    c = CFr()
+    ctypes.memmove(c.bytes, (int(v) % (1 << 256)).to_bytes(32, "little"), 32)
+    return c
+
+
+def _cfr_int(c):
+    return int.from_bytes(bytes(c.bytes), "little")
+
+
+def _take_cfr(p):
+    v = _cfr_int(p.contents)
+    ffi.lib().ffi_cfr_free(p)
+    return v
+
+
+def _vec_cfr(vals):
+    n = len(vals)
+    arr = (CFr * max(n, 1))()
+    for i, v in enumerate(vals):
+        ctypes.memmove(arr[i].bytes, (int(v) % (1 << 256)).to_bytes(32, "little"), 32)
+    v = Vec_CFr(cast(arr, POINTER(CFr)), n, n)
+    v._keep = arr
+    return v
+
+
+def _vec_u8(b):
+    b = bytes(b)
+    arr = (c_uint8 * max(len(b), 1)).from_buffer_copy(b or b"\0")
+    v = Vec_uint8(cast(arr, POINTER(c_uint8)), len(b), len(b))
+    v._keep = arr
+    return v
+
+
+def _take_vec_u8(v):
+    out = ctypes.string_at(v.ptr, v.len) if v.ptr else b""
+    if v.ptr:
+        ffi.lib().ffi_vec_u8_free(v)
+    return out
+
+
+def _check_bool(res):
+    msg = _take_string(res.err)
+    if msg is not None:
+        raise RLNError(msg)
+    return bool(res.ok)
+
+
+def _check_ptr(res):
+    msg = _take_string(res.err)
+    if msg is not None or not res.ok:
+        raise RLNError(msg or "null result")
+    return res.ok
+
+
+def _check_int(rc, err):
+    if rc != 0:
+        raise RLNError(_take_string(err) or f"error {rc}")
+
+
+# ------------------------------------------------------------------------------- free functions
+def hash_to_field_le(data: bytes) -> int:
+    """rln/src/hashers.rs:73-81"""
+    return _take_cfr(ffi.lib().ffi_hash_to_field_le(byref(_vec_u8(data))))
+
+
+def hash_to_field_be(data: bytes) -> int:
+    return _take_cfr(ffi.lib().ffi_hash_to_field_be(byref(_vec_u8(data))))
+
+
+def poseidon_hash_pair(a: int, b: int) -> int:
+    """rln/src/hashers.rs:49-53 (runs on the GPU)"""
+    return _take_cfr(ffi.lib().ffi_poseidon_hash_pair(byref(_cfr(a)), byref(_cfr(b))))
+
+
+def poseidon_hash(inputs) -> int:
+    """rln/src/hashers.rs:32-36 for 1..3 inputs"""
+    buf = b"".join((int(v) % R).to_bytes(32, "little") for v in inputs)
+    out = ctypes.create_string_buffer(32)
+    err = ffi.RlnString()
+    _check_int(ffi.lib().rlnb200_poseidon_hash(buf, len(inputs), out, byref(err)), err)
+    return int.from_bytes(out.raw, "little")
+
+
+def keygen():
+    v = ffi.lib().ffi_key_gen()
+    out = (_cfr_int(v.ptr[0]), _cfr_int(v.ptr[1]))
+    ffi.lib().ffi_vec_cfr_free(v)
+    return out
+
+
+# ------------------------------------------------------------------------------- value types
+class RLNWitnessInput:
+    """rln/src/protocol/witness.rs:52-113 (single message id)"""
+
+    def __init__(self, handle):
+        self._h = c_void_p(handle)
+
+    @classmethod
+    def new_single(cls, identity_secret, user_message_limit, message_id, path_elements, identity_path_index, x, external_nullifier):
+        res = ffi.lib().ffi_rln_witness_input_new_single(
+            byref(_cfr(identity_secret)), byref(_cfr(user_message_limit)), byref(_cfr(message_id)),
+            byref(_vec_cfr(path_elements)), byref(_vec_u8(bytes(identity_path_index))), byref(_cfr(x)), byref(_cfr(external_nullifier)))
+        return cls(_check_ptr(res))
+
+    @classmethod
+    def from_bytes_le(cls, data):
+        return cls(_check_ptr(ffi.lib().ffi_bytes_le_to_rln_witness(byref(_vec_u8(data)))))
+
+    def to_bytes_le(self):
+        res = ffi.lib().ffi_rln_witness_to_bytes_le(byref(self._h))
+        msg = _take_string(res.err)
+        if msg:
+            raise RLNError(msg)
+        return _take_vec_u8(res.ok)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            ffi.lib().ffi_rln_witness_input_free(self._h)
+            self._h = c_void_p(None)
+
+
+class RLNProofValues:
+    """rln/src/protocol/proof.rs:100-190"""
+
+    def __init__(self, root, external_nullifier, x, y, nullifier):
+        self.root, self.external_nullifier, self.x, self.y, self.nullifier = root, external_nullifier, x, y, nullifier
+
+    def public_inputs(self):
+        """circuit order used by the verifier (proof.rs:863-869)"""
+        return [self.y, self.root, self.nullifier, self.x, self.external_nullifier]
+
+
+class RLNProof:
+    """rln/src/protocol/proof.rs RLNProof { proof, proof_values } behind FFI_RLNProof"""
+
+    def __init__(self, handle):
+        self._h = c_void_p(handle)
+
+    @classmethod
+    def from_bytes_le(cls, data):
+        return cls(_check_ptr(ffi.lib().ffi_bytes_le_to_rln_proof(byref(_vec_u8(data)))))
+
+    def to_bytes_le(self):
+        res = ffi.lib().ffi_rln_proof_to_bytes_le(byref(self._h))
+        msg = _take_string(res.err)
+        if msg:
+            raise RLNError(msg)
+        return _take_vec_u8(res.ok)
+
+    def to_bytes_be(self):
+        res = ffi.lib().ffi_rln_proof_to_bytes_be(byref(self._h))
+        return _take_vec_u8(res.ok)
+
+    @property
+    def proof_bytes(self):
+        """the 128-byte ark-compressed Groth16 proof"""
+        return self.to_bytes_le()[1:129]
+
+    @property
+    def values(self):
+        L = ffi.lib()
+        pv = c_void_p(L.ffi_rln_proof_get_values(byref(self._h)))
+        try:
+            root = _take_cfr(L.ffi_rln_proof_values_get_root(byref(pv)))
+            x = _take_cfr(L.ffi_rln_proof_values_get_x(byref(pv)))
+            en = _take_cfr(L.ffi_rln_proof_values_get_external_nullifier(byref(pv)))
+            y = _take_cfr(L.ffi_rln_proof_values_get_y(byref(pv)).ok)
+            nul = _take_cfr(L.ffi_rln_proof_values_get_nullifier(byref(pv)).ok)
+        finally:
+            L.ffi_rln_proof_values_free(pv)
+        return RLNProofValues(root, en, x, y, nul)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            ffi.lib().ffi_rln_proof_free(self._h)
+            self._h = c_void_p(None)
+
+
+# ------------------------------------------------------------------------------- the RLN object
+class RLN:
+    """rln::public::RLN (rln/src/public.rs:65-771) backed by the GPU library"""
+
+    def __init__(self, handle):
+        self._h = c_void_p(handle)
+
+    @classmethod
+    def new(cls, tree_depth=DEFAULT_TREE_DEPTH, config_path=""):
+        """public.rs:110-128 via ffi_rln_new (bundled zkey/graph of that depth)"""
+        return cls(_check_ptr(ffi.lib().ffi_rln_new(tree_depth, config_path.encode())))
+
+    @classmethod
+    def new_with_params(cls, tree_depth, zkey: bytes, graph: bytes, config_path=""):
+        """public.rs:184-209"""
+        return cls(_check_ptr(ffi.lib().ffi_rln_new_with_params(tree_depth, byref(_vec_u8(zkey)), byref(_vec_u8(graph)), config_path.encode())))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            ffi.lib().ffi_rln_free(self._h)
+            self._h = c_void_p(None)
+
+    # ---- tree ------------------------------------------------------------------------------
+    def tree_depth(self):
+        return ffi.lib().ffi_rln_get_tree_depth(byref(self._h))
+
+    def set_tree(self, tree_depth):
+        _check_bool(ffi.lib().ffi_set_tree(byref(self._h), tree_depth))
+
+    def set_leaf(self, index, leaf):
+        _check_bool(ffi.lib().ffi_set_leaf(byref(self._h), index, byref(_cfr(leaf))))
+
+    def get_leaf(self, index):
+        res = ffi.lib().ffi_get_leaf(byref(self._h), index)
+        msg = _take_string(res.err)
+        if msg:
+            raise RLNError(msg)
+        return _take_cfr(res.ok)
+
+    def set_next_leaf(self, leaf):
+        _check_bool(ffi.lib().ffi_set_next_leaf(byref(self._h), byref(_cfr(leaf))))
+
+    def delete_leaf(self, index):
+        _check_bool(ffi.lib().ffi_delete_leaf(byref(self._h), index))
+
+    def leaves_set(self):
+        return ffi.lib().ffi_leaves_set(byref(self._h))
+
+    def set_leaves_from(self, index, leaves):
+        _check_bool(ffi.lib().ffi_set_leaves_from(byref(self._h), index, byref(_vec_cfr(leaves))))
+
+    def init_tree_with_leaves(self, leaves):
+        _check_bool(ffi.lib().ffi_init_tree_with_leaves(byref(self._h), byref(_vec_cfr(leaves))))
+
+    def atomic_operation(self, index, leaves, indices):
+        arr = (ctypes.c_size_t * max(len(indices), 1))(*indices)
+        vs = Vec_size(cast(arr, POINTER(ctypes.c_size_t)), len(indices), len(indices))
+        _check_bool(ffi.lib().ffi_atomic_operation(byref(self._h), index, byref(_vec_cfr(leaves)), byref(vs)))
+
+    def get_root(self):
+        return _take_cfr(ffi.lib().ffi_get_root(byref(self._h)))
+
+    def get_merkle_proof(self, index):
+        """→ (path_elements, identity_path_index), leaf→root, bits LSB-first (public.rs:550-556)"""
+        res = ffi.lib().ffi_get_merkle_proof(byref(self._h), index)
+        msg = _take_string(res.err)
+        if msg:
+            raise RLNError(msg)
+        mp = res.ok.contents
+        elems = [_cfr_int(mp.path_elements.ptr[i]) for i in range(mp.path_elements.len)]
+        bits = [mp.path_index.ptr[i] for i in range(mp.path_index.len)]
+        ffi.lib().ffi_merkle_proof_free(res.ok)
+        return elems, bits
+
+    # bulk extensions
+    def set_leaves_from_bytes(self, index, leaves_le: bytes):
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_set_leaves_from_bytes(byref(self._h), index, leaves_le, len(leaves_le) // 32, byref(err)), err)
+
+    def set_leaves_from_device(self, index, d_ptr, count, stream=0):
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_set_leaves_from_device(byref(self._h), index, c_void_p(d_ptr), count, c_void_p(stream), byref(err)), err)
+
+    def get_merkle_proofs(self, indices):
+        """→ (elements bytes n*depth*32, bits bytes n*depth)"""
+        n, d = len(indices), self.tree_depth_state
+        idx = (ctypes.c_uint64 * max(n, 1))(*indices)
+        el = ctypes.create_string_buffer(32 * n * d)
+        bits = ctypes.create_string_buffer(max(n * d, 1))
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_get_merkle_proofs(byref(self._h), idx, n, el, bits, byref(err)), err)
+        return el.raw, bits.raw[:n * d]
+
+    tree_depth_state = DEFAULT_TREE_DEPTH  # depth of the stateful tree; set by callers that use set_tree
+
+    # ---- proving / verifying -----------------------------------------------------------------
+    def generate_rln_proof(self, witness: RLNWitnessInput) -> RLNProof:
+        """public.rs:624-631"""
+        return RLNProof(_check_ptr(ffi.lib().ffi_generate_rln_proof(byref(self._h), byref(witness._h))))
+
+    def generate_rln_proof_with_rs(self, witness: RLNWitnessInput, r: int, s: int) -> RLNProof:
+        """generate_zk_proof_with_rs (rln/src/protocol/proof.rs:753-777) behind the ABI"""
+        return RLNProof(_check_ptr(ffi.lib().rlnb200_generate_rln_proof_with_rs(byref(self._h), byref(witness._h), byref(_cfr(r)), byref(_cfr(s)))))
+
+    def verify_rln_proof(self, proof: RLNProof, x: int) -> bool:
+        """public.rs:725-745 — raises RLNError with the reference's reason on failure"""
+        return _check_bool(ffi.lib().ffi_verify_rln_proof(byref(self._h), byref(proof._h), byref(_cfr(x))))
+
+    def verify_with_roots(self, proof: RLNProof, x: int, roots) -> bool:
+        """public.rs:750-771"""
+        return _check_bool(ffi.lib().ffi_verify_with_roots(byref(self._h), byref(proof._h), byref(_vec_cfr(roots)), byref(_cfr(x))))
+
+    def prove_batch(self, witnesses_le: bytes, n: int, rs: bytes = None) -> bytes:
+        """n witness records (rln_witness_to_bytes_le) → n × 290-byte rln_proof_to_bytes_le records"""
+        out = ctypes.create_string_buffer(290 * n)
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_prove_batch(byref(self._h), witnesses_le, n, rs, out, byref(err)), err)
+        return out.raw
+
+    def verify_batch(self, proofs_le: bytes, n: int):
+        ok = ctypes.create_string_buffer(max(n, 1))
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_verify_batch(byref(self._h), proofs_le, n, ok, byref(err)), err)
+        return list(ok.raw[:n])
+
+    def prove_batch_device(self, d_inputs, d_rs, n, d_proofs, d_values=0, d_affine=0, stream=0):
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_prove_batch_device(byref(self._h), c_void_p(d_inputs), c_void_p(d_rs), n, c_void_p(d_proofs),
+                                                        c_void_p(d_values), c_void_p(d_affine), c_void_p(stream), byref(err)), err)
+
+    def witness_to_input_slots(self, witness_le: bytes) -> bytes:
+        out = ctypes.create_string_buffer(32 * self.input_slots())
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_witness_to_input_slots(byref(self._h), witness_le, len(witness_le), out, byref(err)), err)
+        return out.raw
+
+    def input_slots(self):
+        return ffi.lib().rlnb200_input_slots(byref(self._h))
+
+    def input_slot(self, name):
+        off, ln = c_uint32(), c_uint32()
+        if not ffi.lib().rlnb200_input_slot(byref(self._h), name.encode(), byref(off), byref(ln)):
+            raise KeyError(name)
+        return off.value, ln.value
+
+    def reserve(self, max_batch):
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_reserve(byref(self._h), max_batch, byref(err)), err)
+
+    def last_stage_ms(self):
+        out = (ctypes.c_float * 4)()
+        ffi.lib().rlnb200_last_stage_ms(byref(self._h), out)
+        return dict(zip(("witness", "qap", "msm_assemble", "values"), list(out)))
+
+    def debug_witness_and_h(self, witness_le: bytes):
+        nw, dom = ffi.lib().rlnb200_num_wires(byref(self._h)), ffi.lib().rlnb200_domain_size(byref(self._h))
+        w = ctypes.create_string_buffer(32 * nw)
+        h = ctypes.create_string_buffer(32 * dom)
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_debug_witness_and_h(byref(self._h), witness_le, len(witness_le), w, h, byref(err)), err)
+        return w.raw, h.raw
+
+
+class G1Msm:
+    """variable-base G1 MSM (rln/src/partial_proof.rs:98-104 `msm`)"""
+
+    def __init__(self, max_n):
+        err = ffi.RlnString()
+        self._h = c_void_p(ffi.lib().rlnb200_msm_new(max_n, byref(err)))
+        if not self._h.value:
+            raise RLNError(_take_string(err) or "msm_new failed")
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            ffi.lib().rlnb200_msm_free(self._h)
+            self._h = c_void_p(None)
+
+    def msm(self, bases: bytes, scalars: bytes, n: int) -> bytes:
+        out = ctypes.create_string_buffer(64)
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_msm_g1(self._h, bases, scalars, n, out, byref(err)), err)
+        return out.raw
+
+    def gen_bases(self, d_scalars, n, d_bases_out, stream=0):
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_msm_gen_bases(self._h, c_void_p(d_scalars), n, c_void_p(d_bases_out), c_void_p(stream), byref(err)), err)
+
+    def upload_bases(self, bases: bytes, n, d_bases_out):
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_msm_upload_bases(self._h, bases, n, c_void_p(d_bases_out), byref(err)), err)
+
+    def msm_device(self, d_bases, d_scalars, n, d_result, stream=0):
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_msm_g1_device(self._h, c_void_p(d_bases), c_void_p(d_scalars), n, c_void_p(d_result), c_void_p(stream), byref(err)), err)
+
+
+def field_op(field, op, a_bytes, b_bytes, n):
+    out = ctypes.create_string_buffer(32 * n)
+    err = ffi.RlnString()
+    _check_int(ffi.lib().rlnb200_field_op(field, op, a_bytes, b_bytes, n, out, byref(err)), err)
+    return out.raw
+
+
+def hash_pairs(pairs_bytes, n):
+    out = ctypes.create_string_buffer(32 * n)
+    err = ffi.RlnString()
+    _check_int(ffi.lib().rlnb200_hash_pairs(pairs_bytes, n, out, byref(err)), err)
+    return out.raw
