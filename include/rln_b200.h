@@ -170,6 +170,8 @@ int rlnb200_prove_batch_device(FFI_RLN_t *const *rln, const void *d_inputs, cons
 int rlnb200_witness_to_input_slots(FFI_RLN_t *const *rln, const uint8_t *witness_le, size_t len, uint8_t *slots_out,
                                    RlnString *err);
 size_t rlnb200_input_slots(FFI_RLN_t *const *rln);
+/* depth of the stateful Merkle tree (differs from the circuit depth only after ffi_set_tree) */
+size_t rlnb200_state_tree_depth(FFI_RLN_t *const *rln);
 /* offset/len of a named circuit input ("identitySecret", "pathElements", …); returns 0 if unknown */
 int rlnb200_input_slot(FFI_RLN_t *const *rln, const char *name, uint32_t *offset, uint32_t *len);
 /* reserve workspace for batches of up to max_batch proofs (otherwise grown on demand) */

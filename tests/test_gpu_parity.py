@@ -1,0 +1,293 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle on the same
+seeded inputs, against the committed golden fixtures, and through size-independent properties."""
+import hashlib
+import os
+import random
+
+import pytest
+
+from common import Q, R, fr_bytes, fr_stream, ints, kat_witness_args, resource, witness_le
+
+pytestmark = pytest.mark.gpu
+
+os.environ.setdefault("RLN_B200_WINDOW_BITS", "8")  # small tables: the tests are about exactness, not speed
+
+
+@pytest.fixture(scope="module")
+def z():
+    import zerokit_b200
+    return zerokit_b200
+
+
+@pytest.fixture(scope="module")
+def rln20(z):
+    return z.RLN.new(20)
+
+
+@pytest.fixture(scope="module")
+def rln10(z):
+    return z.RLN.new(10)
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import cref_binding as C
+    return C
+
+
+# ------------------------------------------------------------------------------- field arithmetic (PTX path)
+@pytest.mark.parametrize("field,p", [(0, R), (1, Q)])
+def test_field_ops_ptx_vs_integers(z, field, p):
+    rnd = random.Random(100 + field)
+    n = 4096
+    a = [0, p - 1, 1, p - 1, 2, (p - 1) // 2] + [rnd.randrange(p) for _ in range(n - 6)]
+    b = [0, p - 1, p - 1, 1, (p + 1) // 2, 2] + [rnd.randrange(p) for _ in range(n - 6)]
+    A, B = fr_bytes(a), fr_bytes(b)
+    assert ints(z.field_op(field, 0, A, B, n)) == [x * y % p for x, y in zip(a, b)]
+    assert ints(z.field_op(field, 3, A, B, n)) == [x * y % p for x, y in zip(a, b)]  # portable CIOS on device
+    assert ints(z.field_op(field, 1, A, B, n)) == [(x + y) % p for x, y in zip(a, b)]
+    assert ints(z.field_op(field, 2, A, B, n)) == [(x - y) % p for x, y in zip(a, b)]
+    inv = ints(z.field_op(field, 4, A[:32 * 64], B[:32 * 64], 64))
+    assert inv == [pow(x, -1, p) if x else 0 for x in a[:64]]
+
+
+# ------------------------------------------------------------------------------- Poseidon
+def test_poseidon_reference_kats(z, goldens):
+    """utils/tests/poseidon_hash_test.rs:21-130"""
+    for k, v in goldens["ref"]["poseidon_single"]["cases"]:
+        assert z.poseidon_hash([int(k)]) == int(v)
+    t = goldens["ref"]["poseidon_pair_tree8"]
+    l = [z.poseidon_hash_pair(2 * i, 2 * i + 1) for i in range(4)]
+    assert [str(x) for x in l] == [t["l01"], t["l23"], t["l45"], t["l67"]]
+    assert str(z.poseidon_hash_pair(z.poseidon_hash_pair(l[0], l[1]), z.poseidon_hash_pair(l[2], l[3]))) == t["root"]
+    assert z.poseidon_hash([1, 2, 3]) == int(goldens["derived"]["poseidon_misc"]["t4"])
+    assert z.poseidon_hash([R - 1]) == int(goldens["derived"]["poseidon_misc"]["t2_rm1"])
+
+
+def test_hash_pairs_vs_oracle(z, oracle):
+    fs = fr_stream(31)
+    n = 5000
+    vals = [next(fs) for _ in range(2 * n)]
+    got = ints(z.hash_pairs(fr_bytes(vals), n))
+    import ctypes
+    out = ctypes.create_string_buffer(32 * n)
+    oracle.lib().orc_poseidon_pairs(fr_bytes(vals), n, out, oracle.threads())
+    assert got == ints(out.raw)
+
+
+# ------------------------------------------------------------------------------- Merkle tree
+def test_tree_kat_depth20(z, rln20, goldens):
+    """rln/tests/protocol.rs:14-88 and its FFI twin rln/tests/ffi.rs:325-422"""
+    k = goldens["ref"]["tree_depth20_leaf3"]
+    rln20.set_tree(20)
+    assert rln20.get_root() == int(goldens["ref"]["empty_tree_depth20_root"]["root"], 16)
+    secret = z.hash_to_field_le(k["secret_preimage"].encode())
+    leaf = z.poseidon_hash_pair(z.poseidon_hash([secret]), k["user_message_limit"])
+    rln20.set_leaf(k["leaf_index"], leaf)
+    assert rln20.get_root() == sum(l << (64 * i) for i, l in enumerate(k["root_limbs_le64"]))
+    elems, bits = rln20.get_merkle_proof(k["leaf_index"])
+    assert elems == [int(x, 16) for x in k["path_elements"]]
+    assert bits == k["identity_path_index"]
+    assert rln20.get_leaf(k["leaf_index"]) == leaf and rln20.leaves_set() == 4
+
+
+def test_tree_vs_oracle_and_fixture(z, rln10, goldens, oracle):
+    m = goldens["derived"]["merkle_d10"]
+    rln10.set_tree(10)
+    rln10.set_leaves_from(m["start"], [int(x) for x in m["leaves"]])
+    assert rln10.get_root() == int(m["root"])
+    for i, pr in m["proofs"].items():
+        e, b = rln10.get_merkle_proof(int(i))
+        assert [str(x) for x in e] == pr["elements"] and b == pr["index"]
+    assert rln10.leaves_set() == m["start"] + len(m["leaves"])
+    # one-by-one == next == batch (rln/tests/public.rs:349-427)
+    fs = fr_stream(32)
+    leaves = [next(fs) for _ in range(70)]
+    rln10.set_tree(10)
+    rln10.set_leaves_from(0, leaves)
+    batch_root = rln10.get_root()
+    rln10.set_tree(10)
+    for i, v in enumerate(leaves):
+        rln10.set_leaf(i, v)
+    assert rln10.get_root() == batch_root
+    rln10.set_tree(10)
+    for v in leaves:
+        rln10.set_next_leaf(v)
+    assert rln10.get_root() == batch_root and rln10.leaves_set() == 70
+    nodes = oracle.merkle_build(10, fr_bytes(leaves), 0, 70)
+    assert batch_root == int.from_bytes(nodes[:32], "little")
+    # delete-all == empty (public.rs), next_index unchanged by delete
+    for i in range(70):
+        rln10.delete_leaf(i)
+    empty = oracle.merkle_build(10, b"", 0, 0)
+    assert rln10.get_root() == int.from_bytes(empty[:32], "little") and rln10.leaves_set() == 70
+    # atomic_operation: remove + insert
+    rln10.set_tree(10)
+    rln10.set_leaves_from(0, leaves[:10])
+    rln10.atomic_operation(10, leaves[10:20], [0, 3])
+    exp = list(leaves[:20])
+    exp[0] = exp[3] = 0
+    nodes = oracle.merkle_build(10, fr_bytes(exp), 0, 20)
+    assert rln10.get_root() == int.from_bytes(nodes[:32], "little")
+    with pytest.raises(z.RLNError, match="set_range got too many leaves"):
+        rln10.set_leaves_from(1020, leaves[:10])
+    with pytest.raises(z.RLNError, match="Leaf index out of bounds"):
+        rln10.set_leaf(1024, 1)
+
+
+def test_tree_full_size_2pow20(z, rln20, oracle):
+    """BASELINE config 3: 2^20 seeded leaves, root + 64 membership paths == oracle FullMerkleTree"""
+    fs = fr_stream(3)
+    n = 1 << 20
+    import numpy as np
+    rng = np.random.default_rng(3)
+    raw = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    raw[:, 31] &= 0x1f  # < 2^253 < r: canonical
+    leaves = raw.tobytes()
+    rln20.set_tree(20)
+    rln20.set_leaves_from_bytes(0, leaves)
+    nodes = oracle.merkle_build(20, leaves, 0, n, oracle.threads())
+    assert rln20.get_root() == int.from_bytes(nodes[:32], "little")
+    idx = [0, 1, n - 1, 12345, 777777] + [int(x) for x in rng.integers(0, n, size=59)]
+    el, bits = rln20.get_merkle_proofs(idx)
+    for k, i in enumerate(idx):
+        e, b = oracle.merkle_proof_from_nodes(nodes, 20, i)
+        assert ints(el[k * 640:(k + 1) * 640]) == e and list(bits[k * 20:(k + 1) * 20]) == b
+    rln20.set_tree(20)
+
+
+# ------------------------------------------------------------------------------- variable-base MSM
+def test_msm_fixture_and_oracle(z, goldens, oracle):
+    ms = goldens["derived"]["msm_g1_48"]
+    pts = b"".join(fr_bytes([int(p[0]), int(p[1])]) for p in ms["bases"])
+    sc = fr_bytes([int(s) for s in ms["scalars"]])
+    m = z.G1Msm(1 << 16)
+    assert [str(x) for x in ints(m.msm(pts, sc, 48))] == ms["result"]
+    # random 2^14 with edge scalars and an infinity base, vs the oracle's ark-rule Pippenger
+    n = 1 << 14
+    fs = fr_stream(1)
+    ks = fr_bytes([next(fs) for _ in range(n)])
+    bases = bytearray(oracle.g1_mul_gen(ks, n, oracle.threads()))
+    bases[64 * 5:64 * 6] = b"\0" * 63 + b"\x40"  # point at infinity flag
+    fs = fr_stream(2)
+    scal = [next(fs) for _ in range(n)]
+    scal[0], scal[1], scal[2], scal[3] = 0, 1, R - 1, (1 << 253)
+    scb = fr_bytes(scal)
+    assert m.msm(bytes(bases), scb, n) == oracle.msm_g1(bytes(bases), scb, n, oracle.threads())
+    # tiny and empty inputs
+    assert m.msm(bytes(bases[:64]), scb[32:64], 1) == bytes(bases[:64])
+    assert m.msm(b"", b"", 0) == b"\0" * 64
+    # linearity: MSM(P, a) + MSM(P, b) == MSM(P, a+b)  checked through the oracle's group law on a 2-term MSM
+    a = [next(fs) for _ in range(n)]
+    b = [next(fs) for _ in range(n)]
+    ra, rb = m.msm(bytes(bases), fr_bytes(a), n), m.msm(bytes(bases), fr_bytes(b), n)
+    rab = m.msm(bytes(bases), fr_bytes([(x + y) % R for x, y in zip(a, b)]), n)
+    assert oracle.msm_g1(ra + rb, fr_bytes([1, 1]), 2) == rab
+
+
+# ------------------------------------------------------------------------------- witness / QAP / proofs
+@pytest.mark.parametrize("depth,key", [(10, "kat_proof_d10"), (20, "kat_proof_d20"), (20, "kat_proof_d20_r0")])
+def test_known_answer_proofs(z, goldens, depth, key, rln10, rln20):
+    """bit-exact against the golden proofs (r = 44, s = 77 as rln/tests/protocol.rs:234-235)"""
+    k = goldens["derived"][key]
+    rln = rln10 if depth == 10 else rln20
+    wb = witness_le(*kat_witness_args(depth, k["inputs"]))
+    assert wb.hex() == k["witness_le_hex"]
+    w, h = rln.debug_witness_and_h(wb)
+    assert hashlib.sha256(w).hexdigest() == k["w_sha256"]
+    assert hashlib.sha256(h).hexdigest() == k["h_sha256"]
+    wit = z.RLNWitnessInput.from_bytes_le(wb)
+    proof = rln.generate_rln_proof_with_rs(wit, int(k["inputs"]["r"]), int(k["inputs"]["s"]))
+    assert proof.to_bytes_le().hex() == k["rln_proof_le_hex"]
+    pv = proof.values
+    assert {n: str(getattr(pv, n)) for n in ("root", "x", "external_nullifier", "y", "nullifier")} == k["public"]
+    # verify under the product verifier and under the oracle verifier
+    assert rln.verify_with_roots(proof, pv.x, []) is True
+    assert rln.verify_with_roots(proof, pv.x, [pv.root]) is True
+    with pytest.raises(z.RLNError, match="Expected one of the provided roots"):
+        rln.verify_with_roots(proof, pv.x, [pv.root + 1])
+    with pytest.raises(z.RLNError, match="Signal value does not match"):
+        rln.verify_with_roots(proof, pv.x + 1, [])
+    # round trip through bytes + mutated value → invalid (rln/tests/protocol.rs:638-656)
+    again = z.RLNProof.from_bytes_le(proof.to_bytes_le())
+    assert again.to_bytes_le() == proof.to_bytes_le()
+    bad = bytearray(proof.to_bytes_le())
+    bad[129 + 1 + 96] ^= 1  # y
+    with pytest.raises(z.RLNError, match="Invalid proof provided"):
+        rln.verify_with_roots(z.RLNProof.from_bytes_le(bytes(bad)), pv.x, [])
+
+
+def test_reference_snarkjs_proof_verifies_on_gpu(z, rln20, goldens, oracle):
+    """rln/tests/public.rs:77-233: the hard-coded snarkjs proof under the bundled depth-20 vk"""
+    v = goldens["ref"]["groth16_verifier_single"]
+    from pyref import groth16 as G
+    proof = ((int(v["pi_a"][0]), int(v["pi_a"][1])),
+             ((int(v["pi_b"][0][0]), int(v["pi_b"][0][1])), (int(v["pi_b"][1][0]), int(v["pi_b"][1][1]))),
+             (int(v["pi_c"][0]), int(v["pi_c"][1])))
+    pv = {k: int(v[k]) for k in ("root", "x", "external_nullifier", "y", "nullifier")}
+    rec = G.rln_proof_to_bytes_le(proof, pv)
+    p = z.RLNProof.from_bytes_le(rec)
+    assert rln20.verify_with_roots(p, pv["x"], []) is True
+    assert rln20.verify_batch(rec, 1) == [1]
+
+
+def _make_batch(rln, oracle_ctx, depth, n, seed):
+    """SURVEY §8d config 4 generator scaled down: member j of a seeded tree, message_id = j mod 100"""
+    from pyref import poseidon as P
+    fs = fr_stream(seed)
+    secrets = [next(fs) for _ in range(n)]
+    limit = 100
+    leaves = [P.poseidon([P.poseidon([s]), limit]) for s in secrets]
+    rln.set_tree(depth)
+    rln.set_leaves_from(0, leaves)
+    el, bits = rln.get_merkle_proofs(list(range(n)))
+    en = P.poseidon([P.hash_to_field_le(b"test-epoch"), P.hash_to_field_le(b"test-rln-identifier")])
+    recs, rs, inputs = [], [], []
+    for j in range(n):
+        pe = ints(el[j * depth * 32:(j + 1) * depth * 32])
+        ix = list(bits[j * depth:(j + 1) * depth])
+        x = next(fs)
+        recs.append(witness_le(secrets[j], limit, j % 100, pe, ix, x, en))
+        rs += [next(fs), next(fs)]
+        inputs.append(oracle_ctx.inputs_buffer(secrets[j], limit, j % 100, pe, ix, x, en))
+    return b"".join(recs), fr_bytes(rs), b"".join(inputs), rln.get_root()
+
+
+@pytest.mark.parametrize("depth,n", [(10, 37), (20, 70)])
+def test_batch_proofs_bit_equal_to_oracle(z, oracle, depth, n, rln10, rln20):
+    rln = rln10 if depth == 10 else rln20
+    ctx = oracle.Ctx(resource(depth, "rln_final.arkzkey"), resource(depth, "graph.bin"))
+    recs, rs, inputs, root = _make_batch(rln, ctx, depth, n, 50 + depth)
+    out = rln.prove_batch(recs, n, rs)
+    want_proofs, want_pub = ctx.prove_batch(inputs, rs, n, oracle.threads())
+    from pyref import groth16 as G
+    for j in range(n):
+        rec = out[290 * j:290 * (j + 1)]
+        v = ints(want_proofs[256 * j:256 * (j + 1)])
+        proof = ((v[0], v[1]), ((v[2], v[3]), (v[4], v[5])), (v[6], v[7]))
+        y, rt, nul, x, en = ints(want_pub[160 * j:160 * (j + 1)])
+        assert rt == root
+        assert rec == G.rln_proof_to_bytes_le(proof, dict(root=rt, external_nullifier=en, x=x, y=y, nullifier=nul)), j
+    # every GPU proof verifies under the oracle verifier and under the GPU verifier
+    proofs_aff = want_proofs  # bit-equal to the GPU's (checked above through the compressed form)
+    assert ctx.verify_batch(proofs_aff, want_pub, n, 5, oracle.threads()) == [1] * n
+    assert rln.verify_batch(out, n) == [1] * n
+    # stateful verification against the tree root (public.rs:725-745)
+    p0 = z.RLNProof.from_bytes_le(out[:290])
+    assert rln.verify_rln_proof(p0, p0.values.x) is True
+    rln.set_leaf(0, 12345)
+    with pytest.raises(z.RLNError, match="Expected one of the provided roots"):
+        rln.verify_rln_proof(p0, p0.values.x)
+    # fresh randomness path (ffi_generate_rln_proof): different bytes, still valid
+    wit = z.RLNWitnessInput.from_bytes_le(recs[:len(recs) // n])
+    pa, pb = rln.generate_rln_proof(wit), rln.generate_rln_proof(wit)
+    assert pa.proof_bytes != pb.proof_bytes
+    assert rln.verify_with_roots(pa, pa.values.x, []) and rln.verify_with_roots(pb, pb.values.x, [])
+
+
+def test_witness_errors(z, rln20):
+    with pytest.raises(z.RLNError, match="tree_depth"):
+        w = z.RLNWitnessInput.new_single(5, 10, 3, [1, 2], [0, 1], 7, 9)
+        rln20.generate_rln_proof(w)
+    with pytest.raises(z.RLNError, match="invalid data|Expected to read|Unknown message mode"):
+        z.RLNProof.from_bytes_le(b"\x00" + b"\xff" * 128 + b"\x00" + b"\x00" * 160)

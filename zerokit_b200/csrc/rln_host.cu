@@ -1306,6 +1306,7 @@ int rlnb200_witness_to_input_slots(FFI_RLN_t* const* rln, const uint8_t* witness
            (*rln)->r->witness_slots(w, slots_out);)
 }
 size_t rlnb200_input_slots(FFI_RLN_t* const* rln) { return (*rln)->r->n_slots(); }
+size_t rlnb200_state_tree_depth(FFI_RLN_t* const* rln) { return (*rln)->r->tree_depth(); }
 int rlnb200_input_slot(FFI_RLN_t* const* rln, const char* name, uint32_t* offset, uint32_t* len) {
     auto& m = (*rln)->r->graph().inputs;
     auto it = m.find(name);

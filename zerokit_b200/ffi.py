@@ -128,6 +128,7 @@ def lib():
         "rlnb200_prove_batch_device": (c_int, [pp, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(RlnString)]),
         "rlnb200_witness_to_input_slots": (c_int, [pp, c_void_p, c_size_t, c_void_p, POINTER(RlnString)]),
         "rlnb200_input_slots": (c_size_t, [pp]),
+        "rlnb200_state_tree_depth": (c_size_t, [pp]),
         "rlnb200_input_slot": (c_int, [pp, c_char_p, POINTER(c_uint32), POINTER(c_uint32)]),
         "rlnb200_reserve": (c_int, [pp, c_size_t, POINTER(RlnString)]),
         "rlnb200_launch_count": (c_uint64, []),

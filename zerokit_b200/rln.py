@@ -293,15 +293,13 @@ class RLN:
 
     def get_merkle_proofs(self, indices):
         """→ (elements bytes n*depth*32, bits bytes n*depth)"""
-        n, d = len(indices), self.tree_depth_state
+        n, d = len(indices), ffi.lib().rlnb200_state_tree_depth(byref(self._h))
         idx = (ctypes.c_uint64 * max(n, 1))(*indices)
         el = ctypes.create_string_buffer(32 * n * d)
         bits = ctypes.create_string_buffer(max(n * d, 1))
         err = ffi.RlnString()
         _check_int(ffi.lib().rlnb200_get_merkle_proofs(byref(self._h), idx, n, el, bits, byref(err)), err)
         return el.raw, bits.raw[:n * d]
-
-    tree_depth_state = DEFAULT_TREE_DEPTH  # depth of the stateful tree; set by callers that use set_tree
 
     # ---- proving / verifying -----------------------------------------------------------------
     def generate_rln_proof(self, witness: RLNWitnessInput) -> RLNProof:
