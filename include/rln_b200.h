@@ -178,8 +178,14 @@ int rlnb200_input_slot(FFI_RLN_t *const *rln, const char *name, uint32_t *offset
 int rlnb200_reserve(FFI_RLN_t *const *rln, size_t max_batch, RlnString *err);
 /* number of kernel launches issued by this library since load (bench bookkeeping) */
 uint64_t rlnb200_launch_count(void);
-/* last stage timings of rlnb200_prove_batch_device in milliseconds: witness, qap, msm+assemble, values */
-void rlnb200_last_stage_ms(FFI_RLN_t *const *rln, float out[4]);
+/* CUDA-event timings (ms) of the last rlnb200_prove_batch_device call, in launch order: witness VM, QAP
+ * (matvec + 6 NTTs), G1 table accumulate, G1 reduce, G2 accumulate, G2 reduce, assembly, proof values */
+void rlnb200_last_stage_ms(FFI_RLN_t *const *rln, float out[8]);
+/* selects the CUDA device used by subsequently created objects (call before ffi_rln_new) */
+int rlnb200_set_device(int device, RlnString *err);
+/* fixed-base table geometry: window bits c, windows K, number of (non-infinity) G1 / G2 bases, bytes in HBM */
+int rlnb200_table_info(FFI_RLN_t *const *rln, int *window_bits, int *windows, uint64_t *g1_bases, uint64_t *g2_bases,
+                       uint64_t *table_bytes);
 
 /* Merkle tree bulk operations on device/host buffers (FullMerkleTree semantics,
  * utils/src/merkle_tree/full_merkle_tree.rs:197-223,288-304) */

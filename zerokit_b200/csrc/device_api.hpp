@@ -101,6 +101,7 @@ struct MsmWorkspace {
     G2XYZZ* sum_g2;   // [B]
     const MsmTask *tasks_g1, *tasks_g2;  // device arrays built from msm_make_tasks for this B
     u32 n_tasks_g1, n_tasks_g2;
+    cudaEvent_t* ev;  // optional: 6 events recorded around [g1 accum, g1 reduce, g2 accum, g2 reduce, assemble]
 };
 // all five MSMs for B proofs + assembly (partial_proof.rs:226-273) + affine + ark-compressed bytes.
 // rs: B × 64 canonical bytes (r | s).  proofs_out: B × 128 bytes.  proofs_affine (optional): B × 256 bytes canonical A|B|C

@@ -326,8 +326,11 @@ void launch_msm_and_assemble(const FixedMsmPlan& plan, const ProverKeyDev& pk, c
         for (int i = 0; i < 4; i++) { a.row[i] = plan.g1[i].row; a.table[i] = (const G1Affine*)plan.g1[i].table; a.which[i] = plan.g1[i].which_src; }
         a.tasks = ws.tasks_g1; a.part = ws.part_g1; a.B = B; a.c = plan.c; a.K = plan.K;
         dim3 grid((B + bx - 1) / bx, ws.n_tasks_g1);
+        if (ws.ev) cudaEventRecord(ws.ev[0], s);
         k_msm_accum<Fq><<<grid, bx, 0, s>>>(a);
+        if (ws.ev) cudaEventRecord(ws.ev[1], s);
         k_msm_reduce<Fq><<<dim3((B + bx - 1) / bx, 4), bx, 0, s>>>(ws.part_g1, ws.tasks_g1, ws.n_tasks_g1, B, ws.sum_g1);
+        if (ws.ev) cudaEventRecord(ws.ev[2], s);
     }
     {   // G2: B2
         AccumArgs<Fq2> a;
@@ -336,10 +339,13 @@ void launch_msm_and_assemble(const FixedMsmPlan& plan, const ProverKeyDev& pk, c
         a.tasks = ws.tasks_g2; a.part = ws.part_g2; a.B = B; a.c = plan.c; a.K = plan.K;
         dim3 grid((B + bx - 1) / bx, ws.n_tasks_g2);
         k_msm_accum<Fq2><<<grid, bx, 0, s>>>(a);
+        if (ws.ev) cudaEventRecord(ws.ev[3], s);
         k_msm_reduce<Fq2><<<dim3((B + bx - 1) / bx, 1), bx, 0, s>>>(ws.part_g2, ws.tasks_g2, ws.n_tasks_g2, B, ws.sum_g2);
+        if (ws.ev) cudaEventRecord(ws.ev[4], s);
     }
     k_assemble_g1<<<(B + 63) / 64, 64, 0, s>>>(pk, ws.sum_g1, B, d_rs, d_proofs_out, d_proofs_affine);
     k_assemble_g2<<<(B + 63) / 64, 64, 0, s>>>(pk, ws.sum_g2, B, d_rs, d_proofs_out, d_proofs_affine);
+    if (ws.ev) cudaEventRecord(ws.ev[5], s);
 }
 
 }  // namespace zk

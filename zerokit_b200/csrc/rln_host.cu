@@ -253,8 +253,16 @@ class Rln {
     void prove_host(const std::vector<Witness>& ws, const uint8_t* rs, std::vector<RlnProof>& out);
     void witness_slots(const Witness& w, uint8_t* slots) const;
     void debug_w_h(const Witness& w, uint8_t* w_out, uint8_t* h_out);
+    void table_info(int* c, int* K, uint64_t* g1, uint64_t* g2, uint64_t* bytes) const {
+        *c = plan_.c; *K = plan_.K;
+        *g1 = (uint64_t)plan_.g1[0].n_bases + plan_.g1[1].n_bases + plan_.g1[2].n_bases + plan_.g1[3].n_bases;
+        *g2 = plan_.g2.n_bases;
+        *bytes = 0;
+        for (int i = 0; i < 5; i++) *bytes += d_tab_[i].bytes;
+    }
     void verify_batch(const uint8_t* proofs128, const uint8_t* publics160_circuit_order, size_t n, uint8_t* ok);
-    float stage_ms[4] = {0, 0, 0, 0};
+    // witness, qap, g1 accumulate, g1 reduce, g2 accumulate, g2 reduce, assemble, proof values
+    float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     std::mutex mu;
 
    private:
@@ -291,6 +299,7 @@ class Rln {
     std::map<u32, std::unique_ptr<TaskSet>> tasks_;
     cudaStream_t stream_ = nullptr;
     cudaEvent_t ev_[5];
+    cudaEvent_t mev_[6];
 };
 
 static void upload_points_g1(const std::vector<uint8_t>& raw, const std::vector<uint32_t>& pick, DevMem& out) {
@@ -346,6 +355,7 @@ Rln::Rln(size_t tree_depth, const uint8_t* zkey, size_t zlen, const uint8_t* gra
     max_batch_ = (size_t)env_int("RLN_B200_MAX_BATCH", 4096);
     ZK_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     for (auto& e : ev_) ZK_CUDA_CHECK(cudaEventCreate(&e));
+    for (auto& e : mev_) ZK_CUDA_CHECK(cudaEventCreate(&e));
     build_circuit();
     build_tables();
     set_tree(tree_depth);
@@ -353,6 +363,7 @@ Rln::Rln(size_t tree_depth, const uint8_t* zkey, size_t zlen, const uint8_t* gra
 Rln::~Rln() {
     cudaDeviceSynchronize();
     for (auto& e : ev_) cudaEventDestroy(e);
+    for (auto& e : mev_) cudaEventDestroy(e);
     if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -701,7 +712,7 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
                        cudaStream_t s) {
     if (n == 0) return;
     reserve(n);
-    float acc[4] = {0, 0, 0, 0};
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (size_t off = 0; off < n; off += cap_) {
         const u32 B = (u32)(n - off < cap_ ? n - off : cap_);
         TaskSet& ts = tasks_for(B);
@@ -724,6 +735,7 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
         mw.tasks_g2 = ts.g2.as<MsmTask>();
         mw.n_tasks_g1 = ts.n1;
         mw.n_tasks_g2 = ts.n2;
+        mw.ev = mev_;
         launch_msm_and_assemble(plan_, pk_, ws_vals_.as<Fr>(), ws_a_.as<Fr>(), B, d_rs + 64 * off, mw, d_proofs + 128 * off,
                                 d_affine ? d_affine + 256 * off : nullptr, s);
         ZK_CUDA_CHECK(cudaEventRecord(ev_[3], s));
@@ -734,15 +746,17 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
         std::vector<u32> err(B);
         ZK_CUDA_CHECK(cudaMemcpyAsync(err.data(), ws_err_.p, 4 * B, cudaMemcpyDeviceToHost, s));
         ZK_CUDA_CHECK(cudaStreamSynchronize(s));
-        for (int i = 0; i < 4; i++) {
+        {
             float ms = 0;
-            cudaEventElapsedTime(&ms, ev_[i], ev_[i + 1]);
-            acc[i] += ms;
+            cudaEventElapsedTime(&ms, ev_[0], ev_[1]); acc[0] += ms;
+            cudaEventElapsedTime(&ms, ev_[1], ev_[2]); acc[1] += ms;
+            for (int i = 0; i < 5; i++) { cudaEventElapsedTime(&ms, mev_[i], mev_[i + 1]); acc[2 + i] += ms; }
+            cudaEventElapsedTime(&ms, ev_[3], ev_[4]); acc[7] += ms;
         }
         for (u32 j = 0; j < B; j++)
             if (err[j]) throw RlnError("Protocol error: Error calculating witness: graph evaluation failed");
     }
-    for (int i = 0; i < 4; i++) stage_ms[i] = acc[i];
+    for (int i = 0; i < 8; i++) stage_ms[i] = acc[i];
 }
 
 void Rln::witness_slots(const Witness& w, uint8_t* slots) const {  // iden3calc.rs:106-181, witness.rs:832-881
@@ -1319,8 +1333,15 @@ int rlnb200_reserve(FFI_RLN_t* const* rln, size_t max_batch, RlnString* err) {
     INT_OP(std::lock_guard<std::mutex> lk((*rln)->r->mu); (*rln)->r->reserve(max_batch);)
 }
 uint64_t rlnb200_launch_count(void) { return g_launch_count.load(); }
-void rlnb200_last_stage_ms(FFI_RLN_t* const* rln, float out[4]) {
-    for (int i = 0; i < 4; i++) out[i] = (*rln)->r->stage_ms[i];
+void rlnb200_last_stage_ms(FFI_RLN_t* const* rln, float out[8]) {
+    for (int i = 0; i < 8; i++) out[i] = (*rln)->r->stage_ms[i];
+}
+int rlnb200_set_device(int device, RlnString* err) {
+    INT_OP(ZK_CUDA_CHECK(cudaSetDevice(device));)
+}
+int rlnb200_table_info(FFI_RLN_t* const* rln, int* window_bits, int* windows, uint64_t* g1_bases, uint64_t* g2_bases, uint64_t* table_bytes) {
+    (*rln)->r->table_info(window_bits, windows, g1_bases, g2_bases, table_bytes);
+    return 0;
 }
 int rlnb200_set_leaves_from_bytes(FFI_RLN_t** rln, size_t index, const uint8_t* leaves_le, size_t count, RlnString* err) {
     INT_OP(std::lock_guard<std::mutex> lk((*rln)->r->mu); (*rln)->r->set_range_host(index, leaves_le, count);)

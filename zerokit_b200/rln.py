@@ -356,9 +356,15 @@ class RLN:
         _check_int(ffi.lib().rlnb200_reserve(byref(self._h), max_batch, byref(err)), err)
 
     def last_stage_ms(self):
-        out = (ctypes.c_float * 4)()
+        out = (ctypes.c_float * 8)()
         ffi.lib().rlnb200_last_stage_ms(byref(self._h), out)
-        return dict(zip(("witness", "qap", "msm_assemble", "values"), list(out)))
+        return dict(zip(("witness", "qap", "msm_g1_accum", "msm_g1_reduce", "msm_g2_accum", "msm_g2_reduce", "assemble", "values"), list(out)))
+
+    def table_info(self):
+        c, k = ctypes.c_int(), ctypes.c_int()
+        g1, g2, b = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        ffi.lib().rlnb200_table_info(byref(self._h), byref(c), byref(k), byref(g1), byref(g2), byref(b))
+        return dict(window_bits=c.value, windows=k.value, g1_bases=g1.value, g2_bases=g2.value, table_bytes=b.value)
 
     def debug_witness_and_h(self, witness_le: bytes):
         nw, dom = ffi.lib().rlnb200_num_wires(byref(self._h)), ffi.lib().rlnb200_domain_size(byref(self._h))
@@ -400,6 +406,16 @@ class G1Msm:
     def msm_device(self, d_bases, d_scalars, n, d_result, stream=0):
         err = ffi.RlnString()
         _check_int(ffi.lib().rlnb200_msm_g1_device(self._h, c_void_p(d_bases), c_void_p(d_scalars), n, c_void_p(d_result), c_void_p(stream), byref(err)), err)
+
+
+def set_device(index):
+    err = ffi.RlnString()
+    _check_int(ffi.lib().rlnb200_set_device(index, byref(err)), err)
+
+
+def mul_throughput(iters=2000):
+    """measured Montgomery products per second (CUDA-event timed)"""
+    return ffi.lib().rlnb200_mul_throughput(iters)
 
 
 def field_op(field, op, a_bytes, b_bytes, n):
