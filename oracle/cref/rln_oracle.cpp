@@ -18,6 +18,8 @@
 // 0.5.0 radix-2 domain (generator 5, two-adicity 28), ark-groth16 0.5.0 verify_proof.
 #include "field.hpp"
 
+#include <malloc.h>
+
 #include <algorithm>
 #include <atomic>
 #include <map>
@@ -449,7 +451,8 @@ static void ntt_inplace(std::vector<Fr>& a, const Fr& w) {
     for (size_t m = 1; m < n; m <<= 1) {
         Fr wm = w;
         for (size_t k = n / (2 * m); k > 1; k >>= 1) wm = wm.sqr();
-        std::vector<Fr> tw(m);
+        static thread_local std::vector<Fr> tw;
+        if (tw.size() < m) tw.resize(m);
         tw[0] = Fr::one();
         for (size_t j = 1; j < m; j++) tw[j] = tw[j - 1] * wm;
         for (size_t k = 0; k < n; k += 2 * m)
@@ -469,7 +472,10 @@ static void intt_inplace(std::vector<Fr>& a, const Fr& w) {
 static void witness_map(const ZkeyData& z, const Fr* w, std::vector<Fr>& h) {  // qap.rs:30-98
     size_t n = 1;
     while (n < z.num_constraints + z.num_instance) n <<= 1;
-    std::vector<Fr> a(n, Fr::zero()), b(n, Fr::zero()), c(n, Fr::zero());
+    static thread_local std::vector<Fr> a, b, c;
+    a.assign(n, Fr::zero());
+    b.assign(n, Fr::zero());
+    c.assign(n, Fr::zero());
     for (size_t i = 0; i < z.num_constraints; i++) {
         Fr sa = Fr::zero(), sb = Fr::zero();
         for (auto& e : z.A[i].e) sa += e.first * w[e.second];
@@ -502,8 +508,11 @@ static Jac<F> msm_pippenger(const Affine<F>* pts, const U256* sc, size_t n, int 
     if (n == 0) return Jac<F>::infinity();
     const int c = c_override ? c_override : ark_window(n);
     const int nwin = (254 + c - 1) / c + 1;  // +1 for the signed-digit carry
-    // signed digits in [−2^(c−1), 2^(c−1)]
-    std::vector<int32_t> digits(n * nwin);
+    // signed digits in [−2^(c−1), 2^(c−1)]; scratch is reused per worker thread (no allocator traffic
+    // when many proofs run side by side)
+    static thread_local std::vector<int32_t> digits_tl;
+    if (digits_tl.size() < n * (size_t)nwin) digits_tl.resize(n * (size_t)nwin);
+    int32_t* digits = digits_tl.data();
     for (size_t i = 0; i < n; i++) {
         int carry = 0;
         for (int w = 0; w < nwin; w++) {
@@ -521,7 +530,9 @@ static Jac<F> msm_pippenger(const Affine<F>* pts, const U256* sc, size_t n, int 
     }
     std::vector<Jac<F>> winsum(nwin);
     parallel_for(nwin, nthreads, [&](size_t w) {
-        std::vector<Jac<F>> buckets(1 << (c - 1), Jac<F>::infinity());
+        static thread_local std::vector<Jac<F>> buckets_tl;
+        buckets_tl.assign((size_t)1 << (c - 1), Jac<F>::infinity());
+        std::vector<Jac<F>>& buckets = buckets_tl;
         for (size_t i = 0; i < n; i++) {
             int d = digits[i * nwin + w];
             if (d == 0 || pts[i].inf) continue;
@@ -556,11 +567,14 @@ static bool prove_one(const OracleCtx& ctx, const Fr* inputs /*inputs_size*/, co
                       Fr* pub5, int nthreads) {
     const ZkeyData& z = ctx.z;
     size_t nw = ctx.g.signals.size();
-    std::vector<Fr> vals, w(nw), h;
+    static thread_local std::vector<Fr> vals, w, h;
+    static thread_local std::vector<U256> ws, hs;
+    w.resize(nw);
     if (!evaluate_graph(ctx.g, inputs, vals, w.data())) return false;
     if (pub5) for (int i = 0; i < 5; i++) pub5[i] = w[1 + i];
     witness_map(z, w.data(), h);
-    std::vector<U256> ws(nw), hs(h.size());
+    ws.resize(nw);
+    hs.resize(h.size());
     for (size_t i = 0; i < nw; i++) ws[i] = w[i].to_u256();
     for (size_t i = 0; i < h.size(); i++) hs[i] = h[i].to_u256();
     const size_t ni = z.num_instance;
@@ -618,6 +632,8 @@ static G2A g2_in(const uint8_t* b) {
 extern "C" {
 
 int orc_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
+// keep big blocks inside the per-thread arenas instead of mmap/munmap round trips (page-fault storms with >100 workers)
+static int oracle_malloc_tuning = [] { mallopt(M_MMAP_THRESHOLD, 1 << 30); mallopt(M_TRIM_THRESHOLD, 1 << 30); mallopt(M_ARENA_MAX, 256); return 0; }();
 
 // Poseidon over n inputs (1..8)
 void orc_poseidon(const uint8_t* in, int n, uint8_t* out) {

@@ -52,7 +52,20 @@ def lib():
 
 
 def threads():
-    return lib().orc_hardware_threads()
+    """worker threads for the CPU arm: hardware threads, capped by the container's cgroup CPU quota
+    (running more runnable threads than the quota only adds throttling stalls)"""
+    n = lib().orc_hardware_threads()
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period) + 0.5)))
+    except (OSError, ValueError):
+        pass
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    return n
 
 
 def fr_bytes(vals):
