@@ -41,9 +41,10 @@ def log(*a):
 
 
 # ----------------------------------------------------------------------------------------------- inputs
-def make_witnesses(rln, n, seed):
+def make_witnesses(rln, n, seed, reps=1):
     """member j of a 2^20-leaf tree, message_id = j mod 100, x / (r,s) seeded.
-    Returns (witness records LE, rs bytes, root).  Uses only the product API + host byte shuffling."""
+    Returns (reps·n witness records LE, rs bytes, root); record g uses member g mod n with its own x, r, s.
+    Uses only the product API + host byte shuffling."""
     import numpy as np
     import zerokit_b200 as z
     from common import fr_stream, fr_bytes, ints, witness_le
@@ -63,10 +64,10 @@ def make_witnesses(rln, n, seed):
     el, bits = rln.get_merkle_proofs(list(range(n)))
     en = z.poseidon_hash_pair(z.hash_to_field_le(b"test-epoch"), z.hash_to_field_le(b"test-rln-identifier"))
     recs, rs = [], []
-    for j in range(n):
-        pe = ints(el[j * DEPTH * 32:(j + 1) * DEPTH * 32])
-        ix = list(bits[j * DEPTH:(j + 1) * DEPTH])
-        recs.append(witness_le(secrets[j], limit, j % 100, pe, ix, next(fs), en))
+    paths = [(ints(el[j * DEPTH * 32:(j + 1) * DEPTH * 32]), list(bits[j * DEPTH:(j + 1) * DEPTH])) for j in range(n)]
+    for g in range(reps * n):
+        j = g % n
+        recs.append(witness_le(secrets[j], limit, j % 100, paths[j][0], paths[j][1], next(fs), en))
         rs += [next(fs), next(fs)]
     return b"".join(recs), fr_bytes(rs), rln.get_root()
 
@@ -192,30 +193,31 @@ def run_gpu(args, rank, local_rank, world):
     t0 = time.time()
     rln = z.RLN.new(DEPTH)
     info = rln.table_info()
-    log(f"[rank {rank}] RLN.new: {time.time() - t0:.1f}s, tables c={info['window_bits']} K={info['windows']} {info['table_bytes'] / 2**30:.1f} GiB")
+    log(f"[rank {rank}] RLN.new: {time.time() - t0:.1f}s, tables G1 c={info['window_bits']} K={info['windows']}, G2 c={info['window_bits_g2']} K={info['windows_g2']}, {info['table_bytes'] / 2**30:.1f} GiB")
     n = BATCH
     slots = rln.input_slots()
-    # ---- inputs: rank 0 generates witnesses for every rank, NCCL scatters the input-slot buffers
+    # ---- inputs: rank 0 generates world·n distinct witnesses; NCCL scatters contiguous slices (zerokit_b200/sharding.py)
+    from zerokit_b200.sharding import scatter_records, gather_records
+    rec_len = 1 + 32 * (5 + DEPTH) + 16 + DEPTH
+    total = n * world
+    full_slots = full_rs = full_recs = None
     if rank == 0:
         t0 = time.time()
-        recs, rs, root = make_witnesses(rln, n, seed=5)
-        log(f"[rank 0] witnesses + 2^20 tree: {time.time() - t0:.1f}s")
-        rec_len = len(recs) // n
-        slot_bytes = b"".join(rln.witness_to_input_slots(recs[rec_len * j:rec_len * (j + 1)]) for j in range(n))
-        h_inputs = torch.frombuffer(bytearray(slot_bytes), dtype=torch.uint8).pin_memory()
-        h_rs = torch.frombuffer(bytearray(rs), dtype=torch.uint8).pin_memory()
-    d_inputs = torch.empty(n * slots * 32, dtype=torch.uint8, device=dev)
-    d_rs = torch.empty(n * 64, dtype=torch.uint8, device=dev)
+        recs_all, rs_all, root = make_witnesses(rln, n, seed=5, reps=world)
+        log(f"[rank 0] {total} witnesses + 2^20 tree: {time.time() - t0:.1f}s")
+        slot_bytes = b"".join(rln.witness_to_input_slots(recs_all[rec_len * j:rec_len * (j + 1)]) for j in range(total))
+        full_slots = torch.frombuffer(bytearray(slot_bytes), dtype=torch.uint8).pin_memory()
+        full_rs = torch.frombuffer(bytearray(rs_all), dtype=torch.uint8).pin_memory()
+        full_recs = torch.frombuffer(bytearray(recs_all), dtype=torch.uint8).pin_memory()
     if dist_on:
-        # every rank proves the same 4 096 witnesses with its own blinding factors (independent proofs)
-        if rank == 0:
-            src_in = [h_inputs.to(dev) for _ in range(world)]
-            src_rs = [(h_rs.to(dev)) for _ in range(world)]
-        dist.scatter(d_inputs, src_in if rank == 0 else None, src=0)
-        dist.scatter(d_rs, src_rs if rank == 0 else None, src=0)
+        d_inputs = scatter_records(full_slots, slots * 32, total, dev).contiguous()
+        d_rs = scatter_records(full_rs, 64, total, dev).contiguous()
+        recs = scatter_records(full_recs, rec_len, total, dev).cpu().numpy().tobytes()   # host records for the e2e leg
+        rs = d_rs.cpu().numpy().tobytes()
     else:
-        d_inputs.copy_(h_inputs)
-        d_rs.copy_(h_rs)
+        d_inputs = full_slots.to(dev)
+        d_rs = full_rs.to(dev)
+        recs, rs = recs_all, rs_all
     d_proofs = torch.empty(n * 128, dtype=torch.uint8, device=dev)
     d_values = torch.empty(n * 160, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
@@ -257,28 +259,19 @@ def run_gpu(args, rank, local_rank, world):
     if args.profile:
         if rank == 0:
             print(json.dumps({"profile_run": True, "value": value, "stage_ms": stage}), flush=True)
+        if dist_on:
+            dist.destroy_process_group()
         return
-    # ---- gather proof bytes on rank 0 (NCCL), check a sample against the oracle
-    out_proofs = torch.cat([d_proofs.view(n, 128), d_values.view(n, 160)], dim=1).contiguous()
-    if dist_on:
-        gathered = [torch.empty_like(out_proofs) for _ in range(world)] if rank == 0 else None
-        dist.gather(out_proofs, gathered, dst=0)
-    else:
-        gathered = [out_proofs]
+    # ---- gather the 288-byte proof records on rank 0 (NCCL), in global order
+    out_proofs = torch.cat([d_proofs.view(n, 128), d_values.view(n, 160)], dim=1).contiguous().view(-1)
+    gathered = gather_records(out_proofs, 288, total) if dist_on else out_proofs
 
-    # ---- e2e: host bytes in → host bytes out through the C ABI (rank-local; rank 0's inputs)
+    # ---- e2e: host bytes in → host bytes out through the C ABI, every rank on its own slice
     e2e_steps = max(1, min(args.steps, 3))
-    if rank == 0:
-        rln.prove_batch(recs, n, rs)
-    if dist_on:
-        # other ranks run the same host-path call on the same records so that the aggregate is N× a measured number
-        obj = [recs, rs] if rank == 0 else [None, None]
-        dist.broadcast_object_list(obj, src=0)
-        recs, rs = obj
-        if rank != 0:
-            rln.prove_batch(recs, n, rs)
-        dist.barrier()
+    rln.prove_batch(recs, n, rs)
     torch.cuda.synchronize(dev)
+    if dist_on:
+        dist.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         host_out = rln.prove_batch(recs, n, rs)
@@ -303,7 +296,9 @@ def run_gpu(args, rank, local_rank, world):
     n_chk = 32
     o_inputs = oracle_inputs_from_records(ctx, recs, n_chk)
     want_p, want_pub = ctx.prove_batch(o_inputs, rs[:64 * n_chk], n_chk, threads)
-    got = gathered[0][:n_chk].cpu().numpy().tobytes()
+    got = gathered[:288 * n_chk].cpu().numpy().tobytes()
+    if dist_on:   # the last rank's slice arrived in order: its first record equals what that rank would print
+        assert gathered.numel() == 288 * total
     for j in range(n_chk):
         v = ints(want_p[256 * j:256 * (j + 1)])
         proof = ((v[0], v[1]), ((v[2], v[3]), (v[4], v[5])), (v[6], v[7]))
@@ -365,9 +360,9 @@ def run_gpu(args, rank, local_rank, world):
         "dtype": "u256-modular (8x32-bit Montgomery limbs, BN254 Fr/Fq)", "data": "synthetic",
         "config": {"workload": f"batch {n} RLN proofs per GPU, tree_depth=20, bundled zkey (BASELINE.json configs[3])",
                    "global_batch": n * world, "parallelism": f"dp{world} (independent proofs, no data-path collective)",
-                   "window_bits": info["window_bits"], "table_gib": round(info["table_bytes"] / 2**30, 1),
+                   "window_bits": info["window_bits"], "window_bits_g2": info["window_bits_g2"], "table_gib": round(info["table_bytes"] / 2**30, 1),
                    "l2": "working set (tables + 6.5 GB of per-batch matrices) exceeds the 126 MB L2 between iterations"},
-        "clocks": clocks, "gpu_launches": int(launches),
+        "clocks": clocks, "gpu_launches": int(launches) * world,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * (slots * 32 + 64), "d2h_bytes_per_step": n * 288,
                 "steps": e2e_steps, "api": "rlnb200_prove_batch (host witness records → host rln_proof bytes)"},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "stage_ms": stage,

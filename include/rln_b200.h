@@ -183,9 +183,10 @@ uint64_t rlnb200_launch_count(void);
 void rlnb200_last_stage_ms(FFI_RLN_t *const *rln, float out[8]);
 /* selects the CUDA device used by subsequently created objects (call before ffi_rln_new) */
 int rlnb200_set_device(int device, RlnString *err);
-/* fixed-base table geometry: window bits c, windows K, number of (non-infinity) G1 / G2 bases, bytes in HBM */
+/* fixed-base table geometry: window bits c / windows K of the G1 and of the G2 tables, number of (non-infinity)
+ * G1 / G2 bases, bytes in HBM */
 int rlnb200_table_info(FFI_RLN_t *const *rln, int *window_bits, int *windows, uint64_t *g1_bases, uint64_t *g2_bases,
-                       uint64_t *table_bytes);
+                       uint64_t *table_bytes, int *window_bits_g2, int *windows_g2);
 
 /* Merkle tree bulk operations on device/host buffers (FullMerkleTree semantics,
  * utils/src/merkle_tree/full_merkle_tree.rs:197-223,288-304) */

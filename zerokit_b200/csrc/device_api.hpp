@@ -73,6 +73,7 @@ void launch_witness(const CircuitDev& c, const uint8_t* d_inputs, Fr* d_vals, u3
 void launch_qap(const CircuitDev& c, const Fr* d_vals, Fr* d_a, Fr* d_b, Fr* d_c, u32 B, cudaStream_t s);
 // plain batched NTT for tests: data [n][B] natural order in/out
 void launch_ntt_test(Fr* d_data, u32 log_n, u32 B, bool inverse, const Fr* tw, cudaStream_t s);
+u32 ntt_launches_per_transform(u32 log_n);
 
 // ---- k_msm_fixed.cu ------------------------------------------------------------------------
 struct MsmGroupDev {
@@ -82,9 +83,12 @@ struct MsmGroupDev {
     u32 which_src;       // 0: vals matrix, 1: h matrix
 };
 struct FixedMsmPlan {
-    int c, K;            // window bits, windows
+    int c, K;            // G1 tables: window bits, windows
+    int c2, K2;          // G2 tables (few bases, so a wider window is affordable)
     MsmGroupDev g1[4];   // A, B1, L, H
     MsmGroupDev g2;      // B2
+    const G1Affine* delta1_table;  // [K][2^(c-1)] multiples of δ₁ (r·δ₁, s·δ₁, rs·δ₁ in the assembly)
+    const G2Affine* delta2_table;  // [K2][2^(c2-1)] multiples of δ₂
 };
 // builds [base][window][digit] tables from affine bases (Montgomery, no infinities)
 void launch_build_table_g1(const G1Affine* d_bases, u32 n, int c, int K, G1Affine* d_table, cudaStream_t s);

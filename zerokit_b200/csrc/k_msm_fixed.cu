@@ -254,7 +254,24 @@ __device__ void compress_g2(const G2Affine& p, uint8_t* out, uint8_t* affine_out
     store_words(out + 32, x1);
 }
 
-__global__ void __launch_bounds__(64) k_assemble_g1(ProverKeyDev pk, const G1XYZZ* __restrict__ sum, u32 B, const uint8_t* __restrict__ rs,
+// k·P for the fixed point whose window table is `tb` ([K][2^(c-1)] multiples): K mixed additions, no doublings
+template <class F>
+__device__ XYZZ<F> fixed_base_mul(const Affine<F>* __restrict__ tb, int c, int K, const u32* k) {
+    XYZZ<F> acc = XYZZ<F>::infinity();
+    const u32 half = 1u << (c - 1);
+    u32 carry = 0;
+    for (int w = 0; w < K; w++) {
+        int d = window_digit(k, w, c, carry);
+        if (d == 0) continue;
+        Affine<F> pt = ld_point<F>(tb + (size_t)w * half + ((d < 0 ? -d : d) - 1));
+        if (d < 0) pt.y = pt.y.neg();
+        acc.add_affine(pt);
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(64) k_assemble_g1(ProverKeyDev pk, const G1Affine* __restrict__ dtab, int c, int K,
+                                                    const G1XYZZ* __restrict__ sum, u32 B, const uint8_t* __restrict__ rs,
                                                     uint8_t* __restrict__ proofs, uint8_t* __restrict__ affine) {
     const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= B) return;
@@ -264,20 +281,19 @@ __global__ void __launch_bounds__(64) k_assemble_g1(ProverKeyDev pk, const G1XYZ
     (Fr::from_canonical(r) * Fr::from_canonical(s)).to_canonical(rsv);
     u32 rnz = 0;
     for (int i = 0; i < 8; i++) rnz |= r[i];
-    const G1XYZZ delta = G1XYZZ::from_affine(pk.delta_g1);
     // g_a
     G1XYZZ g_a = sum[0 * (size_t)B + j];
     g_a.add_affine(pk.alpha_g1);
-    g_a.add(delta.mul(r));
+    g_a.add(fixed_base_mul<Fq>(dtab, c, K, r));
     // g_c = s·g_a + r·g1_b − rs·δ₁ + L + H
     G1XYZZ g_c = g_a.mul(s);
     if (rnz) {
         G1XYZZ g1_b = sum[1 * (size_t)B + j];
         g1_b.add_affine(pk.beta_g1);
-        g1_b.add(delta.mul(s));
+        g1_b.add(fixed_base_mul<Fq>(dtab, c, K, s));
         g_c.add(g1_b.mul(r));
     }
-    g_c.add(delta.mul(rsv).neg());
+    g_c.add(fixed_base_mul<Fq>(dtab, c, K, rsv).neg());
     g_c.add(sum[2 * (size_t)B + j]);
     g_c.add(sum[3 * (size_t)B + j]);
     uint8_t* o = proofs + 128 * (size_t)j;
@@ -285,7 +301,8 @@ __global__ void __launch_bounds__(64) k_assemble_g1(ProverKeyDev pk, const G1XYZ
     compress_g1(g_a.to_affine(), o, af);
     compress_g1(g_c.to_affine(), o + 96, af ? af + 192 : nullptr);
 }
-__global__ void __launch_bounds__(64) k_assemble_g2(ProverKeyDev pk, const G2XYZZ* __restrict__ sum, u32 B, const uint8_t* __restrict__ rs,
+__global__ void __launch_bounds__(64) k_assemble_g2(ProverKeyDev pk, const G2Affine* __restrict__ dtab, int c, int K,
+                                                    const G2XYZZ* __restrict__ sum, u32 B, const uint8_t* __restrict__ rs,
                                                     uint8_t* __restrict__ proofs, uint8_t* __restrict__ affine) {
     const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= B) return;
@@ -293,7 +310,7 @@ __global__ void __launch_bounds__(64) k_assemble_g2(ProverKeyDev pk, const G2XYZ
     load_scalar_bytes(rs + 64 * (size_t)j + 32, s);
     G2XYZZ g2_b = sum[j];
     g2_b.add_affine(pk.beta_g2);
-    g2_b.add(G2XYZZ::from_affine(pk.delta_g2).mul(s));
+    g2_b.add(fixed_base_mul<Fq2>(dtab, c, K, s));
     compress_g2(g2_b.to_affine(), proofs + 128 * (size_t)j + 32, affine ? affine + 256 * (size_t)j + 64 : nullptr);
 }
 
@@ -336,15 +353,15 @@ void launch_msm_and_assemble(const FixedMsmPlan& plan, const ProverKeyDev& pk, c
         AccumArgs<Fq2> a;
         a.src[0] = d_vals; a.src[1] = d_h;
         for (int i = 0; i < 4; i++) { a.row[i] = plan.g2.row; a.table[i] = (const G2Affine*)plan.g2.table; a.which[i] = plan.g2.which_src; }
-        a.tasks = ws.tasks_g2; a.part = ws.part_g2; a.B = B; a.c = plan.c; a.K = plan.K;
+        a.tasks = ws.tasks_g2; a.part = ws.part_g2; a.B = B; a.c = plan.c2; a.K = plan.K2;
         dim3 grid((B + bx - 1) / bx, ws.n_tasks_g2);
         k_msm_accum<Fq2><<<grid, bx, 0, s>>>(a);
         if (ws.ev) cudaEventRecord(ws.ev[3], s);
         k_msm_reduce<Fq2><<<dim3((B + bx - 1) / bx, 1), bx, 0, s>>>(ws.part_g2, ws.tasks_g2, ws.n_tasks_g2, B, ws.sum_g2);
         if (ws.ev) cudaEventRecord(ws.ev[4], s);
     }
-    k_assemble_g1<<<(B + 63) / 64, 64, 0, s>>>(pk, ws.sum_g1, B, d_rs, d_proofs_out, d_proofs_affine);
-    k_assemble_g2<<<(B + 63) / 64, 64, 0, s>>>(pk, ws.sum_g2, B, d_rs, d_proofs_out, d_proofs_affine);
+    k_assemble_g1<<<(B + 63) / 64, 64, 0, s>>>(pk, plan.delta1_table, plan.c, plan.K, ws.sum_g1, B, d_rs, d_proofs_out, d_proofs_affine);
+    k_assemble_g2<<<(B + 63) / 64, 64, 0, s>>>(pk, plan.delta2_table, plan.c2, plan.K2, ws.sum_g2, B, d_rs, d_proofs_out, d_proofs_affine);
     if (ws.ev) cudaEventRecord(ws.ev[5], s);
 }
 

@@ -137,18 +137,79 @@ __global__ void __launch_bounds__(128) k_h_combine(Fr* __restrict__ a, const Fr*
     st_fp(a + o, ld_fp(a + o) * ld_fp(b + o) - ld_fp(c + o));
 }
 
+// Two fused decimation-in-frequency stages (halves h and h/2): one thread owns the 4 points
+// {i, i+h/2, i+h, i+3h/2} of one proof, so the data makes one HBM round trip per two stages.
+__global__ void __launch_bounds__(128) k_ntt_dif_r4(Fr* __restrict__ x, u32 B, u32 h, u32 stride, const Fr* __restrict__ tw) {
+    const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    const u32 q = h >> 1, t = blockIdx.y;
+    const u32 j = t & (q - 1);
+    const u32 base = ((t - j) << 2) + j;  // (t / q) · 2h + j
+    Fr* p0 = x + (size_t)base * B + p;
+    Fr* p1 = p0 + (size_t)q * B;
+    Fr* p2 = p0 + (size_t)h * B;
+    Fr* p3 = p2 + (size_t)q * B;
+    Fr x0 = ld_fp(p0), x1 = ld_fp(p1), x2 = ld_fp(p2), x3 = ld_fp(p3);
+    // stage A (half = h): (x0,x2) with ω^{j·stride}, (x1,x3) with ω^{(j+q)·stride}
+    Fr u0 = x0 + x2, u2 = x0 - x2, u1 = x1 + x3, u3 = x1 - x3;
+    if (j) u2 = u2 * ldg_fp(tw + (size_t)j * stride);
+    u3 = u3 * ldg_fp(tw + (size_t)(j + q) * stride);
+    // stage B (half = q, stride doubled): both pairs with ω^{j·2·stride}
+    Fr y0 = u0 + u1, y1 = u0 - u1, y2 = u2 + u3, y3 = u2 - u3;
+    if (j) {
+        const Fr wb = ldg_fp(tw + (size_t)j * 2 * stride);
+        y1 = y1 * wb;
+        y3 = y3 * wb;
+    }
+    st_fp(p0, y0); st_fp(p1, y1); st_fp(p2, y2); st_fp(p3, y3);
+}
+// Two fused decimation-in-time stages (halves m and 2m): points {i, i+m, i+2m, i+3m}
+__global__ void __launch_bounds__(128) k_ntt_dit_r4(Fr* __restrict__ x, u32 B, u32 m, u32 stride, const Fr* __restrict__ tw) {
+    const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    const u32 t = blockIdx.y;
+    const u32 j = t & (m - 1);
+    const u32 base = ((t - j) << 2) + j;  // (t / m) · 4m + j
+    Fr* p0 = x + (size_t)base * B + p;
+    Fr* p1 = p0 + (size_t)m * B;
+    Fr* p2 = p1 + (size_t)m * B;
+    Fr* p3 = p2 + (size_t)m * B;
+    Fr x0 = ld_fp(p0), x1 = ld_fp(p1), x2 = ld_fp(p2), x3 = ld_fp(p3);
+    // stage A (half = m, stride): (x0,x1) and (x2,x3) with ω^{j·stride}
+    if (j) {
+        const Fr wa = ldg_fp(tw + (size_t)j * stride);
+        x1 = x1 * wa;
+        x3 = x3 * wa;
+    }
+    Fr a0 = x0 + x1, a1 = x0 - x1, a2 = x2 + x3, a3 = x2 - x3;
+    // stage B (half = 2m, stride/2): (a0,a2) with ω^{j·stride/2}, (a1,a3) with ω^{(j+m)·stride/2}
+    const u32 sb = stride >> 1;
+    if (j) a2 = a2 * ldg_fp(tw + (size_t)j * sb);
+    a3 = a3 * ldg_fp(tw + (size_t)(j + m) * sb);
+    st_fp(p0, a0 + a2); st_fp(p2, a0 - a2); st_fp(p1, a1 + a3); st_fp(p3, a1 - a3);
+}
+
 static void ntt_dif(Fr* x, u32 log_n, u32 B, const Fr* tw, cudaStream_t s) {
     const u32 n = 1u << log_n;
-    dim3 grid((B + 127) / 128, n / 2);
-    for (u32 half = n / 2, stride = 1; half >= 1; half >>= 1, stride <<= 1)
-        k_ntt_dif_stage<<<grid, 128, 0, s>>>(x, B, half, stride, tw);
+    u32 half = n / 2, stride = 1;
+    while (half >= 2) {  // two stages per pass
+        k_ntt_dif_r4<<<dim3((B + 127) / 128, n / 4), 128, 0, s>>>(x, B, half, stride, tw);
+        half >>= 2;
+        stride <<= 2;
+    }
+    if (half == 1) k_ntt_dif_stage<<<dim3((B + 127) / 128, n / 2), 128, 0, s>>>(x, B, 1, stride, tw);
 }
 static void ntt_dit(Fr* x, u32 log_n, u32 B, const Fr* tw, cudaStream_t s) {
     const u32 n = 1u << log_n;
-    dim3 grid((B + 127) / 128, n / 2);
-    for (u32 half = 1, stride = n / 2; half < n; half <<= 1, stride >>= 1)
-        k_ntt_dit_stage<<<grid, 128, 0, s>>>(x, B, half, stride, tw);
+    u32 half = 1, stride = n / 2;
+    while (half * 2 < n) {
+        k_ntt_dit_r4<<<dim3((B + 127) / 128, n / 4), 128, 0, s>>>(x, B, half, stride, tw);
+        half <<= 2;
+        stride >>= 2;
+    }
+    if (half < n) k_ntt_dit_stage<<<dim3((B + 127) / 128, n / 2), 128, 0, s>>>(x, B, half, stride, tw);
 }
+u32 ntt_launches_per_transform(u32 log_n) { return log_n / 2 + (log_n & 1); }
 
 void launch_qap(const CircuitDev& c, const Fr* d_vals, Fr* d_a, Fr* d_b, Fr* d_c, u32 B, cudaStream_t s) {
     dim3 grid((B + 127) / 128, c.domain);

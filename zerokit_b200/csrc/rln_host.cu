@@ -253,8 +253,8 @@ class Rln {
     void prove_host(const std::vector<Witness>& ws, const uint8_t* rs, std::vector<RlnProof>& out);
     void witness_slots(const Witness& w, uint8_t* slots) const;
     void debug_w_h(const Witness& w, uint8_t* w_out, uint8_t* h_out);
-    void table_info(int* c, int* K, uint64_t* g1, uint64_t* g2, uint64_t* bytes) const {
-        *c = plan_.c; *K = plan_.K;
+    void table_info(int* c, int* K, uint64_t* g1, uint64_t* g2, uint64_t* bytes, int* c2, int* K2) const {
+        *c = plan_.c; *K = plan_.K; *c2 = plan_.c2; *K2 = plan_.K2;
         *g1 = (uint64_t)plan_.g1[0].n_bases + plan_.g1[1].n_bases + plan_.g1[2].n_bases + plan_.g1[3].n_bases;
         *g2 = plan_.g2.n_bases;
         *bytes = 0;
@@ -286,7 +286,7 @@ class Rln {
     DevMem d_prog_, d_consts_, d_signals_, d_a_ptr_, d_a_col_, d_a_val_, d_b_ptr_, d_b_col_, d_b_val_, d_tw_inv_, d_tw_fwd_, d_coset_;
     CircuitDev circ_{};
     // fixed-base tables
-    DevMem d_tab_[5], d_rows_[5], d_gamma_abc_;
+    DevMem d_tab_[5], d_rows_[5], d_gamma_abc_, d_delta1_tab_, d_delta2_tab_;
     FixedMsmPlan plan_{};
     ProverKeyDev pk_{};
     VerifyKeyDev vk_{};
@@ -297,7 +297,8 @@ class Rln {
     size_t cap_ = 0, max_batch_ = 4096;
     DevMem ws_inputs_, ws_rs_, ws_vals_, ws_a_, ws_b_, ws_c_, ws_err_, ws_part1_, ws_part2_, ws_sum1_, ws_sum2_, ws_proofs_, ws_values_, ws_affine_;
     std::map<u32, std::unique_ptr<TaskSet>> tasks_;
-    cudaStream_t stream_ = nullptr;
+    cudaStream_t stream_ = nullptr, side_ = nullptr;
+    cudaEvent_t fork_ = nullptr, join_ = nullptr;
     cudaEvent_t ev_[5];
     cudaEvent_t mev_[6];
 };
@@ -354,6 +355,9 @@ Rln::Rln(size_t tree_depth, const uint8_t* zkey, size_t zlen, const uint8_t* gra
     check_graph_shape();
     max_batch_ = (size_t)env_int("RLN_B200_MAX_BATCH", 4096);
     ZK_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    ZK_CUDA_CHECK(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
+    ZK_CUDA_CHECK(cudaEventCreateWithFlags(&fork_, cudaEventDisableTiming));
+    ZK_CUDA_CHECK(cudaEventCreateWithFlags(&join_, cudaEventDisableTiming));
     for (auto& e : ev_) ZK_CUDA_CHECK(cudaEventCreate(&e));
     for (auto& e : mev_) ZK_CUDA_CHECK(cudaEventCreate(&e));
     build_circuit();
@@ -365,6 +369,9 @@ Rln::~Rln() {
     for (auto& e : ev_) cudaEventDestroy(e);
     for (auto& e : mev_) cudaEventDestroy(e);
     if (stream_) cudaStreamDestroy(stream_);
+    if (side_) cudaStreamDestroy(side_);
+    if (fork_) cudaEventDestroy(fork_);
+    if (join_) cudaEventDestroy(join_);
 }
 
 void Rln::check_graph_shape() {
@@ -500,19 +507,28 @@ void Rln::build_tables() {
     pick[3] = non_inf(zk_.h_query, 64, domain_, 0);
     pick[4] = non_inf(zk_.b_g2, 128, nw, 0);
     size_t n_g1 = pick[0].size() + pick[1].size() + pick[2].size() + pick[3].size(), n_g2 = pick[4].size();
-    int c = env_int("RLN_B200_WINDOW_BITS", 0);
+    // Window widths: G1 tables cost 64·K·2^(c−1) bytes per base, G2 tables twice that but have 6× fewer bases, so G2
+    // gets the wider window when HBM allows (fewer additions per term: K = ⌈255/c⌉).
+    auto table_bytes = [&](int c1, int c2) {
+        size_t k1 = (255 + c1 - 1) / c1, k2 = (255 + c2 - 1) / c2;
+        return (n_g1 * 64 * k1 << (c1 - 1)) + (n_g2 * 128 * k2 << (c2 - 1));
+    };
+    int c = env_int("RLN_B200_WINDOW_BITS", 0), c2 = env_int("RLN_B200_WINDOW_BITS_G2", 0);
+    const size_t reserve = (size_t)26 << 30;  // proving workspace, tree, MSM scratch, slack
     if (c == 0) {
-        const size_t reserve = (size_t)24 << 30;  // proving workspace, tree, slack
-        for (c = 12; c > 5; c--) {
-            int K = (255 + c - 1) / c;
-            size_t need = (n_g1 * 64 + n_g2 * 128) * (size_t)K << (c - 1);
-            if (need + reserve < free_b) break;
-        }
+        for (c = 12; c > 5; c--)
+            if (table_bytes(c, c2 ? c2 : c) + reserve < free_b) break;
     }
-    if (c < 5 || c > 16) throw RlnError("Configuration error: RLN_B200_WINDOW_BITS must be in [5, 16]");
-    const int K = (255 + c - 1) / c;
+    if (c2 == 0) {
+        for (c2 = c + 2; c2 > c; c2--)
+            if (table_bytes(c, c2) + reserve < free_b) break;
+    }
+    if (c < 5 || c > 16 || c2 < 5 || c2 > 16) throw RlnError("Configuration error: RLN_B200_WINDOW_BITS[_G2] must be in [5, 16]");
+    const int K = (255 + c - 1) / c, K2 = (255 + c2 - 1) / c2;
     plan_.c = c;
     plan_.K = K;
+    plan_.c2 = c2;
+    plan_.K2 = K2;
     // scalar row of each base: A/B use wire i → node signals[i]; L uses wire ni+i; H uses row i of the h matrix
     for (int g = 0; g < 5; g++) {
         std::vector<uint32_t> rows(pick[g].size());
@@ -523,7 +539,7 @@ void Rln::build_tables() {
         }
         d_rows_[g].upload(rows.data(), rows.size() * 4);
         DevMem bases;
-        const size_t half = (size_t)1 << (c - 1);
+        const size_t half = (size_t)1 << ((g < 4 ? c : c2) - 1);
         if (g < 4) {
             const std::vector<uint8_t>& raw = g == 0 ? zk_.a_query : g == 1 ? zk_.b_g1 : g == 2 ? zk_.l_query : zk_.h_query;
             upload_points_g1(raw, pick[g], bases);
@@ -531,8 +547,8 @@ void Rln::build_tables() {
             launch_build_table_g1(bases.as<G1Affine>(), (u32)pick[g].size(), c, K, d_tab_[g].as<G1Affine>(), 0);
         } else {
             upload_points_g2(zk_.b_g2, pick[g], bases);
-            d_tab_[g].alloc(sizeof(G2Affine) * pick[g].size() * K * half);
-            launch_build_table_g2(bases.as<G2Affine>(), (u32)pick[g].size(), c, K, d_tab_[g].as<G2Affine>(), 0);
+            d_tab_[g].alloc(sizeof(G2Affine) * pick[g].size() * K2 * half);
+            launch_build_table_g2(bases.as<G2Affine>(), (u32)pick[g].size(), c2, K2, d_tab_[g].as<G2Affine>(), 0);
         }
         g_launch_count += 2;
         ZK_CUDA_CHECK(cudaDeviceSynchronize());
@@ -541,6 +557,20 @@ void Rln::build_tables() {
         dst.row = d_rows_[g].as<u32>();
         dst.table = d_tab_[g].p;
         dst.which_src = g == 3 ? 1 : 0;
+    }
+    {   // window tables of δ₁ and δ₂ for the blinding terms of the assembly
+        std::vector<uint32_t> one = {0};
+        DevMem b1, b2;
+        upload_points_g1(zk_.delta_g1, one, b1);
+        upload_points_g2(zk_.delta_g2, one, b2);
+        d_delta1_tab_.alloc(sizeof(G1Affine) * K * ((size_t)1 << (c - 1)));
+        d_delta2_tab_.alloc(sizeof(G2Affine) * K2 * ((size_t)1 << (c2 - 1)));
+        launch_build_table_g1(b1.as<G1Affine>(), 1, c, K, d_delta1_tab_.as<G1Affine>(), 0);
+        launch_build_table_g2(b2.as<G2Affine>(), 1, c2, K2, d_delta2_tab_.as<G2Affine>(), 0);
+        g_launch_count += 4;
+        ZK_CUDA_CHECK(cudaDeviceSynchronize());
+        plan_.delta1_table = d_delta1_tab_.as<G1Affine>();
+        plan_.delta2_table = d_delta2_tab_.as<G2Affine>();
     }
     pk_.alpha_g1 = fetch_g1(zk_.alpha_g1);
     pk_.beta_g1 = fetch_g1(zk_.beta_g1);
@@ -721,6 +751,12 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
             ws_part2_.ensure((size_t)ts.n2 * B * sizeof(G2XYZZ));
         }
         const uint8_t* in = d_inputs + off * (size_t)gh_.n_slots * 32;
+        if (d_values) {  // proof values only need the inputs: a latency-bound kernel, run beside the main pipeline
+            ZK_CUDA_CHECK(cudaEventRecord(fork_, s));
+            ZK_CUDA_CHECK(cudaStreamWaitEvent(side_, fork_, 0));
+            launch_proof_values(in, slots_, B, d_values + 160 * off, side_);
+            ZK_CUDA_CHECK(cudaEventRecord(join_, side_));
+        }
         ZK_CUDA_CHECK(cudaEventRecord(ev_[0], s));
         launch_witness(circ_, in, ws_vals_.as<Fr>(), B, ws_err_.as<u32>(), s);
         ZK_CUDA_CHECK(cudaEventRecord(ev_[1], s));
@@ -739,9 +775,9 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
         launch_msm_and_assemble(plan_, pk_, ws_vals_.as<Fr>(), ws_a_.as<Fr>(), B, d_rs + 64 * off, mw, d_proofs + 128 * off,
                                 d_affine ? d_affine + 256 * off : nullptr, s);
         ZK_CUDA_CHECK(cudaEventRecord(ev_[3], s));
-        if (d_values) launch_proof_values(in, slots_, B, d_values + 160 * off, s);
+        if (d_values) ZK_CUDA_CHECK(cudaStreamWaitEvent(s, join_, 0));
         ZK_CUDA_CHECK(cudaEventRecord(ev_[4], s));
-        g_launch_count += 1 + (2 + 3 * (2 * log_domain_ + 1)) + 6 + (d_values ? 1 : 0);
+        g_launch_count += 1 + (2 + 3 * (2 * ntt_launches_per_transform(log_domain_) + 1)) + 6 + (d_values ? 1 : 0);
         // graph-evaluation failures surface as errors, like WitnessCalcError::GraphEvaluation (rln/src/circuit/iden3calc.rs:52-53)
         std::vector<u32> err(B);
         ZK_CUDA_CHECK(cudaMemcpyAsync(err.data(), ws_err_.p, 4 * B, cudaMemcpyDeviceToHost, s));
@@ -825,7 +861,7 @@ void Rln::debug_w_h(const Witness& w, uint8_t* w_out, uint8_t* h_out) {
     ZK_CUDA_CHECK(cudaMemcpyAsync(ws_inputs_.p, slots.data(), slots.size(), cudaMemcpyHostToDevice, stream_));
     launch_witness(circ_, ws_inputs_.as<uint8_t>(), ws_vals_.as<Fr>(), 1, ws_err_.as<u32>(), stream_);
     launch_qap(circ_, ws_vals_.as<Fr>(), ws_a_.as<Fr>(), ws_b_.as<Fr>(), ws_c_.as<Fr>(), 1, stream_);
-    g_launch_count += 3 + 3 * (2 * log_domain_ + 1);
+    g_launch_count += 3 + 3 * (2 * ntt_launches_per_transform(log_domain_) + 1);
     DevMem vals_b, h_b;
     vals_b.alloc(32 * gh_.prog.size());
     h_b.alloc(32 * (size_t)domain_);
@@ -1339,8 +1375,9 @@ void rlnb200_last_stage_ms(FFI_RLN_t* const* rln, float out[8]) {
 int rlnb200_set_device(int device, RlnString* err) {
     INT_OP(ZK_CUDA_CHECK(cudaSetDevice(device));)
 }
-int rlnb200_table_info(FFI_RLN_t* const* rln, int* window_bits, int* windows, uint64_t* g1_bases, uint64_t* g2_bases, uint64_t* table_bytes) {
-    (*rln)->r->table_info(window_bits, windows, g1_bases, g2_bases, table_bytes);
+int rlnb200_table_info(FFI_RLN_t* const* rln, int* window_bits, int* windows, uint64_t* g1_bases, uint64_t* g2_bases, uint64_t* table_bytes,
+                       int* window_bits_g2, int* windows_g2) {
+    (*rln)->r->table_info(window_bits, windows, g1_bases, g2_bases, table_bytes, window_bits_g2, windows_g2);
     return 0;
 }
 int rlnb200_set_leaves_from_bytes(FFI_RLN_t** rln, size_t index, const uint8_t* leaves_le, size_t count, RlnString* err) {

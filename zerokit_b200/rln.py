@@ -361,10 +361,11 @@ class RLN:
         return dict(zip(("witness", "qap", "msm_g1_accum", "msm_g1_reduce", "msm_g2_accum", "msm_g2_reduce", "assemble", "values"), list(out)))
 
     def table_info(self):
-        c, k = ctypes.c_int(), ctypes.c_int()
+        c, k, c2, k2 = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         g1, g2, b = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
-        ffi.lib().rlnb200_table_info(byref(self._h), byref(c), byref(k), byref(g1), byref(g2), byref(b))
-        return dict(window_bits=c.value, windows=k.value, g1_bases=g1.value, g2_bases=g2.value, table_bytes=b.value)
+        ffi.lib().rlnb200_table_info(byref(self._h), byref(c), byref(k), byref(g1), byref(g2), byref(b), byref(c2), byref(k2))
+        return dict(window_bits=c.value, windows=k.value, window_bits_g2=c2.value, windows_g2=k2.value,
+                    g1_bases=g1.value, g2_bases=g2.value, table_bytes=b.value)
 
     def debug_witness_and_h(self, witness_le: bytes):
         nw, dom = ffi.lib().rlnb200_num_wires(byref(self._h)), ffi.lib().rlnb200_domain_size(byref(self._h))
