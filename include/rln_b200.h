@@ -43,6 +43,8 @@ typedef struct FFI_RLN FFI_RLN_t;                      /* rln/src/ffi/ffi_rln.rs
 typedef struct FFI_RLNProof FFI_RLNProof_t;            /* rln/src/ffi/ffi_rln.rs:153-155 */
 typedef struct FFI_RLNProofValues FFI_RLNProofValues_t;/* rln/src/ffi/ffi_rln.rs:714-716 */
 typedef struct FFI_RLNWitnessInput FFI_RLNWitnessInput_t; /* rln/src/ffi/ffi_rln.rs:322-324 */
+typedef struct FFI_RLNPartialWitnessInput FFI_RLNPartialWitnessInput_t; /* rln/src/ffi/ffi_rln.rs:563-565 */
+typedef struct FFI_RLNPartialProof FFI_RLNPartialProof_t;             /* rln/src/ffi/ffi_rln.rs:240-242 */
 typedef struct FFI_MerkleProof {                       /* rln/src/ffi/ffi_tree.rs:13-18 */
     Vec_CFr_t path_elements;
     Vec_uint8_t path_index;
@@ -53,6 +55,8 @@ typedef struct CResult_FFI_RLN { FFI_RLN_t *ok; RlnString err; } CResult_FFI_RLN
 typedef struct CResult_FFI_RLNProof { FFI_RLNProof_t *ok; RlnString err; } CResult_FFI_RLNProof_t;
 typedef struct CResult_FFI_RLNProofValues { FFI_RLNProofValues_t *ok; RlnString err; } CResult_FFI_RLNProofValues_t;
 typedef struct CResult_FFI_RLNWitnessInput { FFI_RLNWitnessInput_t *ok; RlnString err; } CResult_FFI_RLNWitnessInput_t;
+typedef struct CResult_FFI_RLNPartialWitnessInput { FFI_RLNPartialWitnessInput_t *ok; RlnString err; } CResult_FFI_RLNPartialWitnessInput_t;
+typedef struct CResult_FFI_RLNPartialProof { FFI_RLNPartialProof_t *ok; RlnString err; } CResult_FFI_RLNPartialProof_t;
 typedef struct CResult_FFI_MerkleProof { FFI_MerkleProof_t *ok; RlnString err; } CResult_FFI_MerkleProof_t;
 typedef struct CResult_CFr { CFr_t *ok; RlnString err; } CResult_CFr_t;
 typedef struct CResult_Vec_uint8 { Vec_uint8_t ok; RlnString err; } CResult_Vec_uint8_t;
@@ -99,6 +103,19 @@ CBoolResult_t ffi_verify_rln_proof(FFI_RLN_t *const *rln, FFI_RLNProof_t *const 
 CBoolResult_t ffi_verify_with_roots(FFI_RLN_t *const *rln, FFI_RLNProof_t *const *rln_proof,
                                     const Vec_CFr_t *roots, const CFr_t *x);                    /* :986-1010 */
 
+/* two-phase proving: precompute everything that does not depend on (message_id, x, external_nullifier), finish later
+ * (rln/src/protocol/proof.rs:783-849, rln/src/partial_proof.rs:108-274) */
+CResult_FFI_RLNPartialWitnessInput_t ffi_rln_partial_witness_input_new(
+    const CFr_t *identity_secret, const CFr_t *user_message_limit, const Vec_CFr_t *path_elements,
+    const Vec_uint8_t *identity_path_index);                                                    /* :567-592 */
+void ffi_rln_partial_witness_input_free(FFI_RLNPartialWitnessInput_t *witness);                 /* :707-710 */
+CResult_FFI_RLNPartialProof_t ffi_generate_partial_zk_proof(
+    FFI_RLN_t *const *rln, FFI_RLNPartialWitnessInput_t *const *partial_witness);               /* :921-936 */
+CResult_FFI_RLNProof_t ffi_finish_rln_proof(FFI_RLN_t *const *rln, FFI_RLNPartialProof_t *const *partial_proof,
+                                            FFI_RLNWitnessInput_t *const *witness);             /* :938-960 */
+CResult_Vec_uint8_t ffi_rln_partial_proof_to_bytes_le(FFI_RLNPartialProof_t *const *partial_proof); /* :251-265 */
+void ffi_rln_partial_proof_free(FFI_RLNPartialProof_t *partial_proof);                          /* :283-286 */
+
 FFI_RLNProofValues_t *ffi_rln_proof_get_values(FFI_RLNProof_t *const *rln_proof);               /* :157-162 */
 uint8_t ffi_rln_proof_get_version_byte(FFI_RLNProof_t *const *rln_proof);                       /* :164-167 */
 CResult_Vec_uint8_t ffi_rln_proof_to_bytes_le(FFI_RLNProof_t *const *rln_proof);                /* :169-183 */
@@ -144,6 +161,17 @@ Vec_CFr_t ffi_key_gen(void);                                                    
  * caller so that proofs are reproducible bit for bit. */
 CResult_FFI_RLNProof_t rlnb200_generate_rln_proof_with_rs(FFI_RLN_t *const *rln, FFI_RLNWitnessInput_t *const *witness,
                                                           const CFr_t *r, const CFr_t *s);
+
+/* finish_zk_proof_with_rs (rln/src/protocol/proof.rs:822-849) behind the ABI */
+CResult_FFI_RLNProof_t rlnb200_finish_rln_proof_with_rs(FFI_RLN_t *const *rln, FFI_RLNPartialProof_t *const *partial_proof,
+                                                        FFI_RLNWitnessInput_t *const *witness, const CFr_t *r, const CFr_t *s);
+/* ffi_bytes_le_to_rln_partial_proof (ffi_rln.rs:267-281) needs a handle here: the points are validated on the GPU */
+CResult_FFI_RLNPartialProof_t rlnb200_bytes_le_to_rln_partial_proof(FFI_RLN_t *const *rln, const Vec_uint8_t *bytes);
+/* batched two-phase proving on host buffers: witness records as for rlnb200_prove_batch (message_id / x / external_nullifier
+ * are ignored by the partial phase); partial points are n × 320 bytes (canonical affine π_a 64 | ρ 64 | π_b 128 | π_c 64) */
+int rlnb200_partial_batch(FFI_RLN_t *const *rln, const uint8_t *witnesses, size_t n, uint8_t *partial_out, RlnString *err);
+int rlnb200_finish_batch(FFI_RLN_t *const *rln, const uint8_t *witnesses, size_t n, const uint8_t *partial, const uint8_t *rs,
+                         uint8_t *proofs_out, RlnString *err);
 
 /* Batched proving, HOST buffers.  witnesses: n concatenated rln_witness_to_bytes_le records (single
  * message-id layout, rln/src/protocol/witness.rs:369-415; all of length 1+32*(5+depth)+16+depth).

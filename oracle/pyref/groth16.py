@@ -387,6 +387,86 @@ def prove(z, w, h, r, s):
     return (g_a, g2_b, g_c)
 
 
+# ----------------------------------------------------------------------------- partial proofs
+UNKNOWN_INPUTS_SINGLE = ("messageId", "x", "externalNullifier")   # witness.rs:887-931 (None entries)
+
+
+def known_wire_mask(g):
+    """graph.rs:274-312 evaluate_partial: a node is known iff all of its operands are; inputs are known unless
+    they belong to messageId / x / externalNullifier.  Returns one bool per witness signal (wire)."""
+    unknown_slots = set()
+    for name in UNKNOWN_INPUTS_SINGLE:
+        off, ln = g.inputs[name]
+        unknown_slots.update(range(off, off + ln))
+    known = []
+    for nd in g.nodes:
+        k = nd[0]
+        if k == "const":
+            v = True
+        elif k == "input":
+            v = nd[1] not in unknown_slots
+        elif k == "uno":
+            v = known[nd[2]]
+        elif k == "duo":
+            v = known[nd[2]] and known[nd[3]]
+        else:
+            v = known[nd[2]] and known[nd[3]] and known[nd[4]]
+        known.append(v)
+    return [known[i] for i in g.signals]
+
+
+def prove_partial(z, g, w_known):
+    """partial_proof.rs:108-179.  w_known: full-length wire vector whose known entries are correct (unknown
+    entries are ignored).  Returns (mask over w[1:], partial_pi_a, partial_rho, partial_pi_b, partial_pi_c)."""
+    o1, o2 = OPS1, OPS2
+    wire_known = known_wire_mask(g)
+    assert wire_known[0]
+    mask = wire_known[1:]
+    ni = z.num_instance
+    idx = [i for i in range(1, len(w_known)) if wire_known[i]]
+    sc = [w_known[i] for i in idx]
+    a = msm(o1, [z.a_query[i] for i in idx], sc)
+    b1 = msm(o1, [z.b_g1_query[i] for i in idx], sc)
+    b2 = msm(o2, [z.b_g2_query[i] for i in idx], sc)
+    lidx = [i for i in range(ni, len(w_known)) if wire_known[i]]
+    l = msm(o1, [z.l_query[i - ni] for i in lidx], [w_known[i] for i in lidx])
+    pi_a = pt_add(o1, pt_add(o1, z.alpha_g1, z.a_query[0]), a)
+    rho = pt_add(o1, pt_add(o1, z.beta_g1, z.b_g1_query[0]), b1)
+    pi_b = pt_add(o2, pt_add(o2, z.beta_g2, z.b_g2_query[0]), b2)
+    return mask, pi_a, rho, pi_b, l
+
+
+def finish_partial(z, partial, w, h, r, s):
+    """partial_proof.rs:182-274"""
+    o1, o2 = OPS1, OPS2
+    mask, pi_a, rho, pi_b, pi_c = partial
+    ni = z.num_instance
+    idx = [i for i in range(1, len(w)) if not mask[i - 1]]
+    sc = [w[i] for i in idx]
+    g_a = pt_add(o1, pt_add(o1, pi_a, msm(o1, [z.a_query[i] for i in idx], sc)), pt_mul(o1, z.delta_g1, r))
+    if r % R:
+        g1_b = pt_add(o1, pt_add(o1, rho, msm(o1, [z.b_g1_query[i] for i in idx], sc)), pt_mul(o1, z.delta_g1, s))
+    else:
+        g1_b = INF
+    g2_b = pt_add(o2, pt_add(o2, pi_b, msm(o2, [z.b_g2_query[i] for i in idx], sc)), pt_mul(o2, z.delta_g2, s))
+    lidx = [i for i in range(ni, len(w)) if not mask[i - 1]]
+    l_acc = pt_add(o1, pi_c, msm(o1, [z.l_query[i - ni] for i in lidx], [w[i] for i in lidx]))
+    h_acc = msm(o1, z.h_query, h)
+    g_c = pt_mul(o1, g_a, s)
+    g_c = pt_add(o1, g_c, pt_mul(o1, g1_b, r))
+    g_c = pt_add(o1, g_c, pt_neg(o1, pt_mul(o1, z.delta_g1, r * s % R)))
+    g_c = pt_add(o1, pt_add(o1, g_c, l_acc), h_acc)
+    return (g_a, g2_b, g_c)
+
+
+def partial_proof_to_bytes_le(partial):
+    """proof.rs:537-547: version | ark compressed PartialProof = Vec<bool> mask (u64 len + 1 byte each) |
+    partial_pi_a | partial_rho | partial_pi_b | partial_pi_c (projective points serialise as compressed affine)"""
+    mask, pi_a, rho, pi_b, pi_c = partial
+    return (b"\x00" + struct.pack("<Q", len(mask)) + bytes(int(m) for m in mask) + g1_compress(pi_a) + g1_compress(rho)
+            + g2_compress(pi_b) + g1_compress(pi_c))
+
+
 def verify(z, proof, public_inputs):
     """ark-groth16 verify_proof: e(A,B) == e(α,β)·e(vk_x,γ)·e(C,δ)."""
     a, b, c = proof

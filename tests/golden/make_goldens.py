@@ -199,6 +199,27 @@ def derived():
     out["kat_proof_d10"] = kat_proof(10, next(fs), 1000, 7, next(fs), next(fs), next(fs), next(fs), "depth-10 random")
     out["kat_proof_d20_r0"] = kat_proof(20, 987654321, 5, 4, 99, 3, 0, 5, "r = 0 (g1_b skipped, partial_proof.rs:242-248)")
 
+    # partial proof (rln/src/partial_proof.rs:108-274; rln/tests/protocol.rs:222-248 pins full == partial + finish)
+    k = out["kat_proof_d10"]
+    z = G.parse_zkey(open(os.path.join(RES, "tree_depth_10", "rln_final.arkzkey"), "rb").read())
+    g = G.parse_graph(open(os.path.join(RES, "tree_depth_10", "graph.bin"), "rb").read())
+    inp = k["inputs"]
+    pe = [P.poseidon([i + 7]) for i in range(10)]
+    idx = [(5 * i + 1) % 2 for i in range(10)]
+    args = (int(inp["identity_secret"]), int(inp["user_message_limit"]), int(inp["message_id"]), pe, idx, int(inp["x"]),
+            int(inp["external_nullifier"]))
+    w = G.evaluate(g, G.inputs_buffer(g, *args))
+    # the known wires must not depend on the unknown inputs: evaluate with those zeroed and compare
+    w0 = G.evaluate(g, G.inputs_buffer(g, args[0], args[1], 0, pe, idx, 0, 0))
+    km = G.known_wire_mask(g)
+    assert all(a == b for a, b, m in zip(w, w0, km) if m)
+    partial = G.prove_partial(z, g, w0)
+    h = G.witness_map(z, w)
+    fin = G.finish_partial(z, partial, w, h, int(inp["r"]), int(inp["s"]))
+    assert G.proof_to_bytes(fin).hex() == k["proof_bytes_hex"], "full proof != partial + finish"
+    out["partial_proof_d10"] = {"known_wires": sum(km), "unknown_wires": len(km) - sum(km),
+                                "partial_le_hex": G.partial_proof_to_bytes_le(partial).hex(),
+                                "finished_proof_bytes_hex": G.proof_to_bytes(fin).hex()}
     # G1 / G2 MSM samples
     rnd = random.Random(11)
     fs = fr_stream(2)

@@ -285,6 +285,47 @@ def test_batch_proofs_bit_equal_to_oracle(z, oracle, depth, n, rln10, rln20):
     assert rln.verify_with_roots(pa, pa.values.x, []) and rln.verify_with_roots(pb, pb.values.x, [])
 
 
+def test_partial_proofs(z, rln10, rln20, goldens, oracle):
+    """rln/tests/protocol.rs:222-248: with fixed (r, s), full proof == partial + finish; partial bytes == the oracle's"""
+    k = goldens["derived"]["kat_proof_d10"]
+    pg = goldens["derived"]["partial_proof_d10"]
+    args = kat_witness_args(10, k["inputs"])
+    wit = z.RLNWitnessInput.from_bytes_le(witness_le(*args))
+    pw = z.RLNPartialWitnessInput.new(args[0], args[1], args[3], args[4])
+    partial = rln10.generate_partial_zk_proof(pw)
+    assert partial.to_bytes_le().hex() == pg["partial_le_hex"]
+    r, s = int(k["inputs"]["r"]), int(k["inputs"]["s"])
+    fin = rln10.finish_rln_proof_with_rs(partial, wit, r, s)
+    assert fin.to_bytes_le().hex() == k["rln_proof_le_hex"]
+    # through bytes, and with fresh randomness
+    again = rln10.partial_proof_from_bytes_le(partial.to_bytes_le())
+    assert rln10.finish_rln_proof_with_rs(again, wit, r, s).to_bytes_le().hex() == k["rln_proof_le_hex"]
+    p2 = rln10.finish_rln_proof(partial, wit)
+    assert p2.proof_bytes != fin.proof_bytes and rln10.verify_with_roots(p2, p2.values.x, [])
+    bad = bytearray(partial.to_bytes_le())
+    bad[9] ^= 1  # flip a mask bit: no longer the circuit's mask
+    with pytest.raises(z.RLNError, match="malformed verifying key"):
+        rln10.finish_rln_proof_with_rs(rln10.partial_proof_from_bytes_le(bytes(bad)), wit, r, s)
+    # batch, depth 20: one partial proof per member reused for two different messages
+    ctx = oracle.Ctx(resource(20, "rln_final.arkzkey"), resource(20, "graph.bin"))
+    n = 40
+    recs, rs, inputs, root = _make_batch(rln20, ctx, 20, n, 91)
+    partial_pts = rln20.partial_batch(recs, n)
+    assert rln20.finish_batch(recs, n, partial_pts, rs) == rln20.prove_batch(recs, n, rs)
+    # a second message for the same members: new message_id / x / external_nullifier, same partial points
+    rec = len(recs) // n
+    recs2 = bytearray(recs)
+    fs = fr_stream(92)
+    for j in range(n):
+        b = rec * j
+        recs2[b + 65:b + 97] = ((j + 1) % 100).to_bytes(32, "little")
+        recs2[b + rec - 64:b + rec - 32] = next(fs).to_bytes(32, "little")
+        recs2[b + rec - 32:b + rec] = (777 + j).to_bytes(32, "little")
+    out2 = rln20.finish_batch(bytes(recs2), n, partial_pts, rs)
+    assert out2 == rln20.prove_batch(bytes(recs2), n, rs)
+    assert rln20.verify_batch(out2, n) == [1] * n
+
+
 def test_witness_errors(z, rln20):
     with pytest.raises(z.RLNError, match="tree_depth"):
         w = z.RLNWitnessInput.new_single(5, 10, 3, [1, 2], [0, 1], 7, 9)

@@ -77,7 +77,8 @@ u32 ntt_launches_per_transform(u32 log_n);
 
 // ---- k_msm_fixed.cu ------------------------------------------------------------------------
 struct MsmGroupDev {
-    u32 n_bases;         // non-infinity bases
+    u32 n_bases;         // non-infinity bases, ordered [wires known to a partial witness | the rest]
+    u32 n_known;         // length of the known prefix (partial proofs, rln/src/partial_proof.rs:108-179)
     const u32* row;      // scalar row index per base in the source matrix
     const void* table;   // [base][window][2^(c-1)] affine points
     u32 which_src;       // 0: vals matrix, 1: h matrix
@@ -107,12 +108,19 @@ struct MsmWorkspace {
     u32 n_tasks_g1, n_tasks_g2;
     cudaEvent_t* ev;  // optional: 6 events recorded around [g1 accum, g1 reduce, g2 accum, g2 reduce, assemble]
 };
-// all five MSMs for B proofs + assembly (partial_proof.rs:226-273) + affine + ark-compressed bytes.
-// rs: B × 64 canonical bytes (r | s).  proofs_out: B × 128 bytes.  proofs_affine (optional): B × 256 bytes canonical A|B|C
-void launch_msm_and_assemble(const FixedMsmPlan& plan, const ProverKeyDev& pk, const Fr* d_vals, const Fr* d_h, u32 B,
-                             const uint8_t* d_rs, MsmWorkspace& ws, uint8_t* d_proofs_out, uint8_t* d_proofs_affine,
-                             cudaStream_t s);
-std::vector<MsmTask> msm_make_tasks(const FixedMsmPlan& plan, u32 B, bool g2);
+// MSM phases: all bases (full proof), the known prefix of A/B₁/B₂/L (partial proof), or the unknown suffix plus H (finish)
+enum MsmPhase { MSM_FULL = 0, MSM_KNOWN = 1, MSM_UNKNOWN = 2 };
+std::vector<MsmTask> msm_make_tasks(const FixedMsmPlan& plan, u32 B, bool g2, int phase);
+// accumulate + reduce over ws.tasks_* → ws.sum_g1[4][B], ws.sum_g2[B]
+void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, u32 B, MsmWorkspace& ws, cudaStream_t s);
+// assembly (partial_proof.rs:226-273) + affine + ark-compressed bytes.  rs: B × 64 canonical bytes (r | s).
+// d_partial (optional): B × 320 bytes canonical affine partial_pi_a | partial_rho | partial_pi_b | partial_pi_c that replace
+// α₁ / β₁ / β₂ / 0 (finish_partial_proof_with_assignment, partial_proof.rs:182-274).
+// proofs_out: B × 128 bytes.  proofs_affine (optional): B × 256 bytes canonical A|B|C
+void launch_assemble(const FixedMsmPlan& plan, const ProverKeyDev& pk, u32 B, const uint8_t* d_rs, MsmWorkspace& ws,
+                     const uint8_t* d_partial, uint8_t* d_proofs_out, uint8_t* d_proofs_affine, cudaStream_t s);
+// partial proof points from the sums of the known prefix: out_affine B × 320 canonical, out_compressed B × 160 ark-compressed
+void launch_partial_out(const ProverKeyDev& pk, u32 B, MsmWorkspace& ws, uint8_t* d_out_affine, uint8_t* d_out_compressed, cudaStream_t s);
 
 // ---- k_msm_var.cu --------------------------------------------------------------------------
 // variable-base G1 Pippenger MSM (rln/src/partial_proof.rs:98-104 `msm`): bases affine Montgomery (device),

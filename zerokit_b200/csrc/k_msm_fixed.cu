@@ -254,6 +254,45 @@ __device__ void compress_g2(const G2Affine& p, uint8_t* out, uint8_t* affine_out
     store_words(out + 32, x1);
 }
 
+__device__ __forceinline__ Fq load_fq_canonical(const uint8_t* p, bool mask_flags) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    u32 c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (mask_flags) c[7] &= 0x3fffffffu;
+    return Fq::from_canonical(c);
+}
+__device__ __forceinline__ G1Affine load_affine_g1(const uint8_t* p) {  // x|y canonical, 0x40 in the last byte = infinity
+    if (p[63] & 0x40) return G1Affine::infinity();
+    return {load_fq_canonical(p, false), load_fq_canonical(p + 32, true)};
+}
+__device__ __forceinline__ G2Affine load_affine_g2(const uint8_t* p) {
+    if (p[127] & 0x40) return G2Affine::infinity();
+    return {{load_fq_canonical(p, false), load_fq_canonical(p + 32, false)}, {load_fq_canonical(p + 64, false), load_fq_canonical(p + 96, true)}};
+}
+
+// partial proof points (partial_proof.rs:159-170): π_a = α₁ + ΣA, ρ = β₁ + ΣB₁, π_b = β₂ + ΣB₂, π_c = ΣL over the known wires
+__global__ void __launch_bounds__(64) k_partial_g1(ProverKeyDev pk, const G1XYZZ* __restrict__ sum, u32 B, uint8_t* __restrict__ out_affine,
+                                                   uint8_t* __restrict__ out_comp) {
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= B) return;
+    G1XYZZ a = sum[0 * (size_t)B + j], b = sum[1 * (size_t)B + j], c = sum[2 * (size_t)B + j];
+    a.add_affine(pk.alpha_g1);
+    b.add_affine(pk.beta_g1);
+    uint8_t* af = out_affine + 320 * (size_t)j;
+    uint8_t* cp = out_comp + 160 * (size_t)j;
+    compress_g1(a.to_affine(), cp, af);
+    compress_g1(b.to_affine(), cp + 32, af + 64);
+    compress_g1(c.to_affine(), cp + 128, af + 256);
+}
+__global__ void __launch_bounds__(64) k_partial_g2(ProverKeyDev pk, const G2XYZZ* __restrict__ sum, u32 B, uint8_t* __restrict__ out_affine,
+                                                   uint8_t* __restrict__ out_comp) {
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= B) return;
+    G2XYZZ b = sum[j];
+    b.add_affine(pk.beta_g2);
+    compress_g2(b.to_affine(), out_comp + 160 * (size_t)j + 64, out_affine + 320 * (size_t)j + 128);
+}
+
 // k·P for the fixed point whose window table is `tb` ([K][2^(c-1)] multiples): K mixed additions, no doublings
 template <class F>
 __device__ XYZZ<F> fixed_base_mul(const Affine<F>* __restrict__ tb, int c, int K, const u32* k) {
@@ -272,9 +311,17 @@ __device__ XYZZ<F> fixed_base_mul(const Affine<F>* __restrict__ tb, int c, int K
 
 __global__ void __launch_bounds__(64) k_assemble_g1(ProverKeyDev pk, const G1Affine* __restrict__ dtab, int c, int K,
                                                     const G1XYZZ* __restrict__ sum, u32 B, const uint8_t* __restrict__ rs,
-                                                    uint8_t* __restrict__ proofs, uint8_t* __restrict__ affine) {
+                                                    const uint8_t* __restrict__ partial, uint8_t* __restrict__ proofs,
+                                                    uint8_t* __restrict__ affine) {
     const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= B) return;
+    G1Affine base_a = pk.alpha_g1, base_b = pk.beta_g1, base_c = G1Affine::infinity();
+    if (partial) {  // finish phase: the partial proof already contains α₁ / β₁ and the known part of L
+        const uint8_t* pp = partial + 320 * (size_t)j;
+        base_a = load_affine_g1(pp);
+        base_b = load_affine_g1(pp + 64);
+        base_c = load_affine_g1(pp + 256);
+    }
     u32 r[8], s[8], rsv[8];
     load_scalar_bytes(rs + 64 * (size_t)j, r);
     load_scalar_bytes(rs + 64 * (size_t)j + 32, s);
@@ -283,19 +330,20 @@ __global__ void __launch_bounds__(64) k_assemble_g1(ProverKeyDev pk, const G1Aff
     for (int i = 0; i < 8; i++) rnz |= r[i];
     // g_a
     G1XYZZ g_a = sum[0 * (size_t)B + j];
-    g_a.add_affine(pk.alpha_g1);
+    if (!base_a.is_inf()) g_a.add_affine(base_a);
     g_a.add(fixed_base_mul<Fq>(dtab, c, K, r));
     // g_c = s·g_a + r·g1_b − rs·δ₁ + L + H
     G1XYZZ g_c = g_a.mul(s);
     if (rnz) {
         G1XYZZ g1_b = sum[1 * (size_t)B + j];
-        g1_b.add_affine(pk.beta_g1);
+        if (!base_b.is_inf()) g1_b.add_affine(base_b);
         g1_b.add(fixed_base_mul<Fq>(dtab, c, K, s));
         g_c.add(g1_b.mul(r));
     }
     g_c.add(fixed_base_mul<Fq>(dtab, c, K, rsv).neg());
     g_c.add(sum[2 * (size_t)B + j]);
     g_c.add(sum[3 * (size_t)B + j]);
+    if (!base_c.is_inf()) g_c.add_affine(base_c);
     uint8_t* o = proofs + 128 * (size_t)j;
     uint8_t* af = affine ? affine + 256 * (size_t)j : nullptr;
     compress_g1(g_a.to_affine(), o, af);
@@ -303,13 +351,15 @@ __global__ void __launch_bounds__(64) k_assemble_g1(ProverKeyDev pk, const G1Aff
 }
 __global__ void __launch_bounds__(64) k_assemble_g2(ProverKeyDev pk, const G2Affine* __restrict__ dtab, int c, int K,
                                                     const G2XYZZ* __restrict__ sum, u32 B, const uint8_t* __restrict__ rs,
-                                                    uint8_t* __restrict__ proofs, uint8_t* __restrict__ affine) {
+                                                    const uint8_t* __restrict__ partial, uint8_t* __restrict__ proofs,
+                                                    uint8_t* __restrict__ affine) {
     const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= B) return;
     u32 s[8];
     load_scalar_bytes(rs + 64 * (size_t)j + 32, s);
     G2XYZZ g2_b = sum[j];
-    g2_b.add_affine(pk.beta_g2);
+    G2Affine base_b = partial ? load_affine_g2(partial + 320 * (size_t)j + 128) : pk.beta_g2;
+    if (!base_b.is_inf()) g2_b.add_affine(base_b);
     g2_b.add(fixed_base_mul<Fq2>(dtab, c, K, s));
     compress_g2(g2_b.to_affine(), proofs + 128 * (size_t)j + 32, affine ? affine + 256 * (size_t)j + 64 : nullptr);
 }
@@ -322,29 +372,36 @@ static u32 pick_chunk(u32 total_bases, u32 B) {
     if (want > 256) want = 256;
     return (u32)want;
 }
-std::vector<MsmTask> msm_make_tasks(const FixedMsmPlan& plan, u32 B, bool g2) {
+std::vector<MsmTask> msm_make_tasks(const FixedMsmPlan& plan, u32 B, bool g2, int phase) {
     const MsmGroupDev* g = g2 ? &plan.g2 : plan.g1;
     const int n_groups = g2 ? 1 : 4;
+    auto range = [&](int i, u32& lo, u32& hi) {
+        lo = 0;
+        hi = g[i].n_bases;
+        if (phase == MSM_KNOWN) hi = g[i].n_known;      // H has n_known = 0: it belongs to the finish phase only
+        if (phase == MSM_UNKNOWN) lo = g[i].n_known;
+    };
     u32 total = 0;
-    for (int i = 0; i < n_groups; i++) total += g[i].n_bases;
-    const u32 chunk = pick_chunk(total, B);
+    for (int i = 0; i < n_groups; i++) { u32 lo, hi; range(i, lo, hi); total += hi - lo; }
+    const u32 chunk = pick_chunk(total ? total : 1, B);
     std::vector<MsmTask> tasks;
-    for (int i = 0; i < n_groups; i++)
-        for (u32 lo = 0; lo < g[i].n_bases; lo += chunk) tasks.push_back({(u32)i, lo, lo + chunk < g[i].n_bases ? lo + chunk : g[i].n_bases, 0});
+    for (int i = 0; i < n_groups; i++) {
+        u32 lo, hi;
+        range(i, lo, hi);
+        for (u32 b = lo; b < hi; b += chunk) tasks.push_back({(u32)i, b, b + chunk < hi ? b + chunk : hi, 0});
+    }
     return tasks;
 }
 
-void launch_msm_and_assemble(const FixedMsmPlan& plan, const ProverKeyDev& pk, const Fr* d_vals, const Fr* d_h, u32 B,
-                             const uint8_t* d_rs, MsmWorkspace& ws, uint8_t* d_proofs_out, uint8_t* d_proofs_affine, cudaStream_t s) {
+void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, u32 B, MsmWorkspace& ws, cudaStream_t s) {
     const u32 bx = B >= 128 ? 128 : 32;
     {   // G1: A, B1, L, H
         AccumArgs<Fq> a;
         a.src[0] = d_vals; a.src[1] = d_h;
         for (int i = 0; i < 4; i++) { a.row[i] = plan.g1[i].row; a.table[i] = (const G1Affine*)plan.g1[i].table; a.which[i] = plan.g1[i].which_src; }
         a.tasks = ws.tasks_g1; a.part = ws.part_g1; a.B = B; a.c = plan.c; a.K = plan.K;
-        dim3 grid((B + bx - 1) / bx, ws.n_tasks_g1);
         if (ws.ev) cudaEventRecord(ws.ev[0], s);
-        k_msm_accum<Fq><<<grid, bx, 0, s>>>(a);
+        if (ws.n_tasks_g1) k_msm_accum<Fq><<<dim3((B + bx - 1) / bx, ws.n_tasks_g1), bx, 0, s>>>(a);
         if (ws.ev) cudaEventRecord(ws.ev[1], s);
         k_msm_reduce<Fq><<<dim3((B + bx - 1) / bx, 4), bx, 0, s>>>(ws.part_g1, ws.tasks_g1, ws.n_tasks_g1, B, ws.sum_g1);
         if (ws.ev) cudaEventRecord(ws.ev[2], s);
@@ -354,15 +411,23 @@ void launch_msm_and_assemble(const FixedMsmPlan& plan, const ProverKeyDev& pk, c
         a.src[0] = d_vals; a.src[1] = d_h;
         for (int i = 0; i < 4; i++) { a.row[i] = plan.g2.row; a.table[i] = (const G2Affine*)plan.g2.table; a.which[i] = plan.g2.which_src; }
         a.tasks = ws.tasks_g2; a.part = ws.part_g2; a.B = B; a.c = plan.c2; a.K = plan.K2;
-        dim3 grid((B + bx - 1) / bx, ws.n_tasks_g2);
-        k_msm_accum<Fq2><<<grid, bx, 0, s>>>(a);
+        if (ws.n_tasks_g2) k_msm_accum<Fq2><<<dim3((B + bx - 1) / bx, ws.n_tasks_g2), bx, 0, s>>>(a);
         if (ws.ev) cudaEventRecord(ws.ev[3], s);
         k_msm_reduce<Fq2><<<dim3((B + bx - 1) / bx, 1), bx, 0, s>>>(ws.part_g2, ws.tasks_g2, ws.n_tasks_g2, B, ws.sum_g2);
         if (ws.ev) cudaEventRecord(ws.ev[4], s);
     }
-    k_assemble_g1<<<(B + 63) / 64, 64, 0, s>>>(pk, plan.delta1_table, plan.c, plan.K, ws.sum_g1, B, d_rs, d_proofs_out, d_proofs_affine);
-    k_assemble_g2<<<(B + 63) / 64, 64, 0, s>>>(pk, plan.delta2_table, plan.c2, plan.K2, ws.sum_g2, B, d_rs, d_proofs_out, d_proofs_affine);
+}
+
+void launch_assemble(const FixedMsmPlan& plan, const ProverKeyDev& pk, u32 B, const uint8_t* d_rs, MsmWorkspace& ws,
+                     const uint8_t* d_partial, uint8_t* d_proofs_out, uint8_t* d_proofs_affine, cudaStream_t s) {
+    k_assemble_g1<<<(B + 63) / 64, 64, 0, s>>>(pk, plan.delta1_table, plan.c, plan.K, ws.sum_g1, B, d_rs, d_partial, d_proofs_out, d_proofs_affine);
+    k_assemble_g2<<<(B + 63) / 64, 64, 0, s>>>(pk, plan.delta2_table, plan.c2, plan.K2, ws.sum_g2, B, d_rs, d_partial, d_proofs_out, d_proofs_affine);
     if (ws.ev) cudaEventRecord(ws.ev[5], s);
+}
+
+void launch_partial_out(const ProverKeyDev& pk, u32 B, MsmWorkspace& ws, uint8_t* d_out_affine, uint8_t* d_out_compressed, cudaStream_t s) {
+    k_partial_g1<<<(B + 63) / 64, 64, 0, s>>>(pk, ws.sum_g1, B, d_out_affine, d_out_compressed);
+    k_partial_g2<<<(B + 63) / 64, 64, 0, s>>>(pk, ws.sum_g2, B, d_out_affine, d_out_compressed);
 }
 
 }  // namespace zk

@@ -113,6 +113,10 @@ struct RlnProof {
     uint8_t proof[128];  // ark-compressed A|B|C
     ProofValues pv;
 };
+struct PartialProofHost {  // PartialProof (rln/src/partial_proof.rs:30-43); the mask is a property of the circuit
+    uint8_t affine[320];   // partial_pi_a 64 | partial_rho 64 | partial_pi_b 128 | partial_pi_c 64, canonical
+    uint8_t comp[160];     // the same, ark-compressed 32 | 32 | 64 | 32
+};
 
 // rln_witness_to_bytes_le (witness.rs:369-415)
 static std::vector<uint8_t> witness_to_bytes(const Witness& w) {
@@ -249,8 +253,13 @@ class Rln {
     // proving
     void reserve(size_t B);
     void prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, uint8_t* d_proofs, uint8_t* d_values, uint8_t* d_affine,
-                      cudaStream_t s);
-    void prove_host(const std::vector<Witness>& ws, const uint8_t* rs, std::vector<RlnProof>& out);
+                      cudaStream_t s, int phase = MSM_FULL, const uint8_t* d_partial = nullptr, uint8_t* d_partial_affine = nullptr,
+                      uint8_t* d_partial_comp = nullptr);
+    void prove_host(const std::vector<Witness>& ws, const uint8_t* rs, std::vector<RlnProof>& out, const PartialProofHost* partials = nullptr);
+    // two-phase proving (rln/src/protocol/proof.rs:783-849): the unknown inputs of `ws` (message_id, x, external_nullifier) are ignored
+    void partial_host(const std::vector<Witness>& ws, std::vector<PartialProofHost>& out);
+    const std::vector<uint8_t>& partial_mask() const { return mask_; }  // one byte per wire 1..n_wires-1 (1 = known)
+    void decompress_partial(const uint8_t comp[160], uint8_t affine[320]);
     void witness_slots(const Witness& w, uint8_t* slots) const;
     void debug_w_h(const Witness& w, uint8_t* w_out, uint8_t* h_out);
     void table_info(int* c, int* K, uint64_t* g1, uint64_t* g2, uint64_t* bytes, int* c2, int* K2) const {
@@ -270,7 +279,8 @@ class Rln {
         DevMem g1, g2;
         u32 n1 = 0, n2 = 0;
     };
-    TaskSet& tasks_for(u32 B);
+    TaskSet& tasks_for(u32 B, int phase);
+    void compute_known_mask();
     void build_circuit();
     void build_tables();
     void check_graph_shape();
@@ -296,7 +306,9 @@ class Rln {
     // workspace
     size_t cap_ = 0, max_batch_ = 4096;
     DevMem ws_inputs_, ws_rs_, ws_vals_, ws_a_, ws_b_, ws_c_, ws_err_, ws_part1_, ws_part2_, ws_sum1_, ws_sum2_, ws_proofs_, ws_values_, ws_affine_;
-    std::map<u32, std::unique_ptr<TaskSet>> tasks_;
+    std::map<u64, std::unique_ptr<TaskSet>> tasks_;
+    std::vector<uint8_t> wire_known_, mask_;
+    DevMem ws_partial_, ws_partial_comp_;
     cudaStream_t stream_ = nullptr, side_ = nullptr;
     cudaEvent_t fork_ = nullptr, join_ = nullptr;
     cudaEvent_t ev_[5];
@@ -353,6 +365,7 @@ Rln::Rln(size_t tree_depth, const uint8_t* zkey, size_t zlen, const uint8_t* gra
         throw RlnError(std::string("Graph error: ") + e.what());
     }
     check_graph_shape();
+    compute_known_mask();
     max_batch_ = (size_t)env_int("RLN_B200_MAX_BATCH", 4096);
     ZK_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     ZK_CUDA_CHECK(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
@@ -372,6 +385,31 @@ Rln::~Rln() {
     if (side_) cudaStreamDestroy(side_);
     if (fork_) cudaEventDestroy(fork_);
     if (join_) cudaEventDestroy(join_);
+}
+
+// Which wires a partial witness determines (graph.rs:274-312 evaluate_partial): a node is known iff all of its operands
+// are; the unknown inputs are messageId, x and externalNullifier (witness.rs:887-931).
+void Rln::compute_known_mask() {
+    std::vector<uint8_t> slot_unknown(gh_.n_slots, 0);
+    for (const char* name : {"messageId", "x", "externalNullifier"}) {
+        auto it = gh_.inputs.find(name);
+        for (uint32_t i = 0; i < it->second.second; i++) slot_unknown[it->second.first + i] = 1;
+    }
+    std::vector<uint8_t> known(gh_.prog.size());
+    for (size_t i = 0; i < gh_.prog.size(); i++) {
+        const VmInstr& in = gh_.prog[i];
+        switch (in.kind_op & 0xff) {
+            case VM_CONST: known[i] = 1; break;
+            case VM_INPUT: known[i] = !slot_unknown[in.a]; break;
+            case VM_UNO: known[i] = known[in.a]; break;
+            case VM_DUO: known[i] = known[in.a] && known[in.b]; break;
+            default: known[i] = known[in.a] && known[in.b] && known[in.c]; break;
+        }
+    }
+    wire_known_.resize(gh_.signals.size());
+    for (size_t i = 0; i < gh_.signals.size(); i++) wire_known_[i] = known[gh_.signals[i]];
+    if (!wire_known_[0]) throw RlnError("Graph error: the constant wire depends on an unknown input");
+    mask_.assign(wire_known_.begin() + 1, wire_known_.end());
 }
 
 void Rln::check_graph_shape() {
@@ -506,6 +544,13 @@ void Rln::build_tables() {
     pick[2] = non_inf(zk_.l_query, 64, nw - ni, 0);
     pick[3] = non_inf(zk_.h_query, 64, domain_, 0);
     pick[4] = non_inf(zk_.b_g2, 128, nw, 0);
+    // order every group as [bases of wires a partial witness knows | the rest] so both phases are contiguous ranges
+    u32 n_known[5] = {0, 0, 0, 0, 0};
+    for (int g : {0, 1, 2, 4}) {
+        const size_t shift = g == 2 ? ni : 0;
+        auto mid = std::stable_partition(pick[g].begin(), pick[g].end(), [&](uint32_t i) { return wire_known_[i + shift] != 0; });
+        n_known[g] = (u32)(mid - pick[g].begin());
+    }
     size_t n_g1 = pick[0].size() + pick[1].size() + pick[2].size() + pick[3].size(), n_g2 = pick[4].size();
     // Window widths: G1 tables cost 64·K·2^(c−1) bytes per base, G2 tables twice that but have 6× fewer bases, so G2
     // gets the wider window when HBM allows (fewer additions per term: K = ⌈255/c⌉).
@@ -554,6 +599,7 @@ void Rln::build_tables() {
         ZK_CUDA_CHECK(cudaDeviceSynchronize());
         MsmGroupDev& dst = g < 4 ? plan_.g1[g] : plan_.g2;
         dst.n_bases = (u32)pick[g].size();
+        dst.n_known = n_known[g];
         dst.row = d_rows_[g].as<u32>();
         dst.table = d_tab_[g].p;
         dst.which_src = g == 3 ? 1 : 0;
@@ -688,17 +734,18 @@ void Rln::override_range(size_t start, const uint8_t* leaves, size_t n_leaves, s
 }
 
 // ------------------------------------------------------------------------------------------- proving
-Rln::TaskSet& Rln::tasks_for(u32 B) {
-    auto it = tasks_.find(B);
+Rln::TaskSet& Rln::tasks_for(u32 B, int phase) {
+    const u64 key = ((u64)phase << 32) | B;
+    auto it = tasks_.find(key);
     if (it != tasks_.end()) return *it->second;
     auto ts = std::make_unique<TaskSet>();
-    std::vector<MsmTask> t1 = msm_make_tasks(plan_, B, false), t2 = msm_make_tasks(plan_, B, true);
+    std::vector<MsmTask> t1 = msm_make_tasks(plan_, B, false, phase), t2 = msm_make_tasks(plan_, B, true, phase);
     ts->g1.upload(t1.data(), t1.size() * sizeof(MsmTask));
     ts->g2.upload(t2.data(), t2.size() * sizeof(MsmTask));
     ts->n1 = (u32)t1.size();
     ts->n2 = (u32)t2.size();
     TaskSet& ref = *ts;
-    tasks_[B] = std::move(ts);
+    tasks_[key] = std::move(ts);
     return ref;
 }
 void Rln::reserve(size_t B) {
@@ -709,12 +756,12 @@ void Rln::reserve(size_t B) {
     // largest task counts over the batch sizes this capacity can serve
     size_t t1 = 0, t2 = 0;
     for (size_t b = 1; b <= B; b <<= 1) {
-        size_t a = msm_make_tasks(plan_, (u32)b, false).size() * b, c2 = msm_make_tasks(plan_, (u32)b, true).size() * b;
+        size_t a = msm_make_tasks(plan_, (u32)b, false, MSM_FULL).size() * b, c2 = msm_make_tasks(plan_, (u32)b, true, MSM_FULL).size() * b;
         if (a > t1) t1 = a;
         if (c2 > t2) t2 = c2;
     }
     {
-        size_t a = msm_make_tasks(plan_, (u32)B, false).size() * B, c2 = msm_make_tasks(plan_, (u32)B, true).size() * B;
+        size_t a = msm_make_tasks(plan_, (u32)B, false, MSM_FULL).size() * B, c2 = msm_make_tasks(plan_, (u32)B, true, MSM_FULL).size() * B;
         if (a > t1) t1 = a;
         if (c2 > t2) t2 = c2;
     }
@@ -735,23 +782,23 @@ void Rln::reserve(size_t B) {
     ws_proofs_.alloc(128 * B);
     ws_values_.alloc(160 * B);
     ws_affine_.alloc(256 * B);
+    ws_partial_.alloc(320 * B);
+    ws_partial_comp_.alloc(160 * B);
     cap_ = B;
 }
 
 void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, uint8_t* d_proofs, uint8_t* d_values, uint8_t* d_affine,
-                       cudaStream_t s) {
+                       cudaStream_t s, int phase, const uint8_t* d_partial, uint8_t* d_partial_affine, uint8_t* d_partial_comp) {
     if (n == 0) return;
     reserve(n);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (size_t off = 0; off < n; off += cap_) {
         const u32 B = (u32)(n - off < cap_ ? n - off : cap_);
-        TaskSet& ts = tasks_for(B);
-        if ((size_t)ts.n1 * B * sizeof(G1XYZZ) > ws_part1_.bytes || (size_t)ts.n2 * B * sizeof(G2XYZZ) > ws_part2_.bytes) {
-            ws_part1_.ensure((size_t)ts.n1 * B * sizeof(G1XYZZ));
-            ws_part2_.ensure((size_t)ts.n2 * B * sizeof(G2XYZZ));
-        }
+        TaskSet& ts = tasks_for(B, phase);
+        ws_part1_.ensure((size_t)ts.n1 * B * sizeof(G1XYZZ));
+        ws_part2_.ensure((size_t)ts.n2 * B * sizeof(G2XYZZ));
         const uint8_t* in = d_inputs + off * (size_t)gh_.n_slots * 32;
-        if (d_values) {  // proof values only need the inputs: a latency-bound kernel, run beside the main pipeline
+        if (d_values && phase != MSM_KNOWN) {  // proof values only need the inputs: a latency-bound kernel, run beside the main pipeline
             ZK_CUDA_CHECK(cudaEventRecord(fork_, s));
             ZK_CUDA_CHECK(cudaStreamWaitEvent(side_, fork_, 0));
             launch_proof_values(in, slots_, B, d_values + 160 * off, side_);
@@ -760,7 +807,7 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
         ZK_CUDA_CHECK(cudaEventRecord(ev_[0], s));
         launch_witness(circ_, in, ws_vals_.as<Fr>(), B, ws_err_.as<u32>(), s);
         ZK_CUDA_CHECK(cudaEventRecord(ev_[1], s));
-        launch_qap(circ_, ws_vals_.as<Fr>(), ws_a_.as<Fr>(), ws_b_.as<Fr>(), ws_c_.as<Fr>(), B, s);
+        if (phase != MSM_KNOWN) launch_qap(circ_, ws_vals_.as<Fr>(), ws_a_.as<Fr>(), ws_b_.as<Fr>(), ws_c_.as<Fr>(), B, s);
         ZK_CUDA_CHECK(cudaEventRecord(ev_[2], s));
         MsmWorkspace mw;
         mw.part_g1 = ws_part1_.as<G1XYZZ>();
@@ -772,12 +819,18 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
         mw.n_tasks_g1 = ts.n1;
         mw.n_tasks_g2 = ts.n2;
         mw.ev = mev_;
-        launch_msm_and_assemble(plan_, pk_, ws_vals_.as<Fr>(), ws_a_.as<Fr>(), B, d_rs + 64 * off, mw, d_proofs + 128 * off,
-                                d_affine ? d_affine + 256 * off : nullptr, s);
+        launch_msm_sums(plan_, ws_vals_.as<Fr>(), ws_a_.as<Fr>(), B, mw, s);
+        if (phase == MSM_KNOWN) {
+            launch_partial_out(pk_, B, mw, d_partial_affine + 320 * off, d_partial_comp + 160 * off, s);
+            ZK_CUDA_CHECK(cudaEventRecord(mev_[5], s));
+        } else {
+            launch_assemble(plan_, pk_, B, d_rs + 64 * off, mw, d_partial ? d_partial + 320 * off : nullptr, d_proofs + 128 * off,
+                            d_affine ? d_affine + 256 * off : nullptr, s);
+        }
         ZK_CUDA_CHECK(cudaEventRecord(ev_[3], s));
-        if (d_values) ZK_CUDA_CHECK(cudaStreamWaitEvent(s, join_, 0));
+        if (d_values && phase != MSM_KNOWN) ZK_CUDA_CHECK(cudaStreamWaitEvent(s, join_, 0));
         ZK_CUDA_CHECK(cudaEventRecord(ev_[4], s));
-        g_launch_count += 1 + (2 + 3 * (2 * ntt_launches_per_transform(log_domain_) + 1)) + 6 + (d_values ? 1 : 0);
+        g_launch_count += 1 + (phase != MSM_KNOWN ? 2 + 3 * (2 * ntt_launches_per_transform(log_domain_) + 1) : 0) + 6 + (d_values ? 1 : 0);
         // graph-evaluation failures surface as errors, like WitnessCalcError::GraphEvaluation (rln/src/circuit/iden3calc.rs:52-53)
         std::vector<u32> err(B);
         ZK_CUDA_CHECK(cudaMemcpyAsync(err.data(), ws_err_.p, 4 * B, cudaMemcpyDeviceToHost, s));
@@ -789,8 +842,9 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
             for (int i = 0; i < 5; i++) { cudaEventElapsedTime(&ms, mev_[i], mev_[i + 1]); acc[2 + i] += ms; }
             cudaEventElapsedTime(&ms, ev_[3], ev_[4]); acc[7] += ms;
         }
-        for (u32 j = 0; j < B; j++)
-            if (err[j]) throw RlnError("Protocol error: Error calculating witness: graph evaluation failed");
+        if (phase != MSM_KNOWN)  // a partial witness leaves the unknown wires undefined; only full evaluations can fail
+            for (u32 j = 0; j < B; j++)
+                if (err[j]) throw RlnError("Protocol error: Error calculating witness: graph evaluation failed");
     }
     for (int i = 0; i < 8; i++) stage_ms[i] = acc[i];
 }
@@ -807,7 +861,7 @@ void Rln::witness_slots(const Witness& w, uint8_t* slots) const {  // iden3calc.
     memcpy(slots + 32 * slots_.ext_null, w.ext_null, 32);
 }
 
-void Rln::prove_host(const std::vector<Witness>& wsv, const uint8_t* rs, std::vector<RlnProof>& out) {
+void Rln::prove_host(const std::vector<Witness>& wsv, const uint8_t* rs, std::vector<RlnProof>& out, const PartialProofHost* partials) {
     const size_t n = wsv.size();
     out.resize(n);
     if (!n) return;
@@ -834,7 +888,14 @@ void Rln::prove_host(const std::vector<Witness>& wsv, const uint8_t* rs, std::ve
             for (size_t j = 0; j < 2 * B; j++) random_fr(rsb.data() + 32 * j);  // r, s ← rng (proof.rs:743-745)
         ZK_CUDA_CHECK(cudaMemcpyAsync(ws_inputs_.p, slots.data(), B * (size_t)gh_.n_slots * 32, cudaMemcpyHostToDevice, stream_));
         ZK_CUDA_CHECK(cudaMemcpyAsync(ws_rs_.p, rsb.data(), 64 * B, cudaMemcpyHostToDevice, stream_));
-        prove_device(ws_inputs_.as<uint8_t>(), ws_rs_.as<uint8_t>(), B, ws_proofs_.as<uint8_t>(), ws_values_.as<uint8_t>(), nullptr, stream_);
+        if (partials) {
+            std::vector<uint8_t> pb(320 * B);
+            for (size_t j = 0; j < B; j++) memcpy(pb.data() + 320 * j, partials[off + j].affine, 320);
+            ZK_CUDA_CHECK(cudaMemcpyAsync(ws_partial_.p, pb.data(), pb.size(), cudaMemcpyHostToDevice, stream_));
+            ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        }
+        prove_device(ws_inputs_.as<uint8_t>(), ws_rs_.as<uint8_t>(), B, ws_proofs_.as<uint8_t>(), ws_values_.as<uint8_t>(), nullptr, stream_,
+                     partials ? MSM_UNKNOWN : MSM_FULL, partials ? ws_partial_.as<uint8_t>() : nullptr);
         ZK_CUDA_CHECK(cudaMemcpyAsync(proofs.data(), ws_proofs_.p, 128 * B, cudaMemcpyDeviceToHost, stream_));
         ZK_CUDA_CHECK(cudaMemcpyAsync(values.data(), ws_values_.p, 160 * B, cudaMemcpyDeviceToHost, stream_));
         // secrets do not linger in the staging buffers (reference zeroises them: rln/src/circuit/iden3calc.rs:44-57)
@@ -852,6 +913,64 @@ void Rln::prove_host(const std::vector<Witness>& wsv, const uint8_t* rs, std::ve
         }
     }
     memset(slots.data(), 0, slots.size());
+}
+
+void Rln::partial_host(const std::vector<Witness>& wsv, std::vector<PartialProofHost>& out) {
+    const size_t n = wsv.size();
+    out.resize(n);
+    if (!n) return;
+    for (const Witness& w : wsv)
+        if (w.path.size() / 32 != depth_ || w.index.size() != depth_)
+            throw RlnError("Protocol error: partial witness depth does not match the circuit tree_depth");
+    const size_t chunk = n < max_batch_ ? n : max_batch_;
+    reserve(chunk);
+    std::vector<uint8_t> slots(chunk * (size_t)gh_.n_slots * 32), aff(chunk * 320), comp(chunk * 160);
+    for (size_t off = 0; off < n; off += chunk) {
+        const size_t B = n - off < chunk ? n - off : chunk;
+        for (size_t j = 0; j < B; j++) {
+            Witness w = wsv[off + j];
+            memset(w.message_id, 0, 32);  // the unknown inputs are None in the reference; any value works, their wires are not used
+            memset(w.x, 0, 32);
+            memset(w.ext_null, 0, 32);
+            witness_slots(w, slots.data() + j * (size_t)gh_.n_slots * 32);
+            memset(w.secret, 0, 32);
+        }
+        ZK_CUDA_CHECK(cudaMemcpyAsync(ws_inputs_.p, slots.data(), B * (size_t)gh_.n_slots * 32, cudaMemcpyHostToDevice, stream_));
+        prove_device(ws_inputs_.as<uint8_t>(), nullptr, B, nullptr, nullptr, nullptr, stream_, MSM_KNOWN, nullptr, ws_partial_.as<uint8_t>(),
+                     ws_partial_comp_.as<uint8_t>());
+        ZK_CUDA_CHECK(cudaMemcpyAsync(aff.data(), ws_partial_.p, 320 * B, cudaMemcpyDeviceToHost, stream_));
+        ZK_CUDA_CHECK(cudaMemcpyAsync(comp.data(), ws_partial_comp_.p, 160 * B, cudaMemcpyDeviceToHost, stream_));
+        ZK_CUDA_CHECK(cudaMemsetAsync(ws_inputs_.p, 0, B * (size_t)gh_.n_slots * 32, stream_));
+        ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        for (size_t j = 0; j < B; j++) {
+            memcpy(out[off + j].affine, aff.data() + 320 * j, 320);
+            memcpy(out[off + j].comp, comp.data() + 160 * j, 160);
+        }
+    }
+    memset(slots.data(), 0, slots.size());
+}
+
+// PartialProof::deserialize_compressed validates every point (curve, and the subgroup for G2)
+void Rln::decompress_partial(const uint8_t comp[160], uint8_t affine[320]) {
+    // reuse the proof decompressor (G1 | G2 | G1): (π_a, π_b, π_c) and (ρ, π_b, π_c)
+    uint8_t two[256];
+    memcpy(two, comp, 32); memcpy(two + 32, comp + 64, 64); memcpy(two + 96, comp + 128, 32);
+    memcpy(two + 128, comp + 32, 32); memcpy(two + 160, comp + 64, 64); memcpy(two + 224, comp + 128, 32);
+    DevMem dp, da, dok;
+    dp.upload(two, 256);
+    da.alloc(512);
+    dok.alloc(2);
+    launch_decompress(dp.as<uint8_t>(), 2, da.as<uint8_t>(), dok.as<uint8_t>(), stream_);
+    g_launch_count++;
+    uint8_t ok[2], aff[512];
+    ZK_CUDA_CHECK(cudaMemcpyAsync(ok, dok.p, 2, cudaMemcpyDeviceToHost, stream_));
+    ZK_CUDA_CHECK(cudaMemcpyAsync(aff, da.p, 512, cudaMemcpyDeviceToHost, stream_));
+    ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    if (!ok[0] || !ok[1]) throw RlnError("Proof serialization error: the input buffer contained invalid data");
+    memcpy(affine, aff, 64);             // π_a
+    memcpy(affine + 64, aff + 256, 64);  // ρ
+    memcpy(affine + 128, aff + 64, 128); // π_b
+    memcpy(affine + 256, aff + 192, 64); // π_c
 }
 
 void Rln::debug_w_h(const Witness& w, uint8_t* w_out, uint8_t* h_out) {
@@ -897,6 +1016,8 @@ struct FFI_RLNProof { RlnProof p; };
 struct FFI_RLNProofValues { ProofValues v; };
 struct FFI_RLNWitnessInput { Witness w; };
 struct RlnB200Msm { VarMsmWorkspace* ws; size_t max_n; };
+struct FFI_RLNPartialWitnessInput { Witness w; };
+struct FFI_RLNPartialProof { PartialProofHost p; std::vector<uint8_t> mask; };
 
 static RlnString mk_string(const std::string& s) {
     RlnString out;
@@ -1119,6 +1240,110 @@ CResult_FFI_RLNProof_t rlnb200_generate_rln_proof_with_rs(FFI_RLN_t* const* rln,
     return prove_one(rln, witness, rs);
 }
 
+// ---- two-phase proving (rln/src/ffi/ffi_rln.rs:561-712, 238-320, 918-960) ----------------------------
+CResult_FFI_RLNPartialWitnessInput_t ffi_rln_partial_witness_input_new(const CFr_t* identity_secret, const CFr_t* user_message_limit,
+                                                                       const Vec_CFr_t* path_elements, const Vec_uint8_t* identity_path_index) {
+    GUARD_BEGIN
+    auto w = std::make_unique<FFI_RLNPartialWitnessInput>();
+    memset(&w->w.message_id, 0, 32); memset(&w->w.x, 0, 32); memset(&w->w.ext_null, 0, 32);
+    memcpy(w->w.secret, identity_secret->bytes, 32);
+    memcpy(w->w.limit, user_message_limit->bytes, 32);
+    w->w.path.assign((const uint8_t*)path_elements->ptr, (const uint8_t*)path_elements->ptr + 32 * path_elements->len);
+    w->w.index.assign(identity_path_index->ptr, identity_path_index->ptr + identity_path_index->len);
+    if (is_zero32(w->w.limit)) throw RlnError("User message limit cannot be zero");   // RLNPartialWitnessInput::new (witness.rs)
+    if (w->w.path.size() / 32 != w->w.index.size()) {
+        std::ostringstream m;
+        m << "Merkle proof length mismatch: expected " << w->w.path.size() / 32 << ", got " << w->w.index.size();
+        throw RlnError(m.str());
+    }
+    return CResult_FFI_RLNPartialWitnessInput_t{w.release(), no_string()};
+    GUARD_END(return (CResult_FFI_RLNPartialWitnessInput_t{nullptr, mk_string(m)}))
+}
+void ffi_rln_partial_witness_input_free(FFI_RLNPartialWitnessInput_t* w) {
+    if (w) memset(w->w.secret, 0, 32);
+    delete w;
+}
+CResult_FFI_RLNPartialProof_t ffi_generate_partial_zk_proof(FFI_RLN_t* const* rln, FFI_RLNPartialWitnessInput_t* const* partial_witness) {
+    GUARD_BEGIN
+    std::lock_guard<std::mutex> lk((*rln)->r->mu);
+    std::vector<Witness> ws(1, (*partial_witness)->w);
+    std::vector<PartialProofHost> out;
+    (*rln)->r->partial_host(ws, out);
+    memset(ws[0].secret, 0, 32);
+    auto p = std::make_unique<FFI_RLNPartialProof>();
+    p->p = out[0];
+    p->mask = (*rln)->r->partial_mask();
+    return CResult_FFI_RLNPartialProof_t{p.release(), no_string()};
+    GUARD_END(return (CResult_FFI_RLNPartialProof_t{nullptr, mk_string(m)}))
+}
+static CResult_FFI_RLNProof_t finish_one(FFI_RLN_t* const* rln, FFI_RLNPartialProof_t* const* partial, FFI_RLNWitnessInput_t* const* witness,
+                                         const uint8_t* rs) {
+    GUARD_BEGIN
+    std::lock_guard<std::mutex> lk((*rln)->r->mu);
+    if ((*partial)->mask != (*rln)->r->partial_mask()) throw RlnError("Protocol error: Error producing proof: malformed verifying key");
+    std::vector<Witness> ws(1, (*witness)->w);
+    std::vector<RlnProof> out;
+    (*rln)->r->prove_host(ws, rs, out, &(*partial)->p);
+    memset(ws[0].secret, 0, 32);
+    auto p = std::make_unique<FFI_RLNProof>();
+    p->p = out[0];
+    return CResult_FFI_RLNProof_t{p.release(), no_string()};
+    GUARD_END(return (CResult_FFI_RLNProof_t{nullptr, mk_string(m)}))
+}
+CResult_FFI_RLNProof_t ffi_finish_rln_proof(FFI_RLN_t* const* rln, FFI_RLNPartialProof_t* const* partial_proof,
+                                            FFI_RLNWitnessInput_t* const* witness) {
+    return finish_one(rln, partial_proof, witness, nullptr);
+}
+CResult_FFI_RLNProof_t rlnb200_finish_rln_proof_with_rs(FFI_RLN_t* const* rln, FFI_RLNPartialProof_t* const* partial_proof,
+                                                        FFI_RLNWitnessInput_t* const* witness, const CFr_t* r, const CFr_t* s) {
+    uint8_t rs[64];
+    memcpy(rs, r->bytes, 32);
+    memcpy(rs + 32, s->bytes, 32);
+    return finish_one(rln, partial_proof, witness, rs);
+}
+// rln_partial_proof_to_bytes_le (proof.rs:537-547): version | u64 mask length | mask bytes | π_a | ρ | π_b | π_c (ark compressed)
+CResult_Vec_uint8_t ffi_rln_partial_proof_to_bytes_le(FFI_RLNPartialProof_t* const* partial_proof) {
+    const FFI_RLNPartialProof& p = **partial_proof;
+    std::vector<uint8_t> b;
+    b.push_back(0);
+    uint64_t n = p.mask.size();
+    b.insert(b.end(), (uint8_t*)&n, (uint8_t*)&n + 8);
+    b.insert(b.end(), p.mask.begin(), p.mask.end());
+    b.insert(b.end(), p.p.comp, p.p.comp + 160);
+    return CResult_Vec_uint8_t{mk_vec(b.data(), b.size()), no_string()};
+}
+CResult_FFI_RLNPartialProof_t rlnb200_bytes_le_to_rln_partial_proof(FFI_RLN_t* const* rln, const Vec_uint8_t* bytes) {
+    GUARD_BEGIN
+    std::lock_guard<std::mutex> lk((*rln)->r->mu);
+    const uint8_t* b = bytes->ptr;
+    const size_t len = bytes->len;
+    if (len == 0) throw RlnError(msg_read_len(1, 0));
+    if (b[0] != 0) {
+        char t[64];
+        snprintf(t, sizeof t, "Unknown message mode version byte: %#04x", b[0]);
+        throw RlnError(t);
+    }
+    if (len < 9) throw RlnError("Proof serialization error: io error: failed to fill whole buffer");
+    uint64_t n;
+    memcpy(&n, b + 1, 8);
+    if (n > len || 9 + n + 160 > len) throw RlnError("Proof serialization error: io error: failed to fill whole buffer");
+    auto p = std::make_unique<FFI_RLNPartialProof>();
+    p->mask.assign(b + 9, b + 9 + n);
+    for (uint8_t v : p->mask)
+        if (v > 1) throw RlnError("Proof serialization error: the input buffer contained invalid data");
+    memcpy(p->p.comp, b + 9 + n, 160);
+    (*rln)->r->decompress_partial(p->p.comp, p->p.affine);
+    if (9 + n + 160 != len) throw RlnError(msg_read_len(9 + n + 160, len));
+    return CResult_FFI_RLNPartialProof_t{p.release(), no_string()};
+    GUARD_END(return (CResult_FFI_RLNPartialProof_t{nullptr, mk_string(m)}))
+}
+void ffi_rln_partial_proof_free(FFI_RLNPartialProof_t* p) { delete p; }
+// batched two-phase proving on host buffers: witness records as for rlnb200_prove_batch (the unknown fields of the partial
+// phase are ignored), partial points n × 320 bytes (canonical affine π_a | ρ | π_b | π_c)
+int rlnb200_partial_batch(FFI_RLN_t* const* rln, const uint8_t* witnesses, size_t n, uint8_t* partial_out, RlnString* err);
+int rlnb200_finish_batch(FFI_RLN_t* const* rln, const uint8_t* witnesses, size_t n, const uint8_t* partial, const uint8_t* rs,
+                         uint8_t* proofs_out, RlnString* err);
+
 // verify_zk_proof (proof.rs:856-894) then root / signal checks (public.rs:725-771)
 static CBoolResult_t verify_common(FFI_RLN_t* const* rln, const RlnProof& p, const uint8_t* x, const Vec_CFr_t* roots, bool use_tree_root) {
     GUARD_BEGIN
@@ -1328,6 +1553,45 @@ int rlnb200_prove_batch(FFI_RLN_t* const* rln, const uint8_t* witnesses, size_t 
         }
         std::vector<RlnProof> out;
         (*rln)->r->prove_host(ws, rs, out);
+        for (auto& w : ws) memset(w.secret, 0, 32);
+        for (size_t i = 0; i < n; i++) rln_proof_to_bytes(out[i], proofs_out + 290 * i);)
+}
+static std::vector<Witness> parse_records(Rln& r, const uint8_t* witnesses, size_t n, bool partial_phase) {
+    const size_t d = r.depth(), rec = 1 + 32 * (5 + d) + 16 + d;
+    std::vector<Witness> ws(n);
+    for (size_t i = 0; i < n; i++) {
+        if (partial_phase) {  // message_id / x / external_nullifier are not looked at: skip the range checks that involve them
+            const uint8_t* b = witnesses + rec * i;
+            memcpy(ws[i].secret, b + 1, 32); memcpy(ws[i].limit, b + 33, 32);
+            ws[i].path.assign(b + 105, b + 105 + 32 * d);
+            ws[i].index.assign(b + 113 + 32 * d, b + 113 + 33 * d);
+            memset(ws[i].message_id, 0, 32); memset(ws[i].x, 0, 32); memset(ws[i].ext_null, 0, 32);
+            if (!fr_is_canonical(ws[i].secret) || !fr_is_canonical(ws[i].limit)) throw RlnError("Non-canonical field element: value is not in [0, r-1]");
+        } else {
+            size_t used = witness_from_bytes(witnesses + rec * i, rec, ws[i]);
+            if (used != rec) throw RlnError(msg_read_len(used, rec));
+        }
+    }
+    return ws;
+}
+int rlnb200_partial_batch(FFI_RLN_t* const* rln, const uint8_t* witnesses, size_t n, uint8_t* partial_out, RlnString* err) {
+    INT_OP(
+        std::lock_guard<std::mutex> lk((*rln)->r->mu);
+        std::vector<Witness> ws = parse_records(*(*rln)->r, witnesses, n, true);
+        std::vector<PartialProofHost> out;
+        (*rln)->r->partial_host(ws, out);
+        for (auto& w : ws) memset(w.secret, 0, 32);
+        for (size_t i = 0; i < n; i++) memcpy(partial_out + 320 * i, out[i].affine, 320);)
+}
+int rlnb200_finish_batch(FFI_RLN_t* const* rln, const uint8_t* witnesses, size_t n, const uint8_t* partial, const uint8_t* rs,
+                         uint8_t* proofs_out, RlnString* err) {
+    INT_OP(
+        std::lock_guard<std::mutex> lk((*rln)->r->mu);
+        std::vector<Witness> ws = parse_records(*(*rln)->r, witnesses, n, false);
+        std::vector<PartialProofHost> pp(n);
+        for (size_t i = 0; i < n; i++) memcpy(pp[i].affine, partial + 320 * i, 320);
+        std::vector<RlnProof> out;
+        (*rln)->r->prove_host(ws, rs, out, pp.data());
         for (auto& w : ws) memset(w.secret, 0, 32);
         for (size_t i = 0; i < n; i++) rln_proof_to_bytes(out[i], proofs_out + 290 * i);)
 }

@@ -121,7 +121,17 @@ def lib():
         "ffi_hash_to_field_be": (POINTER(CFr), [POINTER(Vec_uint8)]),
         "ffi_poseidon_hash_pair": (POINTER(CFr), [POINTER(CFr), POINTER(CFr)]),
         "ffi_key_gen": (Vec_CFr, []),
+        "ffi_rln_partial_witness_input_new": (CResult_ptr, [POINTER(CFr), POINTER(CFr), POINTER(Vec_CFr), POINTER(Vec_uint8)]),
+        "ffi_rln_partial_witness_input_free": (None, [c_void_p]),
+        "ffi_generate_partial_zk_proof": (CResult_ptr, [pp, pp]),
+        "ffi_finish_rln_proof": (CResult_ptr, [pp, pp, pp]),
+        "ffi_rln_partial_proof_to_bytes_le": (CResult_Vec_uint8, [pp]),
+        "ffi_rln_partial_proof_free": (None, [c_void_p]),
         # extensions
+        "rlnb200_finish_rln_proof_with_rs": (CResult_ptr, [pp, pp, pp, POINTER(CFr), POINTER(CFr)]),
+        "rlnb200_bytes_le_to_rln_partial_proof": (CResult_ptr, [pp, POINTER(Vec_uint8)]),
+        "rlnb200_partial_batch": (c_int, [pp, c_void_p, c_size_t, c_void_p, POINTER(RlnString)]),
+        "rlnb200_finish_batch": (c_int, [pp, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, POINTER(RlnString)]),
         "rlnb200_generate_rln_proof_with_rs": (CResult_ptr, [pp, pp, POINTER(CFr), POINTER(CFr)]),
         "rlnb200_prove_batch": (c_int, [pp, c_void_p, c_size_t, c_void_p, c_void_p, POINTER(RlnString)]),
         "rlnb200_verify_batch": (c_int, [pp, c_void_p, c_size_t, c_void_p, POINTER(RlnString)]),

@@ -151,6 +151,43 @@ class RLNWitnessInput:
             self._h = c_void_p(None)
 
 
+class RLNPartialWitnessInput:
+    """rln/src/protocol/witness.rs:62-76 — the inputs that do not change between messages"""
+
+    def __init__(self, handle):
+        self._h = c_void_p(handle)
+
+    @classmethod
+    def new(cls, identity_secret, user_message_limit, path_elements, identity_path_index):
+        res = ffi.lib().ffi_rln_partial_witness_input_new(byref(_cfr(identity_secret)), byref(_cfr(user_message_limit)),
+                                                          byref(_vec_cfr(path_elements)), byref(_vec_u8(bytes(identity_path_index))))
+        return cls(_check_ptr(res))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            ffi.lib().ffi_rln_partial_witness_input_free(self._h)
+            self._h = c_void_p(None)
+
+
+class RLNPartialProof:
+    """PartialProof (rln/src/partial_proof.rs:30-43) behind FFI_RLNPartialProof"""
+
+    def __init__(self, handle):
+        self._h = c_void_p(handle)
+
+    def to_bytes_le(self):
+        res = ffi.lib().ffi_rln_partial_proof_to_bytes_le(byref(self._h))
+        msg = _take_string(res.err)
+        if msg:
+            raise RLNError(msg)
+        return _take_vec_u8(res.ok)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            ffi.lib().ffi_rln_partial_proof_free(self._h)
+            self._h = c_void_p(None)
+
+
 class RLNProofValues:
     """rln/src/protocol/proof.rs:100-190"""
 
@@ -309,6 +346,32 @@ class RLN:
     def generate_rln_proof_with_rs(self, witness: RLNWitnessInput, r: int, s: int) -> RLNProof:
         """generate_zk_proof_with_rs (rln/src/protocol/proof.rs:753-777) behind the ABI"""
         return RLNProof(_check_ptr(ffi.lib().rlnb200_generate_rln_proof_with_rs(byref(self._h), byref(witness._h), byref(_cfr(r)), byref(_cfr(s)))))
+
+    # two-phase proving (public.rs:664-697)
+    def generate_partial_zk_proof(self, partial_witness: RLNPartialWitnessInput) -> RLNPartialProof:
+        return RLNPartialProof(_check_ptr(ffi.lib().ffi_generate_partial_zk_proof(byref(self._h), byref(partial_witness._h))))
+
+    def finish_rln_proof(self, partial_proof: RLNPartialProof, witness: RLNWitnessInput) -> RLNProof:
+        return RLNProof(_check_ptr(ffi.lib().ffi_finish_rln_proof(byref(self._h), byref(partial_proof._h), byref(witness._h))))
+
+    def finish_rln_proof_with_rs(self, partial_proof: RLNPartialProof, witness: RLNWitnessInput, r: int, s: int) -> RLNProof:
+        return RLNProof(_check_ptr(ffi.lib().rlnb200_finish_rln_proof_with_rs(byref(self._h), byref(partial_proof._h), byref(witness._h),
+                                                                           byref(_cfr(r)), byref(_cfr(s)))))
+
+    def partial_proof_from_bytes_le(self, data: bytes) -> RLNPartialProof:
+        return RLNPartialProof(_check_ptr(ffi.lib().rlnb200_bytes_le_to_rln_partial_proof(byref(self._h), byref(_vec_u8(data)))))
+
+    def partial_batch(self, witnesses_le: bytes, n: int) -> bytes:
+        out = ctypes.create_string_buffer(320 * n)
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_partial_batch(byref(self._h), witnesses_le, n, out, byref(err)), err)
+        return out.raw
+
+    def finish_batch(self, witnesses_le: bytes, n: int, partial: bytes, rs: bytes = None) -> bytes:
+        out = ctypes.create_string_buffer(290 * n)
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_finish_batch(byref(self._h), witnesses_le, n, partial, rs, out, byref(err)), err)
+        return out.raw
 
     def verify_rln_proof(self, proof: RLNProof, x: int) -> bool:
         """public.rs:725-745 — raises RLNError with the reference's reason on failure"""
