@@ -367,6 +367,30 @@ def run_gpu(args, rank, local_rank, world):
                 "steps": e2e_steps, "api": "rlnb200_prove_batch (host witness records → host rln_proof bytes)"},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "stage_ms": stage,
     }
+    # ---- two-phase proving (rln/README.md:356-375): partial proofs computed once, finish per message
+    try:
+        d_pa = torch.empty(n * 320, dtype=torch.uint8, device=dev)
+        d_pc = torch.empty(n * 160, dtype=torch.uint8, device=dev)
+        d_p2 = torch.empty(n * 128, dtype=torch.uint8, device=dev)
+        rln.partial_batch_device(d_inputs.data_ptr(), n, d_pa.data_ptr(), d_pc.data_ptr(), stream.cuda_stream)
+        pe0, pe1, pe2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        pe0.record(stream)
+        rln.partial_batch_device(d_inputs.data_ptr(), n, d_pa.data_ptr(), d_pc.data_ptr(), stream.cuda_stream)
+        pe1.record(stream)
+        for _ in range(3):
+            rln.finish_batch_device(d_inputs.data_ptr(), d_rs.data_ptr(), d_pa.data_ptr(), n, d_p2.data_ptr(), 0, stream.cuda_stream)
+        pe2.record(stream)
+        torch.cuda.synchronize(dev)
+        assert torch.equal(d_p2, d_proofs), "finish(partial) differs from the full proofs"
+        line["two_phase"] = {"partial_proofs_per_s": n / (pe0.elapsed_time(pe1) * 1e-3), "finish_proofs_per_s": 3 * n / (pe1.elapsed_time(pe2) * 1e-3),
+                             "note": "finish output bit-equal to the full-proof output of the timed batch (same r, s)"}
+    except Exception as e:
+        line["two_phase"] = {"error": str(e)}
+    if world == 1 and not args.no_micro:
+        try:
+            line["merkle_microbench"] = merkle_microbench(rln, dev, hbm_peak)
+        except Exception as e:
+            line["merkle_microbench"] = {"error": str(e)}
     if world == 1 and not args.no_micro:
         try:
             line["msm_g1_microbench"] = msm_microbench(z, dev, hbm_peak, args.msm_log2)
@@ -375,6 +399,37 @@ def run_gpu(args, rank, local_rank, world):
     print(json.dumps(line), flush=True)
     if dist_on:
         dist.destroy_process_group()
+
+
+def merkle_microbench(rln, dev, hbm_peak):
+    """BASELINE.json configs[2]: Poseidon Merkle tree build over 2^20 leaves resident in HBM + 4 096 membership paths.
+    Algorithmic bytes: 64 MiB per build (32 MiB leaves read + 32 MiB nodes written), 660 B per path."""
+    import torch
+    import numpy as np
+    n = 1 << DEPTH
+    rng = np.random.default_rng(7)
+    raw = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    raw[:, 31] &= 0x1f
+    d_leaves = torch.from_numpy(raw).to(dev)
+    st = torch.cuda.current_stream(dev)
+    rln.set_tree(DEPTH)
+    rln.set_leaves_from_device(0, d_leaves.data_ptr(), n, st.cuda_stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    torch.cuda.synchronize(dev)
+    e0.record(st)
+    for _ in range(reps):
+        rln.set_leaves_from_device(0, d_leaves.data_ptr(), n, st.cuda_stream)
+    e1.record(st)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    idx = [int(x) for x in rng.integers(0, n, size=4096)]
+    t0 = time.perf_counter()
+    rln.get_merkle_proofs(idx)
+    t_paths = time.perf_counter() - t0
+    gbs = (64 << 20) / (ms * 1e-3) / 1e9
+    return {"leaves": n, "build_ms": ms, "hashes_per_s": (n - 1) / (ms * 1e-3), "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak,
+            "bytes_per_build": 64 << 20, "paths_4096_ms_host_roundtrip": 1e3 * t_paths}
 
 
 def msm_microbench(z, dev, hbm_peak, log2n):

@@ -194,6 +194,12 @@ int rlnb200_verify_batch(FFI_RLN_t *const *rln, const uint8_t *proofs, size_t n,
  * stream: a cudaStream_t (0 = default stream). */
 int rlnb200_prove_batch_device(FFI_RLN_t *const *rln, const void *d_inputs, const void *d_rs, size_t n,
                                void *d_proofs, void *d_values, void *d_affine, void *stream, RlnString *err);
+/* two-phase proving on DEVICE buffers: d_partial_affine n × 320 bytes, d_partial_compressed n × 160 bytes (ark compressed).
+ * The partial phase ignores the messageId / x / externalNullifier slots of d_inputs. */
+int rlnb200_partial_batch_device(FFI_RLN_t *const *rln, const void *d_inputs, size_t n, void *d_partial_affine,
+                                 void *d_partial_compressed, void *stream, RlnString *err);
+int rlnb200_finish_batch_device(FFI_RLN_t *const *rln, const void *d_inputs, const void *d_rs, const void *d_partial_affine, size_t n,
+                                void *d_proofs, void *d_values, void *stream, RlnString *err);
 /* fills the input-slot buffer for one witness record on the host (layout helper for callers/tests) */
 int rlnb200_witness_to_input_slots(FFI_RLN_t *const *rln, const uint8_t *witness_le, size_t len, uint8_t *slots_out,
                                    RlnString *err);
@@ -244,6 +250,8 @@ int rlnb200_hash_pairs(const uint8_t *pairs /* n*64 */, size_t n, uint8_t *out /
 int rlnb200_field_op(int field, int op, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out, RlnString *err);
 /* measured Montgomery-product rate (products/s over all SMs, CUDA-event timed); < 0 on error */
 double rlnb200_mul_throughput(int iters);
+/* pipe probe (thread-instructions per second): mode 0 wide integer MADs, 1 FP64 FMAs, 2 both interleaved */
+int rlnb200_pipe_probe(int mode, int iters, double out[2]);
 /* witness vector w (num_wires × 32) and quotient h (domain × 32) of one witness record */
 int rlnb200_debug_witness_and_h(FFI_RLN_t *const *rln, const uint8_t *witness_le, size_t len, uint8_t *w_out, uint8_t *h_out,
                                 RlnString *err);

@@ -24,6 +24,7 @@ struct Fq2 {
     HD Fq2 dbl() const { return {a.dbl(), b.dbl()}; }
     HD Fq2 conj() const { return {a, b.neg()}; }
     HD Fq2 operator*(const Fq2& o) const {  // Karatsuba, 3 base multiplications
+        // (inlined on purpose: out-of-line Fq products were measured 28 % slower in k_msm_accum<Fq2>, profiles/README.md)
         Fq t0 = a * o.a, t1 = b * o.b;
         Fq t2 = (a + b) * (o.a + o.b);
         return {t0 - t1, t2 - t0 - t1};

@@ -16,6 +16,7 @@
 // of 32 proofs walks the same (base, window) sub-table together.  Partial sums per (task, proof) are
 // combined by a second kernel.  Additions are complete (∞, P = ±Q handled), because duplicate bases
 // in a zkey cannot be excluded.
+#include <cstdlib>
 #include <vector>
 
 #include "device_api.hpp"
@@ -125,8 +126,8 @@ __device__ __forceinline__ int window_digit(const u32* s, int k, int c, u32& car
     return d;
 }
 
-template <class F>
-__global__ void __launch_bounds__(128) k_msm_accum(AccumArgs<F> a) {
+template <class F, bool PREFETCH, int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) k_msm_accum(AccumArgs<F> a) {
     const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= a.B) return;
     const MsmTask t = a.tasks[blockIdx.y];
@@ -144,6 +145,16 @@ __global__ void __launch_bounds__(128) k_msm_accum(AccumArgs<F> a) {
         if (!any) continue;
         const Affine<F>* tb = table + (size_t)b * a.K * half;
         u32 carry = 0;
+        if (!PREFETCH) {
+            for (int k = 0; k < a.K; k++) {
+                const int d = window_digit(s, k, a.c, carry);
+                if (d == 0) continue;
+                Affine<F> pt = ld_point<F>(tb + (size_t)k * half + ((d < 0 ? -d : d) - 1));
+                if (d < 0) pt.y = pt.y.neg();
+                acc.add_affine(pt);
+            }
+            continue;
+        }
         // software pipeline: fetch the table entry of window k+1 while adding that of window k
         int d = window_digit(s, 0, a.c, carry);
         Affine<F> nxt;
@@ -393,6 +404,11 @@ std::vector<MsmTask> msm_make_tasks(const FixedMsmPlan& plan, u32 B, bool g2, in
     return tasks;
 }
 
+static int accum_variant(const char* name) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : 0;
+}
+
 void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, u32 B, MsmWorkspace& ws, cudaStream_t s) {
     const u32 bx = B >= 128 ? 128 : 32;
     {   // G1: A, B1, L, H
@@ -401,7 +417,15 @@ void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, 
         for (int i = 0; i < 4; i++) { a.row[i] = plan.g1[i].row; a.table[i] = (const G1Affine*)plan.g1[i].table; a.which[i] = plan.g1[i].which_src; }
         a.tasks = ws.tasks_g1; a.part = ws.part_g1; a.B = B; a.c = plan.c; a.K = plan.K;
         if (ws.ev) cudaEventRecord(ws.ev[0], s);
-        if (ws.n_tasks_g1) k_msm_accum<Fq><<<dim3((B + bx - 1) / bx, ws.n_tasks_g1), bx, 0, s>>>(a);
+        if (ws.n_tasks_g1) {
+            dim3 grid((B + bx - 1) / bx, ws.n_tasks_g1);
+            switch (accum_variant("RLN_B200_G1_VARIANT")) {
+                case 1: k_msm_accum<Fq, true, 4><<<grid, bx, 0, s>>>(a); break;
+                case 2: k_msm_accum<Fq, false, 4><<<grid, bx, 0, s>>>(a); break;
+                case 3: k_msm_accum<Fq, false, 3><<<grid, bx, 0, s>>>(a); break;
+                default: k_msm_accum<Fq, true, 3><<<grid, bx, 0, s>>>(a); break;
+            }
+        }
         if (ws.ev) cudaEventRecord(ws.ev[1], s);
         k_msm_reduce<Fq><<<dim3((B + bx - 1) / bx, 4), bx, 0, s>>>(ws.part_g1, ws.tasks_g1, ws.n_tasks_g1, B, ws.sum_g1);
         if (ws.ev) cudaEventRecord(ws.ev[2], s);
@@ -411,7 +435,15 @@ void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, 
         a.src[0] = d_vals; a.src[1] = d_h;
         for (int i = 0; i < 4; i++) { a.row[i] = plan.g2.row; a.table[i] = (const G2Affine*)plan.g2.table; a.which[i] = plan.g2.which_src; }
         a.tasks = ws.tasks_g2; a.part = ws.part_g2; a.B = B; a.c = plan.c2; a.K = plan.K2;
-        if (ws.n_tasks_g2) k_msm_accum<Fq2><<<dim3((B + bx - 1) / bx, ws.n_tasks_g2), bx, 0, s>>>(a);
+        if (ws.n_tasks_g2) {
+            dim3 grid((B + bx - 1) / bx, ws.n_tasks_g2);
+            switch (accum_variant("RLN_B200_G2_VARIANT")) {
+                case 1: k_msm_accum<Fq2, false, 2><<<grid, bx, 0, s>>>(a); break;
+                case 2: k_msm_accum<Fq2, false, 3><<<grid, bx, 0, s>>>(a); break;
+                case 3: k_msm_accum<Fq2, true, 3><<<grid, bx, 0, s>>>(a); break;
+                default: k_msm_accum<Fq2, true, 2><<<grid, bx, 0, s>>>(a); break;
+            }
+        }
         if (ws.ev) cudaEventRecord(ws.ev[3], s);
         k_msm_reduce<Fq2><<<dim3((B + bx - 1) / bx, 1), bx, 0, s>>>(ws.part_g2, ws.tasks_g2, ws.n_tasks_g2, B, ws.sum_g2);
         if (ws.ev) cudaEventRecord(ws.ev[4], s);

@@ -40,6 +40,38 @@ __global__ void __launch_bounds__(256) k_mul_throughput(F* __restrict__ data, in
     }
     data[4 * i] = a; data[4 * i + 1] = b; data[4 * i + 2] = c; data[4 * i + 3] = d;
 }
+// pipe probe: mode 0 = wide integer MADs only, 1 = FP64 FMAs only, 2 = both interleaved (do the pipes overlap?)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_pipe_probe(u64* __restrict__ out, int iters) {
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    u64 a0 = t + 1, a1 = t + 2, a2 = t + 3, a3 = t + 5, a4 = t + 7, a5 = t + 11, a6 = t + 13, a7 = t + 17;
+    double d0 = t + 0.5, d1 = t + 1.5, d2 = t + 2.5, d3 = t + 3.5, d4 = t + 4.5, d5 = t + 5.5, d6 = t + 6.5, d7 = t + 7.5;
+    const u32 m = 0x9e3779b9u + t, n = 0x85ebca6bu ^ t;
+    const double x = 1.0000001, y = 0.9999999;
+    for (int i = 0; i < iters; i++) {
+        if (MODE != 1) {
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a0) : "r"(m), "r"(n));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a1) : "r"(m), "r"(n));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a2) : "r"(m), "r"(n));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a3) : "r"(m), "r"(n));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a4) : "r"(m), "r"(n));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a5) : "r"(m), "r"(n));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a6) : "r"(m), "r"(n));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a7) : "r"(m), "r"(n));
+        }
+        if (MODE != 0) {
+            asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(d0) : "d"(x), "d"(y));
+            asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(d1) : "d"(x), "d"(y));
+            asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(d2) : "d"(x), "d"(y));
+            asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(d3) : "d"(x), "d"(y));
+            asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(d4) : "d"(x), "d"(y));
+            asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(d5) : "d"(x), "d"(y));
+            asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(d6) : "d"(x), "d"(y));
+            asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(d7) : "d"(x), "d"(y));
+        }
+    }
+    out[t] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7 ^ (u64)__double_as_longlong(d0 + d1 + d2 + d3 + d4 + d5 + d6 + d7);
+}
 }  // namespace zk
 
 using namespace zk;
@@ -63,6 +95,40 @@ int rlnb200_field_op(int field, int op, const uint8_t* a, const uint8_t* b, size
             size_t l = strlen(m);
             err->ptr = (uint8_t*)malloc(l + 1); memcpy(err->ptr, m, l + 1); err->len = l; err->cap = l + 1;
         }
+        return -1;
+    }
+}
+// per-SM-clock warp instructions of each kind issued per second for the probe above; out[0] = wide MADs/s, out[1] = DFMAs/s
+int rlnb200_pipe_probe(int mode, int iters, double out[2]) {
+    try {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const size_t threads = (size_t)sms * 2048;
+        u64* d = nullptr;
+        ZK_CUDA_CHECK(cudaMalloc(&d, 8 * threads));
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        auto run = [&](int it) {
+            unsigned g = (unsigned)(threads / 256);
+            if (mode == 0) k_pipe_probe<0><<<g, 256>>>(d, it);
+            else if (mode == 1) k_pipe_probe<1><<<g, 256>>>(d, it);
+            else k_pipe_probe<2><<<g, 256>>>(d, it);
+        };
+        run(64);
+        cudaEventRecord(e0);
+        run(iters);
+        cudaEventRecord(e1);
+        ZK_CUDA_CHECK(cudaEventSynchronize(e1));
+        g_launch_count += 2;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaFree(d); cudaEventDestroy(e0); cudaEventDestroy(e1);
+        const double ops = (double)threads * 8.0 * iters / (ms * 1e-3);
+        out[0] = mode != 1 ? ops : 0.0;
+        out[1] = mode != 0 ? ops : 0.0;
+        return 0;
+    } catch (const CudaError&) {
         return -1;
     }
 }

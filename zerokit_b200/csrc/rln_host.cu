@@ -1614,6 +1614,18 @@ int rlnb200_prove_batch_device(FFI_RLN_t* const* rln, const void* d_inputs, cons
            (*rln)->r->prove_device((const uint8_t*)d_inputs, (const uint8_t*)d_rs, n, (uint8_t*)d_proofs, (uint8_t*)d_values, (uint8_t*)d_affine,
                                    (cudaStream_t)stream);)
 }
+int rlnb200_partial_batch_device(FFI_RLN_t* const* rln, const void* d_inputs, size_t n, void* d_partial_affine, void* d_partial_compressed,
+                                 void* stream, RlnString* err) {
+    INT_OP(std::lock_guard<std::mutex> lk((*rln)->r->mu);
+           (*rln)->r->prove_device((const uint8_t*)d_inputs, nullptr, n, nullptr, nullptr, nullptr, (cudaStream_t)stream, MSM_KNOWN, nullptr,
+                                   (uint8_t*)d_partial_affine, (uint8_t*)d_partial_compressed);)
+}
+int rlnb200_finish_batch_device(FFI_RLN_t* const* rln, const void* d_inputs, const void* d_rs, const void* d_partial_affine, size_t n,
+                                void* d_proofs, void* d_values, void* stream, RlnString* err) {
+    INT_OP(std::lock_guard<std::mutex> lk((*rln)->r->mu);
+           (*rln)->r->prove_device((const uint8_t*)d_inputs, (const uint8_t*)d_rs, n, (uint8_t*)d_proofs, (uint8_t*)d_values, nullptr,
+                                   (cudaStream_t)stream, MSM_UNKNOWN, (const uint8_t*)d_partial_affine);)
+}
 int rlnb200_witness_to_input_slots(FFI_RLN_t* const* rln, const uint8_t* witness_le, size_t len, uint8_t* slots_out, RlnString* err) {
     INT_OP(Witness w; witness_from_bytes(witness_le, len, w);
            if (w.path.size() / 32 != (*rln)->r->depth() || w.index.size() != (*rln)->r->depth()) throw RlnError("Protocol error: witness depth does not match the circuit");

@@ -136,6 +136,8 @@ def lib():
         "rlnb200_prove_batch": (c_int, [pp, c_void_p, c_size_t, c_void_p, c_void_p, POINTER(RlnString)]),
         "rlnb200_verify_batch": (c_int, [pp, c_void_p, c_size_t, c_void_p, POINTER(RlnString)]),
         "rlnb200_prove_batch_device": (c_int, [pp, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(RlnString)]),
+        "rlnb200_partial_batch_device": (c_int, [pp, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, POINTER(RlnString)]),
+        "rlnb200_finish_batch_device": (c_int, [pp, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, POINTER(RlnString)]),
         "rlnb200_witness_to_input_slots": (c_int, [pp, c_void_p, c_size_t, c_void_p, POINTER(RlnString)]),
         "rlnb200_input_slots": (c_size_t, [pp]),
         "rlnb200_state_tree_depth": (c_size_t, [pp]),
@@ -161,6 +163,7 @@ def lib():
         "rlnb200_num_wires": (c_size_t, [pp]),
         "rlnb200_domain_size": (c_size_t, [pp]),
         "rlnb200_mul_throughput": (c_double, [c_int]),
+        "rlnb200_pipe_probe": (c_int, [c_int, c_int, POINTER(c_double)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -399,6 +399,16 @@ class RLN:
         _check_int(ffi.lib().rlnb200_prove_batch_device(byref(self._h), c_void_p(d_inputs), c_void_p(d_rs), n, c_void_p(d_proofs),
                                                         c_void_p(d_values), c_void_p(d_affine), c_void_p(stream), byref(err)), err)
 
+    def partial_batch_device(self, d_inputs, n, d_partial_affine, d_partial_comp, stream=0):
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_partial_batch_device(byref(self._h), c_void_p(d_inputs), n, c_void_p(d_partial_affine),
+                                                          c_void_p(d_partial_comp), c_void_p(stream), byref(err)), err)
+
+    def finish_batch_device(self, d_inputs, d_rs, d_partial_affine, n, d_proofs, d_values=0, stream=0):
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_finish_batch_device(byref(self._h), c_void_p(d_inputs), c_void_p(d_rs), c_void_p(d_partial_affine), n,
+                                                         c_void_p(d_proofs), c_void_p(d_values), c_void_p(stream), byref(err)), err)
+
     def witness_to_input_slots(self, witness_le: bytes) -> bytes:
         out = ctypes.create_string_buffer(32 * self.input_slots())
         err = ffi.RlnString()
