@@ -35,6 +35,7 @@ extern "C" {
 typedef struct Vec_uint8 { uint8_t *ptr; size_t len; size_t cap; } Vec_uint8_t;
 typedef Vec_uint8_t RlnString;                         /* repr_c::String */
 typedef struct Vec_size { size_t *ptr; size_t len; size_t cap; } Vec_size_t;
+typedef struct Vec_bool { bool *ptr; size_t len; size_t cap; } Vec_bool_t;
 
 typedef struct CFr { uint8_t bytes[32]; } CFr_t;       /* rln/src/ffi/ffi_utils.rs:33-36 (opaque) */
 typedef struct Vec_CFr { CFr_t *ptr; size_t len; size_t cap; } Vec_CFr_t;
@@ -60,6 +61,7 @@ typedef struct CResult_FFI_RLNPartialProof { FFI_RLNPartialProof_t *ok; RlnStrin
 typedef struct CResult_FFI_MerkleProof { FFI_MerkleProof_t *ok; RlnString err; } CResult_FFI_MerkleProof_t;
 typedef struct CResult_CFr { CFr_t *ok; RlnString err; } CResult_CFr_t;
 typedef struct CResult_Vec_uint8 { Vec_uint8_t ok; RlnString err; } CResult_Vec_uint8_t;
+typedef struct CResult_Vec_CFr { Vec_CFr_t ok; RlnString err; } CResult_Vec_CFr_t;
 
 /* ------------------------------------------------------------------ RLN object (rln/src/ffi/ffi_rln.rs) */
 CResult_FFI_RLN_t ffi_rln_new(size_t tree_depth, const char *config_path);                      /* :22-57  */
@@ -91,6 +93,10 @@ CResult_FFI_RLNWitnessInput_t ffi_rln_witness_input_new_single(
     const CFr_t *identity_secret, const CFr_t *user_message_limit, const CFr_t *message_id,
     const Vec_CFr_t *path_elements, const Vec_uint8_t *identity_path_index,
     const CFr_t *x, const CFr_t *external_nullifier);                                           /* :326-358 */
+CResult_FFI_RLNWitnessInput_t ffi_rln_witness_input_new_multi(
+    const CFr_t *identity_secret, const CFr_t *user_message_limit, const Vec_CFr_t *message_ids,
+    const Vec_CFr_t *path_elements, const Vec_uint8_t *identity_path_index, const CFr_t *x,
+    const CFr_t *external_nullifier, const Vec_bool_t *selector_used);                          /* :360-396 */
 CResult_Vec_uint8_t ffi_rln_witness_to_bytes_le(FFI_RLNWitnessInput_t *const *witness);         /* :476-490 */
 CResult_FFI_RLNWitnessInput_t ffi_bytes_le_to_rln_witness(const Vec_uint8_t *bytes);            /* :508-522 */
 void ffi_rln_witness_input_free(FFI_RLNWitnessInput_t *witness);                                /* :556-559 */
@@ -128,6 +134,10 @@ CFr_t *ffi_rln_proof_values_get_x(FFI_RLNProofValues_t *const *pv);             
 CFr_t *ffi_rln_proof_values_get_external_nullifier(FFI_RLNProofValues_t *const *pv);            /* :728-733 */
 CResult_CFr_t ffi_rln_proof_values_get_y(FFI_RLNProofValues_t *const *pv);                      /* :735-743 */
 CResult_CFr_t ffi_rln_proof_values_get_nullifier(FFI_RLNProofValues_t *const *pv);              /* :745-753 */
+CResult_Vec_CFr_t ffi_rln_proof_values_get_ys(FFI_RLNProofValues_t *const *pv);                 /* :765-779 */
+CResult_Vec_CFr_t ffi_rln_proof_values_get_nullifiers(FFI_RLNProofValues_t *const *pv);         /* :781-795 */
+CResult_Vec_uint8_t ffi_rln_proof_values_get_selector_used(FFI_RLNProofValues_t *const *pv);    /* :755-763 (Vec<bool>) */
+uint8_t ffi_rln_proof_values_get_version_byte(FFI_RLNProofValues_t *const *pv);                 /* :797-800 */
 Vec_uint8_t ffi_rln_proof_values_to_bytes_le(FFI_RLNProofValues_t *const *pv);                  /* :802-805 */
 CResult_FFI_RLNProofValues_t ffi_bytes_le_to_rln_proof_values(const Vec_uint8_t *bytes);        /* :812-826 */
 void ffi_rln_proof_values_free(FFI_RLNProofValues_t *proof_values);                             /* :844-847 */
@@ -172,6 +182,12 @@ CResult_FFI_RLNPartialProof_t rlnb200_bytes_le_to_rln_partial_proof(FFI_RLN_t *c
 int rlnb200_partial_batch(FFI_RLN_t *const *rln, const uint8_t *witnesses, size_t n, uint8_t *partial_out, RlnString *err);
 int rlnb200_finish_batch(FFI_RLN_t *const *rln, const uint8_t *witnesses, size_t n, const uint8_t *partial, const uint8_t *rs,
                          uint8_t *proofs_out, RlnString *err);
+
+/* handle over the bundled multi message-id circuit (rln/resources/tree_depth_20/multi_message_id/max_out_4) */
+CResult_FFI_RLN_t rlnb200_rln_new_multi(size_t tree_depth, size_t max_out);
+/* byte length of one rln_witness_to_bytes_le / rln_proof_to_bytes_le record for this handle's circuit and message mode */
+size_t rlnb200_witness_record_len(FFI_RLN_t *const *rln);
+size_t rlnb200_proof_record_len(FFI_RLN_t *const *rln);
 
 /* Batched proving, HOST buffers.  witnesses: n concatenated rln_witness_to_bytes_le records (single
  * message-id layout, rln/src/protocol/witness.rs:369-415; all of length 1+32*(5+depth)+16+depth).

@@ -571,7 +571,7 @@ static bool prove_one(const OracleCtx& ctx, const Fr* inputs /*inputs_size*/, co
     static thread_local std::vector<U256> ws, hs;
     w.resize(nw);
     if (!evaluate_graph(ctx.g, inputs, vals, w.data())) return false;
-    if (pub5) for (int i = 0; i < 5; i++) pub5[i] = w[1 + i];
+    if (pub5) for (size_t i = 0; i + 1 < z.num_instance; i++) pub5[i] = w[1 + i];  // all public wires (5 single, 15 multi)
     witness_map(z, w.data(), h);
     ws.resize(nw);
     hs.resize(h.size());
@@ -693,6 +693,7 @@ void* orc_ctx_new(const uint8_t* zkey, size_t zlen, const uint8_t* graph, size_t
 void orc_ctx_free(void* p) { delete (OracleCtx*)p; }
 uint32_t orc_ctx_depth(void* p) { return ((OracleCtx*)p)->depth; }
 uint32_t orc_ctx_inputs_size(void* p) { return ((OracleCtx*)p)->g.inputs_size; }
+uint32_t orc_ctx_num_public(void* p) { return (uint32_t)((OracleCtx*)p)->z.num_instance - 1; }
 uint32_t orc_ctx_num_wires(void* p) { return (uint32_t)((OracleCtx*)p)->g.signals.size(); }
 uint32_t orc_ctx_domain(void* p) {
     OracleCtx* c = (OracleCtx*)p; size_t n = 1;
@@ -727,7 +728,8 @@ void orc_qap_h(void* p, const uint8_t* w, uint8_t* h_out) {
 }
 
 // Batch prove.  inputs: n × inputs_size × 32 B; rs: n × 64 B (r|s); proofs_out: n × 256 B
-// (A 64 | B 128 | C 64, affine canonical); pub_out: n × 160 B ([y, root, nullifier, x, en]) or NULL.
+// (A 64 | B 128 | C 64, affine canonical); pub_out: n × num_public × 32 B (the public wires w[1..], i.e.
+// [y, root, nullifier, x, en] for the single circuit) or NULL.
 // One worker thread per proof (the model rln/README.md:324-332 recommends); returns #failures.
 int orc_prove_batch(void* p, size_t n, const uint8_t* inputs, const uint8_t* rs, uint8_t* proofs_out, uint8_t* pub_out,
                     int nthreads) {
@@ -738,13 +740,14 @@ int orc_prove_batch(void* p, size_t n, const uint8_t* inputs, const uint8_t* rs,
     parallel_for(n, n == 1 ? 1 : nthreads, [&](size_t j) {
         std::vector<Fr> in(isz);
         for (size_t i = 0; i < isz; i++) in[i] = Fr::from_le32(inputs + (j * isz + i) * 32);
-        Fr r = Fr::from_le32(rs + 64 * j), s = Fr::from_le32(rs + 64 * j + 32), pub[5];
+        Fr r = Fr::from_le32(rs + 64 * j), s = Fr::from_le32(rs + 64 * j + 32), pub[64];
+        const size_t npub = c->z.num_instance - 1;
         ProofOut po;
         if (!prove_one(*c, in.data(), r, s, po, pub, inner)) { fails++; return; }
         g1_out(po.a, proofs_out + 256 * j);
         g2_out(po.b, proofs_out + 256 * j + 64);
         g1_out(po.c, proofs_out + 256 * j + 192);
-        if (pub_out) for (int i = 0; i < 5; i++) pub[i].to_le32(pub_out + 160 * j + 32 * i);
+        if (pub_out) for (size_t i = 0; i < npub; i++) pub[i].to_le32(pub_out + (npub * j + i) * 32);
     });
     return fails.load();
 }

@@ -27,7 +27,7 @@ def lib():
         L.orc_ctx_new.restype = vp
         L.orc_ctx_new.argtypes = [u8p, sz, u8p, sz]
         L.orc_ctx_free.argtypes = [vp]
-        for f in ("orc_ctx_depth", "orc_ctx_inputs_size", "orc_ctx_num_wires", "orc_ctx_domain"):
+        for f in ("orc_ctx_depth", "orc_ctx_inputs_size", "orc_ctx_num_wires", "orc_ctx_domain", "orc_ctx_num_public"):
             getattr(L, f).restype = ctypes.c_uint32
             getattr(L, f).argtypes = [vp]
         L.orc_ctx_input.argtypes = [vp, u8p, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]
@@ -120,6 +120,7 @@ class Ctx:
         self.inputs_size = L.orc_ctx_inputs_size(self.h)
         self.num_wires = L.orc_ctx_num_wires(self.h)
         self.domain = L.orc_ctx_domain(self.h)
+        self.num_public = L.orc_ctx_num_public(self.h)
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -132,13 +133,17 @@ class Ctx:
             raise KeyError(name)
         return off.value, ln.value
 
-    def inputs_buffer(self, secret, limit, message_id, path_elements, path_index, x, ext_null):
-        """rln/src/circuit/iden3calc.rs:106-181 + protocol/witness.rs:832-881 → bytes(inputs_size*32)"""
+    def inputs_buffer(self, secret, limit, message_id, path_elements, path_index, x, ext_null, selector_used=None):
+        """rln/src/circuit/iden3calc.rs:106-181 + protocol/witness.rs:832-881 → bytes(inputs_size*32).
+        Multi message-id circuits: message_id is a list and selector_used a list of bools."""
         buf = [0] * self.inputs_size
         buf[0] = 1
-        named = {"identitySecret": [secret], "userMessageLimit": [limit], "messageId": [message_id],
+        named = {"identitySecret": [secret], "userMessageLimit": [limit],
+                 "messageId": list(message_id) if selector_used is not None else [message_id],
                  "pathElements": list(path_elements), "identityPathIndex": list(path_index),
                  "x": [x], "externalNullifier": [ext_null]}
+        if selector_used is not None:
+            named["selectorUsed"] = [int(bool(v)) for v in selector_used]
         for k, vals in named.items():
             off, ln = self.input_slot(k)
             assert ln == len(vals), (k, ln, len(vals))
@@ -158,15 +163,17 @@ class Ctx:
         return out.raw
 
     def prove_batch(self, inputs_bytes, rs_bytes, n, nthreads=1):
-        """→ (proofs n×256 B [A|B|C affine canonical], publics n×160 B [y,root,nullifier,x,en])"""
+        """→ (proofs n×256 B [A|B|C affine canonical], publics n×num_public×32 B: the public wires,
+        [y,root,nullifier,x,en] for the single circuit)"""
         proofs = ctypes.create_string_buffer(256 * n)
-        pub = ctypes.create_string_buffer(160 * n)
+        pub = ctypes.create_string_buffer(32 * self.num_public * n)
         fails = lib().orc_prove_batch(self.h, n, inputs_bytes, rs_bytes, proofs, pub, nthreads)
         if fails:
             raise ValueError(f"{fails} proofs failed")
         return proofs.raw, pub.raw
 
-    def verify_batch(self, proofs, pub, n, npub=5, nthreads=1):
+    def verify_batch(self, proofs, pub, n, npub=None, nthreads=1):
+        npub = self.num_public if npub is None else npub
         ok = ctypes.create_string_buffer(n)
         lib().orc_verify_batch(self.h, n, proofs, pub, npub, ok, nthreads)
         return list(ok.raw)

@@ -257,8 +257,9 @@ def _duo(op, a, b):
     raise ValueError(name)
 
 
-def inputs_buffer(g, secret, limit, message_id, path_elements, path_index, x, ext_null):
-    """iden3calc.rs:106-181 + witness.rs:832-881 (single message id)."""
+def inputs_buffer(g, secret, limit, message_id, path_elements, path_index, x, ext_null, selector_used=None):
+    """iden3calc.rs:106-181 + witness.rs:832-881.  Single mode: message_id is one value; multi mode (graph has a
+    `selectorUsed` input): message_id is the list of message ids and selector_used the list of bools."""
     size = 0
     started = False
     for nd in g.nodes:
@@ -270,10 +271,13 @@ def inputs_buffer(g, secret, limit, message_id, path_elements, path_index, x, ex
     buf = [0] * (size + 1)
     buf[0] = 1
     named = {
-        "identitySecret": [secret], "userMessageLimit": [limit], "messageId": [message_id],
+        "identitySecret": [secret], "userMessageLimit": [limit],
+        "messageId": list(message_id) if selector_used is not None else [message_id],
         "pathElements": list(path_elements), "identityPathIndex": list(path_index),
         "x": [x], "externalNullifier": [ext_null],
     }
+    if selector_used is not None:
+        named["selectorUsed"] = [int(bool(v)) for v in selector_used]
     for k, vals in named.items():
         off, ln = g.inputs[k]
         if ln != len(vals):
@@ -479,6 +483,11 @@ def verify(z, proof, public_inputs):
         (pt_neg(OPS1, a), b), (z.alpha_g1, z.beta_g2), (vkx, z.gamma_g2), (c, z.delta_g2)])
 
 
+def public_inputs_multi(pv):
+    """proof.rs:870-884: ys…, root, nullifiers…, x, external_nullifier, selector_used… (as 0/1)"""
+    return list(pv["ys"]) + [pv["root"]] + list(pv["nullifiers"]) + [pv["x"], pv["external_nullifier"]] + [int(bool(v)) for v in pv["selector_used"]]
+
+
 def public_inputs_single(pv):
     """proof.rs:863-869: [y, root, nullifier, x, external_nullifier]"""
     return [pv["y"], pv["root"], pv["nullifier"], pv["x"], pv["external_nullifier"]]
@@ -543,9 +552,30 @@ def proof_values_to_bytes_le(pv):
     return b"\x00" + fr_le(pv["root"]) + fr_le(pv["external_nullifier"]) + fr_le(pv["x"]) + fr_le(pv["y"]) + fr_le(pv["nullifier"])
 
 
+def proof_values_to_bytes_le_multi(pv):
+    """proof.rs:192-236 (multi): 0x01 | root | external_nullifier | x | vec ys | vec nullifiers | vec bool selector_used"""
+    k = len(pv["ys"])
+    out = b"\x01" + fr_le(pv["root"]) + fr_le(pv["external_nullifier"]) + fr_le(pv["x"])
+    out += struct.pack("<Q", k) + b"".join(fr_le(v) for v in pv["ys"])
+    out += struct.pack("<Q", k) + b"".join(fr_le(v) for v in pv["nullifiers"])
+    return out + struct.pack("<Q", k) + bytes(int(bool(v)) for v in pv["selector_used"])
+
+
 def rln_proof_to_bytes_le(proof, pv):
     """proof.rs:413-428"""
+    if "ys" in pv:
+        return b"\x01" + proof_to_bytes(proof) + proof_values_to_bytes_le_multi(pv)
     return b"\x00" + proof_to_bytes(proof) + proof_values_to_bytes_le(pv)
+
+
+def witness_to_bytes_le_multi(secret, limit, message_ids, path_elements, path_index, x, ext_null, selector_used):
+    """witness.rs:400-413 (multi): 0x01 | secret | limit | vec path | vec<u8> index | x | en | vec message_ids | vec bool selector"""
+    out = b"\x01" + fr_le(secret) + fr_le(limit)
+    out += struct.pack("<Q", len(path_elements)) + b"".join(fr_le(e) for e in path_elements)
+    out += struct.pack("<Q", len(path_index)) + bytes(path_index)
+    out += fr_le(x) + fr_le(ext_null)
+    out += struct.pack("<Q", len(message_ids)) + b"".join(fr_le(m) for m in message_ids)
+    return out + struct.pack("<Q", len(selector_used)) + bytes(int(bool(v)) for v in selector_used)
 
 
 def witness_to_bytes_le(secret, limit, message_id, path_elements, path_index, x, ext_null):

@@ -245,3 +245,15 @@ def proof_values_from_witness(secret, limit, message_id, path_elements, path_ind
     y = (secret + x * a1) % R
     nullifier = poseidon([a1])
     return dict(root=root, x=x % R, external_nullifier=ext_null % R, y=y, nullifier=nullifier)
+
+
+def proof_values_from_witness_multi(secret, limit, message_ids, path_elements, path_index, x, ext_null, selector_used):
+    """witness.rs:781-803 (multi message-id): y_i = (secret + x·a1_i)·sel_i, nullifier_i = H(a1_i)·sel_i"""
+    root = compute_tree_root(secret, limit, path_elements, path_index)
+    ys, nulls = [], []
+    for mid, sel in zip(message_ids, selector_used):
+        a1 = poseidon([secret, ext_null, mid])
+        s = int(bool(sel))
+        ys.append((secret + x * a1) % R * s % R)
+        nulls.append(poseidon([a1]) * s % R)
+    return dict(root=root, x=x % R, external_nullifier=ext_null % R, ys=ys, nullifiers=nulls, selector_used=[bool(v) for v in selector_used])

@@ -199,6 +199,28 @@ def derived():
     out["kat_proof_d10"] = kat_proof(10, next(fs), 1000, 7, next(fs), next(fs), next(fs), next(fs), "depth-10 random")
     out["kat_proof_d20_r0"] = kat_proof(20, 987654321, 5, 4, 99, 3, 0, 5, "r = 0 (g1_b skipped, partial_proof.rs:242-248)")
 
+    # multi message-id circuit (max_out = 4), bundled with the reference (rln/src/circuit/mod.rs:36-42)
+    mdir = os.path.join(RES, "tree_depth_20", "multi_message_id", "max_out_4")
+    zm = G.parse_zkey(open(os.path.join(mdir, "rln_final.arkzkey"), "rb").read())
+    gm = G.parse_graph(open(os.path.join(mdir, "graph.bin"), "rb").read())
+    pe20 = [P.poseidon([i + 7]) for i in range(20)]
+    idx20 = [(5 * i + 1) % 2 for i in range(20)]
+    margs = (424242, 50, [3, 7, 11, 0], pe20, idx20, 1234567, 89, [True, False, True, False])
+    wm = G.evaluate(gm, G.inputs_buffer(gm, *margs))
+    pvm = P.proof_values_from_witness_multi(*margs)
+    assert wm[0] == 1 and wm[1:zm.num_instance] == G.public_inputs_multi(pvm), "multi public outputs"
+    hm = G.witness_map(zm, wm)
+    prm = G.prove(zm, wm, hm, 44, 77)
+    assert G.verify(zm, prm, wm[1:zm.num_instance])
+    out["kat_proof_multi_d20"] = {
+        "inputs": {"identity_secret": "424242", "user_message_limit": "50", "message_ids": ["3", "7", "11", "0"], "x": "1234567",
+                   "external_nullifier": "89", "selector_used": [True, False, True, False], "r": "44", "s": "77",
+                   "path_elements": "Poseidon([i+7])", "identity_path_index": "(5*i+1)%2"},
+        "public": {"root": str(pvm["root"]), "ys": [str(v) for v in pvm["ys"]], "nullifiers": [str(v) for v in pvm["nullifiers"]]},
+        "w_sha256": hashlib.sha256(b"".join(v.to_bytes(32, "little") for v in wm)).hexdigest(),
+        "rln_proof_le_hex": G.rln_proof_to_bytes_le(prm, pvm).hex(),
+        "witness_le_hex": G.witness_to_bytes_le_multi(*margs).hex(),
+    }
     # partial proof (rln/src/partial_proof.rs:108-274; rln/tests/protocol.rs:222-248 pins full == partial + finish)
     k = out["kat_proof_d10"]
     z = G.parse_zkey(open(os.path.join(RES, "tree_depth_10", "rln_final.arkzkey"), "rb").read())

@@ -38,6 +38,29 @@ def test_host_only_helpers_work_without_gpu(goldens):
         z.RLNWitnessInput.from_bytes_le(b[:-1])
 
 
+def test_multi_message_id_witness_codec(goldens):
+    """MultiV1 wire layout (rln/src/protocol/mode.rs:26-74, witness.rs:115-176,400-413) — host-only"""
+    import sys, os
+    import zerokit_b200 as z
+    from pyref import poseidon as P
+    k = goldens["derived"]["kat_proof_multi_d20"]
+    pe = [P.poseidon([i + 7]) for i in range(20)]
+    idx = [(5 * i + 1) % 2 for i in range(20)]
+    w = z.RLNWitnessInput.new_multi(424242, 50, [3, 7, 11, 0], pe, idx, 1234567, 89, [True, False, True, False])
+    assert w.to_bytes_le().hex() == k["witness_le_hex"]
+    assert z.RLNWitnessInput.from_bytes_le(bytes.fromhex(k["witness_le_hex"])).to_bytes_le().hex() == k["witness_le_hex"]
+    with pytest.raises(z.RLNError, match="At least one selector_used value must be true"):
+        z.RLNWitnessInput.new_multi(1, 50, [3, 7], pe, idx, 1, 1, [False, False])
+    with pytest.raises(z.RLNError, match="Duplicate message ID"):
+        z.RLNWitnessInput.new_multi(1, 50, [3, 3], pe, idx, 1, 1, [True, True])
+    z.RLNWitnessInput.new_multi(1, 50, [3, 3], pe, idx, 1, 1, [True, False])   # duplicates only count among used slots
+    with pytest.raises(z.RLNError, match=r"Message id \(50\) is not within user_message_limit \(50\)"):
+        z.RLNWitnessInput.new_multi(1, 50, [3, 50], pe, idx, 1, 1, [True, True])
+    z.RLNWitnessInput.new_multi(1, 50, [3, 50], pe, idx, 1, 1, [True, False])  # unused slots are not range-checked
+    with pytest.raises(z.RLNError, match="The field message_ids has length 2, but the field selector_used has length 1"):
+        z.RLNWitnessInput.new_multi(1, 50, [3, 4], pe, idx, 1, 1, [True])
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():

@@ -326,6 +326,60 @@ def test_partial_proofs(z, rln10, rln20, goldens, oracle):
     assert rln20.verify_batch(out2, n) == [1] * n
 
 
+def test_multi_message_id_circuit(z, goldens, oracle):
+    """the bundled max_out = 4 circuit (rln/resources/tree_depth_20/multi_message_id): golden proof, verification, mode checks"""
+    k = goldens["derived"]["kat_proof_multi_d20"]
+    rln = z.RLN.new_multi(20, 4)
+    assert rln.max_out() == 4 and rln.tree_depth() == 20
+    wit = z.RLNWitnessInput.from_bytes_le(bytes.fromhex(k["witness_le_hex"]))
+    proof = rln.generate_rln_proof_with_rs(wit, 44, 77)
+    assert proof.to_bytes_le().hex() == k["rln_proof_le_hex"]
+    pv = proof.values
+    assert [str(v) for v in pv.ys] == k["public"]["ys"] and [str(v) for v in pv.nullifiers] == k["public"]["nullifiers"]
+    assert pv.selector_used == [True, False, True, False] and pv.ys[1] == 0 and pv.nullifiers[3] == 0
+    assert rln.verify_with_roots(proof, pv.x, [pv.root]) is True
+    again = z.RLNProof.from_bytes_le(proof.to_bytes_le())
+    assert again.to_bytes_le() == proof.to_bytes_le()
+    bad = bytearray(proof.to_bytes_le())
+    bad[129 + 1 + 96 + 8] ^= 1  # ys[0]
+    with pytest.raises(z.RLNError, match="Invalid proof provided"):
+        rln.verify_with_roots(z.RLNProof.from_bytes_le(bytes(bad)), pv.x, [])
+    # batch of seeded witnesses against the oracle, plus two-phase proving on this circuit
+    mdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "zerokit_b200", "resources", "tree_depth_20",
+                        "multi_message_id", "max_out_4")
+    ctx = oracle.Ctx(open(os.path.join(mdir, "rln_final.arkzkey"), "rb").read(), open(os.path.join(mdir, "graph.bin"), "rb").read())
+    from pyref import groth16 as G, poseidon as P
+    fs = fr_stream(77)
+    n = 12
+    pe = [P.poseidon([i + 7]) for i in range(20)]
+    recs, rs, inputs, pvs = [], [], [], []
+    for j in range(n):
+        secret, x, en = next(fs), next(fs), next(fs)
+        mids = [(7 * j + i) % 50 for i in range(4)]
+        sel = [bool((j + i) % 3) or i == 0 for i in range(4)]
+        idx = [(j >> i) & 1 for i in range(20)]
+        recs.append(G.witness_to_bytes_le_multi(secret, 50, mids, pe, idx, x, en, sel))
+        inputs.append(ctx.inputs_buffer(secret, 50, mids, pe, idx, x, en, sel))
+        pvs.append(P.proof_values_from_witness_multi(secret, 50, mids, pe, idx, x, en, sel))
+        rs += [next(fs), next(fs)]
+    recs, rsb = b"".join(recs), fr_bytes(rs)
+    assert len(recs) == n * rln.witness_record_len()
+    out = rln.prove_batch(recs, n, rsb)
+    want_p, want_pub = ctx.prove_batch(b"".join(inputs), rsb, n, oracle.threads())
+    rl = rln.proof_record_len()
+    for j in range(n):
+        v = ints(want_p[256 * j:256 * (j + 1)])
+        proof_j = ((v[0], v[1]), ((v[2], v[3]), (v[4], v[5])), (v[6], v[7]))
+        assert ints(want_pub[480 * j:480 * (j + 1)]) == G.public_inputs_multi(pvs[j])
+        assert out[rl * j:rl * (j + 1)] == G.rln_proof_to_bytes_le(proof_j, pvs[j]), j
+    assert rln.verify_batch(out, n) == [1] * n
+    assert rln.finish_batch(recs, n, rln.partial_batch(recs, n), rsb) == out
+    # a single-mode witness on the multi circuit is rejected like validate_witness_against_graph does (proof.rs:658-665)
+    ks = goldens["derived"]["kat_proof_d20"]
+    with pytest.raises(z.RLNError, match="Witness message mode SingleV1 does not match graph mode MultiV1"):
+        rln.generate_rln_proof(z.RLNWitnessInput.from_bytes_le(bytes.fromhex(ks["witness_le_hex"])))
+
+
 def test_witness_errors(z, rln20):
     with pytest.raises(z.RLNError, match="tree_depth"):
         w = z.RLNWitnessInput.new_single(5, 10, 3, [1, 2], [0, 1], 7, 9)

@@ -46,8 +46,9 @@ void launch_merkle_rehash(Fr* d_nodes, u32 depth, size_t start, size_t count, cu
 // membership paths: for each index, depth sibling values (canonical bytes, leaf→root) and depth index bits
 void launch_merkle_paths(const Fr* d_nodes, u32 depth, const u64* d_indices, size_t n, uint8_t* d_elems_bytes, uint8_t* d_bits, cudaStream_t s);
 // proof values per witness (rln/src/protocol/witness.rs:759-828): inputs layout = circuit input slots
-// (canonical bytes, n × n_slots × 32); out = n × 5 × 32 bytes [root, ext_nullifier, x, y, nullifier]
-struct InputSlots { u32 secret, limit, message_id, path, index, x, ext_null, depth, n_slots; };
+// (canonical bytes, n × n_slots × 32); out = n × (3 + 2k) × 32 bytes [root, ext_nullifier, x, y_0..y_{k-1},
+// nullifier_0..nullifier_{k-1}], k = max_out (1 for the single message-id circuit)
+struct InputSlots { u32 secret, limit, message_id, path, index, x, ext_null, depth, n_slots, selector, max_out, multi; };
 void launch_proof_values(const uint8_t* d_inputs, InputSlots sl, size_t n, uint8_t* d_out, cudaStream_t s);
 // generic small helpers used by the FFI utilities (single-thread kernels)
 void launch_poseidon_n(const uint8_t* d_in_bytes, int n_inputs, uint8_t* d_out_bytes, cudaStream_t s);

@@ -158,7 +158,6 @@ __global__ void __launch_bounds__(64) k_proof_values(const uint8_t* __restrict__
     const uint8_t* in = inputs + j * (size_t)sl.n_slots * 32;
     Fr secret = load_canonical(in + 32 * sl.secret);
     Fr limit = load_canonical(in + 32 * sl.limit);
-    Fr mid = load_canonical(in + 32 * sl.message_id);
     Fr x = load_canonical(in + 32 * sl.x);
     Fr en = load_canonical(in + 32 * sl.ext_null);
     Fr root = d_hash2(d_hash1(secret), limit);
@@ -167,15 +166,20 @@ __global__ void __launch_bounds__(64) k_proof_values(const uint8_t* __restrict__
         Fr b = load_canonical(in + 32 * (sl.index + i));
         root = b.is_zero() ? d_hash2(root, e) : d_hash2(e, root);
     }
-    Fr a1 = d_hash3(secret, en, mid);
-    Fr y = secret + x * a1;
-    Fr nullifier = d_hash1(a1);
-    uint8_t* o = out + j * 160;
+    const u32 k = sl.max_out;
+    uint8_t* o = out + j * (size_t)(32 * (3 + 2 * k));
     store_canonical(o, root);
     store_canonical(o + 32, en);
     store_canonical(o + 64, x);
-    store_canonical(o + 96, y);
-    store_canonical(o + 128, nullifier);
+    for (u32 i = 0; i < k; i++) {  // witness.rs:773-798: y = (a0 + x·a1)·selector, nullifier = H(a1)·selector
+        Fr mid = load_canonical(in + 32 * (sl.message_id + i));
+        Fr a1 = d_hash3(secret, en, mid);
+        Fr y = secret + x * a1;
+        Fr nullifier = d_hash1(a1);
+        if (sl.multi && load_canonical(in + 32 * (sl.selector + i)).is_zero()) { y = Fr::zero(); nullifier = Fr::zero(); }
+        store_canonical(o + 96 + 32 * i, y);
+        store_canonical(o + 96 + 32 * (k + i), nullifier);
+    }
 }
 void launch_proof_values(const uint8_t* d_inputs, InputSlots sl, size_t n, uint8_t* d_out, cudaStream_t s) {
     if (!n) return;

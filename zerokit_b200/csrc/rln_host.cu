@@ -101,13 +101,23 @@ static void random_fr(uint8_t out[32]) {
 }
 
 // ------------------------------------------------------------------------------------------- witness record
-struct Witness {  // RLNWitnessInput, single message-id (rln/src/protocol/witness.rs:52-60)
-    uint8_t secret[32], limit[32], message_id[32], x[32], ext_null[32];
+// RLNWitnessInput (rln/src/protocol/witness.rs:52-60); message mode SingleV1 (k = 1) or MultiV1 (k = max_out)
+struct Witness {
+    uint8_t secret[32], limit[32], x[32], ext_null[32];
+    bool multi = false;
+    std::vector<uint8_t> mids;   // k × 32 message ids
+    std::vector<uint8_t> sel;    // k selector_used flags (multi mode only)
     std::vector<uint8_t> path;   // depth × 32
     std::vector<uint8_t> index;  // depth
+    size_t k() const { return mids.size() / 32; }
 };
-struct ProofValues {  // RLNProofValues single (rln/src/protocol/proof.rs:100-190)
-    uint8_t root[32], ext_null[32], x[32], y[32], nullifier[32];
+// RLNProofValues (rln/src/protocol/proof.rs:100-190)
+struct ProofValues {
+    uint8_t root[32], ext_null[32], x[32];
+    bool multi = false;
+    std::vector<uint8_t> ys, nulls;  // k × 32 each
+    std::vector<uint8_t> sel;        // k (multi only)
+    size_t k() const { return ys.size() / 32; }
 };
 struct RlnProof {
     uint8_t proof[128];  // ark-compressed A|B|C
@@ -118,37 +128,68 @@ struct PartialProofHost {  // PartialProof (rln/src/partial_proof.rs:30-43); the
     uint8_t comp[160];     // the same, ark-compressed 32 | 32 | 64 | 32
 };
 
-// rln_witness_to_bytes_le (witness.rs:369-415)
-static std::vector<uint8_t> witness_to_bytes(const Witness& w) {
-    std::vector<uint8_t> b;
-    b.push_back(0);
-    b.insert(b.end(), w.secret, w.secret + 32);
-    b.insert(b.end(), w.limit, w.limit + 32);
-    b.insert(b.end(), w.message_id, w.message_id + 32);
-    uint64_t n = w.path.size() / 32;
-    b.insert(b.end(), (uint8_t*)&n, (uint8_t*)&n + 8);
-    b.insert(b.end(), w.path.begin(), w.path.end());
-    n = w.index.size();
-    b.insert(b.end(), (uint8_t*)&n, (uint8_t*)&n + 8);
-    b.insert(b.end(), w.index.begin(), w.index.end());
-    b.insert(b.end(), w.x, w.x + 32);
-    b.insert(b.end(), w.ext_null, w.ext_null + 32);
-    return b;
-}
+static void put_u64(std::vector<uint8_t>& b, uint64_t v) { b.insert(b.end(), (uint8_t*)&v, (uint8_t*)&v + 8); }
 static std::string msg_read_len(size_t expected, size_t got) {
     std::ostringstream s;
     s << "Expected to read " << expected << " bytes but read " << got << " bytes";
     return s.str();
 }
-static void validate_witness(const Witness& w) {  // RLNWitnessInput::new_single (witness.rs:78-113)
+static std::string msg_mode(uint8_t b) {
+    char t[64];
+    snprintf(t, sizeof t, "Unknown message mode version byte: %#04x", b);
+    return t;
+}
+
+// rln_witness_to_bytes_le (witness.rs:369-415)
+static std::vector<uint8_t> witness_to_bytes(const Witness& w) {
+    std::vector<uint8_t> b;
+    b.push_back(w.multi ? 1 : 0);
+    b.insert(b.end(), w.secret, w.secret + 32);
+    b.insert(b.end(), w.limit, w.limit + 32);
+    if (!w.multi) b.insert(b.end(), w.mids.begin(), w.mids.end());
+    put_u64(b, w.path.size() / 32);
+    b.insert(b.end(), w.path.begin(), w.path.end());
+    put_u64(b, w.index.size());
+    b.insert(b.end(), w.index.begin(), w.index.end());
+    b.insert(b.end(), w.x, w.x + 32);
+    b.insert(b.end(), w.ext_null, w.ext_null + 32);
+    if (w.multi) {
+        put_u64(b, w.k());
+        b.insert(b.end(), w.mids.begin(), w.mids.end());
+        put_u64(b, w.sel.size());
+        b.insert(b.end(), w.sel.begin(), w.sel.end());
+    }
+    return b;
+}
+// RLNWitnessInput::new_single / new_multi (witness.rs:78-176)
+static void validate_witness(const Witness& w) {
     if (is_zero32(w.limit)) throw RlnError("User message limit cannot be zero");
     if (w.path.size() / 32 != w.index.size()) {
         std::ostringstream s;
         s << "Merkle proof length mismatch: expected " << w.path.size() / 32 << ", got " << w.index.size();
         throw RlnError(s.str());
     }
-    if (cmp_le32(w.message_id, w.limit) >= 0)
-        throw RlnError("Message id (" + decimal_le32(w.message_id) + ") is not within user_message_limit (" + decimal_le32(w.limit) + ")");
+    auto range_err = [&](const uint8_t* mid) {
+        return RlnError("Message id (" + decimal_le32(mid) + ") is not within user_message_limit (" + decimal_le32(w.limit) + ")");
+    };
+    if (!w.multi) {
+        if (cmp_le32(w.mids.data(), w.limit) >= 0) throw range_err(w.mids.data());
+        return;
+    }
+    if (w.k() == 0) throw RlnError("The field message_ids must contain at least one message_id");
+    if (w.sel.size() != w.k()) {
+        std::ostringstream s;
+        s << "The field message_ids has length " << w.k() << ", but the field selector_used has length " << w.sel.size();
+        throw RlnError(s.str());
+    }
+    bool any = false;
+    for (uint8_t v : w.sel) any = any || v;
+    if (!any) throw RlnError("At least one selector_used value must be true");
+    for (size_t i = 0; i < w.k(); i++)
+        for (size_t j = 0; j < i; j++)
+            if (w.sel[i] && w.sel[j] && !memcmp(&w.mids[32 * i], &w.mids[32 * j], 32)) throw RlnError("Duplicate message ID found in message_ids");
+    for (size_t i = 0; i < w.k(); i++)
+        if (w.sel[i] && cmp_le32(&w.mids[32 * i], w.limit) >= 0) throw range_err(&w.mids[32 * i]);
 }
 // bytes_le_to_rln_witness (witness.rs:470-560): returns bytes consumed
 static size_t witness_from_bytes(const uint8_t* b, size_t len, Witness& w) {
@@ -157,11 +198,8 @@ static size_t witness_from_bytes(const uint8_t* b, size_t len, Witness& w) {
         if (o + k > len) throw RlnError(msg_read_len(o + k, len));
     };
     need(1);
-    if (b[0] != 0) {
-        char t[64];
-        snprintf(t, sizeof t, "Unknown message mode version byte: %#04x", b[0]);
-        throw RlnError(t);
-    }
+    if (b[0] > 1) throw RlnError(msg_mode(b[0]));
+    w.multi = b[0] == 1;
     o = 1;
     auto fr = [&](uint8_t* dst) {
         need(32);
@@ -169,58 +207,134 @@ static size_t witness_from_bytes(const uint8_t* b, size_t len, Witness& w) {
         if (!fr_is_canonical(dst)) throw RlnError("Non-canonical field element: value is not in [0, r-1]");
         o += 32;
     };
+    auto vec_fr = [&](std::vector<uint8_t>& dst) {
+        need(8);
+        uint64_t n;
+        memcpy(&n, b + o, 8);
+        o += 8;
+        if (n > (len - o) / 32) throw RlnError(msg_read_len(o + n * 32, len));
+        dst.assign(b + o, b + o + 32 * n);
+        for (uint64_t i = 0; i < n; i++)
+            if (!fr_is_canonical(dst.data() + 32 * i)) throw RlnError("Non-canonical field element: value is not in [0, r-1]");
+        o += 32 * n;
+    };
+    auto vec_u8 = [&](std::vector<uint8_t>& dst) {
+        need(8);
+        uint64_t n;
+        memcpy(&n, b + o, 8);
+        o += 8;
+        if (n > len - o) throw RlnError(msg_read_len(o + n, len));
+        dst.assign(b + o, b + o + n);
+        o += n;
+    };
     fr(w.secret);
     fr(w.limit);
-    fr(w.message_id);
-    need(8);
-    uint64_t n;
-    memcpy(&n, b + o, 8);
-    o += 8;
-    if (n > (len - o) / 32) throw RlnError(msg_read_len(o + n * 32, len));
-    w.path.assign(b + o, b + o + 32 * n);
-    for (uint64_t i = 0; i < n; i++)
-        if (!fr_is_canonical(w.path.data() + 32 * i)) throw RlnError("Non-canonical field element: value is not in [0, r-1]");
-    o += 32 * n;
-    need(8);
-    memcpy(&n, b + o, 8);
-    o += 8;
-    if (n > len - o) throw RlnError(msg_read_len(o + n, len));
-    w.index.assign(b + o, b + o + n);
-    o += n;
+    if (!w.multi) {
+        w.mids.resize(32);
+        fr(w.mids.data());
+    }
+    vec_fr(w.path);
+    vec_u8(w.index);
     fr(w.x);
     fr(w.ext_null);
+    if (w.multi) {
+        vec_fr(w.mids);
+        vec_u8(w.sel);
+        for (auto& v : w.sel) v = v != 0;  // bytes_le_to_vec_bool: any non-zero byte is true (utils.rs:407-410)
+    }
     validate_witness(w);
     return o;
 }
-// rln_proof_values_to_bytes_le (proof.rs:192-236): version | root | external_nullifier | x | y | nullifier
-static void proof_values_to_bytes(const ProofValues& pv, uint8_t out[161]) {
-    out[0] = 0;
-    memcpy(out + 1, pv.root, 32);
-    memcpy(out + 33, pv.ext_null, 32);
-    memcpy(out + 65, pv.x, 32);
-    memcpy(out + 97, pv.y, 32);
-    memcpy(out + 129, pv.nullifier, 32);
+// rln_proof_values_to_bytes_le (proof.rs:192-236): version | root | external_nullifier | x | y | nullifier, or for MultiV1
+// version | root | external_nullifier | x | vec ys | vec nullifiers | vec bool selector_used
+static std::vector<uint8_t> proof_values_to_bytes(const ProofValues& pv) {
+    std::vector<uint8_t> b;
+    b.push_back(pv.multi ? 1 : 0);
+    b.insert(b.end(), pv.root, pv.root + 32);
+    b.insert(b.end(), pv.ext_null, pv.ext_null + 32);
+    b.insert(b.end(), pv.x, pv.x + 32);
+    if (!pv.multi) {
+        b.insert(b.end(), pv.ys.begin(), pv.ys.end());
+        b.insert(b.end(), pv.nulls.begin(), pv.nulls.end());
+    } else {
+        put_u64(b, pv.k());
+        b.insert(b.end(), pv.ys.begin(), pv.ys.end());
+        put_u64(b, pv.k());
+        b.insert(b.end(), pv.nulls.begin(), pv.nulls.end());
+        put_u64(b, pv.sel.size());
+        b.insert(b.end(), pv.sel.begin(), pv.sel.end());
+    }
+    return b;
 }
 static size_t proof_values_from_bytes(const uint8_t* b, size_t len, ProofValues& pv) {
     if (len < 1) throw RlnError(msg_read_len(1, 0));
-    if (b[0] != 0) {
-        char t[64];
-        snprintf(t, sizeof t, "Unknown message mode version byte: %#04x", b[0]);
-        throw RlnError(t);
+    if (b[0] > 1) throw RlnError(msg_mode(b[0]));
+    pv.multi = b[0] == 1;
+    size_t o = 1;
+    auto fr = [&](uint8_t* dst) {
+        if (o + 32 > len) throw RlnError("RLN utility error: Input data too short: expected at least 32 bytes, got " + std::to_string(len - o) + " bytes");
+        memcpy(dst, b + o, 32);
+        if (!fr_is_canonical(dst)) throw RlnError("Non-canonical field element: value is not in [0, r-1]");
+        o += 32;
+    };
+    auto vec_fr = [&](std::vector<uint8_t>& dst) {
+        if (o + 8 > len) throw RlnError("RLN utility error: Input data too short: expected at least 8 bytes, got " + std::to_string(len - o) + " bytes");
+        uint64_t n;
+        memcpy(&n, b + o, 8);
+        o += 8;
+        if (n > (len - o) / 32) throw RlnError("RLN utility error: Input data too short: expected at least " + std::to_string(8 + n * 32) + " bytes, got " + std::to_string(len - o + 8) + " bytes");
+        dst.assign(b + o, b + o + 32 * n);
+        for (uint64_t i = 0; i < n; i++)
+            if (!fr_is_canonical(dst.data() + 32 * i)) throw RlnError("Non-canonical field element: value is not in [0, r-1]");
+        o += 32 * n;
+    };
+    fr(pv.root);
+    fr(pv.ext_null);
+    fr(pv.x);
+    if (!pv.multi) {
+        pv.ys.resize(32);
+        pv.nulls.resize(32);
+        fr(pv.ys.data());
+        fr(pv.nulls.data());
+    } else {
+        vec_fr(pv.ys);
+        vec_fr(pv.nulls);
+        if (o + 8 > len) throw RlnError("RLN utility error: Input data too short: expected at least 8 bytes, got " + std::to_string(len - o) + " bytes");
+        uint64_t n;
+        memcpy(&n, b + o, 8);
+        o += 8;
+        if (n > len - o) throw RlnError("RLN utility error: Input data too short: expected at least " + std::to_string(8 + n) + " bytes, got " + std::to_string(len - o + 8) + " bytes");
+        pv.sel.assign(b + o, b + o + n);
+        for (auto& v : pv.sel) v = v != 0;
+        o += n;
+        if (pv.sel.size() != pv.k()) throw RlnError("The field ys has length " + std::to_string(pv.k()) + ", but the field selector_used has length " + std::to_string(pv.sel.size()));
+        if (pv.nulls.size() != pv.ys.size()) throw RlnError("The field ys has length " + std::to_string(pv.k()) + ", but the field nullifiers has length " + std::to_string(pv.nulls.size() / 32));
     }
-    if (len < 161) throw RlnError(msg_read_len(161, len));
-    uint8_t* dst[5] = {pv.root, pv.ext_null, pv.x, pv.y, pv.nullifier};
-    for (int i = 0; i < 5; i++) {
-        memcpy(dst[i], b + 1 + 32 * i, 32);
-        if (!fr_is_canonical(dst[i])) throw RlnError("Non-canonical field element: value is not in [0, r-1]");
-    }
-    return 161;
+    return o;
 }
 // rln_proof_to_bytes_le (proof.rs:413-428): version | proof(128) | proof_values
-static void rln_proof_to_bytes(const RlnProof& p, uint8_t out[290]) {
-    out[0] = 0;
-    memcpy(out + 1, p.proof, 128);
-    proof_values_to_bytes(p.pv, out + 129);
+static std::vector<uint8_t> rln_proof_to_bytes(const RlnProof& p) {
+    std::vector<uint8_t> b;
+    b.push_back(p.pv.multi ? 1 : 0);
+    b.insert(b.end(), p.proof, p.proof + 128);
+    std::vector<uint8_t> v = proof_values_to_bytes(p.pv);
+    b.insert(b.end(), v.begin(), v.end());
+    return b;
+}
+// public inputs in circuit order (proof.rs:863-884): single [y, root, nullifier, x, en]; multi [ys…, root, nullifiers…, x, en, selectors…]
+static std::vector<uint8_t> public_inputs(const ProofValues& pv) {
+    std::vector<uint8_t> b(pv.ys);
+    b.insert(b.end(), pv.root, pv.root + 32);
+    b.insert(b.end(), pv.nulls.begin(), pv.nulls.end());
+    b.insert(b.end(), pv.x, pv.x + 32);
+    b.insert(b.end(), pv.ext_null, pv.ext_null + 32);
+    if (pv.multi)
+        for (uint8_t v : pv.sel) {
+            uint8_t fr[32] = {0};
+            fr[0] = v ? 1 : 0;
+            b.insert(b.end(), fr, fr + 32);
+        }
+    return b;
 }
 
 // ------------------------------------------------------------------------------------------- the RLN object
@@ -231,6 +345,10 @@ class Rln {
 
     size_t depth() const { return depth_; }
     size_t tree_depth() const { return tree_depth_; }
+    size_t max_out() const { return max_out_; }
+    bool multi() const { return multi_; }
+    size_t values_stride() const { return 32 * (3 + 2 * max_out_); }  // root | ext_null | x | ys[k] | nullifiers[k]
+    size_t n_public() const { return vk_.n_public; }
     uint32_t n_slots() const { return gh_.n_slots; }
     uint32_t n_wires() const { return (uint32_t)gh_.signals.size(); }
     uint32_t domain() const { return domain_; }
@@ -269,7 +387,7 @@ class Rln {
         *bytes = 0;
         for (int i = 0; i < 5; i++) *bytes += d_tab_[i].bytes;
     }
-    void verify_batch(const uint8_t* proofs128, const uint8_t* publics160_circuit_order, size_t n, uint8_t* ok);
+    void verify_batch(const uint8_t* proofs128, const uint8_t* publics_circuit_order, size_t n, uint8_t* ok);
     // witness, qap, g1 accumulate, g1 reduce, g2 accumulate, g2 reduce, assemble, proof values
     float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     std::mutex mu;
@@ -288,6 +406,8 @@ class Rln {
     ZkeyHost zk_;
     GraphHost gh_;
     size_t depth_ = 0;       // circuit tree depth (len of pathElements)
+    size_t max_out_ = 1;     // message-id slots per proof (rln/src/circuit/mod.rs:181-194)
+    bool multi_ = false;
     size_t tree_depth_ = 0;  // depth of the stateful tree
     uint32_t domain_ = 0, log_domain_ = 0;
     InputSlots slots_{};
@@ -391,8 +511,9 @@ Rln::~Rln() {
 // are; the unknown inputs are messageId, x and externalNullifier (witness.rs:887-931).
 void Rln::compute_known_mask() {
     std::vector<uint8_t> slot_unknown(gh_.n_slots, 0);
-    for (const char* name : {"messageId", "x", "externalNullifier"}) {
+    for (const char* name : {"messageId", "x", "externalNullifier", "selectorUsed"}) {
         auto it = gh_.inputs.find(name);
+        if (it == gh_.inputs.end()) continue;
         for (uint32_t i = 0; i < it->second.second; i++) slot_unknown[it->second.first + i] = 1;
     }
     std::vector<uint8_t> known(gh_.prog.size());
@@ -418,9 +539,15 @@ void Rln::check_graph_shape() {
         if (it == gh_.inputs.end()) throw RlnError(std::string("Graph error: missing input signal ") + name);
         return it->second;
     };
-    if (gh_.inputs.count("selectorUsed"))
-        throw RlnError("Graph error: multi message-id circuits are not supported by this build (SURVEY §8f item 2)");
     auto pe = need("pathElements"), pi = need("identityPathIndex");
+    auto mid = need("messageId");
+    multi_ = gh_.inputs.count("selectorUsed") != 0;
+    max_out_ = multi_ ? mid.second : 1;
+    if (mid.second != max_out_ || max_out_ == 0 || max_out_ > 16) throw RlnError("Graph error: unsupported number of messageId slots");
+    if (multi_ && need("selectorUsed").second != max_out_) throw RlnError("Graph error: selectorUsed / messageId length mismatch");
+    slots_.selector = multi_ ? need("selectorUsed").first : 0;
+    slots_.max_out = (u32)max_out_;
+    slots_.multi = multi_ ? 1 : 0;
     depth_ = pe.second;
     if (pi.second != depth_) throw RlnError("Graph error: pathElements / identityPathIndex length mismatch");
     slots_.secret = need("identitySecret").first;
@@ -436,6 +563,7 @@ void Rln::check_graph_shape() {
     if (zk_.a_query.size() / 64 != nw || zk_.b_g1.size() / 64 != nw || zk_.b_g2.size() / 128 != nw)
         throw RlnError("ZKey error: query sizes do not match the witness graph");
     if (zk_.l_query.size() / 64 + zk_.num_instance != nw) throw RlnError("ZKey error: l_query size does not match the witness graph");
+    if (zk_.num_instance != 1 + 3 + 2 * max_out_ + (multi_ ? max_out_ : 0)) throw RlnError("ZKey error: number of public inputs does not match the message mode of the graph");
     for (auto c : zk_.a_col)
         if (c >= nw) throw RlnError("ZKey error: matrix column out of range");
     for (auto c : zk_.b_col)
@@ -780,7 +908,7 @@ void Rln::reserve(size_t B) {
     ws_sum1_.alloc(sizeof(G1XYZZ) * 4 * B);
     ws_sum2_.alloc(sizeof(G2XYZZ) * B);
     ws_proofs_.alloc(128 * B);
-    ws_values_.alloc(160 * B);
+    ws_values_.alloc(values_stride() * B);
     ws_affine_.alloc(256 * B);
     ws_partial_.alloc(320 * B);
     ws_partial_comp_.alloc(160 * B);
@@ -801,7 +929,7 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
         if (d_values && phase != MSM_KNOWN) {  // proof values only need the inputs: a latency-bound kernel, run beside the main pipeline
             ZK_CUDA_CHECK(cudaEventRecord(fork_, s));
             ZK_CUDA_CHECK(cudaStreamWaitEvent(side_, fork_, 0));
-            launch_proof_values(in, slots_, B, d_values + 160 * off, side_);
+            launch_proof_values(in, slots_, B, d_values + values_stride() * off, side_);
             ZK_CUDA_CHECK(cudaEventRecord(join_, side_));
         }
         ZK_CUDA_CHECK(cudaEventRecord(ev_[0], s));
@@ -854,7 +982,9 @@ void Rln::witness_slots(const Witness& w, uint8_t* slots) const {  // iden3calc.
     slots[0] = 1;
     memcpy(slots + 32 * slots_.secret, w.secret, 32);
     memcpy(slots + 32 * slots_.limit, w.limit, 32);
-    memcpy(slots + 32 * slots_.message_id, w.message_id, 32);
+    memcpy(slots + 32 * slots_.message_id, w.mids.data(), 32 * max_out_);
+    if (multi_)
+        for (size_t i = 0; i < max_out_; i++) slots[32 * (slots_.selector + i)] = w.sel[i] ? 1 : 0;
     memcpy(slots + 32 * slots_.path, w.path.data(), 32 * depth_);
     for (size_t i = 0; i < depth_; i++) slots[32 * (slots_.index + i)] = w.index[i];
     memcpy(slots + 32 * slots_.x, w.x, 32);
@@ -866,6 +996,14 @@ void Rln::prove_host(const std::vector<Witness>& wsv, const uint8_t* rs, std::ve
     out.resize(n);
     if (!n) return;
     for (const Witness& w : wsv) {  // validate_witness_against_graph (proof.rs:644-700)
+        if (w.multi != multi_)
+            throw RlnError(std::string("Protocol error: Witness message mode ") + (w.multi ? "MultiV1" : "SingleV1") + " does not match graph mode " +
+                           (multi_ ? "MultiV1" : "SingleV1"));
+        if (w.k() != max_out_) {
+            std::ostringstream s;
+            s << "Protocol error: The field message_ids has length " << w.k() << ", but the field max_out has length " << max_out_;
+            throw RlnError(s.str());
+        }
         if (w.path.size() / 32 != depth_) {
             std::ostringstream s;
             s << "Protocol error: The field path_elements has length " << w.path.size() / 32 << ", but the field tree_depth has length " << depth_;
@@ -879,7 +1017,8 @@ void Rln::prove_host(const std::vector<Witness>& wsv, const uint8_t* rs, std::ve
     }
     const size_t chunk = n < max_batch_ ? n : max_batch_;
     reserve(chunk);
-    std::vector<uint8_t> slots(chunk * (size_t)gh_.n_slots * 32), rsb(chunk * 64), proofs(chunk * 128), values(chunk * 160);
+    const size_t vs = values_stride(), k = max_out_;
+    std::vector<uint8_t> slots(chunk * (size_t)gh_.n_slots * 32), rsb(chunk * 64), proofs(chunk * 128), values(chunk * vs);
     for (size_t off = 0; off < n; off += chunk) {
         const size_t B = n - off < chunk ? n - off : chunk;
         for (size_t j = 0; j < B; j++) witness_slots(wsv[off + j], slots.data() + j * (size_t)gh_.n_slots * 32);
@@ -897,19 +1036,21 @@ void Rln::prove_host(const std::vector<Witness>& wsv, const uint8_t* rs, std::ve
         prove_device(ws_inputs_.as<uint8_t>(), ws_rs_.as<uint8_t>(), B, ws_proofs_.as<uint8_t>(), ws_values_.as<uint8_t>(), nullptr, stream_,
                      partials ? MSM_UNKNOWN : MSM_FULL, partials ? ws_partial_.as<uint8_t>() : nullptr);
         ZK_CUDA_CHECK(cudaMemcpyAsync(proofs.data(), ws_proofs_.p, 128 * B, cudaMemcpyDeviceToHost, stream_));
-        ZK_CUDA_CHECK(cudaMemcpyAsync(values.data(), ws_values_.p, 160 * B, cudaMemcpyDeviceToHost, stream_));
+        ZK_CUDA_CHECK(cudaMemcpyAsync(values.data(), ws_values_.p, vs * B, cudaMemcpyDeviceToHost, stream_));
         // secrets do not linger in the staging buffers (reference zeroises them: rln/src/circuit/iden3calc.rs:44-57)
         ZK_CUDA_CHECK(cudaMemsetAsync(ws_inputs_.p, 0, B * (size_t)gh_.n_slots * 32, stream_));
         ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
         for (size_t j = 0; j < B; j++) {
             RlnProof& p = out[off + j];
             memcpy(p.proof, proofs.data() + 128 * j, 128);
-            const uint8_t* v = values.data() + 160 * j;
+            const uint8_t* v = values.data() + vs * j;
             memcpy(p.pv.root, v, 32);
             memcpy(p.pv.ext_null, v + 32, 32);
             memcpy(p.pv.x, v + 64, 32);
-            memcpy(p.pv.y, v + 96, 32);
-            memcpy(p.pv.nullifier, v + 128, 32);
+            p.pv.multi = multi_;
+            p.pv.ys.assign(v + 96, v + 96 + 32 * k);
+            p.pv.nulls.assign(v + 96 + 32 * k, v + 96 + 64 * k);
+            if (multi_) p.pv.sel = wsv[off + j].sel;
         }
     }
     memset(slots.data(), 0, slots.size());
@@ -920,7 +1061,7 @@ void Rln::partial_host(const std::vector<Witness>& wsv, std::vector<PartialProof
     out.resize(n);
     if (!n) return;
     for (const Witness& w : wsv)
-        if (w.path.size() / 32 != depth_ || w.index.size() != depth_)
+        if (w.path.size() / 32 != depth_ || w.index.size() != depth_ || w.k() != max_out_)
             throw RlnError("Protocol error: partial witness depth does not match the circuit tree_depth");
     const size_t chunk = n < max_batch_ ? n : max_batch_;
     reserve(chunk);
@@ -929,7 +1070,8 @@ void Rln::partial_host(const std::vector<Witness>& wsv, std::vector<PartialProof
         const size_t B = n - off < chunk ? n - off : chunk;
         for (size_t j = 0; j < B; j++) {
             Witness w = wsv[off + j];
-            memset(w.message_id, 0, 32);  // the unknown inputs are None in the reference; any value works, their wires are not used
+            std::fill(w.mids.begin(), w.mids.end(), 0);  // the unknown inputs are None in the reference; any value works, their wires are not used
+            std::fill(w.sel.begin(), w.sel.end(), 0);
             memset(w.x, 0, 32);
             memset(w.ext_null, 0, 32);
             witness_slots(w, slots.data() + j * (size_t)gh_.n_slots * 32);
@@ -1073,6 +1215,38 @@ static std::vector<uint8_t> read_file(const std::string& path) {
     return std::vector<uint8_t>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
 }
 
+// record lengths of rln_witness_to_bytes_le / rln_proof_to_bytes_le for the handle's circuit
+static size_t witness_record_len(const Rln& r) {
+    const size_t d = r.depth(), k = r.max_out();
+    return r.multi() ? 1 + 64 + (8 + 32 * d) + (8 + d) + 64 + (8 + 32 * k) + (8 + k) : 1 + 32 * (5 + d) + 16 + d;
+}
+static size_t proof_record_len(const Rln& r) {
+    const size_t k = r.max_out();
+    return r.multi() ? 1 + 128 + 1 + 96 + (8 + 32 * k) * 2 + (8 + k) : 290;
+}
+static std::vector<Witness> parse_records(Rln& r, const uint8_t* witnesses, size_t n, bool partial_phase) {
+    const size_t d = r.depth(), rec = witness_record_len(r);
+    std::vector<Witness> ws(n);
+    for (size_t i = 0; i < n; i++) {
+        if (partial_phase) {  // message ids / x / external_nullifier are not looked at: skip the range checks that involve them
+            const uint8_t* b = witnesses + rec * i;
+            const size_t po = r.multi() ? 65 : 97;  // offset of the path vector (single records carry message_id first)
+            memcpy(ws[i].secret, b + 1, 32); memcpy(ws[i].limit, b + 33, 32);
+            ws[i].path.assign(b + po + 8, b + po + 8 + 32 * d);
+            ws[i].index.assign(b + po + 16 + 32 * d, b + po + 16 + 33 * d);
+            ws[i].multi = r.multi();
+            ws[i].mids.assign(32 * r.max_out(), 0);
+            ws[i].sel.assign(r.multi() ? r.max_out() : 0, 0);
+            memset(ws[i].x, 0, 32); memset(ws[i].ext_null, 0, 32);
+            if (!fr_is_canonical(ws[i].secret) || !fr_is_canonical(ws[i].limit)) throw RlnError("Non-canonical field element: value is not in [0, r-1]");
+        } else {
+            size_t used = witness_from_bytes(witnesses + rec * i, rec, ws[i]);
+            if (used != rec) throw RlnError(msg_read_len(used, rec));
+        }
+    }
+    return ws;
+}
+
 extern "C" {
 
 // ---- RLN object -------------------------------------------------------------------------------
@@ -1108,7 +1282,23 @@ CResult_FFI_RLN_t ffi_rln_new_with_params(size_t tree_depth, const Vec_uint8_t* 
 }
 void ffi_rln_free(FFI_RLN_t* rln) { delete rln; }
 size_t ffi_rln_get_tree_depth(FFI_RLN_t* const* rln) { return (*rln)->r->depth(); }
-size_t ffi_rln_get_max_out(FFI_RLN_t* const* rln) { (void)rln; return 1; }
+size_t ffi_rln_get_max_out(FFI_RLN_t* const* rln) { return (*rln)->r->max_out(); }
+// bundled multi message-id circuit (rln/resources/tree_depth_20/multi_message_id/max_out_4; rln/src/circuit/mod.rs:36-42)
+CResult_FFI_RLN_t rlnb200_rln_new_multi(size_t tree_depth, size_t max_out) {
+    GUARD_BEGIN
+    std::ostringstream dir;
+    dir << resources_dir() << "/tree_depth_" << tree_depth << "/multi_message_id/max_out_" << max_out;
+    std::vector<uint8_t> zkey = read_file(dir.str() + "/rln_final.arkzkey"), graph = read_file(dir.str() + "/graph.bin");
+    FFI_RLN* h = new FFI_RLN();
+    try {
+        h->r = std::make_unique<Rln>(tree_depth, zkey.data(), zkey.size(), graph.data(), graph.size());
+    } catch (...) {
+        delete h;
+        throw;
+    }
+    return CResult_FFI_RLN_t{h, no_string()};
+    GUARD_END(return (CResult_FFI_RLN_t{nullptr, mk_string(m)}))
+}
 
 // ---- tree -------------------------------------------------------------------------------------
 #define BOOL_OP(...)                                                      \
@@ -1191,11 +1381,31 @@ CResult_FFI_RLNWitnessInput_t ffi_rln_witness_input_new_single(const CFr_t* iden
     auto w = std::make_unique<FFI_RLNWitnessInput>();
     memcpy(w->w.secret, identity_secret->bytes, 32);
     memcpy(w->w.limit, user_message_limit->bytes, 32);
-    memcpy(w->w.message_id, message_id->bytes, 32);
+    w->w.mids.assign(message_id->bytes, message_id->bytes + 32);
     memcpy(w->w.x, x->bytes, 32);
     memcpy(w->w.ext_null, external_nullifier->bytes, 32);
     w->w.path.assign((const uint8_t*)path_elements->ptr, (const uint8_t*)path_elements->ptr + 32 * path_elements->len);
     w->w.index.assign(identity_path_index->ptr, identity_path_index->ptr + identity_path_index->len);
+    validate_witness(w->w);
+    return CResult_FFI_RLNWitnessInput_t{w.release(), no_string()};
+    GUARD_END(return (CResult_FFI_RLNWitnessInput_t{nullptr, mk_string(m)}))
+}
+CResult_FFI_RLNWitnessInput_t ffi_rln_witness_input_new_multi(const CFr_t* identity_secret, const CFr_t* user_message_limit,
+                                                              const Vec_CFr_t* message_ids, const Vec_CFr_t* path_elements,
+                                                              const Vec_uint8_t* identity_path_index, const CFr_t* x,
+                                                              const CFr_t* external_nullifier, const Vec_bool_t* selector_used) {
+    GUARD_BEGIN
+    auto w = std::make_unique<FFI_RLNWitnessInput>();
+    w->w.multi = true;
+    memcpy(w->w.secret, identity_secret->bytes, 32);
+    memcpy(w->w.limit, user_message_limit->bytes, 32);
+    memcpy(w->w.x, x->bytes, 32);
+    memcpy(w->w.ext_null, external_nullifier->bytes, 32);
+    w->w.mids.assign((const uint8_t*)message_ids->ptr, (const uint8_t*)message_ids->ptr + 32 * message_ids->len);
+    w->w.path.assign((const uint8_t*)path_elements->ptr, (const uint8_t*)path_elements->ptr + 32 * path_elements->len);
+    w->w.index.assign(identity_path_index->ptr, identity_path_index->ptr + identity_path_index->len);
+    w->w.sel.resize(selector_used->len);
+    for (size_t i = 0; i < selector_used->len; i++) w->w.sel[i] = selector_used->ptr[i] ? 1 : 0;
     validate_witness(w->w);
     return CResult_FFI_RLNWitnessInput_t{w.release(), no_string()};
     GUARD_END(return (CResult_FFI_RLNWitnessInput_t{nullptr, mk_string(m)}))
@@ -1245,7 +1455,7 @@ CResult_FFI_RLNPartialWitnessInput_t ffi_rln_partial_witness_input_new(const CFr
                                                                        const Vec_CFr_t* path_elements, const Vec_uint8_t* identity_path_index) {
     GUARD_BEGIN
     auto w = std::make_unique<FFI_RLNPartialWitnessInput>();
-    memset(&w->w.message_id, 0, 32); memset(&w->w.x, 0, 32); memset(&w->w.ext_null, 0, 32);
+    memset(&w->w.x, 0, 32); memset(&w->w.ext_null, 0, 32);
     memcpy(w->w.secret, identity_secret->bytes, 32);
     memcpy(w->w.limit, user_message_limit->bytes, 32);
     w->w.path.assign((const uint8_t*)path_elements->ptr, (const uint8_t*)path_elements->ptr + 32 * path_elements->len);
@@ -1267,6 +1477,9 @@ CResult_FFI_RLNPartialProof_t ffi_generate_partial_zk_proof(FFI_RLN_t* const* rl
     GUARD_BEGIN
     std::lock_guard<std::mutex> lk((*rln)->r->mu);
     std::vector<Witness> ws(1, (*partial_witness)->w);
+    ws[0].multi = (*rln)->r->multi();   // a partial witness carries no message ids: shape them for the circuit at hand
+    ws[0].mids.assign(32 * (*rln)->r->max_out(), 0);
+    ws[0].sel.assign(ws[0].multi ? (*rln)->r->max_out() : 0, 0);
     std::vector<PartialProofHost> out;
     (*rln)->r->partial_host(ws, out);
     memset(ws[0].secret, 0, 32);
@@ -1348,14 +1561,10 @@ int rlnb200_finish_batch(FFI_RLN_t* const* rln, const uint8_t* witnesses, size_t
 static CBoolResult_t verify_common(FFI_RLN_t* const* rln, const RlnProof& p, const uint8_t* x, const Vec_CFr_t* roots, bool use_tree_root) {
     GUARD_BEGIN
     std::lock_guard<std::mutex> lk((*rln)->r->mu);
-    uint8_t pub[160];  // circuit order [y, root, nullifier, x, external_nullifier] (proof.rs:863-869)
-    memcpy(pub, p.pv.y, 32);
-    memcpy(pub + 32, p.pv.root, 32);
-    memcpy(pub + 64, p.pv.nullifier, 32);
-    memcpy(pub + 96, p.pv.x, 32);
-    memcpy(pub + 128, p.pv.ext_null, 32);
+    std::vector<uint8_t> pub = public_inputs(p.pv);  // circuit order (proof.rs:863-884)
     uint8_t ok = 0;
-    (*rln)->r->verify_batch(p.proof, pub, 1, &ok);
+    if (pub.size() == 32 * (*rln)->r->n_public()) (*rln)->r->verify_batch(p.proof, pub.data(), 1, &ok);
+    else throw RlnError("Protocol error: Error producing proof: malformed verifying key");  // SynthesisError::MalformedVerifyingKey
     if (ok != 1) throw RlnError("Verification error: Invalid proof provided");
     if (use_tree_root) {
         uint8_t root[32];
@@ -1382,28 +1591,31 @@ FFI_RLNProofValues_t* ffi_rln_proof_get_values(FFI_RLNProof_t* const* rln_proof)
     v->v = (*rln_proof)->p.pv;
     return v;
 }
-uint8_t ffi_rln_proof_get_version_byte(FFI_RLNProof_t* const* rln_proof) { (void)rln_proof; return 0; }
+uint8_t ffi_rln_proof_get_version_byte(FFI_RLNProof_t* const* rln_proof) { return (*rln_proof)->p.pv.multi ? 1 : 0; }
 CResult_Vec_uint8_t ffi_rln_proof_to_bytes_le(FFI_RLNProof_t* const* rln_proof) {
-    uint8_t b[290];
-    rln_proof_to_bytes((*rln_proof)->p, b);
-    return CResult_Vec_uint8_t{mk_vec(b, 290), no_string()};
+    std::vector<uint8_t> b = rln_proof_to_bytes((*rln_proof)->p);
+    return CResult_Vec_uint8_t{mk_vec(b.data(), b.size()), no_string()};
 }
 // proof stays LE (arkworks), values big-endian (rln/src/protocol/proof.rs:430-446)
 CResult_Vec_uint8_t ffi_rln_proof_to_bytes_be(FFI_RLNProof_t* const* rln_proof) {
-    uint8_t b[290];
-    rln_proof_to_bytes((*rln_proof)->p, b);
-    for (int i = 0; i < 5; i++) std::reverse(b + 130 + 32 * i, b + 130 + 32 * (i + 1));
-    return CResult_Vec_uint8_t{mk_vec(b, 290), no_string()};
+    const ProofValues& pv = (*rln_proof)->p.pv;
+    std::vector<uint8_t> b = rln_proof_to_bytes((*rln_proof)->p);
+    // every field element and every vector length prefix is big-endian in the BE form (rln/src/utils.rs:141-230)
+    size_t o = 130;
+    auto rev = [&](size_t n) { std::reverse(b.begin() + o, b.begin() + o + n); o += n; };
+    rev(32); rev(32); rev(32);
+    if (!pv.multi) { rev(32); rev(32); }
+    else {
+        for (int v = 0; v < 2; v++) { rev(8); for (size_t i = 0; i < pv.k(); i++) rev(32); }
+        rev(8);
+    }
+    return CResult_Vec_uint8_t{mk_vec(b.data(), b.size()), no_string()};
 }
 CResult_FFI_RLNProof_t ffi_bytes_le_to_rln_proof(const Vec_uint8_t* bytes) {
     GUARD_BEGIN
     global_init();
     if (bytes->len == 0) throw RlnError(msg_read_len(1, 0));
-    if (bytes->ptr[0] != 0) {
-        char t[64];
-        snprintf(t, sizeof t, "Unknown message mode version byte: %#04x", bytes->ptr[0]);
-        throw RlnError(t);
-    }
+    if (bytes->ptr[0] > 1) throw RlnError(msg_mode(bytes->ptr[0]));
     if (bytes->len < 129) throw RlnError(msg_read_len(129, bytes->len));
     auto p = std::make_unique<FFI_RLNProof>();
     memcpy(p->p.proof, bytes->ptr + 1, 128);
@@ -1428,12 +1640,40 @@ void ffi_rln_proof_free(FFI_RLNProof_t* p) { delete p; }
 CFr_t* ffi_rln_proof_values_get_root(FFI_RLNProofValues_t* const* pv) { return mk_cfr((*pv)->v.root); }
 CFr_t* ffi_rln_proof_values_get_x(FFI_RLNProofValues_t* const* pv) { return mk_cfr((*pv)->v.x); }
 CFr_t* ffi_rln_proof_values_get_external_nullifier(FFI_RLNProofValues_t* const* pv) { return mk_cfr((*pv)->v.ext_null); }
-CResult_CFr_t ffi_rln_proof_values_get_y(FFI_RLNProofValues_t* const* pv) { return CResult_CFr_t{mk_cfr((*pv)->v.y), no_string()}; }
-CResult_CFr_t ffi_rln_proof_values_get_nullifier(FFI_RLNProofValues_t* const* pv) { return CResult_CFr_t{mk_cfr((*pv)->v.nullifier), no_string()}; }
+// variant-mismatched getters return the reference's error (rln/src/error.rs:92-99)
+static RlnString variant_err(const char* field, const char* variant) {
+    return mk_string(std::string("Field `") + field + "` does not exist on the `" + variant + "` variant");
+}
+static Vec_CFr_t mk_vec_cfr(const std::vector<uint8_t>& b) {
+    Vec_CFr_t v = ffi_vec_cfr_new(b.size() / 32);
+    memcpy(v.ptr, b.data(), b.size());
+    v.len = b.size() / 32;
+    return v;
+}
+CResult_CFr_t ffi_rln_proof_values_get_y(FFI_RLNProofValues_t* const* pv) {
+    if ((*pv)->v.multi) return CResult_CFr_t{nullptr, variant_err("y", "MultiV1")};
+    return CResult_CFr_t{mk_cfr((*pv)->v.ys.data()), no_string()};
+}
+CResult_CFr_t ffi_rln_proof_values_get_nullifier(FFI_RLNProofValues_t* const* pv) {
+    if ((*pv)->v.multi) return CResult_CFr_t{nullptr, variant_err("nullifier", "MultiV1")};
+    return CResult_CFr_t{mk_cfr((*pv)->v.nulls.data()), no_string()};
+}
+CResult_Vec_CFr_t ffi_rln_proof_values_get_ys(FFI_RLNProofValues_t* const* pv) {
+    if (!(*pv)->v.multi) return CResult_Vec_CFr_t{Vec_CFr_t{nullptr, 0, 0}, variant_err("ys", "SingleV1")};
+    return CResult_Vec_CFr_t{mk_vec_cfr((*pv)->v.ys), no_string()};
+}
+CResult_Vec_CFr_t ffi_rln_proof_values_get_nullifiers(FFI_RLNProofValues_t* const* pv) {
+    if (!(*pv)->v.multi) return CResult_Vec_CFr_t{Vec_CFr_t{nullptr, 0, 0}, variant_err("nullifiers", "SingleV1")};
+    return CResult_Vec_CFr_t{mk_vec_cfr((*pv)->v.nulls), no_string()};
+}
+CResult_Vec_uint8_t ffi_rln_proof_values_get_selector_used(FFI_RLNProofValues_t* const* pv) {
+    if (!(*pv)->v.multi) return CResult_Vec_uint8_t{Vec_uint8_t{nullptr, 0, 0}, variant_err("selector_used", "SingleV1")};
+    return CResult_Vec_uint8_t{mk_vec((*pv)->v.sel.data(), (*pv)->v.sel.size()), no_string()};
+}
+uint8_t ffi_rln_proof_values_get_version_byte(FFI_RLNProofValues_t* const* pv) { return (*pv)->v.multi ? 1 : 0; }
 Vec_uint8_t ffi_rln_proof_values_to_bytes_le(FFI_RLNProofValues_t* const* pv) {
-    uint8_t b[161];
-    proof_values_to_bytes((*pv)->v, b);
-    return mk_vec(b, 161);
+    std::vector<uint8_t> b = proof_values_to_bytes((*pv)->v);
+    return mk_vec(b.data(), b.size());
 }
 CResult_FFI_RLNProofValues_t ffi_bytes_le_to_rln_proof_values(const Vec_uint8_t* bytes) {
     GUARD_BEGIN
@@ -1545,34 +1785,12 @@ Vec_CFr_t ffi_key_gen(void) {  // keygen (rln/src/protocol/keygen.rs:20-30): sec
 int rlnb200_prove_batch(FFI_RLN_t* const* rln, const uint8_t* witnesses, size_t n, const uint8_t* rs, uint8_t* proofs_out, RlnString* err) {
     INT_OP(
         std::lock_guard<std::mutex> lk((*rln)->r->mu);
-        const size_t d = (*rln)->r->depth(), rec = 1 + 32 * (5 + d) + 16 + d;
-        std::vector<Witness> ws(n);
-        for (size_t i = 0; i < n; i++) {
-            size_t used = witness_from_bytes(witnesses + rec * i, rec, ws[i]);
-            if (used != rec) throw RlnError(msg_read_len(used, rec));
-        }
+        std::vector<Witness> ws = parse_records(*(*rln)->r, witnesses, n, false);
         std::vector<RlnProof> out;
         (*rln)->r->prove_host(ws, rs, out);
         for (auto& w : ws) memset(w.secret, 0, 32);
-        for (size_t i = 0; i < n; i++) rln_proof_to_bytes(out[i], proofs_out + 290 * i);)
-}
-static std::vector<Witness> parse_records(Rln& r, const uint8_t* witnesses, size_t n, bool partial_phase) {
-    const size_t d = r.depth(), rec = 1 + 32 * (5 + d) + 16 + d;
-    std::vector<Witness> ws(n);
-    for (size_t i = 0; i < n; i++) {
-        if (partial_phase) {  // message_id / x / external_nullifier are not looked at: skip the range checks that involve them
-            const uint8_t* b = witnesses + rec * i;
-            memcpy(ws[i].secret, b + 1, 32); memcpy(ws[i].limit, b + 33, 32);
-            ws[i].path.assign(b + 105, b + 105 + 32 * d);
-            ws[i].index.assign(b + 113 + 32 * d, b + 113 + 33 * d);
-            memset(ws[i].message_id, 0, 32); memset(ws[i].x, 0, 32); memset(ws[i].ext_null, 0, 32);
-            if (!fr_is_canonical(ws[i].secret) || !fr_is_canonical(ws[i].limit)) throw RlnError("Non-canonical field element: value is not in [0, r-1]");
-        } else {
-            size_t used = witness_from_bytes(witnesses + rec * i, rec, ws[i]);
-            if (used != rec) throw RlnError(msg_read_len(used, rec));
-        }
-    }
-    return ws;
+        const size_t orec = proof_record_len(*(*rln)->r);
+        for (size_t i = 0; i < n; i++) { std::vector<uint8_t> b = rln_proof_to_bytes(out[i]); memcpy(proofs_out + orec * i, b.data(), orec); })
 }
 int rlnb200_partial_batch(FFI_RLN_t* const* rln, const uint8_t* witnesses, size_t n, uint8_t* partial_out, RlnString* err) {
     INT_OP(
@@ -1593,18 +1811,22 @@ int rlnb200_finish_batch(FFI_RLN_t* const* rln, const uint8_t* witnesses, size_t
         std::vector<RlnProof> out;
         (*rln)->r->prove_host(ws, rs, out, pp.data());
         for (auto& w : ws) memset(w.secret, 0, 32);
-        for (size_t i = 0; i < n; i++) rln_proof_to_bytes(out[i], proofs_out + 290 * i);)
+        const size_t orec = proof_record_len(*(*rln)->r);
+        for (size_t i = 0; i < n; i++) { std::vector<uint8_t> b = rln_proof_to_bytes(out[i]); memcpy(proofs_out + orec * i, b.data(), orec); })
 }
 int rlnb200_verify_batch(FFI_RLN_t* const* rln, const uint8_t* proofs, size_t n, uint8_t* ok_out, RlnString* err) {
     INT_OP(
         std::lock_guard<std::mutex> lk((*rln)->r->mu);
-        std::vector<uint8_t> p(128 * n), pub(160 * n);
+        const size_t orec = proof_record_len(*(*rln)->r), np = (*rln)->r->n_public();
+        std::vector<uint8_t> p(128 * n), pub(32 * np * n);
         for (size_t i = 0; i < n; i++) {
-            const uint8_t* b = proofs + 290 * i;
+            const uint8_t* b = proofs + orec * i;
             memcpy(p.data() + 128 * i, b + 1, 128);
-            const uint8_t* v = b + 130;  // root | ext_null | x | y | nullifier
-            uint8_t* o = pub.data() + 160 * i;
-            memcpy(o, v + 96, 32); memcpy(o + 32, v, 32); memcpy(o + 64, v + 128, 32); memcpy(o + 96, v + 64, 32); memcpy(o + 128, v + 32, 32);
+            ProofValues pv;
+            proof_values_from_bytes(b + 129, orec - 129, pv);
+            std::vector<uint8_t> q = public_inputs(pv);
+            if (q.size() != 32 * np) throw RlnError("Protocol error: proof record does not match the circuit's message mode");
+            memcpy(pub.data() + 32 * np * i, q.data(), q.size());
         }
         (*rln)->r->verify_batch(p.data(), pub.data(), n, ok_out);)
 }
@@ -1669,6 +1891,8 @@ int rlnb200_debug_witness_and_h(FFI_RLN_t* const* rln, const uint8_t* witness_le
     INT_OP(std::lock_guard<std::mutex> lk((*rln)->r->mu); Witness w; witness_from_bytes(witness_le, len, w); (*rln)->r->debug_w_h(w, w_out, h_out);)
 }
 size_t rlnb200_num_wires(FFI_RLN_t* const* rln) { return (*rln)->r->n_wires(); }
+size_t rlnb200_witness_record_len(FFI_RLN_t* const* rln) { return witness_record_len(*(*rln)->r); }
+size_t rlnb200_proof_record_len(FFI_RLN_t* const* rln) { return proof_record_len(*(*rln)->r); }
 size_t rlnb200_domain_size(FFI_RLN_t* const* rln) { return (*rln)->r->domain(); }
 
 RlnB200Msm_t* rlnb200_msm_new(size_t max_n, RlnString* err) {

@@ -19,6 +19,10 @@ class Vec_uint8(Structure):
 RlnString = Vec_uint8
 
 
+class Vec_bool(Structure):
+    _fields_ = [("ptr", POINTER(c_bool)), ("len", c_size_t), ("cap", c_size_t)]
+
+
 class Vec_size(Structure):
     _fields_ = [("ptr", POINTER(c_size_t)), ("len", c_size_t), ("cap", c_size_t)]
 
@@ -47,6 +51,7 @@ CResult_ptr = _cresult("CResult_ptr", c_void_p)          # any CResult<Box<T>, S
 CResult_MerkleProof = _cresult("CResult_MerkleProof", POINTER(FFI_MerkleProof))
 CResult_CFr = _cresult("CResult_CFr", POINTER(CFr))
 CResult_Vec_uint8 = _cresult("CResult_Vec_uint8", Vec_uint8)
+CResult_Vec_CFr = _cresult("CResult_Vec_CFr", Vec_CFr)
 
 _lib = None
 
@@ -80,6 +85,8 @@ def lib():
         "ffi_get_merkle_proof": (CResult_MerkleProof, [pp, c_size_t]),
         "ffi_merkle_proof_free": (None, [POINTER(FFI_MerkleProof)]),
         "ffi_rln_witness_input_new_single": (CResult_ptr, [POINTER(CFr)] * 3 + [POINTER(Vec_CFr), POINTER(Vec_uint8), POINTER(CFr), POINTER(CFr)]),
+        "ffi_rln_witness_input_new_multi": (CResult_ptr, [POINTER(CFr), POINTER(CFr), POINTER(Vec_CFr), POINTER(Vec_CFr), POINTER(Vec_uint8),
+                                                           POINTER(CFr), POINTER(CFr), POINTER(Vec_bool)]),
         "ffi_rln_witness_to_bytes_le": (CResult_Vec_uint8, [pp]),
         "ffi_bytes_le_to_rln_witness": (CResult_ptr, [POINTER(Vec_uint8)]),
         "ffi_rln_witness_input_free": (None, [c_void_p]),
@@ -97,6 +104,10 @@ def lib():
         "ffi_rln_proof_values_get_external_nullifier": (POINTER(CFr), [pp]),
         "ffi_rln_proof_values_get_y": (CResult_CFr, [pp]),
         "ffi_rln_proof_values_get_nullifier": (CResult_CFr, [pp]),
+        "ffi_rln_proof_values_get_ys": (CResult_Vec_CFr, [pp]),
+        "ffi_rln_proof_values_get_nullifiers": (CResult_Vec_CFr, [pp]),
+        "ffi_rln_proof_values_get_selector_used": (CResult_Vec_uint8, [pp]),
+        "ffi_rln_proof_values_get_version_byte": (c_uint8, [pp]),
         "ffi_rln_proof_values_to_bytes_le": (Vec_uint8, [pp]),
         "ffi_bytes_le_to_rln_proof_values": (CResult_ptr, [POINTER(Vec_uint8)]),
         "ffi_rln_proof_values_free": (None, [c_void_p]),
@@ -132,6 +143,9 @@ def lib():
         "rlnb200_bytes_le_to_rln_partial_proof": (CResult_ptr, [pp, POINTER(Vec_uint8)]),
         "rlnb200_partial_batch": (c_int, [pp, c_void_p, c_size_t, c_void_p, POINTER(RlnString)]),
         "rlnb200_finish_batch": (c_int, [pp, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, POINTER(RlnString)]),
+        "rlnb200_rln_new_multi": (CResult_ptr, [c_size_t, c_size_t]),
+        "rlnb200_witness_record_len": (c_size_t, [pp]),
+        "rlnb200_proof_record_len": (c_size_t, [pp]),
         "rlnb200_generate_rln_proof_with_rs": (CResult_ptr, [pp, pp, POINTER(CFr), POINTER(CFr)]),
         "rlnb200_prove_batch": (c_int, [pp, c_void_p, c_size_t, c_void_p, c_void_p, POINTER(RlnString)]),
         "rlnb200_verify_batch": (c_int, [pp, c_void_p, c_size_t, c_void_p, POINTER(RlnString)]),

@@ -11,7 +11,7 @@ import ctypes
 from ctypes import POINTER, byref, c_uint8, c_uint32, c_void_p, cast
 
 from . import ffi
-from .ffi import CFr, Vec_CFr, Vec_size, Vec_uint8
+from .ffi import CFr, Vec_bool, Vec_CFr, Vec_size, Vec_uint8
 
 R = 21888242871839275222246405745257275088548364400416034343698204186575808495617
 DEFAULT_TREE_DEPTH = 20  # rln/src/circuit/mod.rs:81
@@ -135,6 +135,17 @@ class RLNWitnessInput:
         return cls(_check_ptr(res))
 
     @classmethod
+    def new_multi(cls, identity_secret, user_message_limit, message_ids, path_elements, identity_path_index, x, external_nullifier,
+                  selector_used):
+        """witness.rs:115-176 (multi message-id mode)"""
+        sel = (ctypes.c_bool * max(len(selector_used), 1))(*[bool(v) for v in selector_used])
+        vb = Vec_bool(cast(sel, POINTER(ctypes.c_bool)), len(selector_used), len(selector_used))
+        res = ffi.lib().ffi_rln_witness_input_new_multi(
+            byref(_cfr(identity_secret)), byref(_cfr(user_message_limit)), byref(_vec_cfr(message_ids)), byref(_vec_cfr(path_elements)),
+            byref(_vec_u8(bytes(identity_path_index))), byref(_cfr(x)), byref(_cfr(external_nullifier)), byref(vb))
+        return cls(_check_ptr(res))
+
+    @classmethod
     def from_bytes_le(cls, data):
         return cls(_check_ptr(ffi.lib().ffi_bytes_le_to_rln_witness(byref(_vec_u8(data)))))
 
@@ -189,13 +200,16 @@ class RLNPartialProof:
 
 
 class RLNProofValues:
-    """rln/src/protocol/proof.rs:100-190"""
+    """rln/src/protocol/proof.rs:100-190 — SingleV1 (y, nullifier) or MultiV1 (ys, nullifiers, selector_used)"""
 
-    def __init__(self, root, external_nullifier, x, y, nullifier):
+    def __init__(self, root, external_nullifier, x, y=None, nullifier=None, ys=None, nullifiers=None, selector_used=None):
         self.root, self.external_nullifier, self.x, self.y, self.nullifier = root, external_nullifier, x, y, nullifier
+        self.ys, self.nullifiers, self.selector_used = ys, nullifiers, selector_used
 
     def public_inputs(self):
-        """circuit order used by the verifier (proof.rs:863-869)"""
+        """circuit order used by the verifier (proof.rs:863-884)"""
+        if self.ys is not None:
+            return list(self.ys) + [self.root] + list(self.nullifiers) + [self.x, self.external_nullifier] + [int(v) for v in self.selector_used]
         return [self.y, self.root, self.nullifier, self.x, self.external_nullifier]
 
 
@@ -233,11 +247,21 @@ class RLNProof:
             root = _take_cfr(L.ffi_rln_proof_values_get_root(byref(pv)))
             x = _take_cfr(L.ffi_rln_proof_values_get_x(byref(pv)))
             en = _take_cfr(L.ffi_rln_proof_values_get_external_nullifier(byref(pv)))
-            y = _take_cfr(L.ffi_rln_proof_values_get_y(byref(pv)).ok)
-            nul = _take_cfr(L.ffi_rln_proof_values_get_nullifier(byref(pv)).ok)
+            if L.ffi_rln_proof_values_get_version_byte(byref(pv)) == 0:
+                y = _take_cfr(L.ffi_rln_proof_values_get_y(byref(pv)).ok)
+                nul = _take_cfr(L.ffi_rln_proof_values_get_nullifier(byref(pv)).ok)
+                return RLNProofValues(root, en, x, y, nul)
+
+            def vec(res):
+                out = [_cfr_int(res.ok.ptr[i]) for i in range(res.ok.len)]
+                L.ffi_vec_cfr_free(res.ok)
+                return out
+            ys = vec(L.ffi_rln_proof_values_get_ys(byref(pv)))
+            nulls = vec(L.ffi_rln_proof_values_get_nullifiers(byref(pv)))
+            sel = [bool(b) for b in _take_vec_u8(L.ffi_rln_proof_values_get_selector_used(byref(pv)).ok)]
+            return RLNProofValues(root, en, x, ys=ys, nullifiers=nulls, selector_used=sel)
         finally:
             L.ffi_rln_proof_values_free(pv)
-        return RLNProofValues(root, en, x, y, nul)
 
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -256,6 +280,20 @@ class RLN:
     def new(cls, tree_depth=DEFAULT_TREE_DEPTH, config_path=""):
         """public.rs:110-128 via ffi_rln_new (bundled zkey/graph of that depth)"""
         return cls(_check_ptr(ffi.lib().ffi_rln_new(tree_depth, config_path.encode())))
+
+    @classmethod
+    def new_multi(cls, tree_depth=DEFAULT_TREE_DEPTH, max_out=4):
+        """the bundled multi message-id circuit (rln/src/circuit/mod.rs:36-42)"""
+        return cls(_check_ptr(ffi.lib().rlnb200_rln_new_multi(tree_depth, max_out)))
+
+    def max_out(self):
+        return ffi.lib().ffi_rln_get_max_out(byref(self._h))
+
+    def witness_record_len(self):
+        return ffi.lib().rlnb200_witness_record_len(byref(self._h))
+
+    def proof_record_len(self):
+        return ffi.lib().rlnb200_proof_record_len(byref(self._h))
 
     @classmethod
     def new_with_params(cls, tree_depth, zkey: bytes, graph: bytes, config_path=""):
@@ -368,7 +406,7 @@ class RLN:
         return out.raw
 
     def finish_batch(self, witnesses_le: bytes, n: int, partial: bytes, rs: bytes = None) -> bytes:
-        out = ctypes.create_string_buffer(290 * n)
+        out = ctypes.create_string_buffer(self.proof_record_len() * n)
         err = ffi.RlnString()
         _check_int(ffi.lib().rlnb200_finish_batch(byref(self._h), witnesses_le, n, partial, rs, out, byref(err)), err)
         return out.raw
@@ -382,8 +420,8 @@ class RLN:
         return _check_bool(ffi.lib().ffi_verify_with_roots(byref(self._h), byref(proof._h), byref(_vec_cfr(roots)), byref(_cfr(x))))
 
     def prove_batch(self, witnesses_le: bytes, n: int, rs: bytes = None) -> bytes:
-        """n witness records (rln_witness_to_bytes_le) → n × 290-byte rln_proof_to_bytes_le records"""
-        out = ctypes.create_string_buffer(290 * n)
+        """n witness records (rln_witness_to_bytes_le) → n rln_proof_to_bytes_le records (290 bytes each in single mode)"""
+        out = ctypes.create_string_buffer(self.proof_record_len() * n)
         err = ffi.RlnString()
         _check_int(ffi.lib().rlnb200_prove_batch(byref(self._h), witnesses_le, n, rs, out, byref(err)), err)
         return out.raw
