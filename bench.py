@@ -367,6 +367,22 @@ def run_gpu(args, rank, local_rank, world):
                 "steps": e2e_steps, "api": "rlnb200_prove_batch (host witness records → host rln_proof bytes)"},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "stage_ms": stage,
     }
+    # ---- single proof through the reference's own entry point (BASELINE.json configs[0]: ffi_generate_rln_proof)
+    try:
+        wit = z.RLNWitnessInput.from_bytes_le(recs[:rec_len])
+        rln.generate_rln_proof(wit)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            p1 = rln.generate_rln_proof(wit)
+        lat = (time.perf_counter() - t0) / 5
+        assert rln.verify_with_roots(p1, p1.values.x, []) is True
+        t0 = time.perf_counter()
+        for _ in range(5):
+            rln.verify_with_roots(p1, p1.values.x, [])
+        line["single_proof"] = {"generate_ms": 1e3 * lat, "verify_ms": 1e3 * (time.perf_counter() - t0) / 5,
+                                "api": "ffi_generate_rln_proof / ffi_verify_with_roots, host in, host out"}
+    except Exception as e:
+        line["single_proof"] = {"error": str(e)}
     # ---- two-phase proving (rln/README.md:356-375): partial proofs computed once, finish per message
     try:
         d_pa = torch.empty(n * 320, dtype=torch.uint8, device=dev)
