@@ -78,6 +78,29 @@ int emu_pairing_check(const uint8_t* g1, const uint8_t* g2, int n) {
     for (int i = 0; i < n; i++) f = f * miller_loop(&pt, ld_g2(g2 + 128 * i), ld_g1(g1 + 64 * i));
     return final_exponentiation(&pt, f) == Fq12::one() ? 1 : 0;
 }
+// 1 if the addition-chain final exponentiation and the generic one agree on "is the result one" for Π e(P_i,Q_i),
+// and additionally the chain result is multiplicative: FE(f·g) == FE(f)·FE(g)
+int emu_final_exp_consistency(const uint8_t* g1, const uint8_t* g2, int n) {
+    static PairingTables pt; static bool init = false;
+    if (!init) { pairing_tables_init(pt); init = true; }
+    Fq12 f = Fq12::one(), g = Fq12::one();
+    for (int i = 0; i < n; i++) {
+        Fq12 m = miller_loop(&pt, ld_g2(g2 + 128 * i), ld_g1(g1 + 64 * i));
+        f = f * m;
+        if (i == 0) g = m;
+    }
+    bool one_chain = final_exponentiation(&pt, f) == Fq12::one();
+    bool one_generic = final_exponentiation_generic(&pt, f) == Fq12::one();
+    Fq12 a = final_exponentiation(&pt, f * g), b = final_exponentiation(&pt, f) * final_exponentiation(&pt, g);
+    // fixed-point Miller loop (precomputed lines) must reproduce the generic one
+    static FixedLines fl;
+    precompute_lines(&pt, ld_g2(g2), fl);
+    bool fixed_ok = miller_loop_fixed(fl.lam, fl.c, ld_g1(g1)) == g;
+    if (!fixed_ok) return 0;
+    // frobenius1 applied twice must equal frobenius2
+    bool frob_ok = frobenius1(&pt, frobenius1(&pt, g)) == frobenius2(&pt, g);
+    return (one_chain == one_generic ? 1 : 0) | (a == b ? 2 : 0) | (frob_ok ? 4 : 0) | (one_chain ? 8 : 0);
+}
 // witness-graph VM: one op on canonical values
 int emu_vm_duo(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     Fr r;

@@ -110,6 +110,15 @@ def test_pairing(emu):
     assert emu.emu_pairing_check(_g1b(P1) + _g1b(P1), _g2b(Q1) + _g2b(F.G2_GEN), 2) == 0
 
 
+def test_final_exponentiation_chain(emu):
+    """the BN addition-chain hard part agrees with plain exponentiation by (q⁴−q²+1)/r on the verifier's predicate"""
+    a, b = 1234567, 7654321
+    P1, Q1 = F.pt_mul(F.OPS1, F.G1_GEN, a), F.pt_mul(F.OPS2, F.G2_GEN, b)
+    P2 = F.pt_neg(F.OPS1, F.pt_mul(F.OPS1, F.G1_GEN, a * b))
+    assert emu.emu_final_exp_consistency(_g1b(P1) + _g1b(P2), _g2b(Q1) + _g2b(F.G2_GEN), 2) == 15   # product is one
+    assert emu.emu_final_exp_consistency(_g1b(P1) + _g1b(P1), _g2b(Q1) + _g2b(F.G2_GEN), 2) == 7    # product is not one
+
+
 def test_vm_ops(emu):
     rnd = random.Random(7)
     for op in range(20):

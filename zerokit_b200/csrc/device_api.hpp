@@ -143,6 +143,10 @@ struct VerifyKeyDev {
     G2Affine beta_g2, gamma_g2, delta_g2;
     const G1Affine* gamma_abc;  // device pointer, n_public + 1 entries
     u32 n_public;
+    // prepare_verifying_key (ark-groth16): everything that depends only on the key is computed once
+    const Fq12* ml_alpha_beta;            // device pointer: Miller value of (α₁, β₂)
+    const Fq2 *gamma_lam, *gamma_c;       // device pointers: line coefficients of γ₂ (MILLER_STEPS each)
+    const Fq2 *delta_lam, *delta_c;       // … and of δ₂
 };
 void pairing_upload_tables(const PairingTables& t);
 // proofs: n × 128 B ark-compressed; publics: n × n_public × 32 canonical bytes (circuit order);

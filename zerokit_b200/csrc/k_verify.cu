@@ -158,10 +158,10 @@ __global__ void __launch_bounds__(32) k_verify(VerifyKeyDev vk, const uint8_t* _
         while (Fr::raw_cmp(x, m) >= 0) Fr::raw_sub(x, x, m);
         vkx.add(G1XYZZ::from_affine(vk.gamma_abc[i + 1]).mul(x));
     }
-    Fq12 f = miller_loop(&c_pair, Bp, A.neg());
-    f = f * miller_loop(&c_pair, vk.beta_g2, vk.alpha_g1);
-    f = f * miller_loop(&c_pair, vk.gamma_g2, vkx.to_affine());
-    f = f * miller_loop(&c_pair, vk.delta_g2, C);
+    Fq12 f = miller_loop(&c_pair, Bp, A.neg());   // the only pairing whose G2 argument varies
+    f = f * (*vk.ml_alpha_beta);
+    f = f * miller_loop_fixed(vk.gamma_lam, vk.gamma_c, vkx.to_affine());
+    f = f * miller_loop_fixed(vk.delta_lam, vk.delta_c, C);
     ok[j] = final_exponentiation(&c_pair, f) == Fq12::one() ? 1 : 0;
 }
 

@@ -18,6 +18,8 @@ inline void pairing_tables_init(PairingTables& pt) {
     }
     pt.gamma2 = t.sqr();
     pt.gamma3 = pt.gamma2 * t;
+    pt.frob1[0] = Fq2::one();
+    for (int k = 1; k < 6; k++) pt.frob1[k] = pt.frob1[k - 1] * t;
     Fq2 n = t * t.conj();
     pt.frob2[0] = Fq::one();
     for (int k = 1; k < 6; k++) pt.frob2[k] = pt.frob2[k - 1] * n.a;

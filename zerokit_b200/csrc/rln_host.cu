@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -416,7 +417,7 @@ class Rln {
     DevMem d_prog_, d_consts_, d_signals_, d_a_ptr_, d_a_col_, d_a_val_, d_b_ptr_, d_b_col_, d_b_val_, d_tw_inv_, d_tw_fwd_, d_coset_;
     CircuitDev circ_{};
     // fixed-base tables
-    DevMem d_tab_[5], d_rows_[5], d_gamma_abc_, d_delta1_tab_, d_delta2_tab_;
+    DevMem d_tab_[5], d_rows_[5], d_gamma_abc_, d_delta1_tab_, d_delta2_tab_, d_vk_pre_;
     FixedMsmPlan plan_{};
     ProverKeyDev pk_{};
     VerifyKeyDev vk_{};
@@ -761,6 +762,22 @@ void Rln::build_tables() {
         upload_points_g1(zk_.gamma_abc, all, d_gamma_abc_);
         vk_.gamma_abc = d_gamma_abc_.as<G1Affine>();
         vk_.n_public = (u32)all.size() - 1;
+    }
+    {   // prepare_verifying_key: key-only parts of the pairing check (one-off, host portable arithmetic)
+        PairingTables pr;
+        pairing_tables_init(pr);
+        struct Pre { Fq12 ml; FixedLines g, d; };
+        auto pre = std::make_unique<Pre>();
+        pre->ml = miller_loop(&pr, vk_.beta_g2, vk_.alpha_g1);
+        precompute_lines(&pr, vk_.gamma_g2, pre->g);
+        precompute_lines(&pr, vk_.delta_g2, pre->d);
+        d_vk_pre_.upload(pre.get(), sizeof(Pre));
+        const uint8_t* base = d_vk_pre_.as<uint8_t>();
+        vk_.ml_alpha_beta = reinterpret_cast<const Fq12*>(base + offsetof(Pre, ml));
+        vk_.gamma_lam = reinterpret_cast<const Fq2*>(base + offsetof(Pre, g) + offsetof(FixedLines, lam));
+        vk_.gamma_c = reinterpret_cast<const Fq2*>(base + offsetof(Pre, g) + offsetof(FixedLines, c));
+        vk_.delta_lam = reinterpret_cast<const Fq2*>(base + offsetof(Pre, d) + offsetof(FixedLines, lam));
+        vk_.delta_c = reinterpret_cast<const Fq2*>(base + offsetof(Pre, d) + offsetof(FixedLines, c));
     }
 }
 

@@ -60,8 +60,9 @@ struct Fq12 {
 struct PairingTables {
     Fq2 gamma2;    // ξ^((q−1)/3)
     Fq2 gamma3;    // ξ^((q−1)/2)
+    Fq2 frob1[6];  // ξ^(k(q−1)/6), k = 0..5: coefficients of the q-power Frobenius on Fq12
     Fq frob2[6];   // ξ^(k(q²−1)/6), k = 0..5 (lie in Fq)
-    u32 hard[24];  // (q⁴ − q² + 1)/r, little-endian words (761 bits)
+    u32 hard[24];  // (q⁴ − q² + 1)/r, little-endian words (761 bits) — reference value for the generic path (tests)
 };
 
 HD Fq12 line_eval(const Fq2& lam, const G2Affine& R, const G1Affine& P) {
@@ -107,6 +108,56 @@ HDN Fq12 miller_loop(const PairingTables* pt, const G2Affine& Qp, const G1Affine
     return f;
 }
 
+// Line coefficients of the Miller loop for a FIXED G2 point (γ₂, δ₂ of the verifying key): per step the slope λ and
+// c = y_R − λ·x_R, so evaluating at P needs no point arithmetic and no inversion.
+constexpr int MILLER_STEPS = 64 + 36 + 2;  // 64 doublings, popcount(ATE_LOW) = 36 additions, 2 Frobenius corrections
+struct FixedLines {
+    Fq2 lam[MILLER_STEPS];
+    Fq2 c[MILLER_STEPS];
+};
+HDN void precompute_lines(const PairingTables* pt, const G2Affine& Qp, FixedLines& out) {
+    const u64 ATE_LOW = 0x9d797039be763ba8ULL;
+    G2Affine R = Qp;
+    int n = 0;
+    auto step = [&](const Fq2& lam, const G2Affine* S) {
+        out.lam[n] = lam;
+        out.c[n] = R.y - lam * R.x;
+        n++;
+        Fq2 x3 = S ? lam.sqr() - R.x - S->x : lam.sqr() - R.x.dbl();
+        R.y = lam * (R.x - x3) - R.y;
+        R.x = x3;
+    };
+    for (int i = 63; i >= 0; i--) {
+        Fq2 xx = R.x.sqr();
+        step((xx.dbl() + xx) * R.y.dbl().inv(), nullptr);
+        if ((ATE_LOW >> i) & 1) step((Qp.y - R.y) * (Qp.x - R.x).inv(), &Qp);
+    }
+    G2Affine Q1 = {Qp.x.conj() * pt->gamma2, Qp.y.conj() * pt->gamma3};
+    G2Affine Q2 = {Q1.x.conj() * pt->gamma2, (Q1.y.conj() * pt->gamma3).neg()};
+    step((Q1.y - R.y) * (Q1.x - R.x).inv(), &Q1);
+    step((Q2.y - R.y) * (Q2.x - R.x).inv(), &Q2);
+}
+HDN Fq12 miller_loop_fixed(const Fq2* __restrict__ lam, const Fq2* __restrict__ cc, const G1Affine& P) {
+    if (P.is_inf()) return Fq12::one();
+    const u64 ATE_LOW = 0x9d797039be763ba8ULL;
+    Fq12 f = Fq12::one();
+    int n = 0;
+    const Fq ny = P.y.neg();
+    auto line = [&](int k) {
+        Fq12 l;
+        l.c0 = {Fq2{ny, Fq::zero()}, Fq2::zero(), Fq2::zero()};
+        l.c1 = {lam[k].scale(P.x), cc[k], Fq2::zero()};
+        return l;
+    };
+    for (int i = 63; i >= 0; i--) {
+        f = f.sqr() * line(n++);
+        if ((ATE_LOW >> i) & 1) f = f * line(n++);
+    }
+    f = f * line(n++);
+    f = f * line(n++);
+    return f;
+}
+
 HDN Fq12 frobenius2(const PairingTables* pt, const Fq12& f) {
     Fq12 r;  // coefficient of w^k is scaled by frob2[k]; c0 = (w⁰,w²,w⁴), c1 = (w¹,w³,w⁵)
     r.c0 = {f.c0.c0, f.c0.c1.scale(pt->frob2[2]), f.c0.c2.scale(pt->frob2[4])};
@@ -114,7 +165,25 @@ HDN Fq12 frobenius2(const PairingTables* pt, const Fq12& f) {
     return r;
 }
 
-HDN Fq12 final_exponentiation(const PairingTables* pt, const Fq12& f) {
+// q-power Frobenius: (Σ a_k w^k)^q = Σ conj(a_k)·ξ^{k(q−1)/6}·w^k
+HDN Fq12 frobenius1(const PairingTables* pt, const Fq12& f) {
+    Fq12 r;
+    r.c0 = {f.c0.c0.conj(), f.c0.c1.conj() * pt->frob1[2], f.c0.c2.conj() * pt->frob1[4]};
+    r.c1 = {f.c1.c0.conj() * pt->frob1[1], f.c1.c1.conj() * pt->frob1[3], f.c1.c2.conj() * pt->frob1[5]};
+    return r;
+}
+// f^u for the BN parameter u = 4965661367192848881 (63 bits)
+HDN Fq12 pow_u(const Fq12& f) {
+    const u64 U = 4965661367192848881ULL;
+    Fq12 r = f;
+    for (int i = 61; i >= 0; i--) {  // bit 62 is the leading one
+        r = r.sqr();
+        if ((U >> i) & 1) r = r * f;
+    }
+    return r;
+}
+// generic hard part (plain exponentiation by (q⁴−q²+1)/r); kept as the cross-check of the addition chain below
+HDN Fq12 final_exponentiation_generic(const PairingTables* pt, const Fq12& f) {
     Fq12 t = f.conj() * f.inv();      // ^(q⁶−1)
     t = frobenius2(pt, t) * t;        // ^(q²+1)
     Fq12 r = Fq12::one();             // ^((q⁴−q²+1)/r)
@@ -123,6 +192,29 @@ HDN Fq12 final_exponentiation(const PairingTables* pt, const Fq12& f) {
         if ((pt->hard[i >> 5] >> (i & 31)) & 1) r = r * t;
     }
     return r;
+}
+// Final exponentiation with the BN hard-part addition chain (Scott et al., "On the final exponentiation for
+// calculating pairings on ordinary elliptic curves"): three powers of u plus Frobenius maps.  After the easy part
+// the element is unitary, so inversion is conjugation.  The result is f^{(q¹²−1)/r·c} for a fixed c coprime to r —
+// equal to 1 exactly when the generic exponentiation gives 1, which is all a verifier needs.
+HDN Fq12 final_exponentiation(const PairingTables* pt, const Fq12& f) {
+    Fq12 t1 = f.conj() * f.inv();       // ^(q⁶−1)
+    t1 = frobenius2(pt, t1) * t1;       // ^(q²+1)
+    Fq12 fp = frobenius1(pt, t1), fp2 = frobenius2(pt, t1), fp3 = frobenius1(pt, fp2);
+    Fq12 fu = pow_u(t1), fu2 = pow_u(fu), fu3 = pow_u(fu2);
+    Fq12 y3 = frobenius1(pt, fu), fu2p = frobenius1(pt, fu2), fu3p = frobenius1(pt, fu3), y2 = frobenius2(pt, fu2);
+    Fq12 y0 = fp * fp2 * fp3;
+    Fq12 y1 = t1.conj(), y5 = fu2.conj();
+    y3 = y3.conj();
+    Fq12 y4 = (fu * fu2p).conj();
+    Fq12 y6 = (fu3 * fu3p).conj();
+    Fq12 t0 = y6.sqr() * y4 * y5;
+    Fq12 t2 = y3 * y5 * t0;
+    t0 = t0 * y2;
+    t2 = (t2.sqr() * t0).sqr();
+    t0 = t2 * y1;
+    t2 = t2 * y0;
+    return t0.sqr() * t2;
 }
 
 }  // namespace zk
