@@ -185,6 +185,69 @@ def test_msm_fixture_and_oracle(z, goldens, oracle):
     assert oracle.msm_g1(ra + rb, fr_bytes([1, 1]), 2) == rab
 
 
+@pytest.mark.parametrize("log2n", [16, 18])
+def test_msm_baseline_sizes_vs_oracle(z, oracle, log2n):
+    """BASELINE.json configs[1]: random bases k_i·G (seed 1), uniform scalars (seed 2); affine result == oracle Pippenger"""
+    import numpy as np
+    n = 1 << log2n
+    rng = np.random.default_rng(1)
+    ks = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    ks[:, 31] &= 0x1f
+    bases = oracle.g1_mul_gen(ks.tobytes(), n, oracle.threads())
+    sc = np.random.default_rng(2).integers(0, 256, size=(n, 32), dtype=np.uint8)
+    sc[:, 31] &= 0x1f
+    m = z.G1Msm(n)
+    assert m.msm(bases, sc.tobytes(), n) == oracle.msm_g1(bases, sc.tobytes(), n, oracle.threads())
+
+
+def test_msm_large_linear_split(z, oracle):
+    """2^20 terms: too slow to re-do on one CPU core, so check Σ over the whole == Σ over the two halves (oracle adds the halves)"""
+    import numpy as np
+    import torch
+    n = 1 << 20
+    m = z.G1Msm(n)
+    dev = torch.device("cuda")
+    rng = np.random.default_rng(5)
+    ks = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    ks[:, 31] &= 0x1f
+    sc = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    sc[:, 31] &= 0x1f
+    d_k, d_s = torch.from_numpy(ks).to(dev), torch.from_numpy(sc).to(dev)
+    d_b = torch.empty(n * 64, dtype=torch.uint8, device=dev)
+    d_o = torch.empty(3 * 64, dtype=torch.uint8, device=dev)
+    m.gen_bases(d_k.data_ptr(), n, d_b.data_ptr())
+    h = n // 2
+    m.msm_device(d_b.data_ptr(), d_s.data_ptr(), n, d_o.data_ptr())
+    m.msm_device(d_b.data_ptr(), d_s.data_ptr(), h, d_o.data_ptr() + 64)
+    m.msm_device(d_b.data_ptr() + 64 * h, d_s.data_ptr() + 32 * h, h, d_o.data_ptr() + 128)
+    torch.cuda.synchronize()
+    o = d_o.cpu().numpy().tobytes()
+    assert oracle.msm_g1(o[64:192], fr_bytes([1, 1]), 2) == o[:64]
+    # the device base generator agrees with the oracle's k·G on a sample
+    sample = oracle.g1_mul_gen(ks[:4].tobytes(), 4)
+    m2 = z.G1Msm(4)
+    assert m2.msm(sample, fr_bytes([1, 0, 0, 0]), 4) == sample[:64]
+
+
+def test_empty_and_full_capacity(z, rln10, oracle):
+    """empty batches are no-ops; a completely full depth-10 tree equals the oracle's; indices at the capacity edge"""
+    assert rln10.prove_batch(b"", 0, b"") == b""
+    assert rln10.verify_batch(b"", 0) == []
+    rln10.set_tree(10)
+    fs = fr_stream(44)
+    leaves = [next(fs) for _ in range(1024)]
+    rln10.init_tree_with_leaves(leaves)
+    nodes = oracle.merkle_build(10, fr_bytes(leaves), 0, 1024)
+    assert rln10.get_root() == int.from_bytes(nodes[:32], "little") and rln10.leaves_set() == 1024
+    e, b = rln10.get_merkle_proof(1023)
+    assert (e, b) == oracle.merkle_proof_from_nodes(nodes, 10, 1023)
+    with pytest.raises(z.RLNError, match="Leaf index out of bounds"):
+        rln10.set_next_leaf(5)   # tree is full
+    with pytest.raises(z.RLNError, match="Leaf index out of bounds"):
+        rln10.get_merkle_proof(1024)
+    rln10.set_tree(10)
+
+
 # ------------------------------------------------------------------------------- witness / QAP / proofs
 @pytest.mark.parametrize("depth,key", [(10, "kat_proof_d10"), (20, "kat_proof_d20"), (20, "kat_proof_d20_r0")])
 def test_known_answer_proofs(z, goldens, depth, key, rln10, rln20):

@@ -194,6 +194,30 @@ __global__ void __launch_bounds__(128) k_msm_reduce(const XYZZ<F>* __restrict__ 
     sum[(size_t)g * B + j] = acc;
 }
 
+// Small batches (a single proof through ffi_generate_rln_proof): thousands of partials per (group, proof) would be
+// summed by one thread above.  Here one CTA owns a (proof, group) pair: 128 threads stride over the tasks, then a
+// shared-memory tree combines them.
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_reduce_small(const XYZZ<F>* __restrict__ part, const MsmTask* __restrict__ tasks, u32 n_tasks,
+                                                          u32 B, XYZZ<F>* __restrict__ sum) {
+    __shared__ XYZZ<F> sh[128];
+    const u32 j = blockIdx.x, g = blockIdx.y;
+    XYZZ<F> acc = XYZZ<F>::infinity();
+    for (u32 t = threadIdx.x; t < n_tasks; t += 128)
+        if (tasks[t].group == g) acc.add(part[(size_t)t * B + j]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (u32 w = 64; w >= 1; w >>= 1) {
+        if (threadIdx.x < w) {
+            XYZZ<F> a = sh[threadIdx.x];
+            a.add(sh[threadIdx.x + w]);
+            sh[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sum[(size_t)g * B + j] = sh[0];
+}
+
 // ------------------------------------------------------------------------------------------- assembly
 __device__ __forceinline__ void load_scalar_bytes(const uint8_t* p, u32* out) {
     const uint4* q = reinterpret_cast<const uint4*>(p);
@@ -427,7 +451,8 @@ void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, 
             }
         }
         if (ws.ev) cudaEventRecord(ws.ev[1], s);
-        k_msm_reduce<Fq><<<dim3((B + bx - 1) / bx, 4), bx, 0, s>>>(ws.part_g1, ws.tasks_g1, ws.n_tasks_g1, B, ws.sum_g1);
+        if (B < 64) k_msm_reduce_small<Fq><<<dim3(B, 4), 128, 0, s>>>(ws.part_g1, ws.tasks_g1, ws.n_tasks_g1, B, ws.sum_g1);
+        else k_msm_reduce<Fq><<<dim3((B + bx - 1) / bx, 4), bx, 0, s>>>(ws.part_g1, ws.tasks_g1, ws.n_tasks_g1, B, ws.sum_g1);
         if (ws.ev) cudaEventRecord(ws.ev[2], s);
     }
     {   // G2: B2
@@ -445,7 +470,8 @@ void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, 
             }
         }
         if (ws.ev) cudaEventRecord(ws.ev[3], s);
-        k_msm_reduce<Fq2><<<dim3((B + bx - 1) / bx, 1), bx, 0, s>>>(ws.part_g2, ws.tasks_g2, ws.n_tasks_g2, B, ws.sum_g2);
+        if (B < 64) k_msm_reduce_small<Fq2><<<dim3(B, 1), 128, 0, s>>>(ws.part_g2, ws.tasks_g2, ws.n_tasks_g2, B, ws.sum_g2);
+        else k_msm_reduce<Fq2><<<dim3((B + bx - 1) / bx, 1), bx, 0, s>>>(ws.part_g2, ws.tasks_g2, ws.n_tasks_g2, B, ws.sum_g2);
         if (ws.ev) cudaEventRecord(ws.ev[4], s);
     }
 }

@@ -74,7 +74,7 @@ void var_msm_workspace_destroy(VarMsmWorkspace* w) {
     delete w;
 }
 
-// keys[k·n + i] = k·2^{c−1} + |d|−1 (or 0xffffffff when the digit is zero); vals = i | sign << 31
+// keys[k·n + i] = k·2^{c−1} + |d|−1 (or K·2^{c−1}, one past the last bucket, when the digit is zero); vals = i | sign << 31
 __global__ void __launch_bounds__(256) k_digits(const uint8_t* __restrict__ scalars, size_t n, int c, int K, u32* __restrict__ keys,
                                                 u32* __restrict__ vals) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) k_digits(const uint8_t* __restrict__ scal
         }
         int d = (int)(v & ((1u << c) - 1)) + (int)carry;
         if (d > (int)half) { d -= (1 << c); carry = 1; } else carry = 0;
-        u32 key = 0xffffffffu, val = (u32)i;
+        u32 key = (u32)K * half, val = (u32)i;  // zero digits sort behind every bucket
         if (d > 0) key = (u32)k * half + (u32)(d - 1);
         else if (d < 0) { key = (u32)k * half + (u32)(-d - 1); val |= 0x80000000u; }
         keys[(size_t)k * n + i] = key;
@@ -105,11 +105,11 @@ __global__ void __launch_bounds__(256) k_digits(const uint8_t* __restrict__ scal
     }
 }
 
-__global__ void k_bucket_bounds(const u32* __restrict__ keys, size_t items, u32* __restrict__ start, u32* __restrict__ end) {
+__global__ void k_bucket_bounds(const u32* __restrict__ keys, size_t items, u32 n_buckets, u32* __restrict__ start, u32* __restrict__ end) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= items) return;
     const u32 k = keys[i];
-    if (k == 0xffffffffu) return;
+    if (k >= n_buckets) return;
     if (i == 0 || keys[i - 1] != k) start[k] = (u32)i;
     if (i + 1 == items || keys[i + 1] != k) end[k] = (u32)i + 1;
 }
@@ -208,13 +208,12 @@ void launch_var_msm_g1(VarMsmWorkspace* w, const G1Affine* d_bases, const uint8_
     const size_t items = n * (size_t)K, n_buckets = (size_t)K * half;
     k_digits<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_scalars, n, c, K, w->keys_in, w->vals_in);
     int key_bits = 0;
-    while (((size_t)1 << key_bits) < n_buckets) key_bits++;
-    // zero digits carry key 0xffffffff: sort on all 32 bits so they land behind every bucket
+    while (((size_t)1 << key_bits) < n_buckets + 1) key_bits++;  // keys are in [0, n_buckets]: sort only the significant bits
     size_t tmp = w->cub_tmp_bytes;
-    cub::DeviceRadixSort::SortPairs(w->cub_tmp, tmp, w->keys_in, w->keys_out, w->vals_in, w->vals_out, (int64_t)items, 0, 32, s);
+    cub::DeviceRadixSort::SortPairs(w->cub_tmp, tmp, w->keys_in, w->keys_out, w->vals_in, w->vals_out, (int64_t)items, 0, key_bits, s);
     ZK_CUDA_CHECK(cudaMemsetAsync(w->bucket_start, 0, 4 * n_buckets, s));
     ZK_CUDA_CHECK(cudaMemsetAsync(w->bucket_end, 0, 4 * n_buckets, s));
-    k_bucket_bounds<<<(unsigned)((items + 255) / 256), 256, 0, s>>>(w->keys_out, items, w->bucket_start, w->bucket_end);
+    k_bucket_bounds<<<(unsigned)((items + 255) / 256), 256, 0, s>>>(w->keys_out, items, (u32)n_buckets, w->bucket_start, w->bucket_end);
     k_bucket_sum<<<(unsigned)((n_buckets + 127) / 128), 128, 0, s>>>(d_bases, w->vals_out, w->bucket_start, w->bucket_end, n_buckets, w->buckets);
     const u32 n_seg = half < (u32)SEGS ? half : (u32)SEGS;
     const u32 seg_len = half / n_seg;
