@@ -25,13 +25,23 @@ struct Fq2 {
     HD Fq2 conj() const { return {a, b.neg()}; }
     HD Fq2 operator*(const Fq2& o) const {  // Karatsuba, 3 base multiplications
         // (inlined on purpose: out-of-line Fq products were measured 28 % slower in k_msm_accum<Fq2>, profiles/README.md)
+#if defined(__CUDA_ARCH__) && defined(ZK_FQ2_OUTLINE)
+        Fq t0 = Fq::mul_ni(a, o.a), t1 = Fq::mul_ni(b, o.b);
+        Fq t2 = Fq::mul_ni(a + b, o.a + o.b);
+#else
         Fq t0 = a * o.a, t1 = b * o.b;
         Fq t2 = (a + b) * (o.a + o.b);
+#endif
         return {t0 - t1, t2 - t0 - t1};
     }
     HD Fq2 sqr() const {
+#if defined(__CUDA_ARCH__) && defined(ZK_FQ2_OUTLINE)
+        Fq t = Fq::mul_ni(a, b);
+        return {Fq::mul_ni(a + b, a - b), t.dbl()};
+#else
         Fq t = a * b;
         return {(a + b) * (a - b), t.dbl()};
+#endif
     }
     HD Fq2 scale(const Fq& k) const { return {a * k, b * k}; }
     HD Fq2 mul_xi() const {  // × (9 + u)

@@ -167,6 +167,9 @@ struct alignas(16) Fp {
         return r;
     }
     HD Fp sqr() const { return (*this) * (*this); }
+    // out-of-line product with operands and result in registers (by value): one copy of the multiplier body per kernel
+    // image, for Fq2 arithmetic whose fully inlined form overflows the instruction cache (ncu: stall_no_instruction)
+    static HDN Fp mul_ni(Fp a, Fp b) { return a * b; }
     HD Fp& operator+=(const Fp& o) { return *this = *this + o; }
     HD Fp& operator-=(const Fp& o) { return *this = *this - o; }
     HD Fp& operator*=(const Fp& o) { return *this = *this * o; }

@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <vector>
 
+#define ZK_FQ2_OUTLINE 1  // this TU only: Fq2 products call one shared out-of-line Fq multiplier (see fp.cuh mul_ni)
 #include "device_api.hpp"
 
 namespace zk {
