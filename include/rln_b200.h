@@ -262,10 +262,13 @@ int rlnb200_msm_g1_device(RlnB200Msm_t *m, const void *d_bases, const void *d_sc
 /* raw kernels for parity tests (host buffers, canonical LE field elements) */
 int rlnb200_poseidon_hash(const uint8_t *inputs, int n_inputs /* 1..3 */, uint8_t *out32, RlnString *err);
 int rlnb200_hash_pairs(const uint8_t *pairs /* n*64 */, size_t n, uint8_t *out /* n*32 */, RlnString *err);
-/* op: 0 mul, 1 add, 2 sub ; field: 0 Fr, 1 Fq ; exercises the PTX field arithmetic */
+/* op: 0 mul, 1 add, 2 sub, 3 portable mul, 4 inverse, 5 square, 6-8 single-reduction dot products ; field: 0 Fr, 1 Fq ; exercises the PTX field arithmetic */
 int rlnb200_field_op(int field, int op, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out, RlnString *err);
 /* measured Montgomery-product rate (products/s over all SMs, CUDA-event timed); < 0 on error */
 double rlnb200_mul_throughput(int iters);
+/* same for the cheaper schedules, in product-equivalents per second: kind 1 = dedicated squaring, 2 = two-term dot
+ * product with one reduction (counted as two products), 3 = Fq2 product (counted as three) */
+double rlnb200_op_throughput(int kind, int iters);
 /* pipe probe (thread-instructions per second): mode 0 wide integer MADs, 1 FP64 FMAs, 2 both interleaved */
 int rlnb200_pipe_probe(int mode, int iters, double out[2]);
 /* witness vector w (num_wires × 32) and quotient h (domain × 32) of one witness record */

@@ -1,0 +1,200 @@
+"""Python model of the PTX carry flag (CC.CF) used to validate carry-chain schedules before they are written
+as inline PTX in zerokit_b200/csrc/fp.cuh.  Mirrors mul_ptx / sqr_ptx instruction for instruction."""
+import random
+
+M = 0xFFFFFFFF
+
+
+class CC:
+    def __init__(self):
+        self.cf = None  # None = undefined (reading it is a bug)
+
+    def _rd(self):
+        assert self.cf is not None, "carry flag read while undefined"
+        return self.cf
+
+    def add_cc(self, a, b):
+        s = a + b; self.cf = s >> 32; return s & M
+
+    def addc_cc(self, a, b):
+        s = a + b + self._rd(); self.cf = s >> 32; return s & M
+
+    def addc(self, a, b):
+        s = a + b + self._rd(); self.cf = None; return s & M
+
+    def mad_lo_cc(self, a, b, c):
+        s = ((a * b) & M) + c; self.cf = s >> 32; return s & M
+
+    def madc_lo_cc(self, a, b, c):
+        s = ((a * b) & M) + c + self._rd(); self.cf = s >> 32; return s & M
+
+    def madc_hi_cc(self, a, b, c):
+        s = ((a * b) >> 32) + c + self._rd(); self.cf = s >> 32; return s & M
+
+    def madc_hi(self, a, b, c):
+        s = ((a * b) >> 32) + c + self._rd(); assert s >> 32 == 0, "madc.hi dropped a carry"; self.cf = None; return s & M
+
+
+def words(v, n=8):
+    return [(v >> (32 * i)) & M for i in range(n)]
+
+
+def val(w):
+    return sum(x << (32 * i) for i, x in enumerate(w))
+
+
+def reduce_row(c, E, O, p, inv):
+    m = (E[0] * inv) & M
+    O[0] = c.mad_lo_cc(p[1], m, O[0]); O[1] = c.madc_hi_cc(p[1], m, O[1])
+    for j in (2, 4, 6):
+        O[j] = c.madc_lo_cc(p[j + 1], m, O[j]); O[j + 1] = c.madc_hi_cc(p[j + 1], m, O[j + 1])
+    assert c.cf == 0, "O chain overflow"
+    E[0] = c.mad_lo_cc(p[0], m, E[0]); E[1] = c.madc_hi_cc(p[0], m, E[1])
+    for j in (2, 4, 6):
+        E[j] = c.madc_lo_cc(p[j], m, E[j]); E[j + 1] = c.madc_hi_cc(p[j], m, E[j + 1])
+    s = O[7] + c._rd(); assert s >> 32 == 0; O[7] = s; c.cf = None
+    assert E[0] == 0
+
+
+def finish(c, E, O, P):
+    r = [0] * 8
+    r[0] = c.add_cc(E[1], O[0])
+    for k in range(1, 7):
+        r[k] = c.addc_cc(E[k + 1], O[k])
+    r[7] = c.addc(O[7], 0)
+    v = val(r)
+    assert v < 2 * P
+    return v - P if v >= P else v
+
+
+def mul_model(a, b, P, inv):
+    c = CC(); A, B, p = words(a), words(b), words(P)
+    E = [0] * 8; O = [0] * 8
+    for i in range(8):
+        bi = B[i]
+        if i == 0:
+            for j in (0, 2, 4, 6):
+                t = A[j] * bi; E[j], E[j + 1] = t & M, t >> 32
+                t = A[j + 1] * bi; O[j], O[j + 1] = t & M, t >> 32
+        else:
+            nE = [0] * 8; nO = [0] * 8
+            nE[0] = c.add_cc(O[0], E[1])
+            for j in (0, 2, 4):
+                nO[j] = c.madc_lo_cc(A[j + 1], bi, E[j + 2]); nO[j + 1] = c.madc_hi_cc(A[j + 1], bi, E[j + 3])
+            nO[6] = c.madc_lo_cc(A[7], bi, 0); nO[7] = c.madc_hi(A[7], bi, 0)
+            nE[0] = c.mad_lo_cc(A[0], bi, nE[0]); nE[1] = c.madc_hi_cc(A[0], bi, O[1])
+            for j in (2, 4, 6):
+                nE[j] = c.madc_lo_cc(A[j], bi, O[j]); nE[j + 1] = c.madc_hi_cc(A[j], bi, O[j + 1])
+            s = nO[7] + c._rd(); assert s >> 32 == 0; nO[7] = s; c.cf = None
+            E, O = nE, nO
+        reduce_row(c, E, O, p, inv)
+    return finish(c, E, O, P)
+
+
+def sqr_model(a, P, inv):
+    c = CC(); A, p = words(a), words(P)
+    d = [0] * 8; s1 = [0] * 8
+    for j in range(1, 8):
+        d[j] = ((A[j] << 1) | (A[j - 1] >> 31)) & M
+        s1[j] = (A[j] << 1) & M
+
+    E = [0] * 8; O = [0] * 8
+    for i in range(8):
+        bi = A[i]
+
+        def V(j):
+            assert j >= i
+            return A[i] if j == i else (s1[j] if j == i + 1 else d[j])
+        if i == 0:
+            for j in (0, 2, 4, 6):
+                t = V(j) * bi; E[j], E[j + 1] = t & M, t >> 32
+                t = V(j + 1) * bi; O[j], O[j + 1] = t & M, t >> 32
+        else:
+            nE = [0] * 8; nO = [0] * 8
+            nE[0] = c.add_cc(O[0], E[1])
+            for j in (0, 2, 4):
+                if j + 1 >= i:
+                    nO[j] = c.madc_lo_cc(V(j + 1), bi, E[j + 2]); nO[j + 1] = c.madc_hi_cc(V(j + 1), bi, E[j + 3])
+                else:
+                    nO[j] = c.addc_cc(E[j + 2], 0); nO[j + 1] = c.addc_cc(E[j + 3], 0)
+            nO[6] = c.madc_lo_cc(V(7), bi, 0); nO[7] = c.madc_hi(V(7), bi, 0)
+            started = False
+            for j in (0, 2, 4, 6):
+                if j >= i:
+                    if not started:
+                        nE[j] = c.mad_lo_cc(V(j), bi, O[j]); started = True
+                    else:
+                        nE[j] = c.madc_lo_cc(V(j), bi, O[j])
+                    nE[j + 1] = c.madc_hi_cc(V(j), bi, O[j + 1])
+                else:
+                    if j > 0:
+                        nE[j] = O[j]
+                    nE[j + 1] = O[j + 1]
+            if started:
+                s = nO[7] + c._rd(); assert s >> 32 == 0; nO[7] = s; c.cf = None
+            E, O = nE, nO
+        reduce_row(c, E, O, p, inv)
+    return finish(c, E, O, P)
+
+
+def inplace_row(c, E, O, A, bi):
+    """E/O += A * bi without shifting (same shape as the reduction row)"""
+    O[0] = c.mad_lo_cc(A[1], bi, O[0]); O[1] = c.madc_hi_cc(A[1], bi, O[1])
+    for j in (2, 4, 6):
+        O[j] = c.madc_lo_cc(A[j + 1], bi, O[j]); O[j + 1] = c.madc_hi_cc(A[j + 1], bi, O[j + 1])
+    assert c.cf == 0, "O chain overflow (row)"
+    E[0] = c.mad_lo_cc(A[0], bi, E[0]); E[1] = c.madc_hi_cc(A[0], bi, E[1])
+    for j in (2, 4, 6):
+        E[j] = c.madc_lo_cc(A[j], bi, E[j]); E[j + 1] = c.madc_hi_cc(A[j], bi, E[j + 1])
+    s = O[7] + c._rd(); assert s >> 32 == 0; O[7] = s; c.cf = None
+
+
+def dot2_model(a, b, cc_, d, P, inv):
+    """a*b + cc_*d with one interleaved reduction"""
+    c = CC(); A, B, C2, D, p = words(a), words(b), words(cc_), words(d), words(P)
+    E = [0] * 8; O = [0] * 8
+    for i in range(8):
+        bi = B[i]
+        if i == 0:
+            for j in (0, 2, 4, 6):
+                t = A[j] * bi; E[j], E[j + 1] = t & M, t >> 32
+                t = A[j + 1] * bi; O[j], O[j + 1] = t & M, t >> 32
+        else:
+            nE = [0] * 8; nO = [0] * 8
+            nE[0] = c.add_cc(O[0], E[1])
+            for j in (0, 2, 4):
+                nO[j] = c.madc_lo_cc(A[j + 1], bi, E[j + 2]); nO[j + 1] = c.madc_hi_cc(A[j + 1], bi, E[j + 3])
+            nO[6] = c.madc_lo_cc(A[7], bi, 0); nO[7] = c.madc_hi(A[7], bi, 0)
+            nE[0] = c.mad_lo_cc(A[0], bi, nE[0]); nE[1] = c.madc_hi_cc(A[0], bi, O[1])
+            for j in (2, 4, 6):
+                nE[j] = c.madc_lo_cc(A[j], bi, O[j]); nE[j + 1] = c.madc_hi_cc(A[j], bi, O[j + 1])
+            s = nO[7] + c._rd(); assert s >> 32 == 0; nO[7] = s; c.cf = None
+            E, O = nE, nO
+        inplace_row(c, E, O, C2, D[i])
+        reduce_row(c, E, O, p, inv)
+    return finish(c, E, O, P)
+
+
+if __name__ == "__main__":
+    R = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    Q = 21888242871839275222246405745257275088696311157297823662689037894645226208583
+    rnd = random.Random(1)
+    for P in (R, Q):
+        inv = (-pow(P, -1, 1 << 32)) % (1 << 32)
+        Rinv = pow(1 << 256, -1, P)
+        cases = [0, 1, P - 1, P - 2, (1 << 253), (1 << 254) - 1 if (1 << 254) - 1 < P else P - 3, 0x80000000 * sum(1 << (32 * i) for i in range(7))]
+        cases += [rnd.randrange(P) for _ in range(3000)]
+        # words with top bits set in every limb (exercise the doubling carries)
+        cases += [val([rnd.choice([M, 0x80000000, 0x7fffffff, rnd.randrange(1 << 32)]) for _ in range(7)] + [rnd.randrange(0x30000000)]) for _ in range(2000)]
+        for a in cases:
+            a %= P
+            b = rnd.randrange(P)
+            assert mul_model(a, b, P, inv) == a * b * Rinv % P
+            assert sqr_model(a, P, inv) == a * a * Rinv % P, hex(a)
+            c2 = rnd.choice([P, P - 1, 0, rnd.randrange(P)]); d2 = rnd.choice([P - 1, rnd.randrange(P)])
+            assert dot2_model(a, b, c2, d2, P, inv) == (a * b + c2 * d2) * Rinv % P
+    for P in (R, Q):
+        inv = (-pow(P, -1, 1 << 32)) % (1 << 32); Rinv = pow(1 << 256, -1, P)
+        for a, b, c2, d2 in ((P - 1, P - 1, P, P - 1), (P - 1, P - 1, P - 1, P - 1), (P, P, P, P)):
+            assert dot2_model(a, b, c2, d2, P, inv) == (a * b + c2 * d2) * Rinv % P
+    print("mul/sqr/dot2 carry-chain schedules OK")

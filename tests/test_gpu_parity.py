@@ -49,6 +49,15 @@ def test_field_ops_ptx_vs_integers(z, field, p):
     assert ints(z.field_op(field, 2, A, B, n)) == [(x - y) % p for x, y in zip(a, b)]
     inv = ints(z.field_op(field, 4, A[:32 * 64], B[:32 * 64], 64))
     assert inv == [pow(x, -1, p) if x else 0 for x in a[:64]]
+    # dedicated squaring and the single-reduction dot products (operands with the top bit of every word set included)
+    hi = [sum(w << (32 * k) for k, w in enumerate([rnd.choice([0xFFFFFFFF, 0x80000000, 0x7FFFFFFF, rnd.getrandbits(32)]) for _ in range(7)]
+                                                  + [rnd.randrange(0x30000000)])) % p for _ in range(n)]
+    for aa, bb in ((a, b), (hi, a), (b, hi)):
+        AA, BB = fr_bytes(aa), fr_bytes(bb)
+        assert ints(z.field_op(field, 5, AA, BB, n)) == [x * x % p for x in aa]
+        assert ints(z.field_op(field, 6, AA, BB, n)) == [(x * x - y * y) % p for x, y in zip(aa, bb)]
+        assert ints(z.field_op(field, 7, AA, BB, n)) == [(y * y - x * x) % p for x, y in zip(aa, bb)]
+        assert ints(z.field_op(field, 8, AA, BB, n)) == [x * x % p for x in aa]
 
 
 # ------------------------------------------------------------------------------- Poseidon

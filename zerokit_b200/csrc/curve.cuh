@@ -23,16 +23,23 @@ struct Fq2 {
     HD Fq2 neg() const { return {a.neg(), b.neg()}; }
     HD Fq2 dbl() const { return {a.dbl(), b.dbl()}; }
     HD Fq2 conj() const { return {a, b.neg()}; }
-    HD Fq2 operator*(const Fq2& o) const {  // Karatsuba, 3 base multiplications
-        // (inlined on purpose: out-of-line Fq products were measured 28 % slower in k_msm_accum<Fq2>, profiles/README.md)
-#if defined(__CUDA_ARCH__) && defined(ZK_FQ2_OUTLINE)
-        Fq t0 = Fq::mul_ni(a, o.a), t1 = Fq::mul_ni(b, o.b);
-        Fq t2 = Fq::mul_ni(a + b, o.a + o.b);
-#else
+    HD Fq2 operator*(const Fq2& o) const {
+        // two 2-term dot products, each with a single Montgomery reduction: 4·64 + 2·64 wide MADs — the same count as
+        // Karatsuba's three full products, without its five 256-bit additions (and with two reductions instead of three)
+#if defined(__CUDA_ARCH__) && defined(ZK_FQ2_KARATSUBA)
         Fq t0 = a * o.a, t1 = b * o.b;
         Fq t2 = (a + b) * (o.a + o.b);
-#endif
         return {t0 - t1, t2 - t0 - t1};
+#else
+        return {Fq::dot2(a, o.a, b.neg_lazy(), o.b), Fq::dot2(a, o.b, b, o.a)};
+#endif
+    }
+    // x·y − z·w: two 4-term dot products
+    static HD Fq2 sub_prod(const Fq2& x, const Fq2& y, const Fq2& z, const Fq2& w) {
+        const Fq nxb = x.b.neg_lazy(), nza = z.a.neg_lazy(), nzb = z.b.neg_lazy();
+        const Fq re_a[4] = {x.a, nxb, nza, z.b}, re_b[4] = {y.a, y.b, w.a, w.b};
+        const Fq im_a[4] = {x.a, x.b, nza, nzb}, im_b[4] = {y.b, y.a, w.b, w.a};
+        return {Fq::dot<4>(re_a, re_b), Fq::dot<4>(im_a, im_b)};
     }
     HD Fq2 sqr() const {
 #if defined(__CUDA_ARCH__) && defined(ZK_FQ2_OUTLINE)
@@ -88,7 +95,7 @@ struct XYZZ {
         F XX = X.sqr();
         F M = XX.dbl() + XX;
         F X3 = M.sqr() - S.dbl();
-        F Y3 = M * (S - X3) - W * Y;
+        F Y3 = F::sub_prod(M, S - X3, W, Y);
         return {X3, Y3, V * ZZ, W * ZZZ};
     }
     // mixed addition acc += p (affine, must not be infinity); complete: handles acc = ∞, p = ±acc
@@ -110,7 +117,7 @@ struct XYZZ {
         F PPP = P * PP;
         F Qv = X * PP;
         F X3 = R.sqr() - PPP - Qv.dbl();
-        Y = R * (Qv - X3) - Y * PPP;
+        Y = F::sub_prod(R, Qv - X3, Y, PPP);
         X = X3;
         ZZ = ZZ * PP;
         ZZZ = ZZZ * PPP;
@@ -128,7 +135,7 @@ struct XYZZ {
         }
         F PP = P.sqr(), PPP = P * PP, Qv = U1 * PP;
         F X3 = R.sqr() - PPP - Qv.dbl();
-        Y = R * (Qv - X3) - S1 * PPP;
+        Y = F::sub_prod(R, Qv - X3, S1, PPP);
         X = X3;
         ZZ = ZZ * o.ZZ * PP;
         ZZZ = ZZZ * o.ZZZ * PPP;

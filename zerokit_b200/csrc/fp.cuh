@@ -166,7 +166,54 @@ struct alignas(16) Fp {
 #endif
         return r;
     }
-    HD Fp sqr() const { return (*this) * (*this); }
+    // dedicated squaring: 36 + 64 wide MADs instead of 64 + 64 (the off-diagonal products are taken once against the
+    // doubled operand); the rows keep the shape of mul_ptx so the interleaved reduction is unchanged
+    HD Fp sqr() const {
+#if ZK_PTX
+        Fp r;
+        sqr_ptx(r.l, l);
+        return r;
+#else
+        return (*this) * (*this);
+#endif
+    }
+    // Σ a[k]·b[k] over N ≤ 5 terms with ONE Montgomery reduction (64·N + 64 wide MADs instead of 128·N).  The a[k] may
+    // equal p (callers pass p − y for differences of products); the result is fully reduced:
+    // (N·p² + R·p)/R < 2p for N ≤ 5.  Schedule validated on scratch/ptx_model.py (dot2_model and its N-term form).
+    template <int N>
+    static HD Fp dot(const Fp* a, const Fp* b) {
+        static_assert(N >= 1 && N <= 5, "dot: the single conditional subtraction covers at most 5 terms");
+        Fp r;
+#if ZK_PTX
+        u32 E[8], O[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (i == 0) row_first_ptx(E, O, a[0].l, b[0].l[0]);
+            else row_shift_ptx(E, O, a[0].l, b[0].l[i]);
+#pragma unroll
+            for (int k = 1; k < N; k++) row_inplace_ptx(E, O, a[k].l, b[k].l[i]);
+            reduce_row_ptx(E, O);
+        }
+        finish_ptx(r.l, E, O);
+#else
+        mul_portable(r.l, a[0].l, b[0].l);
+        for (int k = 1; k < N; k++) { Fp t; mul_portable(t.l, a[k].l, b[k].l); r = r + t; }
+#endif
+        return r;
+    }
+    static HD Fp dot2(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+        const Fp x[2] = {a, c}, y[2] = {b, d};
+        return dot<2>(x, y);
+    }
+    // a·b − c·d with one reduction
+    static HD Fp sub_prod(const Fp& a, const Fp& b, const Fp& c, const Fp& d) { return dot2(a, b, c.neg_lazy(), d); }
+    // p − x as an integer in [1, p] (not reduced: 0 maps to p); only meant as the c operand of dot2
+    HD Fp neg_lazy() const {
+        Fp r, p;
+        for (int i = 0; i < 8; i++) p.l[i] = C::p(i);
+        raw_sub(r.l, p.l, l);
+        return r;
+    }
     // out-of-line product with operands and result in registers (by value): one copy of the multiplier body per kernel
     // image, for Fq2 arithmetic whose fully inlined form overflows the instruction cache (ncu: stall_no_instruction)
     static HDN Fp mul_ni(Fp a, Fp b) { return a * b; }
@@ -196,63 +243,142 @@ struct alignas(16) Fp {
     }
 
 #if ZK_PTX
-    static DEV void mul_ptx(u32* r, const u32* a, const u32* b) {
-        // E: words of weight 2^0, 2^32, …  O: words of weight 2^32, 2^64, …  (sum T = E + O·2^32)
-        u32 E[8], O[8];
+    // one interleaved reduction row: T += m·p with m chosen so that the low word cancels (T = E + O·2^32)
+    static DEV void reduce_row_ptx(u32* E, u32* O) {
+        const u32 m = E[0] * C::INV;
+        O[0] = ptx_mad_lo_cc(C::p(1), m, O[0]);
+        O[1] = ptx_madc_hi_cc(C::p(1), m, O[1]);
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const u32 bi = b[i];
-            if (i == 0) {
-#pragma unroll
-                for (int j = 0; j < 8; j += 2) {
-                    asm("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(E[j]), "=r"(E[j + 1]) : "r"(a[j]), "r"(bi));
-                    asm("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(O[j]), "=r"(O[j + 1]) : "r"(a[j + 1]), "r"(bi));
-                }
-            } else {
-                // shift T right by one word:  E' = O + E[1],  O' = E >> 64;  then accumulate a·b[i]
-                u32 nE[8], nO[8];
-                nE[0] = ptx_add_cc(O[0], E[1]);
-#pragma unroll
-                for (int j = 0; j < 6; j += 2) {
-                    nO[j] = ptx_madc_lo_cc(a[j + 1], bi, E[j + 2]);
-                    nO[j + 1] = ptx_madc_hi_cc(a[j + 1], bi, E[j + 3]);
-                }
-                nO[6] = ptx_madc_lo_cc(a[7], bi, 0);
-                nO[7] = ptx_madc_hi(a[7], bi, 0);
-                nE[0] = ptx_mad_lo_cc(a[0], bi, nE[0]);
-                nE[1] = ptx_madc_hi_cc(a[0], bi, O[1]);
-#pragma unroll
-                for (int j = 2; j < 8; j += 2) {
-                    nE[j] = ptx_madc_lo_cc(a[j], bi, O[j]);
-                    nE[j + 1] = ptx_madc_hi_cc(a[j], bi, O[j + 1]);
-                }
-                nO[7] = ptx_addc(nO[7], 0);
-#pragma unroll
-                for (int j = 0; j < 8; j++) { E[j] = nE[j]; O[j] = nO[j]; }
-            }
-            const u32 m = E[0] * C::INV;
-            O[0] = ptx_mad_lo_cc(C::p(1), m, O[0]);
-            O[1] = ptx_madc_hi_cc(C::p(1), m, O[1]);
-#pragma unroll
-            for (int j = 2; j < 8; j += 2) {
-                O[j] = ptx_madc_lo_cc(C::p(j + 1), m, O[j]);
-                O[j + 1] = ptx_madc_hi_cc(C::p(j + 1), m, O[j + 1]);
-            }
-            E[0] = ptx_mad_lo_cc(C::p(0), m, E[0]);
-            E[1] = ptx_madc_hi_cc(C::p(0), m, E[1]);
-#pragma unroll
-            for (int j = 2; j < 8; j += 2) {
-                E[j] = ptx_madc_lo_cc(C::p(j), m, E[j]);
-                E[j + 1] = ptx_madc_hi_cc(C::p(j), m, E[j + 1]);
-            }
-            O[7] = ptx_addc(O[7], 0);
+        for (int j = 2; j < 8; j += 2) {
+            O[j] = ptx_madc_lo_cc(C::p(j + 1), m, O[j]);
+            O[j + 1] = ptx_madc_hi_cc(C::p(j + 1), m, O[j + 1]);
         }
-        // result = (E >> 32) + O
+        E[0] = ptx_mad_lo_cc(C::p(0), m, E[0]);
+        E[1] = ptx_madc_hi_cc(C::p(0), m, E[1]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            E[j] = ptx_madc_lo_cc(C::p(j), m, E[j]);
+            E[j + 1] = ptx_madc_hi_cc(C::p(j), m, E[j + 1]);
+        }
+        O[7] = ptx_addc(O[7], 0);
+    }
+    // T += a·bi in place (same shape as the reduction row)
+    static DEV void row_inplace_ptx(u32* E, u32* O, const u32* a, u32 bi) {
+        O[0] = ptx_mad_lo_cc(a[1], bi, O[0]);
+        O[1] = ptx_madc_hi_cc(a[1], bi, O[1]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            O[j] = ptx_madc_lo_cc(a[j + 1], bi, O[j]);
+            O[j + 1] = ptx_madc_hi_cc(a[j + 1], bi, O[j + 1]);
+        }
+        E[0] = ptx_mad_lo_cc(a[0], bi, E[0]);
+        E[1] = ptx_madc_hi_cc(a[0], bi, E[1]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            E[j] = ptx_madc_lo_cc(a[j], bi, E[j]);
+            E[j + 1] = ptx_madc_hi_cc(a[j], bi, E[j + 1]);
+        }
+        O[7] = ptx_addc(O[7], 0);
+    }
+    // T = (T >> 32) + a·bi  (the shift is free: the old E words feed the new O chain and vice versa)
+    static DEV void row_shift_ptx(u32* E, u32* O, const u32* a, u32 bi) {
+        u32 nE[8], nO[8];
+        nE[0] = ptx_add_cc(O[0], E[1]);
+#pragma unroll
+        for (int j = 0; j < 6; j += 2) {
+            nO[j] = ptx_madc_lo_cc(a[j + 1], bi, E[j + 2]);
+            nO[j + 1] = ptx_madc_hi_cc(a[j + 1], bi, E[j + 3]);
+        }
+        nO[6] = ptx_madc_lo_cc(a[7], bi, 0);
+        nO[7] = ptx_madc_hi(a[7], bi, 0);
+        nE[0] = ptx_mad_lo_cc(a[0], bi, nE[0]);
+        nE[1] = ptx_madc_hi_cc(a[0], bi, O[1]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            nE[j] = ptx_madc_lo_cc(a[j], bi, O[j]);
+            nE[j + 1] = ptx_madc_hi_cc(a[j], bi, O[j + 1]);
+        }
+        nO[7] = ptx_addc(nO[7], 0);
+#pragma unroll
+        for (int j = 0; j < 8; j++) { E[j] = nE[j]; O[j] = nO[j]; }
+    }
+    static DEV void row_first_ptx(u32* E, u32* O, const u32* a, u32 bi) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            asm("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(E[j]), "=r"(E[j + 1]) : "r"(a[j]), "r"(bi));
+            asm("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(O[j]), "=r"(O[j + 1]) : "r"(a[j + 1]), "r"(bi));
+        }
+    }
+    static DEV void finish_ptx(u32* r, const u32* E, const u32* O) {  // result = (E >> 32) + O, then one conditional −p
         r[0] = ptx_add_cc(E[1], O[0]);
 #pragma unroll
         for (int k = 1; k < 7; k++) r[k] = ptx_addc_cc(E[k + 1], O[k]);
         r[7] = ptx_addc(O[7], 0);
         cond_sub_p(r);
+    }
+    // schedule validated on scratch/ptx_model.py (sqr_model): row i multiplies a[i] by (a[i], 2·a[i+1..7]) only
+    static DEV void sqr_ptx(u32* r, const u32* a) {
+        u32 d[8], s1[8];
+        d[0] = 0; s1[0] = 0;
+#pragma unroll
+        for (int j = 1; j < 8; j++) {
+            d[j] = __funnelshift_l(a[j - 1], a[j], 1);
+            s1[j] = a[j] << 1;
+        }
+        u32 E[8], O[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const u32 bi = a[i];
+            u32 v[8];   // multiplicand words of this row (entries below i are unused)
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = j == i ? a[i] : (j == i + 1 ? s1[j] : d[j]);
+            if (i == 0) {
+                row_first_ptx(E, O, v, bi);
+            } else {
+                u32 nE[8], nO[8];
+                nE[0] = ptx_add_cc(O[0], E[1]);
+#pragma unroll
+                for (int j = 0; j < 6; j += 2) {
+                    if (j + 1 >= i) {
+                        nO[j] = ptx_madc_lo_cc(v[j + 1], bi, E[j + 2]);
+                        nO[j + 1] = ptx_madc_hi_cc(v[j + 1], bi, E[j + 3]);
+                    } else {
+                        nO[j] = ptx_addc_cc(E[j + 2], 0);
+                        nO[j + 1] = ptx_addc_cc(E[j + 3], 0);
+                    }
+                }
+                nO[6] = ptx_madc_lo_cc(v[7], bi, 0);
+                nO[7] = ptx_madc_hi(v[7], bi, 0);
+                bool started = false;
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    if (j >= i) {
+                        nE[j] = started ? ptx_madc_lo_cc(v[j], bi, O[j]) : ptx_mad_lo_cc(v[j], bi, O[j]);
+                        started = true;
+                        nE[j + 1] = ptx_madc_hi_cc(v[j], bi, O[j + 1]);
+                    } else {
+                        if (j > 0) nE[j] = O[j];
+                        nE[j + 1] = O[j + 1];
+                    }
+                }
+                if (started) nO[7] = ptx_addc(nO[7], 0);
+#pragma unroll
+                for (int j = 0; j < 8; j++) { E[j] = nE[j]; O[j] = nO[j]; }
+            }
+            reduce_row_ptx(E, O);
+        }
+        finish_ptx(r, E, O);
+    }
+    static DEV void mul_ptx(u32* r, const u32* a, const u32* b) {
+        // E: words of weight 2^0, 2^32, …  O: words of weight 2^32, 2^64, …  (sum T = E + O·2^32)
+        u32 E[8], O[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (i == 0) row_first_ptx(E, O, a, b[0]);
+            else row_shift_ptx(E, O, a, b[i]);
+            reduce_row_ptx(E, O);
+        }
+        finish_ptx(r, E, O);
     }
 #endif
 

@@ -21,7 +21,16 @@ __global__ void k_field_op(int op, const uint8_t* __restrict__ a, const uint8_t*
     else if (op == 1) fr = fx + fy;
     else if (op == 2) fr = fx - fy;
     else if (op == 3) { F::mul_portable(fr.l, fx.l, fy.l); }   // portable CIOS path on the device, for cross-checking
-    else fr = fx.inv();
+    else if (op == 4) fr = fx.inv();
+    else if (op == 5) fr = fx.sqr();                                           // dedicated squaring schedule
+    else if (op == 6) fr = F::sub_prod(fx, fx, fy, fy);                         // x² − y², one reduction
+    else if (op == 7) {                                                         // 4-term dot product with lazily negated operands: y² − x²
+        const F u[4] = {fx, fy, fx.neg_lazy(), fy.neg_lazy()}, v[4] = {fy, fy, fx, fx};
+        fr = F::template dot<4>(u, v);
+    } else {                                                                    // 5 terms, all operands at their maximum (p and x)
+        const F u[5] = {fx.neg_lazy(), F::zero().neg_lazy(), fy, fx, F::zero().neg_lazy()}, v[5] = {fy, fx, fx, fx, fy};
+        fr = F::template dot<5>(u, v);                                          // −xy + 0 + xy + x² + 0
+    }
     fr.to_canonical(r);
     for (int k = 0; k < 8; k++) reinterpret_cast<u32*>(out + 32 * i)[k] = r[k];
 }
@@ -37,6 +46,19 @@ __global__ void __launch_bounds__(256) k_mul_throughput(F* __restrict__ data, in
         b = b * m;
         c = c * m;
         d = d * m;
+    }
+    data[4 * i] = a; data[4 * i + 1] = b; data[4 * i + 2] = c; data[4 * i + 3] = d;
+}
+// KIND 1 = dedicated squaring, 2 = two-term dot product (counts as two products), 3 = Fq2 product (counts as three)
+template <int KIND>
+__global__ void __launch_bounds__(256) k_op_throughput(Fq* __restrict__ data, int iters) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    Fq a = data[4 * i], b = data[4 * i + 1], c = data[4 * i + 2], d = data[4 * i + 3];
+    const Fq m = a + b;
+    for (int t = 0; t < iters; t++) {
+        if (KIND == 1) { a = a.sqr(); b = b.sqr(); c = c.sqr(); d = d.sqr(); }
+        else if (KIND == 2) { Fq na = Fq::dot2(a, m, b, c), nc = Fq::dot2(c, m, d, a); b = a; d = c; a = na; c = nc; }
+        else { Fq2 x = Fq2{a, b} * Fq2{c, d}; Fq2 y = Fq2{c, d} * Fq2{m, a}; a = x.a; b = x.b; c = y.a; d = y.b; }
     }
     data[4 * i] = a; data[4 * i + 1] = b; data[4 * i + 2] = c; data[4 * i + 3] = d;
 }
@@ -130,6 +152,39 @@ int rlnb200_pipe_probe(int mode, int iters, double out[2]) {
         return 0;
     } catch (const CudaError&) {
         return -1;
+    }
+}
+// product-equivalents per second of the squaring / dot-product / Fq2 schedules (kind as in k_op_throughput)
+double rlnb200_op_throughput(int kind, int iters) {
+    try {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const size_t threads = (size_t)sms * 2048;
+        Fq* d = nullptr;
+        ZK_CUDA_CHECK(cudaMalloc(&d, sizeof(Fq) * 4 * threads));
+        ZK_CUDA_CHECK(cudaMemset(d, 0x11, sizeof(Fq) * 4 * threads));
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        auto run = [&](int it) {
+            unsigned g = (unsigned)(threads / 256);
+            if (kind == 1) k_op_throughput<1><<<g, 256>>>(d, it);
+            else if (kind == 2) k_op_throughput<2><<<g, 256>>>(d, it);
+            else k_op_throughput<3><<<g, 256>>>(d, it);
+        };
+        run(8);
+        cudaEventRecord(e0);
+        run(iters);
+        cudaEventRecord(e1);
+        ZK_CUDA_CHECK(cudaEventSynchronize(e1));
+        g_launch_count += 2;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaFree(d); cudaEventDestroy(e0); cudaEventDestroy(e1);
+        const double per_iter = kind == 1 ? 4.0 : kind == 2 ? 4.0 : 6.0;
+        return (double)threads * per_iter * iters / (ms * 1e-3);
+    } catch (const CudaError&) {
+        return -1.0;
     }
 }
 // returns Montgomery products per second measured with CUDA events (Fq, all SMs busy), or a negative value

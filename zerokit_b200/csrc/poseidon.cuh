@@ -51,12 +51,7 @@ HD Fr poseidon_permute(Fr* st, const Fr* __restrict__ ark, const Fr* __restrict_
         }
         Fr nx[T];
 #pragma unroll
-        for (int i = 0; i < T; i++) {
-            Fr acc = mds[i * T] * st[0];
-#pragma unroll
-            for (int j = 1; j < T; j++) acc += mds[i * T + j] * st[j];
-            nx[i] = acc;
-        }
+        for (int i = 0; i < T; i++) nx[i] = Fr::dot<T>(st, mds + i * T);   // one Montgomery reduction per MDS row
 #pragma unroll
         for (int i = 0; i < T; i++) st[i] = nx[i];
     }

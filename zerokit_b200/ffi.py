@@ -177,6 +177,7 @@ def lib():
         "rlnb200_num_wires": (c_size_t, [pp]),
         "rlnb200_domain_size": (c_size_t, [pp]),
         "rlnb200_mul_throughput": (c_double, [c_int]),
+        "rlnb200_op_throughput": (c_double, [c_int, c_int]),
         "rlnb200_pipe_probe": (c_int, [c_int, c_int, POINTER(c_double)]),
     }
     for name, (res, args) in sig.items():
