@@ -193,7 +193,7 @@ def run_gpu(args, rank, local_rank, world):
     t0 = time.time()
     rln = z.RLN.new(DEPTH)
     info = rln.table_info()
-    log(f"[rank {rank}] RLN.new: {time.time() - t0:.1f}s, tables G1 c={info['window_bits']} K={info['windows']}, G2 c={info['window_bits_g2']} K={info['windows_g2']}, {info['table_bytes'] / 2**30:.1f} GiB")
+    log(f"[rank {rank}] RLN.new: {time.time() - t0:.1f}s, tables G1 c={info['window_bits']} K={info['windows']}{' x2 (GLV)' if info['glv'] else ''}, G2 c={info['window_bits_g2']} K={info['windows_g2']}, {info['table_bytes'] / 2**30:.1f} GiB")
     n = BATCH
     slots = rln.input_slots()
     # ---- inputs: rank 0 generates world·n distinct witnesses; NCCL scatters contiguous slices (zerokit_b200/sharding.py)
@@ -320,19 +320,26 @@ def run_gpu(args, rank, local_rank, world):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
     terms = info["g1_bases"] * n                                     # MSM terms one launch processes
     alg_bytes = 96 * terms                                           # 32 B scalar + 64 B affine base per G1 MSM term
-    table_bytes = terms * (32 + 64 * info["windows"])                # bytes this formulation must touch (scalar + one table entry per window)
+    table_bytes = terms * (32 + 64 * info["adds_per_term"])          # bytes this formulation must touch (scalar + one table entry per window visit)
     k_ms = stage["msm_g1_accum"]
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     mul_rate = z.mul_throughput(2000)
-    madds = terms * info["windows"]
+    madds = terms * info["adds_per_term"]
+    # wide 32x32->64 MADs of one mixed XYZZ addition as compiled (cuobjdump): 6 products (129) + 2 squarings (100) + the
+    # two-term dot product of Y3 (193); IMAD.WIDE occupies the FMA-heavy pipe 4 cycles per warp instruction
+    WIDE_PER_ADD = 6 * 129 + 2 * 100 + 193
+    sm_clock = 1e6 * float(peaks.get("sm_max_mhz", 1965.0))
+    wide_ceiling = 148 * 4 * 8 * sm_clock
     roofline = {
         "bound": "hbm", "kernel": "k_msm_accum<Fq> (fixed-base G1 accumulate)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
         "algorithmic_bytes_per_launch": alg_bytes, "units_per_launch": terms, "bytes_per_unit": 96,
         "table_formulation_bytes_per_launch": table_bytes, "table_formulation_gbs": table_bytes / (k_ms * 1e-3) / 1e9,
         # the honest second number: this kernel is bound by the integer multiply pipe, not by HBM
-        "int_pipe": {"mixed_adds_per_launch": madds, "modmul_per_s_needed": madds * 10 / (k_ms * 1e-3),
-                     "modmul_per_s_measured_peak": mul_rate, "frac": madds * 10 / (k_ms * 1e-3) / mul_rate if mul_rate > 0 else None},
+        "int_pipe": {"mixed_adds_per_launch": madds, "wide_mads_per_add": WIDE_PER_ADD, "wide_mads_per_s": madds * WIDE_PER_ADD / (k_ms * 1e-3),
+                     "wide_mad_ceiling_per_s": wide_ceiling, "frac": madds * WIDE_PER_ADD / (k_ms * 1e-3) / wide_ceiling,
+                     "ceiling": "148 SMs x 4 schedulers x 8 lanes/clk (IMAD.WIDE = 4 cycles per warp instruction) x SM clock",
+                     "modmul_per_s_measured_peak": mul_rate},
     }
     traffic_file = os.path.join(ROOT, "profiles", "traffic_msm_accum_g1.json")
     if os.path.exists(traffic_file):

@@ -237,6 +237,12 @@ int rlnb200_set_device(int device, RlnString *err);
  * G1 / G2 bases, bytes in HBM */
 int rlnb200_table_info(FFI_RLN_t *const *rln, int *window_bits, int *windows, uint64_t *g1_bases, uint64_t *g2_bases,
                        uint64_t *table_bytes, int *window_bits_g2, int *windows_g2);
+/* 1 when the G1 scalars are GLV-split (k = k1 + k2*lambda, two visits of `windows` windows per base; RLN_B200_GLV=0
+ * disables it) */
+int rlnb200_glv_enabled(FFI_RLN_t *const *rln);
+/* self-test of the split kernel: n canonical 32-byte scalars -> n x 36 bytes (|k1| 16 B LE, |k2| 16 B LE, sign1, sign2,
+ * 2 pad bytes) with k = (+-k1) + (+-k2)*lambda mod r and |ki| < 2^128 */
+int rlnb200_glv_split(const uint8_t *scalars_le, size_t n, uint8_t *out36, RlnString *err);
 
 /* Merkle tree bulk operations on device/host buffers (FullMerkleTree semantics,
  * utils/src/merkle_tree/full_merkle_tree.rs:197-223,288-304) */

@@ -60,6 +60,18 @@ def test_field_ops_ptx_vs_integers(z, field, p):
         assert ints(z.field_op(field, 8, AA, BB, n)) == [x * x % p for x in aa]
 
 
+def test_glv_split_kernel(z):
+    """k ≡ k1 + k2·λ (mod r), |ki| < 2^128 — the split the fixed-base G1 accumulate kernel applies to every scalar"""
+    lam = 0xb3c4d79d41a917585bfc41088d8daaa78b17ea66b99c90dd
+    assert (lam * lam + lam + 1) % R == 0
+    rnd = random.Random(77)
+    ks = [0, 1, 2, R - 1, R - 2, lam, lam - 1, lam + 1, R // 2, R // 3, 1 << 253, 1 << 128, (1 << 128) - 1, (1 << 64) - 1]
+    ks += [rnd.randrange(R) for _ in range(4096 - len(ks))]
+    for k, (k1, k2) in zip(ks, z.glv_split(fr_bytes(ks), len(ks))):
+        assert (k1 + k2 * lam - k) % R == 0
+        assert abs(k1) < 1 << 128 and abs(k2) < 1 << 128
+
+
 # ------------------------------------------------------------------------------- Poseidon
 def test_poseidon_reference_kats(z, goldens):
     """utils/tests/poseidon_hash_test.rs:21-130"""

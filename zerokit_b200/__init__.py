@@ -5,4 +5,4 @@ The product is the CUDA shared library zerokit_b200/lib/librln_b200.so (C ABI: i
 benchmark.  Importing the API without the built library raises — there is no CPU fallback.
 """
 from .rln import (RLN, RLNError, RLNProof, RLNProofValues, RLNWitnessInput, RLNPartialWitnessInput, RLNPartialProof, G1Msm, hash_to_field_le, hash_to_field_be,  # noqa: F401
-                  poseidon_hash, poseidon_hash_pair, keygen, field_op, hash_pairs, set_device, mul_throughput, DEFAULT_TREE_DEPTH, R)
+                  poseidon_hash, poseidon_hash_pair, keygen, field_op, glv_split, hash_pairs, set_device, mul_throughput, DEFAULT_TREE_DEPTH, R)

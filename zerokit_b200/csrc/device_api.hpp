@@ -86,6 +86,8 @@ struct MsmGroupDev {
 };
 struct FixedMsmPlan {
     int c, K;            // G1 tables: window bits, windows
+    int glv;             // G1 scalars are split k = k₁ + k₂·λ (|kᵢ| < 2^128): K covers 129 bits and every base is visited twice
+    int cd, Kd;          // window bits / windows of the δ₁ table (full 254-bit scalars, no split)
     int c2, K2;          // G2 tables (few bases, so a wider window is affordable)
     MsmGroupDev g1[4];   // A, B1, L, H
     MsmGroupDev g2;      // B2
@@ -95,11 +97,13 @@ struct FixedMsmPlan {
 // builds [base][window][digit] tables from affine bases (Montgomery, no infinities)
 void launch_build_table_g1(const G1Affine* d_bases, u32 n, int c, int K, G1Affine* d_table, cudaStream_t s);
 void launch_build_table_g2(const G2Affine* d_bases, u32 n, int c, int K, G2Affine* d_table, cudaStream_t s);
+// self-test of the GLV split: n canonical scalars → n × 36 bytes (|k₁| 16 B, |k₂| 16 B, sign₁, sign₂, 2 pad)
+void launch_glv_split(const uint8_t* d_scalars, size_t n, uint8_t* d_out, cudaStream_t s);
 struct ProverKeyDev {  // fixed points of the proving key (affine, Montgomery)
     G1Affine alpha_g1, beta_g1, delta_g1;
     G2Affine beta_g2, delta_g2;
 };
-struct MsmTask { u32 group, lo, hi, pad; };  // bases [lo, hi) of one group, summed by one thread per proof
+struct MsmTask { u32 group, lo, hi, half; };  // bases [lo, hi) of one group, summed by one thread per proof; half = 1: the k₂ part of a GLV split
 struct MsmWorkspace {
     G1XYZZ* part_g1;  // [tasks][B]
     G2XYZZ* part_g2;

@@ -388,6 +388,7 @@ class Rln {
         *bytes = 0;
         for (int i = 0; i < 5; i++) *bytes += d_tab_[i].bytes;
     }
+    bool glv() const { return plan_.glv != 0; }
     void verify_batch(const uint8_t* proofs128, const uint8_t* publics_circuit_order, size_t n, uint8_t* ok);
     // witness, qap, g1 accumulate, g1 reduce, g2 accumulate, g2 reduce, assemble, proof values
     float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -683,24 +684,34 @@ void Rln::build_tables() {
     size_t n_g1 = pick[0].size() + pick[1].size() + pick[2].size() + pick[3].size(), n_g2 = pick[4].size();
     // Window widths: G1 tables cost 64·K·2^(c−1) bytes per base, G2 tables twice that but have 6× fewer bases, so G2
     // gets the wider window when HBM allows (fewer additions per term: K = ⌈255/c⌉).
+    // G1 scalars are GLV-split (k = k₁ + k₂·λ, |kᵢ| < 2^128): the windows only have to cover 129 bits (c·K > 129) and each
+    // base is visited twice, so c = 13 costs 2 × 10 additions per term where the unsplit form needs 22 at c = 12
+    const bool glv = env_int("RLN_B200_GLV", 1) != 0;
+    auto windows_g1 = [&](int c1) { return glv ? (size_t)(129 / c1 + 1) : (size_t)((255 + c1 - 1) / c1); };
     auto table_bytes = [&](int c1, int c2) {
-        size_t k1 = (255 + c1 - 1) / c1, k2 = (255 + c2 - 1) / c2;
+        size_t k1 = windows_g1(c1), k2 = (255 + c2 - 1) / c2;
         return (n_g1 * 64 * k1 << (c1 - 1)) + (n_g2 * 128 * k2 << (c2 - 1));
     };
     int c = env_int("RLN_B200_WINDOW_BITS", 0), c2 = env_int("RLN_B200_WINDOW_BITS_G2", 0);
     const size_t reserve = (size_t)26 << 30;  // proving workspace, tree, MSM scratch, slack
+    const bool c_auto = c == 0;
     if (c == 0) {
-        for (c = 12; c > 5; c--)
+        for (c = glv ? 13 : 12; c > 5; c--)
             if (table_bytes(c, c2 ? c2 : c) + reserve < free_b) break;
     }
     if (c2 == 0) {
-        for (c2 = c + 2; c2 > c; c2--)
+        const int base2 = glv && c_auto ? 12 : c;
+        for (c2 = base2 + 2; c2 > base2; c2--)
             if (table_bytes(c, c2) + reserve < free_b) break;
     }
     if (c < 5 || c > 16 || c2 < 5 || c2 > 16) throw RlnError("Configuration error: RLN_B200_WINDOW_BITS[_G2] must be in [5, 16]");
-    const int K = (255 + c - 1) / c, K2 = (255 + c2 - 1) / c2;
+    const int K = (int)windows_g1(c), K2 = (255 + c2 - 1) / c2;
+    const int cd = c < 12 ? c : 12, Kd = (255 + cd - 1) / cd;   // δ₁ window table: unsplit scalars
     plan_.c = c;
     plan_.K = K;
+    plan_.glv = glv ? 1 : 0;
+    plan_.cd = cd;
+    plan_.Kd = Kd;
     plan_.c2 = c2;
     plan_.K2 = K2;
     // scalar row of each base: A/B use wire i → node signals[i]; L uses wire ni+i; H uses row i of the h matrix
@@ -738,9 +749,9 @@ void Rln::build_tables() {
         DevMem b1, b2;
         upload_points_g1(zk_.delta_g1, one, b1);
         upload_points_g2(zk_.delta_g2, one, b2);
-        d_delta1_tab_.alloc(sizeof(G1Affine) * K * ((size_t)1 << (c - 1)));
+        d_delta1_tab_.alloc(sizeof(G1Affine) * Kd * ((size_t)1 << (cd - 1)));
         d_delta2_tab_.alloc(sizeof(G2Affine) * K2 * ((size_t)1 << (c2 - 1)));
-        launch_build_table_g1(b1.as<G1Affine>(), 1, c, K, d_delta1_tab_.as<G1Affine>(), 0);
+        launch_build_table_g1(b1.as<G1Affine>(), 1, cd, Kd, d_delta1_tab_.as<G1Affine>(), 0);
         launch_build_table_g2(b2.as<G2Affine>(), 1, c2, K2, d_delta2_tab_.as<G2Affine>(), 0);
         g_launch_count += 4;
         ZK_CUDA_CHECK(cudaDeviceSynchronize());
@@ -1906,6 +1917,18 @@ int rlnb200_get_merkle_proofs(FFI_RLN_t* const* rln, const uint64_t* indices, si
 }
 int rlnb200_debug_witness_and_h(FFI_RLN_t* const* rln, const uint8_t* witness_le, size_t len, uint8_t* w_out, uint8_t* h_out, RlnString* err) {
     INT_OP(std::lock_guard<std::mutex> lk((*rln)->r->mu); Witness w; witness_from_bytes(witness_le, len, w); (*rln)->r->debug_w_h(w, w_out, h_out);)
+}
+int rlnb200_glv_enabled(FFI_RLN_t* const* rln) { return (*rln)->r->glv() ? 1 : 0; }
+int rlnb200_glv_split(const uint8_t* scalars_le, size_t n, uint8_t* out36, RlnString* err) {
+    INT_OP(
+        global_init();
+        DevMem d_in; DevMem d_out;
+        d_in.upload(scalars_le, 32 * n);
+        d_out.alloc(36 * n);
+        launch_glv_split(d_in.as<uint8_t>(), n, d_out.as<uint8_t>(), 0);
+        g_launch_count++;
+        ZK_CUDA_CHECK(cudaMemcpy(out36, d_out.p, 36 * n, cudaMemcpyDeviceToHost));
+    )
 }
 size_t rlnb200_num_wires(FFI_RLN_t* const* rln) { return (*rln)->r->n_wires(); }
 size_t rlnb200_witness_record_len(FFI_RLN_t* const* rln) { return witness_record_len(*(*rln)->r); }

@@ -178,6 +178,8 @@ def lib():
         "rlnb200_domain_size": (c_size_t, [pp]),
         "rlnb200_mul_throughput": (c_double, [c_int]),
         "rlnb200_op_throughput": (c_double, [c_int, c_int]),
+        "rlnb200_glv_enabled": (c_int, [pp]),
+        "rlnb200_glv_split": (c_int, [c_void_p, c_size_t, c_void_p, POINTER(RlnString)]),
         "rlnb200_pipe_probe": (c_int, [c_int, c_int, POINTER(c_double)]),
     }
     for name, (res, args) in sig.items():

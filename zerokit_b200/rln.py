@@ -475,8 +475,10 @@ class RLN:
         c, k, c2, k2 = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         g1, g2, b = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
         ffi.lib().rlnb200_table_info(byref(self._h), byref(c), byref(k), byref(g1), byref(g2), byref(b), byref(c2), byref(k2))
-        return dict(window_bits=c.value, windows=k.value, window_bits_g2=c2.value, windows_g2=k2.value,
-                    g1_bases=g1.value, g2_bases=g2.value, table_bytes=b.value)
+        glv = bool(ffi.lib().rlnb200_glv_enabled(byref(self._h)))
+        # adds_per_term: table entries one (scalar, base) term adds up (each GLV half walks all `windows` windows)
+        return dict(window_bits=c.value, windows=k.value, window_bits_g2=c2.value, windows_g2=k2.value, glv=glv,
+                    adds_per_term=k.value * (2 if glv else 1), g1_bases=g1.value, g2_bases=g2.value, table_bytes=b.value)
 
     def debug_witness_and_h(self, witness_le: bytes):
         nw, dom = ffi.lib().rlnb200_num_wires(byref(self._h)), ffi.lib().rlnb200_domain_size(byref(self._h))
@@ -535,6 +537,19 @@ def field_op(field, op, a_bytes, b_bytes, n):
     err = ffi.RlnString()
     _check_int(ffi.lib().rlnb200_field_op(field, op, a_bytes, b_bytes, n, out, byref(err)), err)
     return out.raw
+
+
+def glv_split(scalars_le: bytes, n):
+    """GLV split kernel self-test: returns [(k1, k2)] as signed Python ints"""
+    out = ctypes.create_string_buffer(36 * n)
+    err = ffi.RlnString()
+    _check_int(ffi.lib().rlnb200_glv_split(scalars_le, n, out, byref(err)), err)
+    res = []
+    for i in range(n):
+        r = out.raw[36 * i:36 * i + 36]
+        k1, k2 = int.from_bytes(r[:16], "little"), int.from_bytes(r[16:32], "little")
+        res.append((-k1 if r[32] else k1, -k2 if r[33] else k2))
+    return res
 
 
 def hash_pairs(pairs_bytes, n):
