@@ -111,6 +111,8 @@ struct MsmWorkspace {
     G2XYZZ* sum_g2;   // [B]
     const MsmTask *tasks_g1, *tasks_g2;  // device arrays built from msm_make_tasks for this B
     u32 n_tasks_g1, n_tasks_g2;
+    u32 n_tasks_g1_no_h;   // the first n tasks (groups A, B1, L) are launched before waiting for h_ready; = n_tasks_g1 when not split
+    cudaEvent_t h_ready;   // optional: recorded when the QAP has written h (the H tasks wait for it)
     cudaEvent_t* ev;  // optional: 6 events recorded around [g1 accum, g1 reduce, g2 accum, g2 reduce, assemble]
 };
 // MSM phases: all bases (full proof), the known prefix of A/B₁/B₂/L (partial proof), or the unknown suffix plus H (finish)

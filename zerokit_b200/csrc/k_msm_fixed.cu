@@ -562,18 +562,26 @@ void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, 
         for (int i = 0; i < 4; i++) { a.row[i] = plan.g1[i].row; a.table[i] = (const G1Affine*)plan.g1[i].table; a.which[i] = plan.g1[i].which_src; }
         a.tasks = ws.tasks_g1; a.part = ws.part_g1; a.B = B; a.c = plan.c; a.K = plan.K; a.glv = plan.glv;
         if (ws.ev) cudaEventRecord(ws.ev[0], s);
-        if (ws.n_tasks_g1) {
-            dim3 grid((B + bx - 1) / bx, ws.n_tasks_g1);
+        auto launch_g1 = [&](u32 first, u32 count) {
+            if (!count) return;
+            AccumArgs<Fq> b = a;
+            b.tasks = ws.tasks_g1 + first;
+            b.part = ws.part_g1 + (size_t)first * B;
+            dim3 grid((B + bx - 1) / bx, count);
             if (plan.glv) {
-                if (accum_variant("RLN_B200_G1_VARIANT") == 1) k_msm_accum<Fq, true, 4, true><<<grid, bx, 0, s>>>(a);
-                else k_msm_accum<Fq, true, 3, true><<<grid, bx, 0, s>>>(a);
+                if (accum_variant("RLN_B200_G1_VARIANT") == 1) k_msm_accum<Fq, true, 4, true><<<grid, bx, 0, s>>>(b);
+                else k_msm_accum<Fq, true, 3, true><<<grid, bx, 0, s>>>(b);
             } else switch (accum_variant("RLN_B200_G1_VARIANT")) {
-                case 1: k_msm_accum<Fq, true, 4><<<grid, bx, 0, s>>>(a); break;
-                case 2: k_msm_accum<Fq, false, 4><<<grid, bx, 0, s>>>(a); break;
-                case 3: k_msm_accum<Fq, false, 3><<<grid, bx, 0, s>>>(a); break;
-                default: k_msm_accum<Fq, true, 3><<<grid, bx, 0, s>>>(a); break;
+                case 1: k_msm_accum<Fq, true, 4><<<grid, bx, 0, s>>>(b); break;
+                case 2: k_msm_accum<Fq, false, 4><<<grid, bx, 0, s>>>(b); break;
+                case 3: k_msm_accum<Fq, false, 3><<<grid, bx, 0, s>>>(b); break;
+                default: k_msm_accum<Fq, true, 3><<<grid, bx, 0, s>>>(b); break;
             }
-        }
+        };
+        const u32 first_part = ws.h_ready && ws.n_tasks_g1_no_h < ws.n_tasks_g1 ? ws.n_tasks_g1_no_h : ws.n_tasks_g1;
+        launch_g1(0, first_part);
+        if (ws.h_ready) ZK_CUDA_CHECK(cudaStreamWaitEvent(s, ws.h_ready, 0));
+        launch_g1(first_part, ws.n_tasks_g1 - first_part);
         if (ws.ev) cudaEventRecord(ws.ev[1], s);
         if (B < 64) k_msm_reduce_small<Fq><<<dim3(B, 4), 128, 0, s>>>(ws.part_g1, ws.tasks_g1, ws.n_tasks_g1, B, ws.sum_g1);
         else k_msm_reduce<Fq><<<dim3((B + bx - 1) / bx, 4), bx, 0, s>>>(ws.part_g1, ws.tasks_g1, ws.n_tasks_g1, B, ws.sum_g1);

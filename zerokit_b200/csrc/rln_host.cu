@@ -389,6 +389,7 @@ class Rln {
         for (int i = 0; i < 5; i++) *bytes += d_tab_[i].bytes;
     }
     bool glv() const { return plan_.glv != 0; }
+    bool overlap_qap_ = false;
     void verify_batch(const uint8_t* proofs128, const uint8_t* publics_circuit_order, size_t n, uint8_t* ok);
     // witness, qap, g1 accumulate, g1 reduce, g2 accumulate, g2 reduce, assemble, proof values
     float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -398,6 +399,7 @@ class Rln {
     struct TaskSet {
         DevMem g1, g2;
         u32 n1 = 0, n2 = 0;
+        u32 n1_no_h = 0;   // leading G1 tasks that do not read h (groups A, B1, L): they can start before the QAP finishes
     };
     TaskSet& tasks_for(u32 B, int phase);
     void compute_known_mask();
@@ -431,8 +433,8 @@ class Rln {
     std::map<u64, std::unique_ptr<TaskSet>> tasks_;
     std::vector<uint8_t> wire_known_, mask_;
     DevMem ws_partial_, ws_partial_comp_;
-    cudaStream_t stream_ = nullptr, side_ = nullptr;
-    cudaEvent_t fork_ = nullptr, join_ = nullptr;
+    cudaStream_t stream_ = nullptr, side_ = nullptr, qap_stream_ = nullptr;
+    cudaEvent_t fork_ = nullptr, join_ = nullptr, qap_done_ = nullptr, qev_[2] = {nullptr, nullptr};
     cudaEvent_t ev_[5];
     cudaEvent_t mev_[6];
 };
@@ -491,6 +493,16 @@ Rln::Rln(size_t tree_depth, const uint8_t* zkey, size_t zlen, const uint8_t* gra
     max_batch_ = (size_t)env_int("RLN_B200_MAX_BATCH", 4096);
     ZK_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     ZK_CUDA_CHECK(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
+    {   // the QAP (HBM-bound) runs beside the first MSM tasks (multiplier-bound); high priority so its CTAs are placed first
+        int lo = 0, hi = 0;
+        ZK_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        ZK_CUDA_CHECK(cudaStreamCreateWithPriority(&qap_stream_, cudaStreamNonBlocking, hi));
+        // measured: the 42 dependent QAP launches starve behind the long-running accumulate CTAs (QAP 25 → 216 ms on its
+        // stream, step 484 → 490 ms), so the overlap is opt-in only
+        overlap_qap_ = env_int("RLN_B200_OVERLAP_QAP", 0) != 0;
+        ZK_CUDA_CHECK(cudaEventCreateWithFlags(&qap_done_, cudaEventDisableTiming));
+        for (auto& e : qev_) ZK_CUDA_CHECK(cudaEventCreate(&e));
+    }
     ZK_CUDA_CHECK(cudaEventCreateWithFlags(&fork_, cudaEventDisableTiming));
     ZK_CUDA_CHECK(cudaEventCreateWithFlags(&join_, cudaEventDisableTiming));
     for (auto& e : ev_) ZK_CUDA_CHECK(cudaEventCreate(&e));
@@ -505,6 +517,9 @@ Rln::~Rln() {
     for (auto& e : mev_) cudaEventDestroy(e);
     if (stream_) cudaStreamDestroy(stream_);
     if (side_) cudaStreamDestroy(side_);
+    if (qap_stream_) cudaStreamDestroy(qap_stream_);
+    if (qap_done_) cudaEventDestroy(qap_done_);
+    for (auto& e : qev_) if (e) cudaEventDestroy(e);
     if (fork_) cudaEventDestroy(fork_);
     if (join_) cudaEventDestroy(join_);
 }
@@ -900,6 +915,8 @@ Rln::TaskSet& Rln::tasks_for(u32 B, int phase) {
     ts->g2.upload(t2.data(), t2.size() * sizeof(MsmTask));
     ts->n1 = (u32)t1.size();
     ts->n2 = (u32)t2.size();
+    for (const MsmTask& t : t1)
+        if (t.group != 3) ts->n1_no_h++;   // msm_make_tasks emits the groups in order, H (group 3) last
     TaskSet& ref = *ts;
     tasks_[key] = std::move(ts);
     return ref;
@@ -963,7 +980,16 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
         ZK_CUDA_CHECK(cudaEventRecord(ev_[0], s));
         launch_witness(circ_, in, ws_vals_.as<Fr>(), B, ws_err_.as<u32>(), s);
         ZK_CUDA_CHECK(cudaEventRecord(ev_[1], s));
-        if (phase != MSM_KNOWN) launch_qap(circ_, ws_vals_.as<Fr>(), ws_a_.as<Fr>(), ws_b_.as<Fr>(), ws_c_.as<Fr>(), B, s);
+        const bool overlap_qap = phase != MSM_KNOWN && overlap_qap_;
+        if (overlap_qap) {   // h is only read by the H tasks: the A / B1 / L tasks start right after the witness
+            ZK_CUDA_CHECK(cudaStreamWaitEvent(qap_stream_, ev_[1], 0));
+            ZK_CUDA_CHECK(cudaEventRecord(qev_[0], qap_stream_));
+            launch_qap(circ_, ws_vals_.as<Fr>(), ws_a_.as<Fr>(), ws_b_.as<Fr>(), ws_c_.as<Fr>(), B, qap_stream_);
+            ZK_CUDA_CHECK(cudaEventRecord(qev_[1], qap_stream_));
+            ZK_CUDA_CHECK(cudaEventRecord(qap_done_, qap_stream_));
+        } else if (phase != MSM_KNOWN) {
+            launch_qap(circ_, ws_vals_.as<Fr>(), ws_a_.as<Fr>(), ws_b_.as<Fr>(), ws_c_.as<Fr>(), B, s);
+        }
         ZK_CUDA_CHECK(cudaEventRecord(ev_[2], s));
         MsmWorkspace mw;
         mw.part_g1 = ws_part1_.as<G1XYZZ>();
@@ -975,6 +1001,8 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
         mw.n_tasks_g1 = ts.n1;
         mw.n_tasks_g2 = ts.n2;
         mw.ev = mev_;
+        mw.n_tasks_g1_no_h = overlap_qap ? ts.n1_no_h : ts.n1;
+        mw.h_ready = overlap_qap ? qap_done_ : nullptr;
         launch_msm_sums(plan_, ws_vals_.as<Fr>(), ws_a_.as<Fr>(), B, mw, s);
         if (phase == MSM_KNOWN) {
             launch_partial_out(pk_, B, mw, d_partial_affine + 320 * off, d_partial_comp + 160 * off, s);
@@ -986,7 +1014,8 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
         ZK_CUDA_CHECK(cudaEventRecord(ev_[3], s));
         if (d_values && phase != MSM_KNOWN) ZK_CUDA_CHECK(cudaStreamWaitEvent(s, join_, 0));
         ZK_CUDA_CHECK(cudaEventRecord(ev_[4], s));
-        g_launch_count += 1 + (phase != MSM_KNOWN ? 2 + 3 * (2 * ntt_launches_per_transform(log_domain_) + 1) : 0) + 6 + (d_values ? 1 : 0);
+        g_launch_count += 1 + (phase != MSM_KNOWN ? 2 + 3 * (2 * ntt_launches_per_transform(log_domain_) + 1) : 0) + 6 + (d_values ? 1 : 0) +
+                          (overlap_qap && ts.n1_no_h && ts.n1_no_h < ts.n1 ? 1 : 0);
         // graph-evaluation failures surface as errors, like WitnessCalcError::GraphEvaluation (rln/src/circuit/iden3calc.rs:52-53)
         std::vector<u32> err(B);
         ZK_CUDA_CHECK(cudaMemcpyAsync(err.data(), ws_err_.p, 4 * B, cudaMemcpyDeviceToHost, s));
@@ -994,7 +1023,8 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
         {
             float ms = 0;
             cudaEventElapsedTime(&ms, ev_[0], ev_[1]); acc[0] += ms;
-            cudaEventElapsedTime(&ms, ev_[1], ev_[2]); acc[1] += ms;
+            if (overlap_qap) cudaEventElapsedTime(&ms, qev_[0], qev_[1]); else cudaEventElapsedTime(&ms, ev_[1], ev_[2]);
+            acc[1] += ms;   // with the overlap this is the QAP's own duration on its stream, hidden behind the first G1 tasks
             for (int i = 0; i < 5; i++) { cudaEventElapsedTime(&ms, mev_[i], mev_[i + 1]); acc[2 + i] += ms; }
             cudaEventElapsedTime(&ms, ev_[3], ev_[4]); acc[7] += ms;
         }
