@@ -62,6 +62,7 @@ typedef struct CResult_FFI_MerkleProof { FFI_MerkleProof_t *ok; RlnString err; }
 typedef struct CResult_CFr { CFr_t *ok; RlnString err; } CResult_CFr_t;
 typedef struct CResult_Vec_uint8 { Vec_uint8_t ok; RlnString err; } CResult_Vec_uint8_t;
 typedef struct CResult_Vec_CFr { Vec_CFr_t ok; RlnString err; } CResult_Vec_CFr_t;
+typedef struct CResult_String { RlnString ok; RlnString err; } CResult_String_t;
 
 /* ------------------------------------------------------------------ RLN object (rln/src/ffi/ffi_rln.rs) */
 CResult_FFI_RLN_t ffi_rln_new(size_t tree_depth, const char *config_path);                      /* :22-57  */
@@ -164,6 +165,59 @@ CFr_t *ffi_hash_to_field_le(const Vec_uint8_t *input);                          
 CFr_t *ffi_hash_to_field_be(const Vec_uint8_t *input);                                          /* :353-356 */
 CFr_t *ffi_poseidon_hash_pair(const CFr_t *a, const CFr_t *b);                                  /* :358-361 */
 Vec_CFr_t ffi_key_gen(void);                                                                    /* :365-369 */
+Vec_CFr_t ffi_seeded_key_gen(const Vec_uint8_t *seed);                                          /* :371-377 */
+Vec_CFr_t ffi_extended_key_gen(void);                                                           /* :379-389: trapdoor, nullifier, secret, commitment */
+Vec_CFr_t ffi_seeded_extended_key_gen(const Vec_uint8_t *seed);                                 /* :391-404 */
+CResult_Vec_uint8_t ffi_vec_cfr_to_bytes_le(const Vec_CFr_t *v);                                /* :187-201: u64 LE count | 32-byte LE elements */
+CResult_Vec_uint8_t ffi_vec_cfr_to_bytes_be(const Vec_CFr_t *v);                                /* :203-217: u64 BE count | 32-byte BE elements */
+CResult_Vec_CFr_t ffi_bytes_le_to_vec_cfr(const Vec_uint8_t *bytes);                            /* :219-236 */
+CResult_Vec_CFr_t ffi_bytes_be_to_vec_cfr(const Vec_uint8_t *bytes);                            /* :238-255 */
+RlnString ffi_vec_cfr_debug(const Vec_CFr_t *v);                                                /* :257-266 */
+CResult_Vec_uint8_t ffi_vec_u8_to_bytes_le(const Vec_uint8_t *v);                               /* :275-288 */
+CResult_Vec_uint8_t ffi_vec_u8_to_bytes_be(const Vec_uint8_t *v);                               /* :290-303 */
+CResult_Vec_uint8_t ffi_bytes_le_to_vec_u8(const Vec_uint8_t *bytes);                           /* :305-317 */
+CResult_Vec_uint8_t ffi_bytes_be_to_vec_u8(const Vec_uint8_t *bytes);                           /* :319-331 */
+RlnString ffi_vec_u8_debug(const Vec_uint8_t *v);                                               /* :333-339 */
+
+/* ---- rln/src/ffi/ffi_rln.rs, continued: record getters, big-endian wire formats, partial-witness records, identity-secret
+ * recovery; rln/src/ffi/ffi_tree.rs:226-268 metadata.  Getters on the wrong variant abort like the reference's todo!(). */
+uint8_t ffi_rln_witness_input_get_version_byte(FFI_RLNWitnessInput_t *const *witness);           /* ffi_rln.rs:398-401 */
+CFr_t *ffi_rln_witness_input_get_identity_secret(FFI_RLNWitnessInput_t *const *witness);         /* :403-408 */
+CFr_t *ffi_rln_witness_input_get_user_message_limit(FFI_RLNWitnessInput_t *const *witness);      /* :410-415 */
+CFr_t *ffi_rln_witness_input_get_message_id(FFI_RLNWitnessInput_t *const *witness);              /* :417-422 (SingleV1) */
+Vec_CFr_t ffi_rln_witness_input_get_message_ids(FFI_RLNWitnessInput_t *const *witness);          /* :424-435 (MultiV1) */
+Vec_CFr_t ffi_rln_witness_input_get_path_elements(FFI_RLNWitnessInput_t *const *witness);        /* :437-448 */
+Vec_uint8_t ffi_rln_witness_input_get_identity_path_index(FFI_RLNWitnessInput_t *const *witness);/* :450-455 */
+CFr_t *ffi_rln_witness_input_get_x(FFI_RLNWitnessInput_t *const *witness);                       /* :457-460 */
+CFr_t *ffi_rln_witness_input_get_external_nullifier(FFI_RLNWitnessInput_t *const *witness);      /* :462-467 */
+Vec_bool_t ffi_rln_witness_input_get_selector_used(FFI_RLNWitnessInput_t *const *witness);       /* :469-474 (MultiV1) */
+CResult_Vec_uint8_t ffi_rln_witness_to_bytes_be(FFI_RLNWitnessInput_t *const *witness);          /* :492-506 */
+CResult_FFI_RLNWitnessInput_t ffi_bytes_be_to_rln_witness(const Vec_uint8_t *bytes);             /* :524-538 */
+CResult_String_t ffi_rln_witness_to_bigint_json(FFI_RLNWitnessInput_t *const *witness);          /* :540-554 */
+uint8_t ffi_rln_partial_witness_input_get_version_byte(FFI_RLNPartialWitnessInput_t *const *w);  /* :594-599 */
+CFr_t *ffi_rln_partial_witness_input_get_identity_secret(FFI_RLNPartialWitnessInput_t *const *w);/* :601-606 */
+CFr_t *ffi_rln_partial_witness_input_get_user_message_limit(FFI_RLNPartialWitnessInput_t *const *w); /* :608-613 */
+Vec_CFr_t ffi_rln_partial_witness_input_get_path_elements(FFI_RLNPartialWitnessInput_t *const *w);   /* :615-626 */
+Vec_uint8_t ffi_rln_partial_witness_input_get_identity_path_index(FFI_RLNPartialWitnessInput_t *const *w); /* :628-633 */
+FFI_RLNPartialWitnessInput_t *ffi_rln_witness_to_partial_witness(FFI_RLNWitnessInput_t *const *witness);  /* :635-641 */
+CResult_Vec_uint8_t ffi_rln_partial_witness_to_bytes_le(FFI_RLNPartialWitnessInput_t *const *w); /* :643-657 */
+CResult_Vec_uint8_t ffi_rln_partial_witness_to_bytes_be(FFI_RLNPartialWitnessInput_t *const *w); /* :659-673 */
+CResult_FFI_RLNPartialWitnessInput_t ffi_bytes_le_to_rln_partial_witness(const Vec_uint8_t *bytes); /* :675-689 */
+CResult_FFI_RLNPartialWitnessInput_t ffi_bytes_be_to_rln_partial_witness(const Vec_uint8_t *bytes); /* :691-705 */
+Vec_uint8_t ffi_rln_proof_values_to_bytes_be(FFI_RLNProofValues_t *const *pv);                   /* :807-810 */
+CResult_FFI_RLNProofValues_t ffi_bytes_be_to_rln_proof_values(const Vec_uint8_t *bytes);         /* :828-842 */
+CResult_FFI_RLNProof_t ffi_bytes_be_to_rln_proof(const Vec_uint8_t *bytes);                      /* :217-231 */
+uint8_t ffi_rln_partial_proof_get_version_byte(FFI_RLNPartialProof_t *const *partial_proof);     /* :244-249 */
+CResult_Vec_uint8_t ffi_rln_partial_proof_to_bytes_be(FFI_RLNPartialProof_t *const *partial_proof); /* :288-302 (= LE form) */
+CResult_FFI_RLNPartialProof_t ffi_bytes_le_to_rln_partial_proof(const Vec_uint8_t *bytes);       /* :267-281 */
+CResult_FFI_RLNPartialProof_t ffi_bytes_be_to_rln_partial_proof(const Vec_uint8_t *bytes);       /* :304-318 */
+CResult_CFr_t ffi_compute_id_secret(const CFr_t *share1_x, const CFr_t *share1_y, const CFr_t *share2_x,
+                                    const CFr_t *share2_y);                                      /* :1014-1033 */
+CResult_CFr_t ffi_recover_id_secret(FFI_RLNProofValues_t *const *proof_values_1,
+                                    FFI_RLNProofValues_t *const *proof_values_2);                /* :1035-1049 */
+CBoolResult_t ffi_set_metadata(FFI_RLN_t **rln, const Vec_uint8_t *metadata);                    /* ffi_tree.rs:228-240 */
+CResult_Vec_uint8_t ffi_get_metadata(FFI_RLN_t *const *rln);                                     /* ffi_tree.rs:242-254 */
+CBoolResult_t ffi_flush(FFI_RLN_t **rln);                                                        /* ffi_tree.rs:256-268 */
 
 /* ================================================================== extensions (not in the reference) */
 
@@ -175,7 +229,7 @@ CResult_FFI_RLNProof_t rlnb200_generate_rln_proof_with_rs(FFI_RLN_t *const *rln,
 /* finish_zk_proof_with_rs (rln/src/protocol/proof.rs:822-849) behind the ABI */
 CResult_FFI_RLNProof_t rlnb200_finish_rln_proof_with_rs(FFI_RLN_t *const *rln, FFI_RLNPartialProof_t *const *partial_proof,
                                                         FFI_RLNWitnessInput_t *const *witness, const CFr_t *r, const CFr_t *s);
-/* ffi_bytes_le_to_rln_partial_proof (ffi_rln.rs:267-281) needs a handle here: the points are validated on the GPU */
+/* ffi_bytes_le_to_rln_partial_proof with a handle (serialises with that handle's other GPU work) */
 CResult_FFI_RLNPartialProof_t rlnb200_bytes_le_to_rln_partial_proof(FFI_RLN_t *const *rln, const Vec_uint8_t *bytes);
 /* batched two-phase proving on host buffers: witness records as for rlnb200_prove_batch (message_id / x / external_nullifier
  * are ignored by the partial phase); partial points are n × 320 bytes (canonical affine π_a 64 | ρ 64 | π_b 128 | π_c 64) */

@@ -410,6 +410,54 @@ def test_partial_proofs(z, rln10, rln20, goldens, oracle):
     assert rln20.verify_batch(out2, n) == [1] * n
 
 
+def test_seeded_keygen_kats(z, goldens):
+    """rln/tests/protocol.rs:459-507 and rln/tests/ffi_utils.rs:8-69 (the commitment is hashed on the GPU)"""
+    k = goldens["ref"]["seeded_keygen"]
+    assert z.seeded_keygen(k["phrase"]["seed_utf8"].encode()) == (int(k["phrase"]["identity_secret"], 16), int(k["phrase"]["id_commitment"], 16))
+    assert z.seeded_keygen(bytes.fromhex(k["bytes"]["seed_hex"])) == (int(k["bytes"]["identity_secret"], 16), int(k["bytes"]["id_commitment"], 16))
+    e = k["extended_bytes"]
+    assert z.extended_seeded_keygen(bytes.fromhex(e["seed_hex"])) == tuple(
+        int(e[f], 16) for f in ("identity_trapdoor", "identity_nullifier", "identity_secret", "id_commitment"))
+    # random variants: the relations of rln/tests/protocol.rs:509-520
+    sec, com = z.keygen()
+    assert com == z.poseidon_hash([sec]) and 0 < sec < R
+    t, n, sec, com = z.extended_keygen()
+    assert sec == z.poseidon_hash_pair(t, n) and com == z.poseidon_hash([sec])
+
+
+def test_big_endian_proof_records_and_metadata(z, rln10, goldens):
+    """rln/tests/serialize.rs round trips for the records that need the GPU to parse (point validation)"""
+    k = goldens["derived"]["kat_proof_d10"]
+    args = kat_witness_args(10, k["inputs"])
+    wit = z.RLNWitnessInput.from_bytes_le(witness_le(*args))
+    proof = rln10.generate_rln_proof_with_rs(wit, int(k["inputs"]["r"]), int(k["inputs"]["s"]))
+    le, be = proof.to_bytes_le(), proof.to_bytes_be()
+    assert be[:129] == le[:129] and be[129] == le[129]
+    assert [be[130 + 32 * i:162 + 32 * i] for i in range(5)] == [le[130 + 32 * i:162 + 32 * i][::-1] for i in range(5)]
+    assert z.RLNProof.from_bytes_be(be).to_bytes_le() == le
+    with pytest.raises(z.RLNError, match="Expected to read"):
+        z.RLNProof.from_bytes_be(be + b"\0")
+    with pytest.raises(z.RLNError):
+        z.RLNProof.from_bytes_be(be[:140])
+    pw = wit.to_partial()
+    partial = rln10.generate_partial_zk_proof(pw)
+    pb = partial.to_bytes_le()
+    assert partial.to_bytes_be() == pb and partial.version_byte == 0
+    for parsed in (z.RLNPartialProof.from_bytes_le(pb), z.RLNPartialProof.from_bytes_be(pb)):   # handle-free parse
+        assert parsed.to_bytes_le() == pb
+        fin = rln10.finish_rln_proof_with_rs(parsed, wit, int(k["inputs"]["r"]), int(k["inputs"]["s"]))
+        assert fin.to_bytes_le().hex() == k["rln_proof_le_hex"]
+    bad = bytearray(pb)
+    bad[-1] ^= 0x3f
+    with pytest.raises(z.RLNError, match="invalid data"):
+        z.RLNPartialProof.from_bytes_le(bytes(bad))
+    # metadata / flush (rln/src/ffi/ffi_tree.rs:226-268)
+    assert rln10.get_metadata() == b""
+    rln10.set_metadata(b"block 1234")
+    assert rln10.get_metadata() == b"block 1234"
+    rln10.flush()
+
+
 def test_multi_message_id_circuit(z, goldens, oracle):
     """the bundled max_out = 4 circuit (rln/resources/tree_depth_20/multi_message_id): golden proof, verification, mode checks"""
     k = goldens["derived"]["kat_proof_multi_d20"]

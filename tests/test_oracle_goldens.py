@@ -81,3 +81,14 @@ def test_compressed_encoding_roundtrip(goldens):
     assert G.g1_decompress(G.g1_compress(a)) == a
     assert G.g1_compress(a).hex() == k["proof_bytes_hex"][:64]
     assert F.on_curve(F.OPS1, a)
+
+
+def test_seeded_keygen_kats(goldens):
+    """rln/tests/protocol.rs:459-507, rln/tests/ffi_utils.rs:8-69: pins the ChaCha20Rng + Fr::rand restatement"""
+    from pyref import keygen as K
+    k = goldens["ref"]["seeded_keygen"]
+    assert K.seeded_keygen(k["phrase"]["seed_utf8"].encode()) == (int(k["phrase"]["identity_secret"], 16), int(k["phrase"]["id_commitment"], 16))
+    assert K.seeded_keygen(bytes.fromhex(k["bytes"]["seed_hex"])) == (int(k["bytes"]["identity_secret"], 16), int(k["bytes"]["id_commitment"], 16))
+    e = k["extended_bytes"]
+    assert K.extended_seeded_keygen(bytes.fromhex(e["seed_hex"])) == tuple(
+        int(e[f], 16) for f in ("identity_trapdoor", "identity_nullifier", "identity_secret", "id_commitment"))

@@ -1,0 +1,141 @@
+"""CPU: the host-side wire formats of the C ABI (big-endian records, partial-witness records, Vec helpers, JSON, getters)
+against the oracle's restatement of rln/src/utils.rs and rln/src/protocol/{witness,proof}.rs.  Mirrors the round-trip tests of
+rln/tests/serialize.rs and the Shamir recovery of rln/tests/protocol.rs; nothing here launches a kernel."""
+import json
+import random
+
+import pytest
+
+from common import R, fr_stream
+from pyref import keygen as K
+from pyref import serialize as S
+
+
+@pytest.fixture(scope="module")
+def z():
+    import zerokit_b200
+    return zerokit_b200
+
+
+def _witness_args(seed, depth=20):
+    fs = fr_stream(seed)
+    limit = 100
+    return dict(secret=next(fs), limit=limit, mid=7, path=[next(fs) for _ in range(depth)], idx=[(3 * i + seed) % 2 for i in range(depth)],
+                x=next(fs), en=next(fs))
+
+
+def test_witness_be_le_and_getters(z):
+    for seed, depth in ((1, 20), (2, 10), (3, 0)):
+        a = _witness_args(seed, depth)
+        w = z.RLNWitnessInput.new_single(a["secret"], a["limit"], a["mid"], a["path"], a["idx"], a["x"], a["en"])
+        le = S.witness_to_bytes(a["secret"], a["limit"], a["mid"], a["path"], a["idx"], a["x"], a["en"], be=False)
+        be = S.witness_to_bytes(a["secret"], a["limit"], a["mid"], a["path"], a["idx"], a["x"], a["en"], be=True)
+        assert w.to_bytes_le() == le and w.to_bytes_be() == be
+        assert z.RLNWitnessInput.from_bytes_be(be).to_bytes_le() == le
+        assert z.RLNWitnessInput.from_bytes_le(le).to_bytes_be() == be
+        assert (w.version_byte, w.identity_secret, w.user_message_limit, w.message_id) == (0, a["secret"], a["limit"], a["mid"])
+        assert (w.path_elements, w.identity_path_index, w.x, w.external_nullifier) == (a["path"], a["idx"], a["x"], a["en"])
+        assert w.to_bigint_json() == S.witness_to_bigint_json(a["secret"], a["limit"], a["mid"], a["path"], a["idx"], a["x"], a["en"])
+        assert json.loads(w.to_bigint_json())["pathElements"] == [str(v) for v in a["path"]]
+    # errors: truncated, trailing bytes, non-canonical element, unknown mode byte, message id out of range
+    with pytest.raises(z.RLNError, match="too short"):
+        z.RLNWitnessInput.from_bytes_be(be[:-5])
+    with pytest.raises(z.RLNError, match="Expected to read"):
+        z.RLNWitnessInput.from_bytes_be(be + b"\0")
+    with pytest.raises(z.RLNError, match="Non-canonical field element"):
+        z.RLNWitnessInput.from_bytes_be(be[:1] + R.to_bytes(32, "big") + be[33:])
+    with pytest.raises(z.RLNError, match="Unknown message mode version byte: 0x07"):
+        z.RLNWitnessInput.from_bytes_be(b"\x07" + be[1:])
+    bad = S.witness_to_bytes(a["secret"], 5, 5, a["path"], a["idx"], a["x"], a["en"], be=True)
+    with pytest.raises(z.RLNError, match="is not within user_message_limit"):
+        z.RLNWitnessInput.from_bytes_be(bad)
+
+
+def test_witness_multi_be(z):
+    a = _witness_args(4, 20)
+    mids, sel = [1, 2, 3, 0], [True, True, False, False]
+    w = z.RLNWitnessInput.new_multi(a["secret"], a["limit"], mids, a["path"], a["idx"], a["x"], a["en"], sel)
+    le = S.witness_to_bytes_multi(a["secret"], a["limit"], mids, a["path"], a["idx"], a["x"], a["en"], sel, be=False)
+    be = S.witness_to_bytes_multi(a["secret"], a["limit"], mids, a["path"], a["idx"], a["x"], a["en"], sel, be=True)
+    assert w.to_bytes_le() == le and w.to_bytes_be() == be
+    assert z.RLNWitnessInput.from_bytes_be(be).to_bytes_le() == le
+    assert (w.version_byte, w.message_ids, w.selector_used) == (1, mids, sel)
+    j = json.loads(w.to_bigint_json())
+    assert j["messageId"] == [str(v) for v in mids] and j["selectorUsed"] == ["1", "1", "0", "0"]
+
+
+def test_partial_witness_records(z):
+    a = _witness_args(5, 20)
+    pw = z.RLNPartialWitnessInput.new(a["secret"], a["limit"], a["path"], a["idx"])
+    le = S.partial_witness_to_bytes(a["secret"], a["limit"], a["path"], a["idx"], be=False)
+    be = S.partial_witness_to_bytes(a["secret"], a["limit"], a["path"], a["idx"], be=True)
+    assert pw.to_bytes_le() == le and pw.to_bytes_be() == be
+    assert z.RLNPartialWitnessInput.from_bytes_le(le).to_bytes_be() == be
+    assert z.RLNPartialWitnessInput.from_bytes_be(be).to_bytes_le() == le
+    assert (pw.version_byte, pw.identity_secret, pw.user_message_limit, pw.path_elements, pw.identity_path_index) == \
+        (0, a["secret"], a["limit"], a["path"], a["idx"])
+    # From<&RLNWitnessInput> (witness.rs:305-314)
+    w = z.RLNWitnessInput.new_single(a["secret"], a["limit"], a["mid"], a["path"], a["idx"], a["x"], a["en"])
+    assert w.to_partial().to_bytes_le() == le
+    with pytest.raises(z.RLNError, match="Expected to read"):
+        z.RLNPartialWitnessInput.from_bytes_le(le + b"\x01")
+    with pytest.raises(z.RLNError, match="User message limit cannot be zero"):
+        z.RLNPartialWitnessInput.from_bytes_le(S.partial_witness_to_bytes(a["secret"], 0, a["path"], a["idx"]))
+
+
+def test_proof_values_be(z):
+    fs = fr_stream(6)
+    root, en, x, y, nul = (next(fs) for _ in range(5))
+    le, be = S.proof_values_to_bytes(root, en, x, y, nul), S.proof_values_to_bytes(root, en, x, y, nul, be=True)
+    assert z.proof_values_le_to_be(le) == be and z.proof_values_be_to_le(be) == le
+    ys, nulls, sel = [next(fs) for _ in range(4)], [next(fs) for _ in range(4)], [1, 0, 1, 1]
+    le = S.proof_values_to_bytes_multi(root, en, x, ys, nulls, sel)
+    be = S.proof_values_to_bytes_multi(root, en, x, ys, nulls, sel, be=True)
+    assert z.proof_values_le_to_be(le) == be and z.proof_values_be_to_le(be) == le
+    with pytest.raises(z.RLNError, match="too short"):
+        z.proof_values_be_to_le(be[:-1])
+
+
+def test_vec_helpers(z):
+    fs = fr_stream(7)
+    for n in (0, 1, 5):
+        vals = [next(fs) for _ in range(n)]
+        for be in (False, True):
+            b = z.vec_fr_to_bytes(vals, be)
+            assert b == S.vec_fr(vals, be) and z.bytes_to_vec_fr(b, be) == vals
+        raw = bytes(range(n))
+        for be in (False, True):
+            b = z.vec_u8_to_bytes(raw, be)
+            assert b == S.vec_u8(raw, be) and z.bytes_to_vec_u8(b, be) == raw
+    with pytest.raises(z.RLNError):
+        z.bytes_to_vec_fr(S.vec_fr([1, 2], True)[:-1], True)
+    with pytest.raises(z.RLNError, match="Non-canonical"):
+        z.bytes_to_vec_fr(S.vec_fr([R], True), True)
+    with pytest.raises(z.RLNError):
+        z.bytes_to_vec_u8(b"\x09" + b"\0" * 7 + b"abc", False)
+
+
+def test_compute_and_recover_id_secret(z):
+    """rln/src/protocol/slashing.rs; property test as in rln/tests/protocol.rs (two shares of one line → a0)"""
+    rnd = random.Random(8)
+    for _ in range(20):
+        a0, a1, x1, x2 = (rnd.randrange(R) for _ in range(4))
+        s1, s2 = (x1, (a0 + x1 * a1) % R), (x2, (a0 + x2 * a1) % R)
+        assert z.compute_id_secret(s1, s2) == a0 == K.compute_id_secret(s1, s2)
+    with pytest.raises(z.RLNError, match="division by zero"):
+        z.compute_id_secret((5, 1), (5, 2))
+    a0, a1, en, root, nul = (rnd.randrange(R) for _ in range(5))
+    pv = [S.proof_values_to_bytes(root, en, x, (a0 + x * a1) % R, nul) for x in (11, 12)]
+    assert z.recover_id_secret(pv[0], pv[1]) == a0
+    other = S.proof_values_to_bytes(root, (en + 1) % R, 13, (a0 + 13 * a1) % R, nul)
+    with pytest.raises(z.RLNError, match="External nullifiers mismatch"):
+        z.recover_id_secret(pv[0], other)
+    # multi: the first pair of used slots sharing a nullifier gives the shares
+    m1 = S.proof_values_to_bytes_multi(root, en, 21, [(a0 + 21 * a1) % R, 5], [nul, 77], [1, 1])
+    m2 = S.proof_values_to_bytes_multi(root, en, 22, [9, (a0 + 22 * a1) % R], [78, nul], [1, 1])
+    assert z.recover_id_secret(m1, m2) == a0
+    m3 = S.proof_values_to_bytes_multi(root, en, 22, [9, (a0 + 22 * a1) % R], [78, nul], [1, 0])
+    with pytest.raises(z.RLNError, match="No matching nullifier"):
+        z.recover_id_secret(m1, m3)
+    with pytest.raises(z.RLNError, match="No matching nullifier"):
+        z.recover_id_secret(pv[0], m2)

@@ -22,7 +22,7 @@ def _headers_mtime():
     m = 0.0
     for d in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
         for f in os.listdir(d):
-            if f.endswith((".cuh", ".hpp", ".h")):
+            if f.endswith((".cuh", ".hpp", ".h", ".inc")):
                 m = max(m, os.path.getmtime(os.path.join(d, f)))
     return m
 

@@ -389,6 +389,8 @@ class Rln {
         for (int i = 0; i < 5; i++) *bytes += d_tab_[i].bytes;
     }
     bool glv() const { return plan_.glv != 0; }
+    std::vector<uint8_t> metadata;   // set_metadata / get_metadata (rln/src/public.rs:499-515): opaque bytes kept beside the tree
+    void sync() { ZK_CUDA_CHECK(cudaStreamSynchronize(stream_)); }   // flush: nothing is buffered outside HBM
     bool overlap_qap_ = false;
     void verify_batch(const uint8_t* proofs128, const uint8_t* publics_circuit_order, size_t n, uint8_t* ok);
     // witness, qap, g1 accumulate, g1 reduce, g2 accumulate, g2 reduce, assemble, proof values
@@ -1832,6 +1834,8 @@ Vec_CFr_t ffi_key_gen(void) {  // keygen (rln/src/protocol/keygen.rs:20-30): sec
     v.len = 2;
     return v;
 }
+
+#include "rln_ffi_more.inc"
 
 // ---- extensions -------------------------------------------------------------------------------
 #define INT_OP(...)                                            \

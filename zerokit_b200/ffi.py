@@ -52,6 +52,7 @@ CResult_MerkleProof = _cresult("CResult_MerkleProof", POINTER(FFI_MerkleProof))
 CResult_CFr = _cresult("CResult_CFr", POINTER(CFr))
 CResult_Vec_uint8 = _cresult("CResult_Vec_uint8", Vec_uint8)
 CResult_Vec_CFr = _cresult("CResult_Vec_CFr", Vec_CFr)
+CResult_String = _cresult("CResult_String", RlnString)
 
 _lib = None
 
@@ -138,6 +139,54 @@ def lib():
         "ffi_finish_rln_proof": (CResult_ptr, [pp, pp, pp]),
         "ffi_rln_partial_proof_to_bytes_le": (CResult_Vec_uint8, [pp]),
         "ffi_rln_partial_proof_free": (None, [c_void_p]),
+        "ffi_seeded_key_gen": (Vec_CFr, [POINTER(Vec_uint8)]),
+        "ffi_extended_key_gen": (Vec_CFr, []),
+        "ffi_seeded_extended_key_gen": (Vec_CFr, [POINTER(Vec_uint8)]),
+        "ffi_vec_cfr_to_bytes_le": (CResult_Vec_uint8, [POINTER(Vec_CFr)]),
+        "ffi_vec_cfr_to_bytes_be": (CResult_Vec_uint8, [POINTER(Vec_CFr)]),
+        "ffi_bytes_le_to_vec_cfr": (CResult_Vec_CFr, [POINTER(Vec_uint8)]),
+        "ffi_bytes_be_to_vec_cfr": (CResult_Vec_CFr, [POINTER(Vec_uint8)]),
+        "ffi_vec_cfr_debug": (RlnString, [POINTER(Vec_CFr)]),
+        "ffi_vec_u8_to_bytes_le": (CResult_Vec_uint8, [POINTER(Vec_uint8)]),
+        "ffi_vec_u8_to_bytes_be": (CResult_Vec_uint8, [POINTER(Vec_uint8)]),
+        "ffi_bytes_le_to_vec_u8": (CResult_Vec_uint8, [POINTER(Vec_uint8)]),
+        "ffi_bytes_be_to_vec_u8": (CResult_Vec_uint8, [POINTER(Vec_uint8)]),
+        "ffi_vec_u8_debug": (RlnString, [POINTER(Vec_uint8)]),
+        "ffi_rln_witness_input_get_version_byte": (c_uint8, [pp]),
+        "ffi_rln_witness_input_get_identity_secret": (POINTER(CFr), [pp]),
+        "ffi_rln_witness_input_get_user_message_limit": (POINTER(CFr), [pp]),
+        "ffi_rln_witness_input_get_message_id": (POINTER(CFr), [pp]),
+        "ffi_rln_witness_input_get_message_ids": (Vec_CFr, [pp]),
+        "ffi_rln_witness_input_get_path_elements": (Vec_CFr, [pp]),
+        "ffi_rln_witness_input_get_identity_path_index": (Vec_uint8, [pp]),
+        "ffi_rln_witness_input_get_x": (POINTER(CFr), [pp]),
+        "ffi_rln_witness_input_get_external_nullifier": (POINTER(CFr), [pp]),
+        "ffi_rln_witness_input_get_selector_used": (Vec_bool, [pp]),
+        "ffi_rln_witness_to_bytes_be": (CResult_Vec_uint8, [pp]),
+        "ffi_bytes_be_to_rln_witness": (CResult_ptr, [POINTER(Vec_uint8)]),
+        "ffi_rln_witness_to_bigint_json": (CResult_String, [pp]),
+        "ffi_rln_partial_witness_input_get_version_byte": (c_uint8, [pp]),
+        "ffi_rln_partial_witness_input_get_identity_secret": (POINTER(CFr), [pp]),
+        "ffi_rln_partial_witness_input_get_user_message_limit": (POINTER(CFr), [pp]),
+        "ffi_rln_partial_witness_input_get_path_elements": (Vec_CFr, [pp]),
+        "ffi_rln_partial_witness_input_get_identity_path_index": (Vec_uint8, [pp]),
+        "ffi_rln_witness_to_partial_witness": (c_void_p, [pp]),
+        "ffi_rln_partial_witness_to_bytes_le": (CResult_Vec_uint8, [pp]),
+        "ffi_rln_partial_witness_to_bytes_be": (CResult_Vec_uint8, [pp]),
+        "ffi_bytes_le_to_rln_partial_witness": (CResult_ptr, [POINTER(Vec_uint8)]),
+        "ffi_bytes_be_to_rln_partial_witness": (CResult_ptr, [POINTER(Vec_uint8)]),
+        "ffi_rln_proof_values_to_bytes_be": (Vec_uint8, [pp]),
+        "ffi_bytes_be_to_rln_proof_values": (CResult_ptr, [POINTER(Vec_uint8)]),
+        "ffi_bytes_be_to_rln_proof": (CResult_ptr, [POINTER(Vec_uint8)]),
+        "ffi_rln_partial_proof_get_version_byte": (c_uint8, [pp]),
+        "ffi_rln_partial_proof_to_bytes_be": (CResult_Vec_uint8, [pp]),
+        "ffi_bytes_le_to_rln_partial_proof": (CResult_ptr, [POINTER(Vec_uint8)]),
+        "ffi_bytes_be_to_rln_partial_proof": (CResult_ptr, [POINTER(Vec_uint8)]),
+        "ffi_compute_id_secret": (CResult_CFr, [POINTER(CFr)] * 4),
+        "ffi_recover_id_secret": (CResult_CFr, [pp, pp]),
+        "ffi_set_metadata": (CBoolResult, [pp, POINTER(Vec_uint8)]),
+        "ffi_get_metadata": (CResult_Vec_uint8, [pp]),
+        "ffi_flush": (CBoolResult, [pp]),
         # extensions
         "rlnb200_finish_rln_proof_with_rs": (CResult_ptr, [pp, pp, pp, POINTER(CFr), POINTER(CFr)]),
         "rlnb200_bytes_le_to_rln_partial_proof": (CResult_ptr, [pp, POINTER(Vec_uint8)]),

@@ -70,6 +70,27 @@ def _take_vec_u8(v):
     return out
 
 
+def _take_vec_cfr(v):
+    out = [_cfr_int(v.ptr[i]) for i in range(v.len)]
+    if v.ptr:
+        ffi.lib().ffi_vec_cfr_free(v)
+    return out
+
+
+def _ok_bytes(res):
+    msg = _take_string(res.err)
+    if msg is not None:
+        raise RLNError(msg)
+    return _take_vec_u8(res.ok)
+
+
+def _ok_cfr(res):
+    msg = _take_string(res.err)
+    if msg is not None or not res.ok:
+        raise RLNError(msg or "null result")
+    return _take_cfr(res.ok)
+
+
 def _check_bool(res):
     msg = _take_string(res.err)
     if msg is not None:
@@ -114,10 +135,85 @@ def poseidon_hash(inputs) -> int:
 
 
 def keygen():
-    v = ffi.lib().ffi_key_gen()
-    out = (_cfr_int(v.ptr[0]), _cfr_int(v.ptr[1]))
-    ffi.lib().ffi_vec_cfr_free(v)
-    return out
+    """rln/src/protocol/keygen.rs:13-21 → (identity_secret, id_commitment)"""
+    return tuple(_take_vec_cfr(ffi.lib().ffi_key_gen()))
+
+
+def seeded_keygen(seed: bytes):
+    """keygen.rs:44-58: Keccak-256(seed) → ChaCha20 → Fr::rand"""
+    return tuple(_take_vec_cfr(ffi.lib().ffi_seeded_key_gen(byref(_vec_u8(seed)))))
+
+
+def extended_keygen():
+    """keygen.rs:23-38 → (trapdoor, nullifier, identity_secret, id_commitment)"""
+    return tuple(_take_vec_cfr(ffi.lib().ffi_extended_key_gen()))
+
+
+def extended_seeded_keygen(seed: bytes):
+    """keygen.rs:64-91"""
+    return tuple(_take_vec_cfr(ffi.lib().ffi_seeded_extended_key_gen(byref(_vec_u8(seed)))))
+
+
+def compute_id_secret(share1, share2) -> int:
+    """rln/src/protocol/slashing.rs:7-33: shares are (x, y) pairs"""
+    return _ok_cfr(ffi.lib().ffi_compute_id_secret(byref(_cfr(share1[0])), byref(_cfr(share1[1])), byref(_cfr(share2[0])), byref(_cfr(share2[1]))))
+
+
+def recover_id_secret(proof_values_1_le: bytes, proof_values_2_le: bytes) -> int:
+    """slashing.rs:35-100 on two serialized RLNProofValues (rln_proof_values_to_bytes_le)"""
+    L = ffi.lib()
+    a = c_void_p(_check_ptr(L.ffi_bytes_le_to_rln_proof_values(byref(_vec_u8(proof_values_1_le)))))
+    try:
+        b = c_void_p(_check_ptr(L.ffi_bytes_le_to_rln_proof_values(byref(_vec_u8(proof_values_2_le)))))
+        try:
+            return _ok_cfr(L.ffi_recover_id_secret(byref(a), byref(b)))
+        finally:
+            L.ffi_rln_proof_values_free(b)
+    finally:
+        L.ffi_rln_proof_values_free(a)
+
+
+def vec_fr_to_bytes(vals, be=False) -> bytes:
+    f = ffi.lib().ffi_vec_cfr_to_bytes_be if be else ffi.lib().ffi_vec_cfr_to_bytes_le
+    return _ok_bytes(f(byref(_vec_cfr(vals))))
+
+
+def bytes_to_vec_fr(data: bytes, be=False):
+    f = ffi.lib().ffi_bytes_be_to_vec_cfr if be else ffi.lib().ffi_bytes_le_to_vec_cfr
+    res = f(byref(_vec_u8(data)))
+    msg = _take_string(res.err)
+    if msg is not None:
+        raise RLNError(msg)
+    return _take_vec_cfr(res.ok)
+
+
+def vec_u8_to_bytes(data: bytes, be=False) -> bytes:
+    f = ffi.lib().ffi_vec_u8_to_bytes_be if be else ffi.lib().ffi_vec_u8_to_bytes_le
+    return _ok_bytes(f(byref(_vec_u8(data))))
+
+
+def bytes_to_vec_u8(data: bytes, be=False) -> bytes:
+    f = ffi.lib().ffi_bytes_be_to_vec_u8 if be else ffi.lib().ffi_bytes_le_to_vec_u8
+    return _ok_bytes(f(byref(_vec_u8(data))))
+
+
+def proof_values_le_to_be(data: bytes) -> bytes:
+    """bytes_le_to_rln_proof_values → rln_proof_values_to_bytes_be (proof.rs:192-405)"""
+    L = ffi.lib()
+    pv = c_void_p(_check_ptr(L.ffi_bytes_le_to_rln_proof_values(byref(_vec_u8(data)))))
+    try:
+        return _take_vec_u8(L.ffi_rln_proof_values_to_bytes_be(byref(pv)))
+    finally:
+        L.ffi_rln_proof_values_free(pv)
+
+
+def proof_values_be_to_le(data: bytes) -> bytes:
+    L = ffi.lib()
+    pv = c_void_p(_check_ptr(L.ffi_bytes_be_to_rln_proof_values(byref(_vec_u8(data)))))
+    try:
+        return _take_vec_u8(L.ffi_rln_proof_values_to_bytes_le(byref(pv)))
+    finally:
+        L.ffi_rln_proof_values_free(pv)
 
 
 # ------------------------------------------------------------------------------- value types
@@ -156,6 +252,68 @@ class RLNWitnessInput:
             raise RLNError(msg)
         return _take_vec_u8(res.ok)
 
+    @classmethod
+    def from_bytes_be(cls, data):
+        return cls(_check_ptr(ffi.lib().ffi_bytes_be_to_rln_witness(byref(_vec_u8(data)))))
+
+    def to_bytes_be(self):
+        return _ok_bytes(ffi.lib().ffi_rln_witness_to_bytes_be(byref(self._h)))
+
+    def to_bigint_json(self) -> str:
+        """witness.rs:317-366: the JSON snarkjs / circom witness calculators take"""
+        res = ffi.lib().ffi_rln_witness_to_bigint_json(byref(self._h))
+        msg = _take_string(res.err)
+        if msg is not None:
+            raise RLNError(msg)
+        return _take_string(res.ok)
+
+    def to_partial(self):
+        return RLNPartialWitnessInput(ffi.lib().ffi_rln_witness_to_partial_witness(byref(self._h)))
+
+    # getters (witness.rs:183-246); the variant-specific ones abort on the wrong variant like the reference
+    @property
+    def version_byte(self):
+        return ffi.lib().ffi_rln_witness_input_get_version_byte(byref(self._h))
+
+    @property
+    def identity_secret(self):
+        return _take_cfr(ffi.lib().ffi_rln_witness_input_get_identity_secret(byref(self._h)))
+
+    @property
+    def user_message_limit(self):
+        return _take_cfr(ffi.lib().ffi_rln_witness_input_get_user_message_limit(byref(self._h)))
+
+    @property
+    def message_id(self):
+        return _take_cfr(ffi.lib().ffi_rln_witness_input_get_message_id(byref(self._h)))
+
+    @property
+    def message_ids(self):
+        return _take_vec_cfr(ffi.lib().ffi_rln_witness_input_get_message_ids(byref(self._h)))
+
+    @property
+    def path_elements(self):
+        return _take_vec_cfr(ffi.lib().ffi_rln_witness_input_get_path_elements(byref(self._h)))
+
+    @property
+    def identity_path_index(self):
+        return list(_take_vec_u8(ffi.lib().ffi_rln_witness_input_get_identity_path_index(byref(self._h))))
+
+    @property
+    def x(self):
+        return _take_cfr(ffi.lib().ffi_rln_witness_input_get_x(byref(self._h)))
+
+    @property
+    def external_nullifier(self):
+        return _take_cfr(ffi.lib().ffi_rln_witness_input_get_external_nullifier(byref(self._h)))
+
+    @property
+    def selector_used(self):
+        v = ffi.lib().ffi_rln_witness_input_get_selector_used(byref(self._h))
+        out = [bool(v.ptr[i]) for i in range(v.len)]
+        ffi.lib().ffi_vec_u8_free(Vec_uint8(cast(v.ptr, POINTER(c_uint8)), v.len, v.cap))
+        return out
+
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
             ffi.lib().ffi_rln_witness_input_free(self._h)
@@ -173,6 +331,41 @@ class RLNPartialWitnessInput:
         res = ffi.lib().ffi_rln_partial_witness_input_new(byref(_cfr(identity_secret)), byref(_cfr(user_message_limit)),
                                                           byref(_vec_cfr(path_elements)), byref(_vec_u8(bytes(identity_path_index))))
         return cls(_check_ptr(res))
+
+    @classmethod
+    def from_bytes_le(cls, data):
+        return cls(_check_ptr(ffi.lib().ffi_bytes_le_to_rln_partial_witness(byref(_vec_u8(data)))))
+
+    @classmethod
+    def from_bytes_be(cls, data):
+        return cls(_check_ptr(ffi.lib().ffi_bytes_be_to_rln_partial_witness(byref(_vec_u8(data)))))
+
+    def to_bytes_le(self):
+        """witness.rs:631-651: version | secret | limit | vec path_elements | vec identity_path_index"""
+        return _ok_bytes(ffi.lib().ffi_rln_partial_witness_to_bytes_le(byref(self._h)))
+
+    def to_bytes_be(self):
+        return _ok_bytes(ffi.lib().ffi_rln_partial_witness_to_bytes_be(byref(self._h)))
+
+    @property
+    def version_byte(self):
+        return ffi.lib().ffi_rln_partial_witness_input_get_version_byte(byref(self._h))
+
+    @property
+    def identity_secret(self):
+        return _take_cfr(ffi.lib().ffi_rln_partial_witness_input_get_identity_secret(byref(self._h)))
+
+    @property
+    def user_message_limit(self):
+        return _take_cfr(ffi.lib().ffi_rln_partial_witness_input_get_user_message_limit(byref(self._h)))
+
+    @property
+    def path_elements(self):
+        return _take_vec_cfr(ffi.lib().ffi_rln_partial_witness_input_get_path_elements(byref(self._h)))
+
+    @property
+    def identity_path_index(self):
+        return list(_take_vec_u8(ffi.lib().ffi_rln_partial_witness_input_get_identity_path_index(byref(self._h))))
 
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -192,6 +385,22 @@ class RLNPartialProof:
         if msg:
             raise RLNError(msg)
         return _take_vec_u8(res.ok)
+
+    def to_bytes_be(self):
+        """= the LE form: arkworks points are always little-endian (proof.rs:549-553)"""
+        return _ok_bytes(ffi.lib().ffi_rln_partial_proof_to_bytes_be(byref(self._h)))
+
+    @classmethod
+    def from_bytes_le(cls, data):
+        return cls(_check_ptr(ffi.lib().ffi_bytes_le_to_rln_partial_proof(byref(_vec_u8(data)))))
+
+    @classmethod
+    def from_bytes_be(cls, data):
+        return cls(_check_ptr(ffi.lib().ffi_bytes_be_to_rln_partial_proof(byref(_vec_u8(data)))))
+
+    @property
+    def version_byte(self):
+        return ffi.lib().ffi_rln_partial_proof_get_version_byte(byref(self._h))
 
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -233,6 +442,10 @@ class RLNProof:
     def to_bytes_be(self):
         res = ffi.lib().ffi_rln_proof_to_bytes_be(byref(self._h))
         return _take_vec_u8(res.ok)
+
+    @classmethod
+    def from_bytes_be(cls, data):
+        return cls(_check_ptr(ffi.lib().ffi_bytes_be_to_rln_proof(byref(_vec_u8(data)))))
 
     @property
     def proof_bytes(self):
@@ -341,6 +554,16 @@ class RLN:
         arr = (ctypes.c_size_t * max(len(indices), 1))(*indices)
         vs = Vec_size(cast(arr, POINTER(ctypes.c_size_t)), len(indices), len(indices))
         _check_bool(ffi.lib().ffi_atomic_operation(byref(self._h), index, byref(_vec_cfr(leaves)), byref(vs)))
+
+    def set_metadata(self, data: bytes):
+        """rln/src/public.rs:499-502"""
+        _check_bool(ffi.lib().ffi_set_metadata(byref(self._h), byref(_vec_u8(data))))
+
+    def get_metadata(self) -> bytes:
+        return _ok_bytes(ffi.lib().ffi_get_metadata(byref(self._h)))
+
+    def flush(self):
+        _check_bool(ffi.lib().ffi_flush(byref(self._h)))
 
     def get_root(self):
         return _take_cfr(ffi.lib().ffi_get_root(byref(self._h)))
