@@ -63,6 +63,23 @@ typedef struct CResult_CFr { CFr_t *ok; RlnString err; } CResult_CFr_t;
 typedef struct CResult_Vec_uint8 { Vec_uint8_t ok; RlnString err; } CResult_Vec_uint8_t;
 typedef struct CResult_Vec_CFr { Vec_CFr_t ok; RlnString err; } CResult_Vec_CFr_t;
 typedef struct CResult_String { RlnString ok; RlnString err; } CResult_String_t;
+typedef struct CResult_Vec_bool { Vec_bool_t ok; RlnString err; } CResult_Vec_bool_t;
+
+/* V3 objects (rln/src/ffi/ffi_rln_v3.rs:312,614,866,1013,1097,1141,1365) */
+typedef struct FFI_RLNV3 FFI_RLNV3_t;
+typedef struct FFI_RLNV3WitnessInput FFI_RLNV3WitnessInput_t;
+typedef struct FFI_RLNV3PartialWitnessInput FFI_RLNV3PartialWitnessInput_t;
+typedef struct FFI_RLNV3Proof FFI_RLNV3Proof_t;
+typedef struct FFI_RLNV3PartialProof FFI_RLNV3PartialProof_t;
+typedef struct FFI_RLNV3ProofValues FFI_RLNV3ProofValues_t;
+typedef struct FFI_RLNV3MerkleProof { Vec_CFr_t path_elements; Vec_uint8_t path_index; } FFI_RLNV3MerkleProof_t;
+typedef struct CResult_FFI_RLNV3 { FFI_RLNV3_t *ok; RlnString err; } CResult_FFI_RLNV3_t;
+typedef struct CResult_FFI_RLNV3WitnessInput { FFI_RLNV3WitnessInput_t *ok; RlnString err; } CResult_FFI_RLNV3WitnessInput_t;
+typedef struct CResult_FFI_RLNV3PartialWitnessInput { FFI_RLNV3PartialWitnessInput_t *ok; RlnString err; } CResult_FFI_RLNV3PartialWitnessInput_t;
+typedef struct CResult_FFI_RLNV3Proof { FFI_RLNV3Proof_t *ok; RlnString err; } CResult_FFI_RLNV3Proof_t;
+typedef struct CResult_FFI_RLNV3PartialProof { FFI_RLNV3PartialProof_t *ok; RlnString err; } CResult_FFI_RLNV3PartialProof_t;
+typedef struct CResult_FFI_RLNV3ProofValues { FFI_RLNV3ProofValues_t *ok; RlnString err; } CResult_FFI_RLNV3ProofValues_t;
+typedef struct CResult_FFI_RLNV3MerkleProof { FFI_RLNV3MerkleProof_t *ok; RlnString err; } CResult_FFI_RLNV3MerkleProof_t;
 
 /* ------------------------------------------------------------------ RLN object (rln/src/ffi/ffi_rln.rs) */
 CResult_FFI_RLN_t ffi_rln_new(size_t tree_depth, const char *config_path);                      /* :22-57  */
@@ -218,6 +235,110 @@ CResult_CFr_t ffi_recover_id_secret(FFI_RLNProofValues_t *const *proof_values_1,
 CBoolResult_t ffi_set_metadata(FFI_RLN_t **rln, const Vec_uint8_t *metadata);                    /* ffi_tree.rs:228-240 */
 CResult_Vec_uint8_t ffi_get_metadata(FFI_RLN_t *const *rln);                                     /* ffi_tree.rs:242-254 */
 CBoolResult_t ffi_flush(FFI_RLN_t **rln);                                                        /* ffi_tree.rs:256-268 */
+
+/* ================================================================== rln/src/ffi/ffi_rln_v3.rs: the V3 twins
+ * Same prover, tree and records behind the V3 names.  The three stateful tree flavours are the one HBM tree (same roots and
+ * paths); the *_default constructors return NULL when no GPU is usable (the reference's are infallible); wire formats are
+ * documented in zerokit_b200/csrc/rln_ffi_v3.inc. */
+FFI_RLNV3_t *ffi_rln_v3_new_stateless_default(void);                                                                  /* :323-327 */
+CResult_FFI_RLNV3_t ffi_rln_v3_new_stateless(const Vec_uint8_t *zkey_data, const Vec_uint8_t *graph_data);            /* :329-346 */
+FFI_RLNV3_t *ffi_rln_v3_new_with_full_merkle_tree_default(void);                                                      /* :349-354 */
+CResult_FFI_RLNV3_t ffi_rln_v3_new_with_full_merkle_tree(size_t tree_depth, const Vec_uint8_t *zkey_data,
+                                                         const Vec_uint8_t *graph_data);                              /* :356-387 */
+FFI_RLNV3_t *ffi_rln_v3_new_with_optimal_merkle_tree_default(void);                                                   /* :390-396 */
+CResult_FFI_RLNV3_t ffi_rln_v3_new_with_optimal_merkle_tree(size_t tree_depth, const Vec_uint8_t *zkey_data,
+                                                            const Vec_uint8_t *graph_data);                           /* :398-429 */
+FFI_RLNV3_t *ffi_rln_v3_new_with_pm_tree_default(void);                                                               /* :432-437 */
+CResult_FFI_RLNV3_t ffi_rln_v3_new_with_pm_tree(size_t tree_depth, const Vec_uint8_t *zkey_data, const Vec_uint8_t *graph_data,
+                                                const char *config_path);                                            /* :439-504 */
+void ffi_rln_v3_free(FFI_RLNV3_t *rln);                                                                               /* :605-608 */
+CResult_FFI_RLNV3Proof_t ffi_rln_v3_generate_proof(FFI_RLNV3_t *const *rln, FFI_RLNV3WitnessInput_t *const *witness); /* :506-521 */
+CBoolResult_t ffi_rln_v3_verify(FFI_RLNV3_t *const *rln, FFI_RLNV3Proof_t *const *rln_proof, const CFr_t *x);         /* :523-545 */
+CBoolResult_t ffi_rln_v3_verify_with_roots(FFI_RLNV3_t *const *rln, FFI_RLNV3Proof_t *const *rln_proof, const Vec_CFr_t *roots,
+                                           const CFr_t *x);                                                           /* :547-568 */
+CResult_FFI_RLNV3PartialProof_t ffi_rln_v3_generate_partial_proof(FFI_RLNV3_t *const *rln,
+                                                                  FFI_RLNV3PartialWitnessInput_t *const *partial_witness); /* :570-585 */
+CResult_FFI_RLNV3Proof_t ffi_rln_v3_finish_proof(FFI_RLNV3_t *const *rln, FFI_RLNV3PartialProof_t *const *partial_proof,
+                                                 FFI_RLNV3WitnessInput_t *const *witness);                            /* :587-603 */
+CResult_FFI_RLNV3WitnessInput_t ffi_rln_v3_witness_input_new_single(const CFr_t *identity_secret, const CFr_t *user_message_limit,
+        const CFr_t *message_id, const Vec_CFr_t *path_elements, const Vec_uint8_t *identity_path_index, const CFr_t *x,
+        const CFr_t *external_nullifier);                                                                             /* :616-649 */
+CResult_FFI_RLNV3WitnessInput_t ffi_rln_v3_witness_input_new_multi(const CFr_t *identity_secret, const CFr_t *user_message_limit,
+        const Vec_CFr_t *message_ids, const Vec_CFr_t *path_elements, const Vec_uint8_t *identity_path_index, const CFr_t *x,
+        const CFr_t *external_nullifier, const Vec_bool_t *selector_used);                                            /* :651-688 */
+CFr_t *ffi_rln_v3_witness_input_get_identity_secret(FFI_RLNV3WitnessInput_t *const *witness);                         /* :690-695 */
+CFr_t *ffi_rln_v3_witness_input_get_user_message_limit(FFI_RLNV3WitnessInput_t *const *witness);                      /* :697-702 */
+CResult_CFr_t ffi_rln_v3_witness_input_get_message_id(FFI_RLNV3WitnessInput_t *const *witness);                       /* :704-718 */
+CResult_Vec_CFr_t ffi_rln_v3_witness_input_get_message_ids(FFI_RLNV3WitnessInput_t *const *witness);                  /* :720-739 */
+Vec_CFr_t ffi_rln_v3_witness_input_get_path_elements(FFI_RLNV3WitnessInput_t *const *witness);                        /* :741-752 */
+Vec_uint8_t ffi_rln_v3_witness_input_get_identity_path_index(FFI_RLNV3WitnessInput_t *const *witness);                /* :754-759 */
+CFr_t *ffi_rln_v3_witness_input_get_x(FFI_RLNV3WitnessInput_t *const *witness);                                       /* :761-766 */
+CFr_t *ffi_rln_v3_witness_input_get_external_nullifier(FFI_RLNV3WitnessInput_t *const *witness);                      /* :768-773 */
+CResult_Vec_bool_t ffi_rln_v3_witness_input_get_selector_used(FFI_RLNV3WitnessInput_t *const *witness);               /* :775-789 */
+CResult_Vec_uint8_t ffi_rln_v3_witness_to_bytes_le(FFI_RLNV3WitnessInput_t *const *witness);                          /* :791-806 */
+CResult_Vec_uint8_t ffi_rln_v3_witness_to_bytes_be(FFI_RLNV3WitnessInput_t *const *witness);                          /* :808-823 */
+CResult_FFI_RLNV3WitnessInput_t ffi_bytes_le_to_rln_v3_witness(const Vec_uint8_t *bytes);                             /* :825-839 */
+CResult_FFI_RLNV3WitnessInput_t ffi_bytes_be_to_rln_v3_witness(const Vec_uint8_t *bytes);                             /* :841-855 */
+void ffi_rln_v3_witness_input_free(FFI_RLNV3WitnessInput_t *witness);                                                 /* :857-860 */
+CResult_FFI_RLNV3PartialWitnessInput_t ffi_rln_v3_partial_witness_input_new(const CFr_t *identity_secret,
+        const CFr_t *user_message_limit, const Vec_CFr_t *path_elements, const Vec_uint8_t *identity_path_index);     /* :868-894 */
+CFr_t *ffi_rln_v3_partial_witness_input_get_identity_secret(FFI_RLNV3PartialWitnessInput_t *const *w);                /* :896-901 */
+CFr_t *ffi_rln_v3_partial_witness_input_get_user_message_limit(FFI_RLNV3PartialWitnessInput_t *const *w);             /* :903-908 */
+Vec_CFr_t ffi_rln_v3_partial_witness_input_get_path_elements(FFI_RLNV3PartialWitnessInput_t *const *w);               /* :910-921 */
+Vec_uint8_t ffi_rln_v3_partial_witness_input_get_identity_path_index(FFI_RLNV3PartialWitnessInput_t *const *w);       /* :923-928 */
+FFI_RLNV3PartialWitnessInput_t *ffi_rln_v3_witness_to_partial_witness(FFI_RLNV3WitnessInput_t *const *witness);       /* :930-936 */
+CResult_Vec_uint8_t ffi_rln_v3_partial_witness_to_bytes_le(FFI_RLNV3PartialWitnessInput_t *const *w);                 /* :938-953 */
+CResult_Vec_uint8_t ffi_rln_v3_partial_witness_to_bytes_be(FFI_RLNV3PartialWitnessInput_t *const *w);                 /* :955-970 */
+CResult_FFI_RLNV3PartialWitnessInput_t ffi_bytes_le_to_rln_v3_partial_witness(const Vec_uint8_t *bytes);              /* :972-986 */
+CResult_FFI_RLNV3PartialWitnessInput_t ffi_bytes_be_to_rln_v3_partial_witness(const Vec_uint8_t *bytes);              /* :988-1002 */
+void ffi_rln_v3_partial_witness_input_free(FFI_RLNV3PartialWitnessInput_t *w);                                        /* :1004-1007 */
+FFI_RLNV3ProofValues_t *ffi_rln_v3_proof_get_values(FFI_RLNV3Proof_t *const *rln_proof);                              /* :1015-1020 */
+CResult_Vec_uint8_t ffi_rln_v3_proof_to_bytes_le(FFI_RLNV3Proof_t *const *rln_proof);                                 /* :1022-1037 */
+CResult_Vec_uint8_t ffi_rln_v3_proof_to_bytes_mixed(FFI_RLNV3Proof_t *const *rln_proof);                              /* :1039-1054 */
+CResult_FFI_RLNV3Proof_t ffi_bytes_le_to_rln_v3_proof(const Vec_uint8_t *bytes);                                      /* :1056-1070 */
+CResult_FFI_RLNV3Proof_t ffi_bytes_mixed_to_rln_v3_proof(const Vec_uint8_t *bytes);                                   /* :1072-1086 */
+void ffi_rln_v3_proof_free(FFI_RLNV3Proof_t *rln_proof);                                                              /* :1088-1091 */
+CResult_Vec_uint8_t ffi_rln_v3_partial_proof_to_bytes_le(FFI_RLNV3PartialProof_t *const *partial_proof);              /* :1099-1114 */
+CResult_FFI_RLNV3PartialProof_t ffi_bytes_le_to_rln_v3_partial_proof(const Vec_uint8_t *bytes);                       /* :1116-1130 */
+void ffi_rln_v3_partial_proof_free(FFI_RLNV3PartialProof_t *partial_proof);                                           /* :1132-1135 */
+CFr_t *ffi_rln_v3_proof_values_get_root(FFI_RLNV3ProofValues_t *const *pv);                                           /* :1143-1148 */
+CFr_t *ffi_rln_v3_proof_values_get_x(FFI_RLNV3ProofValues_t *const *pv);                                              /* :1150-1153 */
+CFr_t *ffi_rln_v3_proof_values_get_external_nullifier(FFI_RLNV3ProofValues_t *const *pv);                             /* :1155-1160 */
+CResult_CFr_t ffi_rln_v3_proof_values_get_y(FFI_RLNV3ProofValues_t *const *pv);                                       /* :1162-1176 */
+CResult_CFr_t ffi_rln_v3_proof_values_get_nullifier(FFI_RLNV3ProofValues_t *const *pv);                               /* :1178-1192 */
+CResult_Vec_bool_t ffi_rln_v3_proof_values_get_selector_used(FFI_RLNV3ProofValues_t *const *pv);                      /* :1194-1208 */
+CResult_Vec_CFr_t ffi_rln_v3_proof_values_get_ys(FFI_RLNV3ProofValues_t *const *pv);                                  /* :1210-1229 */
+CResult_Vec_CFr_t ffi_rln_v3_proof_values_get_nullifiers(FFI_RLNV3ProofValues_t *const *pv);                          /* :1231-1250 */
+CResult_Vec_uint8_t ffi_rln_v3_proof_values_to_bytes_le(FFI_RLNV3ProofValues_t *const *pv);                           /* :1252-1267 */
+CResult_Vec_uint8_t ffi_rln_v3_proof_values_to_bytes_be(FFI_RLNV3ProofValues_t *const *pv);                           /* :1269-1284 */
+CResult_FFI_RLNV3ProofValues_t ffi_bytes_le_to_rln_v3_proof_values(const Vec_uint8_t *bytes);                         /* :1286-1300 */
+CResult_FFI_RLNV3ProofValues_t ffi_bytes_be_to_rln_v3_proof_values(const Vec_uint8_t *bytes);                         /* :1302-1316 */
+void ffi_rln_v3_proof_values_free(FFI_RLNV3ProofValues_t *proof_values);                                              /* :1318-1321 */
+CResult_CFr_t ffi_rln_v3_compute_id_secret(const CFr_t *share1_x, const CFr_t *share1_y, const CFr_t *share2_x,
+                                           const CFr_t *share2_y);                                                    /* :1323-1342 */
+CResult_CFr_t ffi_rln_v3_recover_id_secret(FFI_RLNV3ProofValues_t *const *proof_values_1,
+                                           FFI_RLNV3ProofValues_t *const *proof_values_2);                            /* :1344-1361 */
+void ffi_rln_v3_merkle_proof_free(FFI_RLNV3MerkleProof_t *merkle_proof);                                              /* :1370-1373 */
+CBoolResult_t ffi_rln_v3_delete_leaf(FFI_RLNV3_t **rln, size_t index);                                                /* :1375-1387 */
+CBoolResult_t ffi_rln_v3_set_leaf(FFI_RLNV3_t **rln, size_t index, const CFr_t *leaf);                                /* :1389-1405 */
+CResult_CFr_t ffi_rln_v3_get_leaf(FFI_RLNV3_t *const *rln, size_t index);                                             /* :1407-1422 */
+size_t ffi_rln_v3_leaves_set(FFI_RLNV3_t *const *rln);                                                                /* :1424-1427 */
+CBoolResult_t ffi_rln_v3_set_next_leaf(FFI_RLNV3_t **rln, const CFr_t *leaf);                                         /* :1429-1441 */
+CBoolResult_t ffi_rln_v3_set_leaves_from(FFI_RLNV3_t **rln, size_t index, const Vec_CFr_t *leaves);                   /* :1443-1460 */
+CBoolResult_t ffi_rln_v3_init_tree_with_leaves(FFI_RLNV3_t **rln, const Vec_CFr_t *leaves);                           /* :1462-1478 */
+CBoolResult_t ffi_rln_v3_atomic_operation(FFI_RLNV3_t **rln, size_t index, const Vec_CFr_t *leaves,
+                                          const Vec_size_t *indices);                                                 /* :1480-1499 */
+CBoolResult_t ffi_rln_v3_seq_atomic_operation(FFI_RLNV3_t **rln, const Vec_CFr_t *leaves, const Vec_uint8_t *indices);/* :1501-1528 */
+CFr_t *ffi_rln_v3_get_root(FFI_RLNV3_t *const *rln);                                                                  /* :1530-1534 */
+CResult_FFI_RLNV3MerkleProof_t ffi_rln_v3_get_merkle_proof(FFI_RLNV3_t *const *rln, size_t index);                    /* :1536-1562 */
+CBoolResult_t ffi_rln_v3_set_metadata(FFI_RLNV3_t **rln, const Vec_uint8_t *metadata);                                /* :1564-1579 */
+CResult_Vec_uint8_t ffi_rln_v3_get_metadata(FFI_RLNV3_t *const *rln);                                                 /* :1581-1595 */
+CBoolResult_t ffi_rln_v3_flush(FFI_RLNV3_t **rln);                                                                    /* :1597-1609 */
+/* extensions: caller-supplied (r, s) for reproducible V3 proofs */
+CResult_FFI_RLNV3Proof_t rlnb200_v3_generate_proof_with_rs(FFI_RLNV3_t *const *rln, FFI_RLNV3WitnessInput_t *const *witness,
+                                                           const CFr_t *r, const CFr_t *s);
+CResult_FFI_RLNV3Proof_t rlnb200_v3_finish_proof_with_rs(FFI_RLNV3_t *const *rln, FFI_RLNV3PartialProof_t *const *partial_proof,
+                                                         FFI_RLNV3WitnessInput_t *const *witness, const CFr_t *r, const CFr_t *s);
 
 /* ================================================================== extensions (not in the reference) */
 

@@ -59,3 +59,35 @@ def witness_to_bigint_json(secret, limit, message_id, path_elements, path_index,
          "pathElements": [str(v) for v in path_elements], "identityPathIndex": [str(v) for v in path_index],
          "x": str(x), "externalNullifier": str(ext_null)}
     return json.dumps(d, sort_keys=True, separators=(",", ":"))
+
+
+# ---------------------------------------------------------------------------------------------------------------- V3 records
+# rln/src/protocol/serialize.rs: LE is ark's derive (enum tag, then the struct fields in declaration order,
+# witness.rs:1288-1317, proof.rs:983-1048); BE is hand-written there and orders the Single witness differently (:370-381).
+def v3_witness_single(secret, limit, message_id, path_elements, path_index, x, ext_null, be=False):
+    fr = fr_be if be else fr_le
+    if be:
+        return b"\x00" + fr(secret) + fr(limit) + fr(message_id) + vec_fr(path_elements, be) + vec_u8(path_index, be) + fr(x) + fr(ext_null)
+    return b"\x00" + fr(secret) + fr(limit) + vec_fr(path_elements, be) + vec_u8(path_index, be) + fr(x) + fr(ext_null) + fr(message_id)
+
+
+def v3_witness_multi(secret, limit, message_ids, path_elements, path_index, x, ext_null, selector_used, be=False):
+    fr = fr_be if be else fr_le
+    return (b"\x01" + fr(secret) + fr(limit) + vec_fr(path_elements, be) + vec_u8(path_index, be) + fr(x) + fr(ext_null)
+            + vec_fr(message_ids, be) + vec_u8([1 if v else 0 for v in selector_used], be))
+
+
+def v3_partial_witness(secret, limit, path_elements, path_index, be=False):
+    fr = fr_be if be else fr_le
+    return fr(secret) + fr(limit) + vec_fr(path_elements, be) + vec_u8(path_index, be)
+
+
+def v3_values_single(y, root, nullifier, x, ext_null, be=False):
+    fr = fr_be if be else fr_le
+    return b"\x00" + fr(y) + fr(root) + fr(nullifier) + fr(x) + fr(ext_null)
+
+
+def v3_values_multi(ys, root, nullifiers, x, ext_null, selector_used, be=False):
+    fr = fr_be if be else fr_le
+    return (b"\x01" + vec_fr(ys, be) + fr(root) + vec_fr(nullifiers, be) + fr(x) + fr(ext_null)
+            + vec_u8([1 if v else 0 for v in selector_used], be))

@@ -447,15 +447,93 @@ def test_big_endian_proof_records_and_metadata(z, rln10, goldens):
         assert parsed.to_bytes_le() == pb
         fin = rln10.finish_rln_proof_with_rs(parsed, wit, int(k["inputs"]["r"]), int(k["inputs"]["s"]))
         assert fin.to_bytes_le().hex() == k["rln_proof_le_hex"]
-    bad = bytearray(pb)
-    bad[-1] ^= 0x3f
-    with pytest.raises(z.RLNError, match="invalid data"):
-        z.RLNPartialProof.from_bytes_le(bytes(bad))
+    rejected = 0
+    for delta in range(1, 9):   # about half of all x coordinates are not on the curve
+        bad = bytearray(pb)
+        bad[-2] ^= delta
+        try:
+            z.RLNPartialProof.from_bytes_le(bytes(bad))
+        except z.RLNError as e:
+            assert "invalid data" in str(e)
+            rejected += 1
+    assert rejected >= 1
     # metadata / flush (rln/src/ffi/ffi_tree.rs:226-268)
     assert rln10.get_metadata() == b""
     rln10.set_metadata(b"block 1234")
     assert rln10.get_metadata() == b"block 1234"
     rln10.flush()
+
+
+def test_v3_api(z, goldens, oracle):
+    """rln/tests/ffi.rs V3 section + rln/tests/public.rs: RLNV3 over the same prover — stateless and stateful builds, proof ==
+    the V1 golden proof for the same (r, s), verify / verify_with_roots semantics, tree ops, V3 wire forms of the proof"""
+    k = goldens["derived"]["kat_proof_d10"]
+    args = kat_witness_args(10, k["inputs"])
+    zkey, graph = resource(10, "rln_final.arkzkey"), resource(10, "graph.bin")
+    r, s = int(k["inputs"]["r"]), int(k["inputs"]["s"])
+    v3 = z.RLNV3.stateful("optimal", 10, zkey, graph)
+    wit = z.WitnessV3.new_single(args[0], args[1], args[2], args[3], args[4], args[5], args[6])
+    proof = v3.generate_proof_with_rs(wit, r, s)
+    gold = bytes.fromhex(k["rln_proof_le_hex"])      # V1 record: version | proof | version | root | en | x | y | nullifier
+    le = proof.to_bytes_le()
+    assert le[:128] == gold[1:129]
+    v = proof.values
+    assert [v.root, v.external_nullifier, v.x, v.y, v.nullifier] == ints(gold[130:290])
+    from pyref import serialize as S
+    assert le[128:] == S.v3_values_single(v.y, v.root, v.nullifier, v.x, v.external_nullifier)
+    mixed = proof.to_bytes_mixed()
+    assert mixed[:128] == le[:128] and mixed[128:] == S.v3_values_single(v.y, v.root, v.nullifier, v.x, v.external_nullifier, be=True)
+    assert z.ProofV3.from_bytes_le(le).to_bytes_mixed() == mixed and z.ProofV3.from_bytes_mixed(mixed).to_bytes_le() == le
+    bad = bytearray(le)
+    bad[5] ^= 1
+    with pytest.raises(z.RLNError, match="invalid data"):
+        z.ProofV3.from_bytes_le(bytes(bad))
+    # verify: pairing only, Ok(false) on a wrong signal; verify_with_roots: root → signal → proof, errors as text
+    assert v3.verify(proof, v.x) is True and v3.verify(proof, v.x + 1) is False
+    assert v3.verify_with_roots(proof, v.x, []) and v3.verify_with_roots(proof, v.x, [5, v.root])
+    with pytest.raises(z.RLNError, match="Expected one of the provided roots"):
+        v3.verify_with_roots(proof, v.x, [5])
+    with pytest.raises(z.RLNError, match="Signal value does not match"):
+        v3.verify_with_roots(proof, v.x + 1, [])
+    forged = z.ProofV3.from_bytes_le(le[:128] + S.v3_values_single((v.y + 1) % R, v.root, v.nullifier, v.x, v.external_nullifier))
+    assert v3.verify(forged, v.x) is False
+    with pytest.raises(z.RLNError, match="Invalid proof provided"):
+        v3.verify_with_roots(forged, v.x, [])
+    # fresh randomness + shape check against the circuit
+    assert v3.verify(v3.generate_proof(wit), v.x)
+    with pytest.raises(z.RLNError, match="Field `path_elements` has length 9, but circuit tree_depth is 10"):
+        v3.generate_proof(z.WitnessV3.new_single(args[0], args[1], args[2], args[3][:9], args[4][:9], args[5], args[6]))
+    # two-phase
+    partial = v3.generate_partial_proof(wit.to_partial())
+    pb = partial.to_bytes_le()
+    assert b"\0" + pb == bytes.fromhex(goldens["derived"]["partial_proof_d10"]["partial_le_hex"])
+    assert v3.finish_proof_with_rs(z.PartialProofV3.from_bytes_le(pb), wit, r, s).to_bytes_le() == le
+    assert v3.verify(v3.finish_proof(partial, wit), v.x)
+    # tree: same roots / paths as the V1 object and the oracle
+    fs = fr_stream(33)
+    leaves = [next(fs) for _ in range(50)]
+    v3.set_leaves_from(0, leaves)
+    nodes = oracle.merkle_build(10, fr_bytes(leaves), 0, 50)
+    assert v3.get_root() == int.from_bytes(nodes[:32], "little") and v3.leaves_set() == 50 and v3.get_leaf(7) == leaves[7]
+    e, b = v3.get_merkle_proof(13)
+    oe, ob = oracle.merkle_proof_from_nodes(nodes, 10, 13)
+    assert e == oe and b == ob
+    v3.set_next_leaf(99); v3.delete_leaf(3); v3.atomic_operation(51, [7, 8], [0]); v3.seq_atomic_operation([9], [1])
+    exp = leaves + [99, 7, 8, 9]
+    exp[3] = exp[0] = exp[1] = 0
+    nodes = oracle.merkle_build(10, fr_bytes(exp), 0, len(exp))
+    assert v3.get_root() == int.from_bytes(nodes[:32], "little") and v3.leaves_set() == 54
+    v3.init_tree_with_leaves(leaves[:4])
+    assert v3.get_root() == int.from_bytes(oracle.merkle_build(10, fr_bytes(leaves[:4]), 0, 4)[:32], "little")
+    v3.set_metadata(b"abc"); assert v3.get_metadata() == b"abc"; v3.flush()
+    del v3
+    # stateless: proves and verifies, refuses every tree operation
+    sl = z.RLNV3.stateless(zkey, graph)
+    assert sl.generate_proof_with_rs(wit, r, s).to_bytes_le() == le and sl.verify(proof, v.x)
+    assert sl.get_root() == 0 and sl.leaves_set() == 0
+    for op in (lambda: sl.set_leaf(0, 1), lambda: sl.get_leaf(0), lambda: sl.get_merkle_proof(0), lambda: sl.set_metadata(b"x"), lambda: sl.flush()):
+        with pytest.raises(z.RLNError, match="tree op unsupported on stateless RLN"):
+            op()
 
 
 def test_multi_message_id_circuit(z, goldens, oracle):

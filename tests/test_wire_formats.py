@@ -139,3 +139,65 @@ def test_compute_and_recover_id_secret(z):
         z.recover_id_secret(m1, m3)
     with pytest.raises(z.RLNError, match="No matching nullifier"):
         z.recover_id_secret(pv[0], m2)
+
+
+# ------------------------------------------------------------------------------------------------ V3 records (ffi_rln_v3.rs)
+def test_v3_witness_records(z):
+    """rln/tests/serialize.rs V3 round trips; layouts from rln/src/protocol/serialize.rs (the BE Single order differs from LE)"""
+    a = _witness_args(11, 20)
+    w = z.WitnessV3.new_single(a["secret"], a["limit"], a["mid"], a["path"], a["idx"], a["x"], a["en"])
+    le = S.v3_witness_single(a["secret"], a["limit"], a["mid"], a["path"], a["idx"], a["x"], a["en"])
+    be = S.v3_witness_single(a["secret"], a["limit"], a["mid"], a["path"], a["idx"], a["x"], a["en"], be=True)
+    assert w.to_bytes_le() == le and w.to_bytes_be() == be
+    assert z.WitnessV3.from_bytes_le(le).to_bytes_be() == be and z.WitnessV3.from_bytes_be(be).to_bytes_le() == le
+    assert (w.identity_secret, w.user_message_limit, w.message_id, w.message_ids, w.selector_used) == (a["secret"], a["limit"], a["mid"], None, None)
+    assert (w.path_elements, w.identity_path_index, w.x, w.external_nullifier) == (a["path"], a["idx"], a["x"], a["en"])
+    mids, sel = [1, 2, 3, 0], [True, False, True, False]
+    m = z.WitnessV3.new_multi(a["secret"], a["limit"], mids, a["path"], a["idx"], a["x"], a["en"], sel)
+    le = S.v3_witness_multi(a["secret"], a["limit"], mids, a["path"], a["idx"], a["x"], a["en"], sel)
+    be = S.v3_witness_multi(a["secret"], a["limit"], mids, a["path"], a["idx"], a["x"], a["en"], sel, be=True)
+    assert m.to_bytes_le() == le and m.to_bytes_be() == be
+    assert z.WitnessV3.from_bytes_le(le).to_bytes_be() == be and z.WitnessV3.from_bytes_be(be).to_bytes_le() == le
+    assert (m.message_id, m.message_ids, m.selector_used) == (None, mids, sel)
+    # constructor errors carry the V3 texts (rln/src/error.rs:136-167)
+    with pytest.raises(z.RLNError, match="Field `path_elements` has length 20, but field `identity_path_index` has length 19"):
+        z.WitnessV3.new_single(1, 10, 1, a["path"], a["idx"][:-1], 1, 1)
+    with pytest.raises(z.RLNError, match="At least one value in `selector_used` must be true"):
+        z.WitnessV3.new_multi(1, 10, [1, 2], a["path"], a["idx"], 1, 1, [False, False])
+    with pytest.raises(z.RLNError, match="Duplicate message ID found in `message_ids`"):
+        z.WitnessV3.new_multi(1, 10, [2, 2], a["path"], a["idx"], 1, 1, [True, True])
+    with pytest.raises(z.RLNError, match="Field `message_ids` has length 2, but field `selector_used` has length 1"):
+        z.WitnessV3.new_multi(1, 10, [1, 2], a["path"], a["idx"], 1, 1, [True])
+    with pytest.raises(z.RLNError, match="failed to fill whole buffer"):
+        z.WitnessV3.from_bytes_le(le[:-1])
+    with pytest.raises(z.RLNError, match="Non-canonical field element"):
+        z.WitnessV3.from_bytes_be(be[:1] + R.to_bytes(32, "big") + be[33:])
+    # partial witness: no tag byte
+    pw = z.PartialWitnessV3.new(a["secret"], a["limit"], a["path"], a["idx"])
+    ple, pbe = S.v3_partial_witness(a["secret"], a["limit"], a["path"], a["idx"]), S.v3_partial_witness(a["secret"], a["limit"], a["path"], a["idx"], be=True)
+    assert pw.to_bytes_le() == ple and pw.to_bytes_be() == pbe and w.to_partial().to_bytes_le() == ple
+    assert z.PartialWitnessV3.from_bytes_le(ple).to_bytes_be() == pbe and z.PartialWitnessV3.from_bytes_be(pbe).to_bytes_le() == ple
+    assert (pw.identity_secret, pw.user_message_limit, pw.path_elements, pw.identity_path_index) == (a["secret"], a["limit"], a["path"], a["idx"])
+
+
+def test_v3_proof_values_records(z):
+    fs = fr_stream(12)
+    y, root, nul, x, en = (next(fs) for _ in range(5))
+    le, be = S.v3_values_single(y, root, nul, x, en), S.v3_values_single(y, root, nul, x, en, be=True)
+    v = z.ProofValuesV3.from_bytes_le(le)
+    assert v.to_bytes_le() == le and v.to_bytes_be() == be and z.ProofValuesV3.from_bytes_be(be).to_bytes_le() == le
+    assert (v.y, v.root, v.nullifier, v.x, v.external_nullifier, v.ys, v.nullifiers, v.selector_used) == (y, root, nul, x, en, None, None, None)
+    ys, nulls, sel = [next(fs) for _ in range(4)], [next(fs) for _ in range(4)], [True, True, False, True]
+    le, be = S.v3_values_multi(ys, root, nulls, x, en, sel), S.v3_values_multi(ys, root, nulls, x, en, sel, be=True)
+    m = z.ProofValuesV3.from_bytes_le(le)
+    assert m.to_bytes_le() == le and m.to_bytes_be() == be and z.ProofValuesV3.from_bytes_be(be).to_bytes_le() == le
+    assert (m.y, m.nullifier, m.ys, m.nullifiers, m.selector_used) == (None, None, ys, nulls, sel)
+    with pytest.raises(z.RLNError, match="Non-canonical bool byte: expected 0x00 or 0x01, got 0x02"):
+        z.ProofValuesV3.from_bytes_be(be[:-1] + b"\x02")
+    with pytest.raises(z.RLNError, match="failed to fill whole buffer"):
+        z.ProofValuesV3.from_bytes_be(be[:-1])
+    # Shamir recovery through the V3 names
+    a0, a1 = next(fs), next(fs)
+    v1 = z.ProofValuesV3.from_bytes_le(S.v3_values_single((a0 + 5 * a1) % R, root, nul, 5, en))
+    v2 = z.ProofValuesV3.from_bytes_le(S.v3_values_single((a0 + 6 * a1) % R, root, nul, 6, en))
+    assert v1.recover_id_secret(v2) == a0 == z.compute_id_secret_v3((5, (a0 + 5 * a1) % R), (6, (a0 + 6 * a1) % R))

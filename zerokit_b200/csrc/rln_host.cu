@@ -1836,6 +1836,7 @@ Vec_CFr_t ffi_key_gen(void) {  // keygen (rln/src/protocol/keygen.rs:20-30): sec
 }
 
 #include "rln_ffi_more.inc"
+#include "rln_ffi_v3.inc"
 
 // ---- extensions -------------------------------------------------------------------------------
 #define INT_OP(...)                                            \

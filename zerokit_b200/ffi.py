@@ -53,6 +53,7 @@ CResult_CFr = _cresult("CResult_CFr", POINTER(CFr))
 CResult_Vec_uint8 = _cresult("CResult_Vec_uint8", Vec_uint8)
 CResult_Vec_CFr = _cresult("CResult_Vec_CFr", Vec_CFr)
 CResult_String = _cresult("CResult_String", RlnString)
+CResult_Vec_bool = _cresult("CResult_Vec_bool", Vec_bool)
 
 _lib = None
 
@@ -187,6 +188,90 @@ def lib():
         "ffi_set_metadata": (CBoolResult, [pp, POINTER(Vec_uint8)]),
         "ffi_get_metadata": (CResult_Vec_uint8, [pp]),
         "ffi_flush": (CBoolResult, [pp]),
+        # V3 twins (rln/src/ffi/ffi_rln_v3.rs)
+        "ffi_rln_v3_new_stateless_default": (c_void_p, []),
+        "ffi_rln_v3_new_stateless": (CResult_ptr, [POINTER(Vec_uint8), POINTER(Vec_uint8)]),
+        "ffi_rln_v3_new_with_full_merkle_tree_default": (c_void_p, []),
+        "ffi_rln_v3_new_with_full_merkle_tree": (CResult_ptr, [c_size_t, POINTER(Vec_uint8), POINTER(Vec_uint8)]),
+        "ffi_rln_v3_new_with_optimal_merkle_tree_default": (c_void_p, []),
+        "ffi_rln_v3_new_with_optimal_merkle_tree": (CResult_ptr, [c_size_t, POINTER(Vec_uint8), POINTER(Vec_uint8)]),
+        "ffi_rln_v3_new_with_pm_tree_default": (c_void_p, []),
+        "ffi_rln_v3_new_with_pm_tree": (CResult_ptr, [c_size_t, POINTER(Vec_uint8), POINTER(Vec_uint8), c_char_p]),
+        "ffi_rln_v3_free": (None, [c_void_p]),
+        "ffi_rln_v3_generate_proof": (CResult_ptr, [pp, pp]),
+        "ffi_rln_v3_verify": (CBoolResult, [pp, pp, POINTER(CFr)]),
+        "ffi_rln_v3_verify_with_roots": (CBoolResult, [pp, pp, POINTER(Vec_CFr), POINTER(CFr)]),
+        "ffi_rln_v3_generate_partial_proof": (CResult_ptr, [pp, pp]),
+        "ffi_rln_v3_finish_proof": (CResult_ptr, [pp, pp, pp]),
+        "ffi_rln_v3_witness_input_new_single": (CResult_ptr, [POINTER(CFr)] * 3 + [POINTER(Vec_CFr), POINTER(Vec_uint8), POINTER(CFr), POINTER(CFr)]),
+        "ffi_rln_v3_witness_input_new_multi": (CResult_ptr, [POINTER(CFr), POINTER(CFr), POINTER(Vec_CFr), POINTER(Vec_CFr), POINTER(Vec_uint8),
+                                                              POINTER(CFr), POINTER(CFr), POINTER(Vec_bool)]),
+        "ffi_rln_v3_witness_input_get_identity_secret": (POINTER(CFr), [pp]),
+        "ffi_rln_v3_witness_input_get_user_message_limit": (POINTER(CFr), [pp]),
+        "ffi_rln_v3_witness_input_get_message_id": (CResult_CFr, [pp]),
+        "ffi_rln_v3_witness_input_get_message_ids": (CResult_Vec_CFr, [pp]),
+        "ffi_rln_v3_witness_input_get_path_elements": (Vec_CFr, [pp]),
+        "ffi_rln_v3_witness_input_get_identity_path_index": (Vec_uint8, [pp]),
+        "ffi_rln_v3_witness_input_get_x": (POINTER(CFr), [pp]),
+        "ffi_rln_v3_witness_input_get_external_nullifier": (POINTER(CFr), [pp]),
+        "ffi_rln_v3_witness_input_get_selector_used": (CResult_Vec_bool, [pp]),
+        "ffi_rln_v3_witness_to_bytes_le": (CResult_Vec_uint8, [pp]),
+        "ffi_rln_v3_witness_to_bytes_be": (CResult_Vec_uint8, [pp]),
+        "ffi_bytes_le_to_rln_v3_witness": (CResult_ptr, [POINTER(Vec_uint8)]),
+        "ffi_bytes_be_to_rln_v3_witness": (CResult_ptr, [POINTER(Vec_uint8)]),
+        "ffi_rln_v3_witness_input_free": (None, [c_void_p]),
+        "ffi_rln_v3_partial_witness_input_new": (CResult_ptr, [POINTER(CFr), POINTER(CFr), POINTER(Vec_CFr), POINTER(Vec_uint8)]),
+        "ffi_rln_v3_partial_witness_input_get_identity_secret": (POINTER(CFr), [pp]),
+        "ffi_rln_v3_partial_witness_input_get_user_message_limit": (POINTER(CFr), [pp]),
+        "ffi_rln_v3_partial_witness_input_get_path_elements": (Vec_CFr, [pp]),
+        "ffi_rln_v3_partial_witness_input_get_identity_path_index": (Vec_uint8, [pp]),
+        "ffi_rln_v3_witness_to_partial_witness": (c_void_p, [pp]),
+        "ffi_rln_v3_partial_witness_to_bytes_le": (CResult_Vec_uint8, [pp]),
+        "ffi_rln_v3_partial_witness_to_bytes_be": (CResult_Vec_uint8, [pp]),
+        "ffi_bytes_le_to_rln_v3_partial_witness": (CResult_ptr, [POINTER(Vec_uint8)]),
+        "ffi_bytes_be_to_rln_v3_partial_witness": (CResult_ptr, [POINTER(Vec_uint8)]),
+        "ffi_rln_v3_partial_witness_input_free": (None, [c_void_p]),
+        "ffi_rln_v3_proof_get_values": (c_void_p, [pp]),
+        "ffi_rln_v3_proof_to_bytes_le": (CResult_Vec_uint8, [pp]),
+        "ffi_rln_v3_proof_to_bytes_mixed": (CResult_Vec_uint8, [pp]),
+        "ffi_bytes_le_to_rln_v3_proof": (CResult_ptr, [POINTER(Vec_uint8)]),
+        "ffi_bytes_mixed_to_rln_v3_proof": (CResult_ptr, [POINTER(Vec_uint8)]),
+        "ffi_rln_v3_proof_free": (None, [c_void_p]),
+        "ffi_rln_v3_partial_proof_to_bytes_le": (CResult_Vec_uint8, [pp]),
+        "ffi_bytes_le_to_rln_v3_partial_proof": (CResult_ptr, [POINTER(Vec_uint8)]),
+        "ffi_rln_v3_partial_proof_free": (None, [c_void_p]),
+        "ffi_rln_v3_proof_values_get_root": (POINTER(CFr), [pp]),
+        "ffi_rln_v3_proof_values_get_x": (POINTER(CFr), [pp]),
+        "ffi_rln_v3_proof_values_get_external_nullifier": (POINTER(CFr), [pp]),
+        "ffi_rln_v3_proof_values_get_y": (CResult_CFr, [pp]),
+        "ffi_rln_v3_proof_values_get_nullifier": (CResult_CFr, [pp]),
+        "ffi_rln_v3_proof_values_get_selector_used": (CResult_Vec_bool, [pp]),
+        "ffi_rln_v3_proof_values_get_ys": (CResult_Vec_CFr, [pp]),
+        "ffi_rln_v3_proof_values_get_nullifiers": (CResult_Vec_CFr, [pp]),
+        "ffi_rln_v3_proof_values_to_bytes_le": (CResult_Vec_uint8, [pp]),
+        "ffi_rln_v3_proof_values_to_bytes_be": (CResult_Vec_uint8, [pp]),
+        "ffi_bytes_le_to_rln_v3_proof_values": (CResult_ptr, [POINTER(Vec_uint8)]),
+        "ffi_bytes_be_to_rln_v3_proof_values": (CResult_ptr, [POINTER(Vec_uint8)]),
+        "ffi_rln_v3_proof_values_free": (None, [c_void_p]),
+        "ffi_rln_v3_compute_id_secret": (CResult_CFr, [POINTER(CFr)] * 4),
+        "ffi_rln_v3_recover_id_secret": (CResult_CFr, [pp, pp]),
+        "ffi_rln_v3_merkle_proof_free": (None, [POINTER(FFI_MerkleProof)]),
+        "ffi_rln_v3_delete_leaf": (CBoolResult, [pp, c_size_t]),
+        "ffi_rln_v3_set_leaf": (CBoolResult, [pp, c_size_t, POINTER(CFr)]),
+        "ffi_rln_v3_get_leaf": (CResult_CFr, [pp, c_size_t]),
+        "ffi_rln_v3_leaves_set": (c_size_t, [pp]),
+        "ffi_rln_v3_set_next_leaf": (CBoolResult, [pp, POINTER(CFr)]),
+        "ffi_rln_v3_set_leaves_from": (CBoolResult, [pp, c_size_t, POINTER(Vec_CFr)]),
+        "ffi_rln_v3_init_tree_with_leaves": (CBoolResult, [pp, POINTER(Vec_CFr)]),
+        "ffi_rln_v3_atomic_operation": (CBoolResult, [pp, c_size_t, POINTER(Vec_CFr), POINTER(Vec_size)]),
+        "ffi_rln_v3_seq_atomic_operation": (CBoolResult, [pp, POINTER(Vec_CFr), POINTER(Vec_uint8)]),
+        "ffi_rln_v3_get_root": (POINTER(CFr), [pp]),
+        "ffi_rln_v3_get_merkle_proof": (CResult_MerkleProof, [pp, c_size_t]),
+        "ffi_rln_v3_set_metadata": (CBoolResult, [pp, POINTER(Vec_uint8)]),
+        "ffi_rln_v3_get_metadata": (CResult_Vec_uint8, [pp]),
+        "ffi_rln_v3_flush": (CBoolResult, [pp]),
+        "rlnb200_v3_generate_proof_with_rs": (CResult_ptr, [pp, pp, POINTER(CFr), POINTER(CFr)]),
+        "rlnb200_v3_finish_proof_with_rs": (CResult_ptr, [pp, pp, pp, POINTER(CFr), POINTER(CFr)]),
         # extensions
         "rlnb200_finish_rln_proof_with_rs": (CResult_ptr, [pp, pp, pp, POINTER(CFr), POINTER(CFr)]),
         "rlnb200_bytes_le_to_rln_partial_proof": (CResult_ptr, [pp, POINTER(Vec_uint8)]),
