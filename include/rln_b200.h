@@ -63,6 +63,7 @@ typedef struct CResult_CFr { CFr_t *ok; RlnString err; } CResult_CFr_t;
 typedef struct CResult_Vec_uint8 { Vec_uint8_t ok; RlnString err; } CResult_Vec_uint8_t;
 typedef struct CResult_Vec_CFr { Vec_CFr_t ok; RlnString err; } CResult_Vec_CFr_t;
 typedef struct CResult_String { RlnString ok; RlnString err; } CResult_String_t;
+typedef struct Vec_String { RlnString *ptr; size_t len; size_t cap; } Vec_String_t;   /* repr_c::Vec<repr_c::String> */
 typedef struct CResult_Vec_bool { Vec_bool_t ok; RlnString err; } CResult_Vec_bool_t;
 
 /* V3 objects (rln/src/ffi/ffi_rln_v3.rs:312,614,866,1013,1097,1141,1365) */
@@ -232,6 +233,11 @@ CResult_CFr_t ffi_compute_id_secret(const CFr_t *share1_x, const CFr_t *share1_y
                                     const CFr_t *share2_y);                                      /* :1014-1033 */
 CResult_CFr_t ffi_recover_id_secret(FFI_RLNProofValues_t *const *proof_values_1,
                                     FFI_RLNProofValues_t *const *proof_values_2);                /* :1035-1049 */
+/* proof from a witness calculated outside (snarkjs / circom): one decimal string per wire; the graph evaluation is skipped */
+CResult_FFI_RLNProof_t ffi_generate_rln_proof_with_witness(FFI_RLN_t *const *rln, const Vec_String_t *calculated_witness,
+                                                           FFI_RLNWitnessInput_t *const *witness);              /* :874-916 */
+CResult_FFI_RLNProof_t rlnb200_generate_rln_proof_with_witness_rs(FFI_RLN_t *const *rln, const Vec_String_t *calculated_witness,
+                                                                  FFI_RLNWitnessInput_t *const *witness, const CFr_t *r, const CFr_t *s);
 CBoolResult_t ffi_set_metadata(FFI_RLN_t **rln, const Vec_uint8_t *metadata);                    /* ffi_tree.rs:228-240 */
 CResult_Vec_uint8_t ffi_get_metadata(FFI_RLN_t *const *rln);                                     /* ffi_tree.rs:242-254 */
 CBoolResult_t ffi_flush(FFI_RLN_t **rln);                                                        /* ffi_tree.rs:256-268 */

@@ -464,6 +464,29 @@ def test_big_endian_proof_records_and_metadata(z, rln10, goldens):
     rln10.flush()
 
 
+def test_proof_from_external_witness(z, rln10, goldens):
+    """rln/src/public.rs:643-658 / ffi_rln.rs:874-916: the wire assignment is calculated outside (here by the oracle's graph
+    evaluator) and handed over as decimal strings; negative representatives are accepted (proof.rs:593-614)"""
+    from pyref import groth16 as G
+    k = goldens["derived"]["kat_proof_d10"]
+    args = kat_witness_args(10, k["inputs"])
+    g = G.parse_graph(resource(10, "graph.bin"))
+    wires = G.evaluate(g, G.inputs_buffer(g, *args))
+    wires[7] -= R                      # a negative representative of the same field element
+    wires[9] += 3 * R                  # and one above the modulus
+    wit = z.RLNWitnessInput.from_bytes_le(witness_le(*args))
+    proof = rln10.generate_rln_proof_with_witness(wires, wit, int(k["inputs"]["r"]), int(k["inputs"]["s"]))
+    assert proof.to_bytes_le().hex() == k["rln_proof_le_hex"]
+    p2 = rln10.generate_rln_proof_with_witness(wires, wit)
+    assert rln10.verify_with_roots(p2, p2.values.x, [])
+    with pytest.raises(z.RLNError, match="calculated witness has"):
+        rln10.generate_rln_proof_with_witness(wires[:-1], wit)
+    wires[100] += 1                    # an inconsistent assignment still yields a proof (the prover never checks constraints) — it must not verify
+    p3 = rln10.generate_rln_proof_with_witness(wires, wit, 5, 6)
+    with pytest.raises(z.RLNError, match="Invalid proof provided"):
+        rln10.verify_with_roots(p3, p3.values.x, [])
+
+
 def test_v3_api(z, goldens, oracle):
     """rln/tests/ffi.rs V3 section + rln/tests/public.rs: RLNV3 over the same prover — stateless and stateful builds, proof ==
     the V1 golden proof for the same (r, s), verify / verify_with_roots semantics, tree ops, V3 wire forms of the proof"""

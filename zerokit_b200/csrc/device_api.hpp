@@ -70,6 +70,8 @@ struct CircuitDev {
 };
 // inputs: n × n_slots canonical bytes → vals [n_nodes][B] (Montgomery).  err[j] != 0 if node evaluation failed.
 void launch_witness(const CircuitDev& c, const uint8_t* d_inputs, Fr* d_vals, u32 B, u32* d_err, cudaStream_t s);
+// wires: B × n_wires canonical 32-byte values (an externally calculated witness) → the same vals layout
+void launch_scatter_wires(const CircuitDev& c, const uint8_t* d_wires, Fr* d_vals, u32 B, u32* d_err, cudaStream_t s);
 // a,b,c [domain][B]; afterwards abuf holds h = a·b − c on the coset (natural order)
 void launch_qap(const CircuitDev& c, const Fr* d_vals, Fr* d_a, Fr* d_b, Fr* d_c, u32 B, cudaStream_t s);
 // plain batched NTT for tests: data [n][B] natural order in/out

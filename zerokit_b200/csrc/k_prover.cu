@@ -60,6 +60,18 @@ __global__ void __launch_bounds__(32) k_witness(CircuitDev c, const uint8_t* __r
 void launch_witness(const CircuitDev& c, const uint8_t* d_inputs, Fr* d_vals, u32 B, u32* d_err, cudaStream_t s) {
     k_witness<<<(B + 31) / 32, 32, 0, s>>>(c, d_inputs, d_vals, B, d_err);
 }
+// externally calculated witness (generate_zk_proof_with_witness, rln/src/protocol/proof.rs:705-732): wire i of proof j goes to the
+// node the graph assigns to that wire, so the QAP and the MSMs read it exactly as if k_witness had produced it
+__global__ void k_scatter_wires(CircuitDev c, const uint8_t* __restrict__ wires, Fr* __restrict__ vals, u32 B, u32* __restrict__ err) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 j = blockIdx.y;
+    if (i == 0) err[j] = 0;
+    if (i >= c.n_wires) return;
+    st_fp(vals + (size_t)c.signals[i] * B + j, load_canonical_fr(wires + ((size_t)j * c.n_wires + i) * 32));
+}
+void launch_scatter_wires(const CircuitDev& c, const uint8_t* d_wires, Fr* d_vals, u32 B, u32* d_err, cudaStream_t s) {
+    k_scatter_wires<<<dim3((c.n_wires + 127) / 128, B), 128, 0, s>>>(c, d_wires, d_vals, B, d_err);
+}
 
 // ------------------------------------------------------------------------------------------- A·w, B·w, c = a∘b
 // grid: (ceil(B/128), domain).  Row i < n_constraints: sparse dot products (qap.rs:45-52);

@@ -392,6 +392,25 @@ class Rln {
     std::vector<uint8_t> metadata;   // set_metadata / get_metadata (rln/src/public.rs:499-515): opaque bytes kept beside the tree
     void sync() { ZK_CUDA_CHECK(cudaStreamSynchronize(stream_)); }   // flush: nothing is buffered outside HBM
     bool overlap_qap_ = false;
+    const uint8_t* ext_wires_ = nullptr;   // device pointer: B × n_wires canonical values that replace the graph evaluation
+    // generate_rln_proof_with_witness (rln/src/public.rs:643-658): wires = n_wires × 32 canonical bytes calculated by the caller
+    void prove_with_wires(const Witness& w, const std::vector<uint8_t>& wires, const uint8_t* rs, RlnProof& out) {
+        if (wires.size() != 32 * n_wires())
+            throw RlnError("Protocol error: the calculated witness has " + std::to_string(wires.size() / 32) + " elements, the circuit has " +
+                           std::to_string(n_wires()) + " wires");
+        DevMem d;
+        d.upload(wires.data(), wires.size());
+        ext_wires_ = d.as<uint8_t>();
+        std::vector<RlnProof> o;
+        try {
+            prove_host(std::vector<Witness>(1, w), rs, o);
+        } catch (...) {
+            ext_wires_ = nullptr;
+            throw;
+        }
+        ext_wires_ = nullptr;
+        out = o[0];
+    }
     void verify_batch(const uint8_t* proofs128, const uint8_t* publics_circuit_order, size_t n, uint8_t* ok);
     // witness, qap, g1 accumulate, g1 reduce, g2 accumulate, g2 reduce, assemble, proof values
     float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -980,7 +999,8 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
             ZK_CUDA_CHECK(cudaEventRecord(join_, side_));
         }
         ZK_CUDA_CHECK(cudaEventRecord(ev_[0], s));
-        launch_witness(circ_, in, ws_vals_.as<Fr>(), B, ws_err_.as<u32>(), s);
+        if (ext_wires_) launch_scatter_wires(circ_, ext_wires_, ws_vals_.as<Fr>(), B, ws_err_.as<u32>(), s);
+        else launch_witness(circ_, in, ws_vals_.as<Fr>(), B, ws_err_.as<u32>(), s);
         ZK_CUDA_CHECK(cudaEventRecord(ev_[1], s));
         const bool overlap_qap = phase != MSM_KNOWN && overlap_qap_;
         if (overlap_qap) {   // h is only read by the H tasks: the A / B1 / L tasks start right after the witness

@@ -27,6 +27,10 @@ class Vec_size(Structure):
     _fields_ = [("ptr", POINTER(c_size_t)), ("len", c_size_t), ("cap", c_size_t)]
 
 
+class Vec_String(Structure):
+    _fields_ = [("ptr", POINTER(Vec_uint8)), ("len", c_size_t), ("cap", c_size_t)]
+
+
 class CFr(Structure):
     _fields_ = [("bytes", c_uint8 * 32)]
 
@@ -185,6 +189,8 @@ def lib():
         "ffi_bytes_be_to_rln_partial_proof": (CResult_ptr, [POINTER(Vec_uint8)]),
         "ffi_compute_id_secret": (CResult_CFr, [POINTER(CFr)] * 4),
         "ffi_recover_id_secret": (CResult_CFr, [pp, pp]),
+        "ffi_generate_rln_proof_with_witness": (CResult_ptr, [pp, POINTER(Vec_String), pp]),
+        "rlnb200_generate_rln_proof_with_witness_rs": (CResult_ptr, [pp, POINTER(Vec_String), pp, POINTER(CFr), POINTER(CFr)]),
         "ffi_set_metadata": (CBoolResult, [pp, POINTER(Vec_uint8)]),
         "ffi_get_metadata": (CResult_Vec_uint8, [pp]),
         "ffi_flush": (CBoolResult, [pp]),

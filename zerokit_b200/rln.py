@@ -609,6 +609,21 @@ class RLN:
         return RLNProof(_check_ptr(ffi.lib().rlnb200_generate_rln_proof_with_rs(byref(self._h), byref(witness._h), byref(_cfr(r)), byref(_cfr(s)))))
 
     # two-phase proving (public.rs:664-697)
+    def generate_rln_proof_with_witness(self, calculated_witness, witness: RLNWitnessInput, r: int = None, s: int = None) -> RLNProof:
+        """rln/src/public.rs:643-658: `calculated_witness` is the full wire assignment (ints, negative allowed) computed outside"""
+        strs = [str(int(v)).encode() for v in calculated_witness]
+        arr = (Vec_uint8 * max(len(strs), 1))()
+        keep = []
+        for i, b in enumerate(strs):
+            buf = (c_uint8 * len(b)).from_buffer_copy(b)
+            keep.append(buf)
+            arr[i] = Vec_uint8(cast(buf, POINTER(c_uint8)), len(b), len(b))
+        vs = ffi.Vec_String(cast(arr, POINTER(Vec_uint8)), len(strs), len(strs))
+        if r is None:
+            return RLNProof(_check_ptr(ffi.lib().ffi_generate_rln_proof_with_witness(byref(self._h), byref(vs), byref(witness._h))))
+        return RLNProof(_check_ptr(ffi.lib().rlnb200_generate_rln_proof_with_witness_rs(byref(self._h), byref(vs), byref(witness._h),
+                                                                                         byref(_cfr(r)), byref(_cfr(s)))))
+
     def generate_partial_zk_proof(self, partial_witness: RLNPartialWitnessInput) -> RLNPartialProof:
         return RLNPartialProof(_check_ptr(ffi.lib().ffi_generate_partial_zk_proof(byref(self._h), byref(partial_witness._h))))
 
