@@ -39,10 +39,11 @@ void launch_hash_pairs(const Fr* d_in, Fr* d_out, size_t n, cudaStream_t s);
 // Merkle tree in HBM, 1-indexed heap: root = nodes[1], level l = nodes[2^l .. 2^(l+1)), leaf i = nodes[2^depth + i].
 // fill with the empty-tree values (zeros[k] per level)
 void launch_merkle_fill_empty(Fr* d_nodes, u32 depth, cudaStream_t s);
-// leaves (canonical bytes, on device) → nodes[2^depth+start ..), then rehash the touched ancestors level by level
-void launch_merkle_set_range(Fr* d_nodes, u32 depth, size_t start, const uint8_t* d_leaves_bytes, size_t count, cudaStream_t s);
+// leaves (canonical bytes, on device) → nodes[2^depth+start ..), then rehash the touched ancestors level by level;
+// returns the number of kernels launched
+u32 launch_merkle_set_range(Fr* d_nodes, u32 depth, size_t start, const uint8_t* d_leaves_bytes, size_t count, cudaStream_t s);
 // rehash ancestors of leaf range [start, start+count)
-void launch_merkle_rehash(Fr* d_nodes, u32 depth, size_t start, size_t count, cudaStream_t s);
+u32 launch_merkle_rehash(Fr* d_nodes, u32 depth, size_t start, size_t count, cudaStream_t s);
 // membership paths: for each index, depth sibling values (canonical bytes, leaf→root) and depth index bits
 void launch_merkle_paths(const Fr* d_nodes, u32 depth, const u64* d_indices, size_t n, uint8_t* d_elems_bytes, uint8_t* d_bits, cudaStream_t s);
 // proof values per witness (rln/src/protocol/witness.rs:759-828): inputs layout = circuit input slots

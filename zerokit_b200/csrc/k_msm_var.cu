@@ -21,6 +21,7 @@ struct VarMsmWorkspace {
     size_t max_n = 0;
     u32 *keys_in = nullptr, *keys_out = nullptr, *vals_in = nullptr, *vals_out = nullptr;
     u32 *bucket_start = nullptr, *bucket_end = nullptr;
+    u32 *size_key = nullptr, *size_key_out = nullptr, *order_in = nullptr, *order = nullptr;  // buckets ordered by size, largest first
     G1XYZZ* buckets = nullptr;
     G1XYZZ* seg = nullptr;
     G1XYZZ* win = nullptr;
@@ -37,7 +38,7 @@ static void msm_params(size_t n, int& c, int& K) {
     if (c > 16) c = 16;
     K = (255 + c - 1) / c;  // K·c ≥ 255 keeps the top signed digit + carry below 2^(c−1)
 }
-static const int SEGS = 256;  // segments per window in the bucket reduction
+static const int SEGS = 2048;  // segments per window in the bucket reduction (16 buckets each at c = 16: 32 K short threads)
 
 VarMsmWorkspace* var_msm_workspace_create(size_t max_n) {
     VarMsmWorkspace* w = new VarMsmWorkspace();
@@ -61,16 +62,22 @@ VarMsmWorkspace* var_msm_workspace_create(size_t max_n) {
     ZK_CUDA_CHECK(cudaMalloc(&w->bucket_start, 4 * (max_b + 1)));
     ZK_CUDA_CHECK(cudaMalloc(&w->bucket_end, 4 * (max_b + 1)));
     ZK_CUDA_CHECK(cudaMalloc(&w->buckets, sizeof(G1XYZZ) * max_b));
+    ZK_CUDA_CHECK(cudaMalloc(&w->size_key, 4 * max_b));
+    ZK_CUDA_CHECK(cudaMalloc(&w->size_key_out, 4 * max_b));
+    ZK_CUDA_CHECK(cudaMalloc(&w->order_in, 4 * max_b));
+    ZK_CUDA_CHECK(cudaMalloc(&w->order, 4 * max_b));
     ZK_CUDA_CHECK(cudaMalloc(&w->seg, sizeof(G1XYZZ) * 32 * SEGS));
     ZK_CUDA_CHECK(cudaMalloc(&w->win, sizeof(G1XYZZ) * 32));
-    cub::DeviceRadixSort::SortPairs(nullptr, w->cub_tmp_bytes, w->keys_in, w->keys_out, w->vals_in, w->vals_out, (int64_t)max_items, 0, 32);
+    cub::DeviceRadixSort::SortPairs(nullptr, w->cub_tmp_bytes, w->keys_in, w->keys_out, w->vals_in, w->vals_out,
+                                    (int64_t)(max_items > max_b ? max_items : max_b), 0, 32);
     ZK_CUDA_CHECK(cudaMalloc(&w->cub_tmp, w->cub_tmp_bytes));
     return w;
 }
 void var_msm_workspace_destroy(VarMsmWorkspace* w) {
     if (!w) return;
     cudaFree(w->keys_in); cudaFree(w->keys_out); cudaFree(w->vals_in); cudaFree(w->vals_out);
-    cudaFree(w->bucket_start); cudaFree(w->bucket_end); cudaFree(w->buckets); cudaFree(w->seg); cudaFree(w->win); cudaFree(w->cub_tmp);
+    cudaFree(w->bucket_start); cudaFree(w->bucket_end); cudaFree(w->buckets);
+    cudaFree(w->size_key); cudaFree(w->size_key_out); cudaFree(w->order_in); cudaFree(w->order); cudaFree(w->seg); cudaFree(w->win); cudaFree(w->cub_tmp);
     delete w;
 }
 
@@ -114,12 +121,24 @@ __global__ void k_bucket_bounds(const u32* __restrict__ keys, size_t items, u32 
     if (i + 1 == items || keys[i + 1] != k) end[k] = (u32)i + 1;
 }
 
-// the hot kernel: bucket b = Σ ± bases[vals[t]] for t in [start[b], end[b])
-__global__ void __launch_bounds__(128) k_bucket_sum(const G1Affine* __restrict__ bases, const u32* __restrict__ vals,
-                                                    const u32* __restrict__ start, const u32* __restrict__ end, size_t n_buckets,
-                                                    G1XYZZ* __restrict__ buckets) {
-    size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+// sort key of a bucket: ~size, so that an ascending radix sort lists the fullest buckets first
+__global__ void k_bucket_sizes(const u32* __restrict__ start, const u32* __restrict__ end, u32 n_buckets, u32* __restrict__ key,
+                               u32* __restrict__ idx) {
+    const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_buckets) return;
+    key[b] = ~(end[b] - start[b]);
+    idx[b] = b;
+}
+
+// the hot kernel: bucket b = Σ ± bases[vals[t]] for t in [start[b], end[b]).  Thread i takes the i-th fullest bucket: the 32
+// buckets of a warp then hold (almost) the same number of points — no lanes idling behind the longest bucket — and the big
+// buckets of the short top window start first instead of forming the tail of the launch.
+__global__ void __launch_bounds__(128) k_bucket_sum(const G1Affine* __restrict__ bases, const u32* __restrict__ vals,
+                                                    const u32* __restrict__ start, const u32* __restrict__ end, const u32* __restrict__ order,
+                                                    size_t n_buckets, G1XYZZ* __restrict__ buckets) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n_buckets) return;
+    const u32 b = order[i];
     const u32 lo = start[b], hi = end[b];
     G1XYZZ acc = G1XYZZ::infinity();
     if (lo < hi) {
@@ -214,7 +233,11 @@ void launch_var_msm_g1(VarMsmWorkspace* w, const G1Affine* d_bases, const uint8_
     ZK_CUDA_CHECK(cudaMemsetAsync(w->bucket_start, 0, 4 * n_buckets, s));
     ZK_CUDA_CHECK(cudaMemsetAsync(w->bucket_end, 0, 4 * n_buckets, s));
     k_bucket_bounds<<<(unsigned)((items + 255) / 256), 256, 0, s>>>(w->keys_out, items, (u32)n_buckets, w->bucket_start, w->bucket_end);
-    k_bucket_sum<<<(unsigned)((n_buckets + 127) / 128), 128, 0, s>>>(d_bases, w->vals_out, w->bucket_start, w->bucket_end, n_buckets, w->buckets);
+    k_bucket_sizes<<<(unsigned)((n_buckets + 255) / 256), 256, 0, s>>>(w->bucket_start, w->bucket_end, (u32)n_buckets, w->size_key, w->order_in);
+    tmp = w->cub_tmp_bytes;
+    cub::DeviceRadixSort::SortPairs(w->cub_tmp, tmp, w->size_key, w->size_key_out, w->order_in, w->order, (int64_t)n_buckets, 0, 32, s);
+    k_bucket_sum<<<(unsigned)((n_buckets + 127) / 128), 128, 0, s>>>(d_bases, w->vals_out, w->bucket_start, w->bucket_end, w->order, n_buckets,
+                                                                     w->buckets);
     const u32 n_seg = half < (u32)SEGS ? half : (u32)SEGS;
     const u32 seg_len = half / n_seg;
     k_segment_reduce<<<dim3((n_seg + 63) / 64, K), 64, 0, s>>>(w->buckets, half, seg_len, w->seg);

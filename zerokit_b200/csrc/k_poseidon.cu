@@ -117,20 +117,81 @@ __global__ void __launch_bounds__(128) k_merkle_level(Fr* __restrict__ nodes, si
     Fr l = ld_fp(nodes + 2 * p), r = ld_fp(nodes + 2 * p + 1);
     st_fp(nodes + p, d_hash2(l, r));
 }
-void launch_merkle_rehash(Fr* d_nodes, u32 depth, size_t start, size_t count, cudaStream_t s) {
-    if (!count) return;
+// Latency-bound levels (the top of the tree, and every level of a single-leaf update): one hash is ≈ 65 rounds of a serial
+// dependency chain, 0.26 ms for one thread.  Three lanes share a hash instead — lane k owns state element k, applies its own
+// S-box, reads the other two elements with warp shuffles and computes row k of the MDS product — which cuts the chain per
+// round from (3 S-boxes + 3 rows) to (1 S-box + 1 row).  A warp carries 10 hashes on lanes 0..29.
+__device__ __forceinline__ Fr shfl_fr(const Fr& v, int src) {
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = __shfl_sync(0xffffffffu, v.l[i], src);
+    return r;
+}
+// mine: element k of the initial state (0, left, right); returns the hash on every lane of the group
+__device__ __forceinline__ Fr poseidon3_coop(Fr mine, int k, int base) {
+    constexpr int RF = PoseidonShape<3>::RF, RP = PoseidonShape<3>::RP;
+    const Fr m0 = c_pt.mds3[k * 3], m1 = c_pt.mds3[k * 3 + 1], m2 = c_pt.mds3[k * 3 + 2];
+    const int s1 = base + 1 < 32 ? base + 1 : 31, s2 = base + 2 < 32 ? base + 2 : 31;
+#pragma unroll 1
+    for (int r = 0; r < RF + RP; r++) {
+        mine += c_pt.ark3[r * 3 + k];
+        const bool full = (r < RF / 2) || (r >= RF / 2 + RP);
+        if (full || k == 0) mine = sbox5(mine);
+        const Fr st[3] = {shfl_fr(mine, base), shfl_fr(mine, s1), shfl_fr(mine, s2)};
+        const Fr row[3] = {m0, m1, m2};
+        mine = Fr::dot<3>(st, row);
+    }
+    return shfl_fr(mine, base);
+}
+// parents [first, first+count) of one level, 3 lanes per hash
+__global__ void __launch_bounds__(128) k_merkle_level_coop(Fr* __restrict__ nodes, size_t first, size_t count) {
+    const int lane = threadIdx.x & 31, g = lane / 3, k = lane - 3 * g;
+    const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    const size_t i = warp * 10 + g;
+    const bool live = g < 10 && i < count;
+    const size_t p = first + (live ? i : 0);
+    Fr mine = Fr::zero();
+    if (live && k) mine = ld_fp(nodes + 2 * p + (k - 1));
+    const Fr h = poseidon3_coop(mine, k, 3 * g);
+    if (live && k == 0) st_fp(nodes + p, h);
+}
+// the last levels of a range, while a level has at most 10 parents: one warp walks them all in a single launch
+__global__ void __launch_bounds__(32) k_merkle_top_coop(Fr* nodes, size_t lo, size_t hi, u32 levels) {
+    const int lane = threadIdx.x, g = lane / 3, k = lane - 3 * g;
+    for (u32 l = 0; l < levels; l++) {
+        lo >>= 1;
+        hi >>= 1;
+        const bool live = g < 10 && lo + g <= hi;
+        const size_t p = live ? lo + g : lo;
+        Fr mine = Fr::zero();
+        if (live && k) mine = ld_fp(nodes + 2 * p + (k - 1));
+        const Fr h = poseidon3_coop(mine, k, 3 * g);
+        if (live && k == 0) st_fp(nodes + p, h);
+        __threadfence_block();
+        __syncwarp();
+    }
+}
+u32 launch_merkle_rehash(Fr* d_nodes, u32 depth, size_t start, size_t count, cudaStream_t s) {
+    if (!count) return 0;
     size_t lo = ((size_t)1 << depth) + start, hi = lo + count - 1;
     for (u32 l = 0; l < depth; l++) {
+        if (((hi >> 1) - (lo >> 1) + 1) <= 10) {   // and so is every level above
+            k_merkle_top_coop<<<1, 32, 0, s>>>(d_nodes, lo, hi, depth - l);
+            return l + 1;
+        }
         lo >>= 1;
         hi >>= 1;
         size_t n = hi - lo + 1;
-        k_merkle_level<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_nodes, lo, n);
+        // below ≈ 8 K parents the one-thread-per-hash kernel cannot fill the chip and its 0.26 ms chain is the cost of the level
+        if (n <= 8192) k_merkle_level_coop<<<(unsigned)((n + 39) / 40), 128, 0, s>>>(d_nodes, lo, n);
+        else k_merkle_level<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_nodes, lo, n);
     }
+    return depth;
 }
-void launch_merkle_set_range(Fr* d_nodes, u32 depth, size_t start, const uint8_t* d_leaves_bytes, size_t count, cudaStream_t s) {
-    if (!count) return;
+u32 launch_merkle_set_range(Fr* d_nodes, u32 depth, size_t start, const uint8_t* d_leaves_bytes, size_t count, cudaStream_t s) {
+    if (!count) return 0;
     k_set_leaves<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d_nodes, depth, start, d_leaves_bytes, count);
-    launch_merkle_rehash(d_nodes, depth, start, count, s);
+    return 1 + launch_merkle_rehash(d_nodes, depth, start, count, s);
 }
 
 // one thread per (path, level): sibling gather — 32 B read, 32 B write, pure HBM traffic

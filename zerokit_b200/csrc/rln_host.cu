@@ -841,8 +841,7 @@ void Rln::set_tree(size_t depth) {
 void Rln::set_range_device(size_t start, const uint8_t* d_leaves, size_t count, cudaStream_t s) {
     if (count == 0) return;
     if (start + count > capacity() || start + count < start) throw RlnError("Merkle tree error: set_range got too many leaves");
-    launch_merkle_set_range(d_nodes_.as<Fr>(), (u32)tree_depth_, start, d_leaves, count, s);
-    g_launch_count += 1 + tree_depth_;
+    g_launch_count += launch_merkle_set_range(d_nodes_.as<Fr>(), (u32)tree_depth_, start, d_leaves, count, s);
     if (start + count > next_index_) next_index_ = start + count;
 }
 void Rln::set_range_host(size_t start, const uint8_t* leaves, size_t count) {
@@ -917,8 +916,7 @@ void Rln::override_range(size_t start, const uint8_t* leaves, size_t n_leaves, s
     for (size_t i : indices) {  // removals: reset to the default leaf
         DevMem tmp;
         tmp.upload(zero, 32);
-        launch_merkle_set_range(d_nodes_.as<Fr>(), (u32)tree_depth_, i, tmp.as<uint8_t>(), 1, stream_);
-        g_launch_count += 1 + tree_depth_;
+        g_launch_count += launch_merkle_set_range(d_nodes_.as<Fr>(), (u32)tree_depth_, i, tmp.as<uint8_t>(), 1, stream_);
         ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
     }
     next_index_ = keep;
