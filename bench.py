@@ -193,7 +193,7 @@ def run_gpu(args, rank, local_rank, world):
     t0 = time.time()
     rln = z.RLN.new(DEPTH)
     info = rln.table_info()
-    log(f"[rank {rank}] RLN.new: {time.time() - t0:.1f}s, tables G1 c={info['window_bits']} K={info['windows']}{' x2 (GLV)' if info['glv'] else ''}, G2 c={info['window_bits_g2']} K={info['windows_g2']}, {info['table_bytes'] / 2**30:.1f} GiB")
+    log(f"[rank {rank}] RLN.new: {time.time() - t0:.1f}s, tables G1 c={info['window_bits']} K={info['windows']}{' x2 (GLV)' if info['glv'] else ''}, G2 c={info['window_bits_g2']} K={info['windows_g2']}{' x2 (GLV)' if info['glv'] else ''}, {info['table_bytes'] / 2**30:.1f} GiB")
     n = BATCH
     slots = rln.input_slots()
     # ---- inputs: rank 0 generates world·n distinct witnesses; NCCL scatters contiguous slices (zerokit_b200/sharding.py)

@@ -91,6 +91,7 @@ struct FixedMsmPlan {
     int c, K;            // G1 tables: window bits, windows
     int glv;             // G1 scalars are split k = k₁ + k₂·λ (|kᵢ| < 2^128): K covers 129 bits and every base is visited twice
     int cd, Kd;          // window bits / windows of the δ₁ table (full 254-bit scalars, no split)
+    int cd2, Kd2;        // the same for the δ₂ table
     int c2, K2;          // G2 tables (few bases, so a wider window is affordable)
     MsmGroupDev g1[4];   // A, B1, L, H
     MsmGroupDev g2;      // B2

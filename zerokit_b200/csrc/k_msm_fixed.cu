@@ -108,6 +108,12 @@ __device__ __forceinline__ Fq beta() {
     b.l[4] = 0xd4741444u; b.l[5] = 0xaa303344u; b.l[6] = 0x26594943u; b.l[7] = 0x2c3b3f0du;
     return b;
 }
+__device__ __forceinline__ Fq beta2() {   // β² in Montgomery form
+    Fq b;
+    b.l[0] = 0x13e80b9cu; b.l[1] = 0x3350c88eu; b.l[2] = 0xdb5e56b9u; b.l[3] = 0x7dce557cu;
+    b.l[4] = 0xb615564au; b.l[5] = 0x6001b4b8u; b.l[6] = 0x020217e0u; b.l[7] = 0x2682e617u;
+    return b;
+}
 // low NR words of a × b
 template <int NA, int NB, int NR>
 __device__ __forceinline__ void mul_words(const u32* a, const u32* b, u32* r) {
@@ -298,7 +304,12 @@ __device__ __forceinline__ G1XYZZ load_partial(const G1XYZZ* p, u32 half) {
     if (half) v.X = v.X * glv::beta();
     return v;
 }
-__device__ __forceinline__ G2XYZZ load_partial(const G2XYZZ* p, u32) { return *p; }
+// on G2 (the sextic twist over Fq2) the same λ acts as (x, y) ↦ (β²·x, y)
+__device__ __forceinline__ G2XYZZ load_partial(const G2XYZZ* p, u32 half) {
+    G2XYZZ v = *p;
+    if (half) v.X = v.X.scale(glv::beta2());
+    return v;
+}
 
 // sum[group][j] = Σ_{tasks of group} part[task][j]
 template <class F>
@@ -537,7 +548,7 @@ std::vector<MsmTask> msm_make_tasks(const FixedMsmPlan& plan, u32 B, bool g2, in
     };
     u32 total = 0;
     for (int i = 0; i < n_groups; i++) { u32 lo, hi; range(i, lo, hi); total += hi - lo; }
-    const bool glv = !g2 && plan.glv;
+    const bool glv = plan.glv != 0;   // both groups: G1 through β, G2 through β²
     const u32 chunk = pick_chunk((total ? total : 1) * (glv ? 2 : 1), B);
     std::vector<MsmTask> tasks;
     for (int i = 0; i < n_groups; i++) {
@@ -568,9 +579,9 @@ void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, 
             b.tasks = ws.tasks_g1 + first;
             b.part = ws.part_g1 + (size_t)first * B;
             dim3 grid((B + bx - 1) / bx, count);
-            if (plan.glv) {
-                if (accum_variant("RLN_B200_G1_VARIANT") == 1) k_msm_accum<Fq, true, 4, true><<<grid, bx, 0, s>>>(b);
-                else k_msm_accum<Fq, true, 3, true><<<grid, bx, 0, s>>>(b);
+            if (plan.glv) {   // 4 CTAs/SM measured 1.8 % faster than 3 (profiles/README.md)
+                if (accum_variant("RLN_B200_G1_VARIANT") == 1) k_msm_accum<Fq, true, 3, true><<<grid, bx, 0, s>>>(b);
+                else k_msm_accum<Fq, true, 4, true><<<grid, bx, 0, s>>>(b);
             } else switch (accum_variant("RLN_B200_G1_VARIANT")) {
                 case 1: k_msm_accum<Fq, true, 4><<<grid, bx, 0, s>>>(b); break;
                 case 2: k_msm_accum<Fq, false, 4><<<grid, bx, 0, s>>>(b); break;
@@ -591,14 +602,17 @@ void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, 
         AccumArgs<Fq2> a;
         a.src[0] = d_vals; a.src[1] = d_h;
         for (int i = 0; i < 4; i++) { a.row[i] = plan.g2.row; a.table[i] = (const G2Affine*)plan.g2.table; a.which[i] = plan.g2.which_src; }
-        a.tasks = ws.tasks_g2; a.part = ws.part_g2; a.B = B; a.c = plan.c2; a.K = plan.K2; a.glv = 0;
+        a.tasks = ws.tasks_g2; a.part = ws.part_g2; a.B = B; a.c = plan.c2; a.K = plan.K2; a.glv = plan.glv;
         if (ws.n_tasks_g2) {
             dim3 grid((B + bx - 1) / bx, ws.n_tasks_g2);
-            switch (accum_variant("RLN_B200_G2_VARIANT")) {
-                case 1: k_msm_accum<Fq2, false, 2><<<grid, bx, 0, s>>>(a); break;
+            if (plan.glv) {
+                if (accum_variant("RLN_B200_G2_VARIANT") == 1) k_msm_accum<Fq2, true, 2, true><<<grid, bx, 0, s>>>(a);
+                else k_msm_accum<Fq2, false, 2, true><<<grid, bx, 0, s>>>(a);
+            } else switch (accum_variant("RLN_B200_G2_VARIANT")) {
+                case 1: k_msm_accum<Fq2, true, 2><<<grid, bx, 0, s>>>(a); break;
                 case 2: k_msm_accum<Fq2, false, 3><<<grid, bx, 0, s>>>(a); break;
                 case 3: k_msm_accum<Fq2, true, 3><<<grid, bx, 0, s>>>(a); break;
-                default: k_msm_accum<Fq2, true, 2><<<grid, bx, 0, s>>>(a); break;
+                default: k_msm_accum<Fq2, false, 2><<<grid, bx, 0, s>>>(a); break;   // no prefetch: the G2 kernel is register-bound
             }
         }
         if (ws.ev) cudaEventRecord(ws.ev[3], s);
@@ -611,7 +625,7 @@ void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, 
 void launch_assemble(const FixedMsmPlan& plan, const ProverKeyDev& pk, u32 B, const uint8_t* d_rs, MsmWorkspace& ws,
                      const uint8_t* d_partial, uint8_t* d_proofs_out, uint8_t* d_proofs_affine, cudaStream_t s) {
     k_assemble_g1<<<(B + 63) / 64, 64, 0, s>>>(pk, plan.delta1_table, plan.cd, plan.Kd, ws.sum_g1, B, d_rs, d_partial, d_proofs_out, d_proofs_affine);
-    k_assemble_g2<<<(B + 63) / 64, 64, 0, s>>>(pk, plan.delta2_table, plan.c2, plan.K2, ws.sum_g2, B, d_rs, d_partial, d_proofs_out, d_proofs_affine);
+    k_assemble_g2<<<(B + 63) / 64, 64, 0, s>>>(pk, plan.delta2_table, plan.cd2, plan.Kd2, ws.sum_g2, B, d_rs, d_partial, d_proofs_out, d_proofs_affine);
     if (ws.ev) cudaEventRecord(ws.ev[5], s);
 }
 

@@ -725,7 +725,7 @@ void Rln::build_tables() {
     const bool glv = env_int("RLN_B200_GLV", 1) != 0;
     auto windows_g1 = [&](int c1) { return glv ? (size_t)(129 / c1 + 1) : (size_t)((255 + c1 - 1) / c1); };
     auto table_bytes = [&](int c1, int c2) {
-        size_t k1 = windows_g1(c1), k2 = (255 + c2 - 1) / c2;
+        size_t k1 = windows_g1(c1), k2 = windows_g1(c2);
         return (n_g1 * 64 * k1 << (c1 - 1)) + (n_g2 * 128 * k2 << (c2 - 1));
     };
     int c = env_int("RLN_B200_WINDOW_BITS", 0), c2 = env_int("RLN_B200_WINDOW_BITS_G2", 0);
@@ -736,18 +736,21 @@ void Rln::build_tables() {
             if (table_bytes(c, c2 ? c2 : c) + reserve < free_b) break;
     }
     if (c2 == 0) {
-        const int base2 = glv && c_auto ? 12 : c;
+        const int base2 = glv && c_auto ? 13 : c;   // G2 (GLV through β²): c = 15 → 2 × 9 additions per term, 72.6 GB
         for (c2 = base2 + 2; c2 > base2; c2--)
             if (table_bytes(c, c2) + reserve < free_b) break;
     }
     if (c < 5 || c > 16 || c2 < 5 || c2 > 16) throw RlnError("Configuration error: RLN_B200_WINDOW_BITS[_G2] must be in [5, 16]");
-    const int K = (int)windows_g1(c), K2 = (255 + c2 - 1) / c2;
+    const int K = (int)windows_g1(c), K2 = (int)windows_g1(c2);
+    const int cd2 = c2 < 12 ? c2 : 12, Kd2 = (255 + cd2 - 1) / cd2;
     const int cd = c < 12 ? c : 12, Kd = (255 + cd - 1) / cd;   // δ₁ window table: unsplit scalars
     plan_.c = c;
     plan_.K = K;
     plan_.glv = glv ? 1 : 0;
     plan_.cd = cd;
     plan_.Kd = Kd;
+    plan_.cd2 = cd2;
+    plan_.Kd2 = Kd2;
     plan_.c2 = c2;
     plan_.K2 = K2;
     // scalar row of each base: A/B use wire i → node signals[i]; L uses wire ni+i; H uses row i of the h matrix
@@ -786,9 +789,9 @@ void Rln::build_tables() {
         upload_points_g1(zk_.delta_g1, one, b1);
         upload_points_g2(zk_.delta_g2, one, b2);
         d_delta1_tab_.alloc(sizeof(G1Affine) * Kd * ((size_t)1 << (cd - 1)));
-        d_delta2_tab_.alloc(sizeof(G2Affine) * K2 * ((size_t)1 << (c2 - 1)));
+        d_delta2_tab_.alloc(sizeof(G2Affine) * Kd2 * ((size_t)1 << (cd2 - 1)));
         launch_build_table_g1(b1.as<G1Affine>(), 1, cd, Kd, d_delta1_tab_.as<G1Affine>(), 0);
-        launch_build_table_g2(b2.as<G2Affine>(), 1, c2, K2, d_delta2_tab_.as<G2Affine>(), 0);
+        launch_build_table_g2(b2.as<G2Affine>(), 1, cd2, Kd2, d_delta2_tab_.as<G2Affine>(), 0);
         g_launch_count += 4;
         ZK_CUDA_CHECK(cudaDeviceSynchronize());
         plan_.delta1_table = d_delta1_tab_.as<G1Affine>();
