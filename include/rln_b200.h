@@ -418,6 +418,13 @@ int rlnb200_set_device(int device, RlnString *err);
  * G1 / G2 bases, bytes in HBM */
 int rlnb200_table_info(FFI_RLN_t *const *rln, int *window_bits, int *windows, uint64_t *g1_bases, uint64_t *g2_bases,
                        uint64_t *table_bytes, int *window_bits_g2, int *windows_g2);
+/* RLN::get_subtree_root (rln/src/public.rs:877-883; utils/src/merkle_tree/full_merkle_tree.rs:157-184): the ancestor at `level`
+ * (0 = root, tree depth = the leaf itself) of leaf `index`, canonical 32 bytes */
+int rlnb200_get_subtree_root(FFI_RLN_t *const *rln, size_t level, size_t index, uint8_t *out32, RlnString *err);
+/* RLN::get_empty_leaves_indices (public.rs:885-887): indices below leaves_set() that were deleted or never set;
+ * free the result with rlnb200_vec_usize_free */
+int rlnb200_get_empty_leaves_indices(FFI_RLN_t *const *rln, Vec_size_t *out, RlnString *err);
+void rlnb200_vec_usize_free(Vec_size_t v);
 /* 1 when the G1 scalars are GLV-split (k = k1 + k2*lambda, two visits of `windows` windows per base; RLN_B200_GLV=0
  * disables it) */
 int rlnb200_glv_enabled(FFI_RLN_t *const *rln);

@@ -150,6 +150,19 @@ def test_tree_vs_oracle_and_fixture(z, rln10, goldens, oracle):
     exp[0] = exp[3] = 0
     nodes = oracle.merkle_build(10, fr_bytes(exp), 0, 20)
     assert rln10.get_root() == int.from_bytes(nodes[:32], "little")
+    # get_subtree_root / get_empty_leaves_indices (rln/src/public.rs:877-887; utils/tests/merkle_tree.rs)
+    from pyref import poseidon as P
+    assert rln10.get_subtree_root(0, 5) == rln10.get_root() and rln10.get_subtree_root(10, 5) == exp[5]
+    assert rln10.get_subtree_root(9, 4) == P.poseidon([exp[4], exp[5]]) == rln10.get_subtree_root(9, 5)
+    assert rln10.get_subtree_root(8, 6) == P.poseidon([P.poseidon([exp[4], exp[5]]), P.poseidon([exp[6], exp[7]])])
+    assert rln10.get_empty_leaves_indices() == [0, 3]
+    rln10.delete_leaf(7)
+    rln10.set_leaf(0, 5)
+    assert rln10.get_empty_leaves_indices() == [3, 7]
+    with pytest.raises(z.RLNError, match="Invalid index"):
+        rln10.get_subtree_root(11, 0)
+    with pytest.raises(z.RLNError, match="Invalid leaf"):
+        rln10.get_subtree_root(3, 1024)
     with pytest.raises(z.RLNError, match="set_range got too many leaves"):
         rln10.set_leaves_from(1020, leaves[:10])
     with pytest.raises(z.RLNError, match="Leaf index out of bounds"):

@@ -15,9 +15,13 @@
 namespace zk {
 
 __constant__ PoseidonTables c_pt;
+// a second copy in global memory for the cooperative hash: its three lanes read three different constants per round, which the
+// constant cache would serialise; through L1 they are one 96-byte request
+__device__ PoseidonTables g_pt;
 
 void poseidon_upload_tables(const PoseidonTables& t) {
     ZK_CUDA_CHECK(cudaMemcpyToSymbol(c_pt, &t, sizeof(PoseidonTables)));
+    ZK_CUDA_CHECK(cudaMemcpyToSymbol(g_pt, &t, sizeof(PoseidonTables)));
 }
 
 __device__ __forceinline__ Fr d_hash1(const Fr& a) {
@@ -130,11 +134,11 @@ __device__ __forceinline__ Fr shfl_fr(const Fr& v, int src) {
 // mine: element k of the initial state (0, left, right); returns the hash on every lane of the group
 __device__ __forceinline__ Fr poseidon3_coop(Fr mine, int k, int base) {
     constexpr int RF = PoseidonShape<3>::RF, RP = PoseidonShape<3>::RP;
-    const Fr m0 = c_pt.mds3[k * 3], m1 = c_pt.mds3[k * 3 + 1], m2 = c_pt.mds3[k * 3 + 2];
+    const Fr m0 = ldg_fp(&g_pt.mds3[k * 3]), m1 = ldg_fp(&g_pt.mds3[k * 3 + 1]), m2 = ldg_fp(&g_pt.mds3[k * 3 + 2]);
     const int s1 = base + 1 < 32 ? base + 1 : 31, s2 = base + 2 < 32 ? base + 2 : 31;
 #pragma unroll 1
     for (int r = 0; r < RF + RP; r++) {
-        mine += c_pt.ark3[r * 3 + k];
+        mine += ldg_fp(&g_pt.ark3[r * 3 + k]);
         const bool full = (r < RF / 2) || (r >= RF / 2 + RP);
         if (full || k == 0) mine = sbox5(mine);
         const Fr st[3] = {shfl_fr(mine, base), shfl_fr(mine, s1), shfl_fr(mine, s2)};

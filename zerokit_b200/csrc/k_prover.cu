@@ -31,13 +31,29 @@ __global__ void __launch_bounds__(32) k_witness(CircuitDev c, const uint8_t* __r
     if (j >= B) return;
     const uint8_t* in = inputs + (size_t)j * c.n_slots * 32;
     u32 bad = 0;
+    // The program is a serial chain per proof and a warp is alone on its SM, so a node costs (operand load latency + product
+    // latency).  Software pipeline, one node deep: the operands of node i+1 are requested before node i is computed; an
+    // operand that IS node i cannot be requested yet and is forwarded from the register that holds it.
+    uint4 nxt = __ldg(reinterpret_cast<const uint4*>(c.prog));
+    Fr pa = Fr::zero(), pb = Fr::zero(), prev = Fr::zero();
+    bool ha = false, hb = false;
     for (u32 i = 0; i < c.n_nodes; i++) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(c.prog + i));
+        const uint4 raw = nxt;
         const u32 kind = raw.x & 0xff, op = raw.x >> 8;
+        Fr a = pa, b = pb;
+        const bool have_a = ha, have_b = hb;
+        ha = hb = false;
+        if (i + 1 < c.n_nodes) {
+            nxt = __ldg(reinterpret_cast<const uint4*>(c.prog + i + 1));
+            if ((nxt.x & 0xff) == VM_DUO) {
+                if (nxt.y != i) { pa = ld_fp(vals + (size_t)nxt.y * B + j); ha = true; }
+                if (nxt.z != i) { pb = ld_fp(vals + (size_t)nxt.z * B + j); hb = true; }
+            }
+        }
         Fr v;
         if (kind == VM_DUO) {
-            Fr a = ld_fp(vals + (size_t)raw.y * B + j);
-            Fr b = ld_fp(vals + (size_t)raw.z * B + j);
+            if (!have_a) a = prev;   // raw.y == i − 1
+            if (!have_b) b = prev;   // raw.z == i − 1
             if (op == OP_MUL) v = a * b;
             else if (op == OP_ADD) v = a + b;
             else if (op == OP_SUB) v = a - b;
@@ -50,10 +66,11 @@ __global__ void __launch_bounds__(32) k_witness(CircuitDev c, const uint8_t* __r
             if (op == 0) v = ld_fp(vals + (size_t)raw.y * B + j).neg();
             else { bad = 1; v = Fr::zero(); }  // "uno operator Id not implemented" (graph.rs:189-193)
         } else {  // TernCond (graph.rs:216-222)
-            Fr a = ld_fp(vals + (size_t)raw.y * B + j);
-            v = a.is_zero() ? ld_fp(vals + (size_t)raw.w * B + j) : ld_fp(vals + (size_t)raw.z * B + j);
+            Fr t = ld_fp(vals + (size_t)raw.y * B + j);
+            v = t.is_zero() ? ld_fp(vals + (size_t)raw.w * B + j) : ld_fp(vals + (size_t)raw.z * B + j);
         }
         st_fp(vals + (size_t)i * B + j, v);
+        prev = v;
     }
     err[j] = bad;
 }

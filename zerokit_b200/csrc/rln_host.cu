@@ -389,6 +389,30 @@ class Rln {
         for (int i = 0; i < 5; i++) *bytes += d_tab_[i].bytes;
     }
     bool glv() const { return plan_.glv != 0; }
+    // cached_leaves_indices (utils/src/merkle_tree/full_merkle_tree.rs:40-45,186-194): 1 = set, 0 = deleted / never set
+    std::vector<uint8_t> leaf_set_;
+    void mark_leaves(size_t start, size_t count, uint8_t v) {
+        if (start + count > leaf_set_.size()) leaf_set_.resize(start + count, 0);
+        std::fill(leaf_set_.begin() + start, leaf_set_.begin() + start + count, v);
+    }
+    std::vector<size_t> empty_leaves_indices() const {
+        std::vector<size_t> out;
+        for (size_t i = 0; i < next_index_; i++)
+            if (i >= leaf_set_.size() || !leaf_set_[i]) out.push_back(i);
+        return out;
+    }
+    // get_subtree_root (full_merkle_tree.rs:157-184): the ancestor at `level` (0 = root, depth = the leaf itself) of leaf `index`
+    void subtree_root(size_t level, size_t index, uint8_t out[32]) {
+        if (level > tree_depth_) throw RlnError("Merkle tree error: Invalid index");
+        if (index >= capacity()) throw RlnError("Merkle tree error: Invalid leaf");
+        const size_t node = (capacity() + index) >> (tree_depth_ - level);
+        DevMem tmp;
+        tmp.alloc(32);
+        launch_fr_to_bytes(d_nodes_.as<Fr>() + node, tmp.as<uint8_t>(), 1, stream_);
+        g_launch_count++;
+        ZK_CUDA_CHECK(cudaMemcpyAsync(out, tmp.p, 32, cudaMemcpyDeviceToHost, stream_));
+        ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    }
     std::vector<uint8_t> metadata;   // set_metadata / get_metadata (rln/src/public.rs:499-515): opaque bytes kept beside the tree
     void sync() { ZK_CUDA_CHECK(cudaStreamSynchronize(stream_)); }   // flush: nothing is buffered outside HBM
     bool overlap_qap_ = false;
@@ -840,11 +864,13 @@ void Rln::set_tree(size_t depth) {
     g_launch_count += 2;
     ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
     next_index_ = 0;
+    leaf_set_.clear();
 }
 void Rln::set_range_device(size_t start, const uint8_t* d_leaves, size_t count, cudaStream_t s) {
     if (count == 0) return;
     if (start + count > capacity() || start + count < start) throw RlnError("Merkle tree error: set_range got too many leaves");
     g_launch_count += launch_merkle_set_range(d_nodes_.as<Fr>(), (u32)tree_depth_, start, d_leaves, count, s);
+    mark_leaves(start, count, 1);
     if (start + count > next_index_) next_index_ = start + count;
 }
 void Rln::set_range_host(size_t start, const uint8_t* leaves, size_t count) {
@@ -864,6 +890,7 @@ void Rln::delete_leaf(size_t index) {
     uint8_t zero[32] = {0};
     size_t keep = next_index_;
     set_range_host(index, zero, 1);
+    mark_leaves(index, 1, 0);
     next_index_ = keep;  // delete never moves next_index (pm_tree_adapter.rs:365-374)
 }
 void Rln::set_next(const uint8_t* leaf) {
@@ -920,6 +947,7 @@ void Rln::override_range(size_t start, const uint8_t* leaves, size_t n_leaves, s
         DevMem tmp;
         tmp.upload(zero, 32);
         g_launch_count += launch_merkle_set_range(d_nodes_.as<Fr>(), (u32)tree_depth_, i, tmp.as<uint8_t>(), 1, stream_);
+        mark_leaves(i, 1, 0);
         ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
     }
     next_index_ = keep;
@@ -1974,6 +2002,20 @@ int rlnb200_get_merkle_proofs(FFI_RLN_t* const* rln, const uint64_t* indices, si
 int rlnb200_debug_witness_and_h(FFI_RLN_t* const* rln, const uint8_t* witness_le, size_t len, uint8_t* w_out, uint8_t* h_out, RlnString* err) {
     INT_OP(std::lock_guard<std::mutex> lk((*rln)->r->mu); Witness w; witness_from_bytes(witness_le, len, w); (*rln)->r->debug_w_h(w, w_out, h_out);)
 }
+int rlnb200_get_subtree_root(FFI_RLN_t* const* rln, size_t level, size_t index, uint8_t* out32, RlnString* err) {
+    INT_OP(std::lock_guard<std::mutex> lk((*rln)->r->mu); (*rln)->r->subtree_root(level, index, out32))
+}
+int rlnb200_get_empty_leaves_indices(FFI_RLN_t* const* rln, Vec_size_t* out, RlnString* err) {
+    INT_OP(
+        std::lock_guard<std::mutex> lk((*rln)->r->mu);
+        std::vector<size_t> v = (*rln)->r->empty_leaves_indices();
+        out->len = v.size();
+        out->cap = v.size() ? v.size() : 1;
+        out->ptr = (size_t*)malloc(sizeof(size_t) * out->cap);
+        if (!v.empty()) memcpy(out->ptr, v.data(), sizeof(size_t) * v.size());
+    )
+}
+void rlnb200_vec_usize_free(Vec_size_t v) { free(v.ptr); }
 int rlnb200_glv_enabled(FFI_RLN_t* const* rln) { return (*rln)->r->glv() ? 1 : 0; }
 int rlnb200_glv_split(const uint8_t* scalars_le, size_t n, uint8_t* out36, RlnString* err) {
     INT_OP(

@@ -318,6 +318,9 @@ def lib():
         "rlnb200_domain_size": (c_size_t, [pp]),
         "rlnb200_mul_throughput": (c_double, [c_int]),
         "rlnb200_op_throughput": (c_double, [c_int, c_int]),
+        "rlnb200_get_subtree_root": (c_int, [pp, c_size_t, c_size_t, c_void_p, POINTER(RlnString)]),
+        "rlnb200_get_empty_leaves_indices": (c_int, [pp, POINTER(Vec_size), POINTER(RlnString)]),
+        "rlnb200_vec_usize_free": (None, [Vec_size]),
         "rlnb200_glv_enabled": (c_int, [pp]),
         "rlnb200_glv_split": (c_int, [c_void_p, c_size_t, c_void_p, POINTER(RlnString)]),
         "rlnb200_pipe_probe": (c_int, [c_int, c_int, POINTER(c_double)]),

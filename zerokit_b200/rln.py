@@ -555,6 +555,22 @@ class RLN:
         vs = Vec_size(cast(arr, POINTER(ctypes.c_size_t)), len(indices), len(indices))
         _check_bool(ffi.lib().ffi_atomic_operation(byref(self._h), index, byref(_vec_cfr(leaves)), byref(vs)))
 
+    def get_subtree_root(self, level: int, index: int) -> int:
+        """rln/src/public.rs:877-883: ancestor at `level` (0 = root) of leaf `index`"""
+        out = ctypes.create_string_buffer(32)
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_get_subtree_root(byref(self._h), level, index, out, byref(err)), err)
+        return int.from_bytes(out.raw, "little")
+
+    def get_empty_leaves_indices(self):
+        """rln/src/public.rs:885-887"""
+        v = Vec_size()
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_get_empty_leaves_indices(byref(self._h), byref(v), byref(err)), err)
+        out = [v.ptr[i] for i in range(v.len)]
+        ffi.lib().rlnb200_vec_usize_free(v)
+        return out
+
     def set_metadata(self, data: bytes):
         """rln/src/public.rs:499-502"""
         _check_bool(ffi.lib().ffi_set_metadata(byref(self._h), byref(_vec_u8(data))))
