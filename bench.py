@@ -36,6 +36,16 @@ METRIC = "rln_proofs_per_sec_batch4096_depth20"
 UNIT = "proofs/s"
 
 
+# The contract is ONE JSON line on stdout.  Libraries loaded later (NCCL prints its version banner to stdout on some boxes)
+# must not be able to add lines: fd 1 is pointed at stderr for the whole run and the result line goes to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -174,7 +184,7 @@ def run_reference(args, rank, world):
                          "sample": f"{n} proofs per step, one worker thread per proof, C++ restatement of the ark-groth16/ark-circom path"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
@@ -258,7 +268,7 @@ def run_gpu(args, rank, local_rank, world):
 
     if args.profile:
         if rank == 0:
-            print(json.dumps({"profile_run": True, "value": value, "stage_ms": stage}), flush=True)
+            emit({"profile_run": True, "value": value, "stage_ms": stage})
         if dist_on:
             dist.destroy_process_group()
         return
@@ -419,7 +429,7 @@ def run_gpu(args, rank, local_rank, world):
             line["msm_g1_microbench"] = msm_microbench(z, dev, hbm_peak, args.msm_log2)
         except Exception as e:  # the headline line must still be printed
             line["msm_g1_microbench"] = {"error": str(e)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist_on:
         dist.destroy_process_group()
 
