@@ -318,6 +318,9 @@ def run_gpu(args, rank, local_rank, world):
         assert host_out[290 * j + 1:290 * j + 129] == want[:128], f"host-path proof {j} differs from the oracle"
     ok = rln.verify_batch(host_out, n)
     assert ok == [1] * n, "a proof of the timed batch does not verify"
+    t_v = time.perf_counter()
+    rln.verify_batch(host_out, n)
+    verify_batch_ms = 1e3 * (time.perf_counter() - t_v)
     log(f"[rank 0] checked: first {n_chk} proofs bit-equal to the oracle, all {n} verify")
 
     # ---- roofline of the dominant kernel: k_msm_accum<Fq> (fixed-base G1 accumulate)
@@ -384,6 +387,9 @@ def run_gpu(args, rank, local_rank, world):
                 "steps": e2e_steps, "api": "rlnb200_prove_batch (host witness records → host rln_proof bytes)"},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "stage_ms": stage,
     }
+    # ---- batch verification of the timed batch's proofs (rlnb200_verify_batch: host records in, flags out)
+    line["verify_batch"] = {"proofs": n, "ms": verify_batch_ms, "proofs_per_s": n / (verify_batch_ms * 1e-3),
+                            "api": "rlnb200_verify_batch (decompression + subgroup checks + 4 Miller loops + final exponentiation per proof)"}
     # ---- single proof through the reference's own entry point (BASELINE.json configs[0]: ffi_generate_rln_proof)
     try:
         wit = z.RLNWitnessInput.from_bytes_le(recs[:rec_len])
@@ -426,7 +432,9 @@ def run_gpu(args, rank, local_rank, world):
             line["merkle_microbench"] = {"error": str(e)}
     if world == 1 and not args.no_micro:
         try:
-            line["msm_g1_microbench"] = msm_microbench(z, dev, hbm_peak, args.msm_log2)
+            sweep = msm_microbench(z, dev, hbm_peak, sorted(set([16, 18, 20, 22, 24, args.msm_log2])))
+            line["msm_g1_microbench"] = next(r for r in sweep if r["log2_n"] == args.msm_log2)
+            line["msm_g1_sweep"] = sweep   # BASELINE.json configs[1]: 2^16 … 2^24
         except Exception as e:  # the headline line must still be printed
             line["msm_g1_microbench"] = {"error": str(e)}
     emit(line)
@@ -465,37 +473,42 @@ def merkle_microbench(rln, dev, hbm_peak):
             "bytes_per_build": 64 << 20, "paths_4096_ms_host_roundtrip": 1e3 * t_paths}
 
 
-def msm_microbench(z, dev, hbm_peak, log2n):
-    """BASELINE.json configs[1]: variable-base G1 MSM, 2^log2n random scalars, bases k_i·G generated on the GPU."""
+def msm_microbench(z, dev, hbm_peak, sizes):
+    """BASELINE.json configs[1]: variable-base G1 MSM, 2^k random scalars for every k in `sizes`; the bases k_i·G are generated
+    on the GPU once for the largest size and prefixes of them serve the smaller ones."""
     import torch
     import numpy as np
-    n = 1 << log2n
-    m = z.G1Msm(n)
+    nmax = 1 << max(sizes)
+    m = z.G1Msm(nmax)
     rng = np.random.default_rng(1)
-    ks = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    ks = rng.integers(0, 256, size=(nmax, 32), dtype=np.uint8)
     ks[:, 31] &= 0x1f
-    sc = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    sc = rng.integers(0, 256, size=(nmax, 32), dtype=np.uint8)
     sc[:, 31] &= 0x1f
     d_k = torch.from_numpy(ks).to(dev)
     d_s = torch.from_numpy(sc).to(dev)
-    d_bases = torch.empty(n * 64, dtype=torch.uint8, device=dev)
+    d_bases = torch.empty(nmax * 64, dtype=torch.uint8, device=dev)
     d_out = torch.empty(64, dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream(dev)
-    m.gen_bases(d_k.data_ptr(), n, d_bases.data_ptr(), st.cuda_stream)
-    for _ in range(2):
-        m.msm_device(d_bases.data_ptr(), d_s.data_ptr(), n, d_out.data_ptr(), st.cuda_stream)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
-    torch.cuda.synchronize(dev)
-    e0.record(st)
-    for _ in range(reps):
-        m.msm_device(d_bases.data_ptr(), d_s.data_ptr(), n, d_out.data_ptr(), st.cuda_stream)
-    e1.record(st)
-    torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1) / reps
-    gbs = 96 * n / (ms * 1e-3) / 1e9
-    return {"log2_n": log2n, "ms": ms, "mterms_per_s": n / ms / 1e3, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak,
-            "bytes_per_term": 96}
+    m.gen_bases(d_k.data_ptr(), nmax, d_bases.data_ptr(), st.cuda_stream)
+    out = []
+    for lg in sizes:
+        n = 1 << lg
+        for _ in range(2):
+            m.msm_device(d_bases.data_ptr(), d_s.data_ptr(), n, d_out.data_ptr(), st.cuda_stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5 if lg <= 22 else 3
+        torch.cuda.synchronize(dev)
+        e0.record(st)
+        for _ in range(reps):
+            m.msm_device(d_bases.data_ptr(), d_s.data_ptr(), n, d_out.data_ptr(), st.cuda_stream)
+        e1.record(st)
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / reps
+        gbs = 96 * n / (ms * 1e-3) / 1e9
+        out.append({"log2_n": lg, "ms": ms, "mterms_per_s": n / ms / 1e3, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak,
+                    "bytes_per_term": 96})
+    return out
 
 
 def main():

@@ -70,6 +70,12 @@ void emu_g2_add(const uint8_t* p, const uint8_t* q, uint8_t* out) {
     if (!b.is_inf()) a.add_affine(b);
     st_g2(out, a.to_affine());
 }
+// G2 membership test used by the verifier's point decompression (point must be on the twist)
+int emu_g2_in_subgroup(const uint8_t* p) {
+    static PairingTables pt; static bool init = false;
+    if (!init) { pairing_tables_init(pt); init = true; }
+    return g2_in_subgroup(&pt, ld_g2(p)) ? 1 : 0;
+}
 // pairing check: Π e(P_i, Q_i) == 1 ; g1: n×64 B, g2: n×128 B
 int emu_pairing_check(const uint8_t* g1, const uint8_t* g2, int n) {
     static PairingTables pt; static bool init = false;

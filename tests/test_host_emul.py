@@ -102,6 +102,55 @@ def test_curve_ops(emu):
         assert _g2r(o2.raw) == F.pt_double(F.OPS2, P2)
 
 
+def test_g2_subgroup_check(emu):
+    """ψ(P) = [6x²]P accepts exactly the r-torsion: multiples of the generator pass, other points of the twist fail"""
+    rnd = random.Random(9)
+    for _ in range(3):
+        P2 = F.pt_mul(F.OPS2, F.G2_GEN, rnd.randrange(1, R))
+        assert emu.emu_g2_in_subgroup(_g2b(P2)) == 1
+        assert F.pt_add(F.OPS2, F.pt_mul(F.OPS2, P2, R - 1), P2) is None
+    # points of E'(Fq2) found by solving y² = x³ + b' for small x: the cofactor is ≈ 2^254, they are not in G2
+    bt = F.OPS2.b
+    found = 0
+    k = 1
+    while found < 3:
+        x = (k, 1)
+        k += 1
+        rhs = F.f2_add(F.f2_mul(F.f2_sqr(x), x), bt)
+        y = _f2_sqrt(rhs)
+        if y is None:
+            continue
+        Pt = (x, y)
+        assert F.on_curve(F.OPS2, Pt)
+        assert F.pt_add(F.OPS2, F.pt_mul(F.OPS2, Pt, R - 1), Pt) is not None      # [r]P ≠ ∞: outside the subgroup (pt_mul reduces k mod r)
+        assert emu.emu_g2_in_subgroup(_g2b(Pt)) == 0
+        found += 1
+
+
+def _f2_sqrt(a):
+    """square root in Fq2 = Fq[u]/(u²+1), q ≡ 3 mod 4 (complex method); None if a is not a square"""
+    a0, a1 = a
+    if a1 == 0:
+        r = pow(a0, (Q + 1) // 4, Q)
+        if r * r % Q == a0:
+            return (r, 0)
+        r = pow(-a0 % Q, (Q + 1) // 4, Q)
+        return (0, r) if r * r % Q == -a0 % Q else None
+    n = (a0 * a0 + a1 * a1) % Q
+    alpha = pow(n, (Q + 1) // 4, Q)
+    if alpha * alpha % Q != n:
+        return None
+    for al in (alpha, -alpha % Q):
+        delta = (a0 + al) * pow(2, -1, Q) % Q
+        x0 = pow(delta, (Q + 1) // 4, Q)
+        if x0 * x0 % Q != delta:
+            continue
+        x1 = a1 * pow(2 * x0, -1, Q) % Q
+        if F.f2_sqr((x0, x1)) == (a0 % Q, a1 % Q):
+            return (x0, x1)
+    return None
+
+
 def test_pairing(emu):
     a, b = 1234567, 7654321
     P1, Q1 = F.pt_mul(F.OPS1, F.G1_GEN, a), F.pt_mul(F.OPS2, F.G2_GEN, b)

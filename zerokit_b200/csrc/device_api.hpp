@@ -153,6 +153,8 @@ struct VerifyKeyDev {
     G2Affine beta_g2, gamma_g2, delta_g2;
     const G1Affine* gamma_abc;  // device pointer, n_public + 1 entries
     u32 n_public;
+    const G1Affine* gamma_tab;  // window tables of gamma_abc[1..n_public]: [n_public][gK][2^(gc−1)] (vk_x without doublings)
+    int gc, gK;
     // prepare_verifying_key (ark-groth16): everything that depends only on the key is computed once
     const Fq12* ml_alpha_beta;            // device pointer: Miller value of (α₁, β₂)
     const Fq2 *gamma_lam, *gamma_c;       // device pointers: line coefficients of γ₂ (MILLER_STEPS each)

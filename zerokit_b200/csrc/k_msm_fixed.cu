@@ -21,6 +21,7 @@
 
 #define ZK_FQ2_OUTLINE 1  // this TU only: Fq2 products call one shared out-of-line Fq multiplier (see fp.cuh mul_ni)
 #include "device_api.hpp"
+#include "fixed_base.cuh"
 
 namespace zk {
 
@@ -210,31 +211,6 @@ struct AccumArgs {
     int c, K;
     int glv;                     // G1 only: tasks come in (k₁, k₂) pairs, MsmTask::half selects which
 };
-
-template <class F>
-__device__ __forceinline__ Affine<F> ld_point(const Affine<F>* p);
-template <>
-__device__ __forceinline__ Affine<Fq> ld_point<Fq>(const Affine<Fq>* p) {
-    return {ldg_fp(&p->x), ldg_fp(&p->y)};
-}
-template <>
-__device__ __forceinline__ Affine<Fq2> ld_point<Fq2>(const Affine<Fq2>* p) {
-    return {{ldg_fp(&p->x.a), ldg_fp(&p->x.b)}, {ldg_fp(&p->y.a), ldg_fp(&p->y.b)}};
-}
-
-// signed window digit k of the canonical scalar s (with incoming carry); returns digit in [−2^{c−1}, 2^{c−1}]
-__device__ __forceinline__ int window_digit(const u32* s, int k, int c, u32& carry) {
-    const int bit = k * c;
-    const int w = bit >> 5, sh = bit & 31;
-    u32 v = 0;
-    if (w < 8) {
-        v = s[w] >> sh;
-        if (sh + c > 32 && w + 1 < 8) v |= s[w + 1] << (32 - sh);
-    }
-    int d = (int)(v & ((1u << c) - 1)) + (int)carry;
-    if (d > (1 << (c - 1))) { d -= (1 << c); carry = 1; } else carry = 0;
-    return d;
-}
 
 template <class F, bool PREFETCH, int MIN_BLOCKS, bool GLV = false>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_msm_accum(AccumArgs<F> a) {
@@ -456,22 +432,6 @@ __global__ void __launch_bounds__(64) k_partial_g2(ProverKeyDev pk, const G2XYZZ
     G2XYZZ b = sum[j];
     b.add_affine(pk.beta_g2);
     compress_g2(b.to_affine(), out_comp + 160 * (size_t)j + 64, out_affine + 320 * (size_t)j + 128);
-}
-
-// k·P for the fixed point whose window table is `tb` ([K][2^(c-1)] multiples): K mixed additions, no doublings
-template <class F>
-__device__ XYZZ<F> fixed_base_mul(const Affine<F>* __restrict__ tb, int c, int K, const u32* k) {
-    XYZZ<F> acc = XYZZ<F>::infinity();
-    const u32 half = 1u << (c - 1);
-    u32 carry = 0;
-    for (int w = 0; w < K; w++) {
-        int d = window_digit(k, w, c, carry);
-        if (d == 0) continue;
-        Affine<F> pt = ld_point<F>(tb + (size_t)w * half + ((d < 0 ? -d : d) - 1));
-        if (d < 0) pt.y = pt.y.neg();
-        acc.add_affine(pt);
-    }
-    return acc;
 }
 
 __global__ void __launch_bounds__(64) k_assemble_g1(ProverKeyDev pk, const G1Affine* __restrict__ dtab, int c, int K,

@@ -18,6 +18,7 @@ inline void pairing_tables_init(PairingTables& pt) {
     }
     pt.gamma2 = t.sqr();
     pt.gamma3 = pt.gamma2 * t;
+    pt.twist_b = Fq2{Fq::from_u32(3), Fq::zero()} * Fq2{Fq::from_u32(9), Fq::from_u32(1)}.inv();
     pt.frob1[0] = Fq2::one();
     for (int k = 1; k < 6; k++) pt.frob1[k] = pt.frob1[k - 1] * t;
     Fq2 n = t * t.conj();

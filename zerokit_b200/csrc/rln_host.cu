@@ -465,7 +465,7 @@ class Rln {
     DevMem d_prog_, d_consts_, d_signals_, d_a_ptr_, d_a_col_, d_a_val_, d_b_ptr_, d_b_col_, d_b_val_, d_tw_inv_, d_tw_fwd_, d_coset_;
     CircuitDev circ_{};
     // fixed-base tables
-    DevMem d_tab_[5], d_rows_[5], d_gamma_abc_, d_delta1_tab_, d_delta2_tab_, d_vk_pre_;
+    DevMem d_tab_[5], d_rows_[5], d_gamma_abc_, d_gamma_tab_, d_delta1_tab_, d_delta2_tab_, d_vk_pre_;
     FixedMsmPlan plan_{};
     ProverKeyDev pk_{};
     VerifyKeyDev vk_{};
@@ -836,6 +836,14 @@ void Rln::build_tables() {
         upload_points_g1(zk_.gamma_abc, all, d_gamma_abc_);
         vk_.gamma_abc = d_gamma_abc_.as<G1Affine>();
         vk_.n_public = (u32)all.size() - 1;
+        // window tables of gamma_abc[1..]: vk_x = gamma_abc[0] + Σ xᵢ·gamma_abc[i] costs 32 additions per public input
+        vk_.gc = 8;
+        vk_.gK = (255 + vk_.gc - 1) / vk_.gc;
+        d_gamma_tab_.alloc(sizeof(G1Affine) * vk_.n_public * vk_.gK * ((size_t)1 << (vk_.gc - 1)));
+        launch_build_table_g1(d_gamma_abc_.as<G1Affine>() + 1, vk_.n_public, vk_.gc, vk_.gK, d_gamma_tab_.as<G1Affine>(), 0);
+        g_launch_count += 2;
+        ZK_CUDA_CHECK(cudaDeviceSynchronize());
+        vk_.gamma_tab = d_gamma_tab_.as<G1Affine>();
     }
     {   // prepare_verifying_key: key-only parts of the pairing check (one-off, host portable arithmetic)
         PairingTables pr;

@@ -60,6 +60,7 @@ struct Fq12 {
 struct PairingTables {
     Fq2 gamma2;    // ξ^((q−1)/3)
     Fq2 gamma3;    // ξ^((q−1)/2)
+    Fq2 twist_b;   // 3/ξ: the constant of the twist E'(Fq2): y² = x³ + 3/(9+u)
     Fq2 frob1[6];  // ξ^(k(q−1)/6), k = 0..5: coefficients of the q-power Frobenius on Fq12
     Fq frob2[6];   // ξ^(k(q²−1)/6), k = 0..5 (lie in Fq)
     u32 hard[24];  // (q⁴ − q² + 1)/r, little-endian words (761 bits) — reference value for the generic path (tests)
@@ -106,6 +107,16 @@ HDN Fq12 miller_loop(const PairingTables* pt, const G2Affine& Qp, const G1Affine
         R.x = x3;
     }
     return f;
+}
+
+// G2 membership of a point already known to be on the twist: ψ(P) = [6x²]P, the criterion ark-bn254 0.5.0 applies when it
+// deserialises a G2 point (g2.rs, is_in_correct_subgroup_assuming_on_curve; on the r-torsion ψ acts as q ≡ 6x² mod r) —
+// a 127-bit multiple instead of the 254-bit [r]P
+HDN bool g2_in_subgroup(const PairingTables* pt, const G2Affine& p) {
+    const u32 six_x2[8] = {0xe87cfd46u, 0xf83e9682u, 0xeeb859fbu, 0x6f4d8248u, 0, 0, 0, 0};
+    const G2Affine lhs = G2XYZZ::from_affine(p).mul(six_x2).to_affine();
+    const G2Affine psi = {p.x.conj() * pt->gamma2, p.y.conj() * pt->gamma3};
+    return !lhs.is_inf() && lhs.x == psi.x && lhs.y == psi.y;
 }
 
 // Line coefficients of the Miller loop for a FIXED G2 point (γ₂, δ₂ of the verifying key): per step the slope λ and
