@@ -61,6 +61,10 @@ struct CircuitDev {
     const VmInstr* prog;
     const Fr* consts;
     const u32* signals;  // wire → node
+    // list schedule of the graph: bundle b holds up to 4 mutually independent nodes sched[4b .. 4b+3] (0xffffffff = empty slot)
+    // whose operands all lie in earlier bundles; one warp per slot evaluates them side by side (k_witness)
+    const u32* sched;
+    u32 n_bundles;
     // QAP
     u32 n_constraints, n_instance, domain, log_domain;
     const u32 *a_ptr, *a_col, *b_ptr, *b_col;

@@ -22,6 +22,9 @@ struct VarMsmWorkspace {
     u32 *keys_in = nullptr, *keys_out = nullptr, *vals_in = nullptr, *vals_out = nullptr;
     u32 *bucket_start = nullptr, *bucket_end = nullptr;
     u32 *size_key = nullptr, *size_key_out = nullptr, *order_in = nullptr, *order = nullptr;  // buckets ordered by size, largest first
+    u32 *slice_cnt = nullptr, *slice_off = nullptr;   // per ordered bucket: number of ≤ SLICE-point slices and their first slice id
+    G1XYZZ* partial = nullptr;                        // one partial sum per slice
+    size_t max_slices = 0;
     G1XYZZ* buckets = nullptr;
     G1XYZZ* seg = nullptr;
     G1XYZZ* win = nullptr;
@@ -38,6 +41,7 @@ static void msm_params(size_t n, int& c, int& K) {
     if (c > 16) c = 16;
     K = (255 + c - 1) / c;  // K·c ≥ 255 keeps the top signed digit + carry below 2^(c−1)
 }
+static const u32 SLICE = 256;  // a thread never sums more than this many points: heavier buckets are split into slices
 static const int SEGS = 2048;  // segments per window in the bucket reduction (16 buckets each at c = 16: 32 K short threads)
 
 VarMsmWorkspace* var_msm_workspace_create(size_t max_n) {
@@ -66,6 +70,10 @@ VarMsmWorkspace* var_msm_workspace_create(size_t max_n) {
     ZK_CUDA_CHECK(cudaMalloc(&w->size_key_out, 4 * max_b));
     ZK_CUDA_CHECK(cudaMalloc(&w->order_in, 4 * max_b));
     ZK_CUDA_CHECK(cudaMalloc(&w->order, 4 * max_b));
+    ZK_CUDA_CHECK(cudaMalloc(&w->slice_cnt, 4 * max_b));
+    ZK_CUDA_CHECK(cudaMalloc(&w->slice_off, 4 * max_b));
+    w->max_slices = max_items / SLICE + max_b + 1;
+    ZK_CUDA_CHECK(cudaMalloc(&w->partial, sizeof(G1XYZZ) * w->max_slices));
     ZK_CUDA_CHECK(cudaMalloc(&w->seg, sizeof(G1XYZZ) * 32 * SEGS));
     ZK_CUDA_CHECK(cudaMalloc(&w->win, sizeof(G1XYZZ) * 32));
     cub::DeviceRadixSort::SortPairs(nullptr, w->cub_tmp_bytes, w->keys_in, w->keys_out, w->vals_in, w->vals_out,
@@ -77,7 +85,8 @@ void var_msm_workspace_destroy(VarMsmWorkspace* w) {
     if (!w) return;
     cudaFree(w->keys_in); cudaFree(w->keys_out); cudaFree(w->vals_in); cudaFree(w->vals_out);
     cudaFree(w->bucket_start); cudaFree(w->bucket_end); cudaFree(w->buckets);
-    cudaFree(w->size_key); cudaFree(w->size_key_out); cudaFree(w->order_in); cudaFree(w->order); cudaFree(w->seg); cudaFree(w->win); cudaFree(w->cub_tmp);
+    cudaFree(w->size_key); cudaFree(w->size_key_out); cudaFree(w->order_in); cudaFree(w->order);
+    cudaFree(w->slice_cnt); cudaFree(w->slice_off); cudaFree(w->partial); cudaFree(w->seg); cudaFree(w->win); cudaFree(w->cub_tmp);
     delete w;
 }
 
@@ -130,32 +139,67 @@ __global__ void k_bucket_sizes(const u32* __restrict__ start, const u32* __restr
     idx[b] = b;
 }
 
-// the hot kernel: bucket b = Σ ± bases[vals[t]] for t in [start[b], end[b]).  Thread i takes the i-th fullest bucket: the 32
-// buckets of a warp then hold (almost) the same number of points — no lanes idling behind the longest bucket — and the big
-// buckets of the short top window start first instead of forming the tail of the launch.
+// number of slices of the i-th fullest bucket (size_key_out holds ~size in ascending order = sizes in descending order)
+__global__ void k_slice_counts(const u32* __restrict__ size_key_sorted, u32 n_buckets, u32* __restrict__ cnt) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_buckets) cnt[i] = (~size_key_sorted[i] + SLICE - 1) / SLICE;
+}
+
+// The hot kernel.  Work item = one slice of ≤ SLICE points of one bucket; slices are numbered bucket after bucket in size order
+// (fullest first), so the 32 slices of a warp hold (almost) the same number of points — no lanes idling behind a long one —
+// and no thread ever walks a giant bucket alone (skewed scalars, or the few huge buckets of a short top window).
 __global__ void __launch_bounds__(128) k_bucket_sum(const G1Affine* __restrict__ bases, const u32* __restrict__ vals,
                                                     const u32* __restrict__ start, const u32* __restrict__ end, const u32* __restrict__ order,
-                                                    size_t n_buckets, G1XYZZ* __restrict__ buckets) {
-    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i >= n_buckets) return;
-    const u32 b = order[i];
-    const u32 lo = start[b], hi = end[b];
-    G1XYZZ acc = G1XYZZ::infinity();
-    if (lo < hi) {
-        u32 v = vals[lo];
-        G1Affine nxt = {ldg_fp(&bases[v & 0x7fffffffu].x), ldg_fp(&bases[v & 0x7fffffffu].y)};
-        if (v >> 31) nxt.y = nxt.y.neg();
-        for (u32 t = lo; t < hi; t++) {
-            G1Affine cur = nxt;
-            if (t + 1 < hi) {  // prefetch the next point while the current addition runs
-                v = vals[t + 1];
-                nxt = {ldg_fp(&bases[v & 0x7fffffffu].x), ldg_fp(&bases[v & 0x7fffffffu].y)};
-                if (v >> 31) nxt.y = nxt.y.neg();
-            }
-            if (!cur.is_inf()) acc.add_affine(cur);
-        }
+                                                    const u32* __restrict__ cnt, const u32* __restrict__ off, u32 n_buckets,
+                                                    G1XYZZ* __restrict__ partial) {
+    const u32 sl = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 total = off[n_buckets - 1] + cnt[n_buckets - 1];
+    if (sl >= total) return;
+    // ordered position i with off[i] ≤ sl < off[i] + cnt[i]: the last i with off[i] ≤ sl (empty buckets sort last and own no slice)
+    u32 lo_i = 0, hi_i = n_buckets - 1;
+    while (lo_i < hi_i) {
+        const u32 mid = (lo_i + hi_i + 1) >> 1;
+        if (off[mid] <= sl) lo_i = mid; else hi_i = mid - 1;
     }
-    buckets[b] = acc;
+    const u32 b = order[lo_i];
+    const u32 lo = start[b] + (sl - off[lo_i]) * SLICE;
+    const u32 hi = min(end[b], lo + SLICE);
+    G1XYZZ acc = G1XYZZ::infinity();
+    u32 v = vals[lo];
+    G1Affine nxt = {ldg_fp(&bases[v & 0x7fffffffu].x), ldg_fp(&bases[v & 0x7fffffffu].y)};
+    if (v >> 31) nxt.y = nxt.y.neg();
+    for (u32 t = lo; t < hi; t++) {
+        G1Affine cur = nxt;
+        if (t + 1 < hi) {  // prefetch the next point while the current addition runs
+            v = vals[t + 1];
+            nxt = {ldg_fp(&bases[v & 0x7fffffffu].x), ldg_fp(&bases[v & 0x7fffffffu].y)};
+            if (v >> 31) nxt.y = nxt.y.neg();
+        }
+        if (!cur.is_inf()) acc.add_affine(cur);
+    }
+    partial[sl] = acc;
+}
+
+__device__ __forceinline__ G1XYZZ shfl_xor_point(const G1XYZZ& p, int mask);
+// bucket = Σ of its slices' partial sums.  One warp per ordered position: a lane-strided loop and a shuffle tree, so that even a
+// bucket of millions of points (thousands of slices) is combined in ≈ slices/32 + 5 additions.
+__global__ void __launch_bounds__(128) k_bucket_combine(const G1XYZZ* __restrict__ partial, const u32* __restrict__ order,
+                                                        const u32* __restrict__ cnt, const u32* __restrict__ off, u32 n_buckets,
+                                                        G1XYZZ* __restrict__ buckets) {
+    const u32 i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n_buckets) return;
+    const u32 c = cnt[i], o = off[i];
+    G1XYZZ acc = G1XYZZ::infinity();
+    if (c <= 1) {   // the common case: nothing to combine
+        if (lane == 0) buckets[order[i]] = c ? partial[o] : acc;
+        return;
+    }
+    for (u32 t = lane; t < c; t += 32) acc.add(partial[o + t]);
+    for (int m = 16; m >= 1; m >>= 1) {
+        G1XYZZ other = shfl_xor_point(acc, m);
+        acc.add(other);
+    }
+    if (lane == 0) buckets[order[i]] = acc;
 }
 
 // segment s of window k covers buckets [s·L, (s+1)·L): W = Σ (b+1)·B_b over the segment
@@ -236,8 +280,14 @@ void launch_var_msm_g1(VarMsmWorkspace* w, const G1Affine* d_bases, const uint8_
     k_bucket_sizes<<<(unsigned)((n_buckets + 255) / 256), 256, 0, s>>>(w->bucket_start, w->bucket_end, (u32)n_buckets, w->size_key, w->order_in);
     tmp = w->cub_tmp_bytes;
     cub::DeviceRadixSort::SortPairs(w->cub_tmp, tmp, w->size_key, w->size_key_out, w->order_in, w->order, (int64_t)n_buckets, 0, 32, s);
-    k_bucket_sum<<<(unsigned)((n_buckets + 127) / 128), 128, 0, s>>>(d_bases, w->vals_out, w->bucket_start, w->bucket_end, w->order, n_buckets,
-                                                                     w->buckets);
+    k_slice_counts<<<(unsigned)((n_buckets + 255) / 256), 256, 0, s>>>(w->size_key_out, (u32)n_buckets, w->slice_cnt);
+    tmp = w->cub_tmp_bytes;
+    cub::DeviceScan::ExclusiveSum(w->cub_tmp, tmp, w->slice_cnt, w->slice_off, (int)n_buckets, s);
+    const size_t max_slices = items / SLICE + n_buckets;   // upper bound known on the host; threads beyond the real total exit
+    k_bucket_sum<<<(unsigned)((max_slices + 127) / 128), 128, 0, s>>>(d_bases, w->vals_out, w->bucket_start, w->bucket_end, w->order, w->slice_cnt,
+                                                                      w->slice_off, (u32)n_buckets, w->partial);
+    k_bucket_combine<<<(unsigned)((n_buckets * 32 + 127) / 128), 128, 0, s>>>(w->partial, w->order, w->slice_cnt, w->slice_off, (u32)n_buckets,
+                                                                              w->buckets);
     const u32 n_seg = half < (u32)SEGS ? half : (u32)SEGS;
     const u32 seg_len = half / n_seg;
     k_segment_reduce<<<dim3((n_seg + 63) / 64, K), 64, 0, s>>>(w->buckets, half, seg_len, w->seg);
