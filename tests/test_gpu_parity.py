@@ -234,6 +234,27 @@ def test_msm_baseline_sizes_vs_oracle(z, oracle, log2n):
     assert m.msm(bases, sc.tobytes(), n) == oracle.msm_g1(bases, sc.tobytes(), n, oracle.threads())
 
 
+def test_msm_skewed_scalars(z, oracle):
+    """scalars that pile into a few buckets (all equal; 0/1 witness-like; one huge outlier): the bucket slices + combine path"""
+    import numpy as np
+    n = 1 << 15
+    rng = np.random.default_rng(11)
+    ks = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    ks[:, 31] &= 0x1f
+    bases = oracle.g1_mul_gen(ks.tobytes(), n, oracle.threads())
+    m = z.G1Msm(n)
+    same = int.from_bytes(rng.integers(0, 256, size=32, dtype=np.uint8).tobytes(), "little") % R
+    cases = {
+        "all equal": [same] * n,
+        "bits": [int(b) for b in rng.integers(0, 2, size=n)],
+        "all one": [1] * n,
+        "r-1 and small": [R - 1 if i % 3 == 0 else i % 7 for i in range(n)],
+    }
+    for name, sc in cases.items():
+        sb = fr_bytes(sc)
+        assert m.msm(bases, sb, n) == oracle.msm_g1(bases, sb, n, oracle.threads()), name
+
+
 def test_msm_large_linear_split(z, oracle):
     """2^20 terms: too slow to re-do on one CPU core, so check Σ over the whole == Σ over the two halves (oracle adds the halves)"""
     import numpy as np

@@ -41,7 +41,7 @@ static void msm_params(size_t n, int& c, int& K) {
     if (c > 16) c = 16;
     K = (255 + c - 1) / c;  // K·c ≥ 255 keeps the top signed digit + carry below 2^(c−1)
 }
-static const u32 SLICE = 256;  // a thread never sums more than this many points: heavier buckets are split into slices
+static const u32 SLICE_MIN = 256, SLICE_MAX = 2048;  // a thread never sums more than `slice` points: heavier buckets are split
 static const int SEGS = 2048;  // segments per window in the bucket reduction (16 buckets each at c = 16: 32 K short threads)
 
 VarMsmWorkspace* var_msm_workspace_create(size_t max_n) {
@@ -72,12 +72,15 @@ VarMsmWorkspace* var_msm_workspace_create(size_t max_n) {
     ZK_CUDA_CHECK(cudaMalloc(&w->order, 4 * max_b));
     ZK_CUDA_CHECK(cudaMalloc(&w->slice_cnt, 4 * max_b));
     ZK_CUDA_CHECK(cudaMalloc(&w->slice_off, 4 * max_b));
-    w->max_slices = max_items / SLICE + max_b + 1;
+    w->max_slices = max_items / SLICE_MIN + max_b + 1;
     ZK_CUDA_CHECK(cudaMalloc(&w->partial, sizeof(G1XYZZ) * w->max_slices));
     ZK_CUDA_CHECK(cudaMalloc(&w->seg, sizeof(G1XYZZ) * 32 * SEGS));
     ZK_CUDA_CHECK(cudaMalloc(&w->win, sizeof(G1XYZZ) * 32));
     cub::DeviceRadixSort::SortPairs(nullptr, w->cub_tmp_bytes, w->keys_in, w->keys_out, w->vals_in, w->vals_out,
                                     (int64_t)(max_items > max_b ? max_items : max_b), 0, 32);
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, w->slice_cnt, w->slice_off, (int)max_b);
+    if (scan_bytes > w->cub_tmp_bytes) w->cub_tmp_bytes = scan_bytes;
     ZK_CUDA_CHECK(cudaMalloc(&w->cub_tmp, w->cub_tmp_bytes));
     return w;
 }
@@ -140,18 +143,20 @@ __global__ void k_bucket_sizes(const u32* __restrict__ start, const u32* __restr
 }
 
 // number of slices of the i-th fullest bucket (size_key_out holds ~size in ascending order = sizes in descending order)
-__global__ void k_slice_counts(const u32* __restrict__ size_key_sorted, u32 n_buckets, u32* __restrict__ cnt) {
+__global__ void k_slice_counts(const u32* __restrict__ size_key_sorted, u32 n_buckets, u32 slice, u32* __restrict__ cnt) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_buckets) cnt[i] = (~size_key_sorted[i] + SLICE - 1) / SLICE;
+    if (i < n_buckets) cnt[i] = (~size_key_sorted[i] + slice - 1) / slice;
 }
 
-// The hot kernel.  Work item = one slice of ≤ SLICE points of one bucket; slices are numbered bucket after bucket in size order
-// (fullest first), so the 32 slices of a warp hold (almost) the same number of points — no lanes idling behind a long one —
-// and no thread ever walks a giant bucket alone (skewed scalars, or the few huge buckets of a short top window).
+// The hot kernel.  Work item = one slice of ≤ `slice` points of one bucket (slice ≈ twice the mean bucket size, so with uniform
+// scalars every bucket is one slice); slices are numbered bucket after bucket in size order (fullest first), so the 32 slices of
+// a warp hold (almost) the same number of points — no lanes idling behind a long one — and no thread ever walks a giant bucket
+// alone (skewed scalars, or the few huge buckets of a short top window).  A single-slice bucket is written straight to its
+// place; slices of split buckets go to `partial` for k_bucket_combine.
 __global__ void __launch_bounds__(128) k_bucket_sum(const G1Affine* __restrict__ bases, const u32* __restrict__ vals,
                                                     const u32* __restrict__ start, const u32* __restrict__ end, const u32* __restrict__ order,
-                                                    const u32* __restrict__ cnt, const u32* __restrict__ off, u32 n_buckets,
-                                                    G1XYZZ* __restrict__ partial) {
+                                                    const u32* __restrict__ cnt, const u32* __restrict__ off, u32 n_buckets, u32 slice,
+                                                    G1XYZZ* __restrict__ partial, G1XYZZ* __restrict__ buckets) {
     const u32 sl = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 total = off[n_buckets - 1] + cnt[n_buckets - 1];
     if (sl >= total) return;
@@ -162,8 +167,8 @@ __global__ void __launch_bounds__(128) k_bucket_sum(const G1Affine* __restrict__
         if (off[mid] <= sl) lo_i = mid; else hi_i = mid - 1;
     }
     const u32 b = order[lo_i];
-    const u32 lo = start[b] + (sl - off[lo_i]) * SLICE;
-    const u32 hi = min(end[b], lo + SLICE);
+    const u32 lo = start[b] + (sl - off[lo_i]) * slice;
+    const u32 hi = min(end[b], lo + slice);
     G1XYZZ acc = G1XYZZ::infinity();
     u32 v = vals[lo];
     G1Affine nxt = {ldg_fp(&bases[v & 0x7fffffffu].x), ldg_fp(&bases[v & 0x7fffffffu].y)};
@@ -177,23 +182,21 @@ __global__ void __launch_bounds__(128) k_bucket_sum(const G1Affine* __restrict__
         }
         if (!cur.is_inf()) acc.add_affine(cur);
     }
-    partial[sl] = acc;
+    if (cnt[lo_i] == 1) buckets[b] = acc;
+    else partial[sl] = acc;
 }
 
 __device__ __forceinline__ G1XYZZ shfl_xor_point(const G1XYZZ& p, int mask);
-// bucket = Σ of its slices' partial sums.  One warp per ordered position: a lane-strided loop and a shuffle tree, so that even a
-// bucket of millions of points (thousands of slices) is combined in ≈ slices/32 + 5 additions.
+// split buckets only: bucket = Σ of its slices' partial sums.  One warp per ordered position (split buckets sort first): a
+// lane-strided loop and a shuffle tree, so even a bucket of millions of points is combined in ≈ slices/32 + 5 additions.
 __global__ void __launch_bounds__(128) k_bucket_combine(const G1XYZZ* __restrict__ partial, const u32* __restrict__ order,
-                                                        const u32* __restrict__ cnt, const u32* __restrict__ off, u32 n_buckets,
+                                                        const u32* __restrict__ cnt, const u32* __restrict__ off, u32 n_positions,
                                                         G1XYZZ* __restrict__ buckets) {
     const u32 i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (i >= n_buckets) return;
+    if (i >= n_positions) return;
     const u32 c = cnt[i], o = off[i];
+    if (c <= 1) return;   // written by k_bucket_sum (or empty: cleared by the memset)
     G1XYZZ acc = G1XYZZ::infinity();
-    if (c <= 1) {   // the common case: nothing to combine
-        if (lane == 0) buckets[order[i]] = c ? partial[o] : acc;
-        return;
-    }
     for (u32 t = lane; t < c; t += 32) acc.add(partial[o + t]);
     for (int m = 16; m >= 1; m >>= 1) {
         G1XYZZ other = shfl_xor_point(acc, m);
@@ -273,21 +276,27 @@ void launch_var_msm_g1(VarMsmWorkspace* w, const G1Affine* d_bases, const uint8_
     int key_bits = 0;
     while (((size_t)1 << key_bits) < n_buckets + 1) key_bits++;  // keys are in [0, n_buckets]: sort only the significant bits
     size_t tmp = w->cub_tmp_bytes;
-    cub::DeviceRadixSort::SortPairs(w->cub_tmp, tmp, w->keys_in, w->keys_out, w->vals_in, w->vals_out, (int64_t)items, 0, key_bits, s);
+    ZK_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, tmp, w->keys_in, w->keys_out, w->vals_in, w->vals_out, (int64_t)items, 0, key_bits, s));
     ZK_CUDA_CHECK(cudaMemsetAsync(w->bucket_start, 0, 4 * n_buckets, s));
     ZK_CUDA_CHECK(cudaMemsetAsync(w->bucket_end, 0, 4 * n_buckets, s));
     k_bucket_bounds<<<(unsigned)((items + 255) / 256), 256, 0, s>>>(w->keys_out, items, (u32)n_buckets, w->bucket_start, w->bucket_end);
     k_bucket_sizes<<<(unsigned)((n_buckets + 255) / 256), 256, 0, s>>>(w->bucket_start, w->bucket_end, (u32)n_buckets, w->size_key, w->order_in);
     tmp = w->cub_tmp_bytes;
-    cub::DeviceRadixSort::SortPairs(w->cub_tmp, tmp, w->size_key, w->size_key_out, w->order_in, w->order, (int64_t)n_buckets, 0, 32, s);
-    k_slice_counts<<<(unsigned)((n_buckets + 255) / 256), 256, 0, s>>>(w->size_key_out, (u32)n_buckets, w->slice_cnt);
+    ZK_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, tmp, w->size_key, w->size_key_out, w->order_in, w->order, (int64_t)n_buckets, 0, 32, s));
+    u32 slice = SLICE_MIN;   // ≈ twice the mean bucket size
+    while (slice < SLICE_MAX && (size_t)slice * n_buckets < 2 * items) slice <<= 1;
+    k_slice_counts<<<(unsigned)((n_buckets + 255) / 256), 256, 0, s>>>(w->size_key_out, (u32)n_buckets, slice, w->slice_cnt);
     tmp = w->cub_tmp_bytes;
-    cub::DeviceScan::ExclusiveSum(w->cub_tmp, tmp, w->slice_cnt, w->slice_off, (int)n_buckets, s);
-    const size_t max_slices = items / SLICE + n_buckets;   // upper bound known on the host; threads beyond the real total exit
+    ZK_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(w->cub_tmp, tmp, w->slice_cnt, w->slice_off, (int)n_buckets, s));
+    const size_t max_slices = items / slice + n_buckets;   // upper bound known on the host; threads beyond the real total exit
+    ZK_CUDA_CHECK(cudaMemsetAsync(w->buckets, 0, sizeof(G1XYZZ) * n_buckets, s));   // all-zero XYZZ = infinity: the empty buckets
     k_bucket_sum<<<(unsigned)((max_slices + 127) / 128), 128, 0, s>>>(d_bases, w->vals_out, w->bucket_start, w->bucket_end, w->order, w->slice_cnt,
-                                                                      w->slice_off, (u32)n_buckets, w->partial);
-    k_bucket_combine<<<(unsigned)((n_buckets * 32 + 127) / 128), 128, 0, s>>>(w->partial, w->order, w->slice_cnt, w->slice_off, (u32)n_buckets,
-                                                                              w->buckets);
+                                                                      w->slice_off, (u32)n_buckets, slice, w->partial, w->buckets);
+    // a split bucket holds more than `slice` points, so at most items / slice ordered positions can be split
+    const size_t n_split_max = items / slice < n_buckets ? items / slice : n_buckets;
+    if (n_split_max)
+        k_bucket_combine<<<(unsigned)((n_split_max * 32 + 127) / 128), 128, 0, s>>>(w->partial, w->order, w->slice_cnt, w->slice_off,
+                                                                                    (u32)n_split_max, w->buckets);
     const u32 n_seg = half < (u32)SEGS ? half : (u32)SEGS;
     const u32 seg_len = half / n_seg;
     k_segment_reduce<<<dim3((n_seg + 63) / 64, K), 64, 0, s>>>(w->buckets, half, seg_len, w->seg);
