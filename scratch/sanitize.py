@@ -22,4 +22,25 @@ m = z.G1Msm(1 << 10)
 ms = g['msm_g1_48']
 pts = b''.join(fr_bytes([int(q[0]), int(q[1])]) for q in ms['bases'])
 assert [str(x) for x in ints(m.msm(pts, fr_bytes([int(s) for s in ms['scalars']]), 48))] == ms['result']
+# paths added later in the round: cooperative Poseidon levels (> 10 parents per level) and the fused top, single-leaf update,
+# tree queries, sliced-bucket MSM with skewed scalars, V3 object, external witness, seeded keygen
+rln.set_leaves_from(0, list(range(1, 700)))
+rln.set_leaf(3, 99); rln.delete_leaf(4)
+assert rln.get_subtree_root(0, 0) == rln.get_root() and rln.get_empty_leaves_indices() == [4]
+import numpy as np
+n = 1 << 10
+bases = pts * (n // 48) + pts[:64 * (n % 48)]
+for sc in ([5] * n, [i % 2 for i in range(n)]):
+    m.msm(bases, fr_bytes(sc), n)
+v3 = z.RLNV3.stateful("full", 10, resource(10, "rln_final.arkzkey"), resource(10, "graph.bin"))
+args = kat_witness_args(10, k['inputs'])
+w3 = z.WitnessV3.new_single(*args[:3], args[3], args[4], args[5], args[6])
+p3 = v3.generate_proof_with_rs(w3, int(k['inputs']['r']), int(k['inputs']['s']))
+assert p3.to_bytes_le()[:128].hex() == k['rln_proof_le_hex'][2:258] and v3.verify(p3, args[5])
+from pyref import groth16 as G
+gr = G.parse_graph(resource(10, "graph.bin"))
+wires = G.evaluate(gr, G.inputs_buffer(gr, *args))
+pw = rln.generate_rln_proof_with_witness(wires, z.RLNWitnessInput.from_bytes_le(wb), int(k['inputs']['r']), int(k['inputs']['s']))
+assert pw.to_bytes_le().hex() == k['rln_proof_le_hex']
+z.seeded_keygen(b"abc")
 print('sanitize workload ok')
