@@ -431,6 +431,9 @@ int rlnb200_glv_enabled(FFI_RLN_t *const *rln);
 /* self-test of the split kernel: n canonical 32-byte scalars -> n x 36 bytes (|k1| 16 B LE, |k2| 16 B LE, sign1, sign2,
  * 2 pad bytes) with k = (+-k1) + (+-k2)*lambda mod r and |ki| < 2^128 */
 int rlnb200_glv_split(const uint8_t *scalars_le, size_t n, uint8_t *out36, RlnString *err);
+/* self-test of the Straus / GLV double multiplication used by the proof assembly (s*g_a + r*g1_b): n items of
+ * P (64 B canonical affine) | kp (32 B) | Q (64 B) | kq (32 B) -> n x 64 B canonical affine kp*P + kq*Q (use_q = 0: kp*P) */
+int rlnb200_glv_double_mul(const uint8_t *items192, size_t n, int use_q, uint8_t *out64, RlnString *err);
 
 /* Merkle tree bulk operations on device/host buffers (FullMerkleTree semantics,
  * utils/src/merkle_tree/full_merkle_tree.rs:197-223,288-304) */

@@ -9,6 +9,7 @@
 #include "pairing_constants.hpp"
 #include "tower.cuh"
 #include "vm.cuh"
+#include "glv.cuh"
 
 using namespace zk;
 
@@ -69,6 +70,24 @@ void emu_g2_add(const uint8_t* p, const uint8_t* q, uint8_t* out) {
     G2Affine b = ld_g2(q);
     if (!b.is_inf()) a.add_affine(b);
     st_g2(out, a.to_affine());
+}
+// GLV split of a canonical scalar: out = |k1| (16 B) | |k2| (16 B) | sign1 | sign2
+void emu_glv_split(const uint8_t* k, uint8_t* out) {
+    u32 kk[8], h[8];
+    memcpy(kk, k, 32);
+    for (int half = 0; half < 2; half++) {
+        out[32 + half] = glv::split(kk, half, h) ? 1 : 0;
+        memcpy(out + 16 * half, h, 16);
+    }
+}
+// kp·P + kq·Q through the Straus / GLV routine of the proof assembly
+void emu_glv_double_mul(const uint8_t* p, const uint8_t* kp, const uint8_t* q, const uint8_t* kq, int use_q, uint8_t* out) {
+    u32 a[8], b[8];
+    memcpy(a, kp, 32);
+    memcpy(b, kq, 32);
+    G1XYZZ P = G1XYZZ::from_affine(ld_g1(p)), Q = G1XYZZ::from_affine(ld_g1(q));
+    P = P.dbl(); P.add(G1XYZZ::from_affine(ld_g1(p)).neg());   // same point, non-trivial ZZ / ZZZ
+    st_g1(out, glv_double_mul(P, a, Q, b, use_q != 0).to_affine());
 }
 // G2 membership test used by the verifier's point decompression (point must be on the twist)
 int emu_g2_in_subgroup(const uint8_t* p) {

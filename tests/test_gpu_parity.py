@@ -72,6 +72,18 @@ def test_glv_split_kernel(z):
         assert abs(k1) < 1 << 128 and abs(k2) < 1 << 128
 
 
+def test_glv_double_mul_kernel(z):
+    """the Straus / GLV routine of the proof assembly (s·g_a + r·g1_b) against plain double-and-add on Python integers"""
+    from pyref import fields as F
+    lam = 0xb3c4d79d41a917585bfc41088d8daaa78b17ea66b99c90dd
+    rnd = random.Random(78)
+    Pt, Qt = F.pt_mul(F.OPS1, F.G1_GEN, 1234567), F.pt_mul(F.OPS1, F.G1_GEN, 7654321)
+    ks = [(77, 44), (1, 0), (0, 5), (R - 1, R - 2), (lam, lam + 1), (1 << 128, (1 << 127) + 3)] + [(rnd.randrange(R), rnd.randrange(R)) for _ in range(58)]
+    items = [(Pt, kp, Qt, kq) for kp, kq in ks]
+    assert z.glv_double_mul(items) == [F.pt_add(F.OPS1, F.pt_mul(F.OPS1, Pt, kp), F.pt_mul(F.OPS1, Qt, kq)) for kp, kq in ks]
+    assert z.glv_double_mul(items, use_q=False) == [F.pt_mul(F.OPS1, Pt, kp) for kp, kq in ks]
+
+
 # ------------------------------------------------------------------------------- Poseidon
 def test_poseidon_reference_kats(z, goldens):
     """utils/tests/poseidon_hash_test.rs:21-130"""

@@ -102,6 +102,25 @@ def test_curve_ops(emu):
         assert _g2r(o2.raw) == F.pt_double(F.OPS2, P2)
 
 
+def test_glv_split_and_double_mul(emu):
+    """k ≡ k1 + k2·λ with |ki| < 2^128, and the Straus double multiplication of the proof assembly: kp·P + kq·Q"""
+    lam = 0xb3c4d79d41a917585bfc41088d8daaa78b17ea66b99c90dd
+    rnd = random.Random(10)
+    for k in [0, 1, 77, R - 1, lam, 1 << 253] + [rnd.randrange(R) for _ in range(200)]:
+        out = ctypes.create_string_buffer(36)
+        emu.emu_glv_split(b32(k), out)
+        k1, k2 = int.from_bytes(out.raw[:16], "little"), int.from_bytes(out.raw[16:32], "little")
+        k1, k2 = (-k1 if out.raw[32] else k1), (-k2 if out.raw[33] else k2)
+        assert (k1 + k2 * lam - k) % R == 0 and abs(k1) < 1 << 128 and abs(k2) < 1 << 128
+    Pt, Qt = F.pt_mul(F.OPS1, F.G1_GEN, 1234567), F.pt_mul(F.OPS1, F.G1_GEN, 7654321)
+    for kp, kq in [(77, 44), (1, 0), (0, 5), (R - 1, R - 2), (lam, lam + 1)] + [(rnd.randrange(R), rnd.randrange(R)) for _ in range(6)]:
+        out = ctypes.create_string_buffer(64)
+        emu.emu_glv_double_mul(_g1b(Pt), b32(kp), _g1b(Qt), b32(kq), 1, out)
+        assert _g1r(out.raw) == F.pt_add(F.OPS1, F.pt_mul(F.OPS1, Pt, kp), F.pt_mul(F.OPS1, Qt, kq)), (kp, kq)
+        emu.emu_glv_double_mul(_g1b(Pt), b32(kp), _g1b(Qt), b32(kq), 0, out)
+        assert _g1r(out.raw) == F.pt_mul(F.OPS1, Pt, kp)
+
+
 def test_g2_subgroup_check(emu):
     """ψ(P) = [6x²]P accepts exactly the r-torsion: multiples of the generator pass, other points of the twist fail"""
     rnd = random.Random(9)

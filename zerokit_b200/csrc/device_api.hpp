@@ -107,6 +107,8 @@ void launch_build_table_g1(const G1Affine* d_bases, u32 n, int c, int K, G1Affin
 void launch_build_table_g2(const G2Affine* d_bases, u32 n, int c, int K, G2Affine* d_table, cudaStream_t s);
 // self-test of the GLV split: n canonical scalars → n × 36 bytes (|k₁| 16 B, |k₂| 16 B, sign₁, sign₂, 2 pad)
 void launch_glv_split(const uint8_t* d_scalars, size_t n, uint8_t* d_out, cudaStream_t s);
+// self-test of the Straus / GLV double multiplication of the proof assembly: n × (P 64 | kp 32 | Q 64 | kq 32) → n × 64 B
+void launch_glv_double_mul(const uint8_t* d_in, size_t n, int use_q, uint8_t* d_out, cudaStream_t s);
 struct ProverKeyDev {  // fixed points of the proving key (affine, Montgomery)
     G1Affine alpha_g1, beta_g1, delta_g1;
     G2Affine beta_g2, delta_g2;

@@ -22,6 +22,7 @@
 #define ZK_FQ2_OUTLINE 1  // this TU only: Fq2 products call one shared out-of-line Fq multiplier (see fp.cuh mul_ni)
 #include "device_api.hpp"
 #include "fixed_base.cuh"
+#include "glv.cuh"
 
 namespace zk {
 
@@ -96,90 +97,6 @@ void launch_build_table_g2(const G2Affine* d_bases, u32 n, int c, int K, G2Affin
 // Σ k·P = Σ k₁·P + φ(Σ k₂·P), both sums over the SAME table, φ applied once per partial sum in k_msm_reduce.
 // With c = 13 that is 2 × 10 additions per term instead of 22 at c = 12, in 10 % less table memory.
 // (Same group element as ark-ec's msm_bigint, rln/src/partial_proof.rs:98-104 — the result is unique.)
-namespace glv {
-__device__ __constant__ const u32 S[2] = {0x94d213e3u, 0x89d32568u};
-__device__ __constant__ const u32 N1[4] = {0x7d4f1128u, 0x8211bbebu, 0xeeb859fcu, 0x6f4d8248u};
-__device__ __constant__ const u32 N2[4] = {0x1221250bu, 0x0be4e154u, 0xeeb859fdu, 0x6f4d8248u};
-__device__ __constant__ const u32 G1C[3] = {0xc7e0b3d7u, 0xd91d232eu, 0x2u};                             // ⌊2^256·s/r⌋
-__device__ __constant__ const u32 G2C[5] = {0x391eb18du, 0x7a7bd9d4u, 0xa773d2cfu, 0x4ccef014u, 0x2u};   // ⌊2^256·N₁/r⌋
-// β in Montgomery form
-__device__ __forceinline__ Fq beta() {
-    Fq b;
-    b.l[0] = 0xd782e155u; b.l[1] = 0x71930c11u; b.l[2] = 0xffbe3323u; b.l[3] = 0xa6bb947cu;
-    b.l[4] = 0xd4741444u; b.l[5] = 0xaa303344u; b.l[6] = 0x26594943u; b.l[7] = 0x2c3b3f0du;
-    return b;
-}
-__device__ __forceinline__ Fq beta2() {   // β² in Montgomery form
-    Fq b;
-    b.l[0] = 0x13e80b9cu; b.l[1] = 0x3350c88eu; b.l[2] = 0xdb5e56b9u; b.l[3] = 0x7dce557cu;
-    b.l[4] = 0xb615564au; b.l[5] = 0x6001b4b8u; b.l[6] = 0x020217e0u; b.l[7] = 0x2682e617u;
-    return b;
-}
-// low NR words of a × b
-template <int NA, int NB, int NR>
-__device__ __forceinline__ void mul_words(const u32* a, const u32* b, u32* r) {
-#pragma unroll
-    for (int i = 0; i < NR; i++) r[i] = 0;
-#pragma unroll
-    for (int i = 0; i < NA; i++) {
-        u64 carry = 0;
-#pragma unroll
-        for (int j = 0; j < NB; j++) {
-            if (i + j < NR) {
-                u64 t = (u64)a[i] * b[j] + r[i + j] + carry;
-                r[i + j] = (u32)t;
-                carry = t >> 32;
-            }
-        }
-        if (i + NB < NR) r[i + NB] = (u32)carry;
-    }
-}
-// |k₁| (half = 0) or |k₂| (half = 1) of the canonical scalar k into out[0..7] (upper words zero); returns the sign
-__device__ __forceinline__ bool split(const u32* k, int half, u32* out) {
-    u32 t1[11], t2[13];
-    mul_words<8, 3, 11>(k, G1C, t1);
-    mul_words<8, 5, 13>(k, G2C, t2);
-    const u32* c1 = t1 + 8;   // ⌊k·G1/2^256⌋ < 2^66
-    const u32* c2 = t2 + 8;   // ⌊k·G2/2^256⌋ < 2^128
-    u32 a[5], b[5], r[5];
-    if (half == 0) {          // k₁ = k − c1·s − c2·N₂   (mod 2^160, |k₁| < 2^128)
-        mul_words<3, 2, 5>(c1, S, a);
-        mul_words<5, 4, 5>(c2, N2, b);
-        u64 br = 0;
-#pragma unroll
-        for (int i = 0; i < 5; i++) {
-            u64 d = (u64)k[i] - a[i] - br;
-            r[i] = (u32)d; br = (d >> 32) & 1;
-        }
-        br = 0;
-#pragma unroll
-        for (int i = 0; i < 5; i++) {
-            u64 d = (u64)r[i] - b[i] - br;
-            r[i] = (u32)d; br = (d >> 32) & 1;
-        }
-    } else {                  // k₂ = c1·N₁ − c2·s
-        mul_words<3, 4, 5>(c1, N1, a);
-        mul_words<5, 2, 5>(c2, S, b);
-        u64 br = 0;
-#pragma unroll
-        for (int i = 0; i < 5; i++) {
-            u64 d = (u64)a[i] - b[i] - br;
-            r[i] = (u32)d; br = (d >> 32) & 1;
-        }
-    }
-    const bool neg = (r[4] >> 31) != 0;
-    if (neg) {
-        u64 c = 1;
-#pragma unroll
-        for (int i = 0; i < 5; i++) { c += (u64)(~r[i]); r[i] = (u32)c; c >>= 32; }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) out[i] = r[i];
-#pragma unroll
-    for (int i = 4; i < 8; i++) out[i] = 0;
-    return neg;
-}
-}  // namespace glv
 
 __global__ void k_glv_split(const uint8_t* __restrict__ scalars, size_t n, uint8_t* __restrict__ out) {  // self-test: n × (16 B |k₁|, 16 B |k₂|, 2 sign bytes)
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -192,6 +109,26 @@ __global__ void k_glv_split(const uint8_t* __restrict__ scalars, size_t n, uint8
         out[36 * i + 32 + half] = neg ? 1 : 0;
     }
     out[36 * i + 34] = 0; out[36 * i + 35] = 0;
+}
+// self-test of glv_double_mul: per item P (64 B affine canonical), kp (32 B), Q (64 B), kq (32 B) → kp·P + kq·Q (64 B); P enters
+// with non-trivial ZZ / ZZZ (2P − P) like the sums the assembly feeds it
+__global__ void k_glv_double_mul(const uint8_t* __restrict__ in, size_t n, int use_q, uint8_t* __restrict__ out) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t* p = in + 192 * i;
+    auto ld = [](const uint8_t* b) { u32 c[8]; for (int w = 0; w < 8; w++) c[w] = reinterpret_cast<const u32*>(b)[w]; return Fq::from_canonical(c); };
+    const G1Affine Pa = {ld(p), ld(p + 32)}, Qa = {ld(p + 96), ld(p + 128)};
+    u32 kp[8], kq[8];
+    for (int w = 0; w < 8; w++) { kp[w] = reinterpret_cast<const u32*>(p + 64)[w]; kq[w] = reinterpret_cast<const u32*>(p + 160)[w]; }
+    G1XYZZ P = G1XYZZ::from_affine(Pa).dbl();
+    P.add(G1XYZZ::from_affine(Pa).neg());
+    const G1Affine r = glv_double_mul(P, kp, G1XYZZ::from_affine(Qa), kq, use_q != 0).to_affine();
+    u32 x[8] = {0, 0, 0, 0, 0, 0, 0, 0}, y[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (!r.is_inf()) { r.x.to_canonical(x); r.y.to_canonical(y); }
+    for (int w = 0; w < 8; w++) { reinterpret_cast<u32*>(out + 64 * i)[w] = x[w]; reinterpret_cast<u32*>(out + 64 * i + 32)[w] = y[w]; }
+}
+void launch_glv_double_mul(const uint8_t* d_in, size_t n, int use_q, uint8_t* d_out, cudaStream_t s) {
+    if (n) k_glv_double_mul<<<(unsigned)((n + 31) / 32), 32, 0, s>>>(d_in, n, use_q, d_out);
 }
 void launch_glv_split(const uint8_t* d_scalars, size_t n, uint8_t* d_out, cudaStream_t s) {
     if (n) k_glv_split<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_scalars, n, d_out);
@@ -458,13 +395,13 @@ __global__ void __launch_bounds__(64) k_assemble_g1(ProverKeyDev pk, const G1Aff
     if (!base_a.is_inf()) g_a.add_affine(base_a);
     g_a.add(fixed_base_mul<Fq>(dtab, c, K, r));
     // g_c = s·g_a + r·g1_b − rs·δ₁ + L + H
-    G1XYZZ g_c = g_a.mul(s);
+    G1XYZZ g1_b = G1XYZZ::infinity();
     if (rnz) {
-        G1XYZZ g1_b = sum[1 * (size_t)B + j];
+        g1_b = sum[1 * (size_t)B + j];
         if (!base_b.is_inf()) g1_b.add_affine(base_b);
         g1_b.add(fixed_base_mul<Fq>(dtab, c, K, s));
-        g_c.add(g1_b.mul(r));
     }
+    G1XYZZ g_c = glv_double_mul(g_a, s, g1_b, r, rnz != 0);
     g_c.add(fixed_base_mul<Fq>(dtab, c, K, rsv).neg());
     g_c.add(sum[2 * (size_t)B + j]);
     g_c.add(sum[3 * (size_t)B + j]);

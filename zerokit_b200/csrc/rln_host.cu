@@ -2060,6 +2060,17 @@ int rlnb200_glv_split(const uint8_t* scalars_le, size_t n, uint8_t* out36, RlnSt
         ZK_CUDA_CHECK(cudaMemcpy(out36, d_out.p, 36 * n, cudaMemcpyDeviceToHost));
     )
 }
+int rlnb200_glv_double_mul(const uint8_t* items192, size_t n, int use_q, uint8_t* out64, RlnString* err) {
+    INT_OP(
+        global_init();
+        DevMem d_in; DevMem d_out;
+        d_in.upload(items192, 192 * n);
+        d_out.alloc(64 * n);
+        launch_glv_double_mul(d_in.as<uint8_t>(), n, use_q, d_out.as<uint8_t>(), 0);
+        g_launch_count++;
+        ZK_CUDA_CHECK(cudaMemcpy(out64, d_out.p, 64 * n, cudaMemcpyDeviceToHost));
+    )
+}
 size_t rlnb200_num_wires(FFI_RLN_t* const* rln) { return (*rln)->r->n_wires(); }
 size_t rlnb200_witness_record_len(FFI_RLN_t* const* rln) { return witness_record_len(*(*rln)->r); }
 size_t rlnb200_proof_record_len(FFI_RLN_t* const* rln) { return proof_record_len(*(*rln)->r); }

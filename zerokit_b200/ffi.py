@@ -323,6 +323,7 @@ def lib():
         "rlnb200_vec_usize_free": (None, [Vec_size]),
         "rlnb200_glv_enabled": (c_int, [pp]),
         "rlnb200_glv_split": (c_int, [c_void_p, c_size_t, c_void_p, POINTER(RlnString)]),
+        "rlnb200_glv_double_mul": (c_int, [c_void_p, c_size_t, c_int, c_void_p, POINTER(RlnString)]),
         "rlnb200_pipe_probe": (c_int, [c_int, c_int, POINTER(c_double)]),
     }
     for name, (res, args) in sig.items():

@@ -806,6 +806,19 @@ def glv_split(scalars_le: bytes, n):
     return res
 
 
+def glv_double_mul(items, use_q=True):
+    """self-test of the assembly's Straus / GLV routine: items = [(P, kp, Q, kq)] with affine integer points → [kp·P + kq·Q]"""
+    buf = b"".join(b"".join(int(v).to_bytes(32, "little") for v in (P[0], P[1], kp, Q[0], Q[1], kq)) for P, kp, Q, kq in items)
+    out = ctypes.create_string_buffer(64 * len(items))
+    err = ffi.RlnString()
+    _check_int(ffi.lib().rlnb200_glv_double_mul(buf, len(items), 1 if use_q else 0, out, byref(err)), err)
+    res = []
+    for i in range(len(items)):
+        x, y = int.from_bytes(out.raw[64 * i:64 * i + 32], "little"), int.from_bytes(out.raw[64 * i + 32:64 * i + 64], "little")
+        res.append(None if x == 0 and y == 0 else (x, y))
+    return res
+
+
 def hash_pairs(pairs_bytes, n):
     out = ctypes.create_string_buffer(32 * n)
     err = ffi.RlnString()
