@@ -533,6 +533,33 @@ def test_proof_from_external_witness(z, rln10, goldens):
         rln10.verify_with_roots(p3, p3.values.x, [])
 
 
+def test_one_handle_many_threads(z, rln10, goldens):
+    """the reference's prove / verify take &self and may be called from many threads on one handle (SURVEY §8b, threading);
+    here the handle serialises them — results must be the same as single-threaded"""
+    import threading
+    k = goldens["derived"]["kat_proof_d10"]
+    wb = witness_le(*kat_witness_args(10, k["inputs"]))
+    r, s = int(k["inputs"]["r"]), int(k["inputs"]["s"])
+    out, errs = {}, []
+
+    def work(t):
+        try:
+            for i in range(3):
+                wit = z.RLNWitnessInput.from_bytes_le(wb)
+                p = rln10.generate_rln_proof_with_rs(wit, r, s)
+                assert rln10.verify_with_roots(p, p.values.x, [])
+                out[(t, i)] = p.to_bytes_le().hex()
+        except Exception as e:   # noqa: BLE001
+            errs.append(e)
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    assert len(out) == 12 and set(out.values()) == {k["rln_proof_le_hex"]}
+
+
 def test_v3_api(z, goldens, oracle):
     """rln/tests/ffi.rs V3 section + rln/tests/public.rs: RLNV3 over the same prover — stateless and stateful builds, proof ==
     the V1 golden proof for the same (r, s), verify / verify_with_roots semantics, tree ops, V3 wire forms of the proof"""
