@@ -374,6 +374,36 @@ def run_gpu(args, rank, local_rank, world):
                     "sample": f"{n_cpu} proofs of the same batch, one worker thread per proof on {threads} host threads; C++ restatement of the "
                               f"ark-groth16/ark-circom path (oracle/cref), {dt_cpu:.1f} s"}
 
+    # ---- the other rows of BASELINE.md §3 on the CPU restatement (bounded: a few seconds in total)
+    cpu_rows = {}
+    try:
+        import numpy as np
+        t0 = time.perf_counter()
+        ctx.prove_batch(cpu_in[:len(cpu_in) // n_cpu], rs[:64], 1, 1)
+        cpu_rows["single_proof_ms_1_thread"] = 1e3 * (time.perf_counter() - t0)
+        rng = np.random.default_rng(1)
+        ks = rng.integers(0, 256, size=(4096, 32), dtype=np.uint8)
+        ks[:, 31] &= 0x1f
+        tile = C.g1_mul_gen(ks.tobytes(), 4096, threads)          # 4 096 distinct points, tiled: Pippenger's cost does not depend on the values
+        rows = []
+        for lg in (16, 18, 20):
+            nn = 1 << lg
+            sc = rng.integers(0, 256, size=(nn, 32), dtype=np.uint8)
+            sc[:, 31] &= 0x1f
+            t0 = time.perf_counter()
+            C.msm_g1(tile * (nn // 4096), sc.tobytes(), nn, threads)
+            rows.append({"log2_n": lg, "ms": 1e3 * (time.perf_counter() - t0)})
+        cpu_rows["msm_g1"] = rows
+        lv = rng.integers(0, 256, size=(1 << DEPTH, 32), dtype=np.uint8)
+        lv[:, 31] &= 0x1f
+        t0 = time.perf_counter()
+        C.merkle_build(DEPTH, lv.tobytes(), 0, 1 << DEPTH, threads)
+        cpu_rows["merkle_build_2pow20_ms"] = 1e3 * (time.perf_counter() - t0)
+        cpu_rows["threads"] = threads
+        cpu_rows["what"] = "oracle/cref (C++ restatement of the ark path): ark-ec window rule Pippenger, level-parallel FullMerkleTree build"
+    except Exception as e:   # noqa: BLE001
+        cpu_rows["error"] = str(e)
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -387,6 +417,7 @@ def run_gpu(args, rank, local_rank, world):
                 "steps": e2e_steps, "api": "rlnb200_prove_batch (host witness records → host rln_proof bytes)"},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "stage_ms": stage,
     }
+    line["cpu_rows"] = cpu_rows
     # ---- batch verification of the timed batch's proofs (rlnb200_verify_batch: host records in, flags out)
     line["verify_batch"] = {"proofs": n, "ms": verify_batch_ms, "proofs_per_s": n / (verify_batch_ms * 1e-3),
                             "api": "rlnb200_verify_batch (decompression + subgroup checks + 4 Miller loops + final exponentiation per proof)"}
