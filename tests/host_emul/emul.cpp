@@ -10,6 +10,7 @@
 #include "tower.cuh"
 #include "vm.cuh"
 #include "glv.cuh"
+#include "host_util.hpp"
 
 using namespace zk;
 
@@ -70,6 +71,48 @@ void emu_g2_add(const uint8_t* p, const uint8_t* q, uint8_t* out) {
     G2Affine b = ld_g2(q);
     if (!b.is_inf()) a.add_affine(b);
     st_g2(out, a.to_affine());
+}
+// the witness VM exactly as k_witness runs it — bundle schedule, operand sources (ring / constant table / vals) — for ONE proof:
+// slots of a bundle are evaluated one after the other (they are independent), the ring is overwritten in place.
+// inputs: n_slots × 32 canonical bytes; out: n_nodes × 32 canonical bytes.  returns −1 on a parse error, else the "bad" flag.
+int emu_witness_scheduled(const uint8_t* graph, size_t glen, const uint8_t* inputs, uint8_t* out, uint32_t* n_bundles_out) {
+    GraphHost g;
+    try { parse_graph(graph, glen, g); } catch (...) { return -1; }
+    uint32_t nb = 0;
+    std::vector<VmRecord> recs = vm_build_schedule(g.prog, nb);
+    if (n_bundles_out) *n_bundles_out = nb;
+    std::vector<Fr> ring(VM_RING * VM_SLOTS), vals(g.prog.size()), consts(g.consts.size() / 32);
+    for (size_t i = 0; i < consts.size(); i++) consts[i] = ld<Fr>(g.consts.data() + 32 * i);
+    auto operand = [&](uint32_t enc) -> Fr {
+        const uint32_t src = enc >> 30, idx = enc & 0x3fffffffu;
+        return src == VM_SRC_RING ? ring[idx] : src == VM_SRC_CONST ? consts[idx] : vals[idx];
+    };
+    int bad = 0;
+    for (uint32_t b = 0; b < nb; b++) {
+        Fr res[VM_SLOTS];
+        bool have[VM_SLOTS];
+        for (uint32_t sl = 0; sl < VM_SLOTS; sl++) {   // all slots read the ring BEFORE any slot of this bundle writes it
+            const VmRecord& r = recs[(size_t)b * VM_SLOTS + sl];
+            have[sl] = r.kind_op != 0xffffffffu;
+            if (!have[sl]) continue;
+            const uint32_t kind = r.kind_op & 0xff, op = r.kind_op >> 8;
+            Fr v;
+            if (kind == VM_DUO) { if (!vm_eval_duo(op, operand(r.a), operand(r.b), v)) { bad = 1; v = Fr::zero(); } }
+            else if (kind == VM_CONST) v = consts[r.a];
+            else if (kind == VM_INPUT) v = ld<Fr>(inputs + 32 * r.a);
+            else if (kind == VM_UNO) { if (op == 0) v = operand(r.a).neg(); else { bad = 1; v = Fr::zero(); } }
+            else { Fr t = operand(r.a); v = t.is_zero() ? operand(r.c) : operand(r.b); }
+            res[sl] = v;
+        }
+        for (uint32_t sl = 0; sl < VM_SLOTS; sl++) {
+            if (!have[sl]) continue;
+            const VmRecord& r = recs[(size_t)b * VM_SLOTS + sl];
+            ring[(b % VM_RING) * VM_SLOTS + sl] = res[sl];
+            vals[r.out] = res[sl];
+        }
+    }
+    for (size_t i = 0; i < vals.size(); i++) st(out + 32 * i, vals[i]);
+    return bad;
 }
 // GLV split of a canonical scalar: out = |k1| (16 B) | |k2| (16 B) | sign1 | sign2
 void emu_glv_split(const uint8_t* k, uint8_t* out) {

@@ -102,6 +102,32 @@ def test_curve_ops(emu):
         assert _g2r(o2.raw) == F.pt_double(F.OPS2, P2)
 
 
+@pytest.mark.parametrize("depth,sub", [(10, ""), (20, ""), (20, "multi_message_id/max_out_4")])
+def test_scheduled_witness_vm(emu, depth, sub):
+    """the bundle schedule + operand-source encoding of k_witness (ring / constant table / vals), emulated on the host for one
+    proof, reproduces the oracle's graph evaluation node for node"""
+    path = os.path.join(ROOT, "zerokit_b200", "resources", f"tree_depth_{depth}", sub, "graph.bin")
+    graph = open(path, "rb").read()
+    g = G.parse_graph(graph)
+    pe = [P.poseidon([i + 7]) for i in range(depth)]
+    idx = [(5 * i + 1) % 2 for i in range(depth)]
+    if sub:
+        buf = G.inputs_buffer(g, 424242, 50, [3, 7, 11, 0], pe, idx, 1234567, 89, selector_used=[1, 0, 1, 0])
+    else:
+        buf = G.inputs_buffer(g, 123456789, 100, 1, pe, idx, 42, 100)
+    want = G.evaluate_nodes(g, buf) if hasattr(G, "evaluate_nodes") else None
+    inputs = b"".join(int(v).to_bytes(32, "little") for v in buf)
+    out = ctypes.create_string_buffer(32 * len(g.nodes))
+    nb = ctypes.c_uint32()
+    assert emu.emu_witness_scheduled(graph, len(graph), inputs, out, ctypes.byref(nb)) == 0
+    vals = [int.from_bytes(out.raw[32 * i:32 * i + 32], "little") for i in range(len(g.nodes))]
+    wires = G.evaluate(g, buf)
+    assert [vals[s] for s in g.signals] == wires
+    assert nb.value < len(g.nodes) // 2        # the schedule really is ≥ 2 nodes wide on average
+    if want is not None:
+        assert vals == want
+
+
 def test_glv_split_and_double_mul(emu):
     """k ≡ k1 + k2·λ with |ki| < 2^128, and the Straus double multiplication of the proof assembly: kp·P + kq·Q"""
     lam = 0xb3c4d79d41a917585bfc41088d8daaa78b17ea66b99c90dd

@@ -61,9 +61,9 @@ struct CircuitDev {
     const VmInstr* prog;
     const Fr* consts;
     const u32* signals;  // wire → node
-    // list schedule of the graph: bundle b holds up to 4 mutually independent nodes sched[4b .. 4b+3] (0xffffffff = empty slot)
-    // whose operands all lie in earlier bundles; one warp per slot evaluates them side by side (k_witness)
-    const u32* sched;
+    // list schedule of the graph (host_util.hpp vm_build_schedule): bundle b holds up to VM_SLOTS mutually independent nodes,
+    // records sched[VM_SLOTS·b ..], whose operands all lie in earlier bundles; one warp per slot evaluates them (k_witness)
+    const uint4* sched;   // VmRecord, two uint4 each
     u32 n_bundles;
     // QAP
     u32 n_constraints, n_instance, domain, log_domain;

@@ -403,4 +403,60 @@ inline void parse_graph(const uint8_t* d, size_t n, GraphHost& g) {
         if ((in.kind_op & 0xff) == VM_INPUT && in.a >= g.n_slots) throw std::runtime_error("input index out of range");
 }
 
+
+// ------------------------------------------------------------------------------- witness VM schedule
+// k_witness evaluates the graph with four warps per 32 proofs: the nodes are list-scheduled into bundles of ≤ VM_SLOTS mutually
+// independent nodes (every operand lies in an earlier bundle), warp w executes slot w.  Recent values are also kept in a
+// shared-memory ring of VM_RING bundles, so an operand produced ≤ VM_RING − 1 bundles ago is a shared-memory read instead of an
+// L2 round trip on the critical path; constants are read from the constant table; anything older comes from vals[node][B].
+struct VmRecord {            // 32 bytes: two 128-bit loads per (bundle, slot)
+    uint32_t kind_op;        // as VmInstr; 0xffffffff = empty slot
+    uint32_t out;            // node index of the result
+    uint32_t a, b, c;        // operands: source type in the top 2 bits (VM_SRC_*), index below
+    uint32_t pad[3];
+};
+inline std::vector<VmRecord> vm_build_schedule(const std::vector<VmInstr>& prog, uint32_t& n_bundles) {
+    const size_t n = prog.size();
+    std::vector<uint32_t> bundle(n), slot(n), fill;
+    for (size_t i = 0; i < n; i++) {
+        const VmInstr& in = prog[i];
+        const uint32_t kind = in.kind_op & 0xff;
+        uint32_t b = 0;
+        auto after = [&](uint32_t op) { if (bundle[op] + 1 > b) b = bundle[op] + 1; };
+        if (kind == VM_UNO || kind == VM_DUO || kind == VM_TRES) after(in.a);
+        if (kind == VM_DUO || kind == VM_TRES) after(in.b);
+        if (kind == VM_TRES) after(in.c);
+        for (;; b++) {
+            if (b >= fill.size()) fill.resize(b + 1, 0);
+            if (fill[b] < VM_SLOTS) break;
+        }
+        bundle[i] = b;
+        slot[i] = fill[b]++;
+    }
+    n_bundles = (uint32_t)fill.size();
+    VmRecord empty;
+    memset(&empty, 0, sizeof empty);
+    empty.kind_op = 0xffffffffu;
+    std::vector<VmRecord> recs((size_t)n_bundles * VM_SLOTS, empty);
+    for (size_t i = 0; i < n; i++) {
+        const VmInstr& in = prog[i];
+        const uint32_t kind = in.kind_op & 0xff;
+        auto enc = [&](uint32_t op) -> uint32_t {
+            const uint32_t ok = prog[op].kind_op & 0xff;
+            if (ok == VM_CONST) return (VM_SRC_CONST << 30) | prog[op].a;
+            if (bundle[i] - bundle[op] <= VM_RING - 1) return (VM_SRC_RING << 30) | ((bundle[op] % VM_RING) * VM_SLOTS + slot[op]);
+            return (VM_SRC_GLOBAL << 30) | op;
+        };
+        VmRecord r = empty;
+        r.kind_op = in.kind_op;
+        r.out = (uint32_t)i;
+        r.a = in.a; r.b = in.b; r.c = in.c;   // INPUT / CONST keep their raw index
+        if (kind == VM_UNO || kind == VM_DUO || kind == VM_TRES) r.a = enc(in.a);
+        if (kind == VM_DUO || kind == VM_TRES) r.b = enc(in.b);
+        if (kind == VM_TRES) r.c = enc(in.c);
+        recs[(size_t)bundle[i] * VM_SLOTS + slot[i]] = r;
+    }
+    return recs;
+}
+
 }  // namespace zk

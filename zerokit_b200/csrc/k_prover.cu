@@ -27,53 +27,73 @@ __device__ __forceinline__ Fr load_canonical_fr(const uint8_t* p) {
 // The graph is a 23 414-node program whose longest dependency chain is 10 000 nodes, and a single warp evaluating it runs at
 // 0.2 IPC (dependent issue) while three of the four schedulers of its SM idle.  So 32 proofs share a CTA of four warps: the host
 // list-schedules the nodes into bundles of ≤ 4 mutually independent nodes (operands in earlier bundles only), warp w evaluates
-// slot w of every bundle for its 32 proofs, and a barrier separates bundles (values travel through vals[node][B], L1-coherent
-// inside a CTA).  10 337 bundles instead of 23 414 serial nodes at depth 20.
-__device__ __forceinline__ Fr vm_eval_node(const CircuitDev& c, const uint4 raw, const uint8_t* __restrict__ in, const Fr* vals,
-                                           u32 B, u32 j, u32& bad) {
-    const u32 kind = raw.x & 0xff, op = raw.x >> 8;
-    Fr v;
-    if (kind == VM_DUO) {
-        Fr a = ld_fp(vals + (size_t)raw.y * B + j);
-        Fr b = ld_fp(vals + (size_t)raw.z * B + j);
-        if (op == OP_MUL) v = a * b;
-        else if (op == OP_ADD) v = a + b;
-        else if (op == OP_SUB) v = a - b;
-        else if (!vm_eval_duo(op, a, b, v)) { bad = 1; v = Fr::zero(); }
-    } else if (kind == VM_CONST) {
-        v = ldg_fp(c.consts + raw.y);
-    } else if (kind == VM_INPUT) {
-        v = load_canonical_fr(in + 32 * raw.y);
-    } else if (kind == VM_UNO) {
-        if (op == 0) v = ld_fp(vals + (size_t)raw.y * B + j).neg();
-        else { bad = 1; v = Fr::zero(); }  // "uno operator Id not implemented" (graph.rs:189-193)
-    } else {  // TernCond (graph.rs:216-222)
-        Fr t = ld_fp(vals + (size_t)raw.y * B + j);
-        v = t.is_zero() ? ld_fp(vals + (size_t)raw.w * B + j) : ld_fp(vals + (size_t)raw.z * B + j);
+// slot w of every bundle for its 32 proofs, and a barrier separates bundles.  A value is written to vals[node][B] (the QAP and
+// the MSMs read it there) and to a shared-memory ring of the last VM_RING bundles; 77 % of all operands were produced less than
+// 16 bundles earlier and the other 23 % are constants, so the critical path never waits for L2.
+__device__ __forceinline__ Fr vm_operand(u32 enc, const uint4* ring, const Fr* __restrict__ consts, const Fr* vals, u32 B, u32 j, u32 lane) {
+    const u32 src = enc >> 30, idx = enc & 0x3fffffffu;
+    if (src == VM_SRC_RING) {
+        const uint4 lo = ring[(idx * 2) * 32 + lane], hi = ring[(idx * 2 + 1) * 32 + lane];
+        Fr r;
+        r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w;
+        r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+        return r;
     }
-    return v;
+    if (src == VM_SRC_CONST) return ldg_fp(consts + idx);
+    return ld_fp(vals + (size_t)idx * B + j);
 }
 __global__ void __launch_bounds__(128) k_witness(CircuitDev c, const uint8_t* __restrict__ inputs, Fr* vals, u32 B, u32* __restrict__ err) {
+    extern __shared__ uint4 ring[];   // [VM_RING · VM_SLOTS][2][32 lanes]: the two 16-byte halves of a value, lane-contiguous
     const u32 lane = threadIdx.x & 31, slot = threadIdx.x >> 5;
     const u32 j = blockIdx.x * 32 + lane;
     const bool live = j < B;
     const uint8_t* in = inputs + (size_t)(live ? j : 0) * c.n_slots * 32;
     u32 bad = 0;
-    u32 node = c.sched[slot];
+    uint4 r0 = __ldg(c.sched + 2 * slot), r1 = __ldg(c.sched + 2 * slot + 1);
     for (u32 b = 0; b < c.n_bundles; b++) {
-        const u32 cur = node;
-        if (b + 1 < c.n_bundles) node = c.sched[(size_t)(b + 1) * 4 + slot];   // next slot word while this one computes
-        if (cur != 0xffffffffu && live) {
-            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(c.prog + cur));
-            st_fp(vals + (size_t)cur * B + j, vm_eval_node(c, raw, in, vals, B, j, bad));
+        const uint4 w0 = r0, w1 = r1;   // kind_op, out, a, b | c, pad
+        if (b + 1 < c.n_bundles) {      // next record while this one computes
+            r0 = __ldg(c.sched + 2 * ((size_t)(b + 1) * VM_SLOTS + slot));
+            r1 = __ldg(c.sched + 2 * ((size_t)(b + 1) * VM_SLOTS + slot) + 1);
+        }
+        if (w0.x != 0xffffffffu && live) {
+            const u32 kind = w0.x & 0xff, op = w0.x >> 8;
+            Fr v;
+            if (kind == VM_DUO) {
+                const Fr x = vm_operand(w0.z, ring, c.consts, vals, B, j, lane), y = vm_operand(w0.w, ring, c.consts, vals, B, j, lane);
+                if (op == OP_MUL) v = x * y;
+                else if (op == OP_ADD) v = x + y;
+                else if (op == OP_SUB) v = x - y;
+                else if (!vm_eval_duo(op, x, y, v)) { bad = 1; v = Fr::zero(); }
+            } else if (kind == VM_CONST) {
+                v = ldg_fp(c.consts + w0.z);
+            } else if (kind == VM_INPUT) {
+                v = load_canonical_fr(in + 32 * w0.z);
+            } else if (kind == VM_UNO) {
+                if (op == 0) v = vm_operand(w0.z, ring, c.consts, vals, B, j, lane).neg();
+                else { bad = 1; v = Fr::zero(); }  // "uno operator Id not implemented" (graph.rs:189-193)
+            } else {  // TernCond (graph.rs:216-222)
+                const Fr t = vm_operand(w0.z, ring, c.consts, vals, B, j, lane);
+                v = t.is_zero() ? vm_operand(w1.x, ring, c.consts, vals, B, j, lane) : vm_operand(w0.w, ring, c.consts, vals, B, j, lane);
+            }
+            const u32 ri = (b % VM_RING) * VM_SLOTS + slot;
+            ring[(ri * 2) * 32 + lane] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+            ring[(ri * 2 + 1) * 32 + lane] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+            st_fp(vals + (size_t)w0.y * B + j, v);
         }
         __syncthreads();
     }
     if (live && bad) atomicOr(err + j, 1u);
 }
 void launch_witness(const CircuitDev& c, const uint8_t* d_inputs, Fr* d_vals, u32 B, u32* d_err, cudaStream_t s) {
+    static const size_t smem = (size_t)VM_RING * VM_SLOTS * 2 * 32 * sizeof(uint4);   // 64 KB
+    static bool once = false;
+    if (!once) {
+        ZK_CUDA_CHECK(cudaFuncSetAttribute(k_witness, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        once = true;
+    }
     ZK_CUDA_CHECK(cudaMemsetAsync(d_err, 0, 4 * (size_t)B, s));
-    k_witness<<<(B + 31) / 32, 128, 0, s>>>(c, d_inputs, d_vals, B, d_err);
+    k_witness<<<(B + 31) / 32, 128, smem, s>>>(c, d_inputs, d_vals, B, d_err);
 }
 // externally calculated witness (generate_zk_proof_with_witness, rln/src/protocol/proof.rs:705-732): wire i of proof j goes to the
 // node the graph assigns to that wire, so the QAP and the MSMs read it exactly as if k_witness had produced it

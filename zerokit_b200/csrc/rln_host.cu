@@ -705,28 +705,12 @@ void Rln::build_circuit() {
     circ_.prog = d_prog_.as<VmInstr>();
     circ_.consts = d_consts_.as<Fr>();
     circ_.signals = d_signals_.as<u32>();
-    {   // list schedule for k_witness: every node goes to the earliest bundle after its operands that still has one of 4 slots free
-        const size_t n = gh_.prog.size();
-        std::vector<uint32_t> bundle(n), fill;
-        std::vector<uint32_t> sched;
-        for (size_t i = 0; i < n; i++) {
-            const VmInstr& in = gh_.prog[i];
-            const uint32_t kind = in.kind_op & 0xff;
-            uint32_t b = 0;
-            auto after = [&](uint32_t op) { if (bundle[op] + 1 > b) b = bundle[op] + 1; };
-            if (kind == VM_UNO || kind == VM_DUO || kind == VM_TRES) after(in.a);
-            if (kind == VM_DUO || kind == VM_TRES) after(in.b);
-            if (kind == VM_TRES) after(in.c);
-            for (;; b++) {
-                if (b >= fill.size()) { fill.resize(b + 1, 0); sched.resize(4 * (size_t)(b + 1), 0xffffffffu); }
-                if (fill[b] < 4) break;
-            }
-            sched[4 * (size_t)b + fill[b]++] = (uint32_t)i;
-            bundle[i] = b;
-        }
-        d_sched_.upload(sched.data(), sched.size() * 4);
-        circ_.sched = d_sched_.as<u32>();
-        circ_.n_bundles = (u32)fill.size();
+    {   // list schedule for k_witness (host_util.hpp): bundles of 4 independent nodes, operand sources resolved (ring / const / global)
+        uint32_t nb = 0;
+        std::vector<VmRecord> recs = vm_build_schedule(gh_.prog, nb);
+        d_sched_.upload(recs.data(), recs.size() * sizeof(VmRecord));
+        circ_.sched = d_sched_.as<uint4>();
+        circ_.n_bundles = nb;
     }
     circ_.n_constraints = (u32)zk_.num_constraints;
     circ_.n_instance = (u32)zk_.num_instance;

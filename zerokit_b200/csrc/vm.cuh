@@ -14,6 +14,11 @@ enum VmDuo : u32 {
     OP_LAND, OP_LOR, OP_SHL, OP_SHR, OP_BOR, OP_BAND, OP_BXOR
 };
 
+// bundle schedule of the graph (host_util.hpp vm_build_schedule, k_prover.cu k_witness)
+constexpr u32 VM_SLOTS = 4;    // nodes per bundle = warps per CTA
+constexpr u32 VM_RING = 16;    // bundles whose values stay in the shared-memory ring
+enum VmSrc : u32 { VM_SRC_RING = 0, VM_SRC_CONST = 1, VM_SRC_GLOBAL = 2 };
+
 struct VmInstr {  // 16 bytes: one 128-bit load per node
     u32 kind_op;  // kind | op << 8
     u32 a, b, c;
