@@ -70,3 +70,32 @@ def test_no_cpu_fallback():
         z.RLN.new(20)
     with pytest.raises(z.RLNError):
         z.poseidon_hash([1, 2])
+
+
+def _build_c_caller(tmp_path):
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "basic_caller")
+    libdir = os.path.dirname(ffi.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "c_caller", "basic_caller.c"), "-L", libdir, "-lrln_b200",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    return exe
+
+
+def test_plain_c_caller_links_and_runs(tmp_path):
+    """include/rln_b200.h is valid C11 and a C program written against it (the flow of rln/ffi_c_examples/basic_proof.c)
+    links with -lrln_b200; without a GPU it must hear 'no usable CUDA device' and still get the host-only codecs"""
+    import torch
+    ffi.lib()
+    exe = _build_c_caller(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert ("GPU-PATH-OK" if torch.cuda.is_available() else "HOST-PATH-OK") in out.stdout
+
+
+@pytest.mark.gpu
+def test_plain_c_caller_on_gpu(tmp_path):
+    ffi.lib()
+    out = subprocess.run([_build_c_caller(tmp_path)], capture_output=True, text=True, env={"RLN_B200_WINDOW_BITS": "8", "PATH": "/usr/bin:/bin"})
+    assert out.returncode == 0 and "GPU-PATH-OK" in out.stdout, out.stderr + out.stdout
