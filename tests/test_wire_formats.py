@@ -201,3 +201,35 @@ def test_v3_proof_values_records(z):
     v1 = z.ProofValuesV3.from_bytes_le(S.v3_values_single((a0 + 5 * a1) % R, root, nul, 5, en))
     v2 = z.ProofValuesV3.from_bytes_le(S.v3_values_single((a0 + 6 * a1) % R, root, nul, 6, en))
     assert v1.recover_id_secret(v2) == a0 == z.compute_id_secret_v3((5, (a0 + 5 * a1) % R), (6, (a0 + 6 * a1) % R))
+
+
+def test_codec_round_trips_random_shapes(z):
+    """property test in the spirit of rln/tests/serialize.rs: random depths, values at the field boundary, every record type,
+    LE ↔ BE ↔ V3 conversions all return to the same bytes"""
+    rnd = random.Random(99)
+    edge = [0, 1, R - 1, R - 2, 1 << 253, (1 << 128) - 1]
+    for _ in range(40):
+        depth = rnd.choice([0, 1, 2, 7, 20, 32])
+        pick = lambda: rnd.choice(edge + [rnd.randrange(R)])
+        limit = rnd.choice([1, 2, 100, R - 1])
+        mid = rnd.randrange(limit)
+        a = dict(secret=pick(), limit=limit, mid=mid, path=[pick() for _ in range(depth)], idx=[rnd.randrange(2) for _ in range(depth)],
+                 x=pick(), en=pick())
+        w = z.RLNWitnessInput.new_single(a["secret"], a["limit"], a["mid"], a["path"], a["idx"], a["x"], a["en"])
+        le, be = w.to_bytes_le(), w.to_bytes_be()
+        assert le == S.witness_to_bytes(a["secret"], a["limit"], a["mid"], a["path"], a["idx"], a["x"], a["en"])
+        assert z.RLNWitnessInput.from_bytes_le(le).to_bytes_be() == be and z.RLNWitnessInput.from_bytes_be(be).to_bytes_le() == le
+        v3 = z.WitnessV3.from_bytes_be(be)            # the V1 and V3 BE records are the same bytes
+        assert v3.to_bytes_be() == be and z.WitnessV3.from_bytes_le(v3.to_bytes_le()).to_bytes_be() == be
+        assert v3.to_bytes_le() == S.v3_witness_single(a["secret"], a["limit"], a["mid"], a["path"], a["idx"], a["x"], a["en"])
+        pw = w.to_partial()
+        assert z.RLNPartialWitnessInput.from_bytes_be(pw.to_bytes_be()).to_bytes_le() == pw.to_bytes_le()
+        assert pw.to_bytes_le()[1:] == v3.to_partial().to_bytes_le()      # V3 drops the version byte
+        k = rnd.choice([1, 2, 4, 8])
+        ys, nulls, sel = [pick() for _ in range(k)], [pick() for _ in range(k)], [rnd.random() < 0.6 for _ in range(k)]
+        root = pick()
+        m_le = S.proof_values_to_bytes_multi(root, a["en"], a["x"], ys, nulls, sel)
+        assert z.proof_values_be_to_le(z.proof_values_le_to_be(m_le)) == m_le
+        v3v = z.ProofValuesV3.from_bytes_le(S.v3_values_multi(ys, root, nulls, a["x"], a["en"], sel))
+        assert z.ProofValuesV3.from_bytes_be(v3v.to_bytes_be()).to_bytes_le() == v3v.to_bytes_le()
+        assert (v3v.ys, v3v.nullifiers, v3v.selector_used, v3v.root) == (ys, nulls, sel, root)

@@ -87,11 +87,8 @@ __global__ void __launch_bounds__(128) k_witness(CircuitDev c, const uint8_t* __
 }
 void launch_witness(const CircuitDev& c, const uint8_t* d_inputs, Fr* d_vals, u32 B, u32* d_err, cudaStream_t s) {
     static const size_t smem = (size_t)VM_RING * VM_SLOTS * 2 * 32 * sizeof(uint4);   // 64 KB
-    static bool once = false;
-    if (!once) {
-        ZK_CUDA_CHECK(cudaFuncSetAttribute(k_witness, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        once = true;
-    }
+    // per-device attribute (a process may drive several GPUs through rlnb200_set_device): set on every launch, it is a cheap call
+    ZK_CUDA_CHECK(cudaFuncSetAttribute(k_witness, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ZK_CUDA_CHECK(cudaMemsetAsync(d_err, 0, 4 * (size_t)B, s));
     k_witness<<<(B + 31) / 32, 128, smem, s>>>(c, d_inputs, d_vals, B, d_err);
 }
