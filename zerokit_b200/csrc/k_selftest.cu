@@ -72,14 +72,16 @@ __global__ void __launch_bounds__(256) k_pipe_probe(u64* __restrict__ out, int i
     const double x = 1.0000001, y = 0.9999999;
     for (int i = 0; i < iters; i++) {
         if (MODE != 1) {
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a0) : "r"(m), "r"(n));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a1) : "r"(m), "r"(n));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a2) : "r"(m), "r"(n));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a3) : "r"(m), "r"(n));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a4) : "r"(m), "r"(n));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a5) : "r"(m), "r"(n));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a6) : "r"(m), "r"(n));
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a7) : "r"(m), "r"(n));
+            // one multiplicand is the low word of the accumulator itself: a loop-invariant product would be hoisted by ptxas and
+            // the loop would measure 64-bit additions, not the multiplier (an earlier version of this probe did exactly that)
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a0) : "r"((u32)a0), "r"(m));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a1) : "r"((u32)a1), "r"(n));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a2) : "r"((u32)a2), "r"(m));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a3) : "r"((u32)a3), "r"(n));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a4) : "r"((u32)a4), "r"(m));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a5) : "r"((u32)a5), "r"(n));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a6) : "r"((u32)a6), "r"(m));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a7) : "r"((u32)a7), "r"(n));
         }
         if (MODE != 0) {
             asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(d0) : "d"(x), "d"(y));
