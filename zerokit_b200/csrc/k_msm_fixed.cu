@@ -500,7 +500,10 @@ void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, 
         if (ws.h_ready) ZK_CUDA_CHECK(cudaStreamWaitEvent(s, ws.h_ready, 0));
         launch_g1(first_part, ws.n_tasks_g1 - first_part);
         if (ws.ev) cudaEventRecord(ws.ev[1], s);
-        if (B < 64) k_msm_reduce_small<Fq><<<dim3(B, 4), 128, 0, s>>>(ws.part_g1, ws.tasks_g1, ws.n_tasks_g1, B, ws.sum_g1);
+        // one CTA per (proof, group) with a shared-memory tree whenever there are many partials per proof: a thread-per-proof loop
+        // over hundreds of partials leaves the chip idle (4 096 threads)
+        const bool tree = B < 64 || accum_variant("RLN_B200_REDUCE_TREE") == 1;
+        if (tree) k_msm_reduce_small<Fq><<<dim3(B, 4), 128, 0, s>>>(ws.part_g1, ws.tasks_g1, ws.n_tasks_g1, B, ws.sum_g1);
         else k_msm_reduce<Fq><<<dim3((B + bx - 1) / bx, 4), bx, 0, s>>>(ws.part_g1, ws.tasks_g1, ws.n_tasks_g1, B, ws.sum_g1);
         if (ws.ev) cudaEventRecord(ws.ev[2], s);
     }
@@ -522,7 +525,8 @@ void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, 
             }
         }
         if (ws.ev) cudaEventRecord(ws.ev[3], s);
-        if (B < 64) k_msm_reduce_small<Fq2><<<dim3(B, 1), 128, 0, s>>>(ws.part_g2, ws.tasks_g2, ws.n_tasks_g2, B, ws.sum_g2);
+        const bool tree = B < 64 || accum_variant("RLN_B200_REDUCE_TREE") == 1;
+        if (tree) k_msm_reduce_small<Fq2><<<dim3(B, 1), 128, 0, s>>>(ws.part_g2, ws.tasks_g2, ws.n_tasks_g2, B, ws.sum_g2);
         else k_msm_reduce<Fq2><<<dim3((B + bx - 1) / bx, 1), bx, 0, s>>>(ws.part_g2, ws.tasks_g2, ws.n_tasks_g2, B, ws.sum_g2);
         if (ws.ev) cudaEventRecord(ws.ev[4], s);
     }
