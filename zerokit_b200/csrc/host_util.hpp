@@ -141,7 +141,7 @@ struct ByteReader {
     const uint8_t* p;
     size_t n, o = 0;
     void need(size_t k) const {
-        if (o + k > n) throw std::runtime_error("unexpected end of zkey data");
+        if (k > n - o) throw std::runtime_error("unexpected end of zkey data");
     }
     uint64_t u64() {
         need(8);
@@ -191,7 +191,9 @@ inline void parse_zkey(const uint8_t* data, size_t n, ZkeyHost& z) {
             if (k > n / 40) throw std::runtime_error("zkey matrix row too large");
             for (uint64_t e = 0; e < k; e++) {
                 r.take(val, 32);
-                col.push_back((uint32_t)r.u64());
+                const uint64_t c = r.u64();
+                if (c > 0xffffffffull) throw std::runtime_error("zkey matrix column out of range");
+                col.push_back((uint32_t)c);
             }
             ptr.push_back((uint32_t)col.size());
         }
@@ -242,7 +244,7 @@ inline bool pb_next(const uint8_t* p, size_t n, size_t& o, PbField& f) {
         case 0: return rd_varint(p, n, o, f.val);
         case 2: {
             uint64_t l;
-            if (!rd_varint(p, n, o, l) || o + l > n) return false;
+            if (!rd_varint(p, n, o, l) || l > n - o) return false;
             f.ptr = p + o;
             f.len = l;
             o += l;
@@ -301,7 +303,7 @@ inline void parse_graph(const uint8_t* d, size_t n, GraphHost& g) {
     g.prog.reserve(cnt);
     for (uint64_t i = 0; i < cnt; i++) {
         uint64_t len;
-        if (!rd_varint(d, n, o, len) || o + len > n) throw std::runtime_error("Unexpected EOF");
+        if (!rd_varint(d, n, o, len) || len > n - o) throw std::runtime_error("Unexpected EOF");
         const uint8_t* m = d + o;
         o += len;
         size_t mo = 0;
@@ -316,6 +318,8 @@ inline void parse_graph(const uint8_t* d, size_t n, GraphHost& g) {
             if (bf.tag < 5 && bf.wt == 0) vals[bf.tag] = bf.val;
             if (bf.tag == 1 && bf.wt == 2) { sub = bf.ptr; sublen = bf.len; }
         }
+        for (int k = 1; k < 5; k++)   // node indices are u32 on the device; the reference indexes a Vec and would panic
+            if (vals[k] > 0xffffffffull) throw std::runtime_error("node operand out of range");
         VmInstr in{0, 0, 0, 0};
         switch (f.tag) {
             case 1: in.kind_op = VM_INPUT; in.a = (uint32_t)vals[1]; break;
@@ -354,7 +358,7 @@ inline void parse_graph(const uint8_t* d, size_t n, GraphHost& g) {
         g.prog.push_back(in);
     }
     uint64_t mdlen;
-    if (!rd_varint(d, n, o, mdlen) || o + mdlen > n) throw std::runtime_error("Unexpected EOF");
+    if (!rd_varint(d, n, o, mdlen) || mdlen > n - o) throw std::runtime_error("Unexpected EOF");
     const uint8_t* md = d + o;
     size_t mo = 0;
     PbField f;
@@ -364,10 +368,11 @@ inline void parse_graph(const uint8_t* d, size_t n, GraphHost& g) {
             size_t po = 0;
             uint64_t v;
             while (po < f.len) {
-                if (!rd_varint(f.ptr, f.len, po, v)) throw std::runtime_error("malformed witness_signals");
+                if (!rd_varint(f.ptr, f.len, po, v) || v > 0xffffffffull) throw std::runtime_error("malformed witness_signals");
                 g.signals.push_back((uint32_t)v);
             }
         } else if (f.tag == 1 && f.wt == 0) {
+            if (f.val > 0xffffffffull) throw std::runtime_error("malformed witness_signals");
             g.signals.push_back((uint32_t)f.val);
         } else if (f.tag == 2 && f.wt == 2) {
             size_t eo = 0;
@@ -387,6 +392,7 @@ inline void parse_graph(const uint8_t* d, size_t n, GraphHost& g) {
                     }
                 }
             }
+            if (off > 0xffffffffull || ln > 0xffffffffull) throw std::runtime_error("input signal out of range");
             g.inputs[key] = {(uint32_t)off, (uint32_t)ln};
         }
     }
@@ -401,6 +407,8 @@ inline void parse_graph(const uint8_t* d, size_t n, GraphHost& g) {
     g.n_slots = mx + 1;
     for (auto& in : g.prog)
         if ((in.kind_op & 0xff) == VM_INPUT && in.a >= g.n_slots) throw std::runtime_error("input index out of range");
+    for (auto& kv : g.inputs)   // populate_inputs (iden3calc.rs:123-146) writes inputs[offset .. offset + len)
+        if ((uint64_t)kv.second.first + kv.second.second > g.n_slots) throw std::runtime_error("input signal out of range");
 }
 
 

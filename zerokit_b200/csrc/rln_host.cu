@@ -613,16 +613,24 @@ void Rln::check_graph_shape() {
     slots_.multi = multi_ ? 1 : 0;
     depth_ = pe.second;
     if (pi.second != depth_) throw RlnError("Graph error: pathElements / identityPathIndex length mismatch");
-    slots_.secret = need("identitySecret").first;
-    slots_.limit = need("userMessageLimit").first;
-    slots_.message_id = need("messageId").first;
+    auto scalar = [&](const char* name) {
+        auto s = need(name);
+        if (s.second != 1) throw RlnError(std::string("Graph error: input signal ") + name + " is not a single field element");
+        return s.first;
+    };
+    slots_.secret = scalar("identitySecret");
+    slots_.limit = scalar("userMessageLimit");
+    slots_.message_id = mid.first;
     slots_.path = pe.first;
     slots_.index = pi.first;
-    slots_.x = need("x").first;
-    slots_.ext_null = need("externalNullifier").first;
+    slots_.x = scalar("x");
+    slots_.ext_null = scalar("externalNullifier");
     slots_.depth = (u32)depth_;
     slots_.n_slots = gh_.n_slots;
     const size_t nw = gh_.signals.size();
+    if (nw == 0) throw RlnError("Graph error: no witness signals");
+    if (depth_ == 0 || depth_ > 32) throw RlnError("Graph error: unsupported tree depth");
+    if (zk_.gamma_abc.size() / 64 != zk_.num_instance) throw RlnError("ZKey error: gamma_abc size does not match the number of public inputs");
     if (zk_.a_query.size() / 64 != nw || zk_.b_g1.size() / 64 != nw || zk_.b_g2.size() / 128 != nw)
         throw RlnError("ZKey error: query sizes do not match the witness graph");
     if (zk_.l_query.size() / 64 + zk_.num_instance != nw) throw RlnError("ZKey error: l_query size does not match the witness graph");

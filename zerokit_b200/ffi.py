@@ -9,7 +9,7 @@ from ctypes import (POINTER, Structure, c_bool, c_char_p, c_double, c_float, c_i
                     c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "librln_b200.so")
+LIB_PATH = os.environ.get("RLN_B200_LIB") or os.path.join(_HERE, "lib", "librln_b200.so")   # override: instrumented builds
 
 
 class Vec_uint8(Structure):
