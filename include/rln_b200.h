@@ -82,6 +82,28 @@ typedef struct CResult_FFI_RLNV3PartialProof { FFI_RLNV3PartialProof_t *ok; RlnS
 typedef struct CResult_FFI_RLNV3ProofValues { FFI_RLNV3ProofValues_t *ok; RlnString err; } CResult_FFI_RLNV3ProofValues_t;
 typedef struct CResult_FFI_RLNV3MerkleProof { FFI_RLNV3MerkleProof_t *ok; RlnString err; } CResult_FFI_RLNV3MerkleProof_t;
 
+/* The type names safer-ffi generates for the instantiations above (CResult<Ok, Err> → CResult_<Ok>_<Err>_t with Box<T> → T_ptr and
+ * String → Vec_uint8), as callers of the generated rln.h spell them (rln/ffi_c_examples/common.c:8-28).  Same layouts. */
+typedef CResult_FFI_RLN_t                    CResult_FFI_RLN_ptr_Vec_uint8_t;
+typedef CResult_FFI_RLNProof_t               CResult_FFI_RLNProof_ptr_Vec_uint8_t;
+typedef CResult_FFI_RLNProofValues_t         CResult_FFI_RLNProofValues_ptr_Vec_uint8_t;
+typedef CResult_FFI_RLNWitnessInput_t        CResult_FFI_RLNWitnessInput_ptr_Vec_uint8_t;
+typedef CResult_FFI_RLNPartialWitnessInput_t CResult_FFI_RLNPartialWitnessInput_ptr_Vec_uint8_t;
+typedef CResult_FFI_RLNPartialProof_t        CResult_FFI_RLNPartialProof_ptr_Vec_uint8_t;
+typedef CResult_FFI_MerkleProof_t            CResult_FFI_MerkleProof_ptr_Vec_uint8_t;
+typedef CResult_CFr_t                        CResult_CFr_ptr_Vec_uint8_t;
+typedef CResult_Vec_uint8_t                  CResult_Vec_uint8_Vec_uint8_t;
+typedef CResult_Vec_CFr_t                    CResult_Vec_CFr_Vec_uint8_t;
+typedef CResult_Vec_bool_t                   CResult_Vec_bool_Vec_uint8_t;
+typedef Vec_String_t                         Vec_Vec_uint8_t;
+typedef CResult_FFI_RLNV3_t                    CResult_FFI_RLNV3_ptr_Vec_uint8_t;
+typedef CResult_FFI_RLNV3WitnessInput_t        CResult_FFI_RLNV3WitnessInput_ptr_Vec_uint8_t;
+typedef CResult_FFI_RLNV3PartialWitnessInput_t CResult_FFI_RLNV3PartialWitnessInput_ptr_Vec_uint8_t;
+typedef CResult_FFI_RLNV3Proof_t               CResult_FFI_RLNV3Proof_ptr_Vec_uint8_t;
+typedef CResult_FFI_RLNV3PartialProof_t        CResult_FFI_RLNV3PartialProof_ptr_Vec_uint8_t;
+typedef CResult_FFI_RLNV3ProofValues_t         CResult_FFI_RLNV3ProofValues_ptr_Vec_uint8_t;
+typedef CResult_FFI_RLNV3MerkleProof_t         CResult_FFI_RLNV3MerkleProof_ptr_Vec_uint8_t;
+
 /* ------------------------------------------------------------------ RLN object (rln/src/ffi/ffi_rln.rs) */
 CResult_FFI_RLN_t ffi_rln_new(size_t tree_depth, const char *config_path);                      /* :22-57  */
 CResult_FFI_RLN_t ffi_rln_new_with_params(size_t tree_depth, const Vec_uint8_t *zkey_data,
