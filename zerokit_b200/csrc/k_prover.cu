@@ -8,6 +8,8 @@
 // that the B proofs of a batch are the coalescing dimension: a warp that processes 32 proofs reads
 // 32 consecutive 32-byte field elements (two 128-bit loads per lane).  The instruction stream of
 // the witness VM and the NTT twiddles are uniform across the warp.
+#include <cstdlib>
+
 #include "device_api.hpp"
 
 namespace zk {
@@ -42,6 +44,11 @@ __device__ __forceinline__ Fr vm_operand(u32 enc, const uint4* ring, const Fr* _
     if (src == VM_SRC_CONST) return ldg_fp(consts + idx);
     return ld_fp(vals + (size_t)idx * B + j);
 }
+// STAGED (experimental, RLN_B200_WITNESS_STAGED=1, not yet measured): an add-only bundle lasts ≈ 200 cycles, less than the L2 round
+// trip of the one-deep record prefetch, so the record fetch sets the pace of 5 364 of the 10 337 bundles.  Staged, a warp fetches
+// the records of its slot for 16 bundles with one 128-bit load per lane (lane l: half l&1 of bundle base + l/2), one block ahead,
+// and hands them out with shuffles.
+template <bool STAGED>
 __global__ void __launch_bounds__(128) k_witness(CircuitDev c, const uint8_t* __restrict__ inputs, Fr* vals, u32 B, u32* __restrict__ err) {
     extern __shared__ uint4 ring[];   // [VM_RING · VM_SLOTS][2][32 lanes]: the two 16-byte halves of a value, lane-contiguous
     const u32 lane = threadIdx.x & 31, slot = threadIdx.x >> 5;
@@ -49,12 +56,34 @@ __global__ void __launch_bounds__(128) k_witness(CircuitDev c, const uint8_t* __
     const bool live = j < B;
     const uint8_t* in = inputs + (size_t)(live ? j : 0) * c.n_slots * 32;
     u32 bad = 0;
-    uint4 r0 = __ldg(c.sched + 2 * slot), r1 = __ldg(c.sched + 2 * slot + 1);
+    auto fetch16 = [&](u32 base) -> uint4 {
+        const u32 bb = base + (lane >> 1);
+        if (bb < c.n_bundles) return __ldg(c.sched + 2 * ((size_t)bb * VM_SLOTS + slot) + (lane & 1));
+        return make_uint4(0xffffffffu, 0, 0, 0);
+    };
+    uint4 r0, r1, cur, nxt;
+    if (STAGED) {
+        cur = fetch16(0);
+        nxt = fetch16(16);
+    } else {
+        r0 = __ldg(c.sched + 2 * slot);
+        r1 = __ldg(c.sched + 2 * slot + 1);
+    }
     for (u32 b = 0; b < c.n_bundles; b++) {
-        const uint4 w0 = r0, w1 = r1;   // kind_op, out, a, b | c, pad
-        if (b + 1 < c.n_bundles) {      // next record while this one computes
-            r0 = __ldg(c.sched + 2 * ((size_t)(b + 1) * VM_SLOTS + slot));
-            r1 = __ldg(c.sched + 2 * ((size_t)(b + 1) * VM_SLOTS + slot) + 1);
+        uint4 w0, w1;                   // kind_op, out, a, b | c, pad
+        if (STAGED) {
+            const u32 i = b & 15;
+            if (i == 0 && b) { cur = nxt; nxt = fetch16(b + 16); }
+            w0.x = __shfl_sync(0xffffffffu, cur.x, 2 * i); w0.y = __shfl_sync(0xffffffffu, cur.y, 2 * i);
+            w0.z = __shfl_sync(0xffffffffu, cur.z, 2 * i); w0.w = __shfl_sync(0xffffffffu, cur.w, 2 * i);
+            w1.x = __shfl_sync(0xffffffffu, cur.x, 2 * i + 1);
+            w1.y = w1.z = w1.w = 0;
+        } else {
+            w0 = r0; w1 = r1;
+            if (b + 1 < c.n_bundles) {  // next record while this one computes
+                r0 = __ldg(c.sched + 2 * ((size_t)(b + 1) * VM_SLOTS + slot));
+                r1 = __ldg(c.sched + 2 * ((size_t)(b + 1) * VM_SLOTS + slot) + 1);
+            }
         }
         if (w0.x != 0xffffffffu && live) {
             const u32 kind = w0.x & 0xff, op = w0.x >> 8;
@@ -88,9 +117,16 @@ __global__ void __launch_bounds__(128) k_witness(CircuitDev c, const uint8_t* __
 void launch_witness(const CircuitDev& c, const uint8_t* d_inputs, Fr* d_vals, u32 B, u32* d_err, cudaStream_t s) {
     static const size_t smem = (size_t)VM_RING * VM_SLOTS * 2 * 32 * sizeof(uint4);   // 64 KB
     // per-device attribute (a process may drive several GPUs through rlnb200_set_device): set on every launch, it is a cheap call
-    ZK_CUDA_CHECK(cudaFuncSetAttribute(k_witness, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static const bool staged = [] { const char* v = getenv("RLN_B200_WITNESS_STAGED"); return v && atoi(v) != 0; }();
     ZK_CUDA_CHECK(cudaMemsetAsync(d_err, 0, 4 * (size_t)B, s));
-    k_witness<<<(B + 31) / 32, 128, smem, s>>>(c, d_inputs, d_vals, B, d_err);
+    // the shared-memory attribute is per device (a process may drive several GPUs through rlnb200_set_device): set on every launch
+    if (staged) {
+        ZK_CUDA_CHECK(cudaFuncSetAttribute(k_witness<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_witness<true><<<(B + 31) / 32, 128, smem, s>>>(c, d_inputs, d_vals, B, d_err);
+    } else {
+        ZK_CUDA_CHECK(cudaFuncSetAttribute(k_witness<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_witness<false><<<(B + 31) / 32, 128, smem, s>>>(c, d_inputs, d_vals, B, d_err);
+    }
 }
 // externally calculated witness (generate_zk_proof_with_witness, rln/src/protocol/proof.rs:705-732): wire i of proof j goes to the
 // node the graph assigns to that wire, so the QAP and the MSMs read it exactly as if k_witness had produced it
