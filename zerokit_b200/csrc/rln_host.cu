@@ -1105,7 +1105,7 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
         }
         if (phase != MSM_KNOWN)  // a partial witness leaves the unknown wires undefined; only full evaluations can fail
             for (u32 j = 0; j < B; j++)
-                if (err[j]) throw RlnError("Protocol error: Error calculating witness: graph evaluation failed");
+                if (err[j]) throw RlnError("Protocol error: Error calculating witness: Failed to evaluate witness calculation graph: operator not implemented for Montgomery");
     }
     for (int i = 0; i < 8; i++) stage_ms[i] = acc[i];
 }
