@@ -11,9 +11,12 @@
 //   5. Horner over the windows, affine normalisation.
 // Algorithmic HBM bytes: 96 per term (32 B scalar + 64 B base).  The kernel is bound by the integer
 // multiply pipe (≈ 250 IMAD per byte), see DESIGN.md §roofline.
+#include <cstdlib>
+
 #include <cub/cub.cuh>
 
 #include "device_api.hpp"
+#include "glv.cuh"
 
 namespace zk {
 
@@ -31,7 +34,20 @@ struct VarMsmWorkspace {
     void* cub_tmp = nullptr;
     size_t cub_tmp_bytes = 0;
     size_t max_buckets = 0;
+    G1Affine* phi = nullptr;                          // GLV mode only: φ(Pᵢ) = (β·xᵢ, yᵢ), allocated on first use
+    size_t phi_cap = 0;
 };
+
+// Experimental (RLN_B200_VARMSM_GLV=1: n ≤ 2^20, =2: every n; default 0, not yet measured): every scalar is split k = k₁ + k₂·λ with
+// |kᵢ| < 2^128 and the MSM runs over the 2n terms [Pᵢ | φ(Pᵢ)].  At small n the addition count stays (2¹⁶: 2¹⁷ × 12 windows of
+// c = 11 against 2¹⁶ × 26 of c = 10) while the Horner doublings — one thread's dependent chain, the floor of every small MSM —
+// and the bucket reductions halve.  At 2²² it would cost 9 windows instead of 8 per 128 bits, hence the size limit.
+static int var_msm_glv_mode() {
+    static const int m = [] { const char* v = getenv("RLN_B200_VARMSM_GLV"); return v && *v ? atoi(v) : 0; }();
+    return m;
+}
+static bool var_msm_use_glv(size_t n) { return var_msm_glv_mode() == 2 || (var_msm_glv_mode() == 1 && n <= ((size_t)1 << 20)); }
+static int glv_windows(int c) { return 129 / c + 1; }   // c·K ≥ 129: the top signed digit and its carry stay below 2^(c−1)
 
 static void msm_params(size_t n, int& c, int& K) {
     int lg = 0;
@@ -54,10 +70,23 @@ VarMsmWorkspace* var_msm_workspace_create(size_t max_n) {
         if (n * K > max_items) max_items = n * K;
         size_t b = (size_t)K << (c - 1);
         if (b > max_b) max_b = b;
+        if (var_msm_glv_mode()) {
+            msm_params(2 * n, c, K);
+            K = glv_windows(c);
+            if (2 * n * K > max_items) max_items = 2 * n * K;
+            b = (size_t)K << (c - 1);
+            if (b > max_b) max_b = b;
+        }
     }
     msm_params(max_n, c, K);
     if (max_n * K > max_items) max_items = max_n * K;
     if (((size_t)K << (c - 1)) > max_b) max_b = (size_t)K << (c - 1);
+    if (var_msm_glv_mode()) {
+        msm_params(2 * max_n, c, K);
+        K = glv_windows(c);
+        if (2 * max_n * K > max_items) max_items = 2 * max_n * K;
+        if (((size_t)K << (c - 1)) > max_b) max_b = (size_t)K << (c - 1);
+    }
     w->max_buckets = max_b;
     ZK_CUDA_CHECK(cudaMalloc(&w->keys_in, 4 * max_items));
     ZK_CUDA_CHECK(cudaMalloc(&w->keys_out, 4 * max_items));
@@ -90,6 +119,7 @@ void var_msm_workspace_destroy(VarMsmWorkspace* w) {
     cudaFree(w->bucket_start); cudaFree(w->bucket_end); cudaFree(w->buckets);
     cudaFree(w->size_key); cudaFree(w->size_key_out); cudaFree(w->order_in); cudaFree(w->order);
     cudaFree(w->slice_cnt); cudaFree(w->slice_off); cudaFree(w->partial); cudaFree(w->seg); cudaFree(w->win); cudaFree(w->cub_tmp);
+    cudaFree(w->phi);
     delete w;
 }
 
@@ -124,6 +154,54 @@ __global__ void __launch_bounds__(256) k_digits(const uint8_t* __restrict__ scal
     }
 }
 
+// GLV form of k_digits: term i + h·n carries |k_h| of scalar i (h = 0, 1); the sign of the half flips every digit
+__global__ void __launch_bounds__(256) k_digits_glv(const uint8_t* __restrict__ scalars, size_t n, int c, int K, u32* __restrict__ keys,
+                                                    u32* __restrict__ vals) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4* q = reinterpret_cast<const uint4*>(scalars + 32 * i);
+    uint4 a = q[0], b = q[1];
+    u32 s[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    u32 m[8];
+#pragma unroll
+    for (int t = 0; t < 8; t++) m[t] = FrCfg::p(t);
+    while (Fr::raw_cmp(s, m) >= 0) Fr::raw_sub(s, s, m);
+    const u32 half = 1u << (c - 1);
+    const size_t terms = 2 * n;
+    for (int h = 0; h < 2; h++) {
+        u32 kh[8];
+        const bool neg = glv::split(s, h, kh);
+        const size_t term = i + (size_t)h * n;
+        u32 carry = 0;
+        for (int k = 0; k < K; k++) {
+            const int bit = k * c, w = bit >> 5, sh = bit & 31;
+            u32 v = 0;
+            if (w < 8) {
+                v = kh[w] >> sh;
+                if (sh + c > 32 && w + 1 < 8) v |= kh[w + 1] << (32 - sh);
+            }
+            int d = (int)(v & ((1u << c) - 1)) + (int)carry;
+            if (d > (int)half) { d -= (1 << c); carry = 1; } else carry = 0;
+            u32 key = (u32)K * half, val = (u32)term;
+            if (d != 0) {
+                key = (u32)k * half + (u32)((d < 0 ? -d : d) - 1);
+                if ((d < 0) != neg) val |= 0x80000000u;
+            }
+            keys[(size_t)k * terms + term] = key;
+            vals[(size_t)k * terms + term] = val;
+        }
+    }
+}
+// φ(P) = (β·x, y); the point at infinity (0, 0) maps to itself
+__global__ void k_phi_bases(const G1Affine* __restrict__ bases, size_t n, G1Affine* __restrict__ phi) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Affine p = {ldg_fp(&bases[i].x), ldg_fp(&bases[i].y)};
+    p.x = p.x * glv::beta();
+    st_fp(&phi[i].x, p.x);
+    st_fp(&phi[i].y, p.y);
+}
+
 __global__ void k_bucket_bounds(const u32* __restrict__ keys, size_t items, u32 n_buckets, u32* __restrict__ start, u32* __restrict__ end) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= items) return;
@@ -153,10 +231,14 @@ __global__ void k_slice_counts(const u32* __restrict__ size_key_sorted, u32 n_bu
 // a warp hold (almost) the same number of points — no lanes idling behind a long one — and no thread ever walks a giant bucket
 // alone (skewed scalars, or the few huge buckets of a short top window).  A single-slice bucket is written straight to its
 // place; slices of split buckets go to `partial` for k_bucket_combine.
+template <bool GLV>
 __global__ void __launch_bounds__(128) k_bucket_sum(const G1Affine* __restrict__ bases, const u32* __restrict__ vals,
                                                     const u32* __restrict__ start, const u32* __restrict__ end, const u32* __restrict__ order,
                                                     const u32* __restrict__ cnt, const u32* __restrict__ off, u32 n_buckets, u32 slice,
-                                                    G1XYZZ* __restrict__ partial, G1XYZZ* __restrict__ buckets) {
+                                                    G1XYZZ* __restrict__ partial, G1XYZZ* __restrict__ buckets,
+                                                    const G1Affine* __restrict__ phi, u32 n) {
+    // GLV: term index t < n is Pₜ, t ≥ n is φ(P_{t−n})
+    auto base_of = [&](u32 t) -> const G1Affine* { return GLV && t >= n ? phi + (t - n) : bases + t; };
     const u32 sl = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 total = off[n_buckets - 1] + cnt[n_buckets - 1];
     if (sl >= total) return;
@@ -171,13 +253,15 @@ __global__ void __launch_bounds__(128) k_bucket_sum(const G1Affine* __restrict__
     const u32 hi = min(end[b], lo + slice);
     G1XYZZ acc = G1XYZZ::infinity();
     u32 v = vals[lo];
-    G1Affine nxt = {ldg_fp(&bases[v & 0x7fffffffu].x), ldg_fp(&bases[v & 0x7fffffffu].y)};
+    const G1Affine* bp = base_of(v & 0x7fffffffu);
+    G1Affine nxt = {ldg_fp(&bp->x), ldg_fp(&bp->y)};
     if (v >> 31) nxt.y = nxt.y.neg();
     for (u32 t = lo; t < hi; t++) {
         G1Affine cur = nxt;
         if (t + 1 < hi) {  // prefetch the next point while the current addition runs
             v = vals[t + 1];
-            nxt = {ldg_fp(&bases[v & 0x7fffffffu].x), ldg_fp(&bases[v & 0x7fffffffu].y)};
+            bp = base_of(v & 0x7fffffffu);
+            nxt = {ldg_fp(&bp->x), ldg_fp(&bp->y)};
             if (v >> 31) nxt.y = nxt.y.neg();
         }
         if (!cur.is_inf()) acc.add_affine(cur);
@@ -269,10 +353,24 @@ void launch_var_msm_g1(VarMsmWorkspace* w, const G1Affine* d_bases, const uint8_
     if (n == 0) { ZK_CUDA_CHECK(cudaMemsetAsync(d_result, 0, 64, s)); return; }
     if (n > w->max_n) throw CudaError(cudaErrorInvalidValue, "var msm: n exceeds workspace", __FILE__, __LINE__);
     int c, K;
-    msm_params(n, c, K);
+    const bool use_glv = var_msm_use_glv(n);
+    const size_t terms = use_glv ? 2 * n : n;
+    msm_params(terms, c, K);
+    if (use_glv) K = glv_windows(c);
     const u32 half = 1u << (c - 1);
-    const size_t items = n * (size_t)K, n_buckets = (size_t)K * half;
-    k_digits<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_scalars, n, c, K, w->keys_in, w->vals_in);
+    const size_t items = terms * (size_t)K, n_buckets = (size_t)K * half;
+    if (use_glv) {
+        if (w->phi_cap < n) {
+            ZK_CUDA_CHECK(cudaStreamSynchronize(s));
+            if (w->phi) ZK_CUDA_CHECK(cudaFree(w->phi));
+            ZK_CUDA_CHECK(cudaMalloc(&w->phi, sizeof(G1Affine) * n));
+            w->phi_cap = n;
+        }
+        k_phi_bases<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_bases, n, w->phi);
+        k_digits_glv<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_scalars, n, c, K, w->keys_in, w->vals_in);
+    } else {
+        k_digits<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_scalars, n, c, K, w->keys_in, w->vals_in);
+    }
     int key_bits = 0;
     while (((size_t)1 << key_bits) < n_buckets + 1) key_bits++;  // keys are in [0, n_buckets]: sort only the significant bits
     size_t tmp = w->cub_tmp_bytes;
@@ -290,8 +388,14 @@ void launch_var_msm_g1(VarMsmWorkspace* w, const G1Affine* d_bases, const uint8_
     ZK_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(w->cub_tmp, tmp, w->slice_cnt, w->slice_off, (int)n_buckets, s));
     const size_t max_slices = items / slice + n_buckets;   // upper bound known on the host; threads beyond the real total exit
     ZK_CUDA_CHECK(cudaMemsetAsync(w->buckets, 0, sizeof(G1XYZZ) * n_buckets, s));   // all-zero XYZZ = infinity: the empty buckets
-    k_bucket_sum<<<(unsigned)((max_slices + 127) / 128), 128, 0, s>>>(d_bases, w->vals_out, w->bucket_start, w->bucket_end, w->order, w->slice_cnt,
-                                                                      w->slice_off, (u32)n_buckets, slice, w->partial, w->buckets);
+    if (use_glv)
+        k_bucket_sum<true><<<(unsigned)((max_slices + 127) / 128), 128, 0, s>>>(d_bases, w->vals_out, w->bucket_start, w->bucket_end, w->order,
+                                                                                w->slice_cnt, w->slice_off, (u32)n_buckets, slice, w->partial,
+                                                                                w->buckets, w->phi, (u32)n);
+    else
+        k_bucket_sum<false><<<(unsigned)((max_slices + 127) / 128), 128, 0, s>>>(d_bases, w->vals_out, w->bucket_start, w->bucket_end, w->order,
+                                                                                 w->slice_cnt, w->slice_off, (u32)n_buckets, slice, w->partial,
+                                                                                 w->buckets, nullptr, (u32)n);
     // a split bucket holds more than `slice` points, so at most items / slice ordered positions can be split
     const size_t n_split_max = items / slice < n_buckets ? items / slice : n_buckets;
     if (n_split_max)
