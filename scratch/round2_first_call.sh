@@ -12,6 +12,10 @@ RLN_B200_WITNESS_STAGED=1 timeout 600 python -m pytest tests/test_gpu_parity.py 
 echo "staged witness tests exit $?" | tee -a ${O}_summary.txt
 RLN_B200_VARMSM_GLV=2 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "msm" > ${O}_pytest_varglv.log 2>&1
 echo "GLV variable-base MSM tests exit $?" | tee -a ${O}_summary.txt
+# 2b. request coalescing behind the single-item calls (16 threads on one handle), off and on
+RLN_B200_COALESCE=0 timeout 300 python scratch/coalesce_gpu_check.py > ${O}_coalesce_off.log 2>&1; echo "coalesce off exit $? $(tail -1 ${O}_coalesce_off.log)" | tee -a ${O}_summary.txt
+RLN_B200_COALESCE=1 timeout 300 python scratch/coalesce_gpu_check.py > ${O}_coalesce_on.log 2>&1; echo "coalesce on exit $? $(tail -1 ${O}_coalesce_on.log)" | tee -a ${O}_summary.txt
+RLN_B200_COALESCE=1 timeout 900 python -m pytest tests -m gpu -q > ${O}_pytest_coalesce.log 2>&1; echo "suite with coalescing exit $?" | tee -a ${O}_summary.txt
 # 3. numbers: default, staged witness, GLV variable-base MSM (the sweep and single-proof latency are in the bench line)
 timeout 400 python bench.py --steps 3 --warmup 3 > ${O}_bench_default.json 2> ${O}_bench_default.err
 RLN_B200_WITNESS_STAGED=1 timeout 400 python bench.py --steps 3 --warmup 3 > ${O}_bench_staged.json 2> ${O}_bench_staged.err

@@ -44,3 +44,16 @@ def test_record_parsers_do_not_crash():
                        timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "fuzz ok" in r.stdout
+
+
+def test_request_coalescer_thread_sanitizer():
+    """zerokit_b200/csrc/coalesce.hpp (concurrent single-item calls on one handle run as batches) under -fsanitize=thread: every
+    request answered once with its own result, batch limit respected, the batch function never re-entered, batches really shared"""
+    out = os.path.join(ROOT, "tests", "host_fuzz", "_build")
+    os.makedirs(out, exist_ok=True)
+    exe = os.path.join(out, "coalesce_test")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-pthread", "-I", os.path.join(ROOT, "zerokit_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "host_fuzz", "coalesce_test.cpp"), "-o", exe])
+    for args in (("16", "40", "8"), ("48", "20", "4096"), ("3", "50", "2"), ("1", "20", "8")):
+        r = subprocess.run([exe, *args], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "coalesce ok" in r.stdout and "ThreadSanitizer" not in r.stderr, r.stdout + r.stderr[-3000:]

@@ -18,6 +18,7 @@
 
 #include "../../include/rln_b200.h"
 #include "device_api.hpp"
+#include "coalesce.hpp"
 #include "host_util.hpp"
 #include "pairing_constants.hpp"
 #include "poseidon_constants.hpp"
@@ -439,6 +440,12 @@ class Rln {
     // witness, qap, g1 accumulate, g1 reduce, g2 accumulate, g2 reduce, assemble, proof values
     float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     std::mutex mu;
+    // concurrent single-item calls on one handle are run as batches (coalesce.hpp; RLN_B200_COALESCE=1)
+    struct ProveReq { const Witness* w; const uint8_t* rs; RlnProof out; std::string err; bool failed = false; bool done = false; };
+    struct PairingReq { const uint8_t* proof128; const uint8_t* pub; uint8_t ok = 0; std::string err; bool failed = false; bool done = false; };
+    Coalescer<ProveReq> co_prove;
+    Coalescer<PairingReq> co_pairing;
+    size_t max_batch() const { return max_batch_; }
 
    private:
     struct TaskSet {
@@ -1560,8 +1567,81 @@ void ffi_rln_witness_input_free(FFI_RLNWitnessInput_t* w) {
 }
 
 // ---- proving / verifying ----------------------------------------------------------------------
+// Experimental, off by default until it has run on a GPU: see coalesce.hpp
+static bool coalesce_enabled() {
+    static const bool on = env_int("RLN_B200_COALESCE", 0) != 0;
+    return on;
+}
+static void prove_alone(Rln& R, Rln::ProveReq* q) {   // caller holds R.mu
+    try {
+        std::vector<Witness> ws(1, *q->w);
+        std::vector<RlnProof> out;
+        R.prove_host(ws, q->rs, out);
+        memset(ws[0].secret, 0, 32);
+        q->out = out[0];
+    } catch (const CudaError& e) { q->failed = true; q->err = describe(e); }
+    catch (const std::exception& e) { q->failed = true; q->err = describe(e); }
+}
+static void run_prove_batch(Rln& R, std::vector<Rln::ProveReq*>& b) {
+    std::lock_guard<std::mutex> lk(R.mu);
+    if (b.size() == 1) { prove_alone(R, b[0]); return; }
+    try {
+        std::vector<Witness> ws;
+        ws.reserve(b.size());
+        std::vector<uint8_t> rs(64 * b.size());
+        for (size_t i = 0; i < b.size(); i++) {
+            ws.push_back(*b[i]->w);
+            if (b[i]->rs) memcpy(&rs[64 * i], b[i]->rs, 64);
+            else { random_fr(&rs[64 * i]); random_fr(&rs[64 * i + 32]); }   // r, s ← rng (proof.rs:743-745)
+        }
+        std::vector<RlnProof> out;
+        R.prove_host(ws, rs.data(), out);
+        for (Witness& w : ws) memset(w.secret, 0, 32);
+        for (size_t i = 0; i < b.size(); i++) b[i]->out = out[i];
+    } catch (...) {   // one request of the batch is at fault: run them one by one so each caller gets its own result or error
+        for (Rln::ProveReq* q : b) prove_alone(R, q);
+    }
+}
+static void run_pairing_batch(Rln& R, std::vector<Rln::PairingReq*>& b) {
+    std::lock_guard<std::mutex> lk(R.mu);
+    try {
+        const size_t np = 32 * R.n_public();
+        std::vector<uint8_t> proofs(128 * b.size()), pubs(np * b.size()), ok(b.size(), 0);
+        for (size_t i = 0; i < b.size(); i++) {
+            memcpy(&proofs[128 * i], b[i]->proof128, 128);
+            memcpy(&pubs[np * i], b[i]->pub, np);
+        }
+        R.verify_batch(proofs.data(), pubs.data(), b.size(), ok.data());
+        for (size_t i = 0; i < b.size(); i++) b[i]->ok = ok[i];
+    } catch (const CudaError& e) { for (auto* q : b) { q->failed = true; q->err = describe(e); } }
+    catch (const std::exception& e) { for (auto* q : b) { q->failed = true; q->err = describe(e); } }
+}
+// the pairing check of one proof; pub holds n_public() canonical field elements
+static bool pairing_ok(Rln& R, const uint8_t* proof128, const uint8_t* pub) {
+    if (coalesce_enabled()) {
+        Rln::PairingReq q;
+        q.proof128 = proof128; q.pub = pub;
+        R.co_pairing.submit(q, R.max_batch(), [&R](std::vector<Rln::PairingReq*>& b) { run_pairing_batch(R, b); });
+        if (q.failed) throw RlnError(q.err);
+        return q.ok == 1;
+    }
+    std::lock_guard<std::mutex> lk(R.mu);
+    uint8_t ok = 0;
+    R.verify_batch(proof128, pub, 1, &ok);
+    return ok == 1;
+}
 static CResult_FFI_RLNProof_t prove_one(FFI_RLN_t* const* rln, FFI_RLNWitnessInput_t* const* witness, const uint8_t* rs) {
     GUARD_BEGIN
+    if (coalesce_enabled()) {
+        Rln& R = *(*rln)->r;
+        Rln::ProveReq q;
+        q.w = &(*witness)->w; q.rs = rs;
+        R.co_prove.submit(q, R.max_batch(), [&R](std::vector<Rln::ProveReq*>& b) { run_prove_batch(R, b); });
+        if (q.failed) throw RlnError(q.err);
+        auto p = std::make_unique<FFI_RLNProof>();
+        p->p = q.out;
+        return CResult_FFI_RLNProof_t{p.release(), no_string()};
+    }
     std::lock_guard<std::mutex> lk((*rln)->r->mu);
     std::vector<Witness> ws(1, (*witness)->w);
     std::vector<RlnProof> out;
@@ -1693,15 +1773,17 @@ int rlnb200_finish_batch(FFI_RLN_t* const* rln, const uint8_t* witnesses, size_t
 // verify_zk_proof (proof.rs:856-894) then root / signal checks (public.rs:725-771)
 static CBoolResult_t verify_common(FFI_RLN_t* const* rln, const RlnProof& p, const uint8_t* x, const Vec_CFr_t* roots, bool use_tree_root) {
     GUARD_BEGIN
-    std::lock_guard<std::mutex> lk((*rln)->r->mu);
+    Rln& R = *(*rln)->r;
     std::vector<uint8_t> pub = public_inputs(p.pv);  // circuit order (proof.rs:863-884)
-    uint8_t ok = 0;
-    if (pub.size() == 32 * (*rln)->r->n_public()) (*rln)->r->verify_batch(p.proof, pub.data(), 1, &ok);
-    else throw RlnError("Protocol error: Error producing proof: malformed verifying key");  // SynthesisError::MalformedVerifyingKey
-    if (ok != 1) throw RlnError("Verification error: Invalid proof provided");
+    if (pub.size() != 32 * R.n_public())
+        throw RlnError("Protocol error: Error producing proof: malformed verifying key");  // SynthesisError::MalformedVerifyingKey
+    if (!pairing_ok(R, p.proof, pub.data())) throw RlnError("Verification error: Invalid proof provided");
     if (use_tree_root) {
         uint8_t root[32];
-        (*rln)->r->root(root);
+        {
+            std::lock_guard<std::mutex> lk(R.mu);
+            R.root(root);
+        }
         if (memcmp(root, p.pv.root, 32)) throw RlnError("Verification error: Expected one of the provided roots");
     } else if (roots && roots->len) {
         bool found = false;
