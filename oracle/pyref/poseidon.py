@@ -257,3 +257,179 @@ def proof_values_from_witness_multi(secret, limit, message_ids, path_elements, p
         ys.append((secret + x * a1) % R * s % R)
         nulls.append(poseidon([a1]) * s % R)
     return dict(root=root, x=x % R, external_nullifier=ext_null % R, ys=ys, nullifiers=nulls, selector_used=[bool(v) for v in selector_used])
+
+
+# ----------------------------------------------------------------------------- the default stateful tree (PmTree)
+class PmTree:
+    """State model of the reference's default `PoseidonTree` = `PmTree` (rln/src/pm_tree_adapter.rs:184-483) over
+    vacp2p_pmtree 2.0.3 (un-vendored; `set` / `set_range` / `delete` restated from the published crate: a write at
+    [start, start+len) raises next_index to max(next_index, start+len), `set_range` beyond the capacity is
+    MerkleTreeIsFull).  Hashing is delegated to FullMerkleTree above (same roots: rln/tests/public.rs:349-427).
+
+    `cached` mirrors `cached_leaves_indices`.  Pinned by the index lists rln/tests/poseidon_tree.rs:79-146 expects
+    (tests/test_oracle_goldens.py::test_pmtree_override_range_quirks)."""
+
+    def __init__(self, depth):
+        self.depth = depth
+        self.tree = FullMerkleTree(depth)
+        self.cached = [0] * (1 << depth)
+
+    def capacity(self):
+        return 1 << self.depth
+
+    def leaves_set(self):
+        return self.tree.next_index
+
+    def root(self):
+        return self.tree.root()
+
+    def get(self, index):
+        return self.tree.get(index)
+
+    def proof(self, index):
+        return self.tree.proof(index)
+
+    def set(self, index, leaf):
+        """pm_tree_adapter.rs:262-270"""
+        if index >= self.capacity():
+            raise IndexError("Index out of bounds")
+        self.tree.set(index, leaf)
+        self.cached[index] = 1
+
+    def set_range(self, start, values):
+        """pm_tree_adapter.rs:272-283"""
+        values = list(values)
+        if start + len(values) > self.capacity():
+            raise IndexError("Merkle Tree is full")
+        self.tree.set_range(start, values)
+        self.tree.next_index = max(self.tree.next_index, start + len(values))
+        for i in range(start, start + len(values)):
+            self.cached[i] = 1
+
+    def update_next(self, leaf):
+        """pm_tree_adapter.rs:358-363"""
+        self.set(self.tree.next_index, leaf)
+
+    def delete(self, index):
+        """pm_tree_adapter.rs:365-374: next_index is left alone"""
+        keep = self.tree.next_index
+        self.tree.set(index, 0)
+        self.tree.next_index = keep
+        self.cached[index] = 0
+
+    def get_empty_leaves_indices(self):
+        """pm_tree_adapter.rs:309-318"""
+        return [i for i in range(self.leaves_set()) if self.cached[i] == 0]
+
+    def override_range(self, start, leaves, indices):
+        """pm_tree_adapter.rs:320-356 + validate_override_range_inputs (override_range_validation.rs:20-65, policy Allow)
+        + remove_indices (:427-445) + remove_indices_and_set_leaves (:447-483)"""
+        leaves = list(leaves)
+        indices = list(indices)
+        if any(i >= self.capacity() for i in indices):
+            raise ValueError("Invalid indices")
+        indices = sorted(set(indices))
+        max_index = None
+        if leaves:
+            max_index = start + len(leaves)
+            if max_index > self.capacity():
+                raise ValueError("set_range got too many leaves")
+        if indices and max_index is not None and (indices[0] > start or indices[0] >= max_index):
+            raise ValueError("Invalid indices")
+        if not leaves and not indices:
+            raise ValueError("Leaf index out of bounds")
+        if len(leaves) == 1 and not indices:
+            return self.set(start, leaves[0])
+        if not leaves and len(indices) == 1:
+            return self.delete(indices[0])
+        if not indices:
+            return self.set_range(start, leaves)
+        if not leaves:  # remove_indices: the whole span is reset
+            lo, hi = indices[0], indices[-1] + 1
+            self.tree.set_range(lo, [0] * (hi - lo))
+            for i in range(lo, hi):
+                self.cached[i] = 0
+            return None
+        # remove_indices_and_set_leaves: set_values covers [min_index, max_index) but is written AT `start`
+        min_index = indices[0]
+        set_values = [0] * (max_index - min_index)
+        for i in range(min_index, start):
+            if i not in indices:
+                set_values[i - min_index] = self.tree.get(i)
+        for i, leaf in enumerate(leaves):
+            set_values[start - min_index + i] = leaf
+        if start + len(set_values) > self.capacity():
+            raise IndexError("Merkle Tree is full")
+        self.tree.set_range(start, set_values)
+        for i in indices:
+            self.cached[i] = 0
+        for i in range(start, max_index - min_index):
+            self.cached[i] = 1
+        return None
+
+
+class DenseTree:
+    """State model of FullMerkleTree / OptimalMerkleTree bookkeeping (utils/src/merkle_tree/full_merkle_tree.rs:197-286,
+    optimal_merkle_tree.rs:174-260): set_range raises the flags of everything it writes, override_range needs indices and
+    writes its set_values at `start`, delete ignores indices that were never used.  Pinned by the index lists of
+    utils/tests/merkle_tree.rs:222-312 (tests/test_oracle_goldens.py::test_dense_tree_override_range)."""
+
+    def __init__(self, depth, optimal=False):
+        self.depth = depth
+        self.optimal = optimal
+        self.tree = FullMerkleTree(depth)
+        self.cached = [0] * (1 << depth)
+
+    capacity = PmTree.capacity
+    leaves_set = PmTree.leaves_set
+    root = PmTree.root
+    get = PmTree.get
+    proof = PmTree.proof
+    get_empty_leaves_indices = PmTree.get_empty_leaves_indices
+
+    def set_range(self, start, values):
+        values = list(values)
+        if start + len(values) > self.capacity():
+            raise ValueError("set_range got too many leaves")
+        self.tree.set_range(start, values)
+        for i in range(start, start + len(values)):
+            self.cached[i] = 1
+
+    def set(self, index, leaf):
+        if index >= self.capacity():
+            raise IndexError("Leaf index out of bounds")
+        self.set_range(index, [leaf])
+
+    def update_next(self, leaf):
+        self.set(self.tree.next_index, leaf)
+
+    def delete(self, index):
+        if index < self.tree.next_index:
+            self.set(index, 0)
+            self.cached[index] = 0
+
+    def override_range(self, start, leaves, indices):
+        leaves, indices = list(leaves), list(indices)
+        if not indices or any(i >= self.capacity() for i in indices):
+            raise ValueError("Invalid indices")
+        indices = sorted(set(indices))
+        min_index = indices[0]
+        if leaves:
+            max_index = start + len(leaves)
+            if max_index > self.capacity():
+                raise ValueError("set_range got too many leaves")
+            if min_index > start or min_index >= max_index:
+                raise ValueError("Invalid indices")
+        else:
+            max_index = start
+        if min_index > max_index or (self.optimal and min_index >= max_index):
+            raise ValueError("Invalid indices")
+        set_values = [0] * (max_index - min_index)
+        for i in range(min_index, start):
+            if i not in indices:
+                set_values[i - min_index] = self.tree.get(i)
+        for i, leaf in enumerate(leaves):
+            set_values[start - min_index + i] = leaf
+        for i in indices:
+            self.cached[i] = 0
+        self.set_range(start, set_values)

@@ -57,3 +57,112 @@ def kat_witness_args(depth, inputs):
     idx = [(5 * i + 1) % 2 for i in range(depth)]
     return (int(inputs["identity_secret"]), int(inputs["user_message_limit"]), int(inputs["message_id"]), pe, idx,
             int(inputs["x"]), int(inputs["external_nullifier"]))
+
+
+def multi_resource(name, depth=20, max_out=4):
+    return open(os.path.join(RES, f"tree_depth_{depth}", "multi_message_id", f"max_out_{max_out}", name), "rb").read()
+
+
+def multi_kat(v):
+    """rln/tests/public.rs:143-213 → (proof coordinates A|B|C as 8 integers, public inputs in circuit order
+    ys…, root, nullifiers…, x, external_nullifier, selector_used… — rln/src/protocol/proof.rs:870-884)"""
+    proof = [int(x) for x in (v["pi_a"] + v["pi_b"][0] + v["pi_b"][1] + v["pi_c"])]
+    pub = [int(y) for y in v["ys"]] + [int(v["root"])] + [int(n) for n in v["nullifiers"]] + [int(v["x"]), int(v["external_nullifier"])]
+    pub += [int(bool(s)) for s in v["selector_used"]]
+    return proof, pub
+
+
+def pmtree_quirk_script(tree, expected, check=None):
+    """rln/tests/poseidon_tree.rs:79-146 step for step on any object with the PoseidonTree methods
+    (set_range, delete, set, override_range, get_empty_leaves_indices); `expected` is the golden
+    `pmtree_override_range` entry.  `check(tree)` runs after every mutation (the GPU test compares the product's root,
+    leaves and leaves_set with the oracle model there)."""
+    depth = expected["depth"]
+    n = 1 << (depth - 1)
+    leaves = list(range(n))
+    chk = check or (lambda t: None)
+    tree.set_range(0, leaves); chk(tree)
+    assert tree.get_empty_leaves_indices() == []
+    idxs = []
+    for i in range(n):
+        idxs.append(i)
+        tree.delete(i); chk(tree)
+        assert tree.get_empty_leaves_indices() == idxs
+    for i in reversed(range(n)):
+        idxs.pop()
+        tree.set(i, leaves[i]); chk(tree)
+        assert tree.get_empty_leaves_indices() == idxs
+    assert tree.get_empty_leaves_indices() == []
+    l2, l4 = [0, 1], [0, 1, 2, 3]
+    tree.override_range(0, l2, [0, 1, 2, 3]); chk(tree)
+    assert tree.get_empty_leaves_indices() == expected["after_override_0_leaves2_idx0123"]
+    tree.override_range(0, [], [0, 1]); chk(tree)
+    assert tree.get_empty_leaves_indices() == expected["after_override_0_none_idx01"]
+    tree.override_range(0, l2, []); chk(tree)
+    assert tree.get_empty_leaves_indices() == expected["after_override_0_leaves2_none"]
+    tree.override_range(0, l4, [0, 1, 2, 3]); chk(tree)
+    assert tree.get_empty_leaves_indices() == expected["after_override_0_leaves4_idx0123"]
+    tree.override_range(4, l4, [0, 1, 2, 3]); chk(tree)
+    assert tree.get_empty_leaves_indices() == expected["after_override_4_leaves4_idx0123"]
+    tree.override_range(2, l4, [0, 1, 2, 3]); chk(tree)
+    assert tree.get_empty_leaves_indices() == expected["after_override_2_leaves4_idx0123"]
+
+
+def dense_tree_quirk_script(tree, expected, check=None):
+    """utils/tests/merkle_tree.rs:222-312 (FullMerkleTree / OptimalMerkleTree flavour), step for step"""
+    depth = expected["depth"]
+    n = 1 << (depth - 1)
+    leaves = list(range(n))
+    chk = check or (lambda t: None)
+    tree.set_range(0, leaves); chk(tree)
+    assert tree.get_empty_leaves_indices() == []
+    idxs = []
+    for i in range(n):
+        idxs.append(i)
+        tree.delete(i); chk(tree)
+        assert tree.get_empty_leaves_indices() == idxs
+    for i in reversed(range(n)):
+        idxs.pop()
+        tree.set(i, leaves[i]); chk(tree)
+        assert tree.get_empty_leaves_indices() == idxs
+    l2, l4 = [0, 1], [0, 1, 2, 3]
+    tree.override_range(0, l2, [0, 1, 2, 3]); chk(tree)
+    tree.override_range(0, l4, [0, 1, 2, 3]); chk(tree)
+    assert tree.get_empty_leaves_indices() == expected["after_override_0_leaves4_idx0123"]
+    tree.override_range(4, l4, [0, 1, 2, 3]); chk(tree)
+    assert tree.get_empty_leaves_indices() == expected["after_override_4_leaves4_idx0123"]
+    tree.override_range(2, l4, [0, 1, 2, 3]); chk(tree)
+    assert tree.get_empty_leaves_indices() == expected["after_override_2_leaves4_idx0123"]
+
+
+class TreeMirror:
+    """Runs every tree operation on the product (an RLN / RLNV3 handle) AND on the oracle's state model, and compares root,
+    leaves_set, empty indices and the first `watch` leaves after each one — the GPU tests drive the reference's tree tests
+    through this."""
+
+    def __init__(self, handle, model, watch=16):
+        self.h, self.m, self.watch = handle, model, watch
+
+    def _same(self):
+        assert self.h.get_root() == self.m.root()
+        assert self.h.leaves_set() == self.m.leaves_set()
+        assert self.h.get_empty_leaves_indices() == self.m.get_empty_leaves_indices()
+        assert [self.h.get_leaf(i) for i in range(self.watch)] == [self.m.get(i) for i in range(self.watch)]
+
+    def set_range(self, start, leaves):
+        self.h.set_leaves_from(start, list(leaves)); self.m.set_range(start, leaves); self._same()
+
+    def set(self, i, leaf):
+        self.h.set_leaf(i, leaf); self.m.set(i, leaf); self._same()
+
+    def delete(self, i):
+        self.h.delete_leaf(i); self.m.delete(i); self._same()
+
+    def update_next(self, leaf):
+        self.h.set_next_leaf(leaf); self.m.update_next(leaf); self._same()
+
+    def override_range(self, start, leaves, indices):
+        self.h.atomic_operation(start, list(leaves), list(indices)); self.m.override_range(start, leaves, indices); self._same()
+
+    def get_empty_leaves_indices(self):
+        return self.h.get_empty_leaves_indices()

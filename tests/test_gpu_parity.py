@@ -6,7 +6,8 @@ import random
 
 import pytest
 
-from common import Q, R, fr_bytes, fr_stream, ints, kat_witness_args, resource, witness_le
+from common import (Q, R, TreeMirror, dense_tree_quirk_script, fr_bytes, fr_stream, ints, kat_witness_args, multi_kat, pmtree_quirk_script,
+                    resource, witness_le)
 
 pytestmark = pytest.mark.gpu
 
@@ -154,31 +155,71 @@ def test_tree_vs_oracle_and_fixture(z, rln10, goldens, oracle):
         rln10.delete_leaf(i)
     empty = oracle.merkle_build(10, b"", 0, 0)
     assert rln10.get_root() == int.from_bytes(empty[:32], "little") and rln10.leaves_set() == 70
-    # atomic_operation: remove + insert
-    rln10.set_tree(10)
-    rln10.set_leaves_from(0, leaves[:10])
-    rln10.atomic_operation(10, leaves[10:20], [0, 3])
-    exp = list(leaves[:20])
-    exp[0] = exp[3] = 0
-    nodes = oracle.merkle_build(10, fr_bytes(exp), 0, 20)
-    assert rln10.get_root() == int.from_bytes(nodes[:32], "little")
-    # get_subtree_root / get_empty_leaves_indices (rln/src/public.rs:877-887; utils/tests/merkle_tree.rs)
+    # atomic_operation: remove + insert, with the reference's (PmTree) placement: set_values = [min_index, start + n) is written AT
+    # start, so leaves 0..9 stay, the survivors of 0..9 and the ten new leaves land at 10..29 (rln/src/pm_tree_adapter.rs:447-483)
     from pyref import poseidon as P
+    rln10.set_tree(10)
+    model = P.PmTree(10)
+    tm = TreeMirror(rln10, model, watch=32)
+    tm.set_range(0, leaves[:10])
+    tm.override_range(10, leaves[10:20], [0, 3])
+    exp = list(leaves[:10]) + [0] + leaves[1:3] + [0] + leaves[4:10] + leaves[10:20]
+    nodes = oracle.merkle_build(10, fr_bytes(exp), 0, 30)
+    assert rln10.get_root() == int.from_bytes(nodes[:32], "little") == model.root() and rln10.leaves_set() == 30
+    assert rln10.get_empty_leaves_indices() == [0, 3] + list(range(20, 30))
+    # get_subtree_root / get_empty_leaves_indices (rln/src/public.rs:877-887; utils/tests/merkle_tree.rs)
     assert rln10.get_subtree_root(0, 5) == rln10.get_root() and rln10.get_subtree_root(10, 5) == exp[5]
     assert rln10.get_subtree_root(9, 4) == P.poseidon([exp[4], exp[5]]) == rln10.get_subtree_root(9, 5)
     assert rln10.get_subtree_root(8, 6) == P.poseidon([P.poseidon([exp[4], exp[5]]), P.poseidon([exp[6], exp[7]])])
-    assert rln10.get_empty_leaves_indices() == [0, 3]
-    rln10.delete_leaf(7)
-    rln10.set_leaf(0, 5)
-    assert rln10.get_empty_leaves_indices() == [3, 7]
+    tm.delete(7)
+    tm.set(0, 5)
+    assert rln10.get_empty_leaves_indices() == [3, 7] + list(range(20, 30))
+    tm.override_range(0, [], [2, 5])          # removals only: the whole span 2..5 is reset (pm_tree_adapter.rs:427-445)
+    assert [rln10.get_leaf(i) for i in range(2, 6)] == [0, 0, 0, 0]
+    tm.update_next(77)
+    assert rln10.leaves_set() == 31 and rln10.get_leaf(30) == 77
     with pytest.raises(z.RLNError, match="Invalid index"):
         rln10.get_subtree_root(11, 0)
     with pytest.raises(z.RLNError, match="Invalid leaf"):
         rln10.get_subtree_root(3, 1024)
     with pytest.raises(z.RLNError, match="set_range got too many leaves"):
         rln10.set_leaves_from(1020, leaves[:10])
-    with pytest.raises(z.RLNError, match="Leaf index out of bounds"):
+    with pytest.raises(z.RLNError, match="Index out of bounds"):
         rln10.set_leaf(1024, 1)
+    with pytest.raises(z.RLNError, match="Invalid key"):
+        rln10.delete_leaf(500)                # pmtree refuses to delete an index that was never used
+    with pytest.raises(z.RLNError, match="Leaf index out of bounds"):
+        rln10.set_leaves_from(0, [])          # override_range with neither leaves nor indices: InvalidLeaf (pm_tree_adapter.rs:337)
+    with pytest.raises(z.RLNError, match="Merkle Tree is full"):
+        rln10.atomic_operation(600, leaves[:10], [0])   # 600 + (610 − 0) > 1024: pmtree's set_range refuses
+
+
+def test_tree_flavour_quirks(z, rln10, goldens):
+    """the reference's own tree tests, step for step, on the product with the oracle's state model beside it:
+    rln/tests/poseidon_tree.rs:79-146 (default PoseidonTree = PmTree, through the V1 handle at depth 4) and
+    utils/tests/merkle_tree.rs:222-312 (FullMerkleTree / OptimalMerkleTree, through RLNV3 stateful handles)"""
+    from pyref import poseidon as P
+    exp = goldens["ref"]["pmtree_override_range"]
+    rln10.set_tree(exp["depth"])
+    pmtree_quirk_script(TreeMirror(rln10, P.PmTree(exp["depth"])), exp)
+    assert [rln10.get_leaf(i) for i in range(12)] == [0, 1, 0, 0, 0, 1, 2, 3, 0, 1, 2, 3] and rln10.leaves_set() == 12
+    rln10.set_tree(10)
+    zkey, graph = resource(10, "rln_final.arkzkey"), resource(10, "graph.bin")
+    expd = goldens["ref"]["dense_tree_override_range"]
+    for kind in ("full", "optimal"):
+        v3 = z.RLNV3.stateful(kind, 10, zkey, graph)
+        tm = TreeMirror(v3, P.DenseTree(10, kind == "optimal"))
+        dense_tree_quirk_script(tm, expd)
+        assert v3.leaves_set() == 12
+        v3.delete_leaf(700); v3.delete_leaf(5000)     # never-used / out-of-range deletes are ignored by the dense trees
+        assert v3.leaves_set() == 12
+        with pytest.raises(z.RLNError, match="Invalid indices"):
+            v3.atomic_operation(0, [1, 2], [])        # EmptyIndicesPolicy::Reject
+        del v3
+    v3 = z.RLNV3.stateful("pm", 10, zkey, graph)
+    pmtree_quirk_script(TreeMirror(v3, P.PmTree(10)), exp)
+    with pytest.raises(z.RLNError, match="^Pmtree error: Tree error: Invalid key"):
+        v3.delete_leaf(700)
 
 
 def test_tree_full_size_2pow20(z, rln20, oracle):
@@ -614,11 +655,14 @@ def test_v3_api(z, goldens, oracle):
     e, b = v3.get_merkle_proof(13)
     oe, ob = oracle.merkle_proof_from_nodes(nodes, 10, 13)
     assert e == oe and b == ob
-    v3.set_next_leaf(99); v3.delete_leaf(3); v3.atomic_operation(51, [7, 8], [0]); v3.seq_atomic_operation([9], [1])
-    exp = leaves + [99, 7, 8, 9]
-    exp[3] = exp[0] = exp[1] = 0
-    nodes = oracle.merkle_build(10, fr_bytes(exp), 0, len(exp))
-    assert v3.get_root() == int.from_bytes(nodes[:32], "little") and v3.leaves_set() == 54
+    from pyref import poseidon as P
+    model = P.DenseTree(10, optimal=True)
+    model.set_range(0, leaves)
+    tm = TreeMirror(v3, model, watch=64)
+    tm.update_next(99); tm.delete(3); tm.override_range(51, [7, 8], [0])
+    v3.seq_atomic_operation([9], [1]); model.override_range(model.leaves_set(), [9], [1]); tm._same()
+    # OptimalMerkleTree::override_range writes [min_index, start + n) AT start: 53 values at 51, then 104 at 104
+    assert v3.leaves_set() == 208 and v3.get_leaf(207) == 9 and v3.get_leaf(0) == leaves[0] and v3.get_leaf(51) == 0
     v3.init_tree_with_leaves(leaves[:4])
     assert v3.get_root() == int.from_bytes(oracle.merkle_build(10, fr_bytes(leaves[:4]), 0, 4)[:32], "little")
     v3.set_metadata(b"abc"); assert v3.get_metadata() == b"abc"; v3.flush()

@@ -3,7 +3,7 @@ import hashlib
 
 import pytest
 
-from common import fr_bytes, ints, kat_witness_args, resource
+from common import fr_bytes, ints, kat_witness_args, multi_kat, multi_resource, resource
 from oracle import cref_binding as C
 
 
@@ -66,3 +66,14 @@ def test_reference_snarkjs_proof(goldens):
     pr = fr_bytes([int(x) for x in (v["pi_a"] + v["pi_b"][0] + v["pi_b"][1] + v["pi_c"])])
     pub = fr_bytes([int(v[n]) for n in ("y", "root", "nullifier", "x", "external_nullifier")])
     assert ctx.verify_batch(pr, pub, 1) == [1]
+
+
+def test_reference_snarkjs_proof_multi(goldens):
+    """rln/tests/public.rs:143-233 (max_out = 4 circuit)"""
+    ctx = C.Ctx(multi_resource("rln_final.arkzkey"), multi_resource("graph.bin"))
+    proof, pub = multi_kat(goldens["ref"]["groth16_verifier_multi"])
+    assert ctx.num_public == 15
+    assert ctx.verify_batch(fr_bytes(proof), fr_bytes(pub), 1) == [1]
+    bad = list(pub)
+    bad[4] += 1
+    assert ctx.verify_batch(fr_bytes(proof), fr_bytes(bad), 1) == [0]

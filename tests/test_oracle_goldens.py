@@ -6,7 +6,7 @@ from pyref import fields as F
 from pyref import groth16 as G
 from pyref import poseidon as P
 
-from common import resource
+from common import dense_tree_quirk_script, multi_kat, multi_resource, pmtree_quirk_script, resource
 
 
 def test_poseidon_constants_all_widths(goldens):
@@ -58,6 +58,37 @@ def test_reference_snarkjs_proof_verifies(goldens):
     assert G.verify(z, proof, pub)
     pub[0] += 1
     assert not G.verify(z, proof, pub)
+
+
+def test_reference_snarkjs_proof_multi_verifies(goldens):
+    """rln/tests/public.rs:143-233 — the hard-coded snarkjs proof of the multi-message-id circuit (max_out = 4)"""
+    z = G.parse_zkey(multi_resource("rln_final.arkzkey"))
+    c, pub = multi_kat(goldens["ref"]["groth16_verifier_multi"])
+    proof = ((c[0], c[1]), ((c[2], c[3]), (c[4], c[5])), (c[6], c[7]))
+    assert len(pub) == 15 and G.verify(z, proof, pub)
+    for i in (0, 4, 9, 11):
+        bad = list(pub)
+        bad[i] = (bad[i] + 1) % F.R
+        assert not G.verify(z, proof, bad)
+
+
+def test_pmtree_override_range_quirks(goldens):
+    """rln/tests/poseidon_tree.rs:79-146 replayed on the PmTree state model: pins override_range's next_index / cached
+    flags behaviour (the expected index lists are the reference's own assertions)"""
+    exp = goldens["ref"]["pmtree_override_range"]
+    t = P.PmTree(exp["depth"])
+    pmtree_quirk_script(t, exp)
+    # what the last two steps leave in the tree: leaves below `start` keep their values, the new ones land shifted
+    assert [t.get(i) for i in range(12)] == [0, 1, 0, 0, 0, 1, 2, 3, 0, 1, 2, 3] and t.leaves_set() == 12
+
+
+def test_dense_tree_override_range(goldens):
+    """utils/tests/merkle_tree.rs:222-312 replayed on the FullMerkleTree / OptimalMerkleTree state model"""
+    exp = goldens["ref"]["dense_tree_override_range"]
+    for optimal in (False, True):
+        t = P.DenseTree(exp["depth"], optimal)
+        dense_tree_quirk_script(t, exp)
+        assert [t.get(i) for i in range(12)] == [0, 1, 0, 0, 0, 1, 2, 3, 0, 1, 2, 3] and t.leaves_set() == 12
 
 
 def test_witness_and_h_hashes(goldens):

@@ -356,7 +356,15 @@ class Rln {
     uint32_t domain() const { return domain_; }
     const GraphHost& graph() const { return gh_; }
 
-    // tree (FullMerkleTree semantics: utils/src/merkle_tree/full_merkle_tree.rs)
+    // tree: one HBM heap tree; the bookkeeping (next_index, "is set" flags, override_range, error kinds) follows the
+    // reference flavour the handle was built as — PmTree is the reference's default PoseidonTree (rln/src/pm_tree_adapter.rs),
+    // FullMerkleTree / OptimalMerkleTree (utils/src/merkle_tree/*.rs) are selectable through the V3 constructors
+    enum TreeKind { TREE_PM = 0, TREE_FULL = 1, TREE_OPTIMAL = 2 };
+    void set_tree_kind(TreeKind k) { tree_kind_ = k; }
+    TreeKind tree_kind() const { return tree_kind_; }
+    RlnError oob_error() const {   // pmtree TreeErrorKind::IndexOutOfBounds vs ZerokitMerkleTreeError::InvalidLeaf
+        return RlnError(tree_kind_ == TREE_PM ? "Merkle tree error: Pmtree error: Tree error: Index out of bounds" : "Merkle tree error: Leaf index out of bounds");
+    }
     void set_tree(size_t depth);
     void set_range_host(size_t start, const uint8_t* leaves, size_t count);
     void set_range_device(size_t start, const uint8_t* d_leaves, size_t count, cudaStream_t s);
@@ -480,6 +488,9 @@ class Rln {
     // tree
     DevMem d_nodes_;
     size_t next_index_ = 0;
+    TreeKind tree_kind_ = TREE_PM;
+    void override_range_dense(size_t start, const uint8_t* leaves, size_t n_leaves, const std::vector<size_t>& indices);
+    void download_leaves(size_t first, size_t count, uint8_t* out);
     // workspace
     size_t cap_ = 0, max_batch_ = 4096;
     DevMem ws_inputs_, ws_rs_, ws_vals_, ws_a_, ws_b_, ws_c_, ws_err_, ws_part1_, ws_part2_, ws_sum1_, ws_sum2_, ws_proofs_, ws_values_, ws_affine_;
@@ -913,23 +924,39 @@ void Rln::set_range_host(size_t start, const uint8_t* leaves, size_t count) {
     ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
 }
 void Rln::set_leaf(size_t index, const uint8_t* leaf) {
-    if (index >= capacity()) throw RlnError("Merkle tree error: Leaf index out of bounds");
+    if (index >= capacity()) throw oob_error();
     set_range_host(index, leaf, 1);
 }
+// delete never moves next_index.  PmTree: vacp2p_pmtree 2.0.3 `delete` refuses a never-used index (key >= next_index →
+// TreeErrorKind::InvalidKey; pm_tree_adapter.rs:365-374 forwards it); FullMerkleTree / OptimalMerkleTree ignore such a call,
+// whatever the index (full_merkle_tree.rs:278-286, optimal_merkle_tree.rs:253-260)
 void Rln::delete_leaf(size_t index) {
-    if (index >= capacity()) throw RlnError("Merkle tree error: Leaf index out of bounds");
+    if (index >= next_index_) {
+        if (tree_kind_ != TREE_PM) return;
+        if (index >= capacity()) throw oob_error();
+        throw RlnError("Merkle tree error: Pmtree error: Tree error: Invalid key");
+    }
     uint8_t zero[32] = {0};
     size_t keep = next_index_;
     set_range_host(index, zero, 1);
     mark_leaves(index, 1, 0);
-    next_index_ = keep;  // delete never moves next_index (pm_tree_adapter.rs:365-374)
+    next_index_ = keep;
 }
 void Rln::set_next(const uint8_t* leaf) {
-    if (next_index_ >= capacity()) throw RlnError("Merkle tree error: Leaf index out of bounds");
+    if (next_index_ >= capacity()) throw oob_error();
     set_range_host(next_index_, leaf, 1);
 }
+void Rln::download_leaves(size_t first, size_t count, uint8_t* out) {
+    if (!count) return;
+    DevMem tmp;
+    tmp.alloc(32 * count);
+    launch_fr_to_bytes(d_nodes_.as<Fr>() + capacity() + first, tmp.as<uint8_t>(), count, stream_);
+    g_launch_count++;
+    ZK_CUDA_CHECK(cudaMemcpyAsync(out, tmp.p, 32 * count, cudaMemcpyDeviceToHost, stream_));
+    ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
 void Rln::get_leaf(size_t index, uint8_t out[32]) {
-    if (index >= capacity()) throw RlnError("Merkle tree error: Leaf index out of bounds");
+    if (index >= capacity()) throw oob_error();
     DevMem tmp;
     tmp.alloc(32);
     launch_fr_to_bytes(d_nodes_.as<Fr>() + capacity() + index, tmp.as<uint8_t>(), 1, stream_);
@@ -947,7 +974,7 @@ void Rln::root(uint8_t out[32]) {
 }
 void Rln::merkle_proofs(const uint64_t* idx, size_t n, uint8_t* elems, uint8_t* bits) {
     for (size_t i = 0; i < n; i++)
-        if (idx[i] >= capacity()) throw RlnError("Merkle tree error: Leaf index out of bounds");
+        if (idx[i] >= capacity()) throw oob_error();
     DevMem d_idx, d_el, d_bits;
     d_idx.upload(idx, 8 * n);
     d_el.alloc(32 * n * tree_depth_);
@@ -960,7 +987,21 @@ void Rln::merkle_proofs(const uint64_t* idx, size_t n, uint8_t* elems, uint8_t* 
 }
 // override_range with PmTree's "empty indices allowed" policy (rln/src/pm_tree_adapter.rs:320-356,
 // utils/src/merkle_tree/override_range_validation.rs:20-65)
+//
+// This reproduces the reference's default tree (PmTree) state for state, including its two quirks, because RLN peers must
+// agree on roots and on `leaves_set()` (which is where the next seq_atomic_operation starts):
+//  * removals only (`remove_indices`, pm_tree_adapter.rs:427-445): the WHOLE span [first index, last index + 1) is reset to the
+//    default leaf, not only the listed indices, and next_index = max(next_index, last index + 1);
+//  * removals + leaves (`remove_indices_and_set_leaves`, :447-483): set_values = [min_index, start + n) with the listed indices
+//    blanked and the leaves at offset start − min_index is written AT `start` (not at min_index): leaves below `start` keep
+//    their hashes in the tree, the new leaves land (start − min_index) slots higher, next_index advances to
+//    start + (start + n − min_index), and the cached "is set" flags are raised for [start, start + n − min_index) only
+//    (rln/tests/poseidon_tree.rs:127-145 pins the resulting get_empty_leaves_indices()).
+// vacp2p_pmtree 2.0.3 `set_range` (un-vendored): writes the values at [start, start + len), next_index = max(next_index, end),
+// MerkleTreeIsFull when end > capacity.
 void Rln::override_range(size_t start, const uint8_t* leaves, size_t n_leaves, std::vector<size_t> indices) {
+    // validate_override_range_inputs (override_range_validation.rs:20-65); PmTree allows an empty index list, the dense trees do not
+    if (tree_kind_ != TREE_PM && indices.empty()) throw RlnError("Merkle tree error: Invalid indices");
     for (size_t i : indices)
         if (i >= capacity()) throw RlnError("Merkle tree error: Invalid indices");
     std::sort(indices.begin(), indices.end());
@@ -971,18 +1012,59 @@ void Rln::override_range(size_t start, const uint8_t* leaves, size_t n_leaves, s
         if (end < start || end > capacity()) throw RlnError("Merkle tree error: set_range got too many leaves");
         if (!indices.empty() && (indices[0] > start || indices[0] >= end)) throw RlnError("Merkle tree error: Invalid indices");
     }
-    if (n_leaves == 0 && indices.empty()) throw RlnError("Merkle tree error: Leaf index out of bounds");
-    size_t keep = next_index_;
-    uint8_t zero[32] = {0};
-    for (size_t i : indices) {  // removals: reset to the default leaf
+    if (tree_kind_ != TREE_PM) { override_range_dense(start, leaves, n_leaves, indices); return; }
+    const size_t n_idx = indices.size();
+    if (n_leaves == 0 && n_idx == 0) throw RlnError("Merkle tree error: Leaf index out of bounds");
+    if (n_leaves == 1 && n_idx == 0) { set_leaf(start, leaves); return; }
+    if (n_leaves == 0 && n_idx == 1) { delete_leaf(indices[0]); return; }
+    if (n_idx == 0) { set_range_host(start, leaves, n_leaves); return; }
+    if (n_leaves == 0) {   // remove_indices: one set_range of default leaves over the span of the indices
+        const size_t first = indices.front(), span = indices.back() + 1 - first;
+        DevMem zeros;
+        zeros.alloc(32 * span);
+        ZK_CUDA_CHECK(cudaMemsetAsync(zeros.p, 0, 32 * span, stream_));
+        set_range_device(first, zeros.as<uint8_t>(), span, stream_);
+        mark_leaves(first, span, 0);
+        ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        return;
+    }
+    // remove_indices_and_set_leaves
+    const size_t min_index = indices.front(), len = end - min_index, head = start - min_index;
+    if (start + len > capacity() || start + len < start) throw RlnError("Merkle tree error: Pmtree error: Tree error: Merkle Tree is full");
+    std::vector<uint8_t> set_values(32 * len, 0);
+    download_leaves(min_index, head, set_values.data());   // leaves [min_index, start) that are not removed keep their value
+    for (size_t i : indices)
+        if (i < start) memset(&set_values[32 * (i - min_index)], 0, 32);
+    memcpy(&set_values[32 * head], leaves, 32 * n_leaves);
+    {
         DevMem tmp;
-        tmp.upload(zero, 32);
-        g_launch_count += launch_merkle_set_range(d_nodes_.as<Fr>(), (u32)tree_depth_, i, tmp.as<uint8_t>(), 1, stream_);
-        mark_leaves(i, 1, 0);
+        tmp.upload(set_values.data(), set_values.size());
+        g_launch_count += launch_merkle_set_range(d_nodes_.as<Fr>(), (u32)tree_depth_, start, tmp.as<uint8_t>(), len, stream_);
         ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
     }
-    next_index_ = keep;
-    if (n_leaves) set_range_host(start, leaves, n_leaves);
+    if (start + len > next_index_) next_index_ = start + len;
+    if (leaf_set_.size() < next_index_) leaf_set_.resize(next_index_, 0);
+    for (size_t i : indices) mark_leaves(i, 1, 0);
+    if (len > start) mark_leaves(start, len - start, 1);   // `for i in start..(max_index - min_index)`
+}
+// FullMerkleTree / OptimalMerkleTree::override_range (full_merkle_tree.rs:226-269, optimal_merkle_tree.rs:197-244): the same
+// set_values written at `start`, but the flags follow set_range: cleared for the indices first, then raised for the whole
+// written range [start, start + len).  Without leaves max_index is `start`: the surviving leaves of [min_index, start) are
+// re-written from `start` on.  min_index > max_index underflows in the reference (a panic); it is InvalidIndices here, as
+// OptimalMerkleTree already answers for min_index >= max_index.
+void Rln::override_range_dense(size_t start, const uint8_t* leaves, size_t n_leaves, const std::vector<size_t>& indices) {
+    const size_t min_index = indices.front(), max_index = n_leaves ? start + n_leaves : start;
+    if (min_index > max_index || (tree_kind_ == TREE_OPTIMAL && min_index >= max_index)) throw RlnError("Merkle tree error: Invalid indices");
+    const size_t len = max_index - min_index, head = start > min_index ? start - min_index : 0;
+    if (start + len > capacity() || start + len < start) throw RlnError("Merkle tree error: set_range got too many leaves");
+    std::vector<uint8_t> set_values(32 * len, 0);
+    download_leaves(min_index, head < len ? head : len, set_values.data());
+    for (size_t i : indices)
+        if (i >= min_index && i < start && i - min_index < len) memset(&set_values[32 * (i - min_index)], 0, 32);
+    if (n_leaves) memcpy(&set_values[32 * head], leaves, 32 * n_leaves);
+    if (leaf_set_.size() < next_index_) leaf_set_.resize(next_index_, 0);
+    for (size_t i : indices) mark_leaves(i, 1, 0);
+    if (len) set_range_host(start, set_values.data(), len);
 }
 
 // ------------------------------------------------------------------------------------------- proving

@@ -5,7 +5,7 @@ from ctypes import POINTER, byref, c_uint8, c_void_p, cast
 
 from . import ffi
 from .ffi import Vec_bool, Vec_uint8
-from .rln import (RLNError, _cfr, _cfr_int, _check_bool, _check_ptr, _ok_bytes, _ok_cfr, _take_cfr, _take_string, _take_vec_cfr,
+from .rln import (RLNError, _cfr, _cfr_int, _check_bool, _check_int, _check_ptr, _ok_bytes, _ok_cfr, _take_cfr, _take_string, _take_vec_cfr,
                   _take_vec_u8, _vec_cfr, _vec_u8)
 
 
@@ -257,6 +257,15 @@ class RLNV3(_Handle):
 
     def get_root(self):
         return _take_cfr(ffi.lib().ffi_rln_v3_get_root(byref(self._h)))
+
+    def get_empty_leaves_indices(self):
+        """RLNV3::get_empty_leaves_indices (rln/src/public.rs:885-887)"""
+        v = ffi.Vec_size()
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_get_empty_leaves_indices(byref(self._h), byref(v), byref(err)), err)
+        out = [v.ptr[i] for i in range(v.len)]
+        ffi.lib().rlnb200_vec_usize_free(v)
+        return out
 
     def get_merkle_proof(self, index):
         res = ffi.lib().ffi_rln_v3_get_merkle_proof(byref(self._h), index)
