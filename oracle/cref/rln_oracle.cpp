@@ -783,6 +783,20 @@ void orc_g1_mul_gen(const uint8_t* ks, size_t n, uint8_t* out, int nthreads) {
         g1_out(g.mul(k).to_affine(), out + 64 * i);
     });
 }
+// Σ kᵢ·sᵢ mod r.  Checker for MSMs too large to redo on the CPU: with bases kᵢ·G the MSM must equal (Σ kᵢ·sᵢ)·G, an identity that
+// does not go through any group arithmetic of the code under test.  ks, ss: n × 32 B little-endian (reduced mod r on load).
+void orc_fr_dot(const uint8_t* ks, const uint8_t* ss, size_t n, uint8_t* out, int nthreads) {
+    const size_t T = nthreads > 1 ? (size_t)nthreads : 1;
+    std::vector<Fr> part(T, Fr::zero());
+    parallel_for(T, (int)T, [&](size_t t) {
+        Fr acc = Fr::zero();
+        for (size_t i = n * t / T, e = n * (t + 1) / T; i < e; i++) acc = acc + Fr::from_le32(ks + 32 * i) * Fr::from_le32(ss + 32 * i);
+        part[t] = acc;
+    });
+    Fr tot = Fr::zero();
+    for (const Fr& v : part) tot = tot + v;
+    tot.to_le32(out);
+}
 // zkey accessors for parity tests: which: 0 a_query 1 b_g1 2 h_query 3 l_query 4 gamma_abc
 size_t orc_ctx_g1_vec(void* p, int which, uint8_t* out) {
     OracleCtx* c = (OracleCtx*)p;

@@ -42,6 +42,7 @@ def lib():
         L.orc_msm_g1.argtypes = [vp, vp, sz, vp, i32]
         L.orc_msm_g2.argtypes = [vp, vp, sz, vp, i32]
         L.orc_g1_mul_gen.argtypes = [vp, sz, vp, i32]
+        L.orc_fr_dot.argtypes = [vp, vp, sz, vp, i32]
         L.orc_ctx_g1_vec.restype = sz
         L.orc_ctx_g1_vec.argtypes = [vp, i32, vp]
         L.orc_ctx_g2_vec.restype = sz
@@ -200,6 +201,13 @@ def msm_g1(points_bytes, scalars_bytes, n, nthreads=1):
 def msm_g2(points_bytes, scalars_bytes, n, nthreads=1):
     out = ctypes.create_string_buffer(128)
     lib().orc_msm_g2(points_bytes, scalars_bytes, n, out, nthreads)
+    return out.raw
+
+
+def fr_dot(ks_bytes, ss_bytes, n, nthreads=1):
+    """Σ kᵢ·sᵢ mod r as 32 LE bytes: with bases kᵢ·G an MSM must equal g1_mul_gen(fr_dot(k, s))"""
+    out = ctypes.create_string_buffer(32)
+    lib().orc_fr_dot(ks_bytes, ss_bytes, n, out, nthreads)
     return out.raw
 
 

@@ -22,6 +22,7 @@ prove→verify round trips.
 """
 import struct
 
+from . import fields as F
 from .fields import (R, Q, INF, OPS1, OPS2, pt_add, pt_mul, pt_neg, msm, on_curve,
                      pairing_product_is_one, TWO_ADICITY, FR_GENERATOR)
 
@@ -536,6 +537,50 @@ def g1_decompress(b):
         raise ValueError("not on curve")
     big = max(y, Q - y)
     return (x, big if flags & 0x80 else Q - big)
+
+
+def _sqrt_fq2(a):
+    """square root in Fq2 = Fq[u]/(u²+1) by the norm method (q ≡ 3 mod 4): a = (x0 + x1·u)² ⇒ x0² = (a0 ± √(a0² + a1²))/2"""
+    a0, a1 = a[0] % Q, a[1] % Q
+    if a1 == 0:
+        y = _sqrt_fq(a0)
+        if y is not None:
+            return (y, 0)
+        y = _sqrt_fq((-a0) % Q)   # −1 = u²
+        return None if y is None else (0, y)
+    alpha = _sqrt_fq((a0 * a0 + a1 * a1) % Q)
+    if alpha is None:
+        return None
+    half = (Q + 1) // 2
+    for sign in (1, -1):
+        x0 = _sqrt_fq((a0 + sign * alpha) * half % Q)
+        if x0 is not None and x0 != 0:
+            x1 = a1 * pow(2 * x0, -1, Q) % Q
+            if F.f2_sqr((x0, x1)) == (a0, a1):
+                return (x0, x1)
+    return None
+
+
+def g2_decompress(b):
+    """ark-serialize 0.5 compressed G2: x.c0 ‖ x.c1 little-endian, flags in the top bits of the LAST byte (of c1); the y that is
+    the lexicographically larger of {y, −y} (c1 compared first, then c0) when bit 7 is set.  No subgroup check here."""
+    flags = b[63] & 0xC0
+    if flags & 0x40:
+        return INF
+    x0 = int.from_bytes(bytes(b[:32]), "little")
+    x1 = int.from_bytes(bytes(b[32:63]) + bytes([b[63] & 0x3F]), "little")
+    x = (x0, x1)
+    y = _sqrt_fq2(F.f2_add(F.f2_mul(F.f2_sqr(x), x), F.OPS2.b))
+    if y is None:
+        raise ValueError("not on curve")
+    ny = F.f2_neg(y)
+    big = y if (y[1], y[0]) > (ny[1], ny[0]) else ny
+    return (x, big if flags & 0x80 else F.f2_neg(big))
+
+
+def proof_from_bytes(b):
+    """Proof::deserialize_compressed (rln/src/protocol/proof.rs:469): A (32) ‖ B (64) ‖ C (32)"""
+    return (g1_decompress(b[:32]), g2_decompress(b[32:96]), g1_decompress(b[96:128]))
 
 
 def proof_to_bytes(proof):

@@ -223,7 +223,7 @@ def test_tree_flavour_quirks(z, rln10, goldens):
 
 
 def test_tree_full_size_2pow20(z, rln20, oracle):
-    """BASELINE config 3: 2^20 seeded leaves, root + 64 membership paths == oracle FullMerkleTree"""
+    """BASELINE config 3: 2^20 seeded leaves, root + 4 096 membership paths (indices from seed 4) == oracle FullMerkleTree"""
     fs = fr_stream(3)
     n = 1 << 20
     import numpy as np
@@ -235,7 +235,7 @@ def test_tree_full_size_2pow20(z, rln20, oracle):
     rln20.set_leaves_from_bytes(0, leaves)
     nodes = oracle.merkle_build(20, leaves, 0, n, oracle.threads())
     assert rln20.get_root() == int.from_bytes(nodes[:32], "little")
-    idx = [0, 1, n - 1, 12345, 777777] + [int(x) for x in rng.integers(0, n, size=59)]
+    idx = [0, 1, n - 1, 12345, 777777] + [int(x) for x in np.random.default_rng(4).integers(0, n, size=4091)]
     el, bits = rln20.get_merkle_proofs(idx)
     for k, i in enumerate(idx):
         e, b = oracle.merkle_proof_from_nodes(nodes, 20, i)
@@ -308,14 +308,18 @@ def test_msm_skewed_scalars(z, oracle):
         assert m.msm(bases, sb, n) == oracle.msm_g1(bases, sb, n, oracle.threads()), name
 
 
-def test_msm_large_linear_split(z, oracle):
-    """2^20 terms: too slow to re-do on one CPU core, so check Σ over the whole == Σ over the two halves (oracle adds the halves)"""
+@pytest.mark.parametrize("log2n", [20, 22, 24])
+def test_msm_large_sizes(z, oracle, log2n):
+    """BASELINE configs[1] at 2^20 / 2^22 (the north-star size) / 2^24: too slow to redo with the oracle's Pippenger, so
+    (1) absolute: the bases are k_i·G, hence MSM(P, s) must equal (Σ k_i·s_i mod r)·G — the dot product and the single scalar
+        multiplication are the oracle's (no group arithmetic of the code under test involved);
+    (2) linear split: Σ over the whole == Σ over the two halves (the oracle adds the halves)."""
     import numpy as np
     import torch
-    n = 1 << 20
+    n = 1 << log2n
     m = z.G1Msm(n)
     dev = torch.device("cuda")
-    rng = np.random.default_rng(5)
+    rng = np.random.default_rng(5 + log2n)
     ks = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
     ks[:, 31] &= 0x1f
     sc = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
@@ -331,10 +335,12 @@ def test_msm_large_linear_split(z, oracle):
     torch.cuda.synchronize()
     o = d_o.cpu().numpy().tobytes()
     assert oracle.msm_g1(o[64:192], fr_bytes([1, 1]), 2) == o[:64]
-    # the device base generator agrees with the oracle's k·G on a sample
-    sample = oracle.g1_mul_gen(ks[:4].tobytes(), 4)
-    m2 = z.G1Msm(4)
-    assert m2.msm(sample, fr_bytes([1, 0, 0, 0]), 4) == sample[:64]
+    dot = oracle.fr_dot(ks.tobytes(), sc.tobytes(), n, oracle.threads())
+    assert oracle.g1_mul_gen(dot, 1) == o[:64]
+    # the device base generator agrees with the oracle's k·G on a sample from both ends of the array
+    for lo in (0, n - 4):
+        want = oracle.g1_mul_gen(ks[lo:lo + 4].tobytes(), 4)
+        assert d_b[64 * lo:64 * (lo + 4)].cpu().numpy().tobytes() == want
 
 
 def test_empty_and_full_capacity(z, rln10, oracle):
@@ -405,12 +411,13 @@ def test_reference_snarkjs_proof_verifies_on_gpu(z, rln20, goldens, oracle):
 def _make_batch(rln, oracle_ctx, depth, n, seed):
     """SURVEY §8d config 4 generator scaled down: member j of a seeded tree, message_id = j mod 100"""
     from pyref import poseidon as P
+    from oracle import cref_binding as C
     fs = fr_stream(seed)
     secrets = [next(fs) for _ in range(n)]
     limit = 100
-    leaves = [P.poseidon([P.poseidon([s]), limit]) for s in secrets]
+    leaves = [C.poseidon([C.poseidon([s]), limit]) for s in secrets]
     rln.set_tree(depth)
-    rln.set_leaves_from(0, leaves)
+    rln.set_leaves_from_bytes(0, fr_bytes(leaves))
     el, bits = rln.get_merkle_proofs(list(range(n)))
     en = P.poseidon([P.hash_to_field_le(b"test-epoch"), P.hash_to_field_le(b"test-rln-identifier")])
     recs, rs, inputs = [], [], []
@@ -454,6 +461,50 @@ def test_batch_proofs_bit_equal_to_oracle(z, oracle, depth, n, rln10, rln20):
     pa, pb = rln.generate_rln_proof(wit), rln.generate_rln_proof(wit)
     assert pa.proof_bytes != pb.proof_bytes
     assert rln.verify_with_roots(pa, pa.values.x, []) and rln.verify_with_roots(pb, pb.values.x, [])
+
+
+def test_production_window_tables_batch_4096(z, oracle):
+    """BASELINE configs[3] exactly as bench.py runs it: the DEFAULT window sizes (G1 c = 13, G2 c = 15,
+    GLV; ≈ 125 GiB of tables, which every other test replaces by c = 8), batch 4 096 at depth 20: the first 64 proofs bit-equal
+    to the oracle's, ALL 4 096 verified by the ORACLE's pairing verifier (not the product's), and by the product's."""
+    import torch
+    free_b, _ = torch.cuda.mem_get_info()
+    if free_b < 150 << 30:
+        pytest.skip("needs ≈ 135 GiB of free HBM for the production tables")
+    saved = {k: os.environ.pop(k, None) for k in ("RLN_B200_WINDOW_BITS", "RLN_B200_WINDOW_BITS_G2")}
+    try:
+        rln = z.RLN.new(20)
+    finally:
+        for k, v in saved.items():
+            if v is not None:
+                os.environ[k] = v
+    info = rln.table_info()
+    assert info["window_bits"] == 13 and info["window_bits_g2"] == 15 and info["glv"], info
+    ctx = oracle.Ctx(resource(20, "rln_final.arkzkey"), resource(20, "graph.bin"))
+    n, n_eq = 4096, 64
+    recs, rs, inputs, root = _make_batch(rln, ctx, 20, n, 123)
+    out = rln.prove_batch(recs, n, rs)
+    th = oracle.threads()
+    want_proofs, want_pub = ctx.prove_batch(inputs[:n_eq * ctx.inputs_size * 32], rs[:64 * n_eq], n_eq, th)
+    from pyref import groth16 as G
+    for j in range(n_eq):
+        v = ints(want_proofs[256 * j:256 * (j + 1)])
+        proof = ((v[0], v[1]), ((v[2], v[3]), (v[4], v[5])), (v[6], v[7]))
+        y, rt, nul, x, en = ints(want_pub[160 * j:160 * (j + 1)])
+        assert out[290 * j:290 * (j + 1)] == G.rln_proof_to_bytes_le(proof, dict(root=rt, external_nullifier=en, x=x, y=y, nullifier=nul)), j
+    # every one of the 4 096 under the ORACLE verifier, fed from the product's final bytes: oracle decompression (pyref, ark-serialize
+    # rules) of each 128-byte proof → affine coordinates → the C++ oracle's pairing check against the record's own public values
+    pts, pubs = [], []
+    for j in range(n):
+        rec = out[290 * j:290 * (j + 1)]
+        a, b, c = G.proof_from_bytes(rec[1:129])
+        pts.append(fr_bytes([a[0], a[1], b[0][0], b[0][1], b[1][0], b[1][1], c[0], c[1]]))
+        rt, en, x, y, nul = ints(rec[130:290])
+        assert rt == root
+        pubs.append(fr_bytes([y, rt, nul, x, en]))
+    assert ctx.verify_batch(b"".join(pts), b"".join(pubs), n, 5, th) == [1] * n
+    assert rln.verify_batch(out, n) == [1] * n
+    del rln
 
 
 def test_partial_proofs(z, rln10, rln20, goldens, oracle):
@@ -681,6 +732,23 @@ def test_multi_message_id_circuit(z, goldens, oracle):
     k = goldens["derived"]["kat_proof_multi_d20"]
     rln = z.RLN.new_multi(20, 4)
     assert rln.max_out() == 4 and rln.tree_depth() == 20
+    # the reference's own known answer for this circuit: rln/tests/public.rs:143-233 (test_groth16_proof_hardcoded, MultiV1 arm)
+    from pyref import groth16 as G
+    v = goldens["ref"]["groth16_verifier_multi"]
+    c, pub = multi_kat(v)
+    kat_pv = dict(root=int(v["root"]), external_nullifier=int(v["external_nullifier"]), x=int(v["x"]), ys=[int(y) for y in v["ys"]],
+                  nullifiers=[int(n) for n in v["nullifiers"]], selector_used=v["selector_used"])
+    kat_rec = G.rln_proof_to_bytes_le(((c[0], c[1]), ((c[2], c[3]), (c[4], c[5])), (c[6], c[7])), kat_pv)
+    kat_proof = z.RLNProof.from_bytes_le(kat_rec)
+    assert kat_proof.values.public_inputs() == pub
+    assert rln.verify_with_roots(kat_proof, int(v["x"]), []) is True
+    assert rln.verify_batch(kat_rec, 1) == [1]
+    with pytest.raises(z.RLNError, match="Signal value does not match"):
+        rln.verify_with_roots(kat_proof, int(v["x"]) + 1, [])
+    forged = dict(kat_pv, nullifiers=[kat_pv["nullifiers"][0] + 1, 0, 0, 0])
+    with pytest.raises(z.RLNError, match="Invalid proof provided"):
+        rln.verify_with_roots(z.RLNProof.from_bytes_le(G.rln_proof_to_bytes_le(((c[0], c[1]), ((c[2], c[3]), (c[4], c[5])), (c[6], c[7])), forged)),
+                              int(v["x"]), [])
     wit = z.RLNWitnessInput.from_bytes_le(bytes.fromhex(k["witness_le_hex"]))
     proof = rln.generate_rln_proof_with_rs(wit, 44, 77)
     assert proof.to_bytes_le().hex() == k["rln_proof_le_hex"]

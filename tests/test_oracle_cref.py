@@ -77,3 +77,17 @@ def test_reference_snarkjs_proof_multi(goldens):
     bad = list(pub)
     bad[4] += 1
     assert ctx.verify_batch(fr_bytes(proof), fr_bytes(bad), 1) == [0]
+
+
+def test_fr_dot_and_mul_gen():
+    """the checker of the large MSM tests: Σ k_i·s_i mod r, threaded == Python integers; (Σ k_i s_i)·G == MSM over k_i·G"""
+    import random
+    from common import R
+    rnd = random.Random(9)
+    n = 300
+    ks, ss = [rnd.randrange(R) for _ in range(n)], [rnd.randrange(R) for _ in range(n)]
+    want = sum(k * s for k, s in zip(ks, ss)) % R
+    for t in (1, 4):
+        assert int.from_bytes(C.fr_dot(fr_bytes(ks), fr_bytes(ss), n, t), "little") == want
+    bases = C.g1_mul_gen(fr_bytes(ks), n, 2)
+    assert C.msm_g1(bases, fr_bytes(ss), n, 2) == C.g1_mul_gen(fr_bytes([want]), 1)

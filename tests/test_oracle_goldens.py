@@ -112,6 +112,19 @@ def test_compressed_encoding_roundtrip(goldens):
     assert G.g1_decompress(G.g1_compress(a)) == a
     assert G.g1_compress(a).hex() == k["proof_bytes_hex"][:64]
     assert F.on_curve(F.OPS1, a)
+    # the decompressor the production-window GPU test feeds the oracle verifier with: golden proofs and random G2 points
+    for key in ("kat_proof_d20", "kat_proof_d10", "kat_proof_d20_r0"):
+        kk = goldens["derived"][key]
+        pa, pb, pc = G.proof_from_bytes(bytes.fromhex(kk["proof_bytes_hex"]))
+        assert [str(v) for v in pa] == kk["A"] and [str(v) for v in pc] == kk["C"]
+        assert [[str(v) for v in pb[0]], [str(v) for v in pb[1]]] == kk["B"]
+    import random
+    rnd = random.Random(3)
+    for _ in range(20):
+        p = F.pt_mul(F.OPS2, F.G2_GEN, rnd.randrange(F.R))
+        for q in (p, F.pt_neg(F.OPS2, p)):
+            assert G.g2_decompress(G.g2_compress(q)) == q
+    assert G.g2_decompress(G.g2_compress(F.INF)) is F.INF
 
 
 def test_seeded_keygen_kats(goldens):
