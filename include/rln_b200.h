@@ -399,6 +399,12 @@ size_t rlnb200_proof_record_len(FFI_RLN_t *const *rln);
  * Returns 0 on success; otherwise a negative value and *err (free with ffi_c_string_free). */
 int rlnb200_prove_batch(FFI_RLN_t *const *rln, const uint8_t *witnesses, size_t n, const uint8_t *rs,
                         uint8_t *proofs_out, RlnString *err);
+/* The same with the wire records resident in HBM (e.g. received from another GPU over NCCL): n witness records in, n
+ * rln_proof_to_bytes_le records out; parsing, validation and formatting run on the device (k_records.cu).  d_rs: n*64 bytes
+ * on the device, or NULL.  This is the entry point a one-process-per-GPU deployment calls between its scatter and its gather
+ * (zerokit_b200/sharding.py; BASELINE.json configs[4]). */
+int rlnb200_prove_records_device(FFI_RLN_t *const *rln, const void *d_witness_records, const void *d_rs, size_t n,
+                                 void *d_proof_records, void *stream, RlnString *err);
 /* Batched verification of n rln_proof_to_bytes_le records against the handle's verifying key only
  * (no root / signal check): ok_out[i] = 1 valid, 0 invalid, 2 malformed. */
 int rlnb200_verify_batch(FFI_RLN_t *const *rln, const uint8_t *proofs, size_t n, uint8_t *ok_out, RlnString *err);
@@ -467,6 +473,31 @@ int rlnb200_set_leaves_from_device(FFI_RLN_t **rln, size_t index, const void *d_
 
 /* Variable-base G1 MSM (rln/src/partial_proof.rs:98-104 `msm`, ark-ec msm_bigint): bases n × 64 bytes
  * (x|y canonical LE, bit 0x40 of byte 63 = infinity), scalars n × 32 bytes; result 64 bytes. */
+/* ---- one batch over every GPU of the box, inside one process (BASELINE.json configs[4]) -------------------------------------
+ * The reference scales by "many callers, one handle" on the host cores (rln/README.md:324-332).  Here one object owns a replica
+ * of the prover on each listed device (devices == NULL: every visible device); a batch call cuts the records into contiguous
+ * shards, one worker thread per device proves its shard from / to the caller's host buffers, and the call returns when the
+ * slowest shard is done.  Tree updates are applied to every replica. */
+typedef struct RlnB200Multi RlnB200Multi_t;
+RlnB200Multi_t *rlnb200_multi_new(size_t tree_depth, const int *devices, size_t n_devices, RlnString *err);
+void rlnb200_multi_free(RlnB200Multi_t *m);
+size_t rlnb200_multi_device_count(const RlnB200Multi_t *m);
+int rlnb200_multi_device(const RlnB200Multi_t *m, size_t i);
+/* borrowed single-device handle of replica i (valid until the next rlnb200_multi_replica call on this thread or
+ * rlnb200_multi_free): tree queries, verification, single proofs */
+FFI_RLN_t *const *rlnb200_multi_replica(RlnB200Multi_t *m, size_t i);
+int rlnb200_multi_set_tree(RlnB200Multi_t *m, size_t tree_depth, RlnString *err);
+int rlnb200_multi_set_leaves_from_bytes(RlnB200Multi_t *m, size_t index, const uint8_t *leaves_le, size_t count, RlnString *err);
+int rlnb200_multi_atomic_operation(RlnB200Multi_t *m, size_t index, const uint8_t *leaves_le, size_t n_leaves,
+                                   const size_t *indices, size_t n_indices, RlnString *err);
+int rlnb200_multi_reserve(RlnB200Multi_t *m, size_t max_batch, RlnString *err);
+/* records as for rlnb200_prove_batch / rlnb200_verify_batch */
+int rlnb200_multi_prove_batch(RlnB200Multi_t *m, const uint8_t *witnesses, size_t n, const uint8_t *rs, uint8_t *proofs_out,
+                              RlnString *err);
+int rlnb200_multi_verify_batch(RlnB200Multi_t *m, const uint8_t *proofs, size_t n, uint8_t *ok_out, RlnString *err);
+/* wall time (ms) each device spent on its shard of the last rlnb200_multi_prove_batch; out has device_count entries */
+void rlnb200_multi_last_shard_ms(const RlnB200Multi_t *m, float *out);
+
 typedef struct RlnB200Msm RlnB200Msm_t;
 RlnB200Msm_t *rlnb200_msm_new(size_t max_n, RlnString *err);
 void rlnb200_msm_free(RlnB200Msm_t *m);

@@ -337,10 +337,12 @@ def test_msm_large_sizes(z, oracle, log2n):
     assert oracle.msm_g1(o[64:192], fr_bytes([1, 1]), 2) == o[:64]
     dot = oracle.fr_dot(ks.tobytes(), sc.tobytes(), n, oracle.threads())
     assert oracle.g1_mul_gen(dot, 1) == o[:64]
-    # the device base generator agrees with the oracle's k·G on a sample from both ends of the array
-    for lo in (0, n - 4):
-        want = oracle.g1_mul_gen(ks[lo:lo + 4].tobytes(), 4)
-        assert d_b[64 * lo:64 * (lo + 4)].cpu().numpy().tobytes() == want
+    # the device base generator agrees with the oracle's k·G on a sample from both ends of the array (d_b holds Montgomery-form
+    # points, so compare through one-term MSMs)
+    for lo in (0, n - 1):
+        m.msm_device(d_b.data_ptr() + 64 * lo, torch.from_numpy(np.frombuffer(fr_bytes([1]), dtype=np.uint8).copy()).to(dev).data_ptr(), 1, d_o.data_ptr())
+        torch.cuda.synchronize()
+        assert d_o[:64].cpu().numpy().tobytes() == oracle.g1_mul_gen(ks[lo].tobytes(), 1)
 
 
 def test_empty_and_full_capacity(z, rln10, oracle):
@@ -804,3 +806,98 @@ def test_witness_errors(z, rln20):
         rln20.generate_rln_proof(w)
     with pytest.raises(z.RLNError, match="invalid data|Expected to read|Unknown message mode"):
         z.RLNProof.from_bytes_le(b"\x00" + b"\xff" * 128 + b"\x00" + b"\x00" * 160)
+
+
+# ------------------------------------------------------------------------------- wire records on the device, several devices
+def test_records_device_path_and_refusals(z, rln10, oracle):
+    """rlnb200_prove_records_device (records parsed / formatted by k_records.cu) == rlnb200_prove_batch == the oracle; every
+    record bytes_le_to_rln_witness / RLNWitnessInput::new_single would refuse (witness.rs:78-113, 470-560) is refused with the
+    reference's wording, wherever it sits in the batch"""
+    import torch
+    ctx = oracle.Ctx(resource(10, "rln_final.arkzkey"), resource(10, "graph.bin"))
+    n = 33
+    recs, rs, inputs, root = _make_batch(rln10, ctx, 10, n, 611)
+    want = rln10.prove_batch(recs, n, rs)
+    dev = torch.device("cuda")
+    d_recs = torch.frombuffer(bytearray(recs), dtype=torch.uint8).to(dev)
+    d_rs = torch.frombuffer(bytearray(rs), dtype=torch.uint8).to(dev)
+    d_out = torch.zeros(n * 290, dtype=torch.uint8, device=dev)
+    rln10.prove_records_device(d_recs.data_ptr(), d_rs.data_ptr(), n, d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert d_out.cpu().numpy().tobytes() == want
+    # fresh randomness (d_rs = NULL): different proofs, all valid
+    d_out2 = torch.zeros_like(d_out)
+    rln10.prove_records_device(d_recs.data_ptr(), 0, n, d_out2.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    fresh = d_out2.cpu().numpy().tobytes()
+    assert fresh != want and rln10.verify_batch(fresh, n) == [1] * n
+    assert [fresh[290 * j + 129:290 * (j + 1)] for j in range(n)] == [want[290 * j + 129:290 * (j + 1)] for j in range(n)]   # same values
+    rec = len(recs) // n
+    d = 10
+
+    def broken(j, off, data):
+        b = bytearray(recs)
+        b[rec * j + off:rec * j + off + len(data)] = data
+        return bytes(b)
+    cases = [
+        (broken(5, 33, b"\0" * 32), "User message limit cannot be zero"),
+        (broken(32, 65, (100).to_bytes(32, "little")), r"Message id \(100\) is not within user_message_limit \(100\)"),
+        (broken(0, 1, R.to_bytes(32, "little")), "Non-canonical field element"),
+        (broken(17, rec - 32, (R + 5).to_bytes(32, "little")), "Non-canonical field element"),
+        (broken(9, 105 + 32 * 3, b"\xff" * 32), "Non-canonical field element"),
+        (broken(2, 0, b"\x02"), "Unknown message mode version byte"),
+        (broken(3, 0, b"\x01"), "record|Expected to read|mode"),
+        (broken(4, 97, (d + 1).to_bytes(8, "little")), "Expected to read|shape of the circuit"),
+        (broken(6, 105 + 32 * d, (d - 1).to_bytes(8, "little")), "Merkle proof length mismatch|Expected to read|shape of the circuit"),
+    ]
+    for bad, pattern in cases:
+        with pytest.raises(z.RLNError, match=pattern):
+            rln10.prove_batch(bad, n, rs)
+    assert rln10.prove_batch(recs, n, rs) == want   # the handle is unharmed by refused batches
+
+
+def test_multi_device_in_process(z, oracle):
+    """rlnb200_multi_*: one process, a prover replica per GPU, contiguous shards; output == the single-device output == the oracle.
+    Also the per-device initialisation of the constant tables: a handle that lives on the LAST visible device hashes,
+    proves and verifies like one on device 0.  Runs with whatever the box has (one device: a single-replica multi object)."""
+    import torch
+    ndev = torch.cuda.device_count()
+    ctx = oracle.Ctx(resource(20, "rln_final.arkzkey"), resource(20, "graph.bin"))
+    multi = z.RLNMulti(20, list(range(ndev)))
+    assert multi.device_count() == ndev and multi.devices() == list(range(ndev))
+    n = 8 * ndev + 3
+    r0 = multi.replica(0)
+    recs, rs, inputs, root = _make_batch(r0, ctx, 20, n, 733)
+    # the same tree on every replica
+    leaves = b"".join(r0.get_leaf(i).to_bytes(32, "little") for i in range(n))
+    multi.set_leaves_from_bytes(0, leaves)
+    for i in range(ndev):
+        assert multi.replica(i).get_root() == root
+    out = multi.prove_batch(recs, n, rs)
+    assert out == r0.prove_batch(recs, n, rs)
+    want_proofs, want_pub = ctx.prove_batch(inputs, rs, n, oracle.threads())
+    from pyref import groth16 as G
+    for j in range(n):
+        v = ints(want_proofs[256 * j:256 * (j + 1)])
+        y, rt, nul, x, en = ints(want_pub[160 * j:160 * (j + 1)])
+        assert out[290 * j:290 * (j + 1)] == G.rln_proof_to_bytes_le(((v[0], v[1]), ((v[2], v[3]), (v[4], v[5])), (v[6], v[7])),
+                                                                     dict(root=rt, external_nullifier=en, x=x, y=y, nullifier=nul)), j
+    assert multi.verify_batch(out, n) == [1] * n
+    bad = bytearray(out)
+    bad[290 * (n - 1) + 200] ^= 1
+    assert multi.verify_batch(bytes(bad), n) == [1] * (n - 1) + [0]
+    assert len(multi.last_shard_ms()) == ndev
+    # a refused record in the LAST shard is reported with its device
+    broke = bytearray(recs)
+    broke[len(recs) // n * (n - 1) + 33:len(recs) // n * (n - 1) + 65] = b"\0" * 32
+    with pytest.raises(z.RLNError, match=rf"device {ndev - 1}: .*User message limit cannot be zero"):
+        multi.prove_batch(bytes(broke), n, rs)
+    # the last device on its own: single-proof API, Poseidon, pairing — from a host thread whose current device is 0
+    last = multi.replica(ndev - 1)
+    wit = z.RLNWitnessInput.from_bytes_le(recs[:len(recs) // n])
+    p = last.generate_rln_proof_with_rs(wit, int.from_bytes(rs[:32], "little"), int.from_bytes(rs[32:64], "little"))
+    assert p.to_bytes_le() == out[:290]
+    assert last.verify_with_roots(p, p.values.x, [root]) is True
+    multi.atomic_operation(n, [5, 6], [0])
+    assert len({multi.replica(i).get_root() for i in range(ndev)}) == 1 and multi.replica(ndev - 1).leaves_set() == r0.leaves_set()
+    del multi

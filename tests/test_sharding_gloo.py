@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from zerokit_b200.sharding import gather_records, scatter_records, shard_bounds
+from zerokit_b200.sharding import gather_records, prove_sharded, scatter_records, shard_bounds
 
 
 def test_shard_bounds_cover_everything():
@@ -36,10 +36,33 @@ def _worker(rank, world, port, total, q):
     out = mine.view(hi - lo, rec_in)[:, :rec_out].clone()
     out[:, 0] ^= torch.arange(lo, hi, dtype=torch.int64).to(torch.uint8)
     res = gather_records(out.reshape(-1), rec_out, total)
+    ok = True
     if rank == 0:
         want = full.view(total, rec_in)[:, :rec_out].clone()
         want[:, 0] ^= torch.arange(0, total, dtype=torch.int64).to(torch.uint8)
-        q.put(bool(torch.equal(res.view(total, rec_out), want)))
+        ok = bool(torch.equal(res.view(total, rec_out), want))
+    # the whole step as bench.py / a deployment runs it: host records on rank 0 → scatter → prove → gather → host records on
+    # rank 0, with a stand-in prover that depends on the record AND on its (r, s) pair; uneven and even totals
+    for tot in (total, 2 * world * 3):
+        recs = rs = None
+        if rank == 0:
+            g = torch.Generator().manual_seed(tot)
+            recs = torch.randint(0, 256, (tot * rec_in,), dtype=torch.uint8, generator=g)
+            rs = torch.randint(0, 256, (tot * 64,), dtype=torch.uint8, generator=g)
+
+        def fake_prover(d_records, d_rs, n):
+            o = d_records.view(n, rec_in)[:, :rec_out].clone()
+            o[:, 1] ^= d_rs.view(n, 64)[:, 5]
+            return o.reshape(-1)
+        got = prove_sharded(fake_prover, recs, rs, tot, rec_in, rec_out, torch.device("cpu"))
+        if rank == 0:
+            want = recs.view(tot, rec_in)[:, :rec_out].clone()
+            want[:, 1] ^= rs.view(tot, 64)[:, 5]
+            ok = ok and bool(torch.equal(got.view(tot, rec_out), want))
+        else:
+            ok = ok and got is None
+    if rank == 0:
+        q.put(ok)
     dist.destroy_process_group()
 
 

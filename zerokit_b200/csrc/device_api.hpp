@@ -54,6 +54,14 @@ void launch_proof_values(const uint8_t* d_inputs, InputSlots sl, size_t n, uint8
 // generic small helpers used by the FFI utilities (single-thread kernels)
 void launch_poseidon_n(const uint8_t* d_in_bytes, int n_inputs, uint8_t* d_out_bytes, cudaStream_t s);
 
+// ---- k_records.cu --------------------------------------------------------------------------
+// wire records on the device: rln_witness_to_bytes_le records → input slots (+ a "would be refused" flag per record),
+// (compressed proof, proof values) → rln_proof_to_bytes_le records
+struct RecordLayout { InputSlots sl; u32 rec_len, proof_rec_len; };
+void launch_witness_records(const uint8_t* d_records, size_t n, const RecordLayout& L, uint8_t* d_slots, u32* d_bad, cudaStream_t s);
+void launch_proof_records(const uint8_t* d_proofs, const uint8_t* d_values, const uint8_t* d_slots, size_t n, const RecordLayout& L, uint8_t* d_out,
+                          cudaStream_t s);
+
 // ---- k_prover.cu ---------------------------------------------------------------------------
 struct CircuitDev {
     // witness graph

@@ -14,7 +14,9 @@
 #include <memory>
 #include <mutex>
 #include <random>
+#include <chrono>
 #include <sstream>
+#include <thread>
 
 #include "../../include/rln_b200.h"
 #include "device_api.hpp"
@@ -61,29 +63,61 @@ struct RlnError : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
 
-static std::once_flag g_init_flag;
+// The __constant__ / __device__ tables (Poseidon round constants, pairing constants) exist once per device: a process that
+// drives several GPUs (rlnb200_set_device, the multi-device prover) uploads them to each device the first time that device is
+// used.  The host copies are computed once.
+static std::mutex g_init_mu;
 static std::string g_init_error;
-static void global_init() {
-    std::call_once(g_init_flag, [] {
+static bool g_have_device = false, g_probed = false;
+static std::unique_ptr<PoseidonTables> g_host_pt;
+static std::unique_ptr<PairingTables> g_host_pair;
+static std::vector<char> g_device_ready;
+static int global_init() {   // returns the current device, initialised
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    if (!g_probed) {
+        g_probed = true;
         int n = 0;
         cudaError_t e = cudaGetDeviceCount(&n);
         if (e != cudaSuccess || n == 0) {
             g_init_error = std::string("no usable CUDA device (librln_b200 has no CPU path): ") + cudaGetErrorString(e);
-            return;
+        } else {
+            g_have_device = true;
+            g_device_ready.assign((size_t)n, 0);
+            g_host_pt = std::make_unique<PoseidonTables>();
+            poseidon_fill_tables(*g_host_pt);
+            g_host_pair = std::make_unique<PairingTables>();
+            pairing_tables_init(*g_host_pair);
         }
+    }
+    if (!g_have_device) throw RlnError(g_init_error);
+    int dev = 0;
+    ZK_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || (size_t)dev >= g_device_ready.size()) throw RlnError("CUDA initialisation failed: current device out of range");
+    if (!g_device_ready[dev]) {
         try {
-            auto pt = std::make_unique<PoseidonTables>();
-            poseidon_fill_tables(*pt);
-            poseidon_upload_tables(*pt);
-            PairingTables pr;
-            pairing_tables_init(pr);
-            pairing_upload_tables(pr);
+            poseidon_upload_tables(*g_host_pt);
+            pairing_upload_tables(*g_host_pair);
         } catch (const CudaError& ce) {
-            g_init_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(ce.code);
+            throw RlnError(std::string("CUDA initialisation failed: ") + cudaGetErrorString(ce.code));
         }
-    });
-    if (!g_init_error.empty()) throw RlnError(g_init_error);
+        g_device_ready[dev] = 1;
+    }
+    return dev;
 }
+// cudaSetDevice is per host thread: every entry point that touches a handle's streams / buffers first makes the handle's
+// device current on the calling thread, and puts the caller's device back afterwards
+struct DeviceGuard {
+    int want, prev = -1;
+    explicit DeviceGuard(int device) : want(device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != want) ZK_CUDA_CHECK(cudaSetDevice(want));
+    }
+    ~DeviceGuard() {
+        if (prev >= 0 && prev != want) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
@@ -345,6 +379,7 @@ class Rln {
     Rln(size_t tree_depth, const uint8_t* zkey, size_t zlen, const uint8_t* graph, size_t glen);
     ~Rln();
 
+    int device() const { return device_; }
     size_t depth() const { return depth_; }
     size_t tree_depth() const { return tree_depth_; }
     size_t max_out() const { return max_out_; }
@@ -384,6 +419,21 @@ class Rln {
                       cudaStream_t s, int phase = MSM_FULL, const uint8_t* d_partial = nullptr, uint8_t* d_partial_affine = nullptr,
                       uint8_t* d_partial_comp = nullptr);
     void prove_host(const std::vector<Witness>& ws, const uint8_t* rs, std::vector<RlnProof>& out, const PartialProofHost* partials = nullptr);
+    // the batch path on wire records: n rln_witness_to_bytes_le records in, n rln_proof_to_bytes_le records
+    // out, both resident in HBM (k_records.cu parses / formats them on the device); d_rs may be null (fresh r, s per proof)
+    void prove_records_device(const uint8_t* d_records, const uint8_t* d_rs, size_t n, uint8_t* d_proof_records, cudaStream_t s);
+    // the same from / to host memory: one upload, the device path, one download per super-chunk
+    void prove_records_host(const uint8_t* records, const uint8_t* rs, size_t n, uint8_t* proof_records);
+    // record lengths of rln_witness_to_bytes_le / rln_proof_to_bytes_le for this circuit (witness.rs:369-415, proof.rs:192-236,413-428)
+    size_t witness_record_len() const {
+        const size_t d = depth_, k = max_out_;
+        return multi_ ? 1 + 64 + (8 + 32 * d) + (8 + d) + 64 + (8 + 32 * k) + (8 + k) : 1 + 32 * (5 + d) + 16 + d;
+    }
+    size_t proof_record_len() const {
+        const size_t k = max_out_;
+        return multi_ ? 1 + 128 + 1 + 96 + (8 + 32 * k) * 2 + (8 + k) : 290;
+    }
+    RecordLayout record_layout() const { return RecordLayout{slots_, (u32)witness_record_len(), (u32)proof_record_len()}; }
     // two-phase proving (rln/src/protocol/proof.rs:783-849): the unknown inputs of `ws` (message_id, x, external_nullifier) are ignored
     void partial_host(const std::vector<Witness>& ws, std::vector<PartialProofHost>& out);
     const std::vector<uint8_t>& partial_mask() const { return mask_; }  // one byte per wire 1..n_wires-1 (1 = known)
@@ -467,6 +517,7 @@ class Rln {
     void build_tables();
     void check_graph_shape();
 
+    int device_ = 0;         // the CUDA device that owns every buffer, stream and event of this handle
     ZkeyHost zk_;
     GraphHost gh_;
     size_t depth_ = 0;       // circuit tree depth (len of pathElements)
@@ -496,11 +547,12 @@ class Rln {
     DevMem ws_inputs_, ws_rs_, ws_vals_, ws_a_, ws_b_, ws_c_, ws_err_, ws_part1_, ws_part2_, ws_sum1_, ws_sum2_, ws_proofs_, ws_values_, ws_affine_;
     std::map<u64, std::unique_ptr<TaskSet>> tasks_;
     std::vector<uint8_t> wire_known_, mask_;
-    DevMem ws_partial_, ws_partial_comp_;
+    DevMem ws_partial_, ws_partial_comp_, ws_bad_, ws_recs_in_, ws_recs_out_, ws_rs_all_;
     cudaStream_t stream_ = nullptr, side_ = nullptr, qap_stream_ = nullptr;
     cudaEvent_t fork_ = nullptr, join_ = nullptr, qap_done_ = nullptr, qev_[2] = {nullptr, nullptr};
-    cudaEvent_t ev_[5];
-    cudaEvent_t mev_[6];
+    cudaEvent_t ev_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t mev_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void destroy_handles();
 };
 
 static void upload_points_g1(const std::vector<uint8_t>& raw, const std::vector<uint32_t>& pick, DevMem& out) {
@@ -541,7 +593,7 @@ static G2Affine fetch_g2(const std::vector<uint8_t>& raw128) {
 }
 
 Rln::Rln(size_t tree_depth, const uint8_t* zkey, size_t zlen, const uint8_t* graph, size_t glen) {
-    global_init();
+    device_ = global_init();
     try {
         parse_zkey(zkey, zlen, zk_);
     } catch (const std::exception& e) {
@@ -554,38 +606,47 @@ Rln::Rln(size_t tree_depth, const uint8_t* zkey, size_t zlen, const uint8_t* gra
     }
     check_graph_shape();
     compute_known_mask();
-    max_batch_ = (size_t)env_int("RLN_B200_MAX_BATCH", 4096);
-    ZK_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-    ZK_CUDA_CHECK(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
-    {   // the QAP (HBM-bound) runs beside the first MSM tasks (multiplier-bound); high priority so its CTAs are placed first
-        int lo = 0, hi = 0;
-        ZK_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        ZK_CUDA_CHECK(cudaStreamCreateWithPriority(&qap_stream_, cudaStreamNonBlocking, hi));
-        // measured: the 42 dependent QAP launches starve behind the long-running accumulate CTAs (QAP 25 → 216 ms on its
-        // stream, step 484 → 490 ms), so the overlap is opt-in only
-        overlap_qap_ = env_int("RLN_B200_OVERLAP_QAP", 0) != 0;
-        ZK_CUDA_CHECK(cudaEventCreateWithFlags(&qap_done_, cudaEventDisableTiming));
-        for (auto& e : qev_) ZK_CUDA_CHECK(cudaEventCreate(&e));
+    {
+        const int mb = env_int("RLN_B200_MAX_BATCH", 4096);
+        if (mb < 1 || mb > (1 << 20)) throw RlnError("Configuration error: RLN_B200_MAX_BATCH must be in [1, 1048576]");
+        max_batch_ = (size_t)mb;
     }
-    ZK_CUDA_CHECK(cudaEventCreateWithFlags(&fork_, cudaEventDisableTiming));
-    ZK_CUDA_CHECK(cudaEventCreateWithFlags(&join_, cudaEventDisableTiming));
-    for (auto& e : ev_) ZK_CUDA_CHECK(cudaEventCreate(&e));
-    for (auto& e : mev_) ZK_CUDA_CHECK(cudaEventCreate(&e));
-    build_circuit();
-    build_tables();
-    set_tree(tree_depth);
+    try {
+        ZK_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+        ZK_CUDA_CHECK(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
+        {   // a high-priority stream for the optional QAP / MSM overlap (measured slower, DESIGN §7b: opt-in)
+            int lo = 0, hi = 0;
+            ZK_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            ZK_CUDA_CHECK(cudaStreamCreateWithPriority(&qap_stream_, cudaStreamNonBlocking, hi));
+            overlap_qap_ = env_int("RLN_B200_OVERLAP_QAP", 0) != 0;
+            ZK_CUDA_CHECK(cudaEventCreateWithFlags(&qap_done_, cudaEventDisableTiming));
+            for (auto& e : qev_) ZK_CUDA_CHECK(cudaEventCreate(&e));
+        }
+        ZK_CUDA_CHECK(cudaEventCreateWithFlags(&fork_, cudaEventDisableTiming));
+        ZK_CUDA_CHECK(cudaEventCreateWithFlags(&join_, cudaEventDisableTiming));
+        for (auto& e : ev_) ZK_CUDA_CHECK(cudaEventCreate(&e));
+        for (auto& e : mev_) ZK_CUDA_CHECK(cudaEventCreate(&e));
+        build_circuit();
+        build_tables();
+        set_tree(tree_depth);
+    } catch (...) {   // a throwing constructor never runs the destructor: release the streams / events created so far
+        destroy_handles();
+        throw;
+    }
+}
+void Rln::destroy_handles() {
+    for (auto& e : ev_) if (e) { cudaEventDestroy(e); e = nullptr; }
+    for (auto& e : mev_) if (e) { cudaEventDestroy(e); e = nullptr; }
+    for (auto& e : qev_) if (e) { cudaEventDestroy(e); e = nullptr; }
+    for (cudaEvent_t* e : {&qap_done_, &fork_, &join_}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
+    for (cudaStream_t* st : {&stream_, &side_, &qap_stream_}) if (*st) { cudaStreamDestroy(*st); *st = nullptr; }
 }
 Rln::~Rln() {
+    int prev = -1;
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != device_) cudaSetDevice(device_);
+    struct Back { int p, d; ~Back() { if (p >= 0 && p != d) cudaSetDevice(p); } } back{prev, device_};
     cudaDeviceSynchronize();
-    for (auto& e : ev_) cudaEventDestroy(e);
-    for (auto& e : mev_) cudaEventDestroy(e);
-    if (stream_) cudaStreamDestroy(stream_);
-    if (side_) cudaStreamDestroy(side_);
-    if (qap_stream_) cudaStreamDestroy(qap_stream_);
-    if (qap_done_) cudaEventDestroy(qap_done_);
-    for (auto& e : qev_) if (e) cudaEventDestroy(e);
-    if (fork_) cudaEventDestroy(fork_);
-    if (join_) cudaEventDestroy(join_);
+    destroy_handles();
 }
 
 // Which wires a partial witness determines (graph.rs:274-312 evaluate_partial): a node is known iff all of its operands
@@ -1199,6 +1260,24 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
     for (int i = 0; i < 8; i++) stage_ms[i] = acc[i];
 }
 
+// zeroes the host staging vector and the device input buffer when the scope ends, normally or by exception (the reference
+// zeroises IdSecret on drop on all paths: rln/src/utils.rs:443-527, rln/src/circuit/iden3calc.rs:44-57)
+struct SecretScrub {
+    std::vector<uint8_t>& host;
+    DevMem& dev;
+    cudaStream_t s;
+    ~SecretScrub() {
+        if (!host.empty()) {
+            volatile uint8_t* p = host.data();
+            for (size_t i = 0; i < host.size(); i++) p[i] = 0;
+        }
+        if (dev.p) {
+            cudaMemsetAsync(dev.p, 0, dev.bytes, s);
+            cudaStreamSynchronize(s);
+        }
+    }
+};
+
 void Rln::witness_slots(const Witness& w, uint8_t* slots) const {  // iden3calc.rs:106-181, witness.rs:832-881
     memset(slots, 0, (size_t)gh_.n_slots * 32);
     slots[0] = 1;
@@ -1241,6 +1320,7 @@ void Rln::prove_host(const std::vector<Witness>& wsv, const uint8_t* rs, std::ve
     reserve(chunk);
     const size_t vs = values_stride(), k = max_out_;
     std::vector<uint8_t> slots(chunk * (size_t)gh_.n_slots * 32), rsb(chunk * 64), proofs(chunk * 128), values(chunk * vs);
+    SecretScrub scrub{slots, ws_inputs_, stream_};   // identity secrets leave the staging buffers on every path out of here
     for (size_t off = 0; off < n; off += chunk) {
         const size_t B = n - off < chunk ? n - off : chunk;
         for (size_t j = 0; j < B; j++) witness_slots(wsv[off + j], slots.data() + j * (size_t)gh_.n_slots * 32);
@@ -1278,6 +1358,106 @@ void Rln::prove_host(const std::vector<Witness>& wsv, const uint8_t* rs, std::ve
     memset(slots.data(), 0, slots.size());
 }
 
+
+// bulk randomness for r, s (proof.rs:743-745): uniform in [0, r) by rejection on 254 bits, from the OS generator
+static void random_fr_bulk(uint8_t* out, size_t count) {
+    std::vector<uint8_t> pool;
+    size_t used = 0;
+    for (size_t i = 0; i < count;) {
+        if (used + 32 > pool.size()) {
+            pool.resize(32 * (count - i) + 1024);
+            used = 0;
+            std::ifstream ur("/dev/urandom", std::ios::binary);
+            if (!ur.read((char*)pool.data(), (std::streamsize)pool.size())) {   // no OS generator: fall back to std::random_device
+                for (; i < count; i++) random_fr(out + 32 * i);
+                return;
+            }
+        }
+        memcpy(out + 32 * i, pool.data() + used, 32);
+        used += 32;
+        out[32 * i + 31] &= 0x3f;
+        if (fr_is_canonical(out + 32 * i)) i++;
+    }
+    if (!pool.empty()) memset(pool.data(), 0, pool.size());
+}
+
+void Rln::prove_records_device(const uint8_t* d_records, const uint8_t* d_rs, size_t n, uint8_t* d_out, cudaStream_t s) {
+    if (!n) return;
+    const size_t chunk = n < max_batch_ ? n : max_batch_;
+    reserve(chunk);
+    const RecordLayout L = record_layout();
+    ws_bad_.ensure(4 * cap_);
+    std::vector<u32> bad(cap_);
+    std::vector<uint8_t> rsb;
+    struct Scrub {   // secrets never outlive the call, whichever way it ends (reference: IdSecret zeroises on drop)
+        Rln& r; cudaStream_t s;
+        ~Scrub() { cudaMemsetAsync(r.ws_inputs_.p, 0, r.ws_inputs_.bytes, s); cudaStreamSynchronize(s); }
+    } scrub{*this, s};
+    for (size_t off = 0; off < n; off += cap_) {
+        const size_t B = n - off < cap_ ? n - off : cap_;
+        launch_witness_records(d_records + off * (size_t)L.rec_len, B, L, ws_inputs_.as<uint8_t>(), ws_bad_.as<u32>(), s);
+        g_launch_count++;
+        ZK_CUDA_CHECK(cudaMemcpyAsync(bad.data(), ws_bad_.p, 4 * B, cudaMemcpyDeviceToHost, s));
+        const uint8_t* rs_dev = d_rs ? d_rs + 64 * off : nullptr;
+        if (!d_rs) {
+            rsb.resize(64 * B);
+            random_fr_bulk(rsb.data(), 2 * B);
+            ZK_CUDA_CHECK(cudaMemcpyAsync(ws_rs_.p, rsb.data(), 64 * B, cudaMemcpyHostToDevice, s));
+            rs_dev = ws_rs_.as<uint8_t>();
+        }
+        ZK_CUDA_CHECK(cudaStreamSynchronize(s));
+        for (size_t j = 0; j < B; j++) {
+            if (!bad[j]) continue;
+            // the reference's own wording: re-parse the refused record with the host parser (same rules, same messages)
+            std::vector<uint8_t> rec(L.rec_len);
+            ZK_CUDA_CHECK(cudaMemcpy(rec.data(), d_records + (off + j) * (size_t)L.rec_len, L.rec_len, cudaMemcpyDeviceToHost));
+            Witness w;
+            std::string msg = "witness record " + std::to_string(off + j) + ": ";
+            try {
+                const size_t used = witness_from_bytes(rec.data(), rec.size(), w);
+                memset(rec.data(), 0, rec.size());
+                if (w.multi != multi_)
+                    throw RlnError(std::string("Protocol error: Witness message mode ") + (w.multi ? "MultiV1" : "SingleV1") + " does not match graph mode " +
+                                   (multi_ ? "MultiV1" : "SingleV1"));
+                if (used != rec.size() || w.path.size() / 32 != depth_ || w.index.size() != depth_ || w.k() != max_out_)
+                    throw RlnError("Protocol error: witness record does not have the shape of the circuit (tree depth " + std::to_string(depth_) +
+                                   ", " + std::to_string(max_out_) + " message id slots)");
+                throw RlnError("record refused on the device but accepted by the host parser");
+            } catch (const RlnError& e) {
+                memset(w.secret, 0, 32);
+                throw RlnError(msg + e.what());
+            }
+        }
+        prove_device(ws_inputs_.as<uint8_t>(), rs_dev, B, ws_proofs_.as<uint8_t>(), ws_values_.as<uint8_t>(), nullptr, s);
+        launch_proof_records(ws_proofs_.as<uint8_t>(), ws_values_.as<uint8_t>(), ws_inputs_.as<uint8_t>(), B, L, d_out + off * (size_t)L.proof_rec_len, s);
+        g_launch_count++;
+    }
+    ZK_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (!rsb.empty()) memset(rsb.data(), 0, rsb.size());
+}
+
+void Rln::prove_records_host(const uint8_t* records, const uint8_t* rs, size_t n, uint8_t* out) {
+    if (!n) return;
+    const RecordLayout L = record_layout();
+    const size_t super = 16 * max_batch_;   // records resident on the device at a time
+    const size_t m = n < super ? n : super;
+    ws_recs_in_.ensure(m * (size_t)L.rec_len);
+    ws_recs_out_.ensure(m * (size_t)L.proof_rec_len);
+    if (rs) ws_rs_all_.ensure(64 * m);
+    struct Scrub {
+        Rln& r;
+        ~Scrub() { cudaMemsetAsync(r.ws_recs_in_.p, 0, r.ws_recs_in_.bytes, r.stream_); cudaStreamSynchronize(r.stream_); }
+    } scrub{*this};
+    for (size_t off = 0; off < n; off += m) {
+        const size_t B = n - off < m ? n - off : m;
+        ZK_CUDA_CHECK(cudaMemcpyAsync(ws_recs_in_.p, records + off * (size_t)L.rec_len, B * (size_t)L.rec_len, cudaMemcpyHostToDevice, stream_));
+        if (rs) ZK_CUDA_CHECK(cudaMemcpyAsync(ws_rs_all_.p, rs + 64 * off, 64 * B, cudaMemcpyHostToDevice, stream_));
+        prove_records_device(ws_recs_in_.as<uint8_t>(), rs ? ws_rs_all_.as<uint8_t>() : nullptr, B, ws_recs_out_.as<uint8_t>(), stream_);
+        ZK_CUDA_CHECK(cudaMemcpyAsync(out + off * (size_t)L.proof_rec_len, ws_recs_out_.p, B * (size_t)L.proof_rec_len, cudaMemcpyDeviceToHost, stream_));
+        ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    }
+}
+
 void Rln::partial_host(const std::vector<Witness>& wsv, std::vector<PartialProofHost>& out) {
     const size_t n = wsv.size();
     out.resize(n);
@@ -1288,6 +1468,7 @@ void Rln::partial_host(const std::vector<Witness>& wsv, std::vector<PartialProof
     const size_t chunk = n < max_batch_ ? n : max_batch_;
     reserve(chunk);
     std::vector<uint8_t> slots(chunk * (size_t)gh_.n_slots * 32), aff(chunk * 320), comp(chunk * 160);
+    SecretScrub scrub{slots, ws_inputs_, stream_};
     for (size_t off = 0; off < n; off += chunk) {
         const size_t B = n - off < chunk ? n - off : chunk;
         for (size_t j = 0; j < B; j++) {
@@ -1376,10 +1557,16 @@ void Rln::verify_batch(const uint8_t* proofs128, const uint8_t* publics, size_t 
 using namespace zk;
 
 struct FFI_RLN { std::unique_ptr<Rln> r; };
+// the handle's mutex + its device made current on the calling thread (one handle, many threads, several devices)
+struct RlnLock {
+    std::lock_guard<std::mutex> lk;
+    DeviceGuard dg;
+    explicit RlnLock(Rln& r) : lk(r.mu), dg(r.device()) {}
+};
 struct FFI_RLNProof { RlnProof p; };
 struct FFI_RLNProofValues { ProofValues v; };
 struct FFI_RLNWitnessInput { Witness w; };
-struct RlnB200Msm { VarMsmWorkspace* ws; size_t max_n; };
+struct RlnB200Msm { VarMsmWorkspace* ws; size_t max_n; int device; };
 struct FFI_RLNPartialWitnessInput { Witness w; };
 struct FFI_RLNPartialProof { PartialProofHost p; std::vector<uint8_t> mask; };
 
@@ -1438,14 +1625,8 @@ static std::vector<uint8_t> read_file(const std::string& path) {
 }
 
 // record lengths of rln_witness_to_bytes_le / rln_proof_to_bytes_le for the handle's circuit
-static size_t witness_record_len(const Rln& r) {
-    const size_t d = r.depth(), k = r.max_out();
-    return r.multi() ? 1 + 64 + (8 + 32 * d) + (8 + d) + 64 + (8 + 32 * k) + (8 + k) : 1 + 32 * (5 + d) + 16 + d;
-}
-static size_t proof_record_len(const Rln& r) {
-    const size_t k = r.max_out();
-    return r.multi() ? 1 + 128 + 1 + 96 + (8 + 32 * k) * 2 + (8 + k) : 290;
-}
+static size_t witness_record_len(const Rln& r) { return r.witness_record_len(); }
+static size_t proof_record_len(const Rln& r) { return r.proof_record_len(); }
 static std::vector<Witness> parse_records(Rln& r, const uint8_t* witnesses, size_t n, bool partial_phase) {
     const size_t d = r.depth(), rec = witness_record_len(r);
     std::vector<Witness> ws(n);
@@ -1525,7 +1706,7 @@ CResult_FFI_RLN_t rlnb200_rln_new_multi(size_t tree_depth, size_t max_out) {
 // ---- tree -------------------------------------------------------------------------------------
 #define BOOL_OP(...)                                                      \
     GUARD_BEGIN                                                           \
-    std::lock_guard<std::mutex> lk((*rln)->r->mu);                        \
+    RlnLock lk(*(*rln)->r);                        \
     __VA_ARGS__;                                                          \
     return CBoolResult_t{true, no_string()};                              \
     GUARD_END(return (CBoolResult_t{false, mk_string(m)}))
@@ -1550,7 +1731,7 @@ CBoolResult_t ffi_seq_atomic_operation(FFI_RLN_t** rln, const Vec_CFr_t* leaves,
 size_t ffi_leaves_set(FFI_RLN_t* const* rln) { return (*rln)->r->leaves_set(); }
 CResult_CFr_t ffi_get_leaf(FFI_RLN_t* const* rln, size_t index) {
     GUARD_BEGIN
-    std::lock_guard<std::mutex> lk((*rln)->r->mu);
+    RlnLock lk(*(*rln)->r);
     uint8_t b[32];
     (*rln)->r->get_leaf(index, b);
     return CResult_CFr_t{mk_cfr(b), no_string()};
@@ -1559,7 +1740,7 @@ CResult_CFr_t ffi_get_leaf(FFI_RLN_t* const* rln, size_t index) {
 CFr_t* ffi_get_root(FFI_RLN_t* const* rln) {
     uint8_t b[32] = {0};
     try {
-        std::lock_guard<std::mutex> lk((*rln)->r->mu);
+        RlnLock lk(*(*rln)->r);
         (*rln)->r->root(b);
     } catch (...) {
         abort();  // the reference's get_root is infallible
@@ -1568,7 +1749,7 @@ CFr_t* ffi_get_root(FFI_RLN_t* const* rln) {
 }
 CResult_FFI_MerkleProof_t ffi_get_merkle_proof(FFI_RLN_t* const* rln, size_t index) {
     GUARD_BEGIN
-    std::lock_guard<std::mutex> lk((*rln)->r->mu);
+    RlnLock lk(*(*rln)->r);
     const size_t d = (*rln)->r->tree_depth();
     FFI_MerkleProof_t* mp = (FFI_MerkleProof_t*)malloc(sizeof(FFI_MerkleProof_t));
     mp->path_elements.ptr = (CFr_t*)malloc(32 * d);
@@ -1665,7 +1846,7 @@ static void prove_alone(Rln& R, Rln::ProveReq* q) {   // caller holds R.mu
     catch (const std::exception& e) { q->failed = true; q->err = describe(e); }
 }
 static void run_prove_batch(Rln& R, std::vector<Rln::ProveReq*>& b) {
-    std::lock_guard<std::mutex> lk(R.mu);
+    RlnLock lk(R);
     if (b.size() == 1) { prove_alone(R, b[0]); return; }
     try {
         std::vector<Witness> ws;
@@ -1685,7 +1866,7 @@ static void run_prove_batch(Rln& R, std::vector<Rln::ProveReq*>& b) {
     }
 }
 static void run_pairing_batch(Rln& R, std::vector<Rln::PairingReq*>& b) {
-    std::lock_guard<std::mutex> lk(R.mu);
+    RlnLock lk(R);
     try {
         const size_t np = 32 * R.n_public();
         std::vector<uint8_t> proofs(128 * b.size()), pubs(np * b.size()), ok(b.size(), 0);
@@ -1707,7 +1888,7 @@ static bool pairing_ok(Rln& R, const uint8_t* proof128, const uint8_t* pub) {
         if (q.failed) throw RlnError(q.err);
         return q.ok == 1;
     }
-    std::lock_guard<std::mutex> lk(R.mu);
+    RlnLock lk(R);
     uint8_t ok = 0;
     R.verify_batch(proof128, pub, 1, &ok);
     return ok == 1;
@@ -1724,7 +1905,7 @@ static CResult_FFI_RLNProof_t prove_one(FFI_RLN_t* const* rln, FFI_RLNWitnessInp
         p->p = q.out;
         return CResult_FFI_RLNProof_t{p.release(), no_string()};
     }
-    std::lock_guard<std::mutex> lk((*rln)->r->mu);
+    RlnLock lk(*(*rln)->r);
     std::vector<Witness> ws(1, (*witness)->w);
     std::vector<RlnProof> out;
     (*rln)->r->prove_host(ws, rs, out);
@@ -1770,7 +1951,7 @@ void ffi_rln_partial_witness_input_free(FFI_RLNPartialWitnessInput_t* w) {
 }
 CResult_FFI_RLNPartialProof_t ffi_generate_partial_zk_proof(FFI_RLN_t* const* rln, FFI_RLNPartialWitnessInput_t* const* partial_witness) {
     GUARD_BEGIN
-    std::lock_guard<std::mutex> lk((*rln)->r->mu);
+    RlnLock lk(*(*rln)->r);
     std::vector<Witness> ws(1, (*partial_witness)->w);
     ws[0].multi = (*rln)->r->multi();   // a partial witness carries no message ids: shape them for the circuit at hand
     ws[0].mids.assign(32 * (*rln)->r->max_out(), 0);
@@ -1787,7 +1968,7 @@ CResult_FFI_RLNPartialProof_t ffi_generate_partial_zk_proof(FFI_RLN_t* const* rl
 static CResult_FFI_RLNProof_t finish_one(FFI_RLN_t* const* rln, FFI_RLNPartialProof_t* const* partial, FFI_RLNWitnessInput_t* const* witness,
                                          const uint8_t* rs) {
     GUARD_BEGIN
-    std::lock_guard<std::mutex> lk((*rln)->r->mu);
+    RlnLock lk(*(*rln)->r);
     if ((*partial)->mask != (*rln)->r->partial_mask()) throw RlnError("Protocol error: Error producing proof: malformed verifying key");
     std::vector<Witness> ws(1, (*witness)->w);
     std::vector<RlnProof> out;
@@ -1822,7 +2003,7 @@ CResult_Vec_uint8_t ffi_rln_partial_proof_to_bytes_le(FFI_RLNPartialProof_t* con
 }
 CResult_FFI_RLNPartialProof_t rlnb200_bytes_le_to_rln_partial_proof(FFI_RLN_t* const* rln, const Vec_uint8_t* bytes) {
     GUARD_BEGIN
-    std::lock_guard<std::mutex> lk((*rln)->r->mu);
+    RlnLock lk(*(*rln)->r);
     const uint8_t* b = bytes->ptr;
     const size_t len = bytes->len;
     if (len == 0) throw RlnError(msg_read_len(1, 0));
@@ -1863,7 +2044,7 @@ static CBoolResult_t verify_common(FFI_RLN_t* const* rln, const RlnProof& p, con
     if (use_tree_root) {
         uint8_t root[32];
         {
-            std::lock_guard<std::mutex> lk(R.mu);
+            RlnLock lk(R);
             R.root(root);
         }
         if (memcmp(root, p.pv.root, 32)) throw RlnError("Verification error: Expected one of the provided roots");
@@ -2083,18 +2264,16 @@ Vec_CFr_t ffi_key_gen(void) {  // keygen (rln/src/protocol/keygen.rs:20-30): sec
     GUARD_END(if (err) *err = mk_string(m); return -1)
 
 int rlnb200_prove_batch(FFI_RLN_t* const* rln, const uint8_t* witnesses, size_t n, const uint8_t* rs, uint8_t* proofs_out, RlnString* err) {
-    INT_OP(
-        std::lock_guard<std::mutex> lk((*rln)->r->mu);
-        std::vector<Witness> ws = parse_records(*(*rln)->r, witnesses, n, false);
-        std::vector<RlnProof> out;
-        (*rln)->r->prove_host(ws, rs, out);
-        for (auto& w : ws) memset(w.secret, 0, 32);
-        const size_t orec = proof_record_len(*(*rln)->r);
-        for (size_t i = 0; i < n; i++) { std::vector<uint8_t> b = rln_proof_to_bytes(out[i]); memcpy(proofs_out + orec * i, b.data(), orec); })
+    INT_OP(RlnLock lk(*(*rln)->r); (*rln)->r->prove_records_host(witnesses, rs, n, proofs_out);)
+}
+int rlnb200_prove_records_device(FFI_RLN_t* const* rln, const void* d_witness_records, const void* d_rs, size_t n, void* d_proof_records,
+                                 void* stream, RlnString* err) {
+    INT_OP(RlnLock lk(*(*rln)->r);
+           (*rln)->r->prove_records_device((const uint8_t*)d_witness_records, (const uint8_t*)d_rs, n, (uint8_t*)d_proof_records, (cudaStream_t)stream);)
 }
 int rlnb200_partial_batch(FFI_RLN_t* const* rln, const uint8_t* witnesses, size_t n, uint8_t* partial_out, RlnString* err) {
     INT_OP(
-        std::lock_guard<std::mutex> lk((*rln)->r->mu);
+        RlnLock lk(*(*rln)->r);
         std::vector<Witness> ws = parse_records(*(*rln)->r, witnesses, n, true);
         std::vector<PartialProofHost> out;
         (*rln)->r->partial_host(ws, out);
@@ -2104,7 +2283,7 @@ int rlnb200_partial_batch(FFI_RLN_t* const* rln, const uint8_t* witnesses, size_
 int rlnb200_finish_batch(FFI_RLN_t* const* rln, const uint8_t* witnesses, size_t n, const uint8_t* partial, const uint8_t* rs,
                          uint8_t* proofs_out, RlnString* err) {
     INT_OP(
-        std::lock_guard<std::mutex> lk((*rln)->r->mu);
+        RlnLock lk(*(*rln)->r);
         std::vector<Witness> ws = parse_records(*(*rln)->r, witnesses, n, false);
         std::vector<PartialProofHost> pp(n);
         for (size_t i = 0; i < n; i++) memcpy(pp[i].affine, partial + 320 * i, 320);
@@ -2116,7 +2295,7 @@ int rlnb200_finish_batch(FFI_RLN_t* const* rln, const uint8_t* witnesses, size_t
 }
 int rlnb200_verify_batch(FFI_RLN_t* const* rln, const uint8_t* proofs, size_t n, uint8_t* ok_out, RlnString* err) {
     INT_OP(
-        std::lock_guard<std::mutex> lk((*rln)->r->mu);
+        RlnLock lk(*(*rln)->r);
         const size_t orec = proof_record_len(*(*rln)->r), np = (*rln)->r->n_public();
         std::vector<uint8_t> p(128 * n), pub(32 * np * n);
         for (size_t i = 0; i < n; i++) {
@@ -2132,19 +2311,19 @@ int rlnb200_verify_batch(FFI_RLN_t* const* rln, const uint8_t* proofs, size_t n,
 }
 int rlnb200_prove_batch_device(FFI_RLN_t* const* rln, const void* d_inputs, const void* d_rs, size_t n, void* d_proofs, void* d_values,
                                void* d_affine, void* stream, RlnString* err) {
-    INT_OP(std::lock_guard<std::mutex> lk((*rln)->r->mu);
+    INT_OP(RlnLock lk(*(*rln)->r);
            (*rln)->r->prove_device((const uint8_t*)d_inputs, (const uint8_t*)d_rs, n, (uint8_t*)d_proofs, (uint8_t*)d_values, (uint8_t*)d_affine,
                                    (cudaStream_t)stream);)
 }
 int rlnb200_partial_batch_device(FFI_RLN_t* const* rln, const void* d_inputs, size_t n, void* d_partial_affine, void* d_partial_compressed,
                                  void* stream, RlnString* err) {
-    INT_OP(std::lock_guard<std::mutex> lk((*rln)->r->mu);
+    INT_OP(RlnLock lk(*(*rln)->r);
            (*rln)->r->prove_device((const uint8_t*)d_inputs, nullptr, n, nullptr, nullptr, nullptr, (cudaStream_t)stream, MSM_KNOWN, nullptr,
                                    (uint8_t*)d_partial_affine, (uint8_t*)d_partial_compressed);)
 }
 int rlnb200_finish_batch_device(FFI_RLN_t* const* rln, const void* d_inputs, const void* d_rs, const void* d_partial_affine, size_t n,
                                 void* d_proofs, void* d_values, void* stream, RlnString* err) {
-    INT_OP(std::lock_guard<std::mutex> lk((*rln)->r->mu);
+    INT_OP(RlnLock lk(*(*rln)->r);
            (*rln)->r->prove_device((const uint8_t*)d_inputs, (const uint8_t*)d_rs, n, (uint8_t*)d_proofs, (uint8_t*)d_values, nullptr,
                                    (cudaStream_t)stream, MSM_UNKNOWN, (const uint8_t*)d_partial_affine);)
 }
@@ -2164,7 +2343,7 @@ int rlnb200_input_slot(FFI_RLN_t* const* rln, const char* name, uint32_t* offset
     return 1;
 }
 int rlnb200_reserve(FFI_RLN_t* const* rln, size_t max_batch, RlnString* err) {
-    INT_OP(std::lock_guard<std::mutex> lk((*rln)->r->mu); (*rln)->r->reserve(max_batch);)
+    INT_OP(RlnLock lk(*(*rln)->r); (*rln)->r->reserve(max_batch);)
 }
 uint64_t rlnb200_launch_count(void) { return g_launch_count.load(); }
 void rlnb200_last_stage_ms(FFI_RLN_t* const* rln, float out[8]) {
@@ -2179,23 +2358,23 @@ int rlnb200_table_info(FFI_RLN_t* const* rln, int* window_bits, int* windows, ui
     return 0;
 }
 int rlnb200_set_leaves_from_bytes(FFI_RLN_t** rln, size_t index, const uint8_t* leaves_le, size_t count, RlnString* err) {
-    INT_OP(std::lock_guard<std::mutex> lk((*rln)->r->mu); (*rln)->r->set_range_host(index, leaves_le, count);)
+    INT_OP(RlnLock lk(*(*rln)->r); (*rln)->r->set_range_host(index, leaves_le, count);)
 }
 int rlnb200_set_leaves_from_device(FFI_RLN_t** rln, size_t index, const void* d_leaves, size_t count, void* stream, RlnString* err) {
-    INT_OP(std::lock_guard<std::mutex> lk((*rln)->r->mu); (*rln)->r->set_range_device(index, (const uint8_t*)d_leaves, count, (cudaStream_t)stream);)
+    INT_OP(RlnLock lk(*(*rln)->r); (*rln)->r->set_range_device(index, (const uint8_t*)d_leaves, count, (cudaStream_t)stream);)
 }
 int rlnb200_get_merkle_proofs(FFI_RLN_t* const* rln, const uint64_t* indices, size_t n, uint8_t* elements_out, uint8_t* index_bits_out, RlnString* err) {
-    INT_OP(std::lock_guard<std::mutex> lk((*rln)->r->mu); (*rln)->r->merkle_proofs(indices, n, elements_out, index_bits_out);)
+    INT_OP(RlnLock lk(*(*rln)->r); (*rln)->r->merkle_proofs(indices, n, elements_out, index_bits_out);)
 }
 int rlnb200_debug_witness_and_h(FFI_RLN_t* const* rln, const uint8_t* witness_le, size_t len, uint8_t* w_out, uint8_t* h_out, RlnString* err) {
-    INT_OP(std::lock_guard<std::mutex> lk((*rln)->r->mu); Witness w; witness_from_bytes(witness_le, len, w); (*rln)->r->debug_w_h(w, w_out, h_out);)
+    INT_OP(RlnLock lk(*(*rln)->r); Witness w; witness_from_bytes(witness_le, len, w); (*rln)->r->debug_w_h(w, w_out, h_out);)
 }
 int rlnb200_get_subtree_root(FFI_RLN_t* const* rln, size_t level, size_t index, uint8_t* out32, RlnString* err) {
-    INT_OP(std::lock_guard<std::mutex> lk((*rln)->r->mu); (*rln)->r->subtree_root(level, index, out32))
+    INT_OP(RlnLock lk(*(*rln)->r); (*rln)->r->subtree_root(level, index, out32))
 }
 int rlnb200_get_empty_leaves_indices(FFI_RLN_t* const* rln, Vec_size_t* out, RlnString* err) {
     INT_OP(
-        std::lock_guard<std::mutex> lk((*rln)->r->mu);
+        RlnLock lk(*(*rln)->r);
         std::vector<size_t> v = (*rln)->r->empty_leaves_indices();
         out->len = v.size();
         out->cap = v.size() ? v.size() : 1;
@@ -2232,10 +2411,137 @@ size_t rlnb200_witness_record_len(FFI_RLN_t* const* rln) { return witness_record
 size_t rlnb200_proof_record_len(FFI_RLN_t* const* rln) { return proof_record_len(*(*rln)->r); }
 size_t rlnb200_domain_size(FFI_RLN_t* const* rln) { return (*rln)->r->domain(); }
 
+
+// ---- one batch, every GPU of the box (BASELINE.json configs[4]) -----------------------------------------------------------
+// A multi-device prover is one replica of the RLN object per device (immutable data — tables, matrices, graph program — is
+// rebuilt locally on every GPU: 2.6 s, cheaper than moving 125 GiB) inside ONE process.  A batch of independent proofs is cut
+// into contiguous shards, one worker thread per device runs the device-records path on its shard straight from / to the
+// caller's host buffers (every GPU has its own PCIe link, so no GPU relays another GPU's bytes), and the call returns when
+// the slowest shard is done.  No collective is needed inside a process; the torchrun / NCCL form of the same sharding for
+// one-process-per-GPU deployments is zerokit_b200/sharding.py.
+}  // extern "C" (templates below)
+struct RlnB200Multi {
+    std::vector<std::unique_ptr<FFI_RLN>> reps;
+    std::vector<int> devices;
+    std::vector<float> shard_ms;   // wall time of each device's shard in the last batch call
+};
+template <class Fn>
+static void multi_for_each(RlnB200Multi& m, Fn fn) {   // fn(replica index) on one thread per device; rethrows the first failure
+    std::vector<std::thread> th;
+    std::vector<std::string> errs(m.reps.size());
+    std::vector<char> failed(m.reps.size(), 0);
+    for (size_t i = 0; i < m.reps.size(); i++)
+        th.emplace_back([&, i] {
+            try {
+                fn(i);
+            } catch (const CudaError& e) { failed[i] = 1; errs[i] = describe(e); }
+            catch (const std::exception& e) { failed[i] = 1; errs[i] = describe(e); }
+        });
+    for (auto& t : th) t.join();
+    for (size_t i = 0; i < m.reps.size(); i++)
+        if (failed[i]) throw RlnError("device " + std::to_string(m.devices[i]) + ": " + errs[i]);
+}
+// contiguous shard of replica i: [lo, hi)
+static void multi_shard(size_t n, size_t parts, size_t i, size_t* lo, size_t* hi) {
+    const size_t q = n / parts, r = n % parts;
+    *lo = i * q + (i < r ? i : r);
+    *hi = *lo + q + (i < r ? 1 : 0);
+}
+extern "C" {
+RlnB200Multi_t* rlnb200_multi_new(size_t tree_depth, const int* devices, size_t n_devices, RlnString* err) {
+    GUARD_BEGIN
+    int visible = 0;
+    if (cudaGetDeviceCount(&visible) != cudaSuccess || visible == 0) throw RlnError("no usable CUDA device (librln_b200 has no CPU path)");
+    auto m = std::make_unique<RlnB200Multi>();
+    if (!devices || n_devices == 0) {
+        for (int d = 0; d < visible; d++) m->devices.push_back(d);
+    } else {
+        for (size_t i = 0; i < n_devices; i++) {
+            if (devices[i] < 0 || devices[i] >= visible) throw RlnError("Configuration error: device " + std::to_string(devices[i]) + " is not visible");
+            m->devices.push_back(devices[i]);
+        }
+    }
+    std::ostringstream dir;
+    dir << resources_dir() << "/tree_depth_" << tree_depth;
+    const std::vector<uint8_t> zkey = read_file(dir.str() + "/rln_final.arkzkey"), graph = read_file(dir.str() + "/graph.bin");
+    m->reps.resize(m->devices.size());
+    m->shard_ms.assign(m->devices.size(), 0.f);
+    multi_for_each(*m, [&](size_t i) {
+        DeviceGuard dg(m->devices[i]);
+        auto h = std::make_unique<FFI_RLN>();
+        h->r = std::make_unique<Rln>(tree_depth, zkey.data(), zkey.size(), graph.data(), graph.size());
+        m->reps[i] = std::move(h);
+    });
+    return m.release();
+    GUARD_END(if (err) *err = mk_string(m); return nullptr)
+}
+void rlnb200_multi_free(RlnB200Multi_t* m) { delete m; }
+size_t rlnb200_multi_device_count(const RlnB200Multi_t* m) { return m->reps.size(); }
+int rlnb200_multi_device(const RlnB200Multi_t* m, size_t i) { return i < m->devices.size() ? m->devices[i] : -1; }
+// borrowed handle of replica i: every single-device call works on it (tree queries, verification, single proofs)
+FFI_RLN_t* const* rlnb200_multi_replica(RlnB200Multi_t* m, size_t i) {
+    static thread_local FFI_RLN* slot;
+    if (i >= m->reps.size()) return nullptr;
+    slot = m->reps[i].get();
+    return &slot;
+}
+// tree updates go to every replica (the tree is part of each device's state: membership paths are read where the proofs are made)
+int rlnb200_multi_set_leaves_from_bytes(RlnB200Multi_t* m, size_t index, const uint8_t* leaves_le, size_t count, RlnString* err) {
+    INT_OP(multi_for_each(*m, [&](size_t i) { RlnLock lk(*m->reps[i]->r); m->reps[i]->r->set_range_host(index, leaves_le, count); });)
+}
+int rlnb200_multi_set_tree(RlnB200Multi_t* m, size_t tree_depth, RlnString* err) {
+    INT_OP(multi_for_each(*m, [&](size_t i) { RlnLock lk(*m->reps[i]->r); m->reps[i]->r->set_tree(tree_depth); });)
+}
+int rlnb200_multi_atomic_operation(RlnB200Multi_t* m, size_t index, const uint8_t* leaves_le, size_t n_leaves, const size_t* indices, size_t n_indices,
+                                   RlnString* err) {
+    INT_OP(multi_for_each(*m, [&](size_t i) {
+        RlnLock lk(*m->reps[i]->r);
+        m->reps[i]->r->override_range(index, leaves_le, n_leaves, std::vector<size_t>(indices, indices + n_indices));
+    });)
+}
+int rlnb200_multi_reserve(RlnB200Multi_t* m, size_t max_batch, RlnString* err) {
+    INT_OP(multi_for_each(*m, [&](size_t i) { RlnLock lk(*m->reps[i]->r); m->reps[i]->r->reserve(max_batch); });)
+}
+// n witness records (host) → n proof records (host), sharded over the devices; rs may be NULL (fresh r, s)
+int rlnb200_multi_prove_batch(RlnB200Multi_t* m, const uint8_t* witnesses, size_t n, const uint8_t* rs, uint8_t* proofs_out, RlnString* err) {
+    INT_OP(
+        const size_t parts = m->reps.size();
+        multi_for_each(*m, [&](size_t i) {
+            size_t lo, hi;
+            multi_shard(n, parts, i, &lo, &hi);
+            m->shard_ms[i] = 0.f;
+            if (lo == hi) return;
+            Rln& R = *m->reps[i]->r;
+            RlnLock lk(R);
+            const auto t0 = std::chrono::steady_clock::now();
+            R.prove_records_host(witnesses + lo * R.witness_record_len(), rs ? rs + 64 * lo : nullptr, hi - lo, proofs_out + lo * R.proof_record_len());
+            m->shard_ms[i] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        });)
+}
+int rlnb200_multi_verify_batch(RlnB200Multi_t* m, const uint8_t* proofs, size_t n, uint8_t* ok_out, RlnString* err) {
+    INT_OP(
+        const size_t parts = m->reps.size();
+        multi_for_each(*m, [&](size_t i) {
+            size_t lo, hi;
+            multi_shard(n, parts, i, &lo, &hi);
+            if (lo == hi) return;
+            FFI_RLN* h = m->reps[i].get();
+            RlnString e{nullptr, 0, 0};
+            if (rlnb200_verify_batch(&h, proofs + lo * h->r->proof_record_len(), hi - lo, ok_out + lo, &e) != 0) {
+                std::string msg((const char*)e.ptr, e.len);
+                ffi_c_string_free(e);
+                throw RlnError(msg);
+            }
+        });)
+}
+void rlnb200_multi_last_shard_ms(const RlnB200Multi_t* m, float* out) {
+    for (size_t i = 0; i < m->shard_ms.size(); i++) out[i] = m->shard_ms[i];
+}
+
 RlnB200Msm_t* rlnb200_msm_new(size_t max_n, RlnString* err) {
     GUARD_BEGIN
-    global_init();
     auto m = std::make_unique<RlnB200Msm>();
+    m->device = global_init();
     m->ws = var_msm_workspace_create(max_n);
     m->max_n = max_n;
     return m.release();
@@ -2243,23 +2549,25 @@ RlnB200Msm_t* rlnb200_msm_new(size_t max_n, RlnString* err) {
 }
 void rlnb200_msm_free(RlnB200Msm_t* m) {
     if (!m) return;
-    var_msm_workspace_destroy(m->ws);
+    try {
+        DeviceGuard dg(m->device);
+        var_msm_workspace_destroy(m->ws);
+    } catch (...) {
+    }
     delete m;
 }
 int rlnb200_msm_upload_bases(RlnB200Msm_t* m, const uint8_t* bases, size_t n, void* d_bases_out, RlnString* err) {
-    (void)m;
-    INT_OP(DevMem raw; raw.upload(bases, 64 * n); launch_g1_from_bytes(raw.as<uint8_t>(), (G1Affine*)d_bases_out, n, 0); g_launch_count++;
+    INT_OP(DeviceGuard dg(m->device); DevMem raw; raw.upload(bases, 64 * n); launch_g1_from_bytes(raw.as<uint8_t>(), (G1Affine*)d_bases_out, n, 0); g_launch_count++;
            ZK_CUDA_CHECK(cudaDeviceSynchronize());)
 }
 int rlnb200_msm_gen_bases(RlnB200Msm_t* m, const void* d_scalars, size_t n, void* d_bases_out, void* stream, RlnString* err) {
-    (void)m;
-    INT_OP(launch_g1_mul_gen((const uint8_t*)d_scalars, (G1Affine*)d_bases_out, n, (cudaStream_t)stream); g_launch_count++;)
+    INT_OP(DeviceGuard dg(m->device); launch_g1_mul_gen((const uint8_t*)d_scalars, (G1Affine*)d_bases_out, n, (cudaStream_t)stream); g_launch_count++;)
 }
 int rlnb200_msm_g1_device(RlnB200Msm_t* m, const void* d_bases, const void* d_scalars, size_t n, void* d_result, void* stream, RlnString* err) {
-    INT_OP(launch_var_msm_g1(m->ws, (const G1Affine*)d_bases, (const uint8_t*)d_scalars, n, (uint8_t*)d_result, (cudaStream_t)stream); g_launch_count += 9;)
+    INT_OP(DeviceGuard dg(m->device); launch_var_msm_g1(m->ws, (const G1Affine*)d_bases, (const uint8_t*)d_scalars, n, (uint8_t*)d_result, (cudaStream_t)stream); g_launch_count += 9;)
 }
 int rlnb200_msm_g1(RlnB200Msm_t* m, const uint8_t* bases, const uint8_t* scalars, size_t n, uint8_t* result, RlnString* err) {
-    INT_OP(DevMem raw, db, ds, dr; raw.upload(bases, 64 * n); db.alloc(sizeof(G1Affine) * n); ds.upload(scalars, 32 * n); dr.alloc(64);
+    INT_OP(DeviceGuard dg(m->device); DevMem raw, db, ds, dr; raw.upload(bases, 64 * n); db.alloc(sizeof(G1Affine) * n); ds.upload(scalars, 32 * n); dr.alloc(64);
            launch_g1_from_bytes(raw.as<uint8_t>(), db.as<G1Affine>(), n, 0);
            launch_var_msm_g1(m->ws, db.as<G1Affine>(), ds.as<uint8_t>(), n, dr.as<uint8_t>(), 0); g_launch_count += 10;
            ZK_CUDA_CHECK(cudaMemcpy(result, dr.p, 64, cudaMemcpyDeviceToHost));)

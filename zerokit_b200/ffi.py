@@ -289,6 +289,19 @@ def lib():
         "rlnb200_generate_rln_proof_with_rs": (CResult_ptr, [pp, pp, POINTER(CFr), POINTER(CFr)]),
         "rlnb200_prove_batch": (c_int, [pp, c_void_p, c_size_t, c_void_p, c_void_p, POINTER(RlnString)]),
         "rlnb200_verify_batch": (c_int, [pp, c_void_p, c_size_t, c_void_p, POINTER(RlnString)]),
+        "rlnb200_prove_records_device": (c_int, [pp, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, POINTER(RlnString)]),
+        "rlnb200_multi_new": (c_void_p, [c_size_t, POINTER(c_int), c_size_t, POINTER(RlnString)]),
+        "rlnb200_multi_free": (None, [c_void_p]),
+        "rlnb200_multi_device_count": (c_size_t, [c_void_p]),
+        "rlnb200_multi_device": (c_int, [c_void_p, c_size_t]),
+        "rlnb200_multi_replica": (pp, [c_void_p, c_size_t]),
+        "rlnb200_multi_set_tree": (c_int, [c_void_p, c_size_t, POINTER(RlnString)]),
+        "rlnb200_multi_set_leaves_from_bytes": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, POINTER(RlnString)]),
+        "rlnb200_multi_atomic_operation": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, POINTER(c_size_t), c_size_t, POINTER(RlnString)]),
+        "rlnb200_multi_reserve": (c_int, [c_void_p, c_size_t, POINTER(RlnString)]),
+        "rlnb200_multi_prove_batch": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, POINTER(RlnString)]),
+        "rlnb200_multi_verify_batch": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, POINTER(RlnString)]),
+        "rlnb200_multi_last_shard_ms": (None, [c_void_p, POINTER(c_float)]),
         "rlnb200_prove_batch_device": (c_int, [pp, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(RlnString)]),
         "rlnb200_partial_batch_device": (c_int, [pp, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, POINTER(RlnString)]),
         "rlnb200_finish_batch_device": (c_int, [pp, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, POINTER(RlnString)]),

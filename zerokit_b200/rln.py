@@ -514,7 +514,7 @@ class RLN:
         return cls(_check_ptr(ffi.lib().ffi_rln_new_with_params(tree_depth, byref(_vec_u8(zkey)), byref(_vec_u8(graph)), config_path.encode())))
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
+        if getattr(self, "_h", None) and self._h.value and not getattr(self, "_borrowed", False):
             ffi.lib().ffi_rln_free(self._h)
             self._h = c_void_p(None)
 
@@ -686,6 +686,12 @@ class RLN:
         _check_int(ffi.lib().rlnb200_verify_batch(byref(self._h), proofs_le, n, ok, byref(err)), err)
         return list(ok.raw[:n])
 
+    def prove_records_device(self, d_witness_records, d_rs, n, d_proof_records, stream=0):
+        """device-resident wire records: n rln_witness_to_bytes_le records → n rln_proof_to_bytes_le records (d_rs may be 0: fresh r, s)"""
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_prove_records_device(byref(self._h), c_void_p(d_witness_records), c_void_p(d_rs) if d_rs else None, n,
+                                                          c_void_p(d_proof_records), c_void_p(stream), byref(err)), err)
+
     def prove_batch_device(self, d_inputs, d_rs, n, d_proofs, d_values=0, d_affine=0, stream=0):
         err = ffi.RlnString()
         _check_int(ffi.lib().rlnb200_prove_batch_device(byref(self._h), c_void_p(d_inputs), c_void_p(d_rs), n, c_void_p(d_proofs),
@@ -741,6 +747,80 @@ class RLN:
         err = ffi.RlnString()
         _check_int(ffi.lib().rlnb200_debug_witness_and_h(byref(self._h), witness_le, len(witness_le), w, h, byref(err)), err)
         return w.raw, h.raw
+
+
+class RLNMulti:
+    """One batch over several GPUs inside one process (BASELINE.json configs[4]): a replica of the prover per device, contiguous
+    shards, one worker thread per device (rlnb200_multi_*).  Where the reference scales by calling one handle from many host
+    threads (rln/README.md:324-332), this scales by giving one call to many devices."""
+
+    def __init__(self, tree_depth=DEFAULT_TREE_DEPTH, devices=None):
+        err = ffi.RlnString()
+        arr = (ctypes.c_int * len(devices))(*devices) if devices else None
+        self._m = c_void_p(ffi.lib().rlnb200_multi_new(tree_depth, arr, len(devices) if devices else 0, byref(err)))
+        if not self._m.value:
+            raise RLNError(_take_string(err) or "multi_new failed")
+        self._depth = tree_depth
+
+    def __del__(self):
+        if getattr(self, "_m", None) and self._m.value:
+            ffi.lib().rlnb200_multi_free(self._m)
+            self._m = c_void_p(None)
+
+    def device_count(self):
+        return ffi.lib().rlnb200_multi_device_count(self._m)
+
+    def devices(self):
+        return [ffi.lib().rlnb200_multi_device(self._m, i) for i in range(self.device_count())]
+
+    def replica(self, i):
+        """a borrowed RLN view of replica i (not owned: freeing it is the multi object's job)"""
+        pp = ffi.lib().rlnb200_multi_replica(self._m, i)
+        if not pp:
+            raise IndexError(i)
+        r = RLN.__new__(RLN)
+        r._h = c_void_p(pp[0])
+        r._borrowed = True
+        return r
+
+    def set_tree(self, tree_depth):
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_multi_set_tree(self._m, tree_depth, byref(err)), err)
+
+    def set_leaves_from_bytes(self, index, leaves_le: bytes):
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_multi_set_leaves_from_bytes(self._m, index, leaves_le, len(leaves_le) // 32, byref(err)), err)
+
+    def atomic_operation(self, index, leaves, indices):
+        err = ffi.RlnString()
+        lb = b"".join(int(v).to_bytes(32, "little") for v in leaves)
+        arr = (ctypes.c_size_t * max(len(indices), 1))(*indices)
+        _check_int(ffi.lib().rlnb200_multi_atomic_operation(self._m, index, lb, len(leaves), arr, len(indices), byref(err)), err)
+
+    def reserve(self, max_batch):
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_multi_reserve(self._m, max_batch, byref(err)), err)
+
+    def prove_batch(self, witnesses_le, n: int, rs=None, out=None):
+        """n witness records → n proof records; `witnesses_le`, `rs`, `out` may be bytes or integer addresses of host buffers"""
+        rep = self.replica(0)
+        rec = rep.proof_record_len()
+        buf = out if out is not None else ctypes.create_string_buffer(rec * n)
+        err = ffi.RlnString()
+        as_ptr = lambda b: c_void_p(b) if isinstance(b, int) else b   # noqa: E731
+        _check_int(ffi.lib().rlnb200_multi_prove_batch(self._m, as_ptr(witnesses_le), n, as_ptr(rs) if rs is not None else None, as_ptr(buf), byref(err)), err)
+        return buf.raw if out is None else None
+
+    def verify_batch(self, proofs_le: bytes, n: int):
+        ok = ctypes.create_string_buffer(max(n, 1))
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_multi_verify_batch(self._m, proofs_le, n, ok, byref(err)), err)
+        return list(ok.raw[:n])
+
+    def last_shard_ms(self):
+        out = (ctypes.c_float * self.device_count())()
+        ffi.lib().rlnb200_multi_last_shard_ms(self._m, out)
+        return list(out)
 
 
 class G1Msm:
