@@ -440,6 +440,9 @@ uint64_t rlnb200_launch_count(void);
 /* CUDA-event timings (ms) of the last rlnb200_prove_batch_device call, in launch order: witness VM, QAP
  * (matvec + 6 NTTs), G1 table accumulate, G1 reduce, G2 accumulate, G2 reduce, assembly, proof values */
 void rlnb200_last_stage_ms(FFI_RLN_t *const *rln, float out[8]);
+/* how many device batches (= launches of each stage's kernels) the timings above are summed over: 1 after
+ * rlnb200_prove_batch_device up to the handle's maximum batch, ceil(n / 4096) after the record-based calls */
+uint32_t rlnb200_last_stage_batches(FFI_RLN_t *const *rln);
 /* selects the CUDA device used by subsequently created objects (call before ffi_rln_new) */
 int rlnb200_set_device(int device, RlnString *err);
 /* fixed-base table geometry: window bits c / windows K of the G1 and of the G2 tables, number of (non-infinity)
@@ -512,6 +515,10 @@ int rlnb200_msm_g1_device(RlnB200Msm_t *m, const void *d_bases, const void *d_sc
 /* raw kernels for parity tests (host buffers, canonical LE field elements) */
 int rlnb200_poseidon_hash(const uint8_t *inputs, int n_inputs /* 1..3 */, uint8_t *out32, RlnString *err);
 int rlnb200_hash_pairs(const uint8_t *pairs /* n*64 */, size_t n, uint8_t *out /* n*32 */, RlnString *err);
+/* count independent Poseidon hashes of n_inputs (1..3) values each in one launch (e.g. id commitments H(secret), rate
+ * commitments H(id_commitment, limit) of a whole membership set: rln/src/protocol/keygen.rs:20-30, rln/README.md) */
+int rlnb200_poseidon_hash_batch(const uint8_t *inputs /* count*n_inputs*32 */, int n_inputs, size_t count,
+                                uint8_t *out /* count*32 */, RlnString *err);
 /* op: 0 mul, 1 add, 2 sub, 3 portable mul, 4 inverse, 5 square, 6-8 single-reduction dot products ; field: 0 Fr, 1 Fq ; exercises the PTX field arithmetic */
 int rlnb200_field_op(int field, int op, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out, RlnString *err);
 /* measured Montgomery-product rate (products/s over all SMs, CUDA-event timed); < 0 on error */

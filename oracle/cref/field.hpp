@@ -128,37 +128,39 @@ struct Fp {
     Fp neg() const { return is_zero() ? *this : (zero() - *this); }
     Fp dbl() const { return *this + *this; }
 
-    Fp operator*(const Fp& o) const {  // CIOS Montgomery multiplication
-        const u64* a = v.l;
-        const u64* b = o.v.l;
-        const u64* m = P::MOD.l;
-        const u64 ninv = inv_neg();
-        u64 t[6] = {0, 0, 0, 0, 0, 0};
+    // Montgomery multiplication, the "no-carry" CIOS form ark-ff 0.5 selects for moduli whose top bit is clear (both BN254
+    // fields; ark-ff/src/fields/models/fp/montgomery_backend.rs `mul_assign`): the two carry chains of a row (a·b[i] and k·p)
+    // are interleaved and the running total never needs a fifth word.  Fully unrolled, −p⁻¹ mod 2^64 folded to a constant.
+    static constexpr u64 inv_neg_const() {
+        u64 p0 = P::MOD.l[0], x = 1;
+        for (int i = 0; i < 6; i++) x *= 2 - p0 * x;
+        return (u64)(0 - x);
+    }
+    Fp operator*(const Fp& o) const {
+        constexpr u64 NINV = inv_neg_const();
+        constexpr u64 m0 = P::MOD.l[0], m1 = P::MOD.l[1], m2 = P::MOD.l[2], m3 = P::MOD.l[3];
+        const u64 a0 = v.l[0], a1 = v.l[1], a2 = v.l[2], a3 = v.l[3];
+        u64 r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+#pragma GCC unroll 4
         for (int i = 0; i < 4; i++) {
-            u128 c = 0;
-            for (int j = 0; j < 4; j++) {
-                c += (u128)a[j] * b[i] + t[j];
-                t[j] = (u64)c;
-                c >>= 64;
-            }
-            c += t[4];
-            t[4] = (u64)c;
-            t[5] = (u64)(c >> 64);
-            u64 q = t[0] * ninv;
-            c = (u128)q * m[0] + t[0];
-            c >>= 64;
-            for (int j = 1; j < 4; j++) {
-                c += (u128)q * m[j] + t[j];
-                t[j - 1] = (u64)c;
-                c >>= 64;
-            }
-            c += t[4];
-            t[3] = (u64)c;
-            t[4] = t[5] + (u64)(c >> 64);
+            const u64 bi = o.v.l[i];
+            u128 c1 = (u128)a0 * bi + r0;
+            const u64 k = (u64)c1 * NINV;
+            u128 c2 = (u128)k * m0 + (u64)c1;
+            c1 = (u128)a1 * bi + r1 + (u64)(c1 >> 64);
+            c2 = (u128)k * m1 + (u64)c1 + (u64)(c2 >> 64);
+            r0 = (u64)c2;
+            c1 = (u128)a2 * bi + r2 + (u64)(c1 >> 64);
+            c2 = (u128)k * m2 + (u64)c1 + (u64)(c2 >> 64);
+            r1 = (u64)c2;
+            c1 = (u128)a3 * bi + r3 + (u64)(c1 >> 64);
+            c2 = (u128)k * m3 + (u64)c1 + (u64)(c2 >> 64);
+            r2 = (u64)c2;
+            r3 = (u64)(c1 >> 64) + (u64)(c2 >> 64);
         }
         Fp r;
-        r.v = {{t[0], t[1], t[2], t[3]}};
-        if (t[4] || u256_cmp(r.v, P::MOD) >= 0) u256_sub(r.v, r.v, P::MOD);
+        r.v = {{r0, r1, r2, r3}};
+        if (u256_cmp(r.v, P::MOD) >= 0) u256_sub(r.v, r.v, P::MOD);
         return r;
     }
     Fp sqr() const { return (*this) * (*this); }

@@ -43,6 +43,8 @@ def lib():
         L.orc_msm_g2.argtypes = [vp, vp, sz, vp, i32]
         L.orc_g1_mul_gen.argtypes = [vp, sz, vp, i32]
         L.orc_fr_dot.argtypes = [vp, vp, sz, vp, i32]
+        L.orc_bench_primitive.restype = ctypes.c_double
+        L.orc_bench_primitive.argtypes = [i32, i32]
         L.orc_ctx_g1_vec.restype = sz
         L.orc_ctx_g1_vec.argtypes = [vp, i32, vp]
         L.orc_ctx_g2_vec.restype = sz
@@ -202,6 +204,11 @@ def msm_g2(points_bytes, scalars_bytes, n, nthreads=1):
     out = ctypes.create_string_buffer(128)
     lib().orc_msm_g2(points_bytes, scalars_bytes, n, out, nthreads)
     return out.raw
+
+
+def bench_primitive(what, iters):
+    """single-thread ns per Fq product (what = 0) or per G1 mixed addition (what = 1) of this port"""
+    return lib().orc_bench_primitive(what, iters)
 
 
 def fr_dot(ks_bytes, ss_bytes, n, nthreads=1):

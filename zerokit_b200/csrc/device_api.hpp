@@ -53,6 +53,8 @@ struct InputSlots { u32 secret, limit, message_id, path, index, x, ext_null, dep
 void launch_proof_values(const uint8_t* d_inputs, InputSlots sl, size_t n, uint8_t* d_out, cudaStream_t s);
 // generic small helpers used by the FFI utilities (single-thread kernels)
 void launch_poseidon_n(const uint8_t* d_in_bytes, int n_inputs, uint8_t* d_out_bytes, cudaStream_t s);
+// count independent hashes of n_inputs (1…3) canonical values each, one thread per hash
+void launch_poseidon_batch(const uint8_t* d_in_bytes, int n_inputs, size_t count, uint8_t* d_out_bytes, cudaStream_t s);
 
 // ---- k_records.cu --------------------------------------------------------------------------
 // wire records on the device: rln_witness_to_bytes_le records → input slots (+ a "would be refused" flag per record),
@@ -83,6 +85,9 @@ struct CircuitDev {
 };
 // inputs: n × n_slots canonical bytes → vals [n_nodes][B] (Montgomery).  err[j] != 0 if node evaluation failed.
 void launch_witness(const CircuitDev& c, const uint8_t* d_inputs, Fr* d_vals, u32 B, u32* d_err, cudaStream_t s);
+// k_witness streams the schedule through shared memory in blocks of this many bundles: CircuitDev::n_bundles must be a multiple
+// of it (pad with empty records) and the schedule 128-byte aligned
+u32 vm_schedule_block_bundles();
 // wires: B × n_wires canonical 32-byte values (an externally calculated witness) → the same vals layout
 void launch_scatter_wires(const CircuitDev& c, const uint8_t* d_wires, Fr* d_vals, u32 B, u32* d_err, cudaStream_t s);
 // a,b,c [domain][B]; afterwards abuf holds h = a·b − c on the coset (natural order)
@@ -129,8 +134,6 @@ struct MsmWorkspace {
     G2XYZZ* sum_g2;   // [B]
     const MsmTask *tasks_g1, *tasks_g2;  // device arrays built from msm_make_tasks for this B
     u32 n_tasks_g1, n_tasks_g2;
-    u32 n_tasks_g1_no_h;   // the first n tasks (groups A, B1, L) are launched before waiting for h_ready; = n_tasks_g1 when not split
-    cudaEvent_t h_ready;   // optional: recorded when the QAP has written h (the H tasks wait for it)
     cudaEvent_t* ev;  // optional: 6 events recorded around [g1 accum, g1 reduce, g2 accum, g2 reduce, assemble]
 };
 // MSM phases: all bases (full proof), the known prefix of A/B₁/B₂/L (partial proof), or the unknown suffix plus H (finish)

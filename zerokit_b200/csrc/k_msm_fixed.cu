@@ -427,17 +427,11 @@ __global__ void __launch_bounds__(64) k_assemble_g2(ProverKeyDev pk, const G2Aff
 }
 
 // ------------------------------------------------------------------------------------------- host orchestration
-static int accum_variant(const char* name) {
-    const char* v = getenv(name);
-    return v && *v ? atoi(v) : 0;
-}
 // bases per task.  A thread walks `chunk` bases for one proof, a CTA carries 128 proofs, and the CTAs of one launch run in
 // waves of (SMs × resident CTAs): long CTAs in few waves leave part of the chip idle at the end of the launch, short CTAs in
 // many waves cost more partial sums for k_msm_reduce.  Measured at batch 4 096: G1 10 → 24 waves −1.5 % (reduce +0.75 ms);
 // G2 is flat between 8 and 24 waves because its reduce (Fq2 additions) grows as fast as the tail shrinks.
 static u32 pick_chunk(u32 total_bases, u32 B, bool g2) {
-    const int forced = accum_variant(g2 ? "RLN_B200_CHUNK_G2" : "RLN_B200_CHUNK_G1");
-    if (forced > 0) return (u32)forced;
     const u64 ctas_per_task = (B + 127) / 128;
     const u64 per_wave = 148ull * (g2 ? 2 : 4);
     u64 want_tasks = ((g2 ? 12 : 24) * per_wave + ctas_per_task - 1) / ctas_per_task;   // tasks for ~24 (G1) / ~12 (G2) waves
@@ -485,24 +479,17 @@ void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, 
             b.tasks = ws.tasks_g1 + first;
             b.part = ws.part_g1 + (size_t)first * B;
             dim3 grid((B + bx - 1) / bx, count);
-            if (plan.glv) {   // 4 CTAs/SM measured 1.8 % faster than 3 (profiles/README.md)
-                if (accum_variant("RLN_B200_G1_VARIANT") == 1) k_msm_accum<Fq, true, 3, true><<<grid, bx, 0, s>>>(b);
-                else k_msm_accum<Fq, true, 4, true><<<grid, bx, 0, s>>>(b);
-            } else switch (accum_variant("RLN_B200_G1_VARIANT")) {
-                case 1: k_msm_accum<Fq, true, 4><<<grid, bx, 0, s>>>(b); break;
-                case 2: k_msm_accum<Fq, false, 4><<<grid, bx, 0, s>>>(b); break;
-                case 3: k_msm_accum<Fq, false, 3><<<grid, bx, 0, s>>>(b); break;
-                default: k_msm_accum<Fq, true, 3><<<grid, bx, 0, s>>>(b); break;
-            }
+            // prefetch of the next table entry on, 4 CTAs/SM: measured 1.8 % faster than 3 CTAs/SM, the other variants slower still
+            // (round 1 A/B)
+            if (plan.glv) k_msm_accum<Fq, true, 4, true><<<grid, bx, 0, s>>>(b);
+            else k_msm_accum<Fq, true, 3><<<grid, bx, 0, s>>>(b);
         };
-        const u32 first_part = ws.h_ready && ws.n_tasks_g1_no_h < ws.n_tasks_g1 ? ws.n_tasks_g1_no_h : ws.n_tasks_g1;
-        launch_g1(0, first_part);
-        if (ws.h_ready) ZK_CUDA_CHECK(cudaStreamWaitEvent(s, ws.h_ready, 0));
-        launch_g1(first_part, ws.n_tasks_g1 - first_part);
+        launch_g1(0, ws.n_tasks_g1);
         if (ws.ev) cudaEventRecord(ws.ev[1], s);
         // one CTA per (proof, group) with a shared-memory tree whenever there are many partials per proof: a thread-per-proof loop
         // over hundreds of partials leaves the chip idle (4 096 threads)
-        const bool tree = B < 64 || accum_variant("RLN_B200_REDUCE_TREE") == 1;
+        // of hundreds of partials leaves the chip idle; at batch 4 096 the tree is slower (G1 1.27 → 2.15 ms, round 1 A/B)
+        const bool tree = B < 64;
         if (tree) k_msm_reduce_small<Fq><<<dim3(B, 4), 128, 0, s>>>(ws.part_g1, ws.tasks_g1, ws.n_tasks_g1, B, ws.sum_g1);
         else k_msm_reduce<Fq><<<dim3((B + bx - 1) / bx, 4), bx, 0, s>>>(ws.part_g1, ws.tasks_g1, ws.n_tasks_g1, B, ws.sum_g1);
         if (ws.ev) cudaEventRecord(ws.ev[2], s);
@@ -514,18 +501,12 @@ void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, 
         a.tasks = ws.tasks_g2; a.part = ws.part_g2; a.B = B; a.c = plan.c2; a.K = plan.K2; a.glv = plan.glv;
         if (ws.n_tasks_g2) {
             dim3 grid((B + bx - 1) / bx, ws.n_tasks_g2);
-            if (plan.glv) {
-                if (accum_variant("RLN_B200_G2_VARIANT") == 1) k_msm_accum<Fq2, true, 2, true><<<grid, bx, 0, s>>>(a);
-                else k_msm_accum<Fq2, false, 2, true><<<grid, bx, 0, s>>>(a);
-            } else switch (accum_variant("RLN_B200_G2_VARIANT")) {
-                case 1: k_msm_accum<Fq2, true, 2><<<grid, bx, 0, s>>>(a); break;
-                case 2: k_msm_accum<Fq2, false, 3><<<grid, bx, 0, s>>>(a); break;
-                case 3: k_msm_accum<Fq2, true, 3><<<grid, bx, 0, s>>>(a); break;
-                default: k_msm_accum<Fq2, false, 2><<<grid, bx, 0, s>>>(a); break;   // no prefetch: the G2 kernel is register-bound
-            }
+            // no prefetch, 2 CTAs/SM: the G2 kernel is register-bound (prefetch −1.7 %, 3 CTAs/SM spills: −9 %; round 1 A/B)
+            if (plan.glv) k_msm_accum<Fq2, false, 2, true><<<grid, bx, 0, s>>>(a);
+            else k_msm_accum<Fq2, false, 2><<<grid, bx, 0, s>>>(a);
         }
         if (ws.ev) cudaEventRecord(ws.ev[3], s);
-        const bool tree = B < 64 || accum_variant("RLN_B200_REDUCE_TREE") == 1;
+        const bool tree = B < 64;
         if (tree) k_msm_reduce_small<Fq2><<<dim3(B, 1), 128, 0, s>>>(ws.part_g2, ws.tasks_g2, ws.n_tasks_g2, B, ws.sum_g2);
         else k_msm_reduce<Fq2><<<dim3((B + bx - 1) / bx, 1), bx, 0, s>>>(ws.part_g2, ws.tasks_g2, ws.n_tasks_g2, B, ws.sum_g2);
         if (ws.ev) cudaEventRecord(ws.ev[4], s);

@@ -38,12 +38,13 @@ struct VarMsmWorkspace {
     size_t phi_cap = 0;
 };
 
-// Experimental (RLN_B200_VARMSM_GLV=1: n ≤ 2^20, =2: every n; default 0, not yet measured): every scalar is split k = k₁ + k₂·λ with
-// |kᵢ| < 2^128 and the MSM runs over the 2n terms [Pᵢ | φ(Pᵢ)].  At small n the addition count stays (2¹⁶: 2¹⁷ × 12 windows of
-// c = 11 against 2¹⁶ × 26 of c = 10) while the Horner doublings — one thread's dependent chain, the floor of every small MSM —
-// and the bucket reductions halve.  At 2²² it would cost 9 windows instead of 8 per 128 bits, hence the size limit.
+// GLV in the variable-base MSM: every scalar is split k = k₁ + k₂·λ with |kᵢ| < 2^128 and the MSM runs over the 2n terms [Pᵢ | φ(Pᵢ)].
+// At small n the addition count stays (2¹⁶: 2¹⁷ × 12 windows of c = 11 against 2¹⁶ × 26 of c = 10) while the Horner doublings — one
+// thread's dependent chain, the floor of every small MSM — and the bucket reductions halve; at 2²² it would cost 9 windows instead of
+// 8 per 128 bits.  Measured on a B200 (profiles/r02a_flags.txt): 2¹⁶ 3.03 → 2.50 ms, 2¹⁸ 3.94 → 3.11, 2²⁰ 6.40 → 5.01, unchanged above.
+// RLN_B200_VARMSM_GLV: 1 (default) = for n ≤ 2²⁰, 0 = never, 2 = always.
 static int var_msm_glv_mode() {
-    static const int m = [] { const char* v = getenv("RLN_B200_VARMSM_GLV"); return v && *v ? atoi(v) : 0; }();
+    static const int m = [] { const char* v = getenv("RLN_B200_VARMSM_GLV"); return v && *v ? atoi(v) : 1; }();
     return m;
 }
 static bool var_msm_use_glv(size_t n) { return var_msm_glv_mode() == 2 || (var_msm_glv_mode() == 1 && n <= ((size_t)1 << 20)); }

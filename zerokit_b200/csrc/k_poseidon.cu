@@ -261,5 +261,21 @@ __global__ void k_poseidon_n(const uint8_t* in, int n, uint8_t* out) {
 void launch_poseidon_n(const uint8_t* d_in_bytes, int n_inputs, uint8_t* d_out_bytes, cudaStream_t s) {
     k_poseidon_n<<<1, 1, 0, s>>>(d_in_bytes, n_inputs, d_out_bytes);
 }
+// count independent hashes of n inputs each (canonical bytes in and out), one thread per hash
+__global__ void __launch_bounds__(128) k_poseidon_batch(const uint8_t* in, int n, size_t count, uint8_t* out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint8_t* p = in + 32 * (size_t)n * i;
+    Fr r;
+    if (n == 1) r = d_hash1(load_canonical(p));
+    else if (n == 2) r = d_hash2(load_canonical(p), load_canonical(p + 32));
+    else r = d_hash3(load_canonical(p), load_canonical(p + 32), load_canonical(p + 64));
+    store_canonical(out + 32 * i, r);
+}
+void launch_poseidon_batch(const uint8_t* d_in_bytes, int n_inputs, size_t count, uint8_t* d_out_bytes, cudaStream_t s) {
+    if (!count) return;
+    k_poseidon_batch<<<(unsigned)((count + 127) / 128), 128, 0, s>>>(d_in_bytes, n_inputs, count, d_out_bytes);
+    ZK_CUDA_CHECK(cudaGetLastError());
+}
 
 }  // namespace zk

@@ -439,6 +439,7 @@ class Rln {
     const std::vector<uint8_t>& partial_mask() const { return mask_; }  // one byte per wire 1..n_wires-1 (1 = known)
     void decompress_partial(const uint8_t comp[160], uint8_t affine[320]);
     void witness_slots(const Witness& w, uint8_t* slots) const;
+    void check_witness_shape(const Witness& w) const;
     void debug_w_h(const Witness& w, uint8_t* w_out, uint8_t* h_out);
     void table_info(int* c, int* K, uint64_t* g1, uint64_t* g2, uint64_t* bytes, int* c2, int* K2) const {
         *c = plan_.c; *K = plan_.K; *c2 = plan_.c2; *K2 = plan_.K2;
@@ -474,7 +475,6 @@ class Rln {
     }
     std::vector<uint8_t> metadata;   // set_metadata / get_metadata (rln/src/public.rs:499-515): opaque bytes kept beside the tree
     void sync() { ZK_CUDA_CHECK(cudaStreamSynchronize(stream_)); }   // flush: nothing is buffered outside HBM
-    bool overlap_qap_ = false;
     const uint8_t* ext_wires_ = nullptr;   // device pointer: B × n_wires canonical values that replace the graph evaluation
     // generate_rln_proof_with_witness (rln/src/public.rs:643-658): wires = n_wires × 32 canonical bytes calculated by the caller
     void prove_with_wires(const Witness& w, const std::vector<uint8_t>& wires, const uint8_t* rs, RlnProof& out) {
@@ -497,6 +497,7 @@ class Rln {
     void verify_batch(const uint8_t* proofs128, const uint8_t* publics_circuit_order, size_t n, uint8_t* ok);
     // witness, qap, g1 accumulate, g1 reduce, g2 accumulate, g2 reduce, assemble, proof values
     float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    u32 last_chunks = 1;   // device batches (kernel launches per stage) the stage_ms above are summed over
     std::mutex mu;
     // concurrent single-item calls on one handle are run as batches (coalesce.hpp; RLN_B200_COALESCE=1)
     struct ProveReq { const Witness* w; const uint8_t* rs; RlnProof out; std::string err; bool failed = false; bool done = false; };
@@ -509,7 +510,6 @@ class Rln {
     struct TaskSet {
         DevMem g1, g2;
         u32 n1 = 0, n2 = 0;
-        u32 n1_no_h = 0;   // leading G1 tasks that do not read h (groups A, B1, L): they can start before the QAP finishes
     };
     TaskSet& tasks_for(u32 B, int phase);
     void compute_known_mask();
@@ -548,8 +548,8 @@ class Rln {
     std::map<u64, std::unique_ptr<TaskSet>> tasks_;
     std::vector<uint8_t> wire_known_, mask_;
     DevMem ws_partial_, ws_partial_comp_, ws_bad_, ws_recs_in_, ws_recs_out_, ws_rs_all_;
-    cudaStream_t stream_ = nullptr, side_ = nullptr, qap_stream_ = nullptr;
-    cudaEvent_t fork_ = nullptr, join_ = nullptr, qap_done_ = nullptr, qev_[2] = {nullptr, nullptr};
+    cudaStream_t stream_ = nullptr, side_ = nullptr;
+    cudaEvent_t fork_ = nullptr, join_ = nullptr;
     cudaEvent_t ev_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t mev_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     void destroy_handles();
@@ -614,14 +614,6 @@ Rln::Rln(size_t tree_depth, const uint8_t* zkey, size_t zlen, const uint8_t* gra
     try {
         ZK_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
         ZK_CUDA_CHECK(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
-        {   // a high-priority stream for the optional QAP / MSM overlap (measured slower, DESIGN §7b: opt-in)
-            int lo = 0, hi = 0;
-            ZK_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-            ZK_CUDA_CHECK(cudaStreamCreateWithPriority(&qap_stream_, cudaStreamNonBlocking, hi));
-            overlap_qap_ = env_int("RLN_B200_OVERLAP_QAP", 0) != 0;
-            ZK_CUDA_CHECK(cudaEventCreateWithFlags(&qap_done_, cudaEventDisableTiming));
-            for (auto& e : qev_) ZK_CUDA_CHECK(cudaEventCreate(&e));
-        }
         ZK_CUDA_CHECK(cudaEventCreateWithFlags(&fork_, cudaEventDisableTiming));
         ZK_CUDA_CHECK(cudaEventCreateWithFlags(&join_, cudaEventDisableTiming));
         for (auto& e : ev_) ZK_CUDA_CHECK(cudaEventCreate(&e));
@@ -637,9 +629,8 @@ Rln::Rln(size_t tree_depth, const uint8_t* zkey, size_t zlen, const uint8_t* gra
 void Rln::destroy_handles() {
     for (auto& e : ev_) if (e) { cudaEventDestroy(e); e = nullptr; }
     for (auto& e : mev_) if (e) { cudaEventDestroy(e); e = nullptr; }
-    for (auto& e : qev_) if (e) { cudaEventDestroy(e); e = nullptr; }
-    for (cudaEvent_t* e : {&qap_done_, &fork_, &join_}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
-    for (cudaStream_t* st : {&stream_, &side_, &qap_stream_}) if (*st) { cudaStreamDestroy(*st); *st = nullptr; }
+    for (cudaEvent_t* e : {&fork_, &join_}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
+    for (cudaStream_t* st : {&stream_, &side_}) if (*st) { cudaStreamDestroy(*st); *st = nullptr; }
 }
 Rln::~Rln() {
     int prev = -1;
@@ -795,6 +786,14 @@ void Rln::build_circuit() {
     {   // list schedule for k_witness (host_util.hpp): bundles of 4 independent nodes, operand sources resolved (ring / const / global)
         uint32_t nb = 0;
         std::vector<VmRecord> recs = vm_build_schedule(gh_.prog, nb);
+        {   // whole blocks for the bulk copies of k_witness: pad with empty bundles
+            const uint32_t blk = vm_schedule_block_bundles();
+            nb = (nb + blk - 1) / blk * blk;
+            VmRecord empty;
+            memset(&empty, 0, sizeof empty);
+            empty.kind_op = 0xffffffffu;
+            recs.resize((size_t)nb * VM_SLOTS, empty);
+        }
         d_sched_.upload(recs.data(), recs.size() * sizeof(VmRecord));
         circ_.sched = d_sched_.as<uint4>();
         circ_.n_bundles = nb;
@@ -1139,8 +1138,6 @@ Rln::TaskSet& Rln::tasks_for(u32 B, int phase) {
     ts->g2.upload(t2.data(), t2.size() * sizeof(MsmTask));
     ts->n1 = (u32)t1.size();
     ts->n2 = (u32)t2.size();
-    for (const MsmTask& t : t1)
-        if (t.group != 3) ts->n1_no_h++;   // msm_make_tasks emits the groups in order, H (group 3) last
     TaskSet& ref = *ts;
     tasks_[key] = std::move(ts);
     return ref;
@@ -1205,16 +1202,8 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
         if (ext_wires_) launch_scatter_wires(circ_, ext_wires_, ws_vals_.as<Fr>(), B, ws_err_.as<u32>(), s);
         else launch_witness(circ_, in, ws_vals_.as<Fr>(), B, ws_err_.as<u32>(), s);
         ZK_CUDA_CHECK(cudaEventRecord(ev_[1], s));
-        const bool overlap_qap = phase != MSM_KNOWN && overlap_qap_;
-        if (overlap_qap) {   // h is only read by the H tasks: the A / B1 / L tasks start right after the witness
-            ZK_CUDA_CHECK(cudaStreamWaitEvent(qap_stream_, ev_[1], 0));
-            ZK_CUDA_CHECK(cudaEventRecord(qev_[0], qap_stream_));
-            launch_qap(circ_, ws_vals_.as<Fr>(), ws_a_.as<Fr>(), ws_b_.as<Fr>(), ws_c_.as<Fr>(), B, qap_stream_);
-            ZK_CUDA_CHECK(cudaEventRecord(qev_[1], qap_stream_));
-            ZK_CUDA_CHECK(cudaEventRecord(qap_done_, qap_stream_));
-        } else if (phase != MSM_KNOWN) {
-            launch_qap(circ_, ws_vals_.as<Fr>(), ws_a_.as<Fr>(), ws_b_.as<Fr>(), ws_c_.as<Fr>(), B, s);
-        }
+        // (running the QAP on a side stream beside the A / B1 / L accumulate tasks was measured slower, DESIGN §7b, and removed)
+        if (phase != MSM_KNOWN) launch_qap(circ_, ws_vals_.as<Fr>(), ws_a_.as<Fr>(), ws_b_.as<Fr>(), ws_c_.as<Fr>(), B, s);
         ZK_CUDA_CHECK(cudaEventRecord(ev_[2], s));
         MsmWorkspace mw;
         mw.part_g1 = ws_part1_.as<G1XYZZ>();
@@ -1226,8 +1215,6 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
         mw.n_tasks_g1 = ts.n1;
         mw.n_tasks_g2 = ts.n2;
         mw.ev = mev_;
-        mw.n_tasks_g1_no_h = overlap_qap ? ts.n1_no_h : ts.n1;
-        mw.h_ready = overlap_qap ? qap_done_ : nullptr;
         launch_msm_sums(plan_, ws_vals_.as<Fr>(), ws_a_.as<Fr>(), B, mw, s);
         if (phase == MSM_KNOWN) {
             launch_partial_out(pk_, B, mw, d_partial_affine + 320 * off, d_partial_comp + 160 * off, s);
@@ -1239,8 +1226,7 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
         ZK_CUDA_CHECK(cudaEventRecord(ev_[3], s));
         if (d_values && phase != MSM_KNOWN) ZK_CUDA_CHECK(cudaStreamWaitEvent(s, join_, 0));
         ZK_CUDA_CHECK(cudaEventRecord(ev_[4], s));
-        g_launch_count += 1 + (phase != MSM_KNOWN ? 2 + 3 * (2 * ntt_launches_per_transform(log_domain_) + 1) : 0) + 6 + (d_values ? 1 : 0) +
-                          (overlap_qap && ts.n1_no_h && ts.n1_no_h < ts.n1 ? 1 : 0);
+        g_launch_count += 1 + (phase != MSM_KNOWN ? 2 + 3 * (2 * ntt_launches_per_transform(log_domain_) + 1) : 0) + 6 + (d_values ? 1 : 0);
         // graph-evaluation failures surface as errors, like WitnessCalcError::GraphEvaluation (rln/src/circuit/iden3calc.rs:52-53)
         std::vector<u32> err(B);
         ZK_CUDA_CHECK(cudaMemcpyAsync(err.data(), ws_err_.p, 4 * B, cudaMemcpyDeviceToHost, s));
@@ -1248,8 +1234,8 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
         {
             float ms = 0;
             cudaEventElapsedTime(&ms, ev_[0], ev_[1]); acc[0] += ms;
-            if (overlap_qap) cudaEventElapsedTime(&ms, qev_[0], qev_[1]); else cudaEventElapsedTime(&ms, ev_[1], ev_[2]);
-            acc[1] += ms;   // with the overlap this is the QAP's own duration on its stream, hidden behind the first G1 tasks
+            cudaEventElapsedTime(&ms, ev_[1], ev_[2]);
+            acc[1] += ms;
             for (int i = 0; i < 5; i++) { cudaEventElapsedTime(&ms, mev_[i], mev_[i + 1]); acc[2 + i] += ms; }
             cudaEventElapsedTime(&ms, ev_[3], ev_[4]); acc[7] += ms;
         }
@@ -1292,30 +1278,33 @@ void Rln::witness_slots(const Witness& w, uint8_t* slots) const {  // iden3calc.
     memcpy(slots + 32 * slots_.ext_null, w.ext_null, 32);
 }
 
+// validate_witness_against_graph (proof.rs:644-700)
+void Rln::check_witness_shape(const Witness& w) const {
+    if (w.multi != multi_)
+        throw RlnError(std::string("Protocol error: Witness message mode ") + (w.multi ? "MultiV1" : "SingleV1") + " does not match graph mode " +
+                       (multi_ ? "MultiV1" : "SingleV1"));
+    if (w.k() != max_out_) {
+        std::ostringstream s;
+        s << "Protocol error: The field message_ids has length " << w.k() << ", but the field max_out has length " << max_out_;
+        throw RlnError(s.str());
+    }
+    if (w.path.size() / 32 != depth_) {
+        std::ostringstream s;
+        s << "Protocol error: The field path_elements has length " << w.path.size() / 32 << ", but the field tree_depth has length " << depth_;
+        throw RlnError(s.str());
+    }
+    if (w.index.size() != depth_) {
+        std::ostringstream s;
+        s << "Protocol error: The field identity_path_index has length " << w.index.size() << ", but the field tree_depth has length " << depth_;
+        throw RlnError(s.str());
+    }
+}
+
 void Rln::prove_host(const std::vector<Witness>& wsv, const uint8_t* rs, std::vector<RlnProof>& out, const PartialProofHost* partials) {
     const size_t n = wsv.size();
     out.resize(n);
     if (!n) return;
-    for (const Witness& w : wsv) {  // validate_witness_against_graph (proof.rs:644-700)
-        if (w.multi != multi_)
-            throw RlnError(std::string("Protocol error: Witness message mode ") + (w.multi ? "MultiV1" : "SingleV1") + " does not match graph mode " +
-                           (multi_ ? "MultiV1" : "SingleV1"));
-        if (w.k() != max_out_) {
-            std::ostringstream s;
-            s << "Protocol error: The field message_ids has length " << w.k() << ", but the field max_out has length " << max_out_;
-            throw RlnError(s.str());
-        }
-        if (w.path.size() / 32 != depth_) {
-            std::ostringstream s;
-            s << "Protocol error: The field path_elements has length " << w.path.size() / 32 << ", but the field tree_depth has length " << depth_;
-            throw RlnError(s.str());
-        }
-        if (w.index.size() != depth_) {
-            std::ostringstream s;
-            s << "Protocol error: The field identity_path_index has length " << w.index.size() << ", but the field tree_depth has length " << depth_;
-            throw RlnError(s.str());
-        }
-    }
+    for (const Witness& w : wsv) check_witness_shape(w);
     const size_t chunk = n < max_batch_ ? n : max_batch_;
     reserve(chunk);
     const size_t vs = values_stride(), k = max_out_;
@@ -1389,6 +1378,8 @@ void Rln::prove_records_device(const uint8_t* d_records, const uint8_t* d_rs, si
     ws_bad_.ensure(4 * cap_);
     std::vector<u32> bad(cap_);
     std::vector<uint8_t> rsb;
+    float acc_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    u32 n_chunks = 0;
     struct Scrub {   // secrets never outlive the call, whichever way it ends (reference: IdSecret zeroises on drop)
         Rln& r; cudaStream_t s;
         ~Scrub() { cudaMemsetAsync(r.ws_inputs_.p, 0, r.ws_inputs_.bytes, s); cudaStreamSynchronize(s); }
@@ -1429,11 +1420,15 @@ void Rln::prove_records_device(const uint8_t* d_records, const uint8_t* d_rs, si
             }
         }
         prove_device(ws_inputs_.as<uint8_t>(), rs_dev, B, ws_proofs_.as<uint8_t>(), ws_values_.as<uint8_t>(), nullptr, s);
+        for (int i = 0; i < 8; i++) acc_ms[i] += stage_ms[i];
+        n_chunks++;
         launch_proof_records(ws_proofs_.as<uint8_t>(), ws_values_.as<uint8_t>(), ws_inputs_.as<uint8_t>(), B, L, d_out + off * (size_t)L.proof_rec_len, s);
         g_launch_count++;
     }
     ZK_CUDA_CHECK(cudaStreamSynchronize(s));
     if (!rsb.empty()) memset(rsb.data(), 0, rsb.size());
+    for (int i = 0; i < 8; i++) stage_ms[i] = acc_ms[i];   // the whole call, summed over its device batches
+    last_chunks = n_chunks;
 }
 
 void Rln::prove_records_host(const uint8_t* records, const uint8_t* rs, size_t n, uint8_t* out) {
@@ -1557,6 +1552,11 @@ void Rln::verify_batch(const uint8_t* proofs128, const uint8_t* publics, size_t 
 using namespace zk;
 
 struct FFI_RLN { std::unique_ptr<Rln> r; };
+// copies of a caller's witness are zeroised when they go out of scope, on every path (IdSecret's Drop: rln/src/utils.rs:443-527)
+struct WitnessWipe {
+    std::vector<Witness>& v;
+    ~WitnessWipe() { for (Witness& w : v) memset(w.secret, 0, 32); }
+};
 // the handle's mutex + its device made current on the calling thread (one handle, many threads, several devices)
 struct RlnLock {
     std::lock_guard<std::mutex> lk;
@@ -1830,17 +1830,18 @@ void ffi_rln_witness_input_free(FFI_RLNWitnessInput_t* w) {
 }
 
 // ---- proving / verifying ----------------------------------------------------------------------
-// Experimental, off by default until it has run on a GPU: see coalesce.hpp
+// Concurrent single-item calls on one handle are run as device batches (coalesce.hpp).  Measured on a B200 with 16 caller threads
+// (profiles/r02a_coalesce.txt): 28 → 158 proofs/s.  RLN_B200_COALESCE=0 puts every call back behind the handle's mutex.
 static bool coalesce_enabled() {
-    static const bool on = env_int("RLN_B200_COALESCE", 0) != 0;
+    static const bool on = env_int("RLN_B200_COALESCE", 1) != 0;
     return on;
 }
 static void prove_alone(Rln& R, Rln::ProveReq* q) {   // caller holds R.mu
     try {
         std::vector<Witness> ws(1, *q->w);
+        struct Wipe { std::vector<Witness>& v; ~Wipe() { for (Witness& w : v) memset(w.secret, 0, 32); } } wipe{ws};
         std::vector<RlnProof> out;
         R.prove_host(ws, q->rs, out);
-        memset(ws[0].secret, 0, 32);
         q->out = out[0];
     } catch (const CudaError& e) { q->failed = true; q->err = describe(e); }
     catch (const std::exception& e) { q->failed = true; q->err = describe(e); }
@@ -1848,21 +1849,36 @@ static void prove_alone(Rln& R, Rln::ProveReq* q) {   // caller holds R.mu
 static void run_prove_batch(Rln& R, std::vector<Rln::ProveReq*>& b) {
     RlnLock lk(R);
     if (b.size() == 1) { prove_alone(R, b[0]); return; }
+    // the cheap host-side checks of prove_host, per request: a caller with a witness of the wrong mode / shape fails alone and
+    // never reaches the device batch
+    std::vector<Rln::ProveReq*> good;
+    good.reserve(b.size());
+    for (Rln::ProveReq* q : b) {
+        try {
+            R.check_witness_shape(*q->w);
+            good.push_back(q);
+        } catch (const std::exception& e) { q->failed = true; q->err = describe(e); }
+    }
+    if (good.empty()) return;
+    std::vector<Witness> ws;
+    struct Wipe { std::vector<Witness>& v; ~Wipe() { for (Witness& w : v) memset(w.secret, 0, 32); } } wipe{ws};
     try {
-        std::vector<Witness> ws;
-        ws.reserve(b.size());
-        std::vector<uint8_t> rs(64 * b.size());
-        for (size_t i = 0; i < b.size(); i++) {
-            ws.push_back(*b[i]->w);
-            if (b[i]->rs) memcpy(&rs[64 * i], b[i]->rs, 64);
+        ws.reserve(good.size());
+        std::vector<uint8_t> rs(64 * good.size());
+        for (size_t i = 0; i < good.size(); i++) {
+            ws.push_back(*good[i]->w);
+            if (good[i]->rs) memcpy(&rs[64 * i], good[i]->rs, 64);
             else { random_fr(&rs[64 * i]); random_fr(&rs[64 * i + 32]); }   // r, s ← rng (proof.rs:743-745)
         }
         std::vector<RlnProof> out;
         R.prove_host(ws, rs.data(), out);
-        for (Witness& w : ws) memset(w.secret, 0, 32);
-        for (size_t i = 0; i < b.size(); i++) b[i]->out = out[i];
-    } catch (...) {   // one request of the batch is at fault: run them one by one so each caller gets its own result or error
-        for (Rln::ProveReq* q : b) prove_alone(R, q);
+        for (size_t i = 0; i < good.size(); i++) good[i]->out = out[i];
+    } catch (const CudaError& e) {   // a device failure is not one request's fault and is not retried: every request of the batch reports it
+        for (Rln::ProveReq* q : good) { q->failed = true; q->err = describe(e); }
+    } catch (const std::exception&) {
+        // a graph-evaluation failure of some item (the only per-item failure left): each request once more on its own, so that
+        // only the offending callers see an error.  Bounded: a batch holds at most max_batch requests of concurrent callers.
+        for (Rln::ProveReq* q : good) prove_alone(R, q);
     }
 }
 static void run_pairing_batch(Rln& R, std::vector<Rln::PairingReq*>& b) {
@@ -1907,9 +1923,9 @@ static CResult_FFI_RLNProof_t prove_one(FFI_RLN_t* const* rln, FFI_RLNWitnessInp
     }
     RlnLock lk(*(*rln)->r);
     std::vector<Witness> ws(1, (*witness)->w);
+    WitnessWipe wipe{ws};
     std::vector<RlnProof> out;
     (*rln)->r->prove_host(ws, rs, out);
-    memset(ws[0].secret, 0, 32);
     auto p = std::make_unique<FFI_RLNProof>();
     p->p = out[0];
     return CResult_FFI_RLNProof_t{p.release(), no_string()};
@@ -1953,6 +1969,7 @@ CResult_FFI_RLNPartialProof_t ffi_generate_partial_zk_proof(FFI_RLN_t* const* rl
     GUARD_BEGIN
     RlnLock lk(*(*rln)->r);
     std::vector<Witness> ws(1, (*partial_witness)->w);
+    WitnessWipe wipe{ws};
     ws[0].multi = (*rln)->r->multi();   // a partial witness carries no message ids: shape them for the circuit at hand
     ws[0].mids.assign(32 * (*rln)->r->max_out(), 0);
     ws[0].sel.assign(ws[0].multi ? (*rln)->r->max_out() : 0, 0);
@@ -1971,9 +1988,9 @@ static CResult_FFI_RLNProof_t finish_one(FFI_RLN_t* const* rln, FFI_RLNPartialPr
     RlnLock lk(*(*rln)->r);
     if ((*partial)->mask != (*rln)->r->partial_mask()) throw RlnError("Protocol error: Error producing proof: malformed verifying key");
     std::vector<Witness> ws(1, (*witness)->w);
+    WitnessWipe wipe{ws};
     std::vector<RlnProof> out;
     (*rln)->r->prove_host(ws, rs, out, &(*partial)->p);
-    memset(ws[0].secret, 0, 32);
     auto p = std::make_unique<FFI_RLNProof>();
     p->p = out[0];
     return CResult_FFI_RLNProof_t{p.release(), no_string()};
@@ -2349,6 +2366,7 @@ uint64_t rlnb200_launch_count(void) { return g_launch_count.load(); }
 void rlnb200_last_stage_ms(FFI_RLN_t* const* rln, float out[8]) {
     for (int i = 0; i < 8; i++) out[i] = (*rln)->r->stage_ms[i];
 }
+uint32_t rlnb200_last_stage_batches(FFI_RLN_t* const* rln) { return (*rln)->r->last_chunks; }
 int rlnb200_set_device(int device, RlnString* err) {
     INT_OP(ZK_CUDA_CHECK(cudaSetDevice(device));)
 }
@@ -2576,6 +2594,12 @@ int rlnb200_msm_g1(RlnB200Msm_t* m, const uint8_t* bases, const uint8_t* scalars
 int rlnb200_poseidon_hash(const uint8_t* inputs, int n_inputs, uint8_t* out32, RlnString* err) {
     INT_OP(if (n_inputs < 1 || n_inputs > 3) throw RlnError("Input length must be valid with supported round parameters");
            device_poseidon(inputs, n_inputs, out32);)
+}
+int rlnb200_poseidon_hash_batch(const uint8_t* inputs, int n_inputs, size_t count, uint8_t* out, RlnString* err) {
+    INT_OP(if (n_inputs < 1 || n_inputs > 3) throw RlnError("Input length must be valid with supported round parameters");
+           global_init(); DevMem in, res; in.upload(inputs, 32 * (size_t)n_inputs * count); res.alloc(32 * count);
+           launch_poseidon_batch(in.as<uint8_t>(), n_inputs, count, res.as<uint8_t>(), 0); g_launch_count++;
+           ZK_CUDA_CHECK(cudaMemcpy(out, res.p, 32 * count, cudaMemcpyDeviceToHost));)
 }
 int rlnb200_hash_pairs(const uint8_t* pairs, size_t n, uint8_t* out, RlnString* err) {
     INT_OP(global_init(); DevMem raw, in, res, outb; raw.upload(pairs, 64 * n); in.alloc(sizeof(Fr) * 2 * n); res.alloc(sizeof(Fr) * n); outb.alloc(32 * n);

@@ -312,6 +312,7 @@ def lib():
         "rlnb200_reserve": (c_int, [pp, c_size_t, POINTER(RlnString)]),
         "rlnb200_launch_count": (c_uint64, []),
         "rlnb200_last_stage_ms": (None, [pp, POINTER(c_float)]),
+        "rlnb200_last_stage_batches": (c_uint32, [pp]),
         "rlnb200_set_device": (c_int, [c_int, POINTER(RlnString)]),
         "rlnb200_table_info": (c_int, [pp, POINTER(c_int), POINTER(c_int), POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint64), POINTER(c_int), POINTER(c_int)]),
         "rlnb200_set_leaves_from_bytes": (c_int, [pp, c_size_t, c_void_p, c_size_t, POINTER(RlnString)]),
@@ -325,6 +326,7 @@ def lib():
         "rlnb200_msm_g1_device": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, POINTER(RlnString)]),
         "rlnb200_poseidon_hash": (c_int, [c_void_p, c_int, c_void_p, POINTER(RlnString)]),
         "rlnb200_hash_pairs": (c_int, [c_void_p, c_size_t, c_void_p, POINTER(RlnString)]),
+        "rlnb200_poseidon_hash_batch": (c_int, [c_void_p, c_int, c_size_t, c_void_p, POINTER(RlnString)]),
         "rlnb200_field_op": (c_int, [c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p, POINTER(RlnString)]),
         "rlnb200_debug_witness_and_h": (c_int, [pp, c_void_p, c_size_t, c_void_p, c_void_p, POINTER(RlnString)]),
         "rlnb200_num_wires": (c_size_t, [pp]),

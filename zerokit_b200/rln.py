@@ -673,12 +673,15 @@ class RLN:
         """public.rs:750-771"""
         return _check_bool(ffi.lib().ffi_verify_with_roots(byref(self._h), byref(proof._h), byref(_vec_cfr(roots)), byref(_cfr(x))))
 
-    def prove_batch(self, witnesses_le: bytes, n: int, rs: bytes = None) -> bytes:
-        """n witness records (rln_witness_to_bytes_le) → n rln_proof_to_bytes_le records (290 bytes each in single mode)"""
-        out = ctypes.create_string_buffer(self.proof_record_len() * n)
+    def prove_batch(self, witnesses_le, n: int, rs=None, out=None):
+        """n witness records (rln_witness_to_bytes_le) → n rln_proof_to_bytes_le records (290 bytes each in single mode).
+        `witnesses_le`, `rs`, `out` may be bytes-like or integer addresses of host buffers (e.g. pinned tensors); with `out` given
+        the records are written there and nothing is returned"""
+        buf = out if out is not None else ctypes.create_string_buffer(self.proof_record_len() * n)
         err = ffi.RlnString()
-        _check_int(ffi.lib().rlnb200_prove_batch(byref(self._h), witnesses_le, n, rs, out, byref(err)), err)
-        return out.raw
+        as_ptr = lambda b: c_void_p(b) if isinstance(b, int) else b   # noqa: E731
+        _check_int(ffi.lib().rlnb200_prove_batch(byref(self._h), as_ptr(witnesses_le), n, as_ptr(rs) if rs is not None else None, as_ptr(buf), byref(err)), err)
+        return buf.raw if out is None else None
 
     def verify_batch(self, proofs_le: bytes, n: int):
         ok = ctypes.create_string_buffer(max(n, 1))
@@ -730,6 +733,9 @@ class RLN:
         out = (ctypes.c_float * 8)()
         ffi.lib().rlnb200_last_stage_ms(byref(self._h), out)
         return dict(zip(("witness", "qap", "msm_g1_accum", "msm_g1_reduce", "msm_g2_accum", "msm_g2_reduce", "assemble", "values"), list(out)))
+
+    def last_stage_batches(self):
+        return ffi.lib().rlnb200_last_stage_batches(byref(self._h))
 
     def table_info(self):
         c, k, c2, k2 = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
@@ -897,6 +903,14 @@ def glv_double_mul(items, use_q=True):
         x, y = int.from_bytes(out.raw[64 * i:64 * i + 32], "little"), int.from_bytes(out.raw[64 * i + 32:64 * i + 64], "little")
         res.append(None if x == 0 and y == 0 else (x, y))
     return res
+
+
+def poseidon_hash_batch(inputs_bytes, n_inputs, count):
+    """count independent Poseidon hashes of n_inputs canonical values each (one launch) → count × 32 bytes"""
+    out = ctypes.create_string_buffer(32 * count)
+    err = ffi.RlnString()
+    _check_int(ffi.lib().rlnb200_poseidon_hash_batch(inputs_bytes, n_inputs, count, out, byref(err)), err)
+    return out.raw
 
 
 def hash_pairs(pairs_bytes, n):
