@@ -177,3 +177,18 @@ int emu_vm_duo(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     return ok ? 1 : 0;
 }
 }
+
+// tree configuration parser (host_util.hpp parse_tree_config ↔ rln/src/pm_tree_adapter.rs:139-174)
+extern "C" int emu_parse_tree_config(const char* json, char* path_out, size_t path_cap, uint64_t* nums /* temporary, has_path, cache, flush_ms, low_space,
+                                     compression, has_depth, depth */, char* err_out, size_t err_cap) {
+    try {
+        TreeConfig c = parse_tree_config(json);
+        snprintf(path_out, path_cap, "%s", c.path.c_str());
+        nums[0] = c.temporary; nums[1] = c.has_path; nums[2] = c.cache_capacity; nums[3] = c.flush_every_ms; nums[4] = c.low_space;
+        nums[5] = c.use_compression; nums[6] = c.has_depth; nums[7] = c.tree_depth;
+        return 0;
+    } catch (const std::exception& e) {
+        snprintf(err_out, err_cap, "%s", e.what());
+        return 1;
+    }
+}

@@ -901,3 +901,70 @@ def test_multi_device_in_process(z, oracle):
     multi.atomic_operation(n, [5, 6], [0])
     assert len({multi.replica(i).get_root() for i in range(ndev)}) == 1 and multi.replica(ndev - 1).leaves_set() == r0.leaves_set()
     del multi
+
+
+def test_tree_persistence(z, oracle, tmp_path):
+    """rln/tests/pm_tree.rs:108-131 (test_pmtree_multiple_reopen) and :433-452 (test_pmtree_persistence) through the C ABI: a handle
+    opened with a persistent tree configuration (JSON file named by config_path: rln/src/ffi/ffi_rln.rs:24-46, pm_tree_adapter.rs:139-174)
+    writes its tree on flush / drop; the next handle on the same path comes back with the same root, paths, leaves_set and metadata"""
+    import json
+    db = tmp_path / "tree.db"
+    cfg = tmp_path / "config.json"
+    cfg.write_text(json.dumps({"path": str(db), "temporary": False, "cache_capacity": 1 << 20, "flush_every_ms": 100, "mode": "HighThroughput",
+                               "use_compression": False, "tree_depth": 10}))
+    fs = fr_stream(808)
+    leaves = [next(fs) for _ in range(300)]
+    t1 = z.RLN.new(10, str(cfg))
+    t1.set_next_leaf(42)
+    t1.set_leaves_from(1, leaves)
+    t1.delete_leaf(7)
+    t1.atomic_operation(301, [9, 8], [300])
+    root1, n1 = t1.get_root(), t1.leaves_set()
+    path1 = t1.get_merkle_proof(123)
+    t1.set_metadata(b"test metadata")
+    t1.flush()
+    del t1
+    t2 = z.RLN.new(10, str(cfg))
+    assert t2.get_root() == root1 and t2.leaves_set() == n1 and t2.get_metadata() == b"test metadata"
+    assert t2.get_leaf(0) == 42 and t2.get_leaf(5) == leaves[4] and t2.get_leaf(7) == 0 and t2.get_merkle_proof(123) == path1
+    # after a reload the "is set" flags are recomputed from the leaves (pm_tree_adapter.rs:224-233): the empty ones are exactly the zero leaves
+    assert t2.get_empty_leaves_indices() == [i for i in range(n1) if t2.get_leaf(i) == 0]
+    exp = [t2.get_leaf(i) for i in range(n1)]
+    assert root1 == int.from_bytes(oracle.merkle_build(10, fr_bytes(exp), 0, n1)[:32], "little")
+    # second generation: more writes, dropped WITHOUT an explicit flush (sled flushes when the tree is dropped)
+    t2.set_next_leaf(77)
+    root2 = t2.get_root()
+    del t2
+    t3 = z.RLN.new(10, str(cfg))
+    assert t3.get_root() == root2 and t3.leaves_set() == n1 + 1 and t3.get_leaf(n1) == 77 and t3.get_metadata() == b"test metadata"
+    # set_tree replaces the tree by a temporary default one (rln/src/public.rs:298-303): the store keeps the old state
+    t3.set_tree(10)
+    t3.set_next_leaf(5)
+    del t3
+    t4 = z.RLN.new(10, str(cfg))
+    assert t4.get_root() == root2
+    del t4
+    # configuration rules (resolve_path, pm_tree_adapter.rs:93-100, and the depth checks :194-208)
+    bad = tmp_path / "bad.json"
+    bad.write_text(json.dumps({"temporary": False}))
+    with pytest.raises(z.RLNError, match="Configuration error: Error while creating pmtree config: missing path"):
+        z.RLN.new(10, str(bad))
+    bad.write_text(json.dumps({"path": str(db), "temporary": True}))
+    with pytest.raises(z.RLNError, match="path already exists"):
+        z.RLN.new(10, str(bad))
+    bad.write_text(json.dumps({"path": str(db), "temporary": False, "tree_depth": 12}))
+    with pytest.raises(z.RLNError, match="Tree depth"):
+        z.RLN.new(10, str(bad))
+    bad.write_text('{"path": ')
+    with pytest.raises(z.RLNError, match="Configuration error: Error while reading pmtree config"):
+        z.RLN.new(10, str(bad))
+    # a damaged store is refused, not silently replaced
+    f = db / "rlnb200_tree.bin"
+    raw = bytearray(f.read_bytes())
+    raw[60] ^= 1
+    f.write_bytes(bytes(raw))
+    with pytest.raises(z.RLNError, match="Cannot load database: checksum mismatch"):
+        z.RLN.new(10, str(cfg))
+    # a missing config file means the default (temporary) configuration (ffi_rln.rs:28-45)
+    t5 = z.RLN.new(10, str(tmp_path / "nope.json"))
+    assert t5.leaves_set() == 0

@@ -229,3 +229,28 @@ def test_vm_ops(emu):
                 assert ok == 0, (op, a, b)
             else:
                 assert ok == 1 and int.from_bytes(out.raw, "little") == exp, (G.OP_NAMES[op], a, b)
+
+
+def test_tree_config_parser(emu):
+    """the JSON tree configuration of rln/src/pm_tree_adapter.rs:139-174: every key optional, wrong-typed values fall back to the
+    default (serde_json's as_str / as_bool / as_u64 return None), unknown keys ignored, syntax errors reported"""
+    def parse(text):
+        path, err = ctypes.create_string_buffer(512), ctypes.create_string_buffer(512)
+        nums = (ctypes.c_uint64 * 8)()
+        rc = emu.emu_parse_tree_config(text.encode(), path, 512, nums, err, 512)
+        if rc:
+            raise ValueError(err.value.decode())
+        keys = ("temporary", "has_path", "cache_capacity", "flush_every_ms", "low_space", "use_compression", "has_depth", "tree_depth")
+        return dict(zip(keys, list(nums)), path=path.value.decode())
+    d = parse("{}")
+    assert d == dict(temporary=1, has_path=0, cache_capacity=1073741824, flush_every_ms=500, low_space=0, use_compression=0, has_depth=0, tree_depth=0, path="")
+    d = parse('{"path": "/tmp/x y/\\"db\\"", "temporary": false, "cache_capacity": 12345, "flush_every_ms": 7, "mode": "LowSpace",'
+              ' "use_compression": true, "tree_depth": 20, "extra": {"a": [1, 2, {"b": "}"}]}}')
+    assert d == dict(temporary=0, has_path=1, cache_capacity=12345, flush_every_ms=7, low_space=1, use_compression=1, has_depth=1, tree_depth=20,
+                     path='/tmp/x y/"db"')
+    d = parse('{"path": 5, "temporary": "no", "cache_capacity": -3, "flush_every_ms": 1.5, "mode": "Other", "tree_depth": null}')
+    assert d["has_path"] == 0 and d["temporary"] == 1 and d["cache_capacity"] == 1073741824 and d["flush_every_ms"] == 500 and d["low_space"] == 0 and d["has_depth"] == 0
+    assert parse(' [1, 2] ')["temporary"] == 1          # not an object: every key reads as null
+    for bad in ('{"path": "x"', '{"path" "x"}', '{"a": 1,}', '{} x', '', '{"path": "unterminated}'):
+        with pytest.raises(ValueError, match="Error while reading pmtree config"):
+            parse(bad)

@@ -467,4 +467,130 @@ inline std::vector<VmRecord> vm_build_schedule(const std::vector<VmInstr>& prog,
     return recs;
 }
 
+// ------------------------------------------------------------------------------------------- tree configuration (PmTreeConfig)
+// The JSON the reference accepts for its default tree (rln/src/pm_tree_adapter.rs:139-174 `impl FromStr for PmTreeConfig`):
+//   { "path": "...", "temporary": bool, "cache_capacity": u64, "flush_every_ms": u64, "mode": "HighThroughput" | "LowSpace",
+//     "use_compression": bool, "tree_depth": u64 }      every key optional, unknown keys ignored (serde_json::Value indexing)
+// and its path rules (`resolve_path`, :93-100).  cache_capacity / flush_every_ms / mode / use_compression tune sled; they are
+// parsed, kept and otherwise meaningless for a tree that lives in HBM.
+struct TreeConfig {
+    bool has_path = false;
+    std::string path;
+    bool temporary = true;
+    uint64_t cache_capacity = 1073741824ull, flush_every_ms = 500;
+    bool low_space = false, use_compression = false;
+    bool has_depth = false;
+    uint64_t tree_depth = 0;
+    bool persistent() const { return !temporary && has_path; }
+};
+struct JsonCursor {
+    const char* p;
+    const char* end;
+    void ws() { while (p < end && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) p++; }
+    [[noreturn]] void fail(const char* what) const { throw std::runtime_error(std::string("Error while reading pmtree config: ") + what); }
+    std::string string() {
+        if (p >= end || *p != '"') fail("expected a string");
+        p++;
+        std::string out;
+        while (p < end && *p != '"') {
+            if (*p == '\\') {
+                if (++p >= end) fail("EOF while parsing a string");
+                switch (*p) {
+                    case 'n': out += '\n'; break;
+                    case 't': out += '\t'; break;
+                    case 'r': out += '\r'; break;
+                    case 'b': out += '\b'; break;
+                    case 'f': out += '\f'; break;
+                    case 'u': {   // \uXXXX: paths are ASCII in practice; keep the low byte of BMP code points below 0x80, reject the rest
+                        if (end - p < 5) fail("EOF while parsing a string");
+                        unsigned v = 0;
+                        for (int i = 1; i <= 4; i++) {
+                            const char c = p[i];
+                            v = v * 16 + (c >= '0' && c <= '9' ? c - '0' : c >= 'a' && c <= 'f' ? c - 'a' + 10 : c >= 'A' && c <= 'F' ? c - 'A' + 10 : 256);
+                        }
+                        if (v >= 0x80) fail("unsupported escape in a string");
+                        out += (char)v;
+                        p += 4;
+                        break;
+                    }
+                    default: out += *p;
+                }
+                p++;
+            } else out += *p++;
+        }
+        if (p >= end) fail("EOF while parsing a string");
+        p++;
+        return out;
+    }
+    void skip_value() {   // any JSON value; nesting by bracket counting (strings skipped properly)
+        ws();
+        if (p >= end) fail("EOF while parsing a value");
+        if (*p == '"') { string(); return; }
+        if (*p == '{' || *p == '[') {
+            int depth = 0;
+            do {
+                if (p >= end) fail("EOF while parsing a value");
+                if (*p == '"') { string(); continue; }
+                if (*p == '{' || *p == '[') depth++;
+                if (*p == '}' || *p == ']') depth--;
+                p++;
+            } while (depth > 0);
+            return;
+        }
+        while (p < end && *p != ',' && *p != '}' && *p != ']' && *p != ' ' && *p != '\n' && *p != '\t' && *p != '\r') p++;
+    }
+};
+inline TreeConfig parse_tree_config(const std::string& json) {
+    TreeConfig c;
+    JsonCursor j{json.data(), json.data() + json.size()};
+    j.ws();
+    if (j.p >= j.end) j.fail("EOF while parsing a value");
+    if (*j.p != '{') {   // serde_json::Value indexing on a non-object yields Null for every key: all defaults, after a syntax check
+        j.skip_value();
+        j.ws();
+        if (j.p != j.end) j.fail("trailing characters");
+        return c;
+    }
+    j.p++;
+    j.ws();
+    if (j.p < j.end && *j.p == '}') { j.p++; j.ws(); if (j.p != j.end) j.fail("trailing characters"); return c; }
+    for (;;) {
+        j.ws();
+        const std::string key = j.string();
+        j.ws();
+        if (j.p >= j.end || *j.p != ':') j.fail("expected `:`");
+        j.p++;
+        j.ws();
+        const char* v0 = j.p;
+        auto is_lit = [&](const char* lit) { const size_t n = strlen(lit); return (size_t)(j.end - v0) >= n && !memcmp(v0, lit, n); };
+        auto as_u64 = [&](uint64_t& out) -> bool {   // as_u64(): non-negative integers only
+            const char* q = v0;
+            if (q >= j.end || *q < '0' || *q > '9') return false;
+            uint64_t v = 0;
+            while (q < j.end && *q >= '0' && *q <= '9') { v = v * 10 + (uint64_t)(*q - '0'); q++; }
+            if (q < j.end && (*q == '.' || *q == 'e' || *q == 'E')) return false;
+            out = v;
+            return true;
+        };
+        if (key == "path" && j.p < j.end && *j.p == '"') { c.path = j.string(); c.has_path = true; }
+        else if (key == "mode" && j.p < j.end && *j.p == '"') { c.low_space = j.string() == "LowSpace"; }
+        else {
+            uint64_t u = 0;
+            if (key == "temporary") { if (is_lit("true")) c.temporary = true; else if (is_lit("false")) c.temporary = false; }
+            else if (key == "use_compression") { if (is_lit("true")) c.use_compression = true; else if (is_lit("false")) c.use_compression = false; }
+            else if (key == "cache_capacity") { if (as_u64(u)) c.cache_capacity = u; }
+            else if (key == "flush_every_ms") { if (as_u64(u)) c.flush_every_ms = u; }
+            else if (key == "tree_depth") { if (as_u64(u)) { c.tree_depth = u; c.has_depth = true; } }
+            j.skip_value();
+        }
+        j.ws();
+        if (j.p < j.end && *j.p == ',') { j.p++; continue; }
+        if (j.p < j.end && *j.p == '}') { j.p++; break; }
+        j.fail("expected `,` or `}`");
+    }
+    j.ws();
+    if (j.p != j.end) j.fail("trailing characters");
+    return c;
+}
+
 }  // namespace zk
