@@ -357,9 +357,9 @@ def test_empty_and_full_capacity(z, rln10, oracle):
     assert rln10.get_root() == int.from_bytes(nodes[:32], "little") and rln10.leaves_set() == 1024
     e, b = rln10.get_merkle_proof(1023)
     assert (e, b) == oracle.merkle_proof_from_nodes(nodes, 10, 1023)
-    with pytest.raises(z.RLNError, match="Leaf index out of bounds"):
-        rln10.set_next_leaf(5)   # tree is full
-    with pytest.raises(z.RLNError, match="Leaf index out of bounds"):
+    with pytest.raises(z.RLNError, match="Pmtree error: Tree error: Index out of bounds"):
+        rln10.set_next_leaf(5)   # tree is full: pmtree's `set` refuses key == capacity
+    with pytest.raises(z.RLNError, match="Pmtree error: Tree error: Index out of bounds"):
         rln10.get_merkle_proof(1024)
     rln10.set_tree(10)
 

@@ -135,6 +135,8 @@ struct MsmWorkspace {
     const MsmTask *tasks_g1, *tasks_g2;  // device arrays built from msm_make_tasks for this B
     u32 n_tasks_g1, n_tasks_g2;
     cudaEvent_t* ev;  // optional: 6 events recorded around [g1 accum, g1 reduce, g2 accum, g2 reduce, assemble]
+    cudaStream_t side = nullptr;                          // optional second stream + two events: the G2 assembly runs beside the G1 assembly
+    cudaEvent_t side_fork = nullptr, side_join = nullptr;
 };
 // MSM phases: all bases (full proof), the known prefix of A/B₁/B₂/L (partial proof), or the unknown suffix plus H (finish)
 enum MsmPhase { MSM_FULL = 0, MSM_KNOWN = 1, MSM_UNKNOWN = 2 };

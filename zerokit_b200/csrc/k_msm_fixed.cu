@@ -147,13 +147,26 @@ struct AccumArgs {
     u32 B;
     int c, K;
     int glv;                     // G1 only: tasks come in (k₁, k₂) pairs, MsmTask::half selects which
+    // Small batches (B < 32, e.g. a single proof): a warp whose lanes are 32 consecutive proofs would run with 1 … 31 lanes idle
+    // while still paying every IMAD.WIDE's 4 pipe cycles.  Packed, the lanes of a CTA are consecutive (task, proof) pairs, proof
+    // fastest over 2^pack_log ≥ B slots: at B = 1 a warp carries 32 tasks (measured at B = 1, G1: 2.2 → see profiles/README.md).
+    u32 packed, pack_log, n_tasks;
 };
 
 template <class F, bool PREFETCH, int MIN_BLOCKS, bool GLV = false>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_msm_accum(AccumArgs<F> a) {
-    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 j, task;
+    if (a.packed) {
+        const u32 slot = blockIdx.y * blockDim.x + threadIdx.x;
+        j = slot & ((1u << a.pack_log) - 1);
+        task = slot >> a.pack_log;
+        if (task >= a.n_tasks) return;
+    } else {
+        j = blockIdx.x * blockDim.x + threadIdx.x;
+        task = blockIdx.y;
+    }
     if (j >= a.B) return;
-    const MsmTask t = a.tasks[blockIdx.y];
+    const MsmTask t = a.tasks[task];
     const u32* __restrict__ rows = a.row[t.group];
     const Affine<F>* __restrict__ table = a.table[t.group];
     const Fr* __restrict__ src = a.src[a.which[t.group]];
@@ -208,7 +221,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_msm_accum(AccumArgs<F> a) {
             if (cur_valid) acc.add_affine(cur);
         }
     }
-    a.part[(size_t)blockIdx.y * a.B + j] = acc;
+    a.part[(size_t)task * a.B + j] = acc;
 }
 
 // partial sum of a task; the k₂ half of a GLV pair goes through φ: (X, Y, ZZ, ZZZ) ↦ (β·X, Y, ZZ, ZZZ)
@@ -465,8 +478,24 @@ std::vector<MsmTask> msm_make_tasks(const FixedMsmPlan& plan, u32 B, bool g2, in
 }
 
 
+// grid of an accumulate launch over `count` tasks: one CTA row per task for full warps of proofs, packed (task, proof) lanes below 32
+template <class F>
+static dim3 accum_grid(AccumArgs<F>& a, u32 B, u32 bx, u32 count) {
+    a.n_tasks = count;
+    a.packed = B < 32 ? 1 : 0;
+    a.pack_log = 0;
+    if (!a.packed) return dim3((B + bx - 1) / bx, count);
+    while ((1u << a.pack_log) < B) a.pack_log++;
+    const u64 slots = (u64)count << a.pack_log;
+    return dim3(1, (unsigned)((slots + bx - 1) / bx));
+}
+// thread-per-proof loop over a group's partial sums, or one CTA per (proof, group) with a shared-memory tree?  The loop costs
+// ≈ 2.8 µs per partial (G1), the tree ≈ 2.2 ms whatever B is (the number of partials, tasks × B, is roughly constant by
+// construction of pick_chunk): measured B = 256: loop 21.1 ms (7 890 tasks) / B = 4 096: loop 1.27 ms, tree 2.15 ms (447 tasks).
+static bool reduce_by_tree(u32 B, u32 n_tasks, bool g2) { return B < 64 || n_tasks > (g2 ? 400u : 700u); }
+
 void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, u32 B, MsmWorkspace& ws, cudaStream_t s) {
-    const u32 bx = B >= 128 ? 128 : 32;
+    const u32 bx = B >= 128 || B < 32 ? 128 : 32;
     {   // G1: A, B1, L, H
         AccumArgs<Fq> a;
         a.src[0] = d_vals; a.src[1] = d_h;
@@ -478,7 +507,7 @@ void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, 
             AccumArgs<Fq> b = a;
             b.tasks = ws.tasks_g1 + first;
             b.part = ws.part_g1 + (size_t)first * B;
-            dim3 grid((B + bx - 1) / bx, count);
+            const dim3 grid = accum_grid(b, B, bx, count);
             // prefetch of the next table entry on, 4 CTAs/SM: measured 1.8 % faster than 3 CTAs/SM, the other variants slower still
             // (round 1 A/B)
             if (plan.glv) k_msm_accum<Fq, true, 4, true><<<grid, bx, 0, s>>>(b);
@@ -489,9 +518,9 @@ void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, 
         // one CTA per (proof, group) with a shared-memory tree whenever there are many partials per proof: a thread-per-proof loop
         // over hundreds of partials leaves the chip idle (4 096 threads)
         // of hundreds of partials leaves the chip idle; at batch 4 096 the tree is slower (G1 1.27 → 2.15 ms, round 1 A/B)
-        const bool tree = B < 64;
-        if (tree) k_msm_reduce_small<Fq><<<dim3(B, 4), 128, 0, s>>>(ws.part_g1, ws.tasks_g1, ws.n_tasks_g1, B, ws.sum_g1);
-        else k_msm_reduce<Fq><<<dim3((B + bx - 1) / bx, 4), bx, 0, s>>>(ws.part_g1, ws.tasks_g1, ws.n_tasks_g1, B, ws.sum_g1);
+        const u32 rx = B >= 128 ? 128 : 32;
+        if (reduce_by_tree(B, ws.n_tasks_g1, false)) k_msm_reduce_small<Fq><<<dim3(B, 4), 128, 0, s>>>(ws.part_g1, ws.tasks_g1, ws.n_tasks_g1, B, ws.sum_g1);
+        else k_msm_reduce<Fq><<<dim3((B + rx - 1) / rx, 4), rx, 0, s>>>(ws.part_g1, ws.tasks_g1, ws.n_tasks_g1, B, ws.sum_g1);
         if (ws.ev) cudaEventRecord(ws.ev[2], s);
     }
     {   // G2: B2
@@ -500,23 +529,34 @@ void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, 
         for (int i = 0; i < 4; i++) { a.row[i] = plan.g2.row; a.table[i] = (const G2Affine*)plan.g2.table; a.which[i] = plan.g2.which_src; }
         a.tasks = ws.tasks_g2; a.part = ws.part_g2; a.B = B; a.c = plan.c2; a.K = plan.K2; a.glv = plan.glv;
         if (ws.n_tasks_g2) {
-            dim3 grid((B + bx - 1) / bx, ws.n_tasks_g2);
+            const dim3 grid = accum_grid(a, B, bx, ws.n_tasks_g2);
             // no prefetch, 2 CTAs/SM: the G2 kernel is register-bound (prefetch −1.7 %, 3 CTAs/SM spills: −9 %; round 1 A/B)
             if (plan.glv) k_msm_accum<Fq2, false, 2, true><<<grid, bx, 0, s>>>(a);
             else k_msm_accum<Fq2, false, 2><<<grid, bx, 0, s>>>(a);
         }
         if (ws.ev) cudaEventRecord(ws.ev[3], s);
-        const bool tree = B < 64;
-        if (tree) k_msm_reduce_small<Fq2><<<dim3(B, 1), 128, 0, s>>>(ws.part_g2, ws.tasks_g2, ws.n_tasks_g2, B, ws.sum_g2);
-        else k_msm_reduce<Fq2><<<dim3((B + bx - 1) / bx, 1), bx, 0, s>>>(ws.part_g2, ws.tasks_g2, ws.n_tasks_g2, B, ws.sum_g2);
+        const u32 rx = B >= 128 ? 128 : 32;
+        if (reduce_by_tree(B, ws.n_tasks_g2, true)) k_msm_reduce_small<Fq2><<<dim3(B, 1), 128, 0, s>>>(ws.part_g2, ws.tasks_g2, ws.n_tasks_g2, B, ws.sum_g2);
+        else k_msm_reduce<Fq2><<<dim3((B + rx - 1) / rx, 1), rx, 0, s>>>(ws.part_g2, ws.tasks_g2, ws.n_tasks_g2, B, ws.sum_g2);
         if (ws.ev) cudaEventRecord(ws.ev[4], s);
     }
 }
 
 void launch_assemble(const FixedMsmPlan& plan, const ProverKeyDev& pk, u32 B, const uint8_t* d_rs, MsmWorkspace& ws,
                      const uint8_t* d_partial, uint8_t* d_proofs_out, uint8_t* d_proofs_affine, cudaStream_t s) {
-    k_assemble_g1<<<(B + 63) / 64, 64, 0, s>>>(pk, plan.delta1_table, plan.cd, plan.Kd, ws.sum_g1, B, d_rs, d_partial, d_proofs_out, d_proofs_affine);
-    k_assemble_g2<<<(B + 63) / 64, 64, 0, s>>>(pk, plan.delta2_table, plan.cd2, plan.Kd2, ws.sum_g2, B, d_rs, d_partial, d_proofs_out, d_proofs_affine);
+    // π_b (G2) does not depend on π_a / π_c (G1) and both are latency-bound chains of one thread per proof: side by side when the
+    // caller lends a second stream (they write disjoint bytes of every proof)
+    if (ws.side) {
+        ZK_CUDA_CHECK(cudaEventRecord(ws.side_fork, s));
+        ZK_CUDA_CHECK(cudaStreamWaitEvent(ws.side, ws.side_fork, 0));
+        k_assemble_g2<<<(B + 63) / 64, 64, 0, ws.side>>>(pk, plan.delta2_table, plan.cd2, plan.Kd2, ws.sum_g2, B, d_rs, d_partial, d_proofs_out, d_proofs_affine);
+        ZK_CUDA_CHECK(cudaEventRecord(ws.side_join, ws.side));
+        k_assemble_g1<<<(B + 63) / 64, 64, 0, s>>>(pk, plan.delta1_table, plan.cd, plan.Kd, ws.sum_g1, B, d_rs, d_partial, d_proofs_out, d_proofs_affine);
+        ZK_CUDA_CHECK(cudaStreamWaitEvent(s, ws.side_join, 0));
+    } else {
+        k_assemble_g1<<<(B + 63) / 64, 64, 0, s>>>(pk, plan.delta1_table, plan.cd, plan.Kd, ws.sum_g1, B, d_rs, d_partial, d_proofs_out, d_proofs_affine);
+        k_assemble_g2<<<(B + 63) / 64, 64, 0, s>>>(pk, plan.delta2_table, plan.cd2, plan.Kd2, ws.sum_g2, B, d_rs, d_partial, d_proofs_out, d_proofs_affine);
+    }
     if (ws.ev) cudaEventRecord(ws.ev[5], s);
 }
 

@@ -32,10 +32,11 @@ __device__ __forceinline__ Fr load_canonical_fr(const uint8_t* p) {
 // slot w of every bundle for its 32 proofs, and a barrier separates bundles.  A value is written to vals[node][B] (the QAP and
 // the MSMs read it there) and to a shared-memory ring of the last VM_RING bundles; 77 % of all operands were produced less than
 // 16 bundles earlier and the other 23 % are constants, so the critical path never waits for L2.
+template <u32 STRIDE = 32>
 __device__ __forceinline__ Fr vm_operand(u32 enc, const uint4* ring, const Fr* __restrict__ consts, const Fr* vals, u32 B, u32 j, u32 lane) {
     const u32 src = enc >> 30, idx = enc & 0x3fffffffu;
     if (src == VM_SRC_RING) {
-        const uint4 lo = ring[(idx * 2) * 32 + lane], hi = ring[(idx * 2 + 1) * 32 + lane];
+        const uint4 lo = ring[(idx * 2) * STRIDE + lane], hi = ring[(idx * 2 + 1) * STRIDE + lane];
         Fr r;
         r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w;
         r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
@@ -84,16 +85,28 @@ static __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* g
                  : "memory");
 }
 
-__global__ void __launch_bounds__(128) k_witness(CircuitDev c, const uint8_t* __restrict__ inputs, Fr* vals, u32 B, u32* __restrict__ err) {
-    extern __shared__ __align__(128) uint4 ring[];   // [VM_RING · VM_SLOTS][2][32 lanes]: the two 16-byte halves of a value, lane-contiguous
-    uint4* stage = ring + VM_RING_BYTES / sizeof(uint4);                                   // [VM_STAGES][VM_STAGE_BUNDLES][VM_SLOTS][2]
+// Two mappings of (proof, slot) onto threads, same schedule, same ring, same staging:
+//   WARP = false: a CTA of four warps carries 32 proofs; warp w evaluates slot w, lane = proof; a CTA barrier separates bundles.
+//   WARP = true : ONE warp carries 8 proofs; lane = slot + 4·proof; __syncwarp separates bundles.  A product costs a warp the same
+//                 ≈ 520 pipe cycles whether 4 or 32 of its lanes are live, so both mappings spend the same issue slots per
+//                 proof, but the warp form pays no CTA barrier per bundle and a batch spreads over 4× as many warps: a single
+//                 proof (4 live lanes) and a batch of 4 096 (512 independent warps over 592 schedulers) both finish sooner.
+template <bool WARP>
+__global__ void __launch_bounds__(WARP ? 32 : 128) k_witness(CircuitDev c, const uint8_t* __restrict__ inputs, Fr* vals, u32 B, u32* __restrict__ err) {
+    constexpr u32 PROOFS = WARP ? 32 / VM_SLOTS : 32;                                        // proofs per CTA = ring stride
+    constexpr size_t RING_U4 = (size_t)VM_RING * VM_SLOTS * 2 * PROOFS;
+    extern __shared__ __align__(128) uint4 ring[];   // [VM_RING · VM_SLOTS][2][PROOFS]: the two 16-byte halves of a value, proof-contiguous
+    uint4* stage = ring + RING_U4;                                                          // [VM_STAGES][VM_STAGE_BUNDLES][VM_SLOTS][2]
     u64* full = reinterpret_cast<u64*>(stage + (size_t)VM_STAGES * VM_STAGE_BYTES / sizeof(uint4));
-    const u32 lane = threadIdx.x & 31, slot = threadIdx.x >> 5;
-    const u32 j = blockIdx.x * 32 + lane;
+    const u32 lane = threadIdx.x & 31;
+    const u32 slot = WARP ? (lane & (VM_SLOTS - 1)) : (threadIdx.x >> 5);
+    const u32 pl = WARP ? lane / VM_SLOTS : lane;                                            // proof within the CTA
+    const u32 j = blockIdx.x * PROOFS + pl;
     const bool live = j < B;
     const uint8_t* in = inputs + (size_t)(live ? j : 0) * c.n_slots * 32;
     const u32 n_blocks = c.n_bundles / VM_STAGE_BUNDLES;                                   // the host pads the schedule to whole blocks
     const uint8_t* sched = reinterpret_cast<const uint8_t*>(c.sched);
+    auto bundle_sync = [] { if (WARP) __syncwarp(); else __syncthreads(); };
     u32 bad = 0;
     if (threadIdx.x == 0) {
         for (u32 s = 0; s < VM_STAGES; s++) mbar_init(full + s, 1);
@@ -101,7 +114,7 @@ __global__ void __launch_bounds__(128) k_witness(CircuitDev c, const uint8_t* __
         for (u32 s = 0; s < VM_STAGES && s < n_blocks; s++)
             tma_load_1d(stage + (size_t)s * VM_STAGE_BYTES / sizeof(uint4), sched + (size_t)s * VM_STAGE_BYTES, VM_STAGE_BYTES, full + s);
     }
-    __syncthreads();
+    bundle_sync();
     for (u32 blk = 0; blk < n_blocks; blk++) {
         const u32 st = blk % VM_STAGES;
         mbar_wait(full + st, (blk / VM_STAGES) & 1);
@@ -109,12 +122,12 @@ __global__ void __launch_bounds__(128) k_witness(CircuitDev c, const uint8_t* __
 #pragma unroll 1
         for (u32 i = 0; i < VM_STAGE_BUNDLES; i++) {
             const u32 b = blk * VM_STAGE_BUNDLES + i;
-            const uint4 w0 = recs[2 * (i * VM_SLOTS + slot)];       // kind_op, out, a, b   (warp-uniform address: one broadcast load)
+            const uint4 w0 = recs[2 * (i * VM_SLOTS + slot)];       // kind_op, out, a, b   (one address per slot: broadcast loads)
             if (w0.x != 0xffffffffu && live) {
                 const u32 kind = w0.x & 0xff, op = w0.x >> 8;
                 Fr v;
                 if (kind == VM_DUO) {
-                    const Fr x = vm_operand(w0.z, ring, c.consts, vals, B, j, lane), y = vm_operand(w0.w, ring, c.consts, vals, B, j, lane);
+                    const Fr x = vm_operand<PROOFS>(w0.z, ring, c.consts, vals, B, j, pl), y = vm_operand<PROOFS>(w0.w, ring, c.consts, vals, B, j, pl);
                     if (op == OP_MUL) v = x * y;
                     else if (op == OP_ADD) v = x + y;
                     else if (op == OP_SUB) v = x - y;
@@ -124,21 +137,21 @@ __global__ void __launch_bounds__(128) k_witness(CircuitDev c, const uint8_t* __
                 } else if (kind == VM_INPUT) {
                     v = load_canonical_fr(in + 32 * w0.z);
                 } else if (kind == VM_UNO) {
-                    if (op == 0) v = vm_operand(w0.z, ring, c.consts, vals, B, j, lane).neg();
+                    if (op == 0) v = vm_operand<PROOFS>(w0.z, ring, c.consts, vals, B, j, pl).neg();
                     else { bad = 1; v = Fr::zero(); }  // "uno operator Id not implemented" (graph.rs:189-193)
                 } else {  // TernCond (graph.rs:216-222)
                     const u32 third = recs[2 * (i * VM_SLOTS + slot) + 1].x;
-                    const Fr t = vm_operand(w0.z, ring, c.consts, vals, B, j, lane);
-                    v = t.is_zero() ? vm_operand(third, ring, c.consts, vals, B, j, lane) : vm_operand(w0.w, ring, c.consts, vals, B, j, lane);
+                    const Fr t = vm_operand<PROOFS>(w0.z, ring, c.consts, vals, B, j, pl);
+                    v = t.is_zero() ? vm_operand<PROOFS>(third, ring, c.consts, vals, B, j, pl) : vm_operand<PROOFS>(w0.w, ring, c.consts, vals, B, j, pl);
                 }
                 const u32 ri = (b % VM_RING) * VM_SLOTS + slot;
-                ring[(ri * 2) * 32 + lane] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
-                ring[(ri * 2 + 1) * 32 + lane] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+                ring[(ri * 2) * PROOFS + pl] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+                ring[(ri * 2 + 1) * PROOFS + pl] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
                 st_fp(vals + (size_t)w0.y * B + j, v);
             }
-            __syncthreads();
+            bundle_sync();
         }
-        // every warp is past the last record of this block: its buffer takes the block VM_STAGES ahead
+        // every thread is past the last record of this block: its buffer takes the block VM_STAGES ahead
         if (threadIdx.x == 0 && blk + VM_STAGES < n_blocks)
             tma_load_1d(stage + (size_t)st * VM_STAGE_BYTES / sizeof(uint4), sched + (size_t)(blk + VM_STAGES) * VM_STAGE_BYTES, VM_STAGE_BYTES, full + st);
     }
@@ -146,9 +159,17 @@ __global__ void __launch_bounds__(128) k_witness(CircuitDev c, const uint8_t* __
 }
 void launch_witness(const CircuitDev& c, const uint8_t* d_inputs, Fr* d_vals, u32 B, u32* d_err, cudaStream_t s) {
     ZK_CUDA_CHECK(cudaMemsetAsync(d_err, 0, 4 * (size_t)B, s));
+    static const int mode = [] { const char* v = getenv("RLN_B200_WITNESS_WARP"); return v && *v ? atoi(v) : 1; }();   // A/B switch of round 2
     // the shared-memory attribute is per device (a process may drive several GPUs): set on every launch, it is a cheap call
-    ZK_CUDA_CHECK(cudaFuncSetAttribute(k_witness, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VM_SMEM_BYTES));
-    k_witness<<<(B + 31) / 32, 128, VM_SMEM_BYTES, s>>>(c, d_inputs, d_vals, B, d_err);
+    if (mode) {
+        constexpr u32 PW = 32 / VM_SLOTS;
+        constexpr size_t smem = (size_t)VM_RING * VM_SLOTS * 2 * PW * sizeof(uint4) + (size_t)VM_STAGES * VM_STAGE_BYTES + VM_STAGES * sizeof(u64);
+        ZK_CUDA_CHECK(cudaFuncSetAttribute(k_witness<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_witness<true><<<(B + PW - 1) / PW, 32, smem, s>>>(c, d_inputs, d_vals, B, d_err);
+    } else {
+        ZK_CUDA_CHECK(cudaFuncSetAttribute(k_witness<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VM_SMEM_BYTES));
+        k_witness<false><<<(B + 31) / 32, 128, VM_SMEM_BYTES, s>>>(c, d_inputs, d_vals, B, d_err);
+    }
     ZK_CUDA_CHECK(cudaGetLastError());
 }
 u32 vm_schedule_block_bundles() { return VM_STAGE_BUNDLES; }

@@ -569,8 +569,8 @@ class Rln {
     std::map<u64, std::unique_ptr<TaskSet>> tasks_;
     std::vector<uint8_t> wire_known_, mask_;
     DevMem ws_partial_, ws_partial_comp_, ws_bad_, ws_recs_in_, ws_recs_out_, ws_rs_all_;
-    cudaStream_t stream_ = nullptr, side_ = nullptr;
-    cudaEvent_t fork_ = nullptr, join_ = nullptr;
+    cudaStream_t stream_ = nullptr, side_ = nullptr, asm_side_ = nullptr;
+    cudaEvent_t fork_ = nullptr, join_ = nullptr, asm_fork_ = nullptr, asm_join_ = nullptr;
     cudaEvent_t ev_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t mev_[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     void destroy_handles();
@@ -635,8 +635,11 @@ Rln::Rln(size_t tree_depth, const uint8_t* zkey, size_t zlen, const uint8_t* gra
     try {
         ZK_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
         ZK_CUDA_CHECK(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
+        ZK_CUDA_CHECK(cudaStreamCreateWithFlags(&asm_side_, cudaStreamNonBlocking));
         ZK_CUDA_CHECK(cudaEventCreateWithFlags(&fork_, cudaEventDisableTiming));
         ZK_CUDA_CHECK(cudaEventCreateWithFlags(&join_, cudaEventDisableTiming));
+        ZK_CUDA_CHECK(cudaEventCreateWithFlags(&asm_fork_, cudaEventDisableTiming));
+        ZK_CUDA_CHECK(cudaEventCreateWithFlags(&asm_join_, cudaEventDisableTiming));
         for (auto& e : ev_) ZK_CUDA_CHECK(cudaEventCreate(&e));
         for (auto& e : mev_) ZK_CUDA_CHECK(cudaEventCreate(&e));
         build_circuit();
@@ -650,8 +653,8 @@ Rln::Rln(size_t tree_depth, const uint8_t* zkey, size_t zlen, const uint8_t* gra
 void Rln::destroy_handles() {
     for (auto& e : ev_) if (e) { cudaEventDestroy(e); e = nullptr; }
     for (auto& e : mev_) if (e) { cudaEventDestroy(e); e = nullptr; }
-    for (cudaEvent_t* e : {&fork_, &join_}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
-    for (cudaStream_t* st : {&stream_, &side_}) if (*st) { cudaStreamDestroy(*st); *st = nullptr; }
+    for (cudaEvent_t* e : {&fork_, &join_, &asm_fork_, &asm_join_}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
+    for (cudaStream_t* st : {&stream_, &side_, &asm_side_}) if (*st) { cudaStreamDestroy(*st); *st = nullptr; }
 }
 Rln::~Rln() {
     int prev = -1;
@@ -1320,6 +1323,9 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
         mw.n_tasks_g1 = ts.n1;
         mw.n_tasks_g2 = ts.n2;
         mw.ev = mev_;
+        mw.side = asm_side_;
+        mw.side_fork = asm_fork_;
+        mw.side_join = asm_join_;
         launch_msm_sums(plan_, ws_vals_.as<Fr>(), ws_a_.as<Fr>(), B, mw, s);
         if (phase == MSM_KNOWN) {
             launch_partial_out(pk_, B, mw, d_partial_affine + 320 * off, d_partial_comp + 160 * off, s);
