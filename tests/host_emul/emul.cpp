@@ -169,6 +169,51 @@ int emu_final_exp_consistency(const uint8_t* g1, const uint8_t* g2, int n) {
     bool frob_ok = frobenius1(&pt, frobenius1(&pt, g)) == frobenius2(&pt, g);
     return (one_chain == one_generic ? 1 : 0) | (a == b ? 2 : 0) | (frob_ok ? 4 : 0) | (one_chain ? 8 : 0);
 }
+// the verifier's fast paths against the plain ones (bit flags; all must be set):
+//  1  projective Miller loop == affine Miller loop after the final exponentiation
+//  2  mul_by_034 == dense product with the same line            4  mul_by_line_fq == dense product
+//  8  cyclotomic_sqr == sqr on an element of the cyclotomic subgroup
+// 16  the merged Groth16 loop == product of three separate loops after the final exponentiation
+int emu_pairing_fast_paths(const uint8_t* g1, const uint8_t* g2) {   // g1: 3 × 64 B (A, V, C), g2: 3 × 128 B (B, G, D)
+    static PairingTables pt; static bool init = false;
+    if (!init) { pairing_tables_init(pt); init = true; }
+    int flags = 0;
+    const G1Affine A = ld_g1(g1), V = ld_g1(g1 + 64), C = ld_g1(g1 + 128);
+    const G2Affine B = ld_g2(g2), G = ld_g2(g2 + 128), D = ld_g2(g2 + 256);
+    const Fq12 m_aff = miller_loop(&pt, B, A), m_proj = miller_loop_proj(&pt, B, A);
+    if (final_exponentiation(&pt, m_aff) == final_exponentiation(&pt, m_proj)) flags |= 1;
+    {   // sparse products on a dense, non-trivial element
+        const Fq12 f = m_aff;
+        const Fq2 l0 = B.x * B.y, l3 = B.y.sqr(), l4 = B.x.sqr();
+        Fq12 dense;
+        dense.c0 = {l0, Fq2::zero(), Fq2::zero()};
+        dense.c1 = {l3, l4, Fq2::zero()};
+        if (f.mul_by_034(l0, l3, l4) == f * dense) flags |= 2;
+        dense.c0 = {Fq2{A.y, Fq::zero()}, Fq2::zero(), Fq2::zero()};
+        if (f.mul_by_line_fq(A.y, l3, l4) == f * dense) flags |= 4;
+    }
+    {
+        Fq12 t = m_aff.conj() * m_aff.inv();
+        t = frobenius2(&pt, t) * t;   // easy part done: t is in the cyclotomic subgroup
+        if (t.cyclotomic_sqr() == t.sqr() && t.cyclotomic_sqr().cyclotomic_sqr() == t.sqr().sqr()) flags |= 8;
+    }
+    {
+        static FixedLines lg, ld_;
+        precompute_lines(&pt, G, lg);
+        precompute_lines(&pt, D, ld_);
+        const Fq12 merged = miller_loop_groth16(&pt, B, A, lg.lam, lg.c, V, ld_.lam, ld_.c, C);
+        const Fq12 separate = miller_loop(&pt, B, A) * miller_loop(&pt, G, V) * miller_loop(&pt, D, C);
+        if (final_exponentiation(&pt, merged) == final_exponentiation(&pt, separate)) flags |= 16;
+    }
+    return flags;
+}
+// both G2 membership tests on one twist point: bit 0 = ψ(P) = [6x²]P, bit 1 = the one-multiple test
+int emu_g2_subgroup_both(const uint8_t* p) {
+    static PairingTables pt; static bool init = false;
+    if (!init) { pairing_tables_init(pt); init = true; }
+    const G2Affine P = ld_g2(p);
+    return (g2_in_subgroup_6x2(&pt, P) ? 1 : 0) | (g2_in_subgroup(&pt, P) ? 2 : 0);
+}
 // witness-graph VM: one op on canonical values
 int emu_vm_duo(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     Fr r;

@@ -848,7 +848,7 @@ def test_records_device_path_and_refusals(z, rln10, oracle):
         (broken(2, 0, b"\x02"), "Unknown message mode version byte"),
         (broken(3, 0, b"\x01"), "record|Expected to read|mode"),
         (broken(4, 97, (d + 1).to_bytes(8, "little")), "Expected to read|shape of the circuit"),
-        (broken(6, 105 + 32 * d, (d - 1).to_bytes(8, "little")), "Merkle proof length mismatch|Expected to read|shape of the circuit"),
+        (broken(6, 105 + 32 * d, (d - 1).to_bytes(8, "little")), "witness record 6: "),   # a wrong index-length prefix shifts everything after it
     ]
     for bad, pattern in cases:
         with pytest.raises(z.RLNError, match=pattern):

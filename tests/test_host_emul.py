@@ -169,7 +169,16 @@ def test_g2_subgroup_check(emu):
         assert F.on_curve(F.OPS2, Pt)
         assert F.pt_add(F.OPS2, F.pt_mul(F.OPS2, Pt, R - 1), Pt) is not None      # [r]P ≠ ∞: outside the subgroup (pt_mul reduces k mod r)
         assert emu.emu_g2_in_subgroup(_g2b(Pt)) == 0
+        assert emu.emu_g2_subgroup_both(_g2b(Pt)) == 0          # both tests refuse it
+        # a subgroup point plus a point outside is outside; a small multiple of an outside point stays outside
+        for other in (F.pt_add(F.OPS2, Pt, F.G2_GEN), F.pt_double(F.OPS2, Pt), F.pt_add(F.OPS2, F.pt_double(F.OPS2, Pt), Pt)):
+            assert emu.emu_g2_subgroup_both(_g2b(other)) == 0
         found += 1
+    for _ in range(6):   # and both accept the r-torsion, including small multiples and the negated generator
+        P2 = F.pt_mul(F.OPS2, F.G2_GEN, rnd.randrange(1, R))
+        assert emu.emu_g2_subgroup_both(_g2b(P2)) == 3
+    for k in (1, 2, 3, R - 1):
+        assert emu.emu_g2_subgroup_both(_g2b(F.pt_mul(F.OPS2, F.G2_GEN, k))) == 3
 
 
 def _f2_sqrt(a):
@@ -202,6 +211,20 @@ def test_pairing(emu):
     P2 = F.pt_neg(F.OPS1, F.pt_mul(F.OPS1, F.G1_GEN, a * b))
     assert emu.emu_pairing_check(_g1b(P1) + _g1b(P2), _g2b(Q1) + _g2b(F.G2_GEN), 2) == 1
     assert emu.emu_pairing_check(_g1b(P1) + _g1b(P1), _g2b(Q1) + _g2b(F.G2_GEN), 2) == 0
+
+
+def test_verifier_fast_paths(emu):
+    """inversion-free Miller loop, sparse line products, cyclotomic squaring and the merged Groth16 loop against the plain versions
+    (tests/host_emul/emul.cpp emu_pairing_fast_paths), on valid-looking and on arbitrary inputs"""
+    rnd = random.Random(21)
+    for _ in range(3):
+        g1 = b"".join(_g1b(F.pt_mul(F.OPS1, F.G1_GEN, rnd.randrange(1, R))) for _ in range(3))
+        g2 = b"".join(_g2b(F.pt_mul(F.OPS2, F.G2_GEN, rnd.randrange(1, R))) for _ in range(3))
+        assert emu.emu_pairing_fast_paths(g1, g2) == 31
+    # points at infinity among the G1 arguments drop their factor in both forms
+    g1 = _g1b(F.pt_mul(F.OPS1, F.G1_GEN, 5)) + _g1b(None) + _g1b(F.pt_mul(F.OPS1, F.G1_GEN, 9))
+    g2 = b"".join(_g2b(F.pt_mul(F.OPS2, F.G2_GEN, k)) for k in (3, 4, 5))
+    assert emu.emu_pairing_fast_paths(g1, g2) == 31
 
 
 def test_final_exponentiation_chain(emu):

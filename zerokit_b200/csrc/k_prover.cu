@@ -85,28 +85,25 @@ static __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* g
                  : "memory");
 }
 
-// Two mappings of (proof, slot) onto threads, same schedule, same ring, same staging:
-//   WARP = false: a CTA of four warps carries 32 proofs; warp w evaluates slot w, lane = proof; a CTA barrier separates bundles.
-//   WARP = true : ONE warp carries 8 proofs; lane = slot + 4·proof; __syncwarp separates bundles.  A product costs a warp the same
-//                 ≈ 520 pipe cycles whether 4 or 32 of its lanes are live, so both mappings spend the same issue slots per
-//                 proof, but the warp form pays no CTA barrier per bundle and a batch spreads over 4× as many warps: a single
-//                 proof (4 live lanes) and a batch of 4 096 (512 independent warps over 592 schedulers) both finish sooner.
-template <bool WARP>
-__global__ void __launch_bounds__(WARP ? 32 : 128) k_witness(CircuitDev c, const uint8_t* __restrict__ inputs, Fr* vals, u32 B, u32* __restrict__ err) {
-    constexpr u32 PROOFS = WARP ? 32 / VM_SLOTS : 32;                                        // proofs per CTA = ring stride
+// A CTA of four warps carries 32 proofs; warp w evaluates slot w, lane = proof; a CTA barrier separates bundles.  (Round-2
+// experiment, measured and removed: ONE warp carrying 8 proofs with lane = slot + 4·proof and __syncwarp instead of the CTA
+// barrier was SLOWER — single proof 6.83 → 7.63 ms, batch 4 096 8.33 → 15.2 ms: the four slots of a bundle hold different
+// operations and a warp runs divergent lanes one after the other, while four warps run them side by side on four schedulers.)
+__global__ void __launch_bounds__(128) k_witness(CircuitDev c, const uint8_t* __restrict__ inputs, Fr* vals, u32 B, u32* __restrict__ err) {
+    constexpr u32 PROOFS = 32;                                                              // proofs per CTA = ring stride
     constexpr size_t RING_U4 = (size_t)VM_RING * VM_SLOTS * 2 * PROOFS;
     extern __shared__ __align__(128) uint4 ring[];   // [VM_RING · VM_SLOTS][2][PROOFS]: the two 16-byte halves of a value, proof-contiguous
     uint4* stage = ring + RING_U4;                                                          // [VM_STAGES][VM_STAGE_BUNDLES][VM_SLOTS][2]
     u64* full = reinterpret_cast<u64*>(stage + (size_t)VM_STAGES * VM_STAGE_BYTES / sizeof(uint4));
     const u32 lane = threadIdx.x & 31;
-    const u32 slot = WARP ? (lane & (VM_SLOTS - 1)) : (threadIdx.x >> 5);
-    const u32 pl = WARP ? lane / VM_SLOTS : lane;                                            // proof within the CTA
+    const u32 slot = threadIdx.x >> 5;
+    const u32 pl = lane;                                                                    // proof within the CTA
     const u32 j = blockIdx.x * PROOFS + pl;
     const bool live = j < B;
     const uint8_t* in = inputs + (size_t)(live ? j : 0) * c.n_slots * 32;
     const u32 n_blocks = c.n_bundles / VM_STAGE_BUNDLES;                                   // the host pads the schedule to whole blocks
     const uint8_t* sched = reinterpret_cast<const uint8_t*>(c.sched);
-    auto bundle_sync = [] { if (WARP) __syncwarp(); else __syncthreads(); };
+    auto bundle_sync = [] { __syncthreads(); };
     u32 bad = 0;
     if (threadIdx.x == 0) {
         for (u32 s = 0; s < VM_STAGES; s++) mbar_init(full + s, 1);
@@ -159,17 +156,9 @@ __global__ void __launch_bounds__(WARP ? 32 : 128) k_witness(CircuitDev c, const
 }
 void launch_witness(const CircuitDev& c, const uint8_t* d_inputs, Fr* d_vals, u32 B, u32* d_err, cudaStream_t s) {
     ZK_CUDA_CHECK(cudaMemsetAsync(d_err, 0, 4 * (size_t)B, s));
-    static const int mode = [] { const char* v = getenv("RLN_B200_WITNESS_WARP"); return v && *v ? atoi(v) : 1; }();   // A/B switch of round 2
     // the shared-memory attribute is per device (a process may drive several GPUs): set on every launch, it is a cheap call
-    if (mode) {
-        constexpr u32 PW = 32 / VM_SLOTS;
-        constexpr size_t smem = (size_t)VM_RING * VM_SLOTS * 2 * PW * sizeof(uint4) + (size_t)VM_STAGES * VM_STAGE_BYTES + VM_STAGES * sizeof(u64);
-        ZK_CUDA_CHECK(cudaFuncSetAttribute(k_witness<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_witness<true><<<(B + PW - 1) / PW, 32, smem, s>>>(c, d_inputs, d_vals, B, d_err);
-    } else {
-        ZK_CUDA_CHECK(cudaFuncSetAttribute(k_witness<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VM_SMEM_BYTES));
-        k_witness<false><<<(B + 31) / 32, 128, VM_SMEM_BYTES, s>>>(c, d_inputs, d_vals, B, d_err);
-    }
+    ZK_CUDA_CHECK(cudaFuncSetAttribute(k_witness, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VM_SMEM_BYTES));
+    k_witness<<<(B + 31) / 32, 128, VM_SMEM_BYTES, s>>>(c, d_inputs, d_vals, B, d_err);
     ZK_CUDA_CHECK(cudaGetLastError());
 }
 u32 vm_schedule_block_bundles() { return VM_STAGE_BUNDLES; }

@@ -53,12 +53,10 @@ __device__ bool fq2_sqrt(const Fq2& a, Fq2& out) {
     }
     Fq alpha;
     if (!fq_sqrt(a.a.sqr() + a.b.sqr(), alpha)) return false;
-    // two_inv = 1/2
-    Fq two_inv = Fq::from_u32(2).inv();
-    Fq delta = (a.a + alpha) * two_inv;
+    Fq delta = halve(a.a + alpha);
     Fq x0;
     if (!fq_sqrt(delta, x0)) {
-        delta = (a.a - alpha) * two_inv;
+        delta = halve(a.a - alpha);
         if (!fq_sqrt(delta, x0)) return false;
     }
     Fq x1 = a.b * (x0.dbl()).inv();
@@ -155,10 +153,10 @@ __global__ void __launch_bounds__(32) k_verify(VerifyKeyDev vk, const uint8_t* _
         while (Fr::raw_cmp(x, m) >= 0) Fr::raw_sub(x, x, m);
         vkx.add(fixed_base_mul<Fq>(vk.gamma_tab + i * per_base, vk.gc, vk.gK, x));   // 32 additions instead of 254 doublings
     }
-    Fq12 f = miller_loop(&c_pair, Bp, A.neg());   // the only pairing whose G2 argument varies
+    // one Miller loop for the three proof-dependent pairings (shared squarings, inversion-free steps for the variable point B,
+    // precomputed lines for γ₂ and δ₂, sparse products), times the key's own Miller value of (α₁, β₂)
+    Fq12 f = miller_loop_groth16(&c_pair, Bp, A.neg(), vk.gamma_lam, vk.gamma_c, vkx.to_affine(), vk.delta_lam, vk.delta_c, C);
     f = f * (*vk.ml_alpha_beta);
-    f = f * miller_loop_fixed(vk.gamma_lam, vk.gamma_c, vkx.to_affine());
-    f = f * miller_loop_fixed(vk.delta_lam, vk.delta_c, C);
     ok[j] = final_exponentiation(&c_pair, f) == Fq12::one() ? 1 : 0;
 }
 
