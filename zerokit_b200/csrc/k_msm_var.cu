@@ -4,7 +4,9 @@
 // VariableBaseMSM::msm_bigint (Cargo.lock:106).  Same mathematical object (Σ sᵢ·Pᵢ), so the affine
 // result is bit-identical; the schedule is GPU-shaped:
 //   1. signed radix-2^c digits per scalar                         (k_digits, 32 B read / scalar)
-//   2. sort (window,bucket) keys with their point indices          (cub radix sort, library)
+//   2. counting sort of the point indices by (window, bucket): histogram with one atomic per digit, exclusive scan, scatter
+//      through per-bucket cursors (k_digits<COUNT/SCATTER>, k_scan_*: hand-written — the order inside a bucket is irrelevant to
+//      a sum, so no stable radix sort is needed and neither keys nor an unsorted copy of the indices ever touch HBM)
 //   3. one thread per bucket: sum its points with XYZZ mixed adds  (k_bucket_sum: the hot kernel —
 //      128-bit loads of the 64-byte affine bases, ≈ 10 modular products per 64 bytes)
 //   4. per window: Σ (b+1)·B_b by segment running sums, warp-shuffle tree over the segments
@@ -13,8 +15,6 @@
 // multiply pipe (≈ 250 IMAD per byte), see DESIGN.md §roofline.
 #include <cstdlib>
 
-#include <cub/cub.cuh>
-
 #include "device_api.hpp"
 #include "glv.cuh"
 
@@ -22,17 +22,16 @@ namespace zk {
 
 struct VarMsmWorkspace {
     size_t max_n = 0;
-    u32 *keys_in = nullptr, *keys_out = nullptr, *vals_in = nullptr, *vals_out = nullptr;
-    u32 *bucket_start = nullptr, *bucket_end = nullptr;
-    u32 *size_key = nullptr, *size_key_out = nullptr, *order_in = nullptr, *order = nullptr;  // buckets ordered by size, largest first
+    u32* vals_out = nullptr;                          // point index | sign << 31 of every non-zero digit, grouped by (window, bucket)
+    u32 *bucket_cnt = nullptr, *bucket_start = nullptr, *bucket_end = nullptr;
+    u32 *size_bins = nullptr, *order = nullptr;       // buckets ordered by size, largest first (counting sort over clamped sizes)
+    u32* scan_tmp = nullptr;                          // block sums of the exclusive scans
     u32 *slice_cnt = nullptr, *slice_off = nullptr;   // per ordered bucket: number of ≤ SLICE-point slices and their first slice id
     G1XYZZ* partial = nullptr;                        // one partial sum per slice
     size_t max_slices = 0;
     G1XYZZ* buckets = nullptr;
     G1XYZZ* seg = nullptr;
     G1XYZZ* win = nullptr;
-    void* cub_tmp = nullptr;
-    size_t cub_tmp_bytes = 0;
     size_t max_buckets = 0;
     G1Affine* phi = nullptr;                          // GLV mode only: φ(Pᵢ) = (β·xᵢ, yᵢ), allocated on first use
     size_t phi_cap = 0;
@@ -60,6 +59,8 @@ static void msm_params(size_t n, int& c, int& K) {
 }
 static const u32 SLICE_MIN = 256, SLICE_MAX = 2048;  // a thread never sums more than `slice` points: heavier buckets are split
 static const int SEGS = 2048;  // segments per window in the bucket reduction (16 buckets each at c = 16: 32 K short threads)
+static const u32 SIZE_BINS = 4096;   // buckets are ordered by min(size, SIZE_BINS − 1): anything fuller is split into slices anyway
+static const u32 SCAN_TILE = 1024;   // elements per CTA of the exclusive scan
 
 VarMsmWorkspace* var_msm_workspace_create(size_t max_n) {
     VarMsmWorkspace* w = new VarMsmWorkspace();
@@ -89,44 +90,40 @@ VarMsmWorkspace* var_msm_workspace_create(size_t max_n) {
         if (((size_t)K << (c - 1)) > max_b) max_b = (size_t)K << (c - 1);
     }
     w->max_buckets = max_b;
-    ZK_CUDA_CHECK(cudaMalloc(&w->keys_in, 4 * max_items));
-    ZK_CUDA_CHECK(cudaMalloc(&w->keys_out, 4 * max_items));
-    ZK_CUDA_CHECK(cudaMalloc(&w->vals_in, 4 * max_items));
     ZK_CUDA_CHECK(cudaMalloc(&w->vals_out, 4 * max_items));
+    ZK_CUDA_CHECK(cudaMalloc(&w->bucket_cnt, 4 * (max_b + 1)));
     ZK_CUDA_CHECK(cudaMalloc(&w->bucket_start, 4 * (max_b + 1)));
     ZK_CUDA_CHECK(cudaMalloc(&w->bucket_end, 4 * (max_b + 1)));
     ZK_CUDA_CHECK(cudaMalloc(&w->buckets, sizeof(G1XYZZ) * max_b));
-    ZK_CUDA_CHECK(cudaMalloc(&w->size_key, 4 * max_b));
-    ZK_CUDA_CHECK(cudaMalloc(&w->size_key_out, 4 * max_b));
-    ZK_CUDA_CHECK(cudaMalloc(&w->order_in, 4 * max_b));
+    ZK_CUDA_CHECK(cudaMalloc(&w->size_bins, 4 * 2 * SIZE_BINS));
     ZK_CUDA_CHECK(cudaMalloc(&w->order, 4 * max_b));
     ZK_CUDA_CHECK(cudaMalloc(&w->slice_cnt, 4 * max_b));
     ZK_CUDA_CHECK(cudaMalloc(&w->slice_off, 4 * max_b));
+    ZK_CUDA_CHECK(cudaMalloc(&w->scan_tmp, 4 * 4096));   // two scratch areas of ≤ 1024 tile sums (offsets 0 and 2048)
     w->max_slices = max_items / SLICE_MIN + max_b + 1;
     ZK_CUDA_CHECK(cudaMalloc(&w->partial, sizeof(G1XYZZ) * w->max_slices));
     ZK_CUDA_CHECK(cudaMalloc(&w->seg, sizeof(G1XYZZ) * 32 * SEGS));
     ZK_CUDA_CHECK(cudaMalloc(&w->win, sizeof(G1XYZZ) * 32));
-    cub::DeviceRadixSort::SortPairs(nullptr, w->cub_tmp_bytes, w->keys_in, w->keys_out, w->vals_in, w->vals_out,
-                                    (int64_t)(max_items > max_b ? max_items : max_b), 0, 32);
-    size_t scan_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, w->slice_cnt, w->slice_off, (int)max_b);
-    if (scan_bytes > w->cub_tmp_bytes) w->cub_tmp_bytes = scan_bytes;
-    ZK_CUDA_CHECK(cudaMalloc(&w->cub_tmp, w->cub_tmp_bytes));
     return w;
 }
 void var_msm_workspace_destroy(VarMsmWorkspace* w) {
     if (!w) return;
-    cudaFree(w->keys_in); cudaFree(w->keys_out); cudaFree(w->vals_in); cudaFree(w->vals_out);
-    cudaFree(w->bucket_start); cudaFree(w->bucket_end); cudaFree(w->buckets);
-    cudaFree(w->size_key); cudaFree(w->size_key_out); cudaFree(w->order_in); cudaFree(w->order);
-    cudaFree(w->slice_cnt); cudaFree(w->slice_off); cudaFree(w->partial); cudaFree(w->seg); cudaFree(w->win); cudaFree(w->cub_tmp);
+    cudaFree(w->vals_out);
+    cudaFree(w->bucket_cnt); cudaFree(w->bucket_start); cudaFree(w->bucket_end); cudaFree(w->buckets);
+    cudaFree(w->size_bins); cudaFree(w->order); cudaFree(w->scan_tmp);
+    cudaFree(w->slice_cnt); cudaFree(w->slice_off); cudaFree(w->partial); cudaFree(w->seg); cudaFree(w->win);
     cudaFree(w->phi);
     delete w;
 }
 
-// keys[k·n + i] = k·2^{c−1} + |d|−1 (or K·2^{c−1}, one past the last bucket, when the digit is zero); vals = i | sign << 31
-__global__ void __launch_bounds__(256) k_digits(const uint8_t* __restrict__ scalars, size_t n, int c, int K, u32* __restrict__ keys,
-                                                u32* __restrict__ vals) {
+// Signed radix-2^c digits of every scalar, visited twice: PASS 0 counts the digits per (window, bucket) with one atomic each,
+// PASS 1 (after the exclusive scan of the counts) writes the point index | sign << 31 of every non-zero digit to the next free
+// slot of its bucket (cursor = a copy of the bucket starts, advanced by atomics; it ends up holding the bucket ends).  The digits
+// are recomputed instead of stored: 40 integer instructions against 8 bytes of HBM traffic per digit each way.
+// GLV: term i + h·n carries |k_h| of scalar i (h = 0, 1); the sign of the half flips every digit.
+template <bool GLV, int PASS>
+__global__ void __launch_bounds__(256) k_digits(const uint8_t* __restrict__ scalars, size_t n, int c, int K, u32* __restrict__ cnt_or_cursor,
+                                                u32* __restrict__ vals_out) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint4* q = reinterpret_cast<const uint4*>(scalars + 32 * i);
@@ -136,43 +133,16 @@ __global__ void __launch_bounds__(256) k_digits(const uint8_t* __restrict__ scal
 #pragma unroll
     for (int t = 0; t < 8; t++) m[t] = FrCfg::p(t);
     while (Fr::raw_cmp(s, m) >= 0) Fr::raw_sub(s, s, m);  // ark reduces through Fr::into_bigint
-    u32 carry = 0;
     const u32 half = 1u << (c - 1);
-    for (int k = 0; k < K; k++) {
-        const int bit = k * c, w = bit >> 5, sh = bit & 31;
-        u32 v = 0;
-        if (w < 8) {
-            v = s[w] >> sh;
-            if (sh + c > 32 && w + 1 < 8) v |= s[w + 1] << (32 - sh);
-        }
-        int d = (int)(v & ((1u << c) - 1)) + (int)carry;
-        if (d > (int)half) { d -= (1 << c); carry = 1; } else carry = 0;
-        u32 key = (u32)K * half, val = (u32)i;  // zero digits sort behind every bucket
-        if (d > 0) key = (u32)k * half + (u32)(d - 1);
-        else if (d < 0) { key = (u32)k * half + (u32)(-d - 1); val |= 0x80000000u; }
-        keys[(size_t)k * n + i] = key;
-        vals[(size_t)k * n + i] = val;
-    }
-}
-
-// GLV form of k_digits: term i + h·n carries |k_h| of scalar i (h = 0, 1); the sign of the half flips every digit
-__global__ void __launch_bounds__(256) k_digits_glv(const uint8_t* __restrict__ scalars, size_t n, int c, int K, u32* __restrict__ keys,
-                                                    u32* __restrict__ vals) {
-    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint4* q = reinterpret_cast<const uint4*>(scalars + 32 * i);
-    uint4 a = q[0], b = q[1];
-    u32 s[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    u32 m[8];
-#pragma unroll
-    for (int t = 0; t < 8; t++) m[t] = FrCfg::p(t);
-    while (Fr::raw_cmp(s, m) >= 0) Fr::raw_sub(s, s, m);
-    const u32 half = 1u << (c - 1);
-    const size_t terms = 2 * n;
-    for (int h = 0; h < 2; h++) {
+    for (int h = 0; h < (GLV ? 2 : 1); h++) {
         u32 kh[8];
-        const bool neg = glv::split(s, h, kh);
-        const size_t term = i + (size_t)h * n;
+        bool neg = false;
+        if (GLV) neg = glv::split(s, h, kh);
+        else {
+#pragma unroll
+            for (int t = 0; t < 8; t++) kh[t] = s[t];
+        }
+        const u32 term = (u32)(i + (size_t)h * n);
         u32 carry = 0;
         for (int k = 0; k < K; k++) {
             const int bit = k * c, w = bit >> 5, sh = bit & 31;
@@ -183,16 +153,97 @@ __global__ void __launch_bounds__(256) k_digits_glv(const uint8_t* __restrict__ 
             }
             int d = (int)(v & ((1u << c) - 1)) + (int)carry;
             if (d > (int)half) { d -= (1 << c); carry = 1; } else carry = 0;
-            u32 key = (u32)K * half, val = (u32)term;
-            if (d != 0) {
-                key = (u32)k * half + (u32)((d < 0 ? -d : d) - 1);
-                if ((d < 0) != neg) val |= 0x80000000u;
-            }
-            keys[(size_t)k * terms + term] = key;
-            vals[(size_t)k * terms + term] = val;
+            if (d == 0) continue;
+            const u32 bucket = (u32)k * half + (u32)((d < 0 ? -d : d) - 1);
+            if (PASS == 0) atomicAdd(cnt_or_cursor + bucket, 1u);
+            else vals_out[atomicAdd(cnt_or_cursor + bucket, 1u)] = term | (((d < 0) != neg) ? 0x80000000u : 0u);
         }
     }
 }
+
+// ---- exclusive scan of u32 (n ≤ SCAN_TILE²): per-tile scan + tile sums, scan of the tile sums by one CTA, add back -------------
+__global__ void __launch_bounds__(256) k_scan_tiles(const u32* __restrict__ in, u32 n, u32* __restrict__ out, u32* __restrict__ tile_sum) {
+    __shared__ u32 warp_tot[8];
+    const u32 base = blockIdx.x * SCAN_TILE + threadIdx.x * 4;
+    u32 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = base + k < n ? in[base + k] : 0u;
+    const u32 mine = v[0] + v[1] + v[2] + v[3];
+    u32 incl = mine;
+    const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (u32)d) incl += o;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    u32 before = 0;
+    for (u32 w = 0; w < wid; w++) before += warp_tot[w];
+    u32 run = before + incl - mine;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+    if (threadIdx.x == 255) tile_sum[blockIdx.x] = before + incl;
+}
+__global__ void __launch_bounds__(1024) k_scan_top(u32* __restrict__ tile_sum, u32 n_tiles) {   // in place, one CTA, n_tiles ≤ 1024
+    __shared__ u32 warp_tot[32];
+    const u32 t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const u32 mine = t < n_tiles ? tile_sum[t] : 0u;
+    u32 incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (u32)d) incl += o;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    u32 before = 0;
+    for (u32 w = 0; w < wid; w++) before += warp_tot[w];
+    if (t < n_tiles) tile_sum[t] = before + incl - mine;
+}
+__global__ void __launch_bounds__(256) k_scan_add(u32* __restrict__ out, u32 n, const u32* __restrict__ tile_off, u32* __restrict__ copy) {
+    const u32 i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const u32 v = out[i] + tile_off[i / SCAN_TILE];
+    out[i] = v;
+    if (copy) copy[i] = v;   // the scatter cursors start as a copy of the bucket starts
+}
+static void exclusive_scan(const u32* in, u32 n, u32* out, u32* scratch, u32* copy, cudaStream_t s) {
+    const u32 tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (tiles > 1024) throw CudaError(cudaErrorInvalidValue, "var msm: scan longer than 2^20 elements", __FILE__, __LINE__);
+    k_scan_tiles<<<tiles, 256, 0, s>>>(in, n, out, scratch);
+    k_scan_top<<<1, 1024, 0, s>>>(scratch, tiles);
+    k_scan_add<<<(n + 255) / 256, 256, 0, s>>>(out, n, scratch, copy);
+}
+
+// ---- buckets in size order, fullest first: counting sort over bin(size) = SIZE_BINS − 1 − min(size, SIZE_BINS − 1) ---------------
+__global__ void __launch_bounds__(256) k_size_hist(const u32* __restrict__ cnt, u32 n_buckets, u32* __restrict__ bins) {
+    __shared__ u32 sh[SIZE_BINS];
+    for (u32 t = threadIdx.x; t < SIZE_BINS; t += blockDim.x) sh[t] = 0;
+    __syncthreads();
+    for (u32 b = blockIdx.x * blockDim.x + threadIdx.x; b < n_buckets; b += gridDim.x * blockDim.x) {
+        const u32 sz = cnt[b];
+        atomicAdd(&sh[SIZE_BINS - 1 - (sz < SIZE_BINS - 1 ? sz : SIZE_BINS - 1)], 1u);
+    }
+    __syncthreads();
+    for (u32 t = threadIdx.x; t < SIZE_BINS; t += blockDim.x)
+        if (sh[t]) atomicAdd(bins + t, sh[t]);
+}
+__global__ void __launch_bounds__(256) k_size_scatter(const u32* __restrict__ cnt, u32 n_buckets, u32* __restrict__ bin_cursor, u32* __restrict__ order) {
+    const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_buckets) return;
+    const u32 sz = cnt[b];
+    order[atomicAdd(bin_cursor + (SIZE_BINS - 1 - (sz < SIZE_BINS - 1 ? sz : SIZE_BINS - 1)), 1u)] = b;
+}
+// number of slices of the i-th bucket in size order
+__global__ void k_slice_counts(const u32* __restrict__ cnt, const u32* __restrict__ order, u32 n_buckets, u32 slice, u32* __restrict__ out) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_buckets) out[i] = (cnt[order[i]] + slice - 1) / slice;
+}
+
 // φ(P) = (β·x, y); the point at infinity (0, 0) maps to itself
 __global__ void k_phi_bases(const G1Affine* __restrict__ bases, size_t n, G1Affine* __restrict__ phi) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -201,30 +252,6 @@ __global__ void k_phi_bases(const G1Affine* __restrict__ bases, size_t n, G1Affi
     p.x = p.x * glv::beta();
     st_fp(&phi[i].x, p.x);
     st_fp(&phi[i].y, p.y);
-}
-
-__global__ void k_bucket_bounds(const u32* __restrict__ keys, size_t items, u32 n_buckets, u32* __restrict__ start, u32* __restrict__ end) {
-    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i >= items) return;
-    const u32 k = keys[i];
-    if (k >= n_buckets) return;
-    if (i == 0 || keys[i - 1] != k) start[k] = (u32)i;
-    if (i + 1 == items || keys[i + 1] != k) end[k] = (u32)i + 1;
-}
-
-// sort key of a bucket: ~size, so that an ascending radix sort lists the fullest buckets first
-__global__ void k_bucket_sizes(const u32* __restrict__ start, const u32* __restrict__ end, u32 n_buckets, u32* __restrict__ key,
-                               u32* __restrict__ idx) {
-    const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n_buckets) return;
-    key[b] = ~(end[b] - start[b]);
-    idx[b] = b;
-}
-
-// number of slices of the i-th fullest bucket (size_key_out holds ~size in ascending order = sizes in descending order)
-__global__ void k_slice_counts(const u32* __restrict__ size_key_sorted, u32 n_buckets, u32 slice, u32* __restrict__ cnt) {
-    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_buckets) cnt[i] = (~size_key_sorted[i] + slice - 1) / slice;
 }
 
 // The hot kernel.  Work item = one slice of ≤ `slice` points of one bucket (slice ≈ twice the mean bucket size, so with uniform
@@ -360,6 +387,9 @@ void launch_var_msm_g1(VarMsmWorkspace* w, const G1Affine* d_bases, const uint8_
     if (use_glv) K = glv_windows(c);
     const u32 half = 1u << (c - 1);
     const size_t items = terms * (size_t)K, n_buckets = (size_t)K * half;
+    ZK_CUDA_CHECK(cudaMemsetAsync(w->bucket_cnt, 0, 4 * n_buckets, s));
+    ZK_CUDA_CHECK(cudaMemsetAsync(w->size_bins, 0, 4 * SIZE_BINS, s));
+    const unsigned dg = (unsigned)((n + 255) / 256);
     if (use_glv) {
         if (w->phi_cap < n) {
             ZK_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -367,26 +397,25 @@ void launch_var_msm_g1(VarMsmWorkspace* w, const G1Affine* d_bases, const uint8_
             ZK_CUDA_CHECK(cudaMalloc(&w->phi, sizeof(G1Affine) * n));
             w->phi_cap = n;
         }
-        k_phi_bases<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_bases, n, w->phi);
-        k_digits_glv<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_scalars, n, c, K, w->keys_in, w->vals_in);
+        k_phi_bases<<<dg, 256, 0, s>>>(d_bases, n, w->phi);
+        k_digits<true, 0><<<dg, 256, 0, s>>>(d_scalars, n, c, K, w->bucket_cnt, nullptr);
     } else {
-        k_digits<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_scalars, n, c, K, w->keys_in, w->vals_in);
+        k_digits<false, 0><<<dg, 256, 0, s>>>(d_scalars, n, c, K, w->bucket_cnt, nullptr);
     }
-    int key_bits = 0;
-    while (((size_t)1 << key_bits) < n_buckets + 1) key_bits++;  // keys are in [0, n_buckets]: sort only the significant bits
-    size_t tmp = w->cub_tmp_bytes;
-    ZK_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, tmp, w->keys_in, w->keys_out, w->vals_in, w->vals_out, (int64_t)items, 0, key_bits, s));
-    ZK_CUDA_CHECK(cudaMemsetAsync(w->bucket_start, 0, 4 * n_buckets, s));
-    ZK_CUDA_CHECK(cudaMemsetAsync(w->bucket_end, 0, 4 * n_buckets, s));
-    k_bucket_bounds<<<(unsigned)((items + 255) / 256), 256, 0, s>>>(w->keys_out, items, (u32)n_buckets, w->bucket_start, w->bucket_end);
-    k_bucket_sizes<<<(unsigned)((n_buckets + 255) / 256), 256, 0, s>>>(w->bucket_start, w->bucket_end, (u32)n_buckets, w->size_key, w->order_in);
-    tmp = w->cub_tmp_bytes;
-    ZK_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(w->cub_tmp, tmp, w->size_key, w->size_key_out, w->order_in, w->order, (int64_t)n_buckets, 0, 32, s));
+    // bucket starts = exclusive scan of the counts; the scatter cursors (bucket_end) start there and finish at the bucket ends
+    exclusive_scan(w->bucket_cnt, (u32)n_buckets, w->bucket_start, w->scan_tmp, w->bucket_end, s);
+    if (use_glv) k_digits<true, 1><<<dg, 256, 0, s>>>(d_scalars, n, c, K, w->bucket_end, w->vals_out);
+    else k_digits<false, 1><<<dg, 256, 0, s>>>(d_scalars, n, c, K, w->bucket_end, w->vals_out);
+    // buckets in size order
+    u32* bins = w->size_bins;
+    u32* bin_start = w->size_bins + SIZE_BINS;
+    k_size_hist<<<(unsigned)((n_buckets + 2047) / 2048 < 296 ? (n_buckets + 2047) / 2048 : 296), 256, 0, s>>>(w->bucket_cnt, (u32)n_buckets, bins);
+    exclusive_scan(bins, SIZE_BINS, bin_start, w->scan_tmp + 2048, nullptr, s);
+    k_size_scatter<<<(unsigned)((n_buckets + 255) / 256), 256, 0, s>>>(w->bucket_cnt, (u32)n_buckets, bin_start, w->order);
     u32 slice = SLICE_MIN;   // ≈ twice the mean bucket size
     while (slice < SLICE_MAX && (size_t)slice * n_buckets < 2 * items) slice <<= 1;
-    k_slice_counts<<<(unsigned)((n_buckets + 255) / 256), 256, 0, s>>>(w->size_key_out, (u32)n_buckets, slice, w->slice_cnt);
-    tmp = w->cub_tmp_bytes;
-    ZK_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(w->cub_tmp, tmp, w->slice_cnt, w->slice_off, (int)n_buckets, s));
+    k_slice_counts<<<(unsigned)((n_buckets + 255) / 256), 256, 0, s>>>(w->bucket_cnt, w->order, (u32)n_buckets, slice, w->slice_cnt);
+    exclusive_scan(w->slice_cnt, (u32)n_buckets, w->slice_off, w->scan_tmp, nullptr, s);
     const size_t max_slices = items / slice + n_buckets;   // upper bound known on the host; threads beyond the real total exit
     ZK_CUDA_CHECK(cudaMemsetAsync(w->buckets, 0, sizeof(G1XYZZ) * n_buckets, s));   // all-zero XYZZ = infinity: the empty buckets
     if (use_glv)

@@ -2711,12 +2711,12 @@ int rlnb200_msm_gen_bases(RlnB200Msm_t* m, const void* d_scalars, size_t n, void
     INT_OP(DeviceGuard dg(m->device); launch_g1_mul_gen((const uint8_t*)d_scalars, (G1Affine*)d_bases_out, n, (cudaStream_t)stream); g_launch_count++;)
 }
 int rlnb200_msm_g1_device(RlnB200Msm_t* m, const void* d_bases, const void* d_scalars, size_t n, void* d_result, void* stream, RlnString* err) {
-    INT_OP(DeviceGuard dg(m->device); launch_var_msm_g1(m->ws, (const G1Affine*)d_bases, (const uint8_t*)d_scalars, n, (uint8_t*)d_result, (cudaStream_t)stream); g_launch_count += 9;)
+    INT_OP(DeviceGuard dg(m->device); launch_var_msm_g1(m->ws, (const G1Affine*)d_bases, (const uint8_t*)d_scalars, n, (uint8_t*)d_result, (cudaStream_t)stream); g_launch_count += 20;)
 }
 int rlnb200_msm_g1(RlnB200Msm_t* m, const uint8_t* bases, const uint8_t* scalars, size_t n, uint8_t* result, RlnString* err) {
     INT_OP(DeviceGuard dg(m->device); DevMem raw, db, ds, dr; raw.upload(bases, 64 * n); db.alloc(sizeof(G1Affine) * n); ds.upload(scalars, 32 * n); dr.alloc(64);
            launch_g1_from_bytes(raw.as<uint8_t>(), db.as<G1Affine>(), n, 0);
-           launch_var_msm_g1(m->ws, db.as<G1Affine>(), ds.as<uint8_t>(), n, dr.as<uint8_t>(), 0); g_launch_count += 10;
+           launch_var_msm_g1(m->ws, db.as<G1Affine>(), ds.as<uint8_t>(), n, dr.as<uint8_t>(), 0); g_launch_count += 21;
            ZK_CUDA_CHECK(cudaMemcpy(result, dr.p, 64, cudaMemcpyDeviceToHost));)
 }
 
