@@ -521,6 +521,10 @@ int rlnb200_poseidon_hash_batch(const uint8_t *inputs /* count*n_inputs*32 */, i
                                 uint8_t *out /* count*32 */, RlnString *err);
 /* op: 0 mul, 1 add, 2 sub, 3 portable mul, 4 inverse, 5 square, 6-8 single-reduction dot products ; field: 0 Fr, 1 Fq ; exercises the PTX field arithmetic */
 int rlnb200_field_op(int field, int op, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out, RlnString *err);
+/* batched-affine probe: additions per second of bucket-style accumulation with M running sums per thread in
+ * global memory.  mode 0: XYZZ mixed additions (the library's form), 1: affine additions sharing one Fermat inversion per thread
+ * and round, 2: the same with a binary extended-Euclid inversion, 3: self-check of that inversion (returns mismatches, 0 = good) */
+double rlnb200_affine_batch_probe(int mode, int M, int rounds);
 /* measured Montgomery-product rate (products/s over all SMs, CUDA-event timed); < 0 on error */
 double rlnb200_mul_throughput(int iters);
 /* same for the cheaper schedules, in product-equivalents per second: kind 1 = dedicated squaring, 2 = two-term dot

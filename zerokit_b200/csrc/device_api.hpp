@@ -82,6 +82,10 @@ struct CircuitDev {
     const Fr* tw_inv;    // ω^{-k}, k < domain/2
     const Fr* tw_fwd;    // ω^{k}
     const Fr* coset;     // position p (bit-reversed order) → g^{rev(p)} / domain
+    // tiled transforms (k_ntt_outer / k_ntt_middle): twiddles stored tile-major so that one bulk copy fetches a tile's
+    const Fr* tw_tile_dif = nullptr;   // [64][R], R = domain / 64: tile i0, stage with local half lh at i0·R + R − 2·lh: ω^{−(i0 + 64·kj)·R/(2·lh)}
+    const Fr* tw_tile_dit = nullptr;   // the same with ω
+    const Fr* tw_mid = nullptr;        // [2][64]: ω^{−j·domain/(2h)} then ω^{+j·domain/(2h)} for the stage with half h ≤ 32 at 64 − 2·h
 };
 // inputs: n × n_slots canonical bytes → vals [n_nodes][B] (Montgomery).  err[j] != 0 if node evaluation failed.
 void launch_witness(const CircuitDev& c, const uint8_t* d_inputs, Fr* d_vals, u32 B, u32* d_err, cudaStream_t s);

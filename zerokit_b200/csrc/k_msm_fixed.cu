@@ -225,99 +225,6 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_msm_accum(AccumArgs<F> a) {
 }
 
 
-// ---- G2 accumulate with the accumulator in shared memory ------------------------------------------------------------------------
-// k_msm_accum<Fq2> needs 255 registers (an XYZZ accumulator over Fq2 is 64 of them), so only 2 CTAs fit an SM and its 8 warps
-// cannot hide the dependent-issue latency of the wide-MAD chains (ncu r01c: FMA-heavy pipe 79.4 % busy against 87.6 % for G1).
-// Here X, Y, ZZ, ZZZ of every thread live in shared memory (component-major, thread-contiguous: conflict-free 128-bit accesses) and
-// the mixed addition fetches each component where it is used and writes it back as soon as it is final, so at most six Fq2 values
-// are live at once and three CTAs fit.  Same operations, same order of additions, same result bits.
-__device__ __forceinline__ Fq2 sacc_ld(const uint4* sacc, int comp) {
-    Fq2 v;
-    const uint4 a = sacc[(comp * 4 + 0) * 128 + threadIdx.x], b = sacc[(comp * 4 + 1) * 128 + threadIdx.x];
-    const uint4 c = sacc[(comp * 4 + 2) * 128 + threadIdx.x], d = sacc[(comp * 4 + 3) * 128 + threadIdx.x];
-    v.a.l[0] = a.x; v.a.l[1] = a.y; v.a.l[2] = a.z; v.a.l[3] = a.w; v.a.l[4] = b.x; v.a.l[5] = b.y; v.a.l[6] = b.z; v.a.l[7] = b.w;
-    v.b.l[0] = c.x; v.b.l[1] = c.y; v.b.l[2] = c.z; v.b.l[3] = c.w; v.b.l[4] = d.x; v.b.l[5] = d.y; v.b.l[6] = d.z; v.b.l[7] = d.w;
-    return v;
-}
-__device__ __forceinline__ void sacc_st(uint4* sacc, int comp, const Fq2& v) {
-    sacc[(comp * 4 + 0) * 128 + threadIdx.x] = make_uint4(v.a.l[0], v.a.l[1], v.a.l[2], v.a.l[3]);
-    sacc[(comp * 4 + 1) * 128 + threadIdx.x] = make_uint4(v.a.l[4], v.a.l[5], v.a.l[6], v.a.l[7]);
-    sacc[(comp * 4 + 2) * 128 + threadIdx.x] = make_uint4(v.b.l[0], v.b.l[1], v.b.l[2], v.b.l[3]);
-    sacc[(comp * 4 + 3) * 128 + threadIdx.x] = make_uint4(v.b.l[4], v.b.l[5], v.b.l[6], v.b.l[7]);
-}
-template <bool GLV>
-__global__ void __launch_bounds__(128, 3) k_msm_accum_g2s(AccumArgs<Fq2> a) {
-    __shared__ uint4 sacc[16 * 128];   // [X, Y, ZZ, ZZZ][4 × 128 bits][thread]: 32 KB
-    u32 j, task;
-    if (a.packed) {
-        const u32 slot = blockIdx.y * blockDim.x + threadIdx.x;
-        j = slot & ((1u << a.pack_log) - 1);
-        task = slot >> a.pack_log;
-        if (task >= a.n_tasks) return;
-    } else {
-        j = blockIdx.x * blockDim.x + threadIdx.x;
-        task = blockIdx.y;
-    }
-    if (j >= a.B) return;
-    const MsmTask t = a.tasks[task];
-    const u32* __restrict__ rows = a.row[t.group];
-    const G2Affine* __restrict__ table = a.table[t.group];
-    const Fr* __restrict__ src = a.src[a.which[t.group]];
-    const u32 half = 1u << (a.c - 1);
-    bool acc_inf = true;
-    for (u32 b = t.lo; b < t.hi; b++) {
-        u32 s[8];
-        ld_fp(src + (size_t)rows[b] * a.B + j).to_canonical(s);
-        bool flip = false;
-        if (GLV) {
-            u32 h[8];
-            flip = glv::split(s, t.half, h);
-#pragma unroll
-            for (int i = 0; i < 8; i++) s[i] = h[i];
-        }
-        u32 any = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) any |= s[i];
-        if (!any) continue;
-        const G2Affine* tb = table + (size_t)b * a.K * half;
-        u32 carry = 0;
-        for (int k = 0; k < a.K; k++) {
-            const int d = window_digit(s, k, a.c, carry);
-            if (d == 0) continue;
-            const G2Affine* src_pt = tb + (size_t)k * half + ((d < 0 ? -d : d) - 1);
-            const bool negate = (d < 0) != flip;
-            G2Affine pt = ld_point<Fq2>(src_pt);
-            if (negate) pt.y = pt.y.neg();
-            if (acc_inf) {   // acc = pt
-                sacc_st(sacc, 0, pt.x); sacc_st(sacc, 1, pt.y); sacc_st(sacc, 2, Fq2::one()); sacc_st(sacc, 3, Fq2::one());
-                acc_inf = false;
-                continue;
-            }
-            const Fq2 P = pt.x * sacc_ld(sacc, 2) - sacc_ld(sacc, 0);
-            const Fq2 Y = sacc_ld(sacc, 1);
-            const Fq2 R = pt.y * sacc_ld(sacc, 3) - Y;
-            if (P.is_zero()) {   // pt = ±acc: the rare complete-addition cases, through the register form
-                G2XYZZ acc = {sacc_ld(sacc, 0), Y, sacc_ld(sacc, 2), sacc_ld(sacc, 3)};
-                if (R.is_zero()) acc = G2XYZZ::from_affine(pt).dbl(); else acc = G2XYZZ::infinity();
-                acc_inf = acc.is_inf();
-                sacc_st(sacc, 0, acc.X); sacc_st(sacc, 1, acc.Y); sacc_st(sacc, 2, acc.ZZ); sacc_st(sacc, 3, acc.ZZZ);
-                continue;
-            }
-            const Fq2 PP = P.sqr();
-            const Fq2 PPP = P * PP;
-            const Fq2 Qv = sacc_ld(sacc, 0) * PP;
-            const Fq2 X3 = R.sqr() - PPP - Qv.dbl();
-            sacc_st(sacc, 0, X3);
-            sacc_st(sacc, 1, Fq2::sub_prod(R, Qv - X3, Y, PPP));
-            sacc_st(sacc, 2, sacc_ld(sacc, 2) * PP);
-            sacc_st(sacc, 3, sacc_ld(sacc, 3) * PPP);
-        }
-    }
-    G2XYZZ out = G2XYZZ::infinity();
-    if (!acc_inf) out = {sacc_ld(sacc, 0), sacc_ld(sacc, 1), sacc_ld(sacc, 2), sacc_ld(sacc, 3)};
-    a.part[(size_t)task * a.B + j] = out;
-}
-
 // partial sum of a task; the k₂ half of a GLV pair goes through φ: (X, Y, ZZ, ZZZ) ↦ (β·X, Y, ZZ, ZZZ)
 __device__ __forceinline__ G1XYZZ load_partial(const G1XYZZ* p, u32 half) {
     G1XYZZ v = *p;
@@ -625,11 +532,10 @@ void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, 
         if (ws.n_tasks_g2) {
             const dim3 grid = accum_grid(a, B, bx, ws.n_tasks_g2);
             // no prefetch, 2 CTAs/SM: the G2 kernel is register-bound (prefetch −1.7 %, 3 CTAs/SM spills: −9 %; round 1 A/B)
-            static const int sacc = [] { const char* v = getenv("RLN_B200_G2_SACC"); return v && *v ? atoi(v) : 1; }();   // round-2 A/B
-            if (sacc && bx == 128) {
-                if (plan.glv) k_msm_accum_g2s<true><<<grid, bx, 0, s>>>(a);
-                else k_msm_accum_g2s<false><<<grid, bx, 0, s>>>(a);
-            } else if (plan.glv) k_msm_accum<Fq2, false, 2, true><<<grid, bx, 0, s>>>(a);
+            // Round 2 tried the other way to a third CTA per SM: X, Y, ZZ, ZZZ of every thread in shared memory, fetched where the
+            // mixed addition uses them (168 registers, 88 B of spills, 3 CTAs/SM): 131.3 → 144.4 ms at batch 4 096 — the extra
+            // shared-memory round trips sit on the dependent chain of every addition.  Measured and removed.
+            if (plan.glv) k_msm_accum<Fq2, false, 2, true><<<grid, bx, 0, s>>>(a);
             else k_msm_accum<Fq2, false, 2><<<grid, bx, 0, s>>>(a);
         }
         if (ws.ev) cudaEventRecord(ws.ev[3], s);

@@ -100,7 +100,7 @@ VarMsmWorkspace* var_msm_workspace_create(size_t max_n) {
     ZK_CUDA_CHECK(cudaMalloc(&w->slice_cnt, 4 * max_b));
     ZK_CUDA_CHECK(cudaMalloc(&w->slice_off, 4 * max_b));
     ZK_CUDA_CHECK(cudaMalloc(&w->scan_tmp, 4 * 4096));   // two scratch areas of ≤ 1024 tile sums (offsets 0 and 2048)
-    w->max_slices = max_items / SLICE_MIN + max_b + 1;
+    w->max_slices = (max_items / SLICE_MIN > 2 * 65536 ? max_items / SLICE_MIN : 2 * 65536) + max_b + 1;   // slices only shrink below SLICE_MIN while there are < 64 K of them
     ZK_CUDA_CHECK(cudaMalloc(&w->partial, sizeof(G1XYZZ) * w->max_slices));
     ZK_CUDA_CHECK(cudaMalloc(&w->seg, sizeof(G1XYZZ) * 32 * SEGS));
     ZK_CUDA_CHECK(cudaMalloc(&w->win, sizeof(G1XYZZ) * 32));
@@ -329,9 +329,16 @@ __global__ void __launch_bounds__(64) k_segment_reduce(const G1XYZZ* __restrict_
         run.add(B[b]);
         acc.add(run);  // after the loop: acc = Σ (b+1)·B_b (local index), run = Σ B_b
     }
-    // shift the local weights by s·seg_len
-    u32 off[8] = {s * seg_len, 0, 0, 0, 0, 0, 0, 0};
-    if (off[0]) acc.add(run.mul(off));
+    // shift the local weights by s·seg_len (< 2^16: a short double-and-add, not the 256-bit ladder)
+    const u32 off = s * seg_len;
+    if (off) {
+        G1XYZZ m = G1XYZZ::infinity();
+        for (int i = 31 - __clz(off); i >= 0; i--) {
+            m = m.dbl();
+            if ((off >> i) & 1) m.add(run);
+        }
+        acc.add(m);
+    }
     seg[(size_t)k * n_seg + s] = acc;
 }
 
@@ -365,10 +372,32 @@ __global__ void __launch_bounds__(256) k_window_reduce(const G1XYZZ* __restrict_
     }
 }
 
+// c doublings of an XYZZ point through Jacobian coordinates: (X, Y, ZZ, ZZZ) ↦ (X·ZZ², Y·ZZ³, Z = ZZZ) costs 4 products, a Jacobian
+// doubling with a = 0 (dbl-2009-l) 2M + 5S against XYZZ's 6M + 3S, and the way back is ZZ = Z², ZZZ = Z³.  This chain is ONE
+// thread's dependent latency and the floor of every small MSM (2^16: 0.73 of 2.46 ms before).
+__device__ G1XYZZ xyzz_dbl_n(const G1XYZZ& p, int n) {
+    if (p.is_inf() || n <= 0) return p;
+    const Fq zz2 = p.ZZ.sqr();
+    Fq X = p.X * zz2, Y = p.Y * (zz2 * p.ZZ), Z = p.ZZZ;
+    for (int i = 0; i < n; i++) {
+        if (Y.is_zero()) return G1XYZZ::infinity();   // a point of order two does not exist on BN254 G1 (odd order); kept for completeness
+        const Fq A = X.sqr(), Bq = Y.sqr(), C = Bq.sqr();
+        const Fq D = ((X + Bq).sqr() - A - C).dbl();
+        const Fq E = A.dbl() + A;
+        const Fq X3 = E.sqr() - D.dbl();
+        const Fq C8 = C.dbl().dbl().dbl();
+        const Fq Z3 = (Y * Z).dbl();
+        Y = E * (D - X3) - C8;
+        X = X3;
+        Z = Z3;
+    }
+    const Fq ZZ = Z.sqr();
+    return {X, Y, ZZ, ZZ * Z};
+}
 __global__ void k_horner(const G1XYZZ* __restrict__ win, int c, int K, uint8_t* __restrict__ out) {
     G1XYZZ t = win[K - 1];
     for (int k = K - 2; k >= 0; k--) {
-        for (int i = 0; i < c; i++) t = t.dbl();
+        t = xyzz_dbl_n(t, c);
         t.add(win[k]);
     }
     G1Affine a = t.to_affine();
@@ -412,8 +441,12 @@ void launch_var_msm_g1(VarMsmWorkspace* w, const G1Affine* d_bases, const uint8_
     k_size_hist<<<(unsigned)((n_buckets + 2047) / 2048 < 296 ? (n_buckets + 2047) / 2048 : 296), 256, 0, s>>>(w->bucket_cnt, (u32)n_buckets, bins);
     exclusive_scan(bins, SIZE_BINS, bin_start, w->scan_tmp + 2048, nullptr, s);
     k_size_scatter<<<(unsigned)((n_buckets + 255) / 256), 256, 0, s>>>(w->bucket_cnt, (u32)n_buckets, bin_start, w->order);
-    u32 slice = SLICE_MIN;   // ≈ twice the mean bucket size
+    // slice ≈ twice the mean bucket size at large n (one thread per bucket); at small n there are too few buckets to fill the chip
+    // (2^16: 12 K buckets of 128 points on 75 K thread slots), so slices shrink until there are ≈ 64 K of them and the split
+    // buckets are re-assembled by k_bucket_combine
+    u32 slice = SLICE_MIN;
     while (slice < SLICE_MAX && (size_t)slice * n_buckets < 2 * items) slice <<= 1;
+    while (slice > 16 && items / slice < 65536) slice >>= 1;
     k_slice_counts<<<(unsigned)((n_buckets + 255) / 256), 256, 0, s>>>(w->bucket_cnt, w->order, (u32)n_buckets, slice, w->slice_cnt);
     exclusive_scan(w->slice_cnt, (u32)n_buckets, w->slice_off, w->scan_tmp, nullptr, s);
     const size_t max_slices = items / slice + n_buckets;   // upper bound known on the host; threads beyond the real total exit

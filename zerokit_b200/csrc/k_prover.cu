@@ -325,11 +325,176 @@ static void ntt_dit(Fr* x, u32 log_n, u32 B, const Fr* tw, cudaStream_t s) {
 }
 u32 ntt_launches_per_transform(u32 log_n) { return log_n / 2 + (log_n & 1); }
 
+// ---- tiled NTTs: TMA bulk copies into shared memory, 6–7 butterfly stages per HBM round trip ---------------------------------------
+// The pass-per-two-stages transforms above make 7 HBM round trips per transform, 15 per buffer with the coset scaling (47 launches
+// per QAP), and move 7× the algorithmic 3 MiB per proof.  For small batches — where those launches ARE the cost — the
+// iNTT → coset shift → NTT chain of one buffer is THREE kernels, each moving a tile of NTT_P = 16 proofs through shared memory:
+//   A  decimation-in-frequency, the outer L − 6 stages: tile = the 2^(L−6) rows {i0 + 64·k} (64 tiles per 16 proofs);
+//   B  a contiguous block of 64 rows: the last 6 DIF stages, × g^rev(i)/n, the first 6 decimation-in-time stages;
+//   C  decimation-in-time, the outer L − 6 stages, same tiles as A.
+// Rows arrive by 1-D TMA bulk copies (cp.async.bulk, 512 B per row and tile, completing on one mbarrier), so do the tile's
+// twiddles — stored tile-major on the host so that each tile's are contiguous (64·R + 2·64 values: 0.3 MB) — and results leave by bulk
+// stores (cp.async.bulk.global.shared::cta + bulk_group).  Same butterflies, same twiddles, same order: bit-identical output.
+constexpr u32 NTT_P = 16;          // proofs per tile
+constexpr u32 NTT_TILED_MAX_BATCH = 256;
+constexpr u32 NTT_MID = 64;        // rows of the middle block (6 stages)
+static __device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, u32 bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_addr(smem_src)), "r"(bytes) : "memory");
+}
+static __device__ __forceinline__ void tma_store_commit_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the writes have landed, not just the shared-memory reads
+}
+static __device__ __forceinline__ void mbar_expect(u64* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+static __device__ __forceinline__ void tma_load_1d_noexpect(void* smem_dst, const void* gmem_src, u32 bytes, u64* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(smem_dst)), "l"(gmem_src),
+                 "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+static __device__ __forceinline__ Fr sm_ld(const uint4* sm, u32 row, u32 p) {
+    const uint4 lo = sm[(row * NTT_P + p) * 2], hi = sm[(row * NTT_P + p) * 2 + 1];
+    Fr r;
+    r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w; r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+    return r;
+}
+static __device__ __forceinline__ void sm_st(uint4* sm, u32 row, u32 p, const Fr& v) {
+    sm[(row * NTT_P + p) * 2] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    sm[(row * NTT_P + p) * 2 + 1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+static __device__ __forceinline__ Fr sm_tw(const uint4* tw, u32 i) {
+    const uint4 lo = tw[2 * i], hi = tw[2 * i + 1];
+    Fr r;
+    r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w; r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+    return r;
+}
+// outer stages.  DIT = false: kernel A (stages with local half R/2 … 1, twiddle on the difference); DIT = true: kernel C (local half
+// 1 … R/2, twiddle on the second operand).  tw_tiles: [64][R] values, tile i0's at offset i0·R, stage with local half lh at R − 2·lh.
+// grid: (64, ceil(B / NTT_P)); dynamic shared memory: R·NTT_P·32 + R·32 + 8 bytes
+template <bool DIT>
+__global__ void __launch_bounds__(256) k_ntt_outer(Fr* __restrict__ x, u32 B, u32 R, const Fr* __restrict__ tw_tiles) {
+    extern __shared__ __align__(128) uint4 sm[];
+    uint4* tw = sm + (size_t)R * NTT_P * 2;
+    u64* bar = reinterpret_cast<u64*>(tw + (size_t)R * 2);
+    const u32 i0 = blockIdx.x, p0 = blockIdx.y * NTT_P;
+    const u32 pv = B - p0 < NTT_P ? B - p0 : NTT_P;            // proofs really in this tile
+    const u32 row_bytes = pv * 32;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect(bar, R * row_bytes + R * 32);
+    }
+    __syncthreads();
+    if (threadIdx.x < R) tma_load_1d_noexpect(sm + (size_t)threadIdx.x * NTT_P * 2, x + (size_t)(i0 + NTT_MID * threadIdx.x) * B + p0, row_bytes, bar);
+    if (threadIdx.x == 255) tma_load_1d_noexpect(tw, tw_tiles + (size_t)i0 * R, R * 32, bar);
+    mbar_wait(bar, 0);
+    const u32 p = threadIdx.x & (NTT_P - 1), q = threadIdx.x / NTT_P;   // 16 butterfly lanes per proof
+    const u32 pairs = R / 2;
+    for (u32 st = 0; (1u << st) < R; st++) {
+        const u32 lh = DIT ? (1u << st) : (pairs >> st);
+        if (p < pv)
+            for (u32 t = q; t < pairs; t += 256 / NTT_P) {
+                const u32 kj = t & (lh - 1), k0 = ((t - kj) << 1) + kj, k1 = k0 + lh;
+                const Fr w = sm_tw(tw, R - 2 * lh + kj);
+                Fr u = sm_ld(sm, k0, p), v = sm_ld(sm, k1, p);
+                if (DIT) {
+                    v = v * w;
+                    sm_st(sm, k0, p, u + v);
+                    sm_st(sm, k1, p, u - v);
+                } else {
+                    sm_st(sm, k0, p, u + v);
+                    sm_st(sm, k1, p, (u - v) * w);
+                }
+            }
+        __syncthreads();
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes above → visible to the bulk stores below
+    __syncthreads();
+    if (threadIdx.x < R) {
+        tma_store_1d(x + (size_t)(i0 + NTT_MID * threadIdx.x) * B + p0, sm + (size_t)threadIdx.x * NTT_P * 2, row_bytes);
+        tma_store_commit_wait();
+    }
+}
+// middle block: rows [64·blk, 64·blk + 64).  tw_mid: [2][64] values (DIF twiddles then DIT twiddles, stage with half h at 64 − 2·h);
+// factor: the per-row coset / 1/n factor in bit-reversed position order (CircuitDev::coset).
+// grid: (n / 64, ceil(B / NTT_P)); dynamic shared memory: 64·NTT_P·32 + 3·64·32 + 8 bytes
+__global__ void __launch_bounds__(256) k_ntt_middle(Fr* __restrict__ x, u32 B, const Fr* __restrict__ tw_mid, const Fr* __restrict__ factor) {
+    extern __shared__ __align__(128) uint4 sm[];
+    uint4* tw = sm + (size_t)NTT_MID * NTT_P * 2;       // 128 twiddles
+    uint4* fac = tw + 2 * 2 * NTT_MID;                  // 64 factors
+    u64* bar = reinterpret_cast<u64*>(fac + 2 * NTT_MID);
+    const u32 r0 = blockIdx.x * NTT_MID, p0 = blockIdx.y * NTT_P;
+    const u32 pv = B - p0 < NTT_P ? B - p0 : NTT_P;
+    const u32 row_bytes = pv * 32;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect(bar, NTT_MID * row_bytes + 3 * NTT_MID * 32);
+    }
+    __syncthreads();
+    if (threadIdx.x < NTT_MID) tma_load_1d_noexpect(sm + (size_t)threadIdx.x * NTT_P * 2, x + (size_t)(r0 + threadIdx.x) * B + p0, row_bytes, bar);
+    if (threadIdx.x == 254) tma_load_1d_noexpect(tw, tw_mid, 2 * NTT_MID * 32, bar);
+    if (threadIdx.x == 255) tma_load_1d_noexpect(fac, factor + r0, NTT_MID * 32, bar);
+    mbar_wait(bar, 0);
+    const u32 p = threadIdx.x & (NTT_P - 1), q = threadIdx.x / NTT_P;
+    const u32 pairs = NTT_MID / 2;
+    for (u32 h = pairs; h >= 1; h >>= 1) {           // decimation in frequency, halves 32 … 1
+        if (p < pv)
+            for (u32 t = q; t < pairs; t += 256 / NTT_P) {
+                const u32 kj = t & (h - 1), k0 = ((t - kj) << 1) + kj, k1 = k0 + h;
+                const Fr u = sm_ld(sm, k0, p), v = sm_ld(sm, k1, p);
+                sm_st(sm, k0, p, u + v);
+                sm_st(sm, k1, p, (u - v) * sm_tw(tw, NTT_MID - 2 * h + kj));
+            }
+        __syncthreads();
+    }
+    if (p < pv)                                      // · g^rev(row) / n
+        for (u32 k = q; k < NTT_MID; k += 256 / NTT_P) sm_st(sm, k, p, sm_ld(sm, k, p) * sm_tw(fac, k));
+    __syncthreads();
+    for (u32 h = 1; h <= pairs; h <<= 1) {           // decimation in time, halves 1 … 32
+        if (p < pv)
+            for (u32 t = q; t < pairs; t += 256 / NTT_P) {
+                const u32 kj = t & (h - 1), k0 = ((t - kj) << 1) + kj, k1 = k0 + h;
+                const Fr u = sm_ld(sm, k0, p), v = sm_ld(sm, k1, p) * sm_tw(tw, NTT_MID + NTT_MID - 2 * h + kj);
+                sm_st(sm, k0, p, u + v);
+                sm_st(sm, k1, p, u - v);
+            }
+        __syncthreads();
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < NTT_MID) {
+        tma_store_1d(x + (size_t)(r0 + threadIdx.x) * B + p0, sm + (size_t)threadIdx.x * NTT_P * 2, row_bytes);
+        tma_store_commit_wait();
+    }
+}
+// iNTT (unscaled, DIF) → × coset factors → NTT (DIT) of one [n][B] buffer in three launches
+static void ntt_chain_tiled(Fr* x, const CircuitDev& c, u32 B, cudaStream_t s) {
+    const u32 R = c.domain / NTT_MID;                          // rows of an outer tile = 2^(L − 6)
+    const size_t smem_outer = (size_t)R * NTT_P * 32 + (size_t)R * 32 + 16, smem_mid = (size_t)NTT_MID * NTT_P * 32 + 3 * NTT_MID * 32 + 16;
+    const dim3 grid_outer(NTT_MID, (B + NTT_P - 1) / NTT_P), grid_mid(c.domain / NTT_MID, (B + NTT_P - 1) / NTT_P);
+    ZK_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_outer<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_outer));
+    ZK_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_outer<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_outer));
+    ZK_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_middle, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mid));
+    k_ntt_outer<false><<<grid_outer, 256, smem_outer, s>>>(x, B, R, c.tw_tile_dif);
+    k_ntt_middle<<<grid_mid, 256, smem_mid, s>>>(x, B, c.tw_mid, c.coset);
+    k_ntt_outer<true><<<grid_outer, 256, smem_outer, s>>>(x, B, R, c.tw_tile_dit);
+    ZK_CUDA_CHECK(cudaGetLastError());
+}
+static bool ntt_tiled_ok(const CircuitDev& c) { return c.tw_tile_dif && c.log_domain >= 8 && c.log_domain <= 13; }
+
 void launch_qap(const CircuitDev& c, const Fr* d_vals, Fr* d_a, Fr* d_b, Fr* d_c, u32 B, cudaStream_t s) {
     dim3 grid((B + 127) / 128, c.domain);
     k_matvec<<<grid, 128, 0, s>>>(c, d_vals, d_a, d_b, d_c, B);
     Fr* bufs[3] = {d_a, d_b, d_c};
+    // Which form?  Measured on a B200 (profiles/r02g_ntt_msm_affine.txt): the tiled chain wins where launches and HBM round trips
+    // dominate — single proof 0.54 → 0.37 ms for the whole QAP (11 launches instead of 47) — is level at batch 256 (1.88 / 1.89 ms)
+    // and LOSES at batch 4 096 (24.8 → 26.5 ms): there the two-stage passes already keep the multiplier 86 % busy, and a stage in
+    // shared memory pays a barrier plus four 128-bit shared accesses per butterfly.  So: tiled up to NTT_TILED_MAX_BATCH proofs.
+    const bool tiled = B <= NTT_TILED_MAX_BATCH && ntt_tiled_ok(c);
     for (Fr* x : bufs) {
+        if (tiled) { ntt_chain_tiled(x, c, B, s); continue; }
         ntt_dif(x, c.log_domain, B, c.tw_inv, s);            // ifft (unscaled), output bit-reversed
         k_scale_rows<<<grid, 128, 0, s>>>(x, B, c.coset);    // · g^i / n   (qap.rs:72-79)
         ntt_dit(x, c.log_domain, B, c.tw_fwd, s);            // fft on the coset, natural order

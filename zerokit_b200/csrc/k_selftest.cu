@@ -96,10 +96,159 @@ __global__ void __launch_bounds__(256) k_pipe_probe(u64* __restrict__ out, int i
     }
     out[t] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7 ^ (u64)__double_as_longlong(d0 + d1 + d2 + d3 + d4 + d5 + d6 + d7);
 }
+
+// ---- batched-affine probe (measured, not estimated) -------------------------------------------------------------------
+// Bucket-style accumulation, M independent running sums per thread kept in global memory (as Pippenger buckets are), one random-ish
+// point added to each per round.  mode 0: XYZZ mixed additions (what every MSM kernel of this library does: 8M + 2S, no inversion);
+// mode 1 / 2: affine additions that share ONE inversion per thread and round (Montgomery's trick over the M denominators):
+// 3 products per addition for the trick + 2M + 1S for the addition itself + the inversion / M; mode 1 inverts by Fermat (a^(q−2),
+// ≈ 380 products), mode 2 by the binary extended Euclid below.  Probe only: no special cases (the points are distinct by
+// construction), results are folded into a checksum so nothing is optimised away.
+__device__ void raw_shr1(u32* a, u32 top) {
+#pragma unroll
+    for (int i = 0; i < 7; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
+    a[7] = (a[7] >> 1) | (top << 31);
+}
+__device__ Fq fq_inv_egcd(const Fq& a) {   // a ≠ 0, Montgomery in and out
+    u32 u[8], v[8], x1[8], x2[8], p[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { u[i] = a.l[i]; p[i] = FqCfg::p(i); v[i] = p[i]; x1[i] = 0; x2[i] = 0; }
+    x1[0] = 1;
+    auto is_one = [](const u32* w) { u32 t = w[0] ^ 1u; for (int i = 1; i < 8; i++) t |= w[i]; return t == 0; };
+    auto halve_mod = [&](u32* x) {   // x/2 mod p
+        u32 carry = 0;
+        if (x[0] & 1) carry = Fq::raw_add(x, x, p);
+        raw_shr1(x, carry);
+    };
+    while (!is_one(u) && !is_one(v)) {
+        while (!(u[0] & 1)) { raw_shr1(u, 0); halve_mod(x1); }
+        while (!(v[0] & 1)) { raw_shr1(v, 0); halve_mod(x2); }
+        if (Fq::raw_cmp(u, v) >= 0) {
+            Fq::raw_sub(u, u, v);
+            if (Fq::raw_sub(x1, x1, x2)) Fq::raw_add(x1, x1, p);
+        } else {
+            Fq::raw_sub(v, v, u);
+            if (Fq::raw_sub(x2, x2, x1)) Fq::raw_add(x2, x2, p);
+        }
+    }
+    Fq r;   // raw inverse of a·R is a⁻¹·R⁻¹: one Montgomery product by R³ brings it back to a⁻¹·R
+    const u32* w = is_one(u) ? x1 : x2;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = w[i];
+    const Fq r3 = Fq::rsquared() * Fq::rsquared();
+    return r * r3;
+}
+__global__ void k_probe_points(G1Affine* __restrict__ pts, u32 n) {   // pts[i] = (i + 2)·G
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const G1Affine g = {Fq::from_u32(1), Fq::from_u32(2)};
+    u32 k[8] = {i + 2, 0, 0, 0, 0, 0, 0, 0};
+    pts[i] = G1XYZZ::from_affine(g).mul(k).to_affine();
+}
+__global__ void k_egcd_check(const G1Affine* __restrict__ pts, u32 n, u32* __restrict__ bad) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Fq a = pts[i].x * pts[(i * 7 + 3) % n].y + Fq::from_u32(i + 1);
+    if (a.is_zero()) return;
+    if (!(fq_inv_egcd(a) == a.inv()) || !(fq_inv_egcd(a) * a == Fq::one())) atomicAdd(bad, 1u);
+}
+template <int MODE>
+__global__ void __launch_bounds__(128) k_affine_probe(const G1Affine* __restrict__ pts, u32 n_pts, int M, int rounds, G1XYZZ* __restrict__ acc_x,
+                                                      G1Affine* __restrict__ acc_a, Fq* __restrict__ pref, u32* __restrict__ check) {
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x, T = gridDim.x * blockDim.x;
+    // start every running sum at a different point so that no addition meets its own operand
+    for (int m = 0; m < M; m++) {
+        const G1Affine p0 = pts[(t * 7 + m * 131 + 1) % n_pts];
+        if (MODE == 0) acc_x[(size_t)m * T + t] = G1XYZZ::from_affine(p0);
+        else acc_a[(size_t)m * T + t] = p0;
+    }
+    for (int r = 0; r < rounds; r++) {
+        if (MODE == 0) {
+            for (int m = 0; m < M; m++) {
+                G1XYZZ a = acc_x[(size_t)m * T + t];
+                a.add_affine(pts[(t * 13 + m * 17 + r * 29 + 5) % n_pts]);
+                acc_x[(size_t)m * T + t] = a;
+            }
+        } else {
+            Fq run = Fq::one();
+            for (int m = 0; m < M; m++) {   // forward: prefix products of the denominators
+                const Fq d = ldg_fp(&pts[(t * 13 + m * 17 + r * 29 + 5) % n_pts].x) - ld_fp(&acc_a[(size_t)m * T + t].x);
+                pref[(size_t)m * T + t] = run;
+                run = run * (d.is_zero() ? Fq::one() : d);
+            }
+            Fq inv = MODE == 1 ? run.inv() : fq_inv_egcd(run);
+            for (int m = M - 1; m >= 0; m--) {   // backward: individual inverses, then the additions
+                const G1Affine q = pts[(t * 13 + m * 17 + r * 29 + 5) % n_pts];
+                G1Affine a = acc_a[(size_t)m * T + t];
+                Fq d = q.x - a.x;
+                if (d.is_zero()) d = Fq::one();
+                const Fq dinv = inv * pref[(size_t)m * T + t];
+                inv = inv * d;
+                const Fq lam = (q.y - a.y) * dinv;
+                const Fq x3 = lam.sqr() - a.x - q.x;
+                a.y = lam * (a.x - x3) - a.y;
+                a.x = x3;
+                acc_a[(size_t)m * T + t] = a;
+            }
+        }
+    }
+    u32 c = 0;
+    for (int m = 0; m < M; m++) c ^= MODE == 0 ? acc_x[(size_t)m * T + t].X.l[0] : acc_a[(size_t)m * T + t].x.l[0];
+    check[t] = c;
+}
 }  // namespace zk
 
 using namespace zk;
 extern "C" {
+// additions per second of the batched-affine probe; mode 0 XYZZ, 1 affine + Fermat inversion, 2 affine + binary EGCD; M running sums
+// per thread.  mode 3: self-check of the EGCD inversion against Fermat on 4 096 values (returns the number of mismatches).
+double rlnb200_affine_batch_probe(int mode, int M, int rounds) {
+    try {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const u32 n_pts = 4096;
+        G1Affine* pts = nullptr;
+        ZK_CUDA_CHECK(cudaMalloc(&pts, sizeof(G1Affine) * n_pts));
+        k_probe_points<<<n_pts / 128, 128>>>(pts, n_pts);
+        if (mode == 3) {
+            u32* bad = nullptr;
+            ZK_CUDA_CHECK(cudaMalloc(&bad, 4));
+            ZK_CUDA_CHECK(cudaMemset(bad, 0, 4));
+            k_egcd_check<<<n_pts / 128, 128>>>(pts, n_pts, bad);
+            u32 h = 0;
+            ZK_CUDA_CHECK(cudaMemcpy(&h, bad, 4, cudaMemcpyDeviceToHost));
+            cudaFree(bad); cudaFree(pts);
+            return (double)h;
+        }
+        const u32 T = (u32)sms * 4 * 128;   // 4 CTAs of 128 threads per SM
+        G1XYZZ* ax = nullptr; G1Affine* aa = nullptr; Fq* pref = nullptr; u32* check = nullptr;
+        ZK_CUDA_CHECK(cudaMalloc(&ax, sizeof(G1XYZZ) * (size_t)M * T));
+        ZK_CUDA_CHECK(cudaMalloc(&aa, sizeof(G1Affine) * (size_t)M * T));
+        ZK_CUDA_CHECK(cudaMalloc(&pref, sizeof(Fq) * (size_t)M * T));
+        ZK_CUDA_CHECK(cudaMalloc(&check, 4 * (size_t)T));
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        auto run = [&](int r) {
+            if (mode == 0) k_affine_probe<0><<<T / 128, 128>>>(pts, n_pts, M, r, ax, aa, pref, check);
+            else if (mode == 1) k_affine_probe<1><<<T / 128, 128>>>(pts, n_pts, M, r, ax, aa, pref, check);
+            else k_affine_probe<2><<<T / 128, 128>>>(pts, n_pts, M, r, ax, aa, pref, check);
+        };
+        run(1);
+        cudaEventRecord(e0);
+        run(rounds);
+        cudaEventRecord(e1);
+        ZK_CUDA_CHECK(cudaEventSynchronize(e1));
+        g_launch_count += 3;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaFree(ax); cudaFree(aa); cudaFree(pref); cudaFree(check); cudaFree(pts);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        return (double)T * M * rounds / (ms * 1e-3);
+    } catch (const CudaError&) {
+        return -1.0;
+    }
+}
 int rlnb200_field_op(int field, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out, RlnString* err) {
     try {
         void *da = nullptr, *db = nullptr, *dout = nullptr;

@@ -547,7 +547,7 @@ class Rln {
     InputSlots slots_{};
 
     // device-resident circuit
-    DevMem d_prog_, d_consts_, d_signals_, d_a_ptr_, d_a_col_, d_a_val_, d_b_ptr_, d_b_col_, d_b_val_, d_tw_inv_, d_tw_fwd_, d_coset_;
+    DevMem d_prog_, d_consts_, d_signals_, d_a_ptr_, d_a_col_, d_a_val_, d_b_ptr_, d_b_col_, d_b_val_, d_tw_inv_, d_tw_fwd_, d_coset_, d_tw_tile_dif_, d_tw_tile_dit_, d_tw_mid_;
     CircuitDev circ_{};
     // fixed-base tables
     DevMem d_sched_;
@@ -804,6 +804,25 @@ void Rln::build_circuit() {
         d_tw_fwd_.upload(fwd.data(), fwd.size() * sizeof(Fr));
         d_tw_inv_.upload(inv.data(), inv.size() * sizeof(Fr));
         d_coset_.upload(coset.data(), coset.size() * sizeof(Fr));
+        if (log_domain_ >= 8 && log_domain_ <= 13) {   // tile-major twiddles of the tiled transforms (k_prover.cu k_ntt_outer / k_ntt_middle)
+            const u32 MID = 64, R = n / MID;
+            std::vector<Fr> t_dif((size_t)MID * R, Fr::one()), t_dit((size_t)MID * R, Fr::one()), mid(2 * MID, Fr::one());
+            for (u32 i0 = 0; i0 < MID; i0++)
+                for (u32 lh = 1; lh <= R / 2; lh <<= 1)
+                    for (u32 kj = 0; kj < lh; kj++) {
+                        const u32 e = (i0 + MID * kj) * (R / (2 * lh));   // exponent < n/2: j_global · stride of that stage
+                        t_dif[(size_t)i0 * R + R - 2 * lh + kj] = inv[e];
+                        t_dit[(size_t)i0 * R + R - 2 * lh + kj] = fwd[e];
+                    }
+            for (u32 h = 1; h <= MID / 2; h <<= 1)
+                for (u32 j = 0; j < h; j++) {
+                    mid[MID - 2 * h + j] = inv[(size_t)j * (n / (2 * h))];
+                    mid[MID + MID - 2 * h + j] = fwd[(size_t)j * (n / (2 * h))];
+                }
+            d_tw_tile_dif_.upload(t_dif.data(), t_dif.size() * sizeof(Fr));
+            d_tw_tile_dit_.upload(t_dit.data(), t_dit.size() * sizeof(Fr));
+            d_tw_mid_.upload(mid.data(), mid.size() * sizeof(Fr));
+        }
     }
     circ_.n_nodes = (u32)gh_.prog.size();
     circ_.n_slots = gh_.n_slots;
@@ -835,6 +854,11 @@ void Rln::build_circuit() {
     circ_.tw_inv = d_tw_inv_.as<Fr>();
     circ_.tw_fwd = d_tw_fwd_.as<Fr>();
     circ_.coset = d_coset_.as<Fr>();
+    if (d_tw_tile_dif_.p) {
+        circ_.tw_tile_dif = d_tw_tile_dif_.as<Fr>();
+        circ_.tw_tile_dit = d_tw_tile_dit_.as<Fr>();
+        circ_.tw_mid = d_tw_mid_.as<Fr>();
+    }
     ZK_CUDA_CHECK(cudaDeviceSynchronize());
 }
 

@@ -315,9 +315,12 @@ class RLNWitnessInput:
         return out
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            ffi.lib().ffi_rln_witness_input_free(self._h)
-            self._h = c_void_p(None)
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                ffi.lib().ffi_rln_witness_input_free(self._h)
+                self._h = c_void_p(None)
+        except Exception:   # interpreter shutdown: module globals may already be gone
+            pass
 
 
 class RLNPartialWitnessInput:
@@ -368,9 +371,12 @@ class RLNPartialWitnessInput:
         return list(_take_vec_u8(ffi.lib().ffi_rln_partial_witness_input_get_identity_path_index(byref(self._h))))
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            ffi.lib().ffi_rln_partial_witness_input_free(self._h)
-            self._h = c_void_p(None)
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                ffi.lib().ffi_rln_partial_witness_input_free(self._h)
+                self._h = c_void_p(None)
+        except Exception:   # interpreter shutdown: module globals may already be gone
+            pass
 
 
 class RLNPartialProof:
@@ -403,9 +409,12 @@ class RLNPartialProof:
         return ffi.lib().ffi_rln_partial_proof_get_version_byte(byref(self._h))
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            ffi.lib().ffi_rln_partial_proof_free(self._h)
-            self._h = c_void_p(None)
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                ffi.lib().ffi_rln_partial_proof_free(self._h)
+                self._h = c_void_p(None)
+        except Exception:   # interpreter shutdown: module globals may already be gone
+            pass
 
 
 class RLNProofValues:
@@ -477,9 +486,12 @@ class RLNProof:
             L.ffi_rln_proof_values_free(pv)
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            ffi.lib().ffi_rln_proof_free(self._h)
-            self._h = c_void_p(None)
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                ffi.lib().ffi_rln_proof_free(self._h)
+                self._h = c_void_p(None)
+        except Exception:   # interpreter shutdown: module globals may already be gone
+            pass
 
 
 # ------------------------------------------------------------------------------- the RLN object
@@ -514,9 +526,12 @@ class RLN:
         return cls(_check_ptr(ffi.lib().ffi_rln_new_with_params(tree_depth, byref(_vec_u8(zkey)), byref(_vec_u8(graph)), config_path.encode())))
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value and not getattr(self, "_borrowed", False):
-            ffi.lib().ffi_rln_free(self._h)
-            self._h = c_void_p(None)
+        try:
+            if getattr(self, "_h", None) and self._h.value and not getattr(self, "_borrowed", False):
+                ffi.lib().ffi_rln_free(self._h)
+                self._h = c_void_p(None)
+        except Exception:   # interpreter shutdown: module globals may already be gone
+            pass
 
     # ---- tree ------------------------------------------------------------------------------
     def tree_depth(self):
@@ -769,9 +784,12 @@ class RLNMulti:
         self._depth = tree_depth
 
     def __del__(self):
-        if getattr(self, "_m", None) and self._m.value:
-            ffi.lib().rlnb200_multi_free(self._m)
-            self._m = c_void_p(None)
+        try:
+            if getattr(self, "_m", None) and self._m.value:
+                ffi.lib().rlnb200_multi_free(self._m)
+                self._m = c_void_p(None)
+        except Exception:   # interpreter shutdown: module globals may already be gone
+            pass
 
     def device_count(self):
         return ffi.lib().rlnb200_multi_device_count(self._m)
@@ -839,9 +857,12 @@ class G1Msm:
             raise RLNError(_take_string(err) or "msm_new failed")
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            ffi.lib().rlnb200_msm_free(self._h)
-            self._h = c_void_p(None)
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                ffi.lib().rlnb200_msm_free(self._h)
+                self._h = c_void_p(None)
+        except Exception:   # interpreter shutdown: module globals may already be gone
+            pass
 
     def msm(self, bases: bytes, scalars: bytes, n: int) -> bytes:
         out = ctypes.create_string_buffer(64)

@@ -29,9 +29,12 @@ class _Handle:
         self._h = c_void_p(handle)
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            getattr(ffi.lib(), self._free)(self._h)
-            self._h = c_void_p(None)
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                getattr(ffi.lib(), self._free)(self._h)
+                self._h = c_void_p(None)
+        except Exception:   # interpreter shutdown: module globals may already be gone
+            pass
 
 
 class WitnessV3(_Handle):
