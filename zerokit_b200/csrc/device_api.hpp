@@ -99,6 +99,7 @@ void launch_qap(const CircuitDev& c, const Fr* d_vals, Fr* d_a, Fr* d_b, Fr* d_c
 // plain batched NTT for tests: data [n][B] natural order in/out
 void launch_ntt_test(Fr* d_data, u32 log_n, u32 B, bool inverse, const Fr* tw, cudaStream_t s);
 u32 ntt_launches_per_transform(u32 log_n);
+u32 qap_launch_count(const CircuitDev& c, u32 B);
 
 // ---- k_msm_fixed.cu ------------------------------------------------------------------------
 struct MsmGroupDev {

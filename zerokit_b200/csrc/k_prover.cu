@@ -484,6 +484,11 @@ static void ntt_chain_tiled(Fr* x, const CircuitDev& c, u32 B, cudaStream_t s) {
 }
 static bool ntt_tiled_ok(const CircuitDev& c) { return c.tw_tile_dif && c.log_domain >= 8 && c.log_domain <= 13; }
 
+// kernels one launch_qap enqueues (bench bookkeeping: gpu_launches)
+u32 qap_launch_count(const CircuitDev& c, u32 B) {
+    if (B <= NTT_TILED_MAX_BATCH && ntt_tiled_ok(c)) return 2 + 3 * 3;
+    return 2 + 3 * (2 * ntt_launches_per_transform(c.log_domain) + 1);
+}
 void launch_qap(const CircuitDev& c, const Fr* d_vals, Fr* d_a, Fr* d_b, Fr* d_c, u32 B, cudaStream_t s) {
     dim3 grid((B + 127) / 128, c.domain);
     k_matvec<<<grid, 128, 0, s>>>(c, d_vals, d_a, d_b, d_c, B);

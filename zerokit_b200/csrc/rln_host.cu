@@ -1361,7 +1361,7 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
         ZK_CUDA_CHECK(cudaEventRecord(ev_[3], s));
         if (d_values && phase != MSM_KNOWN) ZK_CUDA_CHECK(cudaStreamWaitEvent(s, join_, 0));
         ZK_CUDA_CHECK(cudaEventRecord(ev_[4], s));
-        g_launch_count += 1 + (phase != MSM_KNOWN ? 2 + 3 * (2 * ntt_launches_per_transform(log_domain_) + 1) : 0) + 6 + (d_values ? 1 : 0);
+        g_launch_count += 1 + (phase != MSM_KNOWN ? qap_launch_count(circ_, B) : 0) + 6 + (d_values ? 1 : 0);
         // graph-evaluation failures surface as errors, like WitnessCalcError::GraphEvaluation (rln/src/circuit/iden3calc.rs:52-53)
         std::vector<u32> err(B);
         ZK_CUDA_CHECK(cudaMemcpyAsync(err.data(), ws_err_.p, 4 * B, cudaMemcpyDeviceToHost, s));
@@ -1655,7 +1655,7 @@ void Rln::debug_w_h(const Witness& w, uint8_t* w_out, uint8_t* h_out) {
     ZK_CUDA_CHECK(cudaMemcpyAsync(ws_inputs_.p, slots.data(), slots.size(), cudaMemcpyHostToDevice, stream_));
     launch_witness(circ_, ws_inputs_.as<uint8_t>(), ws_vals_.as<Fr>(), 1, ws_err_.as<u32>(), stream_);
     launch_qap(circ_, ws_vals_.as<Fr>(), ws_a_.as<Fr>(), ws_b_.as<Fr>(), ws_c_.as<Fr>(), 1, stream_);
-    g_launch_count += 3 + 3 * (2 * ntt_launches_per_transform(log_domain_) + 1);
+    g_launch_count += 1 + qap_launch_count(circ_, 1);
     DevMem vals_b, h_b;
     vals_b.alloc(32 * gh_.prog.size());
     h_b.alloc(32 * (size_t)domain_);
