@@ -506,7 +506,7 @@ def run_gpu(args, rank, local_rank, world):
     line["cpu_rows"] = cpu_rows
     # ---- batch verification of the timed batch's proofs (rlnb200_verify_batch: host records in, flags out)
     line["verify_batch"] = {"proofs": total, "ms": verify_batch_ms, "proofs_per_s": total / (verify_batch_ms * 1e-3),
-                            "api": "rlnb200_verify_batch (decompression + subgroup checks + 4 Miller loops + final exponentiation per proof)"}
+                            "api": "rlnb200_verify_batch (decompression + G2 membership + one merged Miller loop + final exponentiation per proof, one thread each)"}
     # ---- single proof / single verification through the reference's own entry points (BASELINE.json configs[0])
     try:
         wit = z.RLNWitnessInput.from_bytes_le(all_recs[:REC_IN])
