@@ -71,14 +71,11 @@ __device__ int decompress_g1(const uint8_t* b, G1Affine& p) {
     const u32 flags = x[7] >> 30;
     x[7] &= 0x3fffffffu;
     if (flags == 3) return 1;
-    if (flags & 1) {  // infinity
-        u32 any = 0;
-        for (int i = 0; i < 8; i++) any |= x[i];
-        if (any) return 1;
-        p = G1Affine::infinity();
+    if (!fq_canonical_ok(x)) return 1;
+    if (flags & 1) {  // infinity: ark-serialize reads x as a canonical field element and then ignores it (ark-ec short_weierstrass
+        p = G1Affine::infinity();   // deserialize_with_mode: `if flags.is_infinity() { Self::identity() }`)
         return 0;
     }
-    if (!fq_canonical_ok(x)) return 1;
     Fq X = Fq::from_canonical(x), y;
     if (!fq_sqrt(X.sqr() * X + Fq::from_u32(3), y)) return 1;
     const bool want_larger = (flags & 2) != 0;
@@ -93,14 +90,11 @@ __device__ int decompress_g2(const uint8_t* b, G2Affine& p) {
     const u32 flags = x1[7] >> 30;
     x1[7] &= 0x3fffffffu;
     if (flags == 3) return 1;
-    if (flags & 1) {
-        u32 any = 0;
-        for (int i = 0; i < 8; i++) any |= x0[i] | x1[i];
-        if (any) return 1;
+    if (!fq_canonical_ok(x0) || !fq_canonical_ok(x1)) return 1;
+    if (flags & 1) {   // infinity with any canonical x, as ark-serialize accepts it
         p = G2Affine::infinity();
         return 0;
     }
-    if (!fq_canonical_ok(x0) || !fq_canonical_ok(x1)) return 1;
     Fq2 X = {Fq::from_canonical(x0), Fq::from_canonical(x1)};
     Fq2 y;
     if (!fq2_sqrt(X.sqr() * X + c_pair.twist_b, y)) return 1;
