@@ -214,6 +214,16 @@ int emu_g2_subgroup_both(const uint8_t* p) {
     const G2Affine P = ld_g2(p);
     return (g2_in_subgroup_6x2(&pt, P) ? 1 : 0) | (g2_in_subgroup(&pt, P) ? 2 : 0);
 }
+// the low-latency Montgomery product (fp.cuh mul_lowlat; device-only in the product, plain C so it runs here): Montgomery in / out
+void emu_mul_lowlat(int field, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+    if (field == 0) { Fr x = ld<Fr>(a), y = ld<Fr>(b), r; Fr::mul_lowlat(r.l, x.l, y.l); st(out, r); }
+    else { Fq x = ld<Fq>(a), y = ld<Fq>(b), r; Fq::mul_lowlat(r.l, x.l, y.l); st(out, r); }
+}
+// with the first operand replaced by p itself (neg_lazy operands reach the product as p − 0 = p): must give 0
+void emu_mul_lowlat_p(int field, const uint8_t* b, uint8_t* out) {
+    if (field == 0) { Fr x = Fr::zero().neg_lazy(), y = ld<Fr>(b), r; Fr::mul_lowlat(r.l, x.l, y.l); st(out, r); }
+    else { Fq x = Fq::zero().neg_lazy(), y = ld<Fq>(b), r; Fq::mul_lowlat(r.l, x.l, y.l); st(out, r); }
+}
 // witness-graph VM: one op on canonical values
 int emu_vm_duo(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     Fr r;

@@ -49,6 +49,26 @@ def test_field_ops(emu):
             assert fop(field, 3, a) == pow(a, -1, p)
 
 
+def test_low_latency_product(emu):
+    """fp.cuh mul_lowlat (separated Montgomery reduction on 4×4-limb blocks, the product of the latency-bound kernels) against
+    Python integers: edge values, values with saturated words, random values; and the lazily negated operand p"""
+    rnd = random.Random(77)
+    for field, p in ((0, R), (1, Q)):
+        edge = [0, 1, 2, p - 1, p - 2, (p - 1) // 2, (1 << 128) - 1, 1 << 128, (1 << 253) + 12345, 0xFFFFFFFF, 0xFFFFFFFF00000000FFFFFFFF]
+        sat = [sum(w << (32 * k) for k, w in enumerate([rnd.choice([0xFFFFFFFF, 0x80000000, 0, 1, rnd.getrandbits(32)]) for _ in range(7)] + [rnd.randrange(0x30000000)])) % p
+               for _ in range(200)]
+        vals = edge + sat + [rnd.randrange(p) for _ in range(400)]
+        for i, a in enumerate(vals):
+            for b in (vals[(i * 7 + 3) % len(vals)], vals[(i * 13 + 1) % len(vals)], a):
+                out = ctypes.create_string_buffer(32)
+                emu.emu_mul_lowlat(field, b32(a), b32(b), out)
+                assert int.from_bytes(out.raw, "little") == a * b % p, (field, a, b)
+        for b in vals[:50]:
+            out = ctypes.create_string_buffer(32)
+            emu.emu_mul_lowlat_p(field, b32(b), out)
+            assert int.from_bytes(out.raw, "little") == 0
+
+
 def test_poseidon(emu):
     for v in ([0], [1], [R - 1], [0, 1], [5, R - 2], [1, 2, 3], [R - 1, 0, 7]):
         out = ctypes.create_string_buffer(32)

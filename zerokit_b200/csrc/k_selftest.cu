@@ -196,10 +196,61 @@ __global__ void __launch_bounds__(128) k_affine_probe(const G1Affine* __restrict
     for (int m = 0; m < M; m++) c ^= MODE == 0 ? acc_x[(size_t)m * T + t].X.l[0] : acc_a[(size_t)m * T + t].x.l[0];
     check[t] = c;
 }
+// ---- latency probe: cycles per DEPENDENT product in a lone warp (what the witness VM and every one-thread-per-proof chain pay) -----
+// kind 0: mul_ptx (fewest wide MADs, two long carry chains), 1: mul_portable (CIOS in C), 2: mul_lowlat (4×4 blocks, separated
+// reduction), 3: sqr_ptx, 4: modular addition; `lanes` live lanes of ONE warp on one SM
+template <int KIND>
+__global__ void k_latency_probe(Fq* __restrict__ data, int iters, long long* __restrict__ cycles) {
+    Fq a = data[threadIdx.x], b = data[32 + threadIdx.x];
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; i++) {
+        Fq r;
+#if ZK_PTX
+        if (KIND == 0) Fq::mul_ptx(r.l, a.l, b.l);
+        else if (KIND == 1) Fq::mul_portable(r.l, a.l, b.l);
+        else if (KIND == 2) Fq::mul_lowlat(r.l, a.l, b.l);
+        else if (KIND == 3) Fq::sqr_ptx(r.l, a.l);
+        else r = a + b;
+#else
+        r = a + b;
+#endif
+        a = r;
+    }
+    const long long t1 = clock64();
+    data[threadIdx.x] = a;
+    if (threadIdx.x == 0) *cycles = t1 - t0;
+}
 }  // namespace zk
 
 using namespace zk;
 extern "C" {
+double rlnb200_latency_probe(int kind, int lanes, int iters) {
+    try {
+        Fq* d = nullptr;
+        long long* c = nullptr;
+        ZK_CUDA_CHECK(cudaMalloc(&d, sizeof(Fq) * 64));
+        ZK_CUDA_CHECK(cudaMalloc(&c, 8));
+        ZK_CUDA_CHECK(cudaMemset(d, 0x11, sizeof(Fq) * 64));
+        if (lanes < 1) lanes = 1;
+        if (lanes > 32) lanes = 32;
+        for (int rep = 0; rep < 2; rep++) {
+            switch (kind) {
+                case 0: k_latency_probe<0><<<1, lanes>>>(d, iters, c); break;
+                case 1: k_latency_probe<1><<<1, lanes>>>(d, iters, c); break;
+                case 2: k_latency_probe<2><<<1, lanes>>>(d, iters, c); break;
+                case 3: k_latency_probe<3><<<1, lanes>>>(d, iters, c); break;
+                default: k_latency_probe<4><<<1, lanes>>>(d, iters, c); break;
+            }
+        }
+        long long h = 0;
+        ZK_CUDA_CHECK(cudaMemcpy(&h, c, 8, cudaMemcpyDeviceToHost));
+        g_launch_count += 2;
+        cudaFree(d); cudaFree(c);
+        return (double)h / iters;
+    } catch (const CudaError&) {
+        return -1.0;
+    }
+}
 // additions per second of the batched-affine probe; mode 0 XYZZ, 1 affine + Fermat inversion, 2 affine + binary EGCD; M running sums
 // per thread.  mode 3: self-check of the EGCD inversion against Fermat on 4 096 values (returns the number of mismatches).
 double rlnb200_affine_batch_probe(int mode, int M, int rounds) {

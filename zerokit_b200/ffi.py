@@ -341,6 +341,7 @@ def lib():
         "rlnb200_glv_double_mul": (c_int, [c_void_p, c_size_t, c_int, c_void_p, POINTER(RlnString)]),
         "rlnb200_pipe_probe": (c_int, [c_int, c_int, POINTER(c_double)]),
         "rlnb200_affine_batch_probe": (c_double, [c_int, c_int, c_int]),
+        "rlnb200_latency_probe": (c_double, [c_int, c_int, c_int]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
