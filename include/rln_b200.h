@@ -525,9 +525,8 @@ int rlnb200_field_op(int field, int op, const uint8_t *a, const uint8_t *b, size
  * global memory.  mode 0: XYZZ mixed additions (the library's form), 1: affine additions sharing one Fermat inversion per thread
  * and round, 2: the same with a binary extended-Euclid inversion, 3: self-check of that inversion (returns mismatches, 0 = good) */
 double rlnb200_affine_batch_probe(int mode, int M, int rounds);
-/* cycles per DEPENDENT Fq operation in a lone warp with `lanes` live lanes.  kind 0: the throughput product (129 wide MADs, two
- * carry chains through 16 rows), 1: portable CIOS, 2: the low-latency product (4x4-limb blocks, separated reduction, 164 wide
- * MADs), 3: dedicated squaring, 4: modular addition */
+/* cycles per DEPENDENT Fq operation in a lone warp with `lanes` live lanes.  kind 0: the library's product (129 wide MADs on two
+ * interleaved carry chains), 1: portable CIOS, 3: dedicated squaring, 4: modular addition */
 double rlnb200_latency_probe(int kind, int lanes, int iters);
 /* measured Montgomery-product rate (products/s over all SMs, CUDA-event timed); < 0 on error */
 double rlnb200_mul_throughput(int iters);

@@ -72,22 +72,33 @@ void emu_g2_add(const uint8_t* p, const uint8_t* q, uint8_t* out) {
     if (!b.is_inf()) a.add_affine(b);
     st_g2(out, a.to_affine());
 }
-// the witness VM exactly as k_witness runs it — bundle schedule, operand sources (ring / constant table / vals) — for ONE proof:
-// slots of a bundle are evaluated one after the other (they are independent), the ring is overwritten in place.
-// inputs: n_slots × 32 canonical bytes; out: n_nodes × 32 canonical bytes.  returns −1 on a parse error, else the "bad" flag.
-int emu_witness_scheduled(const uint8_t* graph, size_t glen, const uint8_t* inputs, uint8_t* out, uint32_t* n_bundles_out) {
+// the witness VM exactly as k_witness runs it — bundle schedule, operand sources (ring / constant table / vals), the store flag
+// in bit 31 of `out` — for ONE proof: slots of a bundle are evaluated one after the other (they are independent), the ring is
+// overwritten in place.  consts_resident = 1: the constant table is an operand source and dead constant nodes are skipped (the
+// kernel's shared-memory mode); 0: constants are ordinary nodes.  Nodes the kernel never stores to vals stay at the poison value,
+// so a consumer that reads one of them from vals shows up as a wrong wire.
+// inputs: n_slots × 32 canonical bytes; out: n_nodes × 32 canonical bytes (32 × 0xff for a node that is never stored).
+// returns −1 on a parse error, else the "bad" flag.
+int emu_witness_scheduled(const uint8_t* graph, size_t glen, const uint8_t* inputs, uint8_t* out, uint32_t* n_bundles_out, int consts_resident,
+                          uint32_t* n_stored_out) {
     GraphHost g;
     try { parse_graph(graph, glen, g); } catch (...) { return -1; }
     uint32_t nb = 0;
-    std::vector<VmRecord> recs = vm_build_schedule(g.prog, nb);
+    std::vector<uint8_t> is_signal(g.prog.size(), 0);
+    for (uint32_t node : g.signals) is_signal[node] = 1;
+    std::vector<VmRecord> recs = vm_build_schedule(g.prog, nb, &is_signal, consts_resident != 0);
     if (n_bundles_out) *n_bundles_out = nb;
-    std::vector<Fr> ring(VM_RING * VM_SLOTS), vals(g.prog.size()), consts(g.consts.size() / 32);
+    Fr poison = Fr::zero();   // a value no node of these tests takes: a wrong read shows up as a wrong wire
+    poison.l[0] = 0xdeadbeefu; poison.l[3] = 0x1234567u;
+    std::vector<Fr> ring(VM_RING * VM_SLOTS), vals(g.prog.size(), poison), consts(g.consts.size() / 32);
+    std::vector<uint8_t> is_stored(g.prog.size(), 0);
     for (size_t i = 0; i < consts.size(); i++) consts[i] = ld<Fr>(g.consts.data() + 32 * i);
     auto operand = [&](uint32_t enc) -> Fr {
         const uint32_t src = enc >> 30, idx = enc & 0x3fffffffu;
         return src == VM_SRC_RING ? ring[idx] : src == VM_SRC_CONST ? consts[idx] : vals[idx];
     };
     int bad = 0;
+    uint32_t stored = 0;
     for (uint32_t b = 0; b < nb; b++) {
         Fr res[VM_SLOTS];
         bool have[VM_SLOTS];
@@ -108,10 +119,14 @@ int emu_witness_scheduled(const uint8_t* graph, size_t glen, const uint8_t* inpu
             if (!have[sl]) continue;
             const VmRecord& r = recs[(size_t)b * VM_SLOTS + sl];
             ring[(b % VM_RING) * VM_SLOTS + sl] = res[sl];
-            vals[r.out] = res[sl];
+            if (r.out >> 31) { vals[r.out & 0x7fffffffu] = res[sl]; is_stored[r.out & 0x7fffffffu] = 1; stored++; }
         }
     }
-    for (size_t i = 0; i < vals.size(); i++) st(out + 32 * i, vals[i]);
+    if (n_stored_out) *n_stored_out = stored;
+    for (size_t i = 0; i < vals.size(); i++) {
+        if (is_stored[i]) st(out + 32 * i, vals[i]);
+        else memset(out + 32 * i, 0xff, 32);   // never stored: not a canonical value
+    }
     return bad;
 }
 // GLV split of a canonical scalar: out = |k1| (16 B) | |k2| (16 B) | sign1 | sign2
@@ -213,16 +228,6 @@ int emu_g2_subgroup_both(const uint8_t* p) {
     if (!init) { pairing_tables_init(pt); init = true; }
     const G2Affine P = ld_g2(p);
     return (g2_in_subgroup_6x2(&pt, P) ? 1 : 0) | (g2_in_subgroup(&pt, P) ? 2 : 0);
-}
-// the low-latency Montgomery product (fp.cuh mul_lowlat; device-only in the product, plain C so it runs here): Montgomery in / out
-void emu_mul_lowlat(int field, const uint8_t* a, const uint8_t* b, uint8_t* out) {
-    if (field == 0) { Fr x = ld<Fr>(a), y = ld<Fr>(b), r; Fr::mul_lowlat(r.l, x.l, y.l); st(out, r); }
-    else { Fq x = ld<Fq>(a), y = ld<Fq>(b), r; Fq::mul_lowlat(r.l, x.l, y.l); st(out, r); }
-}
-// with the first operand replaced by p itself (neg_lazy operands reach the product as p − 0 = p): must give 0
-void emu_mul_lowlat_p(int field, const uint8_t* b, uint8_t* out) {
-    if (field == 0) { Fr x = Fr::zero().neg_lazy(), y = ld<Fr>(b), r; Fr::mul_lowlat(r.l, x.l, y.l); st(out, r); }
-    else { Fq x = Fq::zero().neg_lazy(), y = ld<Fq>(b), r; Fq::mul_lowlat(r.l, x.l, y.l); st(out, r); }
 }
 // witness-graph VM: one op on canonical values
 int emu_vm_duo(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {

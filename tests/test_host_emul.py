@@ -49,26 +49,6 @@ def test_field_ops(emu):
             assert fop(field, 3, a) == pow(a, -1, p)
 
 
-def test_low_latency_product(emu):
-    """fp.cuh mul_lowlat (separated Montgomery reduction on 4×4-limb blocks, the product of the latency-bound kernels) against
-    Python integers: edge values, values with saturated words, random values; and the lazily negated operand p"""
-    rnd = random.Random(77)
-    for field, p in ((0, R), (1, Q)):
-        edge = [0, 1, 2, p - 1, p - 2, (p - 1) // 2, (1 << 128) - 1, 1 << 128, (1 << 253) + 12345, 0xFFFFFFFF, 0xFFFFFFFF00000000FFFFFFFF]
-        sat = [sum(w << (32 * k) for k, w in enumerate([rnd.choice([0xFFFFFFFF, 0x80000000, 0, 1, rnd.getrandbits(32)]) for _ in range(7)] + [rnd.randrange(0x30000000)])) % p
-               for _ in range(200)]
-        vals = edge + sat + [rnd.randrange(p) for _ in range(400)]
-        for i, a in enumerate(vals):
-            for b in (vals[(i * 7 + 3) % len(vals)], vals[(i * 13 + 1) % len(vals)], a):
-                out = ctypes.create_string_buffer(32)
-                emu.emu_mul_lowlat(field, b32(a), b32(b), out)
-                assert int.from_bytes(out.raw, "little") == a * b % p, (field, a, b)
-        for b in vals[:50]:
-            out = ctypes.create_string_buffer(32)
-            emu.emu_mul_lowlat_p(field, b32(b), out)
-            assert int.from_bytes(out.raw, "little") == 0
-
-
 def test_poseidon(emu):
     for v in ([0], [1], [R - 1], [0, 1], [5, R - 2], [1, 2, 3], [R - 1, 0, 7]):
         out = ctypes.create_string_buffer(32)
@@ -122,10 +102,11 @@ def test_curve_ops(emu):
         assert _g2r(o2.raw) == F.pt_double(F.OPS2, P2)
 
 
+@pytest.mark.parametrize("consts_resident", [1, 0])
 @pytest.mark.parametrize("depth,sub", [(10, ""), (20, ""), (20, "multi_message_id/max_out_4")])
-def test_scheduled_witness_vm(emu, depth, sub):
-    """the bundle schedule + operand-source encoding of k_witness (ring / constant table / vals), emulated on the host for one
-    proof, reproduces the oracle's graph evaluation node for node"""
+def test_scheduled_witness_vm(emu, depth, sub, consts_resident):
+    """the bundle schedule + operand-source encoding of k_witness (ring / constant table / vals, store flag), emulated on the host
+    for one proof, reproduces the oracle's graph evaluation: every wire, and every node the schedule marks as stored"""
     path = os.path.join(ROOT, "zerokit_b200", "resources", f"tree_depth_{depth}", sub, "graph.bin")
     graph = open(path, "rb").read()
     g = G.parse_graph(graph)
@@ -138,14 +119,15 @@ def test_scheduled_witness_vm(emu, depth, sub):
     want = G.evaluate_nodes(g, buf) if hasattr(G, "evaluate_nodes") else None
     inputs = b"".join(int(v).to_bytes(32, "little") for v in buf)
     out = ctypes.create_string_buffer(32 * len(g.nodes))
-    nb = ctypes.c_uint32()
-    assert emu.emu_witness_scheduled(graph, len(graph), inputs, out, ctypes.byref(nb)) == 0
+    nb, stored = ctypes.c_uint32(), ctypes.c_uint32()
+    assert emu.emu_witness_scheduled(graph, len(graph), inputs, out, ctypes.byref(nb), consts_resident, ctypes.byref(stored)) == 0
     vals = [int.from_bytes(out.raw[32 * i:32 * i + 32], "little") for i in range(len(g.nodes))]
     wires = G.evaluate(g, buf)
     assert [vals[s] for s in g.signals] == wires
     assert nb.value < len(g.nodes) // 2        # the schedule really is ≥ 2 nodes wide on average
+    assert len(set(g.signals)) <= stored.value < len(g.nodes) // 2   # most nodes never travel to HBM
     if want is not None:
-        assert vals == want
+        assert all(v == w for v, w in zip(vals, want) if v != (1 << 256) - 1)
 
 
 def test_glv_split_and_double_mul(emu):

@@ -75,6 +75,7 @@ struct CircuitDev {
     // records sched[VM_SLOTS·b ..], whose operands all lie in earlier bundles; one warp per slot evaluates them (k_witness)
     const uint4* sched;   // VmRecord, two uint4 each
     u32 n_bundles;
+    u32 n_consts_smem;    // constants k_witness keeps in shared memory (all of them, or 0 when the table is larger than vm_const_smem_max())
     // QAP
     u32 n_constraints, n_instance, domain, log_domain;
     const u32 *a_ptr, *a_col, *b_ptr, *b_col;
@@ -92,6 +93,7 @@ void launch_witness(const CircuitDev& c, const uint8_t* d_inputs, Fr* d_vals, u3
 // k_witness streams the schedule through shared memory in blocks of this many bundles: CircuitDev::n_bundles must be a multiple
 // of it (pad with empty records) and the schedule 128-byte aligned
 u32 vm_schedule_block_bundles();
+u32 vm_const_smem_max();
 // wires: B × n_wires canonical 32-byte values (an externally calculated witness) → the same vals layout
 void launch_scatter_wires(const CircuitDev& c, const uint8_t* d_wires, Fr* d_vals, u32 B, u32* d_err, cudaStream_t s);
 // a,b,c [domain][B]; afterwards abuf holds h = a·b − c on the coset (natural order)

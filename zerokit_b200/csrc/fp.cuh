@@ -64,10 +64,6 @@ struct FrCfg {  // scalar field r (rln/src/circuit/iden3calc/graph.rs:14-15)
              : i == 4 ? 0x7879462eu : i == 5 ? 0x666ea36fu : i == 6 ? 0x9a07df2fu : 0x0e0a77c1u;
     }
     static constexpr u32 INV = 0xefffffffu;  // −r^{-1} mod 2^32
-    static HD constexpr u32 ninv(int i) {  // −r^{-1} mod 2^256 (low-latency product: the whole reduction factor at once)
-        return i == 0 ? 0xefffffffu : i == 1 ? 0xc2e1f593u : i == 2 ? 0x4c6911b3u : i == 3 ? 0x6586864bu
-             : i == 4 ? 0x99062391u : i == 5 ? 0xe39a9828u : i == 6 ? 0x0d8341b2u : 0x73f82f1du;
-    }
 };
 struct FqCfg {  // base field q
     static HD constexpr u32 p(int i) {
@@ -83,10 +79,6 @@ struct FqCfg {  // base field q
              : i == 4 ? 0x7879462cu : i == 5 ? 0x666ea36fu : i == 6 ? 0x9a07df2fu : 0x0e0a77c1u;
     }
     static constexpr u32 INV = 0xe4866389u;  // −q^{-1} mod 2^32
-    static HD constexpr u32 ninv(int i) {  // −q^{-1} mod 2^256
-        return i == 0 ? 0xe4866389u : i == 1 ? 0x87d20782u : i == 2 ? 0x1eca6ac9u : i == 3 ? 0x9ede7d65u
-             : i == 4 ? 0x1833da80u : i == 5 ? 0xd8afcbd0u : i == 6 ? 0x91888c6bu : 0xf57a22b7u;
-    }
 };
 
 template <class C>
@@ -165,13 +157,9 @@ struct alignas(16) Fp {
     HD Fp dbl() const { return *this + *this; }
 
     // Montgomery product ----------------------------------------------------------------------
-    // ZK_MUL_LOWLAT (defined by the translation units whose kernels are latency-bound: lone warps, one thread per proof) selects the
-    // short-dependency-chain product below for every multiplication, squaring and dot product of that unit's device code
     HD Fp operator*(const Fp& o) const {
         Fp r;
-#if ZK_PTX && defined(ZK_MUL_LOWLAT)
-        mul_lowlat(r.l, l, o.l);
-#elif ZK_PTX
+#if ZK_PTX
         mul_ptx(r.l, l, o.l);
 #else
         mul_portable(r.l, l, o.l);
@@ -181,7 +169,7 @@ struct alignas(16) Fp {
     // dedicated squaring: 36 + 64 wide MADs instead of 64 + 64 (the off-diagonal products are taken once against the
     // doubled operand); the rows keep the shape of mul_ptx so the interleaved reduction is unchanged
     HD Fp sqr() const {
-#if ZK_PTX && !defined(ZK_MUL_LOWLAT)
+#if ZK_PTX
         Fp r;
         sqr_ptx(r.l, l);
         return r;
@@ -196,7 +184,7 @@ struct alignas(16) Fp {
     static HD Fp dot(const Fp* a, const Fp* b) {
         static_assert(N >= 1 && N <= 5, "dot: the single conditional subtraction covers at most 5 terms");
         Fp r;
-#if ZK_PTX && !defined(ZK_MUL_LOWLAT)
+#if ZK_PTX
         u32 E[8], O[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) {
@@ -207,9 +195,6 @@ struct alignas(16) Fp {
             reduce_row_ptx(E, O);
         }
         finish_ptx(r.l, E, O);
-#elif ZK_PTX
-        mul_lowlat(r.l, a[0].l, b[0].l);   // independent products: they overlap in a lone warp, which is the point of this mode
-        for (int k = 1; k < N; k++) { Fp t; mul_lowlat(t.l, a[k].l, b[k].l); r = r + t; }
 #else
         mul_portable(r.l, a[0].l, b[0].l);
         for (int k = 1; k < N; k++) { Fp t; mul_portable(t.l, a[k].l, b[k].l); r = r + t; }
@@ -257,100 +242,6 @@ struct alignas(16) Fp {
         cond_sub_p(r);
     }
 
-
-    // ---- low-latency product -------------------------------------------------------------------------------------------------------
-    // mul_ptx above minimises wide MADs (129) and is what the throughput kernels want.  Its cost in a LONE warp is not the MAD count
-    // but the dependency depth: two carry chains run through all sixteen rows (≈ 128 dependent carry-in/carry-out MADs), and a warp
-    // issues in order.  Latency-bound code (the witness VM, one-thread-per-proof pairing / assembly / Horner chains) wants the
-    // opposite trade: more MADs, short chains.  Here the three big products of a separated Montgomery reduction
-    //     T = a·b,   m = (T mod 2^256)·(−p⁻¹) mod 2^256,   r = (T + m·p) / 2^256
-    // are each cut into independent 4×4-limb sub-products (depth 16 instead of 64), combined by a few multi-word additions:
-    // 164 wide MADs instead of 129, ≈ 3× shallower.  Plain C on 64-bit accumulators, so the same code runs on the host for tests.
-    static HD void mul4x4(const u32* a, const u32* b, u32* r) {   // r[0..8) = a[0..4) · b[0..4)
-        u32 t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            u64 c = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                c += (u64)a[j] * b[i] + t[i + j];
-                t[i + j] = (u32)c;
-                c >>= 32;
-            }
-            t[i + 4] = (u32)c;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; i++) r[i] = t[i];
-    }
-    static HD void mullo4x4(const u32* a, const u32* b, u32* r) {   // r[0..4) = a[0..4) · b[0..4) mod 2^128
-        u32 t[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            u64 c = 0;
-#pragma unroll
-            for (int j = 0; i + j < 4; j++) {
-                c += (u64)a[j] * b[i] + t[i + j];
-                t[i + j] = (u32)c;
-                c >>= 32;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++) r[i] = t[i];
-    }
-    // r[0..n) += x[0..n); returns the carry out
-    template <int N>
-    static HD u32 add_n(u32* r, const u32* x) {
-        u64 c = 0;
-#pragma unroll
-        for (int i = 0; i < N; i++) { c += (u64)r[i] + x[i]; r[i] = (u32)c; c >>= 32; }
-        return (u32)c;
-    }
-    // full 8×8 → 16-word product from four 4×4 blocks
-    static HD void mul8x8_blocks(const u32* a, const u32* b, u32* T) {
-        u32 ll[8], lh[8], hl[8], hh[8];
-        mul4x4(a, b, ll);
-        mul4x4(a, b + 4, lh);
-        mul4x4(a + 4, b, hl);
-        mul4x4(a + 4, b + 4, hh);
-        // T = ll + (lh + hl)·2^128 + hh·2^256
-        u32 mid[9];
-#pragma unroll
-        for (int i = 0; i < 8; i++) mid[i] = lh[i];
-        mid[8] = add_n<8>(mid, hl);
-#pragma unroll
-        for (int i = 0; i < 8; i++) { T[i] = ll[i]; T[8 + i] = hh[i]; }
-        // add mid (9 words) at word 4
-        u64 c = 0;
-#pragma unroll
-        for (int i = 0; i < 9; i++) { c += (u64)T[4 + i] + mid[i]; T[4 + i] = (u32)c; c >>= 32; }
-#pragma unroll
-        for (int i = 13; i < 16; i++) { c += T[i]; T[i] = (u32)c; c >>= 32; }
-    }
-    static HD void mul_lowlat(u32* r, const u32* a, const u32* b) {
-        u32 T[16];
-        mul8x8_blocks(a, b, T);
-        // m = T_lo · N' mod 2^256 : low block full, the two cross blocks only their low halves
-        u32 np[8], pp[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) { np[i] = C::ninv(i); pp[i] = C::p(i); }
-        u32 m[8], x1[4], x2[4];
-        mul4x4(T, np, m);
-        mullo4x4(T, np + 4, x1);
-        mullo4x4(T + 4, np, x2);
-        add_n<4>(m + 4, x1);
-        add_n<4>(m + 4, x2);
-        // U = m·p ; T + U ≡ 0 mod 2^256, so the low halves only contribute their carry: 1 unless T_lo = 0
-        u32 U[16];
-        mul8x8_blocks(m, pp, U);
-        u32 lo_nonzero = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) lo_nonzero |= T[i];
-        u64 c = lo_nonzero ? 1 : 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) { c += (u64)T[8 + i] + U[8 + i]; r[i] = (u32)c; c >>= 32; }
-        // a, b < p ⇒ result < 2p < 2^256·… : one conditional subtraction (the carry out is always 0 for these 254-bit moduli)
-        cond_sub_p(r);
-    }
 
 #if ZK_PTX
     // one interleaved reduction row: T += m·p with m chosen so that the low word cancels (T = E + O·2^32)

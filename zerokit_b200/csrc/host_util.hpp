@@ -419,18 +419,28 @@ inline void parse_graph(const uint8_t* d, size_t n, GraphHost& g) {
 // L2 round trip on the critical path; constants are read from the constant table; anything older comes from vals[node][B].
 struct VmRecord {            // 32 bytes: two 128-bit loads per (bundle, slot)
     uint32_t kind_op;        // as VmInstr; 0xffffffff = empty slot
-    uint32_t out;            // node index of the result
+    uint32_t out;            // node index of the result; bit 31: the value is also stored to vals[node][B] (a wire, or a far consumer)
     uint32_t a, b, c;        // operands: source type in the top 2 bits (VM_SRC_*), index below
     uint32_t pad[3];
 };
-inline std::vector<VmRecord> vm_build_schedule(const std::vector<VmInstr>& prog, uint32_t& n_bundles) {
+// consts_resident: the kernel keeps the whole constant table in shared memory, so an operand that is a constant node is read from
+// there and constant nodes that are not wires need not be evaluated at all; otherwise constants are ordinary nodes (loaded once by
+// their own record, then read from the ring or from vals like any other value).  is_signal[i] != 0: node i is a wire of the witness.
+inline std::vector<VmRecord> vm_build_schedule(const std::vector<VmInstr>& prog, uint32_t& n_bundles, const std::vector<uint8_t>* is_signal = nullptr,
+                                               bool consts_resident = true) {
     const size_t n = prog.size();
-    std::vector<uint32_t> bundle(n), slot(n), fill;
+    const uint32_t NONE = 0xffffffffu;
+    std::vector<uint32_t> bundle(n, NONE), slot(n, 0), fill;
+    auto wire = [&](size_t i) { return !is_signal || (*is_signal)[i]; };
     for (size_t i = 0; i < n; i++) {
         const VmInstr& in = prog[i];
         const uint32_t kind = in.kind_op & 0xff;
+        if (kind == VM_CONST && consts_resident && !wire(i)) continue;   // dead: every consumer reads the constant table itself
         uint32_t b = 0;
-        auto after = [&](uint32_t op) { if (bundle[op] + 1 > b) b = bundle[op] + 1; };
+        auto after = [&](uint32_t op) {
+            if (bundle[op] == NONE) return;   // a resident constant: available from the start
+            if (bundle[op] + 1 > b) b = bundle[op] + 1;
+        };
         if (kind == VM_UNO || kind == VM_DUO || kind == VM_TRES) after(in.a);
         if (kind == VM_DUO || kind == VM_TRES) after(in.b);
         if (kind == VM_TRES) after(in.c);
@@ -446,13 +456,17 @@ inline std::vector<VmRecord> vm_build_schedule(const std::vector<VmInstr>& prog,
     memset(&empty, 0, sizeof empty);
     empty.kind_op = 0xffffffffu;
     std::vector<VmRecord> recs((size_t)n_bundles * VM_SLOTS, empty);
+    std::vector<uint8_t> to_global(n, 0);
+    for (size_t i = 0; i < n; i++) to_global[i] = wire(i) ? 1 : 0;
     for (size_t i = 0; i < n; i++) {
+        if (bundle[i] == NONE) continue;
         const VmInstr& in = prog[i];
         const uint32_t kind = in.kind_op & 0xff;
         auto enc = [&](uint32_t op) -> uint32_t {
             const uint32_t ok = prog[op].kind_op & 0xff;
-            if (ok == VM_CONST) return (VM_SRC_CONST << 30) | prog[op].a;
+            if (ok == VM_CONST && consts_resident) return (VM_SRC_CONST << 30) | prog[op].a;
             if (bundle[i] - bundle[op] <= VM_RING - 1) return (VM_SRC_RING << 30) | ((bundle[op] % VM_RING) * VM_SLOTS + slot[op]);
+            to_global[op] = 1;
             return (VM_SRC_GLOBAL << 30) | op;
         };
         VmRecord r = empty;
@@ -464,6 +478,8 @@ inline std::vector<VmRecord> vm_build_schedule(const std::vector<VmInstr>& prog,
         if (kind == VM_TRES) r.c = enc(in.c);
         recs[(size_t)bundle[i] * VM_SLOTS + slot[i]] = r;
     }
+    for (size_t i = 0; i < n; i++)   // the producers are always earlier in the program than their consumers: flags are final here
+        if (bundle[i] != NONE && to_global[i]) recs[(size_t)bundle[i] * VM_SLOTS + slot[i]].out |= 0x80000000u;
     return recs;
 }
 

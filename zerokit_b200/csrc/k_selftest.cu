@@ -197,8 +197,8 @@ __global__ void __launch_bounds__(128) k_affine_probe(const G1Affine* __restrict
     check[t] = c;
 }
 // ---- latency probe: cycles per DEPENDENT product in a lone warp (what the witness VM and every one-thread-per-proof chain pay) -----
-// kind 0: mul_ptx (fewest wide MADs, two long carry chains), 1: mul_portable (CIOS in C), 2: mul_lowlat (4×4 blocks, separated
-// reduction), 3: sqr_ptx, 4: modular addition; `lanes` live lanes of ONE warp on one SM
+// kind 0: mul_ptx (865 cycles measured), 1: mul_portable (CIOS in C: 1 131), 3: sqr_ptx (682), 4: modular addition (76);
+// `lanes` live lanes of ONE warp on one SM (the figure does not depend on it)
 template <int KIND>
 __global__ void k_latency_probe(Fq* __restrict__ data, int iters, long long* __restrict__ cycles) {
     Fq a = data[threadIdx.x], b = data[32 + threadIdx.x];
@@ -208,7 +208,6 @@ __global__ void k_latency_probe(Fq* __restrict__ data, int iters, long long* __r
 #if ZK_PTX
         if (KIND == 0) Fq::mul_ptx(r.l, a.l, b.l);
         else if (KIND == 1) Fq::mul_portable(r.l, a.l, b.l);
-        else if (KIND == 2) Fq::mul_lowlat(r.l, a.l, b.l);
         else if (KIND == 3) Fq::sqr_ptx(r.l, a.l);
         else r = a + b;
 #else
@@ -237,7 +236,6 @@ double rlnb200_latency_probe(int kind, int lanes, int iters) {
             switch (kind) {
                 case 0: k_latency_probe<0><<<1, lanes>>>(d, iters, c); break;
                 case 1: k_latency_probe<1><<<1, lanes>>>(d, iters, c); break;
-                case 2: k_latency_probe<2><<<1, lanes>>>(d, iters, c); break;
                 case 3: k_latency_probe<3><<<1, lanes>>>(d, iters, c); break;
                 default: k_latency_probe<4><<<1, lanes>>>(d, iters, c); break;
             }

@@ -832,7 +832,12 @@ void Rln::build_circuit() {
     circ_.signals = d_signals_.as<u32>();
     {   // list schedule for k_witness (host_util.hpp): bundles of 4 independent nodes, operand sources resolved (ring / const / global)
         uint32_t nb = 0;
-        std::vector<VmRecord> recs = vm_build_schedule(gh_.prog, nb);
+        std::vector<uint8_t> is_signal(gh_.prog.size(), 0);
+        for (uint32_t node : gh_.signals) is_signal[node] = 1;
+        const uint32_t n_consts = (uint32_t)(gh_.consts.size() / 32);
+        const bool consts_resident = n_consts <= vm_const_smem_max();
+        circ_.n_consts_smem = consts_resident ? n_consts : 0;
+        std::vector<VmRecord> recs = vm_build_schedule(gh_.prog, nb, &is_signal, consts_resident);
         {   // whole blocks for the bulk copies of k_witness: pad with empty bundles
             const uint32_t blk = vm_schedule_block_bundles();
             nb = (nb + blk - 1) / blk * blk;
