@@ -6,7 +6,7 @@ NVFLAGS  := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisib
 CSRC     := zerokit_b200/csrc
 OBJDIR   := zerokit_b200/lib/obj
 LIB      := zerokit_b200/lib/librln_b200.so
-UNITS    := rln_host k_poseidon k_prover k_msm_fixed k_msm_var k_verify k_selftest k_records k_witness
+UNITS    := rln_host k_poseidon k_prover k_msm_fixed k_msm_var k_verify k_selftest k_records k_witness k_verify_vm
 OBJS     := $(UNITS:%=$(OBJDIR)/%.o)
 HEADERS  := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.hpp $(CSRC)/*.inc include/*.h)
 

@@ -449,6 +449,12 @@ int rlnb200_set_device(int device, RlnString *err);
  * G1 / G2 bases, bytes in HBM */
 int rlnb200_table_info(FFI_RLN_t *const *rln, int *window_bits, int *windows, uint64_t *g1_bases, uint64_t *g2_bases,
                        uint64_t *table_bytes, int *window_bits_g2, int *windows_g2);
+/* verifier path (rln/src/protocol/proof.rs:856-894 has one; this library has two kernels with the same results): batches of up to
+ * `max_batch` proofs — a single ffi_verify* call is a batch of one — run on the lane-parallel kernel (one CTA per proof, a
+ * host-scheduled program of sums of products, k_verify_vm.cu), larger ones on the one-thread-per-proof kernel (k_verify.cu);
+ * 0 selects the latter always.  Default 1024, or RLN_B200_VERIFY_VM_MAX.  info: levels, slots, constants of the program. */
+int rlnb200_set_verify_vm_max(FFI_RLN_t *const *rln, size_t max_batch);
+int rlnb200_verify_vm_info(FFI_RLN_t *const *rln, uint32_t *levels, uint32_t *slots, uint32_t *constants);
 /* RLN::get_subtree_root (rln/src/public.rs:877-883; utils/src/merkle_tree/full_merkle_tree.rs:157-184): the ancestor at `level`
  * (0 = root, tree depth = the leaf itself) of leaf `index`, canonical 32 bytes */
 int rlnb200_get_subtree_root(FFI_RLN_t *const *rln, size_t level, size_t index, uint8_t *out32, RlnString *err);

@@ -166,3 +166,88 @@ class TreeMirror:
 
     def get_empty_leaves_indices(self):
         return self.h.get_empty_leaves_indices()
+
+
+# ---- verifier test inputs: one valid compressed proof and its mutations (used on the host interpreter of the pairing VM and on
+# the GPU, where both verifier kernels must return the same codes) ----------------------------------------------------------------
+def verifier_mutations(proof128, publics):
+    """[(label, proof bytes, public inputs)]: sign bits, neighbouring x coordinates (on / off the curve), flags, a point of the
+    twist outside G2, non-canonical coordinates, wrong public inputs"""
+    from pyref import fields as F
+    from pyref import groth16 as G
+    out = [("valid", bytes(proof128), list(publics))]
+    for i in (0, 2, 4):
+        bad = list(publics)
+        bad[i] = (bad[i] + 1) % R
+        out.append((f"public[{i}]+1", bytes(proof128), bad))
+    big = list(publics)
+    big[1] = publics[1] + R          # not reduced: the verifier reduces it (< 2^256)
+    if big[1] < 1 << 256:
+        out.append(("public[1]+r", bytes(proof128), big))
+    for name, off in (("A", 31), ("B", 95), ("C", 127)):
+        m = bytearray(proof128)
+        m[off] ^= 0x80
+        out.append((f"{name} sign flipped", bytes(m), list(publics)))
+        m = bytearray(proof128)
+        m[off] = (m[off] & 0x3F) | 0x40
+        out.append((f"{name} infinity flag", bytes(m), list(publics)))
+        m = bytearray(proof128)
+        m[off] |= 0xC0
+        out.append((f"{name} both flags", bytes(m), list(publics)))
+    for name, lo in (("A", 0), ("B.c0", 32), ("B.c1", 64), ("C", 96)):
+        for d in range(1, 7):
+            m = bytearray(proof128)
+            v = int.from_bytes(m[lo:lo + 8], "little") + d
+            m[lo:lo + 8] = (v & (2**64 - 1)).to_bytes(8, "little")
+            out.append((f"{name}.x+{d}", bytes(m), list(publics)))
+    for name, lo in (("A", 0), ("B.c0", 32), ("C", 96)):   # x = q: not canonical
+        m = bytearray(proof128)
+        top = m[lo + 31] & 0xC0 if lo != 32 else 0
+        m[lo:lo + 32] = Q.to_bytes(32, "little")
+        m[lo + 31] |= top
+        out.append((f"{name}.x = q", bytes(m), list(publics)))
+    k, found = 1, 0
+    while found < 2:   # points of the twist outside the r-torsion, compressed
+        x = (k, 1)
+        k += 1
+        try:
+            pt = G.g2_decompress(G.g2_compress((x, (0, 0)))[:63] + b"\x00")
+        except ValueError:
+            continue
+        if pt is None or F.pt_add(F.OPS2, F.pt_mul(F.OPS2, pt, R - 1), pt) is None:
+            continue
+        m = bytearray(proof128)
+        m[32:96] = G.g2_compress(pt)
+        out.append((f"B outside G2 ({k - 1})", bytes(m), list(publics)))
+        found += 1
+    m = bytearray(proof128)   # B replaced by another point of G2: well-formed, wrong
+    m[32:96] = G.g2_compress(F.pt_mul(F.OPS2, F.G2_GEN, 123456789))
+    out.append(("B = another G2 point", bytes(m), list(publics)))
+    return out
+
+
+def verifier_expected_code(zkey, proof128, publics):
+    """what rln/src/protocol/proof.rs:456-470,856-894 do with these bytes, by the Python oracle: 1 valid, 0 invalid, 2 refused by
+    deserialisation (flags, non-canonical, not on the curve, B outside G2); None where a point at infinity is involved"""
+    from pyref import fields as F
+    from pyref import groth16 as G
+    for lo, n in ((0, 32), (32, 64), (96, 32)):
+        fl = proof128[lo + n - 1] >> 6
+        if fl == 3:
+            return 2
+        xs = [proof128[lo:lo + 32]] if n == 32 else [proof128[lo:lo + 32], proof128[lo + 32:lo + 64]]
+        for i, xb in enumerate(xs):
+            v = int.from_bytes(xb, "little")
+            if i == len(xs) - 1:
+                v &= (1 << 254) - 1
+            if v >= Q:
+                return 2
+    if any(proof128[o] & 0x40 for o in (31, 95, 127)):
+        return None
+    try:
+        proof = G.proof_from_bytes(proof128)
+    except ValueError:
+        return 2
+    if F.pt_add(F.OPS2, F.pt_mul(F.OPS2, proof[1], R - 1), proof[1]) is not None:
+        return 2
+    return 1 if G.verify(zkey, proof, [p % R for p in publics]) else 0

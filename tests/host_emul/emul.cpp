@@ -11,6 +11,7 @@
 #include "vm.cuh"
 #include "glv.cuh"
 #include "host_util.hpp"
+#include "verify_vm_program.hpp"
 
 using namespace zk;
 
@@ -128,6 +129,98 @@ int emu_witness_scheduled(const uint8_t* graph, size_t glen, const uint8_t* inpu
         else memset(out + 32 * i, 0xff, 32);   // never stored: not a canonical value
     }
     return bad;
+}
+// ---- the pairing VM (verify_vm*.hpp): program built by the product's own tracer / scheduler, executed here lane by lane -------------
+// One level at a time: every lane's sum is evaluated against the slots as they were before the level, lane pairs are combined,
+// then the results are stored — the order the kernel's barrier enforces.  Arithmetic: the portable Montgomery product on the
+// scaled / complemented operand, results summed mod q (the kernel's single-reduction sum gives the same fully reduced value).
+static Fq vm_host_term(const Fq& a_in, const Fq& b, bool neg, u32 sh) {
+    Fq a = neg ? a_in.neg_lazy() : a_in;
+    for (u32 s = 0; s < sh; s++) { u32 t[8]; Fq::raw_add(t, a.l, a.l); memcpy(a.l, t, 32); }   // ≤ 4q < 2^256
+    return a * b;
+}
+static int vm_host_run(const pvm::Program& P, const uint8_t* proof, const G1XYZZ& vkx, uint64_t* n_terms_out) {
+    using namespace pvm;
+    std::vector<Fq> slots(P.n_slots, Fq::zero());
+    for (u32 i = 0; i < P.n_const; i++) slots[i] = P.consts[i];
+    ProofFlags fl{0};
+    u32 st = pv_prologue(proof, slots.data(), fl);
+    if (st != ST_RUNNING) return (int)st;
+    uint64_t n_terms = 0;
+    for (u32 l = 0; l < P.n_levels; l++) {
+        const u32* rec = P.code.data() + (size_t)l * REC_WORDS * LANES;
+        const u32 special = rec[1 * LANES] >> 8;
+        if (special) {
+            u32 args[32];
+            for (int k = 0; k < 32; k++) args[k] = rec[k];
+            if (special == SP_VKX) {
+                if (vkx.is_inf()) return ST_FALLBACK;
+                slots[S_VX] = vkx.X; slots[S_VY] = vkx.Y; slots[S_VZZ] = vkx.ZZ; slots[S_VZZZ] = vkx.ZZZ;
+            } else if (special == SP_SELECT) {
+                st = pv_select(slots.data(), args, fl);
+                if (st != ST_RUNNING) return (int)st;
+            } else if (special == SP_FINAL) {
+                if (n_terms_out) *n_terms_out = n_terms;
+                return (int)pv_final(slots.data(), args);
+            } else return -2;
+            continue;
+        }
+        Fq res[LANES];
+        for (int gl = 0; gl < LANES; gl++) {
+            const u32 w1 = rec[1 * LANES + gl];
+            const u32 N = w1 & 15;
+            Fq r = Fq::zero();
+            for (u32 t = 0; t < N; t++) {
+                const u32 tw = rec[(2 + t) * LANES + gl];
+                r = r + vm_host_term(slots[tw & 0xfff], slots[(tw >> 12) & 0xfff], (tw >> 24) & 1, (tw >> 25) & 3);
+                if ((tw & 0xffffff) != 0) n_terms++;
+            }
+            res[gl] = r;
+        }
+        for (int gl = 0; gl < LANES; gl++) {
+            const u32 w0 = rec[gl];
+            if (!(w0 & W0_STORE)) continue;
+            Fq r = res[gl];
+            if (w0 & W0_COMBINE) r = r + res[gl ^ 16];
+            slots[w0 & 0xfff] = r;
+        }
+    }
+    return -3;   // no SP_FINAL reached
+}
+// vk: alpha_g1 (64 B) | beta_g2 (128) | gamma_g2 (128) | delta_g2 (128), canonical affine; gamma_abc: (n_public + 1) × 64 B;
+// publics: n_proofs × n_public × 32 B canonical scalars; proofs: n_proofs × 128 B ark-compressed.  out[j] = status of proof j
+// (pvm::Status); info = {levels, slots, constants, nodes, estimated cycles, terms executed per proof}
+int emu_verify_vm(const uint8_t* vk, const uint8_t* gamma_abc, int n_public, const uint8_t* publics, const uint8_t* proofs, int n_proofs, int* out,
+                  uint64_t* info) {
+    static PairingTables pt; static bool init = false;
+    if (!init) { pairing_tables_init(pt); init = true; }
+    static pvm::Program P;
+    static std::vector<uint8_t> key;
+    try {
+        if (key.size() != 448 || memcmp(key.data(), vk, 448) != 0) {
+            static FixedLines lg, ld_;
+            precompute_lines(&pt, ld_g2(vk + 192), lg);
+            precompute_lines(&pt, ld_g2(vk + 320), ld_);
+            pvm::VerifyKeyHost h{&lg, &ld_, miller_loop(&pt, ld_g2(vk + 64), ld_g1(vk))};
+            P = pvm::build_verify_program(pt, h);
+            key.assign(vk, vk + 448);
+        }
+    } catch (const std::exception& e) {
+        fprintf(stderr, "emu_verify_vm: %s\n", e.what());
+        return -1;
+    }
+    uint64_t n_terms = 0;
+    for (int j = 0; j < n_proofs; j++) {
+        G1XYZZ vkx = G1XYZZ::from_affine(ld_g1(gamma_abc));
+        for (int i = 0; i < n_public; i++) {
+            u32 k[8];
+            memcpy(k, publics + ((size_t)j * n_public + i) * 32, 32);
+            vkx.add(G1XYZZ::from_affine(ld_g1(gamma_abc + 64 * (i + 1))).mul(k));
+        }
+        out[j] = vm_host_run(P, proofs + 128 * (size_t)j, vkx, &n_terms);
+    }
+    if (info) { info[0] = P.n_levels; info[1] = P.n_slots; info[2] = P.n_const; info[3] = P.n_nodes; info[4] = (uint64_t)P.est_cycles; info[5] = n_terms; }
+    return 0;
 }
 // GLV split of a canonical scalar: out = |k1| (16 B) | |k2| (16 B) | sign1 | sign2
 void emu_glv_split(const uint8_t* k, uint8_t* out) {

@@ -410,6 +410,39 @@ def test_reference_snarkjs_proof_verifies_on_gpu(z, rln20, goldens, oracle):
     assert rln20.verify_batch(rec, 1) == [1]
 
 
+def test_lane_parallel_verifier_agrees_with_thread_verifier(z, rln20, goldens):
+    """both verifier kernels (k_verify_vm: one CTA per proof, host-scheduled program; k_verify: one thread per proof, complete
+    formulas) on the reference's snarkjs proof (rln/tests/public.rs:77-142) and 43 mutations of it — sign bits, flags,
+    neighbouring coordinates on and off the curve, twist points outside G2, non-canonical coordinates, wrong public inputs:
+    the same code for every input, and the code the Python oracle's deserialisation + pairing check gives"""
+    from pyref import groth16 as G
+    from common import verifier_expected_code, verifier_mutations
+    v = goldens["ref"]["groth16_verifier_single"]
+    proof = ((int(v["pi_a"][0]), int(v["pi_a"][1])),
+             ((int(v["pi_b"][0][0]), int(v["pi_b"][0][1])), (int(v["pi_b"][1][0]), int(v["pi_b"][1][1]))),
+             (int(v["pi_c"][0]), int(v["pi_c"][1])))
+    pub = [int(v[k]) for k in ("y", "root", "nullifier", "x", "external_nullifier")]
+    zk = G.parse_zkey(resource(20, "rln_final.arkzkey"))
+    muts = [m for m in verifier_mutations(G.proof_to_bytes(proof), pub) if all(x < R for x in m[2])]
+    recs = b"".join(b"\x00" + p + G.proof_values_to_bytes_le(dict(y=q[0], root=q[1], nullifier=q[2], x=q[3], external_nullifier=q[4])) for _, p, q in muts)
+    n = len(muts)
+    info = rln20.verify_vm_info()
+    assert 0 < info["levels"] < 2500 and info["slots"] <= 4096
+    try:
+        rln20.set_verify_vm_max(0)
+        serial = rln20.verify_batch(recs, n)
+        rln20.set_verify_vm_max(1024)
+        vm = rln20.verify_batch(recs, n)
+        one_by_one = [rln20.verify_batch(recs[290 * j:290 * (j + 1)], 1)[0] for j in range(n)]
+    finally:
+        rln20.set_verify_vm_max(1024)
+    assert vm == serial, [(m[0], a, b) for m, a, b in zip(muts, vm, serial) if a != b]
+    assert one_by_one == serial
+    want = [verifier_expected_code(zk, p, q) for _, p, q in muts]
+    assert [a for a, w in zip(serial, want) if w is not None] == [w for w in want if w is not None]
+    assert serial[0] == 1 and 0 in serial and 2 in serial
+
+
 def _make_batch(rln, oracle_ctx, depth, n, seed):
     """SURVEY §8d config 4 generator scaled down: member j of a seeded tree, message_id = j mod 100"""
     from pyref import poseidon as P

@@ -229,6 +229,44 @@ def test_verifier_fast_paths(emu):
     assert emu.emu_pairing_fast_paths(g1, g2) == 31
 
 
+def _snarkjs_kat(goldens, multi=False):
+    from common import multi_kat
+    if multi:
+        c, pub = multi_kat(goldens["ref"]["groth16_verifier_multi"])
+        return ((c[0], c[1]), ((c[2], c[3]), (c[4], c[5])), (c[6], c[7])), pub
+    v = goldens["ref"]["groth16_verifier_single"]
+    proof = ((int(v["pi_a"][0]), int(v["pi_a"][1])),
+             ((int(v["pi_b"][0][0]), int(v["pi_b"][0][1])), (int(v["pi_b"][1][0]), int(v["pi_b"][1][1]))),
+             (int(v["pi_c"][0]), int(v["pi_c"][1])))
+    return proof, [int(v[k]) for k in ("y", "root", "nullifier", "x", "external_nullifier")]
+
+
+@pytest.mark.parametrize("multi", [False, True])
+def test_pairing_vm_program(emu, goldens, multi):
+    """the lane-parallel verifier (verify_vm*.hpp: program traced and scheduled by the product's host code, interpreted here lane
+    by lane with the portable arithmetic) on the reference's hard-coded snarkjs proofs (rln/tests/public.rs:77-213) and their
+    mutations — flags, sign bits, neighbouring coordinates on and off the curve, a twist point outside G2, wrong public inputs —
+    against the Python oracle's deserialisation + pairing check; inputs with a point at infinity must be handed back (code 3)"""
+    from common import multi_resource, resource, verifier_expected_code, verifier_mutations
+    z = G.parse_zkey(multi_resource("rln_final.arkzkey") if multi else resource(20, "rln_final.arkzkey"))
+    proof, pub = _snarkjs_kat(goldens, multi)
+    vk = _g1b(z.alpha_g1) + _g2b(z.beta_g2) + _g2b(z.gamma_g2) + _g2b(z.delta_g2)
+    gabc = b"".join(_g1b(p) for p in z.gamma_abc_g1)
+    muts = verifier_mutations(G.proof_to_bytes(proof), pub)
+    if multi:
+        muts = muts[:8] + muts[-3:]
+    n = len(muts)
+    out = (ctypes.c_int * n)()
+    info = (ctypes.c_uint64 * 6)()
+    assert emu.emu_verify_vm(vk, gabc, len(pub), b"".join(b"".join(b32(x) for x in q) for _, _, q in muts), b"".join(p for _, p, _ in muts), n, out, info) == 0
+    want = [verifier_expected_code(z, p, q) for _, p, q in muts]
+    want = [3 if w is None else 4 if w == 0 else w for w in want]   # the VM's status codes: 4 = invalid, 3 = not decided here
+    assert list(out) == want, [(m[0], o, w) for m, o, w in zip(muts, out, want) if o != w]
+    assert want[0] == 1 and 2 in want and 4 in want
+    levels, slots, consts = info[0], info[1], info[2]
+    assert levels < 2500 and slots <= 4096 and consts < slots
+
+
 def test_final_exponentiation_chain(emu):
     """the BN addition-chain hard part agrees with plain exponentiation by (q⁴−q²+1)/r on the verifier's predicate"""
     a, b = 1234567, 7654321

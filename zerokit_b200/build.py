@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "lib", "obj")
 LIB = os.path.join(HERE, "lib", "librln_b200.so")
-UNITS = ["rln_host.cu", "k_poseidon.cu", "k_prover.cu", "k_msm_fixed.cu", "k_msm_var.cu", "k_verify.cu", "k_selftest.cu", "k_records.cu", "k_witness.cu"]
+UNITS = ["rln_host.cu", "k_poseidon.cu", "k_prover.cu", "k_msm_fixed.cu", "k_msm_var.cu", "k_verify.cu", "k_selftest.cu", "k_records.cu", "k_witness.cu", "k_verify_vm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=default"]

@@ -190,6 +190,16 @@ void pairing_upload_tables(const PairingTables& t);
 // proofs: n × 128 B ark-compressed; publics: n × n_public × 32 canonical bytes (circuit order);
 // ok[j] = 1 valid, 0 invalid, 2 malformed encoding (not on curve / bad flags)
 void launch_verify(const VerifyKeyDev& vk, const uint8_t* d_proofs, const uint8_t* d_publics, size_t n, uint8_t* d_ok, cudaStream_t s);
+// ---- k_verify_vm.cu ------------------------------------------------------------------------
+// the same verification, one CTA per proof, as a host-scheduled program of lane-parallel sums of products (verify_vm.hpp);
+// ok codes as launch_verify plus 3 = "not decided here" (a point at infinity, an exceptional addition): re-run with launch_verify
+struct VerifyVmDev {
+    const u32* code;      // n_levels × REC_WORDS × LANES record words
+    const Fq* consts;     // image of the pinned slots [0, n_const)
+    u32 n_levels, n_const, n_slots;
+};
+void launch_verify_vm(const VerifyVmDev& prog, const VerifyKeyDev& vk, const uint8_t* d_proofs, const uint8_t* d_publics, size_t n, uint8_t* d_ok,
+                      cudaStream_t s);
 // decompress n proofs to affine canonical bytes (256 B each: A 64 | B 128 | C 64); ok[j]=0 if malformed
 void launch_decompress(const uint8_t* d_proofs, size_t n, uint8_t* d_affine, uint8_t* d_ok, cudaStream_t s);
 

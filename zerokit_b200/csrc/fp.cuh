@@ -201,6 +201,34 @@ struct alignas(16) Fp {
 #endif
         return r;
     }
+    // the same sum for up to 8 terms whose a operands may be any integers below 2^256 (complements p − x, shifted by up to two
+    // bits): with W = Σ a[k]/p the result is below (0.19·W + 1)·p, which the caller keeps below 2^256 and finishes reducing
+    // (dot_wide subtracts p once).  Inside a row T < (Σ a[k] + p)·2^32 exceeds the 2^288 of E + O·2^32 as soon as W > 4, so
+    // these rows carry a ninth word X (weight 2^288).  Schedule validated on scratch/ptx_model_wide.py.  Used by the pairing VM.
+    template <int N>
+    static HD Fp dot_wide(const Fp* a, const Fp* b) {
+        static_assert(N >= 1 && N <= 8, "dot_wide: at most 8 terms");
+        Fp r;
+#if ZK_PTX
+        u32 E[8], O[8], X = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (i == 0) row_first_ptx(E, O, a[0].l, b[0].l[0]);
+            else row_shift_w_ptx(E, O, X, a[0].l, b[0].l[i]);
+#pragma unroll
+            for (int k = 1; k < N; k++) row_inplace_w_ptx(E, O, X, a[k].l, b[k].l[i]);
+            u32 pw[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) pw[j] = C::p(j);
+            row_inplace_w_ptx(E, O, X, pw, E[0] * C::INV);   // the reduction row: T += m·p
+        }
+        finish_ptx(r.l, E, O);   // X is spent by now: the caller's bound keeps the value below 2^256
+#else
+        mul_portable(r.l, a[0].l, b[0].l);
+        for (int k = 1; k < N; k++) { Fp t; mul_portable(t.l, a[k].l, b[k].l); r = r + t; }
+#endif
+        return r;
+    }
     static HD Fp dot2(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
         const Fp x[2] = {a, c}, y[2] = {b, d};
         return dot<2>(x, y);
@@ -280,6 +308,49 @@ struct alignas(16) Fp {
             E[j + 1] = ptx_madc_hi_cc(a[j], bi, E[j + 1]);
         }
         O[7] = ptx_addc(O[7], 0);
+    }
+    // the same with the carries of both chains kept in a ninth word X (weight 2^288)
+    static DEV void row_inplace_w_ptx(u32* E, u32* O, u32& X, const u32* a, u32 bi) {
+        O[0] = ptx_mad_lo_cc(a[1], bi, O[0]);
+        O[1] = ptx_madc_hi_cc(a[1], bi, O[1]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            O[j] = ptx_madc_lo_cc(a[j + 1], bi, O[j]);
+            O[j + 1] = ptx_madc_hi_cc(a[j + 1], bi, O[j + 1]);
+        }
+        X = ptx_addc(X, 0);
+        E[0] = ptx_mad_lo_cc(a[0], bi, E[0]);
+        E[1] = ptx_madc_hi_cc(a[0], bi, E[1]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            E[j] = ptx_madc_lo_cc(a[j], bi, E[j]);
+            E[j + 1] = ptx_madc_hi_cc(a[j], bi, E[j + 1]);
+        }
+        O[7] = ptx_addc_cc(O[7], 0);
+        X = ptx_addc(X, 0);
+    }
+    static DEV void row_shift_w_ptx(u32* E, u32* O, u32& X, const u32* a, u32 bi) {
+        u32 nE[8], nO[8];
+        nE[0] = ptx_add_cc(O[0], E[1]);
+#pragma unroll
+        for (int j = 0; j < 6; j += 2) {
+            nO[j] = ptx_madc_lo_cc(a[j + 1], bi, E[j + 2]);
+            nO[j + 1] = ptx_madc_hi_cc(a[j + 1], bi, E[j + 3]);
+        }
+        nO[6] = ptx_madc_lo_cc(a[7], bi, 0);
+        nO[7] = ptx_madc_hi_cc(a[7], bi, X);
+        u32 nX = ptx_addc(0, 0);
+        nE[0] = ptx_mad_lo_cc(a[0], bi, nE[0]);
+        nE[1] = ptx_madc_hi_cc(a[0], bi, O[1]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            nE[j] = ptx_madc_lo_cc(a[j], bi, O[j]);
+            nE[j + 1] = ptx_madc_hi_cc(a[j], bi, O[j + 1]);
+        }
+        nO[7] = ptx_addc_cc(nO[7], 0);
+        X = ptx_addc(nX, 0);
+#pragma unroll
+        for (int j = 0; j < 8; j++) { E[j] = nE[j]; O[j] = nO[j]; }
     }
     // T = (T >> 32) + a·bi  (the shift is free: the old E words feed the new O chain and vice versa)
     static DEV void row_shift_ptx(u32* E, u32* O, const u32* a, u32 bi) {

@@ -28,6 +28,7 @@
 #include "host_util.hpp"
 #include "pairing_constants.hpp"
 #include "poseidon_constants.hpp"
+#include "verify_vm_program.hpp"
 
 namespace zk {
 
@@ -514,6 +515,8 @@ class Rln {
         out = o[0];
     }
     void verify_batch(const uint8_t* proofs128, const uint8_t* publics_circuit_order, size_t n, uint8_t* ok);
+    bool set_verify_vm_max(size_t n) { if (n && !vm_.code) return false; vm_max_batch_ = n; return true; }
+    void verify_vm_info(uint32_t* levels, uint32_t* slots, uint32_t* constants) const { *levels = vm_.n_levels; *slots = vm_.n_slots; *constants = vm_.n_const; }
     // witness, qap, g1 accumulate, g1 reduce, g2 accumulate, g2 reduce, assemble, proof values
     float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     u32 last_chunks = 1;   // device batches (kernel launches per stage) the stage_ms above are summed over
@@ -551,7 +554,9 @@ class Rln {
     CircuitDev circ_{};
     // fixed-base tables
     DevMem d_sched_;
-    DevMem d_tab_[5], d_rows_[5], d_gamma_abc_, d_gamma_tab_, d_delta1_tab_, d_delta2_tab_, d_vk_pre_;
+    DevMem d_tab_[5], d_rows_[5], d_gamma_abc_, d_gamma_tab_, d_delta1_tab_, d_delta2_tab_, d_vk_pre_, d_vm_code_, d_vm_consts_, d_vfy_in_, d_vfy_ok_;
+    VerifyVmDev vm_{};
+    size_t vm_max_batch_ = 0;   // verify_batch takes the lane-parallel kernel up to this many proofs (0: never)
     FixedMsmPlan plan_{};
     ProverKeyDev pk_{};
     VerifyKeyDev vk_{};
@@ -1011,6 +1016,15 @@ void Rln::build_tables() {
         vk_.gamma_c = reinterpret_cast<const Fq2*>(base + offsetof(Pre, g) + offsetof(FixedLines, c));
         vk_.delta_lam = reinterpret_cast<const Fq2*>(base + offsetof(Pre, d) + offsetof(FixedLines, lam));
         vk_.delta_c = reinterpret_cast<const Fq2*>(base + offsetof(Pre, d) + offsetof(FixedLines, c));
+        // the lane-parallel verifier's program for this key (verify_vm_program.hpp): traced and scheduled here, once
+        vm_max_batch_ = (size_t)std::max(0, env_int("RLN_B200_VERIFY_VM_MAX", 1024));
+        {
+            pvm::VerifyKeyHost h{&pre->g, &pre->d, pre->ml};
+            const pvm::Program prog = pvm::build_verify_program(pr, h);
+            d_vm_code_.upload(prog.code.data(), prog.code.size() * sizeof(u32));
+            d_vm_consts_.upload(prog.consts.data(), prog.consts.size() * sizeof(Fq));
+            vm_ = VerifyVmDev{d_vm_code_.as<u32>(), d_vm_consts_.as<Fq>(), prog.n_levels, prog.n_const, prog.n_slots};
+        }
     }
 }
 
@@ -1676,14 +1690,40 @@ void Rln::debug_w_h(const Witness& w, uint8_t* w_out, uint8_t* h_out) {
 
 void Rln::verify_batch(const uint8_t* proofs128, const uint8_t* publics, size_t n, uint8_t* ok) {
     if (!n) return;
-    DevMem dp, dv, dok;
-    dp.upload(proofs128, 128 * n);
-    dv.upload(publics, 32 * n * vk_.n_public);
-    dok.alloc(n);
-    launch_verify(vk_, dp.as<uint8_t>(), dv.as<uint8_t>(), n, dok.as<uint8_t>(), stream_);
+    // one staging buffer (proofs | publics) kept between calls: a single verification is two copies and one launch
+    const size_t pb = 128 * n, vb = 32 * n * vk_.n_public;
+    d_vfy_in_.ensure(pb + vb);
+    d_vfy_ok_.ensure(n);
+    uint8_t* dp = d_vfy_in_.as<uint8_t>();
+    uint8_t* dv = dp + pb;
+    ZK_CUDA_CHECK(cudaMemcpyAsync(dp, proofs128, pb, cudaMemcpyHostToDevice, stream_));
+    ZK_CUDA_CHECK(cudaMemcpyAsync(dv, publics, vb, cudaMemcpyHostToDevice, stream_));
+    const bool use_vm = vm_max_batch_ && n <= vm_max_batch_ && vk_.n_public <= 32;
+    if (use_vm) launch_verify_vm(vm_, vk_, dp, dv, n, d_vfy_ok_.as<uint8_t>(), stream_);
+    else launch_verify(vk_, dp, dv, n, d_vfy_ok_.as<uint8_t>(), stream_);
     g_launch_count++;
-    ZK_CUDA_CHECK(cudaMemcpyAsync(ok, dok.p, n, cudaMemcpyDeviceToHost, stream_));
+    ZK_CUDA_CHECK(cudaMemcpyAsync(ok, d_vfy_ok_.p, n, cudaMemcpyDeviceToHost, stream_));
     ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    if (!use_vm) return;
+    // proofs the lane-parallel kernel does not decide (a point at infinity, an exceptional addition in the membership test):
+    // the one-thread-per-proof kernel has complete formulas
+    std::vector<size_t> redo;
+    for (size_t j = 0; j < n; j++) if (ok[j] == 3) redo.push_back(j);
+    if (redo.empty()) return;
+    std::vector<uint8_t> rp(128 * redo.size()), rv(32 * (size_t)vk_.n_public * redo.size()), rok(redo.size());
+    for (size_t k = 0; k < redo.size(); k++) {
+        memcpy(rp.data() + 128 * k, proofs128 + 128 * redo[k], 128);
+        memcpy(rv.data() + 32 * (size_t)vk_.n_public * k, publics + 32 * (size_t)vk_.n_public * redo[k], 32 * (size_t)vk_.n_public);
+    }
+    DevMem d2, v2, o2;
+    d2.upload(rp.data(), rp.size());
+    v2.upload(rv.data(), rv.size());
+    o2.alloc(redo.size());
+    launch_verify(vk_, d2.as<uint8_t>(), v2.as<uint8_t>(), redo.size(), o2.as<uint8_t>(), stream_);
+    g_launch_count++;
+    ZK_CUDA_CHECK(cudaMemcpyAsync(rok.data(), o2.p, redo.size(), cudaMemcpyDeviceToHost, stream_));
+    ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    for (size_t k = 0; k < redo.size(); k++) ok[redo[k]] = rok[k];
 }
 
 }  // namespace zk
@@ -2531,6 +2571,14 @@ int rlnb200_set_device(int device, RlnString* err) {
 int rlnb200_table_info(FFI_RLN_t* const* rln, int* window_bits, int* windows, uint64_t* g1_bases, uint64_t* g2_bases, uint64_t* table_bytes,
                        int* window_bits_g2, int* windows_g2) {
     (*rln)->r->table_info(window_bits, windows, g1_bases, g2_bases, table_bytes, window_bits_g2, windows_g2);
+    return 0;
+}
+int rlnb200_set_verify_vm_max(FFI_RLN_t* const* rln, size_t max_batch) {
+    std::lock_guard<std::mutex> lk((*rln)->r->mu);
+    return (*rln)->r->set_verify_vm_max(max_batch) ? 0 : 1;
+}
+int rlnb200_verify_vm_info(FFI_RLN_t* const* rln, uint32_t* levels, uint32_t* slots, uint32_t* constants) {
+    (*rln)->r->verify_vm_info(levels, slots, constants);
     return 0;
 }
 int rlnb200_set_leaves_from_bytes(FFI_RLN_t** rln, size_t index, const uint8_t* leaves_le, size_t count, RlnString* err) {

@@ -761,6 +761,16 @@ class RLN:
         return dict(window_bits=c.value, windows=k.value, window_bits_g2=c2.value, windows_g2=k2.value, glv=glv,
                     adds_per_term=k.value * (2 if glv else 1), g1_bases=g1.value, g2_bases=g2.value, table_bytes=b.value)
 
+    def set_verify_vm_max(self, max_batch: int):
+        """batches up to max_batch proofs are verified by the lane-parallel kernel (0: always one thread per proof)"""
+        if ffi.lib().rlnb200_set_verify_vm_max(byref(self._h), max_batch) != 0:
+            raise RLNError("no verifier program for this key")
+
+    def verify_vm_info(self):
+        a, b, c = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+        ffi.lib().rlnb200_verify_vm_info(byref(self._h), byref(a), byref(b), byref(c))
+        return dict(levels=a.value, slots=b.value, constants=c.value)
+
     def debug_witness_and_h(self, witness_le: bytes):
         nw, dom = ffi.lib().rlnb200_num_wires(byref(self._h)), ffi.lib().rlnb200_domain_size(byref(self._h))
         w = ctypes.create_string_buffer(32 * nw)
