@@ -506,7 +506,22 @@ def run_gpu(args, rank, local_rank, world):
     line["cpu_rows"] = cpu_rows
     # ---- batch verification of the timed batch's proofs (rlnb200_verify_batch: host records in, flags out)
     line["verify_batch"] = {"proofs": total, "ms": verify_batch_ms, "proofs_per_s": total / (verify_batch_ms * 1e-3),
-                            "api": "rlnb200_verify_batch (decompression + G2 membership + one merged Miller loop + final exponentiation per proof, one thread each)"}
+                            "api": "rlnb200_verify_batch (decompression + G2 membership + one merged Miller loop + final exponentiation per proof; above 4 096 proofs one thread each, up to 4 096 one CTA each on the lane-parallel program)"}
+    try:   # the same check on 1 … 4 096 proofs: the lane-parallel verifier (k_verify_vm) that single calls and small batches take
+        small = {}
+        for nv in (1, 32, 296, 4096):
+            if nv > total:
+                continue
+            buf = host_out[:REC_OUT * nv]
+            assert rln.verify_batch(buf, nv) == [1] * nv
+            t_v = time.perf_counter()
+            for _ in range(5):
+                rln.verify_batch(buf, nv)
+            ms = 1e3 * (time.perf_counter() - t_v) / 5
+            small[str(nv)] = {"ms": ms, "proofs_per_s": nv / (ms * 1e-3)}
+        line["verify_batch"]["lane_parallel"] = dict(small, program=rln.verify_vm_info())
+    except Exception as e:
+        line["verify_batch"]["lane_parallel"] = {"error": str(e)}
     # ---- single proof / single verification through the reference's own entry points (BASELINE.json configs[0])
     try:
         wit = z.RLNWitnessInput.from_bytes_le(all_recs[:REC_IN])

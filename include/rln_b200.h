@@ -452,9 +452,14 @@ int rlnb200_table_info(FFI_RLN_t *const *rln, int *window_bits, int *windows, ui
 /* verifier path (rln/src/protocol/proof.rs:856-894 has one; this library has two kernels with the same results): batches of up to
  * `max_batch` proofs — a single ffi_verify* call is a batch of one — run on the lane-parallel kernel (one CTA per proof, a
  * host-scheduled program of sums of products, k_verify_vm.cu), larger ones on the one-thread-per-proof kernel (k_verify.cu);
- * 0 selects the latter always.  Default 1024, or RLN_B200_VERIFY_VM_MAX.  info: levels, slots, constants of the program. */
+ * 0 selects the latter always.  Default 4096 (measured break-even on a B200), or RLN_B200_VERIFY_VM_MAX.  info: levels, slots, constants of the program. */
 int rlnb200_set_verify_vm_max(FFI_RLN_t *const *rln, size_t max_batch);
 int rlnb200_verify_vm_info(FFI_RLN_t *const *rln, uint32_t *levels, uint32_t *slots, uint32_t *constants);
+/* diagnostic: one proof record through the lane-parallel kernel with a clock64() sample per level of the program.
+ * cycles[levels + 1]; meta[levels] = terms per lane of warp 0..3 (4 bits each) | conditional subtractions << 16 | lane-pair
+ * combine << 18 | special id << 20 */
+int rlnb200_verify_vm_trace(FFI_RLN_t *const *rln, const uint8_t *proof_record, long long *cycles, uint32_t *meta, uint8_t *ok_out,
+                            RlnString *err);
 /* RLN::get_subtree_root (rln/src/public.rs:877-883; utils/src/merkle_tree/full_merkle_tree.rs:157-184): the ancestor at `level`
  * (0 = root, tree depth = the leaf itself) of leaf `index`, canonical 32 bytes */
 int rlnb200_get_subtree_root(FFI_RLN_t *const *rln, size_t level, size_t index, uint8_t *out32, RlnString *err);

@@ -35,5 +35,5 @@ for mode, mx in (('thread_per_proof', 0), ('lane_parallel', 1 << 20)):
         assert rln.verify_with_roots(p0, p0.values.x, [])
     res[f'{mode}_ffi_verify_with_roots'] = round((time.perf_counter() - t0) / 20 * 1e3, 3)
     print(mode, 'ffi_verify_with_roots ms', res[f'{mode}_ffi_verify_with_roots'], flush=True)
-rln.set_verify_vm_max(1024)
+rln.set_verify_vm_max(4096)
 json.dump(res, open(os.path.join(ROOT, 'gpurun_out', 'verify_timing.json'), 'w'), indent=1)

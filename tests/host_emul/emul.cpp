@@ -149,7 +149,16 @@ static int vm_host_run(const pvm::Program& P, const uint8_t* proof, const G1XYZZ
     uint64_t n_terms = 0;
     for (u32 l = 0; l < P.n_levels; l++) {
         const u32* rec = P.code.data() + (size_t)l * REC_WORDS * LANES;
-        const u32 special = rec[1 * LANES] >> 8;
+        const u32 special = (rec[1 * LANES] >> 8) & 0xff;
+        if (special == SP_EXP) {
+            for (int gl = 0; gl < EXP_LANES; gl++) {
+                const u32 w0 = rec[gl], t0 = rec[2 * LANES + gl];
+                if (!(w0 & W0_STORE)) continue;
+                slots[w0 & 0xfff] = pv_pow(slots[t0 & 0xfff], P.exps[(rec[1 * LANES] >> 16) & 3], slots.data() + ((t0 >> 12) & 0xfff));
+                n_terms += 330;
+            }
+            continue;
+        }
         if (special) {
             u32 args[32];
             for (int k = 0; k < 32; k++) args[k] = rec[k];
@@ -177,12 +186,12 @@ static int vm_host_run(const pvm::Program& P, const uint8_t* proof, const G1XYZZ
             }
             res[gl] = r;
         }
+        Fq step1[LANES];   // the two shuffle steps of the kernel: lane ^ 16, then lane ^ 8
+        for (int gl = 0; gl < LANES; gl++) step1[gl] = (rec[gl] & W0_COMBINE) ? res[gl] + res[gl ^ 16] : res[gl];
         for (int gl = 0; gl < LANES; gl++) {
             const u32 w0 = rec[gl];
             if (!(w0 & W0_STORE)) continue;
-            Fq r = res[gl];
-            if (w0 & W0_COMBINE) r = r + res[gl ^ 16];
-            slots[w0 & 0xfff] = r;
+            slots[w0 & 0xfff] = (w0 & W0_COMBINE4) ? step1[gl] + step1[gl ^ 8] : step1[gl];
         }
     }
     return -3;   // no SP_FINAL reached

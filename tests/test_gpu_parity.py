@@ -431,11 +431,11 @@ def test_lane_parallel_verifier_agrees_with_thread_verifier(z, rln20, goldens):
     try:
         rln20.set_verify_vm_max(0)
         serial = rln20.verify_batch(recs, n)
-        rln20.set_verify_vm_max(1024)
+        rln20.set_verify_vm_max(4096)
         vm = rln20.verify_batch(recs, n)
         one_by_one = [rln20.verify_batch(recs[290 * j:290 * (j + 1)], 1)[0] for j in range(n)]
     finally:
-        rln20.set_verify_vm_max(1024)
+        rln20.set_verify_vm_max(4096)
     assert vm == serial, [(m[0], a, b) for m, a, b in zip(muts, vm, serial) if a != b]
     assert one_by_one == serial
     want = [verifier_expected_code(zk, p, q) for _, p, q in muts]

@@ -197,6 +197,8 @@ struct VerifyVmDev {
     const u32* code;      // n_levels × REC_WORDS × LANES record words
     const Fq* consts;     // image of the pinned slots [0, n_const)
     u32 n_levels, n_const, n_slots;
+    u32 exps[3][8];       // the public exponents of the SP_EXP levels
+    long long* trace;     // optional: clock64() of thread 0 at the start of every level (+ one at the end), for the cost model
 };
 void launch_verify_vm(const VerifyVmDev& prog, const VerifyKeyDev& vk, const uint8_t* d_proofs, const uint8_t* d_publics, size_t n, uint8_t* d_ok,
                       cudaStream_t s);

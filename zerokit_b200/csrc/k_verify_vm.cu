@@ -7,6 +7,7 @@
 // A proof this kernel cannot decide (a point at infinity, an exceptional addition) is reported as 3 and re-run by k_verify.
 #include "device_api.hpp"
 #include "fixed_base.cuh"
+#include "tma.cuh"
 #include "verify_vm_special.cuh"
 
 namespace zk {
@@ -27,7 +28,6 @@ __device__ __forceinline__ void st_slot(Fq* p, const Fq& v) {
 }
 // one lane's sum of N products: operands from the slot file, the a operand complemented (q − a) and / or shifted as its term
 // word says — integers below 2^256 either way (a ≤ q, shift ≤ 2)
-struct TermWords { u32 t[NMAX]; };   // by value into the out-of-line sum: registers, not the caller's frame
 template <int N>
 __device__ __forceinline__ Fq vm_dot(const u32* t, const Fq* slots) {
     Fq A[N], B[N];
@@ -43,6 +43,11 @@ __device__ __forceinline__ Fq vm_dot(const u32* t, const Fq* slots) {
     }
     return Fq::dot_wide<N>(A, B);
 }
+// out of line (one copy of each width; inlined into the level loop the shuffles of the combine step lost their converged fast
+// path: 3 400 → 7 000 cycles per level).  The caller must have no global loads in flight into registers at the call: the call waits
+// for them (registers the callee may clobber) — which is why the records are staged in shared memory by bulk copies, not prefetched
+// into registers (that cost 1 100 cycles of L2 latency per level, ncu round 2).
+struct TermWords { u32 t[NMAX]; };
 __device__ __noinline__ Fq vm_dot_n(u32 N, TermWords tw, const Fq* slots) {
     const u32* t = tw.t;
     switch (N) {
@@ -56,6 +61,8 @@ __device__ __noinline__ Fq vm_dot_n(u32 N, TermWords tw, const Fq* slots) {
         default: return vm_dot<8>(t, slots);
     }
 }
+constexpr u32 PVM_RING = 4;                                   // levels of records in flight
+constexpr u32 PVM_REC_BYTES = REC_WORDS * LANES * 4;
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 // vk_x = γ_abc[0] + Σ xᵢ·γ_abc[i+1] on one warp: every public input's windows are spread over 32 / n_public lanes (a lane adds
@@ -136,21 +143,33 @@ __global__ void __launch_bounds__(32 * (NW + 1)) k_verify_vm(VerifyVmDev vm, Ver
         bar_sync(2, 32 * (NW + 1));
         return;
     }
-    const u32* code = vm.code + tid;
-    u32 w[REC_WORDS];
-#pragma unroll
-    for (int k = 0; k < REC_WORDS; k++) w[k] = __ldg(code + k * LANES);
+    // the program streams through a ring of PVM_RING levels in shared memory: one elected thread keeps the bulk copies going
+    // (cp.async.bulk + mbarrier, as the witness VM does for its schedule), every lane reads its own words of the current level
+    u32* ring = reinterpret_cast<u32*>(slots + vm.n_slots);
+    u64* full = reinterpret_cast<u64*>(ring + PVM_RING * REC_WORDS * LANES);
+    if (tid == 0) {
+        for (u32 s = 0; s < PVM_RING; s++) mbar_init(full + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (u32 s = 0; s < PVM_RING && s < vm.n_levels; s++)
+            tma_load_1d(ring + s * REC_WORDS * LANES, vm.code + (size_t)s * REC_WORDS * LANES, PVM_REC_BYTES, full + s);
+    }
+    bar_sync(1, LANES);
     for (u32 l = 0; l < vm.n_levels; l++) {
-        u32 nw[REC_WORDS];
-        if (l + 1 < vm.n_levels) {
-            const u32* nc = code + (size_t)(l + 1) * REC_WORDS * LANES;
+        const u32 st = l % PVM_RING;
+        mbar_wait(full + st, (l / PVM_RING) & 1);
+        u32 w[REC_WORDS];
 #pragma unroll
-            for (int k = 0; k < REC_WORDS; k++) nw[k] = __ldg(nc + k * LANES);
-        }
-        const u32 special = w[1] >> 8;
+        for (int k = 0; k < REC_WORDS; k++) w[k] = ring[st * REC_WORDS * LANES + k * LANES + tid];
+        if (vm.trace && tid == 0) vm.trace[l] = clock64();
+        const u32 special = (w[1] >> 8) & 0xff;
         if (special) {
             if (special == SP_VKX) {
                 bar_sync(2, 32 * (NW + 1));
+            } else if (special == SP_EXP) {
+                if (w[0] & W0_STORE) {   // lanes 0..EXP_LANES−1 of warp 0: each raises its own value, table in its scratch slots
+                    const Fq r = pv_pow(ld_slot(slots + (w[2] & 0xfff)), vm.exps[(w[1] >> 16) & 3], slots + ((w[2] >> 12) & 0xfff));
+                    st_slot(slots + (w[0] & 0xfff), r);
+                }
             } else if (warp == 0) {
                 u32 args[32];
 #pragma unroll
@@ -180,14 +199,21 @@ __global__ void __launch_bounds__(32 * (NW + 1)) k_verify_vm(VerifyVmDev vm, Ver
 #pragma unroll
                     for (int i = 0; i < 8; i++) o.l[i] = __shfl_xor_sync(0xffffffffu, r.l[i], 16);
                     if (w[0] & W0_COMBINE) r = r + o;
+                    if (w[1] & 128) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) o.l[i] = __shfl_xor_sync(0xffffffffu, r.l[i], 8);
+                        if (w[0] & W0_COMBINE4) r = r + o;
+                    }
                 }
                 if (w[0] & W0_STORE) st_slot(slots + (w[0] & 0xfff), r);
             }
             bar_sync(1, LANES);
         }
-#pragma unroll
-        for (int k = 0; k < REC_WORDS; k++) w[k] = nw[k];
+        // every lane is past this level's records: their buffer takes the level PVM_RING ahead
+        if (tid == 0 && l + PVM_RING < vm.n_levels)
+            tma_load_1d(ring + st * REC_WORDS * LANES, vm.code + (size_t)(l + PVM_RING) * REC_WORDS * LANES, PVM_REC_BYTES, full + st);
     }
+    if (vm.trace && tid == 0) vm.trace[vm.n_levels] = clock64();
     if (tid == 0) {
         const u32 st = s_status;
         ok[j] = (uint8_t)(st == ST_VALID ? 1 : st == ST_INVALID ? 0 : st == ST_RUNNING ? ST_FALLBACK : st);
@@ -197,7 +223,7 @@ __global__ void __launch_bounds__(32 * (NW + 1)) k_verify_vm(VerifyVmDev vm, Ver
 void launch_verify_vm(const VerifyVmDev& prog, const VerifyKeyDev& vk, const uint8_t* d_proofs, const uint8_t* d_publics, size_t n, uint8_t* d_ok,
                       cudaStream_t s) {
     if (!n) return;
-    const size_t smem = (size_t)prog.n_slots * sizeof(Fq);
+    const size_t smem = (size_t)prog.n_slots * sizeof(Fq) + (size_t)PVM_RING * PVM_REC_BYTES + PVM_RING * sizeof(u64);
     ZK_CUDA_CHECK(cudaFuncSetAttribute(k_verify_vm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_verify_vm<<<(unsigned)n, 32 * (NW + 1), smem, s>>>(prog, vk, d_proofs, d_publics, n, d_ok);
     ZK_CUDA_CHECK(cudaGetLastError());

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(128) k_witness(CircuitDev c, const uint8_t* __
                 Fr v;
                 if (kind == VM_DUO) {
                     const Fr x = vm_operand(w0.z, sm, const_base, vals, B, j, lane), y = vm_operand(w0.w, sm, const_base, vals, B, j, lane);
-                    if (op == OP_MUL) v = x * y;
+                    if (op == OP_MUL) v = w0.z == w0.w ? x.sqr() : x * y;   // x·x (two of the three products of every x⁵ S-box): the dedicated squaring, 682 instead of 865 cycles
                     else if (op == OP_ADD) v = x + y;
                     else if (op == OP_SUB) v = x - y;
                     else bad |= vm_eval_rare(op, x, y, &v);

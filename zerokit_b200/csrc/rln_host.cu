@@ -515,6 +515,24 @@ class Rln {
         out = o[0];
     }
     void verify_batch(const uint8_t* proofs128, const uint8_t* publics_circuit_order, size_t n, uint8_t* ok);
+    // one proof through the lane-parallel kernel with a clock sample per level: cycles[levels + 1], meta[levels]
+    void verify_vm_trace(const uint8_t* proof128, const uint8_t* publics, long long* cycles, uint32_t* meta, uint8_t* ok) {
+        DevMem dp, dv, dok, dt;
+        dp.upload(proof128, 128);
+        dv.upload(publics, 32 * (size_t)vk_.n_public);
+        dok.alloc(1);
+        dt.alloc(sizeof(long long) * (vm_.n_levels + 1));
+        ZK_CUDA_CHECK(cudaMemset(dt.p, 0, sizeof(long long) * (vm_.n_levels + 1)));
+        VerifyVmDev t = vm_;
+        t.trace = dt.as<long long>();
+        launch_verify_vm(t, vk_, dp.as<uint8_t>(), dv.as<uint8_t>(), 1, dok.as<uint8_t>(), stream_);
+        ZK_CUDA_CHECK(cudaMemcpyAsync(cycles, dt.p, sizeof(long long) * (vm_.n_levels + 1), cudaMemcpyDeviceToHost, stream_));
+        ZK_CUDA_CHECK(cudaMemcpyAsync(ok, dok.p, 1, cudaMemcpyDeviceToHost, stream_));
+        ZK_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        memcpy(meta, vm_meta_.data(), 4 * vm_meta_.size());
+    }
+    double verify_vm_est_cycles() const { return vm_est_cycles_; }
+    size_t n_public_inputs() const { return vk_.n_public; }
     bool set_verify_vm_max(size_t n) { if (n && !vm_.code) return false; vm_max_batch_ = n; return true; }
     void verify_vm_info(uint32_t* levels, uint32_t* slots, uint32_t* constants) const { *levels = vm_.n_levels; *slots = vm_.n_slots; *constants = vm_.n_const; }
     // witness, qap, g1 accumulate, g1 reduce, g2 accumulate, g2 reduce, assemble, proof values
@@ -556,6 +574,8 @@ class Rln {
     DevMem d_sched_;
     DevMem d_tab_[5], d_rows_[5], d_gamma_abc_, d_gamma_tab_, d_delta1_tab_, d_delta2_tab_, d_vk_pre_, d_vm_code_, d_vm_consts_, d_vfy_in_, d_vfy_ok_;
     VerifyVmDev vm_{};
+    std::vector<uint32_t> vm_meta_;
+    double vm_est_cycles_ = 0;
     size_t vm_max_batch_ = 0;   // verify_batch takes the lane-parallel kernel up to this many proofs (0: never)
     FixedMsmPlan plan_{};
     ProverKeyDev pk_{};
@@ -1017,13 +1037,26 @@ void Rln::build_tables() {
         vk_.delta_lam = reinterpret_cast<const Fq2*>(base + offsetof(Pre, d) + offsetof(FixedLines, lam));
         vk_.delta_c = reinterpret_cast<const Fq2*>(base + offsetof(Pre, d) + offsetof(FixedLines, c));
         // the lane-parallel verifier's program for this key (verify_vm_program.hpp): traced and scheduled here, once
-        vm_max_batch_ = (size_t)std::max(0, env_int("RLN_B200_VERIFY_VM_MAX", 1024));
+        vm_max_batch_ = (size_t)std::max(0, env_int("RLN_B200_VERIFY_VM_MAX", 4096));
         {
             pvm::VerifyKeyHost h{&pre->g, &pre->d, pre->ml};
             const pvm::Program prog = pvm::build_verify_program(pr, h);
             d_vm_code_.upload(prog.code.data(), prog.code.size() * sizeof(u32));
             d_vm_consts_.upload(prog.consts.data(), prog.consts.size() * sizeof(Fq));
-            vm_ = VerifyVmDev{d_vm_code_.as<u32>(), d_vm_consts_.as<Fq>(), prog.n_levels, prog.n_const, prog.n_slots};
+            vm_ = VerifyVmDev{d_vm_code_.as<u32>(), d_vm_consts_.as<Fq>(), prog.n_levels, prog.n_const, prog.n_slots, {}, nullptr};
+            memcpy(vm_.exps, prog.exps, sizeof vm_.exps);
+            vm_meta_.assign(prog.n_levels, 0);
+            for (u32 l = 0; l < prog.n_levels; l++) {   // per level: N of each warp, max nsub, any combine, special id (for reports)
+                const u32* rec = prog.code.data() + (size_t)l * pvm::REC_WORDS * pvm::LANES;
+                u32 m = 0, nsub = 0, comb = 0;
+                for (int w = 0; w < pvm::NW && w < 4; w++) {
+                    const u32 w1 = rec[pvm::LANES + 32 * w];
+                    m |= (w1 & 15) << (4 * w);
+                    if (w1 & 15) { nsub = std::max(nsub, (w1 >> 4) & 3); comb |= (w1 >> 6) & 1; }
+                }
+                vm_meta_[l] = m | (nsub << 16) | (comb << 18) | (((rec[pvm::LANES] >> 8) & 0xff) << 20);
+            }
+            vm_est_cycles_ = prog.est_cycles;
         }
     }
 }
@@ -2576,6 +2609,16 @@ int rlnb200_table_info(FFI_RLN_t* const* rln, int* window_bits, int* windows, ui
 int rlnb200_set_verify_vm_max(FFI_RLN_t* const* rln, size_t max_batch) {
     std::lock_guard<std::mutex> lk((*rln)->r->mu);
     return (*rln)->r->set_verify_vm_max(max_batch) ? 0 : 1;
+}
+int rlnb200_verify_vm_trace(FFI_RLN_t* const* rln, const uint8_t* proof_record, long long* cycles, uint32_t* meta, uint8_t* ok_out, RlnString* err) {
+    INT_OP(
+        RlnLock lk(*(*rln)->r);
+        const size_t orec = proof_record_len(*(*rln)->r), np = (*rln)->r->n_public();
+        ProofValues pv;
+        proof_values_from_bytes(proof_record + 129, orec - 129, pv);
+        std::vector<uint8_t> q = public_inputs(pv);
+        if (q.size() != 32 * np) throw RlnError("Protocol error: proof record does not match the circuit's message mode");
+        (*rln)->r->verify_vm_trace(proof_record + 1, q.data(), cycles, meta, ok_out);)
 }
 int rlnb200_verify_vm_info(FFI_RLN_t* const* rln, uint32_t* levels, uint32_t* slots, uint32_t* constants) {
     (*rln)->r->verify_vm_info(levels, slots, constants);

@@ -41,12 +41,21 @@ constexpr int NW = 4;                 // VM warps per proof
 constexpr int LANES = 32 * NW;
 constexpr int NMAX = 8;               // terms per lane and level
 constexpr int REC_WORDS = 2 + NMAX;   // per lane and level: w0, w1, NMAX term words; stored [level][word][lane]
-// w0: dst slot (12 bits) | STORE << 12 | COMBINE << 13 (add the result of lane ^ 16 before storing)
-// w1: N (4 bits: terms of this warp in this level) | nsub << 4 (2 bits: conditional subtractions) | any-combine << 6 | special id << 8
-// term: slot a (12 bits) | slot b << 12 | negate << 24 | shift << 25 (2 bits: the a operand is scaled by 2^shift)
+// w0: dst slot (12 bits) | STORE << 12 | COMBINE << 13 (add the result of lane ^ 16) | COMBINE4 << 14 (then that of lane ^ 8):
+//     a sum split over two lanes sits on (l, l+16), one split over four on (l, l+8, l+16, l+24), l < 8
+// w1: N (4 bits: terms of this warp in this level) | nsub << 4 (2 bits: conditional subtractions) | any-combine << 6 | any-combine4 << 7 | special id << 8
+//     (8 bits) | exponent index << 16 (SP_EXP)
+// term: slot a (12 bits) | slot b << 12 | negate << 24 | shift << 25 (2 bits: the a operand is scaled by 2^shift); SP_EXP: term 0
+//     = source slot | first scratch slot << 12
 // a special level carries its argument slots in w0 of lanes 0..n_args−1 of warp 0
-constexpr u32 W0_STORE = 1u << 12, W0_COMBINE = 1u << 13;
-enum SpecialId : u32 { SP_NONE = 0, SP_VKX = 1, SP_SELECT = 2, SP_FINAL = 3 };
+constexpr u32 W0_STORE = 1u << 12, W0_COMBINE = 1u << 13, W0_COMBINE4 = 1u << 14;
+enum SpecialId : u32 { SP_NONE = 0, SP_VKX = 1, SP_SELECT = 2, SP_FINAL = 3, SP_EXP = 4 };
+// an SP_EXP level raises up to EXP_LANES values to one of the three public exponents of the verification, each lane on its own
+// (a chain of ≈ 320 dependent products would otherwise be ≈ 320 levels of one product each, and a level costs ≈ 1 000 cycles
+// before its first product): lane i < EXP_LANES of warp 0 with W0_STORE set computes slot[dst] = slot[src]^e, src in term word 0,
+// the exponent's index in bits 16.. of w1; its window table lives in the scratch block i at the top of the slot file
+constexpr int EXP_LANES = 4, EXP_TABLE = 16;
+enum ExpId : u32 { EXP_SQRT = 0, EXP_INV_SQRT = 1, EXP_INV = 2 };   // (q+1)/4, (q−3)/4, q−2
 enum Status : u32 { ST_RUNNING = 0, ST_VALID = 1, ST_INVALID = 4, ST_MALFORMED = 2, ST_FALLBACK = 3 };   // ok[] codes: 1 valid, 0 invalid, 2 malformed, 3 re-run
 // pinned slots
 enum Pinned : int {
@@ -57,7 +66,8 @@ constexpr int MAX_SLOTS = 4096;
 struct Program {
     std::vector<u32> code;        // n_levels × REC_WORDS × LANES
     std::vector<Fq> consts;       // image of slots [0, n_const): pinned constants (inputs are zero here)
-    u32 n_levels = 0, n_const = 0, n_slots = 0;
+    u32 n_levels = 0, n_const = 0, n_slots = 0;   // n_slots includes the EXP_LANES × EXP_TABLE scratch slots at the top
+    u32 exps[3][8] = {};          // the public exponents, little-endian words
     double est_cycles = 0;        // the scheduler's cost model, for reports
     u32 n_nodes = 0;
 };
@@ -99,12 +109,12 @@ inline S2 mul_xi(const S2& x) { return {x.a * 9 - x.b, x.b * 9 + x.a}; }   // la
 struct Term { int a, b, coef; };
 
 struct Node {
-    enum Kind : uint8_t { PINNED, DOT, SPECIAL, SPECIAL_OUT } kind = DOT;
+    enum Kind : uint8_t { PINNED, DOT, SPECIAL, SPECIAL_OUT, EXP } kind = DOT;
     std::vector<Term> terms;      // DOT (after coefficient splitting: |coef| ∈ {1, 2, 4})
     std::vector<int> deps;        // SPECIAL: argument nodes (inputs then outputs); SPECIAL_OUT: the special
-    int special_id = 0;
+    int special_id = 0;           // SPECIAL: which; EXP: the exponent's index
     int slot = -1;                // PINNED / pinned SPECIAL_OUT: fixed
-    bool split = false;           // terms spread over the lane pair (l, l ^ 16)
+    int split = 1;                // terms spread over 1, 2 or 4 lanes
     int n = 0, nsub = 1;          // terms per lane, conditional subtractions
     int level = -1, lane = -1;
     double prio = 0;
@@ -169,20 +179,23 @@ struct Builder {
         }
         if (n.terms.empty()) return Val{};
         const int nt = (int)n.terms.size();
-        if (nt > 2 * NMAX) throw std::runtime_error("pvm: sum too long: " + std::to_string(nt));
-        n.split = nt > split_threshold;
-        n.n = n.split ? (nt + 1) / 2 : nt;
-        if (n.split) {   // balance the weight of the two halves: heavy terms alternate
+        if (nt > 4 * NMAX) throw std::runtime_error("pvm: sum too long: " + std::to_string(nt));
+        n.split = nt <= split_threshold ? 1 : nt <= 2 * split_threshold ? 2 : 4;
+        if ((nt + n.split - 1) / n.split > NMAX) n.split *= 2;
+        n.n = (nt + n.split - 1) / n.split;
+        if (n.split > 1) {   // balance the weight of the parts: heavy terms are dealt round robin
             std::stable_sort(n.terms.begin(), n.terms.end(), [](const Term& a, const Term& b) { return std::abs(a.coef) > std::abs(b.coef); });
-            std::vector<Term> h0, h1;
-            for (size_t i = 0; i < n.terms.size(); i++) (i & 1 ? h1 : h0).push_back(n.terms[i]);
-            n.terms = h0;
-            n.terms.resize(n.n, Term{zero_, zero_, 1});
-            n.terms.insert(n.terms.end(), h1.begin(), h1.end());
-            n.terms.resize(2 * n.n, Term{zero_, zero_, 1});
-            int w0 = 0, w1 = 0;
-            for (int i = 0; i < n.n; i++) { w0 += std::abs(n.terms[i].coef); w1 += std::abs(n.terms[n.n + i].coef); }
-            W = std::max(w0, w1);
+            std::vector<std::vector<Term>> part(n.split);
+            for (size_t i = 0; i < n.terms.size(); i++) part[i % n.split].push_back(n.terms[i]);
+            n.terms.clear();
+            W = 0;
+            for (auto& h : part) {
+                h.resize(n.n, Term{zero_, zero_, 1});
+                int w = 0;
+                for (auto& t : h) if (t.a != zero_) w += std::abs(t.coef);
+                W = std::max(W, w);
+                n.terms.insert(n.terms.end(), h.begin(), h.end());
+            }
         }
         // (W·p² + R·p)/R = (0.18903·W + 1)·p must come below p after nsub conditional subtractions
         n.nsub = W <= 5 ? 1 : W <= 10 ? 2 : W <= 15 ? 3 : 0;
@@ -247,21 +260,16 @@ struct Builder {
     S2 one2() const { return {one(), Val{}}; }
 
     // ---------------------------------------------------------------------------------------------- fixed exponents
-    // a^e for a public exponent: 4-bit windows (one table of a¹…a¹⁵, then 4 squarings + at most one product per digit)
-    Val pow_fixed(const Val& a_in, const u32* e) {
+    // a^e for one of the public exponents: one node, evaluated by a lane on its own in an SP_EXP level
+    Val pow_fixed(const Val& a_in, int exp_id) {
         const Val a = mat(a_in);
-        Val tab[16];
-        tab[1] = a;
-        for (int k = 2; k < 16; k++) tab[k] = (k & 1) ? mul(tab[k - 1], a) : mul(tab[k / 2], tab[k / 2]);
-        int top = 63;
-        auto digit = [&](int d) { return (e[d >> 3] >> ((d & 7) * 4)) & 15; };
-        while (top > 0 && digit(top) == 0) top--;
-        Val r = tab[digit(top)];
-        for (int d = top - 1; d >= 0; d--) {
-            for (int s = 0; s < 4; s++) r = mul(r, r);
-            if (digit(d)) r = mul(r, tab[digit(d)]);
-        }
-        return r;
+        Node n;
+        n.kind = Node::EXP;
+        n.special_id = exp_id;
+        n.deps.push_back(a.t[0].first);
+        n.n = 1;
+        nodes.push_back(n);
+        return v((int)nodes.size() - 1);
     }
 
     // ---------------------------------------------------------------------------------------------- Fq12 = Fq2[w]/(w⁶ − ξ)
@@ -371,7 +379,9 @@ struct Builder {
     }
 
     // ---------------------------------------------------------------------------------------------- scheduling
-    static double level_cost(int n, int nsub, bool comb) { return 330.0 + 4.6 * (74.0 * n + 64) + 150.0 * (nsub - 1) + (comb ? 250.0 : 0.0); }
+    static constexpr double EXP_COST = 250000.0;   // ≈ 254 squarings + 78 products of one lane
+    // measured on a B200 (scratch/vm_trace.py, profiles/r02m_*): ≈ 1 350 cycles per level + 570 per term
+    static double level_cost(int n, int nsub, bool comb) { return 1350.0 + 570.0 * n + 70.0 * (nsub - 1) + (comb ? 250.0 : 0.0); }
     Program schedule(int window = 6000) {
         const int NN = (int)nodes.size();
         // consumers / priorities (nodes are in topological order)
@@ -382,7 +392,7 @@ struct Builder {
                 for (auto& t : n.terms) { deps[i].push_back(t.a); deps[i].push_back(t.b); }
             } else if (n.kind == Node::SPECIAL) {
                 for (int k = 0; k < n.n; k++) deps[i].push_back(n.deps[k]);
-            } else if (n.kind == Node::SPECIAL_OUT) {
+            } else if (n.kind == Node::SPECIAL_OUT || n.kind == Node::EXP) {
                 deps[i].push_back(n.deps[0]);
             }
             std::sort(deps[i].begin(), deps[i].end());
@@ -398,7 +408,7 @@ struct Builder {
         for (int i = NN - 1; i >= 0; i--) {
             Node& n = nodes[i];
             if (!live[i]) continue;
-            const double own = n.kind == Node::DOT ? level_cost(n.n, n.nsub, n.split) : n.kind == Node::SPECIAL ? 2000.0 : 0.0;
+            const double own = n.kind == Node::DOT ? level_cost(n.n, n.nsub, n.split > 1) : n.kind == Node::SPECIAL ? 2000.0 : n.kind == Node::EXP ? EXP_COST : 0.0;
             n.prio += own;
             for (int d : deps[i]) nodes[d].prio = std::max(nodes[d].prio, n.prio);
         }
@@ -413,7 +423,7 @@ struct Builder {
             if (nodes[i].kind == Node::PINNED) { nodes[i].level = -1; continue; }
             if (!remaining[i]) ready.push_back(i);
         }
-        struct Level { int special = -1; int lane_node[LANES]; int lane_half[LANES]; };
+        struct Level { int special = -1; int exp_id = -1; int lane_node[LANES]; int lane_half[LANES]; };
         std::vector<Level> levels;
         int n_done = 0, n_todo = 0, lowest_open = 0;
         for (int i = 0; i < NN; i++) if (nodes[i].kind != Node::PINNED && live[i]) n_todo++;
@@ -461,6 +471,15 @@ struct Builder {
                 L.special = cand[0];
                 placed.push_back(cand[0]);
                 est += 2000.0;
+            } else if (nodes[cand[0]].kind == Node::EXP) {   // every ready power with the same exponent shares the level
+                L.exp_id = nodes[cand[0]].special_id;
+                for (int i : cand)
+                    if (nodes[i].kind == Node::EXP && nodes[i].special_id == L.exp_id && (int)placed.size() < EXP_LANES) {
+                        L.lane_node[placed.size()] = i;
+                        nodes[i].lane = (int)placed.size();
+                        placed.push_back(i);
+                    }
+                est += EXP_COST;
             } else {
                 int warp_n[NW], warp_cap[NW];
                 for (int w = 0; w < NW; w++) { warp_n[w] = 0; warp_cap[w] = 0; }
@@ -475,7 +494,8 @@ struct Builder {
                         for (int l = 0; l < 32; l++) {
                             const int gl = w * 32 + l;
                             if (L.lane_node[gl] >= 0) continue;
-                            if (n.split) { if (l >= 16 || L.lane_node[gl + 16] >= 0) continue; }
+                            if (n.split == 2) { if (l >= 16 || L.lane_node[gl + 16] >= 0) continue; }
+                            if (n.split == 4) { if (l >= 8 || L.lane_node[gl + 8] >= 0 || L.lane_node[gl + 16] >= 0 || L.lane_node[gl + 24] >= 0) continue; }
                             best_w = w; best_l = l;
                             break;
                         }
@@ -483,7 +503,8 @@ struct Builder {
                     if (best_w < 0) continue;
                     const int gl = best_w * 32 + best_l;
                     L.lane_node[gl] = i; L.lane_half[gl] = 0;
-                    if (n.split) { L.lane_node[gl + 16] = i; L.lane_half[gl + 16] = 1; }
+                    if (n.split == 2) { L.lane_node[gl + 16] = i; L.lane_half[gl + 16] = 1; }
+                    if (n.split == 4) for (int h = 1; h < 4; h++) { L.lane_node[gl + 8 * h] = i; L.lane_half[gl + 8 * h] = h; }
                     if (!warp_cap[best_w]) warp_cap[best_w] = std::max(n.n, 2);
                     warp_n[best_w] = std::max(warp_n[best_w], n.n);
                     n.lane = gl;
@@ -493,7 +514,7 @@ struct Builder {
                 for (int w = 0; w < NW; w++) {
                     if (!warp_n[w]) continue;
                     int nsub = 1; bool comb = false;
-                    for (int l = 0; l < 32; l++) if (L.lane_node[w * 32 + l] >= 0) { nsub = std::max(nsub, nodes[L.lane_node[w * 32 + l]].nsub); comb |= nodes[L.lane_node[w * 32 + l]].split; }
+                    for (int l = 0; l < 32; l++) if (L.lane_node[w * 32 + l] >= 0) { nsub = std::max(nsub, nodes[L.lane_node[w * 32 + l]].nsub); comb |= nodes[L.lane_node[w * 32 + l]].split > 1; }
                     c = std::max(c, level_cost(warp_n[w], nsub, comb));
                 }
                 est += c;
@@ -533,6 +554,8 @@ struct Builder {
                 else nodes[i].slot = next_slot++;
             }
         }
+        const int scratch_base = next_slot;
+        next_slot += EXP_LANES * EXP_TABLE;
         if (next_slot > MAX_SLOTS) throw std::runtime_error("pvm: out of slots: " + std::to_string(next_slot));
         // ---- records
         Program P;
@@ -557,12 +580,22 @@ struct Builder {
                 }
                 continue;
             }
+            if (L.exp_id >= 0) {
+                for (int gl = 0; gl < LANES; gl++) {
+                    const int i = gl < EXP_LANES ? L.lane_node[gl] : -1;
+                    for (int t = 0; t < NMAX; t++) rec[(2 + t) * LANES + gl] = zero_term;
+                    rec[0 * LANES + gl] = i >= 0 ? ((u32)nodes[i].slot | W0_STORE) : 0;
+                    if (i >= 0) rec[2 * LANES + gl] = (u32)nodes[nodes[i].deps[0]].slot | ((u32)(scratch_base + gl * EXP_TABLE) << 12);
+                    rec[1 * LANES + gl] = ((u32)SP_EXP << 8) | ((u32)L.exp_id << 16);
+                }
+                continue;
+            }
             for (int w = 0; w < NW; w++) {
-                int N = 0, nsub = 1; bool comb = false;
+                int N = 0, nsub = 1; bool comb = false, comb4 = false;
                 for (int lane = 0; lane < 32; lane++) {
                     const int i = L.lane_node[w * 32 + lane];
                     if (i < 0) continue;
-                    N = std::max(N, nodes[i].n); nsub = std::max(nsub, nodes[i].nsub); comb |= nodes[i].split;
+                    N = std::max(N, nodes[i].n); nsub = std::max(nsub, nodes[i].nsub); comb |= nodes[i].split > 1; comb4 |= nodes[i].split == 4;
                 }
                 for (int lane = 0; lane < 32; lane++) {
                     const int gl = w * 32 + lane;
@@ -572,7 +605,8 @@ struct Builder {
                     if (i >= 0) {
                         const Node& n = nodes[i];
                         const int half = L.lane_half[gl];
-                        if (half == 0) w0 = (u32)n.slot | W0_STORE | (n.split ? W0_COMBINE : 0);
+                        if (half == 0) w0 = (u32)n.slot | W0_STORE | (n.split > 1 ? W0_COMBINE : 0) | (n.split == 4 ? W0_COMBINE4 : 0);
+                        if (half == 1 && n.split == 4) w0 = W0_COMBINE;   // lane l+8 collects lane l+24 first
                         for (int t = 0; t < n.n; t++) {
                             const Term& tm = n.terms[half * n.n + t];
                             const int c = tm.coef < 0 ? -tm.coef : tm.coef;
@@ -581,7 +615,7 @@ struct Builder {
                         }
                     }
                     rec[0 * LANES + gl] = w0;
-                    rec[1 * LANES + gl] = (u32)N | ((u32)nsub << 4) | (comb ? 1u << 6 : 0);
+                    rec[1 * LANES + gl] = (u32)N | ((u32)nsub << 4) | (comb ? 1u << 6 : 0) | (comb4 ? 1u << 7 : 0);
                 }
             }
         }

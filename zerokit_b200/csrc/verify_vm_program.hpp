@@ -74,8 +74,7 @@ struct ProgramBuilder : Builder {
     Program build(const VerifyKeyHost& vk) {
         const Val XA = v(S_XA), XC = v(S_XC), R2 = v(S_R2), RAW1 = v(S_RAW1);
         const Val HALF = cfq(Fq::from_u32(2).inv());
-        u32 e_sqrt[8], e_m3[8], e_inv[8];
-        exp_words(e_sqrt, 1); exp_words(e_m3, -3); exp_words(e_inv, -2);
+        const int e_sqrt = EXP_SQRT, e_m3 = EXP_INV_SQRT, e_inv = EXP_INV;
         // ------------------------------------------------------------------ decompression (chains 1 and 2)
         const Val xA = B::mul(XA, R2), xC = B::mul(XC, R2);
         const S2 xB = {B::mul(v(S_XB0), R2), B::mul(v(S_XB1), R2)};
@@ -175,7 +174,7 @@ struct ProgramBuilder : Builder {
             const S12 L = mul_line(fixed_M(n_fixed++), ln);
             f = mul12(f, L, true);
         };
-        split_threshold = 4;   // the f chain is the critical one: its sums go to lane pairs
+        split_threshold = getenv("PVM_T1") ? atoi(getenv("PVM_T1")) : 3;   // the f chain is the critical one: its sums are spread over lanes
         for (int i = 63; i >= 0; i--) {
             const bool bit = (ATE_LOW >> i) & 1;
             if (i != 63) f = sqr12(f);
@@ -200,7 +199,7 @@ struct ProgramBuilder : Builder {
             K.has_x = K.has_x2 = true;
             f = mul12(f, K, true);
         }
-        split_threshold = NMAX;
+        split_threshold = getenv("PVM_T2") ? atoi(getenv("PVM_T2")) : 3;
 
         // ------------------------------------------------------------------ final exponentiation (tower.cuh final_exponentiation)
         S12 t1;
@@ -307,7 +306,9 @@ struct ProgramBuilder : Builder {
         fin.push_back(lhs.ZZ.a); fin.push_back(lhs.ZZ.b); fin.push_back(rhs.ZZ.a); fin.push_back(rhs.ZZ.b);
         if ((int)fin.size() != FA_COUNT) throw std::runtime_error("pvm: SP_FINAL layout");
         special(SP_FINAL, fin, 0);
-        return schedule();
+        Program P = schedule();
+        exp_words(P.exps[EXP_SQRT], 1); exp_words(P.exps[EXP_INV_SQRT], -3); exp_words(P.exps[EXP_INV], -2);
+        return P;
     }
 };
 

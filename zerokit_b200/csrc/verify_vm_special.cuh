@@ -43,6 +43,21 @@ HD u32 pv_prologue(const uint8_t* proof, Fq* slots, ProofFlags& fl) {
     return ST_RUNNING;
 }
 
+// SP_EXP: a^e with 4-bit windows; the table a¹…a¹⁵ goes to the lane's scratch slots tab[1..15]
+HDN Fq pv_pow(const Fq& a, const u32* e, Fq* tab) {
+    tab[1] = a;
+    for (int k = 2; k < 16; k++) tab[k] = (k & 1) ? tab[k - 1] * a : tab[k / 2].sqr();
+    int top = 63;
+    while (top > 0 && ((e[top >> 3] >> ((top & 7) * 4)) & 15) == 0) top--;
+    Fq r = tab[(e[top >> 3] >> ((top & 7) * 4)) & 15];
+    for (int d = top - 1; d >= 0; d--) {
+        r = r.sqr().sqr().sqr().sqr();
+        const u32 dg = (e[d >> 3] >> ((d & 7) * 4)) & 15;
+        if (dg) r = r * tab[dg];
+    }
+    return r;
+}
+
 // SP_SELECT arguments (slot numbers), in order
 enum SelectArg {
     SA_CHK_A = 0, SA_RHS_A, SA_Y_A, SA_YC_A,          // y², x³+3, y, canonical y of A

@@ -317,6 +317,7 @@ def lib():
         "rlnb200_table_info": (c_int, [pp, POINTER(c_int), POINTER(c_int), POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint64), POINTER(c_int), POINTER(c_int)]),
         "rlnb200_set_verify_vm_max": (c_int, [pp, c_size_t]),
         "rlnb200_verify_vm_info": (c_int, [pp, POINTER(c_uint32), POINTER(c_uint32), POINTER(c_uint32)]),
+        "rlnb200_verify_vm_trace": (c_int, [pp, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(RlnString)]),
         "rlnb200_set_leaves_from_bytes": (c_int, [pp, c_size_t, c_void_p, c_size_t, POINTER(RlnString)]),
         "rlnb200_set_leaves_from_device": (c_int, [pp, c_size_t, c_void_p, c_size_t, c_void_p, POINTER(RlnString)]),
         "rlnb200_get_merkle_proofs": (c_int, [pp, c_void_p, c_size_t, c_void_p, c_void_p, POINTER(RlnString)]),

@@ -771,6 +771,17 @@ class RLN:
         ffi.lib().rlnb200_verify_vm_info(byref(self._h), byref(a), byref(b), byref(c))
         return dict(levels=a.value, slots=b.value, constants=c.value)
 
+    def verify_vm_trace(self, proof_record: bytes):
+        """(ok code, cycles per level, meta per level) of one proof on the lane-parallel verifier"""
+        n = self.verify_vm_info()["levels"]
+        cyc = (ctypes.c_longlong * (n + 1))()
+        meta = (ctypes.c_uint32 * n)()
+        ok = ctypes.create_string_buffer(1)
+        err = ffi.RlnString()
+        _check_int(ffi.lib().rlnb200_verify_vm_trace(byref(self._h), proof_record, cyc, meta, ok, byref(err)), err)
+        c = list(cyc)
+        return ok.raw[0], [c[i + 1] - c[i] for i in range(n)], list(meta)
+
     def debug_witness_and_h(self, witness_le: bytes):
         nw, dom = ffi.lib().rlnb200_num_wires(byref(self._h)), ffi.lib().rlnb200_domain_size(byref(self._h))
         w = ctypes.create_string_buffer(32 * nw)
