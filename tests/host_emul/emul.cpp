@@ -130,6 +130,58 @@ int emu_witness_scheduled(const uint8_t* graph, size_t glen, const uint8_t* inpu
     }
     return bad;
 }
+// the same for the depth-reduced program (host_util.hpp vm_optimize_program → vm_build_schedule, what the product runs): only the
+// wires are comparable with the oracle.  wires_out: n_signals × 32 canonical bytes; stats: nodes, constants, bundles, stores
+int emu_witness_optimized(const uint8_t* graph, size_t glen, const uint8_t* inputs, uint8_t* wires_out, uint32_t* stats) {
+    GraphHost g;
+    try { parse_graph(graph, glen, g); } catch (...) { return -1; }
+    VmOptimized opt = vm_optimize_program(g.prog, g.consts, g.signals);
+    uint32_t nb = 0;
+    std::vector<uint8_t> is_signal(opt.prog.size(), 0);
+    for (uint32_t node : opt.signals) is_signal[node] = 1;
+    const bool resident = true;
+    std::vector<VmRecord> recs = vm_build_schedule(opt.prog, nb, &is_signal, resident);
+    Fr poison = Fr::zero();
+    poison.l[0] = 0xdeadbeefu; poison.l[3] = 0x1234567u;
+    std::vector<Fr> ring(VM_RING * VM_SLOTS), vals(opt.prog.size(), poison), consts(opt.consts.size() / 32);
+    for (size_t i = 0; i < consts.size(); i++) consts[i] = ld<Fr>(opt.consts.data() + 32 * i);
+    auto operand = [&](uint32_t enc) -> Fr {
+        const uint32_t src = enc >> 30, idx = enc & 0x3fffffffu;
+        return src == VM_SRC_RING ? ring[idx] : src == VM_SRC_CONST ? consts[idx] : vals[idx];
+    };
+    int bad = 0;
+    uint32_t stored = 0;
+    for (uint32_t b = 0; b < nb; b++) {
+        Fr res[VM_SLOTS];
+        bool have[VM_SLOTS];
+        for (uint32_t sl = 0; sl < VM_SLOTS; sl++) {
+            const VmRecord& r = recs[(size_t)b * VM_SLOTS + sl];
+            have[sl] = r.kind_op != 0xffffffffu;
+            if (!have[sl]) continue;
+            const uint32_t kind = r.kind_op & 0xff, op = r.kind_op >> 8;
+            Fr v;
+            if (kind == VM_DUO) { if (!vm_eval_duo(op, operand(r.a), operand(r.b), v)) { bad = 1; v = Fr::zero(); } }
+            else if (kind == VM_CONST) v = consts[r.a];
+            else if (kind == VM_INPUT) v = ld<Fr>(inputs + 32 * r.a);
+            else if (kind == VM_UNO) { if (op == 0) v = operand(r.a).neg(); else { bad = 1; v = Fr::zero(); } }
+            else { Fr t = operand(r.a); v = t.is_zero() ? operand(r.c) : operand(r.b); }
+            res[sl] = v;
+        }
+        for (uint32_t sl = 0; sl < VM_SLOTS; sl++) {
+            if (!have[sl]) continue;
+            const VmRecord& r = recs[(size_t)b * VM_SLOTS + sl];
+            ring[(b % VM_RING) * VM_SLOTS + sl] = res[sl];
+            if (r.out >> 31) { vals[r.out & 0x7fffffffu] = res[sl]; stored++; }
+        }
+    }
+    for (size_t w = 0; w < opt.signals.size(); w++) {
+        // a wire that is a resident constant has no record: the product reads it from the constant table as well
+        const VmInstr& n = opt.prog[opt.signals[w]];
+        st(wires_out + 32 * w, (n.kind_op & 0xff) == VM_CONST ? consts[n.a] : vals[opt.signals[w]]);
+    }
+    if (stats) { stats[0] = (uint32_t)opt.prog.size(); stats[1] = (uint32_t)consts.size(); stats[2] = nb; stats[3] = stored; }
+    return bad;
+}
 // ---- the pairing VM (verify_vm*.hpp): program built by the product's own tracer / scheduler, executed here lane by lane -------------
 // One level at a time: every lane's sum is evaluated against the slots as they were before the level, lane pairs are combined,
 // then the results are stored — the order the kernel's barrier enforces.  Arithmetic: the portable Montgomery product on the

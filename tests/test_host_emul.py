@@ -130,6 +130,33 @@ def test_scheduled_witness_vm(emu, depth, sub, consts_resident):
         assert all(v == w for v, w in zip(vals, want) if v != (1 << 256) - 1)
 
 
+@pytest.mark.parametrize("depth,sub", [(10, ""), (20, ""), (20, "multi_message_id/max_out_4")])
+def test_depth_reduced_witness_program(emu, depth, sub):
+    """host_util.hpp vm_optimize_program (re-association of the graph's sums and products so that the value that is ready last
+    is combined last; constants folded) followed by the bundle schedule, as the product runs it: every wire of the witness
+    equals the oracle's evaluation of the ORIGINAL graph, and the schedule is at least a third shorter than the graph's
+    10 000-node dependency chain"""
+    path = os.path.join(ROOT, "zerokit_b200", "resources", f"tree_depth_{depth}", sub, "graph.bin")
+    graph = open(path, "rb").read()
+    g = G.parse_graph(graph)
+    rnd = random.Random(depth)
+    for trial in range(2):
+        pe = [P.poseidon([i + 7 + trial]) for i in range(depth)]
+        idx = [rnd.randrange(2) for i in range(depth)]
+        if sub:
+            buf = G.inputs_buffer(g, rnd.randrange(R), 50, [3, 7, 11, 0], pe, idx, rnd.randrange(R), 89, selector_used=[1, 0, 1, 0])
+        else:
+            buf = G.inputs_buffer(g, rnd.randrange(R), 100, 1 + trial, pe, idx, rnd.randrange(R), 100)
+        inputs = b"".join(int(v).to_bytes(32, "little") for v in buf)
+        out = ctypes.create_string_buffer(32 * len(g.signals))
+        stats = (ctypes.c_uint32 * 4)()
+        assert emu.emu_witness_optimized(graph, len(graph), inputs, out, stats) == 0
+        wires = [int.from_bytes(out.raw[32 * i:32 * i + 32], "little") for i in range(len(g.signals))]
+        assert wires == G.evaluate(g, buf)
+    nodes, consts, bundles, stored = stats
+    assert bundles < 0.68 * (10000 if depth == 20 else 5440) and consts <= 1536 and stored < nodes // 3
+
+
 def test_glv_split_and_double_mul(emu):
     """k ≡ k1 + k2·λ with |ki| < 2^128, and the Straus double multiplication of the proof assembly: kp·P + kq·Q"""
     lam = 0xb3c4d79d41a917585bfc41088d8daaa78b17ea66b99c90dd

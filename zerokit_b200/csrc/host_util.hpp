@@ -6,6 +6,7 @@
 //   arkzkey layout               rln/src/circuit/mod.rs:256-305 (ark-serialize uncompressed, unchecked)
 //   graph.bin layout             rln/src/circuit/iden3calc/storage.rs:16-22,265-302; proto.rs:7-117
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <map>
@@ -413,6 +414,228 @@ inline void parse_graph(const uint8_t* d, size_t n, GraphHost& g) {
 
 
 // ------------------------------------------------------------------------------- witness VM schedule
+// ---- depth reduction of the witness program ---------------------------------------------------------------------------------
+// k_witness is paced by the graph's longest dependency chain, not by its node count (one CTA, lone warps: a bundle whose slowest
+// slot is a product costs ≈ 1 200 cycles however few nodes it holds).  circom's Poseidon spends, per partial round and on that
+// chain, x → x² → x⁴ → x⁵ → x⁵ + c → k·(x⁵ + c) → + a → + b: four products and three additions.  Field arithmetic is exact, so the
+// program may be re-associated freely as long as every WIRE keeps its value:
+//   k·(t + c)            → k·t + k·c        (constants folded; t + c is repeated in each of its consumers, it is one addition)
+//   k·(x⁴·x)             → (k·x)·x⁴         (products re-paired so that the factor that is ready last is multiplied in last)
+//   ((late + e₁) + e₂)   → late + (e₁ + e₂) (sums likewise)
+// which leaves x → x² → x⁴ → (k·x)·x⁴ → + (k·c + a + b): three products and one addition (−29 % on the depth-20 graph's chain).
+// Nodes that are wires, or have several consumers, are kept as they are (and may be computed a second time inside a consumer's
+// re-associated form); identical nodes are merged.  The node count grows (23 414 → 37 481 at depth 20: the (k·x) products are
+// new work), which is why k_witness runs eight slots per bundle.  Output: a new program, constant table and wire → node map.
+struct VmOptimized {
+    std::vector<VmInstr> prog;
+    std::vector<uint8_t> consts;
+    std::vector<uint32_t> signals;
+};
+class VmOptimizer {
+    static constexpr uint64_t COST_MUL = 1170, COST_ADD = 400;   // cycles of a bundle by its slowest slot (measured), for ordering only
+    const std::vector<VmInstr>& in_;
+    const std::vector<uint8_t>& cin_;
+    std::vector<uint8_t> wire_;
+    std::vector<uint32_t> uses_;
+    std::vector<int64_t> map_;
+    std::vector<VmInstr> out_;
+    std::vector<uint64_t> ready_;
+    std::vector<Fr> cval_;                                       // value of every new constant (Montgomery), by constant index
+    std::map<std::vector<uint32_t>, uint32_t> cmap_;             // canonical words → node
+    std::map<std::vector<uint32_t>, uint32_t> cse_;
+    static uint32_t kind(const VmInstr& i) { return i.kind_op & 0xff; }
+    static uint32_t op(const VmInstr& i) { return i.kind_op >> 8; }
+    bool is_duo(uint32_t o, uint32_t want) const { return kind(in_[o]) == VM_DUO && op(in_[o]) == want; }
+    bool is_const(uint32_t o) const { return kind(in_[o]) == VM_CONST; }
+    Fr const_old(uint32_t o) const {
+        u32 c[8];
+        memcpy(c, cin_.data() + 32 * (size_t)in_[o].a, 32);
+        return Fr::from_canonical(c);
+    }
+    uint32_t add_const(const Fr& v) {
+        u32 c[8];
+        v.to_canonical(c);
+        std::vector<uint32_t> key(c, c + 8);
+        auto it = cmap_.find(key);
+        if (it != cmap_.end()) return it->second;
+        VmInstr n{VM_CONST, (uint32_t)cval_.size(), 0, 0};
+        cval_.push_back(v);
+        out_.push_back(n);
+        ready_.push_back(0);
+        cmap_[key] = (uint32_t)out_.size() - 1;
+        return (uint32_t)out_.size() - 1;
+    }
+    uint32_t add_node(VmInstr n) {
+        const uint32_t k = kind(n);
+        if (k == VM_DUO && (op(n) == OP_ADD || op(n) == OP_MUL) && n.a > n.b) std::swap(n.a, n.b);
+        std::vector<uint32_t> key = {n.kind_op, n.a, n.b, n.c};
+        if (k != VM_INPUT) {
+            auto it = cse_.find(key);
+            if (it != cse_.end()) return it->second;
+        }
+        uint64_t r = 0;
+        if (k == VM_UNO || k == VM_DUO || k == VM_TRES) r = ready_[n.a];
+        if (k == VM_DUO || k == VM_TRES) r = std::max(r, ready_[n.b]);
+        if (k == VM_TRES) r = std::max(r, ready_[n.c]);
+        const uint64_t c = k == VM_INPUT ? 0 : (k == VM_DUO && op(n) != OP_ADD && op(n) != OP_SUB) ? COST_MUL : COST_ADD;
+        out_.push_back(n);
+        ready_.push_back(r + c);
+        if (k != VM_INPUT) cse_[key] = (uint32_t)out_.size() - 1;
+        return (uint32_t)out_.size() - 1;
+    }
+    // may the consumer fold old node o (a sum / a product) into its own expression?
+    bool absorbable(uint32_t o, uint32_t want) const {
+        if (!is_duo(o, want)) return false;
+        if (wire_[o]) return false;
+        if (want == OP_ADD && (is_const(in_[o].a) || is_const(in_[o].b))) return true;   // t + c: cheap to repeat per consumer
+        return uses_[o] == 1;
+    }
+    void flat(uint32_t o, uint32_t want, std::vector<uint32_t>& leaves) const {
+        if (absorbable(o, want)) { flat(in_[o].a, want, leaves); flat(in_[o].b, want, leaves); }
+        else leaves.push_back(o);
+    }
+    uint32_t combine(std::vector<uint32_t> items, uint32_t o) {   // the two operands that are ready first are paired first
+        auto by_ready = [&](uint32_t x, uint32_t y) { return ready_[x] != ready_[y] ? ready_[x] < ready_[y] : x < y; };
+        std::sort(items.begin(), items.end(), by_ready);
+        while (items.size() > 1) {
+            const uint32_t n = add_node(VmInstr{VM_DUO | (o << 8), items[0], items[1], 0});
+            items.erase(items.begin(), items.begin() + 2);
+            items.insert(std::upper_bound(items.begin(), items.end(), n, by_ready), n);
+        }
+        return items[0];
+    }
+    uint32_t prod_of(std::vector<uint32_t> new_items, const std::vector<uint32_t>& old_factors) {
+        Fr c = Fr::one();
+        bool have_c = false;
+        for (uint32_t f : old_factors) {
+            if (is_const(f)) { c = c * const_old(f); have_c = true; }
+            else new_items.push_back(emit(f));
+        }
+        if (have_c && (c != Fr::one() || new_items.empty())) new_items.push_back(add_const(c));
+        if (new_items.empty()) new_items.push_back(add_const(Fr::one()));
+        return combine(new_items, OP_MUL);
+    }
+    // old node o as a sum: new summands + a constant
+    void sum_items(uint32_t o, std::vector<uint32_t>& items, Fr& c) {
+        if (is_const(o)) { c = c + const_old(o); return; }
+        if (absorbable(o, OP_ADD)) { sum_items(in_[o].a, items, c); sum_items(in_[o].b, items, c); return; }
+        if (absorbable(o, OP_MUL)) {
+            std::vector<uint32_t> fs, rest;
+            flat(o, OP_MUL, fs);
+            Fr k = Fr::one();
+            for (uint32_t f : fs) { if (is_const(f)) k = k * const_old(f); else rest.push_back(f); }
+            if (k != Fr::one() && rest.size() == 1 && absorbable(rest[0], OP_ADD)) {
+                std::vector<uint32_t> terms, nc;
+                flat(rest[0], OP_ADD, terms);
+                Fr cs = Fr::zero();
+                for (uint32_t t : terms) { if (is_const(t)) cs = cs + const_old(t); else nc.push_back(t); }
+                if (nc.size() <= 1) {   // k·(t + c) = k·t + k·c, the product k·t re-paired by readiness
+                    if (!nc.empty()) {
+                        std::vector<uint32_t> f2;
+                        flat(nc[0], OP_MUL, f2);
+                        items.push_back(prod_of({add_const(k)}, f2));
+                    }
+                    c = c + k * cs;
+                    return;
+                }
+            }
+        }
+        items.push_back(emit(o));
+    }
+    uint32_t emit(uint32_t o) {
+        if (map_[o] >= 0) return (uint32_t)map_[o];
+        const VmInstr& n = in_[o];
+        uint32_t r;
+        if (is_const(o)) {
+            r = add_const(const_old(o));
+        } else if (is_duo(o, OP_ADD)) {
+            std::vector<uint32_t> items;
+            Fr c = Fr::zero();
+            sum_items(n.a, items, c);
+            sum_items(n.b, items, c);
+            if (!c.is_zero() || items.empty()) items.push_back(add_const(c));
+            r = combine(items, OP_ADD);
+        } else if (is_duo(o, OP_MUL)) {
+            std::vector<uint32_t> fs;
+            flat(n.a, OP_MUL, fs);
+            flat(n.b, OP_MUL, fs);
+            // k·(t + c) at the top of a product that nobody sums up: the same distribution, as a sum of its own
+            std::vector<uint32_t> items;
+            Fr c = Fr::zero();
+            bool as_sum = false;
+            {
+                std::vector<uint32_t> rest;
+                Fr k = Fr::one();
+                for (uint32_t f : fs) { if (is_const(f)) k = k * const_old(f); else rest.push_back(f); }
+                if (k != Fr::one() && rest.size() == 1 && absorbable(rest[0], OP_ADD)) {
+                    std::vector<uint32_t> terms, nc;
+                    flat(rest[0], OP_ADD, terms);
+                    Fr cs = Fr::zero();
+                    for (uint32_t t : terms) { if (is_const(t)) cs = cs + const_old(t); else nc.push_back(t); }
+                    if (nc.size() <= 1) {
+                        if (!nc.empty()) {
+                            std::vector<uint32_t> f2;
+                            flat(nc[0], OP_MUL, f2);
+                            items.push_back(prod_of({add_const(k)}, f2));
+                        }
+                        c = k * cs;
+                        as_sum = true;
+                    }
+                }
+            }
+            if (as_sum) {
+                if (!c.is_zero() || items.empty()) items.push_back(add_const(c));
+                r = combine(items, OP_ADD);
+            } else {
+                r = prod_of({}, fs);
+            }
+        } else {
+            VmInstr m = n;
+            const uint32_t k = kind(n);
+            if (k == VM_UNO || k == VM_DUO || k == VM_TRES) m.a = emit(n.a);
+            if (k == VM_DUO || k == VM_TRES) m.b = emit(n.b);
+            if (k == VM_TRES) m.c = emit(n.c);
+            r = add_node(m);
+        }
+        map_[o] = r;
+        return r;
+    }
+
+public:
+    VmOptimizer(const std::vector<VmInstr>& prog, const std::vector<uint8_t>& consts, const std::vector<uint32_t>& signals)
+        : in_(prog), cin_(consts), wire_(prog.size(), 0), uses_(prog.size(), 0), map_(prog.size(), -1) {
+        for (uint32_t s : signals) wire_[s] = 1;
+        for (const VmInstr& n : prog) {
+            const uint32_t k = kind(n);
+            if (k == VM_UNO || k == VM_DUO || k == VM_TRES) uses_[n.a]++;
+            if (k == VM_DUO || k == VM_TRES) uses_[n.b]++;
+            if (k == VM_TRES) uses_[n.c]++;
+        }
+    }
+    VmOptimized run(const std::vector<uint32_t>& signals) {
+        for (uint32_t o = 0; o < in_.size(); o++) {
+            // a node that its consumers fold in is emitted by them (or never); wires, shared nodes and everything else now
+            if (!wire_[o] && (absorbable(o, OP_ADD) || absorbable(o, OP_MUL) || is_const(o))) continue;
+            if (!wire_[o] && uses_[o] == 0) continue;
+            emit(o);
+        }
+        VmOptimized r;
+        r.prog = out_;
+        r.consts.resize(32 * cval_.size());
+        for (size_t i = 0; i < cval_.size(); i++) {
+            u32 c[8];
+            cval_[i].to_canonical(c);
+            memcpy(r.consts.data() + 32 * i, c, 32);
+        }
+        for (uint32_t s : signals) r.signals.push_back(emit(s));
+        return r;
+    }
+};
+inline VmOptimized vm_optimize_program(const std::vector<VmInstr>& prog, const std::vector<uint8_t>& consts, const std::vector<uint32_t>& signals) {
+    VmOptimizer o(prog, consts, signals);
+    return o.run(signals);
+}
+
 // k_witness evaluates the graph with four warps per 32 proofs: the nodes are list-scheduled into bundles of ≤ VM_SLOTS mutually
 // independent nodes (every operand lies in an earlier bundle), warp w executes slot w.  Recent values are also kept in a
 // shared-memory ring of VM_RING bundles, so an operand produced ≤ VM_RING − 1 bundles ago is a shared-memory read instead of an

@@ -73,7 +73,7 @@ static size_t vm_smem_bytes(u32 n_consts_smem) {
 // experiment, measured and removed: ONE warp carrying 8 proofs with lane = slot + 4·proof and __syncwarp instead of the CTA
 // barrier was SLOWER — single proof 6.83 → 7.63 ms, batch 4 096 8.33 → 15.2 ms: the four slots of a bundle hold different
 // operations and a warp runs divergent lanes one after the other, while four warps run them side by side on four schedulers.)
-__global__ void __launch_bounds__(128) k_witness(CircuitDev c, const uint8_t* __restrict__ inputs, Fr* vals, u32 B, u32* __restrict__ err) {
+__global__ void __launch_bounds__(32 * VM_SLOTS) k_witness(CircuitDev c, const uint8_t* __restrict__ inputs, Fr* vals, u32 B, u32* __restrict__ err) {
     extern __shared__ __align__(128) uint4 sm[];   // ring [VM_RING · VM_SLOTS][2][32 lanes] | constants [n][2] | schedule stages | mbarriers
     const u32 const_base = (u32)(VM_RING_BYTES / sizeof(uint4));
     uint4* stage = sm + const_base + (size_t)c.n_consts_smem * 2;                           // [VM_STAGES][VM_STAGE_BUNDLES][VM_SLOTS][2]
@@ -143,7 +143,7 @@ void launch_witness(const CircuitDev& c, const uint8_t* d_inputs, Fr* d_vals, u3
     // the shared-memory attribute is per device (a process may drive several GPUs): set on every launch, it is a cheap call
     const size_t smem = vm_smem_bytes(c.n_consts_smem);
     ZK_CUDA_CHECK(cudaFuncSetAttribute(k_witness, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_witness<<<(B + 31) / 32, 128, smem, s>>>(c, d_inputs, d_vals, B, d_err);
+    k_witness<<<(B + 31) / 32, 32 * VM_SLOTS, smem, s>>>(c, d_inputs, d_vals, B, d_err);
     ZK_CUDA_CHECK(cudaGetLastError());
 }
 u32 vm_schedule_block_bundles() { return VM_STAGE_BUNDLES; }

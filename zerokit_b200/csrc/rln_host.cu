@@ -651,7 +651,15 @@ Rln::Rln(size_t tree_depth, const uint8_t* zkey, size_t zlen, const uint8_t* gra
         throw RlnError(std::string("Graph error: ") + e.what());
     }
     check_graph_shape();
-    compute_known_mask();
+    compute_known_mask();   // on the graph as the reference sees it
+    if (env_int("RLN_B200_WITNESS_REASSOC", 1)) {
+        // the witness program with its sums and products re-associated by readiness (host_util.hpp vm_optimize_program): same wires,
+        // a dependency chain a third shorter — k_witness is paced by that chain
+        VmOptimized o = vm_optimize_program(gh_.prog, gh_.consts, gh_.signals);
+        gh_.prog.swap(o.prog);
+        gh_.consts.swap(o.consts);
+        gh_.signals.swap(o.signals);
+    }
     {
         const int mb = env_int("RLN_B200_MAX_BATCH", 4096);
         if (mb < 1 || mb > (1 << 20)) throw RlnError("Configuration error: RLN_B200_MAX_BATCH must be in [1, 1048576]");

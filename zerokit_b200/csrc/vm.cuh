@@ -15,8 +15,8 @@ enum VmDuo : u32 {
 };
 
 // bundle schedule of the graph (host_util.hpp vm_build_schedule, k_prover.cu k_witness)
-constexpr u32 VM_SLOTS = 4;    // nodes per bundle = warps per CTA
-constexpr u32 VM_RING = 16;    // bundles whose values stay in the shared-memory ring
+constexpr u32 VM_SLOTS = 8;    // nodes per bundle = warps per CTA (two per scheduler: they are latency-bound, so they interleave for free)
+constexpr u32 VM_RING = 8;     // bundles whose values stay in the shared-memory ring
 enum VmSrc : u32 { VM_SRC_RING = 0, VM_SRC_CONST = 1, VM_SRC_GLOBAL = 2 };
 
 struct VmInstr {  // 16 bytes: one 128-bit load per node
