@@ -113,6 +113,7 @@ int emu_witness_scheduled(const uint8_t* graph, size_t glen, const uint8_t* inpu
             else if (kind == VM_CONST) v = consts[r.a];
             else if (kind == VM_INPUT) v = ld<Fr>(inputs + 32 * r.a);
             else if (kind == VM_UNO) { if (op == 0) v = operand(r.a).neg(); else { bad = 1; v = Fr::zero(); } }
+            else if (op == VM_TRES_FMA) v = operand(r.a) * operand(r.b) + operand(r.c);
             else { Fr t = operand(r.a); v = t.is_zero() ? operand(r.c) : operand(r.b); }
             res[sl] = v;
         }
@@ -164,6 +165,7 @@ int emu_witness_optimized(const uint8_t* graph, size_t glen, const uint8_t* inpu
             else if (kind == VM_CONST) v = consts[r.a];
             else if (kind == VM_INPUT) v = ld<Fr>(inputs + 32 * r.a);
             else if (kind == VM_UNO) { if (op == 0) v = operand(r.a).neg(); else { bad = 1; v = Fr::zero(); } }
+            else if (op == VM_TRES_FMA) v = operand(r.a) * operand(r.b) + operand(r.c);
             else { Fr t = operand(r.a); v = t.is_zero() ? operand(r.c) : operand(r.b); }
             res[sl] = v;
         }
@@ -179,7 +181,15 @@ int emu_witness_optimized(const uint8_t* graph, size_t glen, const uint8_t* inpu
         const VmInstr& n = opt.prog[opt.signals[w]];
         st(wires_out + 32 * w, (n.kind_op & 0xff) == VM_CONST ? consts[n.a] : vals[opt.signals[w]]);
     }
-    if (stats) { stats[0] = (uint32_t)opt.prog.size(); stats[1] = (uint32_t)consts.size(); stats[2] = nb; stats[3] = stored; }
+    uint32_t far = 0, operands = 0;
+    for (const VmRecord& r : recs) {
+        if (r.kind_op == 0xffffffffu) continue;
+        const uint32_t kind = r.kind_op & 0xff;
+        const uint32_t ops[3] = {r.a, r.b, r.c};
+        const int no = kind == VM_UNO ? 1 : kind == VM_DUO ? 2 : kind == VM_TRES ? 3 : 0;
+        for (int k = 0; k < no; k++) { operands++; if ((ops[k] >> 30) == VM_SRC_GLOBAL) far++; }
+    }
+    if (stats) { stats[0] = (uint32_t)opt.prog.size(); stats[1] = (uint32_t)consts.size(); stats[2] = nb; stats[3] = stored; stats[4] = far; stats[5] = operands; }
     return bad;
 }
 // ---- the pairing VM (verify_vm*.hpp): program built by the product's own tracer / scheduler, executed here lane by lane -------------

@@ -149,12 +149,13 @@ def test_depth_reduced_witness_program(emu, depth, sub):
             buf = G.inputs_buffer(g, rnd.randrange(R), 100, 1 + trial, pe, idx, rnd.randrange(R), 100)
         inputs = b"".join(int(v).to_bytes(32, "little") for v in buf)
         out = ctypes.create_string_buffer(32 * len(g.signals))
-        stats = (ctypes.c_uint32 * 4)()
+        stats = (ctypes.c_uint32 * 6)()
         assert emu.emu_witness_optimized(graph, len(graph), inputs, out, stats) == 0
         wires = [int.from_bytes(out.raw[32 * i:32 * i + 32], "little") for i in range(len(g.signals))]
         assert wires == G.evaluate(g, buf)
-    nodes, consts, bundles, stored = stats
-    assert bundles < 0.68 * (10000 if depth == 20 else 5440) and consts <= 1536 and stored < nodes // 3
+    nodes, consts, bundles, stored, far, operands = stats
+    assert bundles < 0.55 * (10000 if depth == 20 else 5440) and consts <= 1536 and stored < nodes // 3
+    assert far < 0.05 * operands        # operands that come from HBM instead of the shared-memory ring or the constant table
 
 
 def test_glv_split_and_double_mul(emu):

@@ -612,6 +612,7 @@ public:
             if (k == VM_TRES) uses_[n.c]++;
         }
     }
+public:
     VmOptimized run(const std::vector<uint32_t>& signals) {
         for (uint32_t o = 0; o < in_.size(); o++) {
             // a node that its consumers fold in is emitted by them (or never); wires, shared nodes and everything else now
@@ -619,16 +620,64 @@ public:
             if (!wire_[o] && uses_[o] == 0) continue;
             emit(o);
         }
+        std::vector<uint32_t> sig;
+        for (uint32_t s : signals) sig.push_back(emit(s));
+        fuse_and_compact(sig);
         VmOptimized r;
         r.prog = out_;
+        r.signals = sig;
         r.consts.resize(32 * cval_.size());
         for (size_t i = 0; i < cval_.size(); i++) {
             u32 c[8];
             cval_[i].to_canonical(c);
             memcpy(r.consts.data() + 32 * i, c, 32);
         }
-        for (uint32_t s : signals) r.signals.push_back(emit(s));
         return r;
+    }
+
+private:
+    // late·product + early sum → one node (a·b + c: the addition rides in the product's bundle), then dead nodes are dropped
+    void fuse_and_compact(std::vector<uint32_t>& sig) {
+        const size_t n = out_.size();
+        std::vector<uint32_t> uses(n, 0);
+        std::vector<uint8_t> wire(n, 0), dead(n, 0);
+        for (uint32_t s : sig) wire[s] = 1;
+        auto count = [&](const VmInstr& i, int d) {
+            const uint32_t k = kind(i);
+            if (k == VM_UNO || k == VM_DUO || k == VM_TRES) uses[i.a] += d;
+            if (k == VM_DUO || k == VM_TRES) uses[i.b] += d;
+            if (k == VM_TRES) uses[i.c] += d;
+        };
+        for (const VmInstr& i : out_) count(i, 1);
+        for (size_t i = 0; i < n; i++) {
+            VmInstr& a = out_[i];
+            if (!(kind(a) == VM_DUO && op(a) == OP_ADD)) continue;
+            uint32_t p = a.a, q = a.b;
+            auto fusable = [&](uint32_t x) { return kind(out_[x]) == VM_DUO && op(out_[x]) == OP_MUL && uses[x] == 1 && !wire[x]; };
+            if (fusable(q) && (!fusable(p) || ready_[q] > ready_[p])) std::swap(p, q);
+            if (!fusable(p) || ready_[p] < ready_[q]) continue;   // only when the product is the operand that arrives last
+            const VmInstr m = out_[p];
+            a = VmInstr{VM_TRES | (VM_TRES_FMA << 8), m.a, m.b, q};
+            dead[p] = 1;
+        }
+        for (size_t i = n; i-- > 0;) {   // whatever nobody reads any more
+            if (dead[i]) continue;
+            if (!wire[i] && uses[i] == 0) dead[i] = 1;
+        }
+        std::vector<uint32_t> renum(n, 0);
+        std::vector<VmInstr> packed;
+        for (size_t i = 0; i < n; i++) {
+            if (dead[i]) continue;
+            VmInstr x = out_[i];
+            const uint32_t k = kind(x);
+            if (k == VM_UNO || k == VM_DUO || k == VM_TRES) x.a = renum[x.a];
+            if (k == VM_DUO || k == VM_TRES) x.b = renum[x.b];
+            if (k == VM_TRES) x.c = renum[x.c];
+            renum[i] = (uint32_t)packed.size();
+            packed.push_back(x);
+        }
+        for (uint32_t& s : sig) s = renum[s];
+        out_.swap(packed);
     }
 };
 inline VmOptimized vm_optimize_program(const std::vector<VmInstr>& prog, const std::vector<uint8_t>& consts, const std::vector<uint32_t>& signals) {
@@ -653,7 +702,21 @@ inline std::vector<VmRecord> vm_build_schedule(const std::vector<VmInstr>& prog,
                                                bool consts_resident = true) {
     const size_t n = prog.size();
     const uint32_t NONE = 0xffffffffu;
-    std::vector<uint32_t> bundle(n, NONE), slot(n, 0), fill;
+    // Slots s and s + VM_SLOTS/2 are warps of the same scheduler.  A product keeps that scheduler's multiplier busy for most of its
+    // 865 cycles, so two products on one scheduler take twice as long (measured: 8 free-for-all slots, 1 700 cycles per bundle);
+    // an addition next to a product is nearly free.  Hence two classes: heavy nodes (anything with a product in it) go to the
+    // first half of the slots, light ones (additions, loads, selections) to the second half.
+    const bool two_classes = VM_SLOTS >= 8;   // with one warp per scheduler every slot is as good as any other
+    const uint32_t CAP = two_classes ? VM_SLOTS / 2 : VM_SLOTS;
+    std::vector<uint32_t> bundle(n, NONE), slot(n, 0);
+    std::vector<uint32_t> fill[2];   // per bundle: heavy, light
+    auto heavy = [&](size_t i) -> int {
+        if (!two_classes) return 0;
+        const uint32_t k = prog[i].kind_op & 0xff, o = prog[i].kind_op >> 8;
+        if (k == VM_DUO) return (o == OP_ADD || o == OP_SUB) ? 0 : 1;
+        if (k == VM_TRES) return o == VM_TRES_FMA ? 1 : 0;
+        return 0;
+    };
     auto wire = [&](size_t i) { return !is_signal || (*is_signal)[i]; };
     for (size_t i = 0; i < n; i++) {
         const VmInstr& in = prog[i];
@@ -667,14 +730,39 @@ inline std::vector<VmRecord> vm_build_schedule(const std::vector<VmInstr>& prog,
         if (kind == VM_UNO || kind == VM_DUO || kind == VM_TRES) after(in.a);
         if (kind == VM_DUO || kind == VM_TRES) after(in.b);
         if (kind == VM_TRES) after(in.c);
+        const int h = heavy(i);
         for (;; b++) {
-            if (b >= fill.size()) fill.resize(b + 1, 0);
-            if (fill[b] < VM_SLOTS) break;
+            if (b >= fill[0].size()) { fill[0].resize(b + 1, 0); fill[1].resize(b + 1, 0); }
+            if (fill[h][b] < CAP) break;
         }
         bundle[i] = b;
-        slot[i] = fill[b]++;
+        fill[h][b]++;
     }
-    n_bundles = (uint32_t)fill.size();
+    n_bundles = (uint32_t)fill[0].size();
+    // As-soon-as-possible leaves values that are ready early but consumed late (the side sums of every Poseidon round) far from their
+    // reader: beyond the ring, i.e. an L2 round trip inside the reader's bundle.  Push every node as late as its readers and the free
+    // slots of its class allow (readers have larger indices, so they are final when the node is visited).
+    {
+        std::vector<uint32_t> first_reader(n, NONE);
+        for (size_t i = n; i-- > 0;) {
+            if (bundle[i] == NONE) continue;
+            const int h = heavy(i);
+            if (first_reader[i] != NONE) {
+                for (uint32_t b = first_reader[i] - 1; b > bundle[i]; b--)
+                    if (fill[h][b] < CAP) { fill[h][bundle[i]]--; fill[h][b]++; bundle[i] = b; break; }
+            }
+            const VmInstr& in = prog[i];
+            const uint32_t kind = in.kind_op & 0xff;
+            auto seen_by = [&](uint32_t op) { if (bundle[op] != NONE && bundle[i] < first_reader[op]) first_reader[op] = bundle[i]; };
+            if (kind == VM_UNO || kind == VM_DUO || kind == VM_TRES) seen_by(in.a);
+            if (kind == VM_DUO || kind == VM_TRES) seen_by(in.b);
+            if (kind == VM_TRES) seen_by(in.c);
+        }
+        std::fill(fill[0].begin(), fill[0].end(), 0);
+        std::fill(fill[1].begin(), fill[1].end(), 0);
+        for (size_t i = 0; i < n; i++)
+            if (bundle[i] != NONE) { const int h = heavy(i); slot[i] = (h || !two_classes ? 0 : CAP) + fill[h][bundle[i]]++; }
+    }
     VmRecord empty;
     memset(&empty, 0, sizeof empty);
     empty.kind_op = 0xffffffffu;

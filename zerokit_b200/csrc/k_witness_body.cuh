@@ -120,6 +120,11 @@ __global__ void __launch_bounds__(32 * VM_SLOTS) k_witness(CircuitDev c, const u
                 } else if (kind == VM_UNO) {
                     if (op == 0) v = vm_operand(w0.z, sm, const_base, vals, B, j, lane).neg();
                     else { bad = 1; v = Fr::zero(); }  // "uno operator Id not implemented" (graph.rs:189-193)
+                } else if (op == VM_TRES_FMA) {   // a·b + c (the rewrite's fused node: the sum rides in the product's bundle)
+                    const u32 third = recs[2 * (i * VM_SLOTS + slot) + 1].x;
+                    const Fr z = vm_operand(third, sm, const_base, vals, B, j, lane);   // fetched before the product, not after it
+                    const Fr x = vm_operand(w0.z, sm, const_base, vals, B, j, lane), y = vm_operand(w0.w, sm, const_base, vals, B, j, lane);
+                    v = (w0.z == w0.w ? x.sqr() : x * y) + z;
                 } else {  // TernCond (graph.rs:216-222)
                     const u32 third = recs[2 * (i * VM_SLOTS + slot) + 1].x;
                     const Fr t = vm_operand(w0.z, sm, const_base, vals, B, j, lane);

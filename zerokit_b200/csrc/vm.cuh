@@ -8,6 +8,8 @@
 namespace zk {
 
 enum VmKind : u32 { VM_INPUT = 0, VM_CONST = 1, VM_UNO = 2, VM_DUO = 3, VM_TRES = 4 };
+// VM_TRES with op 0 is the graph's TernCond; op 1 is a·b + c, which only the depth-reducing rewrite of host_util.hpp produces
+constexpr u32 VM_TRES_FMA = 1;
 // DuoOp numbering of the protobuf schema (rln/src/circuit/iden3calc/proto.rs:84-106)
 enum VmDuo : u32 {
     OP_MUL = 0, OP_DIV, OP_ADD, OP_SUB, OP_POW, OP_IDIV, OP_MOD, OP_EQ, OP_NEQ, OP_LT, OP_GT, OP_LEQ, OP_GEQ,
