@@ -440,6 +440,80 @@ __global__ void __launch_bounds__(64) k_assemble_g2(ProverKeyDev pk, const G2Aff
     compress_g2(g2_b.to_affine(), proofs + 128 * (size_t)j + 32, affine ? affine + 256 * (size_t)j + 64 : nullptr);
 }
 
+// The same assembly for a handful of proofs (a single ffi_generate_rln_proof call): one CTA per proof, the independent chains on
+// four warps — four schedulers — instead of one thread doing them one after the other (2.0 ms of a single proof's 8 ms).  With
+// P = ΣA + α₁ and Q = ΣB₁ + β₁,   s·g_a + r·g1_b − rs·δ₁ = s·P + r·Q + rs·δ₁,   so the Straus double multiplication does not wait for
+// the r·δ₁ / s·δ₁ terms:  warp 0: π_c = s·P + r·Q + (warp 2's sum), warp 1: π_a = P + r·δ₁, warp 2: rs·δ₁ + ΣL + ΣH, warp 3: π_b.
+// Same group elements as k_assemble_g1 / _g2, hence the same bytes.
+__global__ void __launch_bounds__(128) k_assemble_small(ProverKeyDev pk, const G1Affine* __restrict__ dtab, int c, int K,
+                                                        const G2Affine* __restrict__ dtab2, int c2, int K2, const G1XYZZ* __restrict__ sum,
+                                                        const G2XYZZ* __restrict__ sum2, u32 B, const uint8_t* __restrict__ rs,
+                                                        const uint8_t* __restrict__ partial, uint8_t* __restrict__ proofs,
+                                                        uint8_t* __restrict__ affine) {
+    __shared__ G1XYZZ s_tail;
+    const u32 j = blockIdx.x, warp = threadIdx.x >> 5;
+    const bool lead = (threadIdx.x & 31) == 0;   // one lane per warp works; the others stay for the warp-wide barrier
+    u32 r[8], s[8];
+    load_scalar_bytes(rs + 64 * (size_t)j, r);
+    load_scalar_bytes(rs + 64 * (size_t)j + 32, s);
+    uint8_t* o = proofs + 128 * (size_t)j;
+    uint8_t* af = affine ? affine + 256 * (size_t)j : nullptr;
+    const uint8_t* pp = partial ? partial + 320 * (size_t)j : nullptr;
+    if (warp == 3) {
+        if (!lead) return;
+        G2XYZZ g2_b = sum2[j];
+        const G2Affine base_b = pp ? load_affine_g2(pp + 128) : pk.beta_g2;
+        if (!base_b.is_inf()) g2_b.add_affine(base_b);
+        g2_b.add(fixed_base_mul<Fq2>(dtab2, c2, K2, s));
+        compress_g2(g2_b.to_affine(), o + 32, af ? af + 64 : nullptr);
+        return;
+    }
+    if (warp == 2) {
+        if (lead) {
+            u32 rsv[8];
+            (Fr::from_canonical(r) * Fr::from_canonical(s)).to_canonical(rsv);
+            G1XYZZ t = fixed_base_mul<Fq>(dtab, c, K, rsv);
+            t.add(sum[2 * (size_t)B + j]);
+            t.add(sum[3 * (size_t)B + j]);
+            if (pp) { const G1Affine base_c = load_affine_g1(pp + 256); if (!base_c.is_inf()) t.add_affine(base_c); }
+            s_tail = t;
+        }
+        __syncwarp();
+        asm volatile("bar.sync 1, 64;" ::: "memory");   // with warp 0
+        return;
+    }
+    if (warp == 1) {
+        if (!lead) return;
+        G1XYZZ P = sum[0 * (size_t)B + j];
+        const G1Affine base_a = pp ? load_affine_g1(pp) : pk.alpha_g1;
+        if (!base_a.is_inf()) P.add_affine(base_a);
+        P.add(fixed_base_mul<Fq>(dtab, c, K, r));
+        compress_g1(P.to_affine(), o, af);
+        return;
+    }
+    G1XYZZ g_c = G1XYZZ::infinity();
+    if (lead) {
+        G1XYZZ P = sum[0 * (size_t)B + j];
+        const G1Affine base_a = pp ? load_affine_g1(pp) : pk.alpha_g1;
+        if (!base_a.is_inf()) P.add_affine(base_a);
+        u32 rnz = 0;
+        for (int i = 0; i < 8; i++) rnz |= r[i];
+        G1XYZZ Q = G1XYZZ::infinity();
+        if (rnz) {
+            Q = sum[1 * (size_t)B + j];
+            const G1Affine base_b = pp ? load_affine_g1(pp + 64) : pk.beta_g1;
+            if (!base_b.is_inf()) Q.add_affine(base_b);
+        }
+        g_c = glv_double_mul(P, s, Q, r, rnz != 0);
+    }
+    __syncwarp();
+    asm volatile("bar.sync 1, 64;" ::: "memory");   // warp 2's sum is in shared memory
+    if (lead) {
+        g_c.add(s_tail);
+        compress_g1(g_c.to_affine(), o + 96, af ? af + 192 : nullptr);
+    }
+}
+
 // ------------------------------------------------------------------------------------------- host orchestration
 // bases per task.  A thread walks `chunk` bases for one proof, a CTA carries 128 proofs, and the CTAs of one launch run in
 // waves of (SMs × resident CTAs): long CTAs in few waves leave part of the chip idle at the end of the launch, short CTAs in
@@ -550,7 +624,10 @@ void launch_assemble(const FixedMsmPlan& plan, const ProverKeyDev& pk, u32 B, co
                      const uint8_t* d_partial, uint8_t* d_proofs_out, uint8_t* d_proofs_affine, cudaStream_t s) {
     // π_b (G2) does not depend on π_a / π_c (G1) and both are latency-bound chains of one thread per proof: side by side when the
     // caller lends a second stream (they write disjoint bytes of every proof)
-    if (ws.side) {
+    if (B <= 32) {   // few proofs: latency is what counts — one CTA per proof, the chains on four warps, one launch
+        k_assemble_small<<<B, 128, 0, s>>>(pk, plan.delta1_table, plan.cd, plan.Kd, plan.delta2_table, plan.cd2, plan.Kd2, ws.sum_g1, ws.sum_g2, B,
+                                           d_rs, d_partial, d_proofs_out, d_proofs_affine);
+    } else if (ws.side) {
         ZK_CUDA_CHECK(cudaEventRecord(ws.side_fork, s));
         ZK_CUDA_CHECK(cudaStreamWaitEvent(ws.side, ws.side_fork, 0));
         k_assemble_g2<<<(B + 63) / 64, 64, 0, ws.side>>>(pk, plan.delta2_table, plan.cd2, plan.Kd2, ws.sum_g2, B, d_rs, d_partial, d_proofs_out, d_proofs_affine);
