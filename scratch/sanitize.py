@@ -13,6 +13,15 @@ p = rln.generate_rln_proof_with_rs(z.RLNWitnessInput.from_bytes_le(wb), int(k['i
 assert p.to_bytes_le().hex() == k['rln_proof_le_hex']
 out = rln.prove_batch(wb * 3, 3, fr_bytes([1, 2, 3, 4, 5, 6]))
 assert rln.verify_batch(out, 3) == [1, 1, 1]
+# both verifier kernels on good, wrong, malformed and handed-back inputs (the lane-parallel program, its fallback, the thread kernel)
+bad = bytearray(out[:290]); bad[32] ^= 0x80                      # A's sign bit: a valid encoding of the wrong point
+inf = bytearray(out[:290]); inf[32] = (inf[32] & 0x3F) | 0x40    # A at infinity: the program hands the proof back
+mal = bytearray(out[:290]); mal[32] |= 0xC0                      # both flags: refused
+mix = out[:290] + bytes(bad) + bytes(inf) + bytes(mal)
+assert rln.verify_batch(mix, 4) == [1, 0, 0, 2]
+rln.set_verify_vm_max(0)
+assert rln.verify_batch(mix, 4) == [1, 0, 0, 2]
+rln.set_verify_vm_max(4096)
 pp = rln.partial_batch(wb * 3, 3)
 assert rln.finish_batch(wb * 3, 3, pp, fr_bytes([1, 2, 3, 4, 5, 6])) == out
 rln.set_leaves_from(5, list(range(1, 40)))

@@ -51,6 +51,8 @@ void launch_merkle_paths(const Fr* d_nodes, u32 depth, const u64* d_indices, siz
 // nullifier_0..nullifier_{k-1}], k = max_out (1 for the single message-id circuit)
 struct InputSlots { u32 secret, limit, message_id, path, index, x, ext_null, depth, n_slots, selector, max_out, multi; };
 void launch_proof_values(const uint8_t* d_inputs, InputSlots sl, size_t n, uint8_t* d_out, cudaStream_t s);
+// the same record read off an evaluated witness (vals [node][B], wire → node map): the public signals
+void launch_values_from_wires(const Fr* d_vals, const u32* d_signals, u32 B, u32 max_out, uint8_t* d_out, cudaStream_t s);
 // generic small helpers used by the FFI utilities (single-thread kernels)
 void launch_poseidon_n(const uint8_t* d_in_bytes, int n_inputs, uint8_t* d_out_bytes, cudaStream_t s);
 // count independent hashes of n_inputs (1…3) canonical values each, one thread per hash
@@ -121,6 +123,7 @@ struct FixedMsmPlan {
     MsmGroupDev g2;      // B2
     const G1Affine* delta1_table;  // [K][2^(c-1)] multiples of δ₁ (r·δ₁, s·δ₁, rs·δ₁ in the assembly)
     const G2Affine* delta2_table;  // [K2][2^(c2-1)] multiples of δ₂
+    const G1Affine *alpha1_table, *beta1_table;   // the same for α₁ and β₁ (geometry of the δ₁ table): s·α₁, r·β₁ of the folded assembly
 };
 // builds [base][window][digit] tables from affine bases (Montgomery, no infinities)
 void launch_build_table_g1(const G1Affine* d_bases, u32 n, int c, int K, G1Affine* d_table, cudaStream_t s);
@@ -142,12 +145,19 @@ struct MsmWorkspace {
     const MsmTask *tasks_g1, *tasks_g2;  // device arrays built from msm_make_tasks for this B
     u32 n_tasks_g1, n_tasks_g2;
     cudaEvent_t* ev;  // optional: 6 events recorded around [g1 accum, g1 reduce, g2 accum, g2 reduce, assemble]
+    // optional (a handful of full proofs): s·ΣzᵢAᵢ and r·ΣzᵢB₁ᵢ as two more table sums over the scaled witness values fold_s = s·z,
+    // fold_r = r·z ([node][B] like vals), so that the assembly needs no variable-base multiplication: partial sums and sums [2][B]
+    const Fr *fold_s = nullptr, *fold_r = nullptr;
+    G1XYZZ *fold_part = nullptr, *fold_sum = nullptr;
+    u32 n_tasks_ab = 0;                                   // tasks of the groups A and B₁ (a prefix of tasks_g1)
     cudaStream_t side = nullptr;                          // optional second stream + two events: the G2 assembly runs beside the G1 assembly
     cudaEvent_t side_fork = nullptr, side_join = nullptr;
 };
 // MSM phases: all bases (full proof), the known prefix of A/B₁/B₂/L (partial proof), or the unknown suffix plus H (finish)
 enum MsmPhase { MSM_FULL = 0, MSM_KNOWN = 1, MSM_UNKNOWN = 2 };
 std::vector<MsmTask> msm_make_tasks(const FixedMsmPlan& plan, u32 B, bool g2, int phase);
+// out_s[row][j] = s_j·vals[row][j], out_r[row][j] = r_j·vals[row][j]   (rs: B × (r | s), 32 canonical bytes each)
+void launch_scale_vals(const Fr* d_vals, const uint8_t* d_rs, u32 n_rows, u32 B, Fr* d_out_s, Fr* d_out_r, cudaStream_t s);
 // accumulate + reduce over ws.tasks_* → ws.sum_g1[4][B], ws.sum_g2[B]
 void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, u32 B, MsmWorkspace& ws, cudaStream_t s);
 // assembly (partial_proof.rs:226-273) + affine + ark-compressed bytes.  rs: B × 64 canonical bytes (r | s).

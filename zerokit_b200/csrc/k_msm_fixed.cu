@@ -445,12 +445,74 @@ __global__ void __launch_bounds__(64) k_assemble_g2(ProverKeyDev pk, const G2Aff
 // P = ΣA + α₁ and Q = ΣB₁ + β₁,   s·g_a + r·g1_b − rs·δ₁ = s·P + r·Q + rs·δ₁,   so the Straus double multiplication does not wait for
 // the r·δ₁ / s·δ₁ terms:  warp 0: π_c = s·P + r·Q + (warp 2's sum), warp 1: π_a = P + r·δ₁, warp 2: rs·δ₁ + ΣL + ΣH, warp 3: π_b.
 // Same group elements as k_assemble_g1 / _g2, hence the same bytes.
-__global__ void __launch_bounds__(128) k_assemble_small(ProverKeyDev pk, const G1Affine* __restrict__ dtab, int c, int K,
+__global__ void __launch_bounds__(160) k_assemble_small(ProverKeyDev pk, const G1Affine* __restrict__ dtab, int c, int K,
                                                         const G2Affine* __restrict__ dtab2, int c2, int K2, const G1XYZZ* __restrict__ sum,
                                                         const G2XYZZ* __restrict__ sum2, u32 B, const uint8_t* __restrict__ rs,
                                                         const uint8_t* __restrict__ partial, uint8_t* __restrict__ proofs,
-                                                        uint8_t* __restrict__ affine) {
-    __shared__ G1XYZZ s_tail;
+                                                        uint8_t* __restrict__ affine, const G1XYZZ* __restrict__ fold,
+                                                        const G1Affine* __restrict__ atab, const G1Affine* __restrict__ btab) {
+    __shared__ G1XYZZ s_tail, s_beta;
+    if (fold) {
+        // Folded form (full proofs only): s·P + r·Q = s·α₁ + r·β₁ + Σ(s·zᵢ)Aᵢ + Σ(r·zᵢ)B₁ᵢ, the two sums being fold[0], fold[1] — table
+        // sums like every other, so no variable-base multiplication is left (the Straus run was ≈ 3 000 dependent products).
+        // warp 0: π_c, warp 1: π_a, warp 2: rs·δ₁ + ΣL + ΣH, warp 3: π_b, warp 4: r·β₁.
+        const u32 j = blockIdx.x, warp = threadIdx.x >> 5;
+        const bool lead = (threadIdx.x & 31) == 0;
+        u32 r[8], s[8];
+        load_scalar_bytes(rs + 64 * (size_t)j, r);
+        load_scalar_bytes(rs + 64 * (size_t)j + 32, s);
+        uint8_t* o = proofs + 128 * (size_t)j;
+        uint8_t* af = affine ? affine + 256 * (size_t)j : nullptr;
+        if (warp == 3) {
+            if (!lead) return;
+            G2XYZZ g2_b = sum2[j];
+            g2_b.add_affine(pk.beta_g2);
+            g2_b.add(fixed_base_mul<Fq2>(dtab2, c2, K2, s));
+            compress_g2(g2_b.to_affine(), o + 32, af ? af + 64 : nullptr);
+            return;
+        }
+        if (warp == 1) {
+            if (!lead) return;
+            G1XYZZ P = sum[0 * (size_t)B + j];
+            P.add_affine(pk.alpha_g1);
+            P.add(fixed_base_mul<Fq>(dtab, c, K, r));
+            compress_g1(P.to_affine(), o, af);
+            return;
+        }
+        if (warp == 2 || warp == 4) {
+            if (lead) {
+                if (warp == 2) {
+                    u32 rsv[8];
+                    (Fr::from_canonical(r) * Fr::from_canonical(s)).to_canonical(rsv);
+                    G1XYZZ t = fixed_base_mul<Fq>(dtab, c, K, rsv);
+                    t.add(sum[2 * (size_t)B + j]);
+                    t.add(sum[3 * (size_t)B + j]);
+                    s_tail = t;
+                } else {
+                    G1XYZZ t = fixed_base_mul<Fq>(btab, c, K, r);
+                    t.add(fold[1 * (size_t)B + j]);
+                    s_beta = t;
+                }
+            }
+            __syncwarp();
+            asm volatile("bar.sync 1, 96;" ::: "memory");   // with warp 0
+            return;
+        }
+        G1XYZZ g_c = G1XYZZ::infinity();
+        if (lead && warp == 0) {
+            g_c = fixed_base_mul<Fq>(atab, c, K, s);
+            g_c.add(fold[0 * (size_t)B + j]);
+        }
+        __syncwarp();
+        asm volatile("bar.sync 1, 96;" ::: "memory");
+        if (lead) {
+            g_c.add(s_beta);
+            g_c.add(s_tail);
+            compress_g1(g_c.to_affine(), o + 96, af ? af + 192 : nullptr);
+        }
+        return;
+    }
+    if (threadIdx.x >= 128) return;
     const u32 j = blockIdx.x, warp = threadIdx.x >> 5;
     const bool lead = (threadIdx.x & 31) == 0;   // one lane per warp works; the others stay for the warp-wide barrier
     u32 r[8], s[8];
@@ -514,6 +576,23 @@ __global__ void __launch_bounds__(128) k_assemble_small(ProverKeyDev pk, const G
     }
 }
 
+__global__ void __launch_bounds__(128) k_scale_vals(const Fr* __restrict__ vals, const uint8_t* __restrict__ rs, u32 n_rows, u32 B,
+                                                    Fr* __restrict__ out_s, Fr* __restrict__ out_r) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= (size_t)n_rows * B) return;
+    const u32 j = (u32)(t % B);
+    u32 r[8], s[8];
+    load_scalar_bytes(rs + 64 * (size_t)j, r);
+    load_scalar_bytes(rs + 64 * (size_t)j + 32, s);
+    const Fr v = ld_fp(vals + t);
+    st_fp(out_s + t, v * Fr::from_canonical(s));
+    st_fp(out_r + t, v * Fr::from_canonical(r));
+}
+void launch_scale_vals(const Fr* d_vals, const uint8_t* d_rs, u32 n_rows, u32 B, Fr* d_out_s, Fr* d_out_r, cudaStream_t s) {
+    const size_t n = (size_t)n_rows * B;
+    k_scale_vals<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_vals, d_rs, n_rows, B, d_out_s, d_out_r);
+}
+
 // ------------------------------------------------------------------------------------------- host orchestration
 // bases per task.  A thread walks `chunk` bases for one proof, a CTA carries 128 proofs, and the CTAs of one launch run in
 // waves of (SMs × resident CTAs): long CTAs in few waves leave part of the chip idle at the end of the launch, short CTAs in
@@ -571,6 +650,14 @@ static bool reduce_by_tree(u32 B, u32 n_tasks, bool g2) { return B < 64 || n_tas
 
 void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, u32 B, MsmWorkspace& ws, cudaStream_t s) {
     const u32 bx = B >= 128 || B < 32 ? 128 : 32;
+    // a handful of proofs: none of these launches fills the chip, so the G2 sum runs beside the G1 sums on the caller's second stream
+    const bool g2_aside = B <= 32 && ws.side && ws.side_fork && ws.side_join;
+    cudaStream_t s2 = s;
+    if (g2_aside) {
+        ZK_CUDA_CHECK(cudaEventRecord(ws.side_fork, s));
+        ZK_CUDA_CHECK(cudaStreamWaitEvent(ws.side, ws.side_fork, 0));
+        s2 = ws.side;
+    }
     {   // G1: A, B1, L, H
         AccumArgs<Fq> a;
         a.src[0] = d_vals; a.src[1] = d_h;
@@ -589,6 +676,15 @@ void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, 
             else k_msm_accum<Fq, true, 3><<<grid, bx, 0, s>>>(b);
         };
         launch_g1(0, ws.n_tasks_g1);
+        if (ws.fold_s && ws.n_tasks_ab) {   // the same A and B₁ tasks once more over s·z and r·z (folded assembly, few proofs)
+            AccumArgs<Fq> b = a;
+            b.src[0] = ws.fold_s; b.src[1] = ws.fold_r;
+            b.which[0] = 0; b.which[1] = 1;
+            b.part = ws.fold_part;
+            const dim3 grid = accum_grid(b, B, bx, ws.n_tasks_ab);
+            if (plan.glv) k_msm_accum<Fq, true, 4, true><<<grid, bx, 0, s>>>(b);
+            else k_msm_accum<Fq, true, 3><<<grid, bx, 0, s>>>(b);
+        }
         if (ws.ev) cudaEventRecord(ws.ev[1], s);
         // one CTA per (proof, group) with a shared-memory tree whenever there are many partials per proof: a thread-per-proof loop
         // over hundreds of partials leaves the chip idle (4 096 threads)
@@ -596,9 +692,11 @@ void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, 
         const u32 rx = B >= 128 ? 128 : 32;
         if (reduce_by_tree(B, ws.n_tasks_g1, false)) k_msm_reduce_small<Fq><<<dim3(B, 4), 128, 0, s>>>(ws.part_g1, ws.tasks_g1, ws.n_tasks_g1, B, ws.sum_g1);
         else k_msm_reduce<Fq><<<dim3((B + rx - 1) / rx, 4), rx, 0, s>>>(ws.part_g1, ws.tasks_g1, ws.n_tasks_g1, B, ws.sum_g1);
+        if (ws.fold_s && ws.n_tasks_ab) k_msm_reduce_small<Fq><<<dim3(B, 2), 128, 0, s>>>(ws.fold_part, ws.tasks_g1, ws.n_tasks_ab, B, ws.fold_sum);
         if (ws.ev) cudaEventRecord(ws.ev[2], s);
     }
     {   // G2: B2
+        cudaStream_t s = s2;
         AccumArgs<Fq2> a;
         a.src[0] = d_vals; a.src[1] = d_h;
         for (int i = 0; i < 4; i++) { a.row[i] = plan.g2.row; a.table[i] = (const G2Affine*)plan.g2.table; a.which[i] = plan.g2.which_src; }
@@ -612,11 +710,16 @@ void launch_msm_sums(const FixedMsmPlan& plan, const Fr* d_vals, const Fr* d_h, 
             if (plan.glv) k_msm_accum<Fq2, false, 2, true><<<grid, bx, 0, s>>>(a);
             else k_msm_accum<Fq2, false, 2><<<grid, bx, 0, s>>>(a);
         }
-        if (ws.ev) cudaEventRecord(ws.ev[3], s);
+        if (ws.ev && !g2_aside) cudaEventRecord(ws.ev[3], s);
         const u32 rx = B >= 128 ? 128 : 32;
         if (reduce_by_tree(B, ws.n_tasks_g2, true)) k_msm_reduce_small<Fq2><<<dim3(B, 1), 128, 0, s>>>(ws.part_g2, ws.tasks_g2, ws.n_tasks_g2, B, ws.sum_g2);
         else k_msm_reduce<Fq2><<<dim3((B + rx - 1) / rx, 1), rx, 0, s>>>(ws.part_g2, ws.tasks_g2, ws.n_tasks_g2, B, ws.sum_g2);
-        if (ws.ev) cudaEventRecord(ws.ev[4], s);
+        if (ws.ev && !g2_aside) cudaEventRecord(ws.ev[4], s);
+    }
+    if (g2_aside) {
+        ZK_CUDA_CHECK(cudaEventRecord(ws.side_join, s2));
+        ZK_CUDA_CHECK(cudaStreamWaitEvent(s, ws.side_join, 0));
+        if (ws.ev) { cudaEventRecord(ws.ev[3], s); cudaEventRecord(ws.ev[4], s); }   // the G2 stages are hidden behind the G1 ones
     }
 }
 
@@ -625,8 +728,10 @@ void launch_assemble(const FixedMsmPlan& plan, const ProverKeyDev& pk, u32 B, co
     // π_b (G2) does not depend on π_a / π_c (G1) and both are latency-bound chains of one thread per proof: side by side when the
     // caller lends a second stream (they write disjoint bytes of every proof)
     if (B <= 32) {   // few proofs: latency is what counts — one CTA per proof, the chains on four warps, one launch
-        k_assemble_small<<<B, 128, 0, s>>>(pk, plan.delta1_table, plan.cd, plan.Kd, plan.delta2_table, plan.cd2, plan.Kd2, ws.sum_g1, ws.sum_g2, B,
-                                           d_rs, d_partial, d_proofs_out, d_proofs_affine);
+        const bool fold = ws.fold_sum && !d_partial;
+        k_assemble_small<<<B, fold ? 160 : 128, 0, s>>>(pk, plan.delta1_table, plan.cd, plan.Kd, plan.delta2_table, plan.cd2, plan.Kd2, ws.sum_g1, ws.sum_g2,
+                                                        B, d_rs, d_partial, d_proofs_out, d_proofs_affine, fold ? ws.fold_sum : nullptr,
+                                                        plan.alpha1_table, plan.beta1_table);
     } else if (ws.side) {
         ZK_CUDA_CHECK(cudaEventRecord(ws.side_fork, s));
         ZK_CUDA_CHECK(cudaStreamWaitEvent(ws.side, ws.side_fork, 0));

@@ -251,6 +251,28 @@ void launch_proof_values(const uint8_t* d_inputs, InputSlots sl, size_t n, uint8
     k_proof_values<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(d_inputs, sl, n, d_out);
 }
 
+// The same values read off the witness: y…, root, nullifier…, x, external nullifier are the circuit's public signals, wires 1 … 2k+3
+// (rln/src/protocol/proof.rs:863-884 lists them in that order).  For a handful of proofs this replaces k_proof_values, whose one
+// thread per proof hashes the whole Merkle path again (6 ms: longer than the rest of a single proof once that is below 7 ms).
+__global__ void __launch_bounds__(64) k_values_from_wires(const Fr* __restrict__ vals, const u32* __restrict__ signals, u32 B, u32 k,
+                                                         uint8_t* __restrict__ out) {
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= B) return;
+    auto wire = [&](u32 w) { return ld_fp(vals + (size_t)__ldg(signals + w) * B + j); };
+    uint8_t* o = out + j * (size_t)(32 * (3 + 2 * k));
+    store_canonical(o, wire(k + 1));
+    store_canonical(o + 32, wire(2 * k + 3));
+    store_canonical(o + 64, wire(2 * k + 2));
+    for (u32 i = 0; i < k; i++) {
+        store_canonical(o + 96 + 32 * i, wire(1 + i));
+        store_canonical(o + 96 + 32 * (k + i), wire(k + 2 + i));
+    }
+}
+void launch_values_from_wires(const Fr* d_vals, const u32* d_signals, u32 B, u32 max_out, uint8_t* d_out, cudaStream_t s) {
+    if (!B) return;
+    k_values_from_wires<<<(B + 63) / 64, 64, 0, s>>>(d_vals, d_signals, B, max_out, d_out);
+}
+
 __global__ void k_poseidon_n(const uint8_t* in, int n, uint8_t* out) {
     Fr r;
     if (n == 1) r = d_hash1(load_canonical(in));

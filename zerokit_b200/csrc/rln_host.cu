@@ -549,7 +549,7 @@ class Rln {
    private:
     struct TaskSet {
         DevMem g1, g2;
-        u32 n1 = 0, n2 = 0;
+        u32 n1 = 0, n2 = 0, n_ab = 0;   // n_ab: tasks of the groups A and B₁ (they come first)
     };
     TaskSet& tasks_for(u32 B, int phase);
     void compute_known_mask();
@@ -572,8 +572,12 @@ class Rln {
     CircuitDev circ_{};
     // fixed-base tables
     DevMem d_sched_;
-    DevMem d_tab_[5], d_rows_[5], d_gamma_abc_, d_gamma_tab_, d_delta1_tab_, d_delta2_tab_, d_vk_pre_, d_vm_code_, d_vm_consts_, d_vfy_in_, d_vfy_ok_;
+    DevMem d_tab_[5], d_rows_[5], d_gamma_abc_, d_gamma_tab_, d_delta1_tab_, d_delta2_tab_, d_alpha1_tab_, d_beta1_tab_, d_vk_pre_, d_vm_code_, d_vm_consts_, d_vfy_in_, d_vfy_ok_;
     VerifyVmDev vm_{};
+    DevMem ws_fold_s_, ws_fold_r_, ws_fold_part_, ws_fold_sum_;   // folded assembly of ≤ FOLD_MAX full proofs
+    static constexpr size_t FOLD_MAX = 16;          // measured: the fold wins up to 16 proofs (1: 7.46 → 6.88 ms, 32: 10.47 → 10.68)
+    static constexpr size_t SMALL_MAX = 32;         // batches that take the latency-oriented small-batch kernels
+    bool fold_on_ = true;
     std::vector<uint32_t> vm_meta_;
     double vm_est_cycles_ = 0;
     size_t vm_max_batch_ = 0;   // verify_batch takes the lane-parallel kernel up to this many proofs (0: never)
@@ -664,6 +668,7 @@ Rln::Rln(size_t tree_depth, const uint8_t* zkey, size_t zlen, const uint8_t* gra
         const int mb = env_int("RLN_B200_MAX_BATCH", 4096);
         if (mb < 1 || mb > (1 << 20)) throw RlnError("Configuration error: RLN_B200_MAX_BATCH must be in [1, 1048576]");
         max_batch_ = (size_t)mb;
+        fold_on_ = env_int("RLN_B200_ASSEMBLE_FOLD", 1) != 0;
     }
     try {
         ZK_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
@@ -1003,6 +1008,19 @@ void Rln::build_tables() {
         g_launch_count += 4;
         ZK_CUDA_CHECK(cudaDeviceSynchronize());
         plan_.delta1_table = d_delta1_tab_.as<G1Affine>();
+        {   // α₁ and β₁ with the same geometry: s·α₁ and r·β₁ of the folded assembly (a handful of proofs)
+            DevMem ba, bb;
+            upload_points_g1(zk_.alpha_g1, one, ba);
+            upload_points_g1(zk_.beta_g1, one, bb);
+            d_alpha1_tab_.alloc(sizeof(G1Affine) * Kd * ((size_t)1 << (cd - 1)));
+            d_beta1_tab_.alloc(sizeof(G1Affine) * Kd * ((size_t)1 << (cd - 1)));
+            launch_build_table_g1(ba.as<G1Affine>(), 1, cd, Kd, d_alpha1_tab_.as<G1Affine>(), 0);
+            launch_build_table_g1(bb.as<G1Affine>(), 1, cd, Kd, d_beta1_tab_.as<G1Affine>(), 0);
+            g_launch_count += 4;
+            ZK_CUDA_CHECK(cudaDeviceSynchronize());
+            plan_.alpha1_table = d_alpha1_tab_.as<G1Affine>();
+            plan_.beta1_table = d_beta1_tab_.as<G1Affine>();
+        }
         plan_.delta2_table = d_delta2_tab_.as<G2Affine>();
     }
     pk_.alpha_g1 = fetch_g1(zk_.alpha_g1);
@@ -1330,6 +1348,8 @@ Rln::TaskSet& Rln::tasks_for(u32 B, int phase) {
     ts->g2.upload(t2.data(), t2.size() * sizeof(MsmTask));
     ts->n1 = (u32)t1.size();
     ts->n2 = (u32)t2.size();
+    for (const MsmTask& t : t1) if (t.group <= 1) ts->n_ab++;
+    for (size_t i = 0; i < ts->n_ab; i++) if (t1[i].group > 1) throw RlnError("internal: MSM tasks are not ordered by group");
     TaskSet& ref = *ts;
     tasks_[key] = std::move(ts);
     return ref;
@@ -1384,7 +1404,8 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
         ws_part1_.ensure((size_t)ts.n1 * B * sizeof(G1XYZZ));
         ws_part2_.ensure((size_t)ts.n2 * B * sizeof(G2XYZZ));
         const uint8_t* in = d_inputs + off * (size_t)gh_.n_slots * 32;
-        if (d_values && phase != MSM_KNOWN) {  // proof values only need the inputs: a latency-bound kernel, run beside the main pipeline
+        const bool values_from_wires = B <= SMALL_MAX && phase == MSM_FULL && !d_partial && !ext_wires_;   // a handful of full proofs: see below
+        if (d_values && phase != MSM_KNOWN && !values_from_wires) {  // proof values only need the inputs: a latency-bound kernel, run beside the main pipeline
             ZK_CUDA_CHECK(cudaEventRecord(fork_, s));
             ZK_CUDA_CHECK(cudaStreamWaitEvent(side_, fork_, 0));
             launch_proof_values(in, slots_, B, d_values + values_stride() * off, side_);
@@ -1393,6 +1414,10 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
         ZK_CUDA_CHECK(cudaEventRecord(ev_[0], s));
         if (ext_wires_) launch_scatter_wires(circ_, ext_wires_, ws_vals_.as<Fr>(), B, ws_err_.as<u32>(), s);
         else launch_witness(circ_, in, ws_vals_.as<Fr>(), B, ws_err_.as<u32>(), s);
+        // for a handful of proofs the values are read off the witness (they are its public signals): the side kernel would hash
+        // every Merkle path a second time on one thread per proof, 6 ms — longer than everything else here
+        if (d_values && values_from_wires)
+            launch_values_from_wires(ws_vals_.as<Fr>(), circ_.signals, B, (u32)max_out_, d_values + values_stride() * off, s);
         ZK_CUDA_CHECK(cudaEventRecord(ev_[1], s));
         // (running the QAP on a side stream beside the A / B1 / L accumulate tasks was measured slower, DESIGN §7b, and removed)
         if (phase != MSM_KNOWN) launch_qap(circ_, ws_vals_.as<Fr>(), ws_a_.as<Fr>(), ws_b_.as<Fr>(), ws_c_.as<Fr>(), B, s);
@@ -1410,6 +1435,20 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
         mw.side = asm_side_;
         mw.side_fork = asm_fork_;
         mw.side_join = asm_join_;
+        if (fold_on_ && B <= FOLD_MAX && phase == MSM_FULL && !d_partial) {
+            // a handful of full proofs: s·(ΣzᵢAᵢ) and r·(ΣzᵢB₁ᵢ) as table sums over s·z and r·z instead of the Straus run of the assembly
+            ws_fold_s_.ensure(sizeof(Fr) * gh_.prog.size() * FOLD_MAX);
+            ws_fold_r_.ensure(sizeof(Fr) * gh_.prog.size() * FOLD_MAX);
+            ws_fold_part_.ensure(sizeof(G1XYZZ) * (size_t)ts.n_ab * B);
+            ws_fold_sum_.ensure(sizeof(G1XYZZ) * 2 * FOLD_MAX);
+            launch_scale_vals(ws_vals_.as<Fr>(), d_rs + 64 * off, (u32)gh_.prog.size(), B, ws_fold_s_.as<Fr>(), ws_fold_r_.as<Fr>(), s);
+            mw.fold_s = ws_fold_s_.as<Fr>();
+            mw.fold_r = ws_fold_r_.as<Fr>();
+            mw.fold_part = ws_fold_part_.as<G1XYZZ>();
+            mw.fold_sum = ws_fold_sum_.as<G1XYZZ>();
+            mw.n_tasks_ab = ts.n_ab;
+            g_launch_count += 3;
+        }
         launch_msm_sums(plan_, ws_vals_.as<Fr>(), ws_a_.as<Fr>(), B, mw, s);
         if (phase == MSM_KNOWN) {
             launch_partial_out(pk_, B, mw, d_partial_affine + 320 * off, d_partial_comp + 160 * off, s);
@@ -1419,7 +1458,7 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
                             d_affine ? d_affine + 256 * off : nullptr, s);
         }
         ZK_CUDA_CHECK(cudaEventRecord(ev_[3], s));
-        if (d_values && phase != MSM_KNOWN) ZK_CUDA_CHECK(cudaStreamWaitEvent(s, join_, 0));
+        if (d_values && phase != MSM_KNOWN && !values_from_wires) ZK_CUDA_CHECK(cudaStreamWaitEvent(s, join_, 0));
         ZK_CUDA_CHECK(cudaEventRecord(ev_[4], s));
         g_launch_count += 1 + (phase != MSM_KNOWN ? qap_launch_count(circ_, B) : 0) + 6 + (d_values ? 1 : 0);
         // graph-evaluation failures surface as errors, like WitnessCalcError::GraphEvaluation (rln/src/circuit/iden3calc.rs:52-53)
