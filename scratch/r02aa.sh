@@ -1,9 +1,9 @@
 #!/bin/bash
-# round 2, call z: folded assembly (no variable-base multiplication for ≤ 32 full proofs) + proof values read off the witness:
+# round 2, call aa: G2 sums beside the G1 sums for small batches, fold up to 16 proofs
 # full GPU suite, per-stage times with the fold on and off
 set -u
 mkdir -p gpurun_out
-O=gpurun_out/r02z
+O=gpurun_out/r02aa
 timeout 1500 python -m pytest tests -m gpu -x -q > ${O}_pytest.log 2>&1; echo "suite exit $?" | tee ${O}_summary.txt
 tail -3 ${O}_pytest.log
 for v in 1 0; do
