@@ -126,3 +126,21 @@ def test_reference_c_examples_build_unmodified(tmp_path, example):
         assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     else:
         assert out.returncode == 1 and "no usable CUDA device" in out.stderr, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+REF_BUILT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "examples")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("example", ["basic_proof", "multi_message_id", "partial_proof", "recover_secret", "stateless", "type_serialization"])
+def test_reference_c_examples_run_on_gpu(example):
+    """The reference's own C programs (rln/ffi_c_examples/*.c: tree + proof + verify, multi-message-id, partial proofs, secret
+    recovery, stateless mode, type serialisation), compiled UNMODIFIED in this container by oracle/build_ref_examples.py (called
+    from __graft_entry__.build()) and shipped as binaries, run to completion against librln_b200.so on the GPU box."""
+    exe = os.path.join(REF_BUILT, example)
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/examples not built (needs /root/reference at build time)")
+    libdir = os.path.dirname(ffi.LIB_PATH)       # the programs open ../resources/tree_depth_20/… relative to their cwd
+    env = dict(os.environ, RLN_B200_WINDOW_BITS="8", RLN_B200_WINDOW_BITS_G2="10")
+    out = subprocess.run([exe], capture_output=True, text=True, cwd=libdir, timeout=600, env=env)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
