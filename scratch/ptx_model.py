@@ -198,3 +198,137 @@ if __name__ == "__main__":
         for a, b, c2, d2 in ((P - 1, P - 1, P, P - 1), (P - 1, P - 1, P - 1, P - 1), (P, P, P, P)):
             assert dot2_model(a, b, c2, d2, P, inv) == (a * b + c2 * d2) * Rinv % P
     print("mul/sqr/dot2 carry-chain schedules OK")
+
+
+# ---- lazy-reduction Fq2 arithmetic (round 2, G2 accumulate): unreduced 512-bit products, one reduction per output coordinate ----
+class CCs(CC):
+    def sub_cc(self, a, b):
+        s = a - b; self.cf = 1 if s < 0 else 0; return s & M      # cf models the BORROW here (sub.cc/subc.cc pair up consistently)
+
+    def subc_cc(self, a, b):
+        s = a - b - self._rd(); self.cf = 1 if s < 0 else 0; return s & M
+
+    def subc(self, a, b):
+        s = a - b - self._rd(); self.cf = None; return s & M
+
+
+def shift_row(c, E, O, A, bi):
+    """T = (T >> 32) + A*bi; E[0] of the old T is dropped by the caller's contract (it has been emitted or cancelled)"""
+    nE = [0] * 8; nO = [0] * 8
+    nE[0] = c.add_cc(O[0], E[1])
+    for j in (0, 2, 4):
+        nO[j] = c.madc_lo_cc(A[j + 1], bi, E[j + 2]); nO[j + 1] = c.madc_hi_cc(A[j + 1], bi, E[j + 3])
+    nO[6] = c.madc_lo_cc(A[7], bi, 0); nO[7] = c.madc_hi(A[7], bi, 0)
+    nE[0] = c.mad_lo_cc(A[0], bi, nE[0]); nE[1] = c.madc_hi_cc(A[0], bi, O[1])
+    for j in (2, 4, 6):
+        nE[j] = c.madc_lo_cc(A[j], bi, O[j]); nE[j + 1] = c.madc_hi_cc(A[j], bi, O[j + 1])
+    s = nO[7] + c._rd(); assert s >> 32 == 0; nO[7] = s; c.cf = None
+    return nE, nO
+
+
+def mul_wide_model(a, b):
+    """16-word product of two integers below 2^256 (mul_wide_ptx): the rows of mul_model without the reduction rows, the low
+    word of every row is emitted instead of cancelled"""
+    c = CC(); A, B = words(a), words(b)
+    E = [0] * 8; O = [0] * 8; out = [0] * 16
+    for j in (0, 2, 4, 6):
+        t = A[j] * B[0]; E[j], E[j + 1] = t & M, t >> 32
+        t = A[j + 1] * B[0]; O[j], O[j + 1] = t & M, t >> 32
+    out[0] = E[0]
+    for i in range(1, 8):
+        E, O = shift_row(c, E, O, A, B[i])
+        out[i] = E[0]
+    out[8] = c.add_cc(E[1], O[0])
+    for k in range(1, 7):
+        out[8 + k] = c.addc_cc(E[k + 1], O[k])
+    out[15] = c.addc(O[7], 0)
+    return val(out)
+
+
+def redc_wide_model(w, P, inv):
+    """Montgomery reduction of a 16-word integer w < P·2^256 (redc_wide_ptx): reduction rows on the low half, the words of the
+    high half enter at the top of the shifted accumulator one per row, the last one in the closing addition"""
+    c = CC(); W = words(w, 16); p = words(P)
+    E = W[:8]; O = [0] * 8
+    for i in range(8):
+        reduce_row(c, E, O, p, inv)
+        if i == 7:
+            break
+        nE = [0] * 8; nO = [0] * 8
+        nE[0] = c.add_cc(O[0], E[1])
+        for j in range(6):
+            nO[j] = c.addc_cc(E[j + 2], 0)
+        nO[6] = c.addc_cc(W[8 + i], 0)
+        nO[7] = c.addc(0, 0)
+        for j in range(1, 8):
+            nE[j] = O[j]
+        E, O = nE, nO
+    r = [0] * 8
+    r[0] = c.add_cc(E[1], O[0])
+    for k in range(1, 7):
+        r[k] = c.addc_cc(E[k + 1], O[k])
+    s = O[7] + W[15] + c._rd(); assert s >> 32 == 0, "redc_wide: result does not fit 256 bits"; r[7] = s; c.cf = None
+    v = val(r)
+    assert v < 2 * P, "redc_wide: more than one subtraction needed"
+    return v - P if v >= P else v
+
+
+def wide_add(x, y):
+    return (x + y) & ((1 << 512) - 1)
+
+
+def wide_sub(x, y):
+    return (x - y) & ((1 << 512) - 1)
+
+
+def fq2_mul_lazy_model(a0, a1, b0, b1, P, inv):
+    OFF = P << 255
+    P0 = mul_wide_model(a0, b0); P1 = mul_wide_model(a1, b1)
+    sa = a0 + a1; sb = b0 + b1
+    assert sa < 1 << 256 and sb < 1 << 256
+    X = mul_wide_model(sa, sb)
+    D = wide_add(wide_sub(P0, P1), OFF)
+    X = wide_sub(wide_sub(X, P0), P1)
+    return redc_wide_model(D, P, inv), redc_wide_model(X, P, inv)
+
+
+def fq2_sub_prod_lazy_model(x, y, z, w, P, inv):
+    """x·y − z·w over Fq2 = Fq[u]/(u² + 1), every argument a pair"""
+    OFF = P << 255
+    re = OFF; im = OFF
+    t = mul_wide_model(x[0], y[0]); re = wide_add(re, t); im = wide_sub(im, t)
+    t = mul_wide_model(x[1], y[1]); re = wide_sub(re, t); im = wide_sub(im, t)
+    t = mul_wide_model(x[0] + x[1], y[0] + y[1]); im = wide_add(im, t)
+    t = mul_wide_model(z[0], w[0]); re = wide_sub(re, t); im = wide_add(im, t)
+    t = mul_wide_model(z[1], w[1]); re = wide_add(re, t); im = wide_add(im, t)
+    t = mul_wide_model(z[0] + z[1], w[0] + w[1]); im = wide_sub(im, t)
+    return redc_wide_model(re, P, inv), redc_wide_model(im, P, inv)
+
+
+def check_lazy():
+    Q = 21888242871839275222246405745257275088696311157297823662689037894645226208583
+    rnd = random.Random(7)
+    inv = (-pow(Q, -1, 1 << 32)) % (1 << 32); Rinv = pow(1 << 256, -1, Q)
+    edge = [0, 1, Q - 1, Q - 2, (1 << 253), Q - 3, 0xFFFFFFFF, (1 << 224) - 1]
+    for it in range(6000):
+        pick = (lambda: rnd.choice(edge)) if it < 1500 else (lambda: rnd.randrange(Q))
+        a0, a1, b0, b1 = pick(), pick(), pick(), pick()
+        assert mul_wide_model(a0 + a1, b0 + b1) == (a0 + a1) * (b0 + b1)
+        c0, c1 = fq2_mul_lazy_model(a0, a1, b0, b1, Q, inv)
+        assert c0 == (a0 * b0 - a1 * b1) * Rinv % Q and c1 == (a0 * b1 + a1 * b0) * Rinv % Q
+        x, y, z, w = (pick(), pick()), (pick(), pick()), (pick(), pick()), (pick(), pick())
+        re, im = fq2_sub_prod_lazy_model(x, y, z, w, Q, inv)
+        assert re == (x[0] * y[0] - x[1] * y[1] - z[0] * w[0] + z[1] * w[1]) * Rinv % Q
+        assert im == (x[0] * y[1] + x[1] * y[0] - z[0] * w[1] - z[1] * w[0]) * Rinv % Q
+    # extremes of the bound: everything at q − 1 in the direction that maximises / minimises the wide sums
+    m = Q - 1
+    for x, y, z, w in (((m, 0), (m, 0), (0, m), (0, m)), ((0, m), (0, m), (m, 0), (m, 0)), ((m, m), (m, m), (m, m), (m, m)),
+                       ((m, m), (m, m), (0, 0), (0, 0)), ((0, 0), (0, 0), (m, m), (m, m))):
+        re, im = fq2_sub_prod_lazy_model(x, y, z, w, Q, inv)
+        assert re == (x[0] * y[0] - x[1] * y[1] - z[0] * w[0] + z[1] * w[1]) * Rinv % Q
+        assert im == (x[0] * y[1] + x[1] * y[0] - z[0] * w[1] - z[1] * w[0]) * Rinv % Q
+    print("lazy Fq2 product / difference of products: carry-chain schedules OK")
+
+
+if __name__ == "__main__":
+    check_lazy()
