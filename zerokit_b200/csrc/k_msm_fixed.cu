@@ -598,15 +598,21 @@ void launch_scale_vals(const Fr* d_vals, const uint8_t* d_rs, u32 n_rows, u32 B,
 // waves of (SMs × resident CTAs): long CTAs in few waves leave part of the chip idle at the end of the launch, short CTAs in
 // many waves cost more partial sums for k_msm_reduce.  Measured at batch 4 096: G1 10 → 24 waves −1.5 % (reduce +0.75 ms);
 // G2 is flat between 8 and 24 waves because its reduce (Fq2 additions) grows as fast as the tail shrinks.
-static u32 pick_chunk(u32 total_bases, u32 B, bool g2) {
+// Bases per task: the smallest chunk whose task count fits the target number of "waves" of 148 × (4 | 2) resident CTAs (24 for
+// G1, 12 for G2), so that the launch does not end with a nearly empty extra wave.  Measured at batch 4 096 (round 2): G1 452 tasks =
+// 24.4 waves → 442 = 23.9: 285.0 → 283.8 ms; G2 112 = 12.1 → 110 = 11.9: 131.7 → 131.7 ms — CTAs of a launch drift apart, so there
+// is hardly a wave structure left to fit by the end; kept because it is never worse.
+static u32 pick_chunk(const u32* group_sizes, int n_groups, u32 halves, u32 B, bool g2) {
     const u64 ctas_per_task = (B + 127) / 128;
     const u64 per_wave = 148ull * (g2 ? 2 : 4);
-    u64 want_tasks = ((g2 ? 12 : 24) * per_wave + ctas_per_task - 1) / ctas_per_task;   // tasks for ~24 (G1) / ~12 (G2) waves
-    if (want_tasks < 1) want_tasks = 1;
-    u64 chunk = total_bases / want_tasks;
-    if (chunk < 4) chunk = 4;
-    if (chunk > 256) chunk = 256;
-    return (u32)chunk;
+    u64 max_tasks = (g2 ? 12 : 24) * per_wave / ctas_per_task;
+    if (max_tasks < halves) max_tasks = halves;
+    for (u32 chunk = 4; chunk < 256; chunk++) {
+        u64 tasks = 0;
+        for (int i = 0; i < n_groups; i++) tasks += (u64)((group_sizes[i] + chunk - 1) / chunk) * halves;
+        if (tasks <= max_tasks) return chunk;
+    }
+    return 256;
 }
 std::vector<MsmTask> msm_make_tasks(const FixedMsmPlan& plan, u32 B, bool g2, int phase) {
     const MsmGroupDev* g = g2 ? &plan.g2 : plan.g1;
@@ -617,10 +623,10 @@ std::vector<MsmTask> msm_make_tasks(const FixedMsmPlan& plan, u32 B, bool g2, in
         if (phase == MSM_KNOWN) hi = g[i].n_known;      // H has n_known = 0: it belongs to the finish phase only
         if (phase == MSM_UNKNOWN) lo = g[i].n_known;
     };
-    u32 total = 0;
-    for (int i = 0; i < n_groups; i++) { u32 lo, hi; range(i, lo, hi); total += hi - lo; }
+    u32 sizes[4] = {0, 0, 0, 0};
+    for (int i = 0; i < n_groups; i++) { u32 lo, hi; range(i, lo, hi); sizes[i] = hi - lo; }
     const bool glv = plan.glv != 0;   // both groups: G1 through β, G2 through β²
-    const u32 chunk = pick_chunk((total ? total : 1) * (glv ? 2 : 1), B, g2);
+    const u32 chunk = pick_chunk(sizes, n_groups, glv ? 2 : 1, B, g2);
     std::vector<MsmTask> tasks;
     for (int i = 0; i < n_groups; i++) {
         u32 lo, hi;
