@@ -332,3 +332,127 @@ def check_lazy():
 
 if __name__ == "__main__":
     check_lazy()
+
+
+# ---- one-level Karatsuba on the 8 x 8 limb product + Montgomery reduction with the shift fused into the reduction rows -------------
+def mul4_wide_model(c, x, y):
+    """8-word product of two 4-word integers, two interleaved carry chains (16 wide MADs)"""
+    E = [0] * 4; O = [0] * 4; out = [0] * 8
+    for j in (0, 2):
+        t = x[j] * y[0]; E[j], E[j + 1] = t & M, t >> 32
+        t = x[j + 1] * y[0]; O[j], O[j + 1] = t & M, t >> 32
+    out[0] = E[0]
+    for i in range(1, 4):
+        bi = y[i]
+        nE = [0] * 4; nO = [0] * 4
+        nE[0] = c.add_cc(O[0], E[1])
+        nO[0] = c.madc_lo_cc(x[1], bi, E[2]); nO[1] = c.madc_hi_cc(x[1], bi, E[3])
+        nO[2] = c.madc_lo_cc(x[3], bi, 0); nO[3] = c.madc_hi(x[3], bi, 0)
+        nE[0] = c.mad_lo_cc(x[0], bi, nE[0]); nE[1] = c.madc_hi_cc(x[0], bi, O[1])
+        nE[2] = c.madc_lo_cc(x[2], bi, O[2]); nE[3] = c.madc_hi_cc(x[2], bi, O[3])
+        s = nO[3] + c._rd(); assert s >> 32 == 0; nO[3] = s; c.cf = None
+        E, O = nE, nO
+        out[i] = E[0]
+    out[4] = c.add_cc(E[1], O[0]); out[5] = c.addc_cc(E[2], O[1]); out[6] = c.addc_cc(E[3], O[2]); out[7] = c.addc(O[3], 0)
+    return out
+
+
+def kara_wide_model(a, b):
+    """16-word product by one level of subtractive Karatsuba: a0·b0, a1·b1, |a0 − a1|·|b1 − b0| (48 wide MADs)"""
+    c = CCs(); A, B = words(a), words(b)
+    a0, a1, b0, b1 = A[:4], A[4:], B[:4], B[4:]
+    z0 = mul4_wide_model(c, a0, b0); z2 = mul4_wide_model(c, a1, b1)
+
+    def absdiff(x, y):
+        d = [0] * 4
+        d[0] = c.sub_cc(x[0], y[0])
+        for i in (1, 2, 3):
+            d[i] = c.subc_cc(x[i], y[i])
+        neg = c.subc(0, 0) & 1                       # borrow
+        mk = (0 - neg) & M
+        d[0] = c.add_cc(d[0] ^ mk, neg)
+        for i in (1, 2):
+            d[i] = c.addc_cc(d[i] ^ mk, 0)
+        d[3] = c.addc(d[3] ^ mk, 0)
+        return d, neg
+    da, sa = absdiff(a0, a1); db, sb = absdiff(b1, b0)
+    assert val(da) == abs(val(a0) - val(a1)) and val(db) == abs(val(b1) - val(b0))
+    z1 = mul4_wide_model(c, da, db)
+    s = sa ^ sb; mz = (0 - s) & M
+    m = [0] * 9
+    m[0] = c.add_cc(z0[0], z2[0])
+    for i in range(1, 8):
+        m[i] = c.addc_cc(z0[i], z2[i])
+    m[8] = c.addc(0, 0)
+    c.add_cc(s, M)                                   # CF = s
+    for i in range(8):
+        m[i] = c.addc_cc(m[i], z1[i] ^ mz)
+    m[8] = c.addc(m[8], mz)
+    assert m[8] <= 1
+    w = [0] * 16
+    w[0:4] = z0[0:4]
+    w[4] = c.add_cc(z0[4], m[0])
+    for i in (1, 2, 3):
+        w[4 + i] = c.addc_cc(z0[4 + i], m[i])
+    for i in range(4):
+        w[8 + i] = c.addc_cc(z2[i], m[4 + i])
+    w[12] = c.addc_cc(z2[4], m[8]); w[13] = c.addc_cc(z2[5], 0); w[14] = c.addc_cc(z2[6], 0); w[15] = c.addc(z2[7], 0)
+    return val(w)
+
+
+def redc_fused_model(w, P, inv):
+    """Montgomery reduction of a 16-word integer: row 0 reduces in place, rows 1..7 shift and reduce in one pass (the shift's
+    carry ripple rides in the MAD chains), the high words enter at the top one per row"""
+    c = CC(); W = words(w, 16); p = words(P)
+    E = W[:8]; O = [0] * 8
+    reduce_row(c, E, O, p, inv)
+    for i in range(1, 8):
+        m = (((O[0] + E[1]) & M) * inv) & M
+        nE = [0] * 8; nO = [0] * 8
+        nE[0] = c.add_cc(O[0], E[1])
+        for j in (0, 2, 4):
+            nO[j] = c.madc_lo_cc(p[j + 1], m, E[j + 2]); nO[j + 1] = c.madc_hi_cc(p[j + 1], m, E[j + 3])
+        nO[6] = c.madc_lo_cc(p[7], m, W[8 + i - 1]); nO[7] = c.madc_hi(p[7], m, 0)
+        nE[0] = c.mad_lo_cc(p[0], m, nE[0]); nE[1] = c.madc_hi_cc(p[0], m, O[1])
+        for j in (2, 4, 6):
+            nE[j] = c.madc_lo_cc(p[j], m, O[j]); nE[j + 1] = c.madc_hi_cc(p[j], m, O[j + 1])
+        s = nO[7] + c._rd(); assert s >> 32 == 0; nO[7] = s; c.cf = None
+        assert nE[0] == 0
+        E, O = nE, nO
+    r = [0] * 8
+    r[0] = c.add_cc(E[1], O[0])
+    for k in range(1, 7):
+        r[k] = c.addc_cc(E[k + 1], O[k])
+    s = O[7] + W[15] + c._rd(); assert s >> 32 == 0, "redc_fused: result does not fit 256 bits"; r[7] = s; c.cf = None
+    v = val(r)
+    assert v < 2 * P, "redc_fused: more than one subtraction needed"
+    return v - P if v >= P else v
+
+
+def check_kara():
+    R = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    Q = 21888242871839275222246405745257275088696311157297823662689037894645226208583
+    rnd = random.Random(11)
+    for P in (R, Q):
+        inv = (-pow(P, -1, 1 << 32)) % (1 << 32); Rinv = pow(1 << 256, -1, P)
+        edge = [0, 1, P - 1, P - 2, P, (1 << 253), (1 << 128) - 1, 1 << 128, (1 << 128) + 1, ((1 << 128) - 1) << 96, 0xFFFFFFFF,
+                sum(0xFFFFFFFF << (64 * i) for i in range(4)) % P, sum(0x80000000 << (32 * i) for i in range(7))]
+        for it in range(8000):
+            if it < 2500:
+                a, b = rnd.choice(edge), rnd.choice(edge)
+            elif it < 4000:
+                a = val([rnd.choice([M, 0, 0x80000000, rnd.randrange(1 << 32)]) for _ in range(7)] + [rnd.randrange(0x30000000)])
+                b = val([rnd.choice([M, 0, 1, rnd.randrange(1 << 32)]) for _ in range(7)] + [rnd.randrange(0x30000000)])
+            else:
+                a, b = rnd.randrange(P), rnd.randrange(P)
+            assert kara_wide_model(a, b) == a * b, (hex(a), hex(b))
+            assert redc_fused_model(a * b, P, inv) == a * b * Rinv % P
+            c2, d2 = rnd.choice([P, P - 1, 0, rnd.randrange(P)]), rnd.choice([P - 1, rnd.randrange(P)])
+            assert redc_fused_model(a * b + c2 * d2, P, inv) == (a * b + c2 * d2) * Rinv % P
+        for n_terms in (3, 4):        # up to 4 products of operands at their maximum (p): 4p² < 0.76·p·2^256
+            assert redc_fused_model(n_terms * P * P, P, inv) == 0
+    print("Karatsuba product + fused-shift reduction: carry-chain schedules OK")
+
+
+if __name__ == "__main__":
+    check_kara()

@@ -10,8 +10,13 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+# A/B builds: RLN_B200_BUILD_VARIANT=name compiles the units listed in RLN_B200_BUILD_VARIANT_UNITS (comma separated) with the extra
+# flags of RLN_B200_BUILD_VARIANT_FLAGS into lib/obj_<name>/ and links lib/librln_b200_<name>.so with the other units' plain objects
+VARIANT = os.environ.get("RLN_B200_BUILD_VARIANT", "")
+VARIANT_UNITS = [u for u in os.environ.get("RLN_B200_BUILD_VARIANT_UNITS", "").split(",") if u]
+VARIANT_FLAGS = os.environ.get("RLN_B200_BUILD_VARIANT_FLAGS", "").split()
 OBJ = os.path.join(HERE, "lib", "obj")
-LIB = os.path.join(HERE, "lib", "librln_b200.so")
+LIB = os.path.join(HERE, "lib", "librln_b200.so" if not VARIANT else f"librln_b200_{VARIANT}.so")
 UNITS = ["rln_host.cu", "k_poseidon.cu", "k_prover.cu", "k_msm_fixed.cu", "k_msm_var.cu", "k_verify.cu", "k_selftest.cu", "k_records.cu", "k_witness.cu", "k_verify_vm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
@@ -27,12 +32,19 @@ def _headers_mtime():
     return m
 
 
+def _obj(unit):
+    d = OBJ + "_" + VARIANT if (VARIANT and unit in VARIANT_UNITS) else OBJ
+    os.makedirs(d, exist_ok=True)
+    return os.path.join(d, unit.replace(".cu", ".o"))
+
+
 def _compile(unit, force, hm):
     src = os.path.join(CSRC, unit)
-    obj = os.path.join(OBJ, unit.replace(".cu", ".o"))
+    obj = _obj(unit)
     if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hm):
         return unit, False, ""
-    r = subprocess.run([NVCC] + FLAGS + ["-c", src, "-o", obj], capture_output=True, text=True)
+    extra = VARIANT_FLAGS if (VARIANT and unit in VARIANT_UNITS) else []
+    r = subprocess.run([NVCC] + FLAGS + extra + ["-c", src, "-o", obj], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {unit}:\n{r.stdout}\n{r.stderr}")
     return unit, True, r.stderr
@@ -47,7 +59,7 @@ def build(force=False, verbose=True):
             rebuilt = rebuilt or did
             if verbose and did:
                 print(f"[build] compiled {unit}", flush=True)
-    objs = [os.path.join(OBJ, u.replace(".cu", ".o")) for u in UNITS]
+    objs = [_obj(u) for u in UNITS]
     if rebuilt or not os.path.exists(LIB):
         r = subprocess.run([NVCC, "-shared", "-o", LIB] + objs + ["-ldl"], capture_output=True, text=True)
         if r.returncode != 0:
