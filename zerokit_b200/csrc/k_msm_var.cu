@@ -299,22 +299,52 @@ __global__ void __launch_bounds__(128) k_bucket_sum(const G1Affine* __restrict__
 }
 
 __device__ __forceinline__ G1XYZZ shfl_xor_point(const G1XYZZ& p, int mask);
-// split buckets only: bucket = Σ of its slices' partial sums.  One warp per ordered position (split buckets sort first): a
-// lane-strided loop and a shuffle tree, so even a bucket of millions of points is combined in ≈ slices/32 + 5 additions.
+// split buckets only: bucket = Σ of its slices' partial sums.  L lanes per ordered position — a lane-strided loop and a shuffle
+// tree, so even a bucket of millions of points is combined in ≈ slices/32 + 5 additions.  Positions are in size order (fullest
+// first), so their slice counts never increase: the kernel finds where they drop to ≤ 16, ≤ 8 and ≤ 4 and gives those stretches
+// 16 / 8 / 4 lanes per bucket (2 / 4 / 8 buckets per warp, trees of 4 / 3 / 2 levels).  Small MSMs cut their slices short to fill
+// the chip, so nearly every bucket is split in a handful of slices there, next to the few giant buckets of the short top window
+// (2^16 terms: 12 K warps of mostly idle lanes with 32 lanes per bucket).  Buckets at the clamp of the size ordering
+// (≥ SIZE_BINS − 1 points, unordered among themselves) have more than 16 slices whenever slice ≤ 255; otherwise every position
+// keeps 32 lanes.
+__device__ __forceinline__ u32 first_at_most(const u32* __restrict__ cnt, u32 n, u32 bound) {   // cnt is non-increasing
+    u32 lo = 0, hi = n;
+    while (lo < hi) {
+        const u32 mid = (lo + hi) >> 1;
+        if (cnt[mid] <= bound) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
 __global__ void __launch_bounds__(128) k_bucket_combine(const G1XYZZ* __restrict__ partial, const u32* __restrict__ order,
                                                         const u32* __restrict__ cnt, const u32* __restrict__ off, u32 n_positions,
-                                                        G1XYZZ* __restrict__ buckets) {
-    const u32 i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (i >= n_positions) return;
-    const u32 c = cnt[i], o = off[i];
-    if (c <= 1) return;   // written by k_bucket_sum (or empty: cleared by the memset)
+                                                        u32 slice, G1XYZZ* __restrict__ buckets) {
+    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    u32 p16 = n_positions, p8 = n_positions, p4 = n_positions;
+    if (16 * slice < SIZE_BINS - 1) {                       // the order is exact wherever counts are ≤ 16
+        p16 = first_at_most(cnt, n_positions, 16);
+        p8 = first_at_most(cnt, n_positions, 8);
+        p4 = first_at_most(cnt, n_positions, 4);
+    }
+    const u32 w16 = (p8 - p16 + 1) / 2, w8 = (p4 - p8 + 3) / 4, w4 = (n_positions - p4 + 7) / 8;
+    u32 L, i, end;
+    if (warp < p16) { L = 32; i = warp; end = p16; }
+    else if (warp < p16 + w16) { L = 16; i = p16 + (warp - p16) * 2 + lane / 16; end = p8; }
+    else if (warp < p16 + w16 + w8) { L = 8; i = p8 + (warp - p16 - w16) * 4 + lane / 8; end = p4; }
+    else if (warp < p16 + w16 + w8 + w4) { L = 4; i = p4 + (warp - p16 - w16 - w8) * 8 + lane / 4; end = n_positions; }
+    else return;                                           // the whole warp: the grid is sized for 32 lanes per position
+    const u32 l = lane % L;
+    const bool live = i < end;
+    const u32 c = live ? cnt[i] : 0, o = live ? off[i] : 0;
+    if (!__any_sync(0xffffffffu, c > 1)) return;           // single-slice buckets were written by k_bucket_sum, empty ones by the memset
     G1XYZZ acc = G1XYZZ::infinity();
-    for (u32 t = lane; t < c; t += 32) acc.add(partial[o + t]);
-    for (int m = 16; m >= 1; m >>= 1) {
-        G1XYZZ other = shfl_xor_point(acc, m);
+    if (c > 1)
+        for (u32 t = l; t < c; t += L) acc.add(partial[o + t]);
+    for (u32 m = 16; m >= 1; m >>= 1) {
+        if (m >= L) continue;                              // uniform over the warp
+        G1XYZZ other = shfl_xor_point(acc, (int)m);
         acc.add(other);
     }
-    if (lane == 0) buckets[order[i]] = acc;
+    if (l == 0 && c > 1) buckets[order[i]] = acc;
 }
 
 // segment s of window k covers buckets [s·L, (s+1)·L): W = Σ (b+1)·B_b over the segment
@@ -481,7 +511,7 @@ void launch_var_msm_g1(VarMsmWorkspace* w, const G1Affine* d_bases, const uint8_
     const size_t n_split_max = items / slice < n_buckets ? items / slice : n_buckets;
     if (n_split_max)
         k_bucket_combine<<<(unsigned)((n_split_max * 32 + 127) / 128), 128, 0, s>>>(w->partial, w->order, w->slice_cnt, w->slice_off,
-                                                                                    (u32)n_split_max, w->buckets);
+                                                                                    (u32)n_split_max, slice, w->buckets);
     const u32 n_seg = half < (u32)SEGS ? half : (u32)SEGS;
     const u32 seg_len = half / n_seg;
     k_segment_reduce<<<dim3((n_seg + 63) / 64, K), 64, 0, s>>>(w->buckets, half, seg_len, w->seg);
