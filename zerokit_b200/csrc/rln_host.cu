@@ -1405,15 +1405,20 @@ void Rln::prove_device(const uint8_t* d_inputs, const uint8_t* d_rs, size_t n, u
         ws_part2_.ensure((size_t)ts.n2 * B * sizeof(G2XYZZ));
         const uint8_t* in = d_inputs + off * (size_t)gh_.n_slots * 32;
         const bool values_from_wires = B <= SMALL_MAX && phase == MSM_FULL && !d_partial && !ext_wires_;   // a handful of full proofs: see below
-        if (d_values && phase != MSM_KNOWN && !values_from_wires) {  // proof values only need the inputs: a latency-bound kernel, run beside the main pipeline
+        ZK_CUDA_CHECK(cudaEventRecord(ev_[0], s));
+        if (ext_wires_) launch_scatter_wires(circ_, ext_wires_, ws_vals_.as<Fr>(), B, ws_err_.as<u32>(), s);
+        else launch_witness(circ_, in, ws_vals_.as<Fr>(), B, ws_err_.as<u32>(), s);
+        if (d_values && phase != MSM_KNOWN && !values_from_wires) {
+            // proof values only need the inputs: a latency-bound kernel, run beside the main pipeline — but forked AFTER the witness
+            // kernel: started beside it, its CTAs (no shared memory) take 32 SMs out of the 82 KB carve-out the witness CTAs need,
+            // a dozen SMs then host two witness CTAs each, and two CTAs on one SM run their products half as fast: the witness
+            // kernel took 7.7 ms per 4 096 proofs in the pipeline where it takes 3.9 ms alone (ncu launch list r02at).  Beside the
+            // QAP and the MSM launches the 4 096 threads of this kernel disappear.
             ZK_CUDA_CHECK(cudaEventRecord(fork_, s));
             ZK_CUDA_CHECK(cudaStreamWaitEvent(side_, fork_, 0));
             launch_proof_values(in, slots_, B, d_values + values_stride() * off, side_);
             ZK_CUDA_CHECK(cudaEventRecord(join_, side_));
         }
-        ZK_CUDA_CHECK(cudaEventRecord(ev_[0], s));
-        if (ext_wires_) launch_scatter_wires(circ_, ext_wires_, ws_vals_.as<Fr>(), B, ws_err_.as<u32>(), s);
-        else launch_witness(circ_, in, ws_vals_.as<Fr>(), B, ws_err_.as<u32>(), s);
         // for a handful of proofs the values are read off the witness (they are its public signals): the side kernel would hash
         // every Merkle path a second time on one thread per proof, 6 ms — longer than everything else here
         if (d_values && values_from_wires)
